@@ -1,0 +1,17 @@
+"""B200-native hash-repartition shuffle for datafusion-distributed.
+
+Host mirror of the reference's operator surface for ONE path
+(RepartitionExec(Hash) -> exchange -> NetworkShuffleExec); all compute is in
+hand-written sm_100a CUDA behind the C ABI in include/dfd_b200.h.  The package
+has no CPU fallback: importing is cheap, but every compute call requires the
+built `_lib/libdfd_b200.so` and a CUDA device.
+"""
+from . import _native
+from ._native import DfdError, LIB_PATH
+from .device import DeviceBuffer, DeviceColumn, WorkerContext
+from .partitioner import HashPartitioner, Partitioning, scale_partitioning
+
+__all__ = [
+    "DfdError", "LIB_PATH", "DeviceBuffer", "DeviceColumn", "WorkerContext",
+    "HashPartitioner", "Partitioning", "scale_partitioning",
+]

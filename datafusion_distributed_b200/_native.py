@@ -1,0 +1,116 @@
+"""ctypes binding of the C ABI declared in include/dfd_b200.h.
+
+This is the same binding a Rust `extern "C"` block would make;
+Python is only the test/bench host.  There is no CPU fallback: if the shared
+library is missing or CUDA is unavailable every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libdfd_b200.so")
+
+DFD_OK = 0
+STATUS = {
+    0: "DFD_OK", 1: "DFD_ERR_INVALID_ARGUMENT", 2: "DFD_ERR_OOM", 3: "DFD_ERR_CUDA", 4: "DFD_ERR_NCCL",
+    5: "DFD_ERR_INTERNAL", 6: "DFD_ERR_UNSUPPORTED", 7: "DFD_ERR_CAPACITY",
+}
+
+COL_FIXED, COL_BOOL, COL_UTF8, COL_LARGE_UTF8, COL_BINARY = 0, 1, 2, 3, 4
+
+
+class DfdError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{STATUS.get(status, status)}: {message}")
+        self.status = status
+        self.message = message
+
+
+class DfdColumn(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("width", C.c_int32),
+        ("values", C.c_void_p),
+        ("offsets", C.c_void_p),
+        ("validity", C.c_void_p),
+        ("offset", C.c_int64),
+    ]
+
+
+class DfdMetrics(C.Structure):
+    _fields_ = [
+        ("calls", C.c_uint64),
+        ("rows", C.c_uint64),
+        ("bytes_in", C.c_uint64),
+        ("bytes_out", C.c_uint64),
+        ("kernel_launches", C.c_uint64),
+        ("hist_ms", C.c_double),
+        ("scan_ms", C.c_double),
+        ("scatter_ms", C.c_double),
+        ("h2d_ms", C.c_double),
+        ("d2h_ms", C.c_double),
+        ("scatter_launches", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+# name -> (restype, argtypes).  Every symbol include/dfd_b200.h declares.
+_VP = C.c_void_p
+SIGNATURES = {
+    "dfd_abi_version": (C.c_int, []),
+    "dfd_last_error": (C.c_char_p, []),
+    "dfd_status_name": (C.c_char_p, [C.c_int]),
+    "dfd_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "dfd_ctx_create": (C.c_int, [C.c_int, C.POINTER(_VP)]),
+    "dfd_ctx_destroy": (None, [_VP]),
+    "dfd_ctx_stream": (_VP, [_VP]),
+    "dfd_ctx_synchronize": (C.c_int, [_VP]),
+    "dfd_ctx_set_profiling": (C.c_int, [_VP, C.c_int]),
+    "dfd_device_alloc": (C.c_int, [_VP, C.c_size_t, C.POINTER(_VP)]),
+    "dfd_device_free": (C.c_int, [_VP, _VP]),
+    "dfd_host_alloc": (C.c_int, [_VP, C.c_size_t, C.POINTER(_VP)]),
+    "dfd_host_free": (C.c_int, [_VP, _VP]),
+    "dfd_memcpy_h2d": (C.c_int, [_VP, _VP, _VP, C.c_size_t]),
+    "dfd_memcpy_d2h": (C.c_int, [_VP, _VP, _VP, C.c_size_t]),
+    "dfd_memset_device": (C.c_int, [_VP, _VP, C.c_int, C.c_size_t]),
+    "dfd_flush_l2": (C.c_int, [_VP]),
+    "dfd_timer_start": (C.c_int, [_VP]),
+    "dfd_timer_stop": (C.c_int, [_VP, C.POINTER(C.c_float)]),
+    "dfd_partitioner_create": (C.c_int, [_VP, C.c_uint32, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_uint64), C.POINTER(_VP)]),
+    "dfd_partitioner_destroy": (None, [_VP]),
+    "dfd_partitioner_num_partitions": (C.c_uint32, [_VP]),
+    "dfd_partition_ids_device": (C.c_int, [_VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, _VP]),
+    "dfd_partition_device": (C.c_int, [_VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.POINTER(DfdColumn), C.POINTER(C.c_int64)]),
+    "dfd_partitioner_part_starts_device": (_VP, [_VP]),
+    "dfd_metrics_get": (C.c_int, [_VP, C.POINTER(DfdMetrics)]),
+    "dfd_metrics_reset": (C.c_int, [_VP]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libdfd_b200.so (fails loudly if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the CUDA path)"
+            )
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status: int):
+    if status != DFD_OK:
+        raise DfdError(status, lib().dfd_last_error().decode("utf-8", "replace"))

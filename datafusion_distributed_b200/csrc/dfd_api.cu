@@ -1,0 +1,509 @@
+// dfd_api.cu — C ABI (include/dfd_b200.h) over the sm_100a kernels.
+// Host side of the producer half of the shuffle: what DataFusion's
+// RepartitionExec(Hash) does inside `plan.execute(partition)` on a worker
+// (reference: src/worker/impl_execute_task.rs:77-86), re-designed as
+// whole-table device passes instead of per-8192-row-batch CPU gathers.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "dfd_b200.h"
+#include "dfd_internal.h"
+#include "dfd_kernels.cuh"
+
+namespace dfd {
+
+thread_local std::string g_last_error;
+
+int set_error(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+int cuda_error(cudaError_t e, const char* what) {
+    int code = (e == cudaErrorMemoryAllocation) ? DFD_ERR_OOM : DFD_ERR_CUDA;
+    return set_error(code, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+// Tile geometry of K1/K2 (rows per CTA = THREADS * K).
+constexpr int TILE_THREADS = 256;
+constexpr int TILE_K = 8;
+constexpr int TILE_ROWS = TILE_THREADS * TILE_K;
+
+int Scratch::ensure(size_t need, int device) {
+    if (need <= bytes) return DFD_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    size_t want = need + need / 4;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) return cuda_error(e, "cudaMalloc(scratch)");
+    bytes = want;
+    (void)device;
+    return DFD_OK;
+}
+
+}  // namespace dfd
+
+using namespace dfd;
+
+static int build_keyset(const dfd_partitioner* p, const dfd_column* cols, int n_cols, KeySet* ks) {
+    memset(ks, 0, sizeof *ks);
+    ks->n = (int32_t)p->key_cols.size();
+    for (int k = 0; k < ks->n; ++k) {
+        int ci = p->key_cols[k];
+        if (ci >= n_cols) return set_error(DFD_ERR_INVALID_ARGUMENT, "key column %d out of range (n_cols=%d)", ci, n_cols);
+        const dfd_column& c = cols[ci];
+        KeyCol& kc = ks->col[k];
+        kc.values = c.values;
+        kc.offsets = c.offsets;
+        kc.validity = c.validity;
+        kc.offset = c.offset;
+        kc.kind = c.kind;
+        kc.width = c.width;
+        switch (c.kind) {
+            case DFD_COL_FIXED:
+                if (c.width != 1 && c.width != 2 && c.width != 4 && c.width != 8 && c.width != 16)
+                    return set_error(DFD_ERR_UNSUPPORTED, "key column %d: fixed width %d not in {1,2,4,8,16}", ci, c.width);
+                if (!c.values) return set_error(DFD_ERR_INVALID_ARGUMENT, "key column %d: values is NULL", ci);
+                break;
+            case DFD_COL_BOOL:
+                if (!c.values) return set_error(DFD_ERR_INVALID_ARGUMENT, "key column %d: values is NULL", ci);
+                break;
+            case DFD_COL_UTF8:
+            case DFD_COL_LARGE_UTF8:
+            case DFD_COL_BINARY:
+                if (!c.offsets) return set_error(DFD_ERR_INVALID_ARGUMENT, "key column %d: offsets is NULL", ci);
+                break;
+            default: return set_error(DFD_ERR_UNSUPPORTED, "key column %d: unknown kind %d", ci, c.kind);
+        }
+    }
+    ks->fast_i64 = (ks->n == 1 && ks->col[0].kind == COL_FIXED && ks->col[0].width == 8 && !ks->col[0].validity &&
+                    ks->col[0].offset == 0)
+                       ? 1
+                       : 0;
+    return DFD_OK;
+}
+
+#define LAUNCH_CHECK(what)                                             \
+    {                                                                  \
+        cudaError_t _e = cudaGetLastError();                           \
+        if (_e != cudaSuccess) return cuda_error(_e, what);            \
+    }
+
+int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,
+                                 const dfd_column* out_cols, cudaStream_t stream) {
+    Ctx* c = p->ctx;
+    const uint32_t N = p->N;
+    if (n_rows < 0 || n_cols < 0 || (n_cols > 0 && (!in_cols || !out_cols)))
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_partition_device: bad arguments");
+    if (n_rows == 0) {
+        cudaError_t e = cudaMemsetAsync(p->d_part_starts, 0, sizeof(int64_t) * (size_t)(N + 1), stream);
+        return e == cudaSuccess ? DFD_OK : cuda_error(e, "cudaMemsetAsync");
+    }
+    KeySet ks;
+    int rc = build_keyset(p, in_cols, n_cols, &ks);
+    if (rc) return rc;
+
+    // payload passes: every column's values, plus a bit pass per validity bitmap
+    std::vector<PayloadCol> passes;
+    int stage_width = 1;
+    uint64_t bytes = 0;
+    for (int i = 0; i < n_cols; ++i) {
+        const dfd_column& ic = in_cols[i];
+        const dfd_column& oc = out_cols[i];
+        if (ic.kind != oc.kind || ic.width != oc.width)
+            return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: in/out layout mismatch", i);
+        if (!ic.values || !oc.values) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: values is NULL", i);
+        PayloadCol pc{};
+        if (ic.kind == DFD_COL_FIXED) {
+            if (ic.width != 1 && ic.width != 2 && ic.width != 4 && ic.width != 8 && ic.width != 16)
+                return set_error(DFD_ERR_UNSUPPORTED, "column %d: fixed width %d not in {1,2,4,8,16}", i, ic.width);
+            if (((uintptr_t)ic.values | (uintptr_t)oc.values) & (uintptr_t)(ic.width - 1))
+                return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: buffers must be aligned to the value width", i);
+            pc.in = ic.values;
+            pc.out = oc.values;
+            pc.in_offset = ic.offset;
+            pc.width = ic.width;
+            if (ic.width > stage_width) stage_width = ic.width;
+            bytes += (uint64_t)n_rows * ic.width;
+        } else if (ic.kind == DFD_COL_BOOL) {
+            if ((uintptr_t)oc.values & 3) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: output bitmap must be 4-byte aligned", i);
+            pc.in = ic.values;
+            pc.out = oc.values;
+            pc.in_offset = ic.offset;
+            pc.width = 0;
+            bytes += (uint64_t)(n_rows + 7) / 8;
+        } else {
+            return set_error(DFD_ERR_UNSUPPORTED, "column %d: variable-width payload columns are not supported by dfd_partition_device yet", i);
+        }
+        passes.push_back(pc);
+        if (ic.validity) {
+            if (!oc.validity) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: input has a validity bitmap but out validity is NULL", i);
+            if ((uintptr_t)oc.validity & 3) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: output validity must be 4-byte aligned", i);
+            PayloadCol vc{};
+            vc.in = ic.validity;
+            vc.out = oc.validity;
+            vc.in_offset = ic.offset;
+            vc.width = 0;
+            passes.push_back(vc);
+            bytes += (uint64_t)(n_rows + 7) / 8;
+        }
+    }
+
+    const int64_t n_tiles = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
+    if (n_tiles > 0x7fffffffLL) return set_error(DFD_ERR_UNSUPPORTED, "n_rows too large for one call");
+    // scratch: hist u32 [N][n_tiles] | tile_base i64 [N][n_tiles] | totals i64 [N]
+    size_t hist_bytes = (((size_t)N * n_tiles * 4) + 255) & ~(size_t)255;
+    size_t base_bytes = (((size_t)N * n_tiles * 8) + 255) & ~(size_t)255;
+    size_t need = hist_bytes + base_bytes + (size_t)N * 8;
+    rc = c->scratch.ensure(need, c->device);
+    if (rc) return rc;
+    uint32_t* d_hist = (uint32_t*)c->scratch.ptr;
+    int64_t* d_base = (int64_t*)((char*)c->scratch.ptr + hist_bytes);
+    int64_t* d_totals = (int64_t*)((char*)c->scratch.ptr + hist_bytes + base_bytes);
+
+    const bool prof = c->profiling;
+    if (prof) cudaEventRecord(c->ev[0], stream);
+    {
+        size_t smem = (size_t)N * 4;
+        k_tile_hist<TILE_THREADS, TILE_K><<<(unsigned)n_tiles, TILE_THREADS, smem, stream>>>(ks, p->st, p->mod, n_rows, n_tiles, N, d_hist);
+        LAUNCH_CHECK("k_tile_hist");
+    }
+    if (prof) cudaEventRecord(c->ev[1], stream);
+    k_scan_tiles<1024><<<N, 1024, 0, stream>>>(d_hist, d_base, d_totals, n_tiles);
+    LAUNCH_CHECK("k_scan_tiles");
+    k_part_starts<<<1, 1024, 0, stream>>>(d_totals, p->d_part_starts, N);
+    LAUNCH_CHECK("k_part_starts");
+    if (prof) cudaEventRecord(c->ev[2], stream);
+    c->metrics.kernel_launches += 3;
+
+    size_t smem = scatter_smem_bytes<TILE_THREADS, TILE_K>(N, stage_width);
+    if (smem > 200 * 1024) return set_error(DFD_ERR_UNSUPPORTED, "num_partitions %u needs %zu B of shared memory per CTA", N, smem);
+    if (smem > 48 * 1024 && smem > p->smem_configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_scatter<TILE_THREADS, TILE_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(k_scatter)");
+        p->smem_configured = smem;
+    }
+    ScatterParams sp{};
+    sp.keys = ks;
+    sp.st = p->st;
+    sp.mod = p->mod;
+    sp.n_rows = n_rows;
+    sp.n_tiles = n_tiles;
+    sp.hist = d_hist;
+    sp.tile_base = d_base;
+    sp.part_starts = p->d_part_starts;
+    sp.N = N;
+    sp.stage_width = stage_width;
+    int launches = 0;
+    for (size_t first = 0; first < passes.size(); first += MAX_COLS_PER_LAUNCH) {
+        size_t n = passes.size() - first < (size_t)MAX_COLS_PER_LAUNCH ? passes.size() - first : (size_t)MAX_COLS_PER_LAUNCH;
+        for (size_t i = 0; i < n; ++i) sp.cols[i] = passes[first + i];
+        sp.n_cols = (int32_t)n;
+        k_scatter<TILE_THREADS, TILE_K><<<(unsigned)n_tiles, TILE_THREADS, smem, stream>>>(sp);
+        LAUNCH_CHECK("k_scatter");
+        ++launches;
+    }
+    if (prof) cudaEventRecord(c->ev[3], stream);
+    c->metrics.kernel_launches += launches;
+    c->metrics.scatter_launches += launches;
+    c->metrics.calls++;
+    c->metrics.rows += (uint64_t)n_rows;
+    c->metrics.bytes_in += bytes;
+    c->metrics.bytes_out += bytes;
+    if (prof) {
+        cudaError_t e = cudaEventSynchronize(c->ev[3]);
+        if (e != cudaSuccess) return cuda_error(e, "partition kernels");
+        float a = 0, b = 0, d = 0;
+        cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
+        cudaEventElapsedTime(&d, c->ev[2], c->ev[3]);
+        c->metrics.hist_ms += a;
+        c->metrics.scan_ms += b;
+        c->metrics.scatter_ms += d;
+    }
+    return DFD_OK;
+}
+
+extern "C" {
+
+int dfd_abi_version(void) { return DFD_ABI_VERSION; }
+const char* dfd_last_error(void) { return g_last_error.c_str(); }
+
+const char* dfd_status_name(int s) {
+    switch (s) {
+        case DFD_OK: return "DFD_OK";
+        case DFD_ERR_INVALID_ARGUMENT: return "DFD_ERR_INVALID_ARGUMENT";
+        case DFD_ERR_OOM: return "DFD_ERR_OOM";
+        case DFD_ERR_CUDA: return "DFD_ERR_CUDA";
+        case DFD_ERR_NCCL: return "DFD_ERR_NCCL";
+        case DFD_ERR_INTERNAL: return "DFD_ERR_INTERNAL";
+        case DFD_ERR_UNSUPPORTED: return "DFD_ERR_UNSUPPORTED";
+        case DFD_ERR_CAPACITY: return "DFD_ERR_CAPACITY";
+    }
+    return "DFD_ERR_UNKNOWN";
+}
+
+int dfd_device_count(int* out) {
+    if (!out) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_device_count: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *out = 0;
+        return cuda_error(e, "cudaGetDeviceCount");
+    }
+    *out = n;
+    return DFD_OK;
+}
+
+int dfd_ctx_create(int device, dfd_ctx** out) {
+    if (!out) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_error(e, "cudaGetDeviceCount (no CUDA device: this library has no CPU fallback)");
+    if (device < 0 || device >= n) return set_error(DFD_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device, n);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_error(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_error(e, "cudaGetDeviceProperties");
+    if (prop.major < 10)
+        return set_error(DFD_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                         prop.major, prop.minor);
+    dfd_ctx* c = new (std::nothrow) dfd_ctx();
+    if (!c) return set_error(DFD_ERR_OOM, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->l2_bytes = (size_t)prop.l2CacheSize;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete c;
+        return cuda_error(e, "cudaStreamCreate");
+    }
+    for (auto& ev : c->ev) cudaEventCreate(&ev);
+    cudaEventCreate(&c->timer_a);
+    cudaEventCreate(&c->timer_b);
+    *out = c;
+    return DFD_OK;
+}
+
+void dfd_ctx_destroy(dfd_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->scratch.ptr) cudaFree(c->scratch.ptr);
+    if (c->flush.ptr) cudaFree(c->flush.ptr);
+    for (auto& ev : c->ev) cudaEventDestroy(ev);
+    cudaEventDestroy(c->timer_a);
+    cudaEventDestroy(c->timer_b);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void* dfd_ctx_stream(dfd_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+#define CTX_GUARD(c)                                                            \
+    if (!(c)) return set_error(DFD_ERR_INVALID_ARGUMENT, "%s: ctx is NULL", __func__); \
+    std::lock_guard<std::mutex> _lk((c)->mu);                                   \
+    {                                                                           \
+        cudaError_t _e = cudaSetDevice((c)->device);                            \
+        if (_e != cudaSuccess) return cuda_error(_e, "cudaSetDevice");          \
+    }
+
+int dfd_ctx_synchronize(dfd_ctx* c) {
+    CTX_GUARD(c);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    return e == cudaSuccess ? DFD_OK : cuda_error(e, "cudaStreamSynchronize");
+}
+
+int dfd_ctx_set_profiling(dfd_ctx* c, int on) {
+    CTX_GUARD(c);
+    c->profiling = on != 0;
+    return DFD_OK;
+}
+
+int dfd_device_alloc(dfd_ctx* c, size_t bytes, void** out) {
+    CTX_GUARD(c);
+    if (!out) return set_error(DFD_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(out, bytes);
+    return e == cudaSuccess ? DFD_OK : cuda_error(e, "cudaMalloc");
+}
+
+int dfd_device_free(dfd_ctx* c, void* p) {
+    CTX_GUARD(c);
+    cudaError_t e = cudaFree(p);
+    return e == cudaSuccess ? DFD_OK : cuda_error(e, "cudaFree");
+}
+
+int dfd_host_alloc(dfd_ctx* c, size_t bytes, void** out) {
+    CTX_GUARD(c);
+    if (!out) return set_error(DFD_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    return e == cudaSuccess ? DFD_OK : cuda_error(e, "cudaHostAlloc");
+}
+
+int dfd_host_free(dfd_ctx* c, void* p) {
+    CTX_GUARD(c);
+    cudaError_t e = cudaFreeHost(p);
+    return e == cudaSuccess ? DFD_OK : cuda_error(e, "cudaFreeHost");
+}
+
+int dfd_memcpy_h2d(dfd_ctx* c, void* dst, const void* src, size_t bytes) {
+    CTX_GUARD(c);
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    return e == cudaSuccess ? DFD_OK : cuda_error(e, "cudaMemcpy H2D");
+}
+
+int dfd_memcpy_d2h(dfd_ctx* c, void* dst, const void* src, size_t bytes) {
+    CTX_GUARD(c);
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    return e == cudaSuccess ? DFD_OK : cuda_error(e, "cudaMemcpy D2H");
+}
+
+int dfd_memset_device(dfd_ctx* c, void* dst, int value, size_t bytes) {
+    CTX_GUARD(c);
+    cudaError_t e = cudaMemsetAsync(dst, value, bytes, c->stream);
+    return e == cudaSuccess ? DFD_OK : cuda_error(e, "cudaMemsetAsync");
+}
+
+int dfd_flush_l2(dfd_ctx* c) {
+    CTX_GUARD(c);
+    size_t need = c->l2_bytes * 2 > (size_t)(256u << 20) ? c->l2_bytes * 2 : (size_t)(256u << 20);
+    int rc = c->flush.ensure(need, c->device);
+    if (rc) return rc;
+    cudaError_t e = cudaMemsetAsync(c->flush.ptr, 0x5a, need, c->stream);
+    return e == cudaSuccess ? DFD_OK : cuda_error(e, "cudaMemsetAsync(flush)");
+}
+
+int dfd_timer_start(dfd_ctx* c) {
+    CTX_GUARD(c);
+    cudaError_t e = cudaEventRecord(c->timer_a, c->stream);
+    return e == cudaSuccess ? DFD_OK : cuda_error(e, "cudaEventRecord");
+}
+
+int dfd_timer_stop(dfd_ctx* c, float* out_ms) {
+    CTX_GUARD(c);
+    cudaError_t e = cudaEventRecord(c->timer_b, c->stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(c->timer_b);
+    if (e == cudaSuccess && out_ms) e = cudaEventElapsedTime(out_ms, c->timer_a, c->timer_b);
+    return e == cudaSuccess ? DFD_OK : cuda_error(e, "timer_stop");
+}
+
+int dfd_metrics_get(dfd_ctx* c, dfd_metrics* out) {
+    CTX_GUARD(c);
+    if (!out) return set_error(DFD_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = c->metrics;
+    return DFD_OK;
+}
+
+int dfd_metrics_reset(dfd_ctx* c) {
+    CTX_GUARD(c);
+    memset(&c->metrics, 0, sizeof c->metrics);
+    return DFD_OK;
+}
+
+/* ---- partitioner ------------------------------------------------------ */
+
+int dfd_partitioner_create(dfd_ctx* c, uint32_t num_partitions, const int32_t* key_cols, int n_keys,
+                           const uint64_t* seeds, dfd_partitioner** out) {
+    if (!c) return set_error(DFD_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (!out) return set_error(DFD_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (num_partitions < 1 || num_partitions > MAX_PARTITIONS)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "num_partitions %u not in [1, %u]", num_partitions, MAX_PARTITIONS);
+    if (n_keys < 1 || n_keys > MAX_KEYS || !key_cols)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "n_keys %d not in [1, %d]", n_keys, MAX_KEYS);
+    for (int k = 0; k < n_keys; ++k)
+        if (key_cols[k] < 0) return set_error(DFD_ERR_INVALID_ARGUMENT, "key_cols[%d] is negative", k);
+    dfd_partitioner* p = new (std::nothrow) dfd_partitioner();
+    if (!p) return set_error(DFD_ERR_OOM, "out of host memory");
+    p->ctx = c;
+    p->N = num_partitions;
+    p->key_cols.assign(key_cols, key_cols + n_keys);
+    // ahash RandomState::with_seeds: seed ^ PI2 (random_state.rs); DataFusion's
+    // REPARTITION_RANDOM_STATE uses seeds (0,0,0,0).
+    static const uint64_t PI2[4] = {0x452821e638d01377ULL, 0xbe5466cf34e90c6cULL, 0xc0ac29b7c97c50ddULL,
+                                    0x3f84d5b5b5470917ULL};
+    uint64_t s[4] = {0, 0, 0, 0};
+    if (seeds) memcpy(s, seeds, sizeof s);
+    p->st = HashState{s[0] ^ PI2[0], s[1] ^ PI2[1], s[2] ^ PI2[2], s[3] ^ PI2[3]};
+    p->mod = make_modn(num_partitions);
+    {
+        CTX_GUARD(c);
+        cudaError_t e = cudaMalloc((void**)&p->d_part_starts, sizeof(int64_t) * (size_t)(num_partitions + 1));
+        if (e != cudaSuccess) {
+            delete p;
+            return cuda_error(e, "cudaMalloc(part_starts)");
+        }
+    }
+    *out = p;
+    return DFD_OK;
+}
+
+void dfd_partitioner_destroy(dfd_partitioner* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(p->ctx->mu);
+        cudaSetDevice(p->ctx->device);
+        cudaStreamSynchronize(p->ctx->stream);
+        cudaFree(p->d_part_starts);
+    }
+    delete p;
+}
+
+uint32_t dfd_partitioner_num_partitions(const dfd_partitioner* p) { return p ? p->N : 0; }
+const int64_t* dfd_partitioner_part_starts_device(const dfd_partitioner* p) { return p ? p->d_part_starts : nullptr; }
+
+int dfd_partition_ids_device(dfd_partitioner* p, const dfd_column* cols, int n_cols, int64_t n_rows,
+                             uint32_t* dest_device) {
+    if (!p) return set_error(DFD_ERR_INVALID_ARGUMENT, "partitioner is NULL");
+    dfd_ctx* c = p->ctx;
+    CTX_GUARD(c);
+    if (n_rows < 0 || !cols || !dest_device) return set_error(DFD_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (n_rows == 0) return DFD_OK;
+    KeySet ks;
+    int rc = build_keyset(p, cols, n_cols, &ks);
+    if (rc) return rc;
+    int64_t blocks = (n_rows + 255) / 256;
+    int64_t cap = (int64_t)c->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    k_partition_ids<<<(unsigned)blocks, 256, 0, c->stream>>>(ks, p->st, p->mod, n_rows, dest_device);
+    LAUNCH_CHECK("k_partition_ids");
+    c->metrics.kernel_launches++;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    return e == cudaSuccess ? DFD_OK : cuda_error(e, "k_partition_ids");
+}
+
+int dfd_partition_device(dfd_partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,
+                         const dfd_column* out_cols, int64_t* part_starts_host) {
+    if (!p) return set_error(DFD_ERR_INVALID_ARGUMENT, "partitioner is NULL");
+    dfd_ctx* c = p->ctx;
+    CTX_GUARD(c);
+    int rc = partition_device_locked(p, in_cols, n_cols, n_rows, out_cols, c->stream);
+    if (rc) return rc;
+    if (part_starts_host) {
+        cudaError_t e = cudaMemcpyAsync(part_starts_host, p->d_part_starts, sizeof(int64_t) * (size_t)(p->N + 1),
+                                        cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return cuda_error(e, "dfd_partition_device");
+    }
+    return DFD_OK;
+}
+
+}  // extern "C"

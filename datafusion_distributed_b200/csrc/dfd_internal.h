@@ -1,0 +1,60 @@
+// dfd_internal.h — host-side objects behind the opaque C ABI handles.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "dfd_b200.h"
+#include "dfd_hash.cuh"
+
+namespace dfd {
+
+int set_error(int code, const char* fmt, ...);
+int cuda_error(cudaError_t e, const char* what);
+
+struct Scratch {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need, int device);
+};
+
+}  // namespace dfd
+
+// One worker == one GPU (reference `Worker`, src/worker/worker_service.rs:39-49).
+struct dfd_ctx {
+    int device = 0;
+    int sm_count = 148;
+    size_t l2_bytes = 0;
+    cudaStream_t stream = nullptr;  // compute stream: K1/K1b/K2 launch here
+    cudaEvent_t ev[4] = {};
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
+    bool profiling = false;
+    dfd::Scratch scratch;  // tile histograms / cursors
+    dfd::Scratch flush;    // L2 flush buffer
+    dfd_metrics metrics = {};
+    std::mutex mu;
+};
+
+// ≙ DataFusion BatchPartitioner::Hash { exprs, num_partitions, hash_buffer, random_state }
+struct dfd_partitioner {
+    dfd_ctx* ctx = nullptr;
+    uint32_t N = 0;
+    std::vector<int32_t> key_cols;
+    dfd::HashState st{};
+    dfd::ModN mod{};
+    int64_t* d_part_starts = nullptr;  // [N+1]
+    size_t smem_configured = 0;
+};
+
+namespace dfd {
+using Ctx = ::dfd_ctx;
+using Partitioner = ::dfd_partitioner;
+
+// Launches K1 -> K1b -> K2 on `stream`; caller holds ctx->mu and has set the device.
+int partition_device_locked(Partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,
+                            const dfd_column* out_cols, cudaStream_t stream);
+
+}  // namespace dfd

@@ -1,0 +1,368 @@
+// dfd_kernels.cuh — sm_100a kernels of the hash-repartition hot path.
+//
+// Replaces the CPU inner loop of DataFusion's RepartitionExec(Hash) that the
+// reference runs on every producer worker (src/worker/impl_execute_task.rs:77-86):
+//   create_hashes -> `hash % N` -> per-destination index vectors -> take per column
+// with three device passes over Arrow columnar buffers:
+//   K1 k_tile_hist     hash(keys) -> destination -> per-tile radix histogram
+//   K1b k_scan_tiles / k_part_starts   exclusive scans -> per-(tile,destination) write cursors
+//   K2 k_scatter       fused hash -> stable rank (warp match/ballot) -> shared-memory
+//                      staging of each column in destination order -> coalesced run writes
+// Integer / byte work bounded by HBM bandwidth; no tensor cores.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "dfd_hash.cuh"
+
+namespace dfd {
+
+constexpr int MAX_COLS_PER_LAUNCH = 24;
+constexpr uint32_t MAX_PARTITIONS = 4096;
+
+struct PayloadCol {
+    const void* in;          // values (fixed) or bitmap (bool / validity pass)
+    void* out;
+    int64_t in_offset;       // Arrow logical offset of the input (rows)
+    int32_t width;           // bytes; 0 => bit column (bool values or validity)
+    int32_t pad;
+};
+
+struct ScatterParams {
+    KeySet keys;
+    HashState st;
+    ModN mod;
+    int64_t n_rows;
+    int64_t n_tiles;
+    const uint32_t* hist;        // [N][n_tiles] per-tile destination counts (K1)
+    const int64_t* tile_base;    // [N][n_tiles] exclusive scan of hist along tiles
+    const int64_t* part_starts;  // [N+1] exclusive scan of destination totals
+    PayloadCol cols[MAX_COLS_PER_LAUNCH];
+    int32_t n_cols;
+    uint32_t N;
+    int32_t stage_width;         // widest staged element (bytes)
+    int32_t pad;
+};
+
+// ---------------------------------------------------------------------------
+// small block-scan helper: exclusive scan of one value per thread
+// ---------------------------------------------------------------------------
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp /*[THREADS/32 + 1]*/,
+                                                         uint32_t& block_total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t x = lane < THREADS / 32 ? s_warp[lane] : 0;
+        uint32_t xi = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, xi, d);
+            if (lane >= d) xi += t;
+        }
+        if (lane < THREADS / 32) s_warp[lane] = xi - x;
+        if (lane == 31) s_warp[THREADS / 32] = xi;
+    }
+    __syncthreads();
+    uint32_t res = s_warp[w] + inc - v;
+    block_total = s_warp[THREADS / 32];
+    __syncthreads();
+    return res;
+}
+
+// ---------------------------------------------------------------------------
+// K0 (debug / parity): destination id per row
+// ---------------------------------------------------------------------------
+__global__ void k_partition_ids(KeySet keys, HashState st, ModN mod, int64_t n_rows, uint32_t* __restrict__ dest) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x)
+        dest[r] = mod_n(row_hash(keys, r, st), mod);
+}
+
+// ---------------------------------------------------------------------------
+// K1: per-tile destination histogram.  Tile t covers rows [t*T, (t+1)*T).
+// hist is destination-major ([N][n_tiles]) so the tile scan reads contiguously.
+// ---------------------------------------------------------------------------
+template <int THREADS, int K>
+__global__ void __launch_bounds__(THREADS) k_tile_hist(KeySet keys, HashState st, ModN mod, int64_t n_rows,
+                                                        int64_t n_tiles, uint32_t N, uint32_t* __restrict__ hist) {
+    constexpr int T = THREADS * K;
+    extern __shared__ uint32_t s_hist[];
+    const int lane = threadIdx.x & 31;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t p = threadIdx.x; p < N; p += THREADS) s_hist[p] = 0;
+        __syncthreads();
+        const int64_t row0 = tile * T;
+        uint32_t d[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            int64_t r = row0 + j * THREADS + threadIdx.x;
+            d[j] = r < n_rows ? mod_n(row_hash(keys, r, st), mod) : N;
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            unsigned peers = __match_any_sync(0xffffffffu, d[j]);
+            if (d[j] < N && (peers & ((1u << lane) - 1)) == 0) atomicAdd(&s_hist[d[j]], __popc(peers));
+        }
+        __syncthreads();
+        for (uint32_t p = threadIdx.x; p < N; p += THREADS) hist[(int64_t)p * n_tiles + tile] = s_hist[p];
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K1b: one block per destination: exclusive scan of its tile counts.
+// ---------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_scan_tiles(const uint32_t* __restrict__ hist, int64_t* __restrict__ tile_base,
+                                                         int64_t* __restrict__ totals, int64_t n_tiles) {
+    __shared__ unsigned long long s_part[THREADS];
+    const uint32_t p = blockIdx.x;
+    const uint32_t* h = hist + (int64_t)p * n_tiles;
+    int64_t* b = tile_base + (int64_t)p * n_tiles;
+    const int64_t per = (n_tiles + THREADS - 1) / THREADS;
+    const int64_t lo = (int64_t)threadIdx.x * per;
+    const int64_t hi = lo + per < n_tiles ? lo + per : n_tiles;
+    unsigned long long sum = 0;
+    for (int64_t i = lo; i < hi; ++i) sum += h[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    // simple Hillis-Steele over THREADS partial sums
+    for (int d = 1; d < THREADS; d <<= 1) {
+        unsigned long long t = threadIdx.x >= d ? s_part[threadIdx.x - d] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += t;
+        __syncthreads();
+    }
+    unsigned long long run = s_part[threadIdx.x] - sum;
+    for (int64_t i = lo; i < hi; ++i) {
+        b[i] = (int64_t)run;
+        run += h[i];
+    }
+    if (threadIdx.x == THREADS - 1) totals[p] = (int64_t)s_part[THREADS - 1];
+}
+
+// part_starts[p] = sum(totals[0..p)), part_starts[N] = n_rows.  Single block.
+__global__ void k_part_starts(const int64_t* __restrict__ totals, int64_t* __restrict__ part_starts, uint32_t N) {
+    __shared__ unsigned long long s_part[1024];
+    const uint32_t per = (N + 1023) / 1024;
+    const uint32_t lo = threadIdx.x * per;
+    const uint32_t hi = lo + per < N ? lo + per : N;
+    unsigned long long sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) sum += (unsigned long long)totals[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        unsigned long long t = threadIdx.x >= d ? s_part[threadIdx.x - d] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += t;
+        __syncthreads();
+    }
+    unsigned long long run = s_part[threadIdx.x] - sum;
+    for (uint32_t i = lo; i < hi; ++i) {
+        part_starts[i] = (int64_t)run;
+        run += (unsigned long long)totals[i];
+    }
+    if (threadIdx.x == 1023) part_starts[N] = (int64_t)s_part[1023];
+}
+
+// ---------------------------------------------------------------------------
+// K2: fused hash -> stable rank -> staged scatter of every column.
+//
+// One CTA owns one tile of T = THREADS*K rows.  Warp w owns the contiguous
+// rows [w*32K, (w+1)*32K) of the tile and walks them in K rounds of 32, so
+// every global load is one fully coalesced 32-lane request.  Ranks come from
+// __match_any_sync + running per-warp counters in shared memory (stable: rank
+// order == row order), a block scan turns them into positions in a tile-local
+// staging buffer sorted by destination, and each column is then (a) scattered
+// into the staging buffer and (b) streamed out so that every destination's
+// run is written as consecutive, coalesced global stores.
+// ---------------------------------------------------------------------------
+template <typename V>
+struct StageIO {
+    static __device__ __forceinline__ V ld(const void* base, int64_t i) { return ((const V*)base)[i]; }
+};
+
+template <int THREADS, int K, typename V>
+__device__ __forceinline__ void scatter_fixed_column(const PayloadCol& c, void* stage_raw, int64_t row0, int64_t n_rows,
+                                                     int tile_rows, const uint32_t (&pos)[K], const int64_t (&dst)[K],
+                                                     int w, int lane) {
+    V* stage = (V*)stage_raw;
+    const V* in = (const V*)c.in + c.in_offset;
+    V* out = (V*)c.out;
+    V v[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        int64_t r = row0 + (int64_t)w * (K * 32) + j * 32 + lane;
+        if (r < n_rows) v[j] = in[r];
+    }
+    __syncthreads();  // staging buffer free (previous column fully written out)
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        int64_t r = row0 + (int64_t)w * (K * 32) + j * 32 + lane;
+        if (r < n_rows) stage[pos[j]] = v[j];
+    }
+    __syncthreads();  // staging buffer holds the tile in destination order
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        int i = k * THREADS + (int)threadIdx.x;
+        if (i < tile_rows) out[dst[k]] = stage[i];
+    }
+}
+
+// bit column (boolean values or a validity bitmap): staged as one byte per row,
+// written back with warp-aggregated atomicOr on 32-bit output words.
+template <int THREADS, int K>
+__device__ __forceinline__ void scatter_bit_column(const PayloadCol& c, void* stage_raw, int64_t row0, int64_t n_rows,
+                                                   int tile_rows, const uint32_t (&pos)[K], const int64_t (&dst)[K],
+                                                   int w, int lane) {
+    uint8_t* stage = (uint8_t*)stage_raw;
+    const uint8_t* in = (const uint8_t*)c.in;
+    unsigned* out = (unsigned*)c.out;
+    uint8_t v[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        int64_t r = row0 + (int64_t)w * (K * 32) + j * 32 + lane;
+        v[j] = (r < n_rows) ? (uint8_t)bit_is_set(in, r + c.in_offset) : 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        int64_t r = row0 + (int64_t)w * (K * 32) + j * 32 + lane;
+        if (r < n_rows) stage[pos[j]] = v[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        int i = k * THREADS + (int)threadIdx.x;
+        bool active = i < tile_rows;
+        int64_t d = active ? dst[k] : -1;
+        unsigned bit = (active && stage[i]) ? (1u << (d & 31)) : 0u;
+        int64_t word = active ? (d >> 5) : -1;
+        unsigned peers = __match_any_sync(0xffffffffu, word);
+        unsigned merged = __reduce_or_sync(peers, bit);
+        if (active && merged && (peers & ((1u << lane) - 1)) == 0) atomicOr(out + word, merged);
+    }
+}
+
+template <int THREADS, int K>
+__global__ void __launch_bounds__(THREADS) k_scatter(const __grid_constant__ ScatterParams P) {
+    constexpr int T = THREADS * K;
+    constexpr int W = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t N = P.N;
+    // layout: stage | warp_cnt[W][N] | tile_start[N+1] | delta[N] | scan scratch
+    unsigned char* stage = smem;
+    size_t off = ((size_t)T * P.stage_width + 15) & ~(size_t)15;
+    int64_t* delta = (int64_t*)(smem + off);
+    off += (size_t)N * 8;
+    uint32_t* warp_cnt = (uint32_t*)(smem + off);
+    off += (size_t)W * N * 4;
+    uint32_t* tile_start = (uint32_t*)(smem + off);
+    off += (size_t)(N + 1) * 4;
+    uint32_t* s_scan = (uint32_t*)(smem + off);  // [W + 1]
+
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t tile = blockIdx.x;
+    const int64_t row0 = tile * T;
+    const int tile_rows = (int)((P.n_rows - row0) < T ? (P.n_rows - row0) : T);
+
+    // ---- tile_start / delta from the K1 histogram (independent of phase 1)
+    {
+        uint32_t carry = 0;
+        for (uint32_t p0 = 0; p0 < N; p0 += THREADS) {
+            uint32_t p = p0 + threadIdx.x;
+            uint32_t c = p < N ? P.hist[(int64_t)p * P.n_tiles + tile] : 0;
+            uint32_t tot;
+            uint32_t ex = block_exclusive_scan<THREADS>(c, s_scan, tot);
+            if (p < N) {
+                uint32_t ts = carry + ex;
+                tile_start[p] = ts;
+                delta[p] = P.part_starts[p] + P.tile_base[(int64_t)p * P.n_tiles + tile] - (int64_t)ts;
+            }
+            carry += tot;
+        }
+        if (threadIdx.x == 0) tile_start[N] = carry;
+    }
+
+    // ---- phase 1: destination + stable rank of every row of the tile
+    uint32_t* wc = warp_cnt + (size_t)w * N;
+    for (uint32_t p = lane; p < N; p += 32) wc[p] = 0;
+    __syncwarp();
+    uint32_t pos[K];  // first: (dest << 16 | rank) ; later: staging position
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        int64_t r = row0 + (int64_t)w * (K * 32) + j * 32 + lane;
+        bool valid = r < P.n_rows;
+        uint32_t d = valid ? mod_n(row_hash(P.keys, r, P.st), P.mod) : N;
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        uint32_t rank = __popc(peers & ((1u << lane) - 1));
+        uint32_t base = valid ? wc[d] : 0;
+        __syncwarp();
+        if (valid && rank == 0) wc[d] = base + __popc(peers);
+        __syncwarp();
+        pos[j] = (d << 16) | (base + rank);
+    }
+    __syncthreads();
+    // warp_cnt[w][p] -> staging base of (warp w, destination p)
+    for (uint32_t p = threadIdx.x; p < N; p += THREADS) {
+        uint32_t run = tile_start[p];
+#pragma unroll
+        for (int ww = 0; ww < W; ++ww) {
+            uint32_t c = warp_cnt[(size_t)ww * N + p];
+            warp_cnt[(size_t)ww * N + p] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        uint32_t d = pos[j] >> 16;
+        pos[j] = d < N ? wc[d] + (pos[j] & 0xffffu) : 0;
+    }
+    // ---- destination row of every staging slot this thread will write out
+    int64_t dst[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        int i = k * THREADS + (int)threadIdx.x;
+        // last p with tile_start[p] <= i
+        uint32_t lo = 0, hi = N;  // invariant: tile_start[lo] <= i < tile_start[hi] (when i < tile_rows)
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (tile_start[mid] <= (uint32_t)i) lo = mid; else hi = mid;
+        }
+        dst[k] = (int64_t)i + delta[lo];
+    }
+
+    // ---- phase 2: every column through the staging buffer
+    for (int c = 0; c < P.n_cols; ++c) {
+        const PayloadCol& col = P.cols[c];
+        switch (col.width) {
+            case 8: scatter_fixed_column<THREADS, K, uint64_t>(col, stage, row0, P.n_rows, tile_rows, pos, dst, w, lane); break;
+            case 4: scatter_fixed_column<THREADS, K, uint32_t>(col, stage, row0, P.n_rows, tile_rows, pos, dst, w, lane); break;
+            case 2: scatter_fixed_column<THREADS, K, uint16_t>(col, stage, row0, P.n_rows, tile_rows, pos, dst, w, lane); break;
+            case 1: scatter_fixed_column<THREADS, K, uint8_t>(col, stage, row0, P.n_rows, tile_rows, pos, dst, w, lane); break;
+            case 16: scatter_fixed_column<THREADS, K, uint4>(col, stage, row0, P.n_rows, tile_rows, pos, dst, w, lane); break;
+            default: scatter_bit_column<THREADS, K>(col, stage, row0, P.n_rows, tile_rows, pos, dst, w, lane); break;
+        }
+    }
+}
+
+template <int THREADS, int K>
+inline size_t scatter_smem_bytes(uint32_t N, int stage_width) {
+    size_t off = ((size_t)THREADS * K * stage_width + 15) & ~(size_t)15;
+    off += (size_t)N * 8;
+    off += (size_t)(THREADS / 32) * N * 4;
+    off += (size_t)(N + 1) * 4;
+    off += (size_t)(THREADS / 32 + 1) * 4;
+    return off;
+}
+
+}  // namespace dfd

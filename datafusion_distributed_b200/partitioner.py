@@ -1,0 +1,78 @@
+"""Host mirror of the producer half: Partitioning::Hash + BatchPartitioner.
+
+Names follow the reference's operator surface
+(`Partitioning::Hash(exprs, n)`, `scale_partitioning`,
+src/execution_plans/common.rs:17-26; `BatchPartitioner` is DataFusion's).
+All compute goes through the C ABI into the CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as nv
+from .device import DeviceColumn, WorkerContext, columns_to_c
+
+
+@dataclass(frozen=True)
+class Partitioning:
+    """`Partitioning::Hash(exprs, n)` restricted to column-reference exprs."""
+
+    key_cols: Tuple[int, ...]
+    partition_count: int
+
+    @staticmethod
+    def Hash(key_cols: Sequence[int], n: int) -> "Partitioning":
+        return Partitioning(tuple(int(k) for k in key_cols), int(n))
+
+
+def scale_partitioning(p: Partitioning, f) -> Partitioning:
+    """src/execution_plans/common.rs:17-26 — Hash(exprs, p) -> Hash(exprs, f(p))."""
+    return Partitioning(p.key_cols, int(f(p.partition_count)))
+
+
+class HashPartitioner:
+    """≙ `BatchPartitioner::try_new(Partitioning::Hash(..), ..)` on one GPU."""
+
+    def __init__(self, ctx: WorkerContext, partitioning: Partitioning, seeds: Optional[Sequence[int]] = None):
+        self.ctx = ctx
+        self.partitioning = partitioning
+        self._h = C.c_void_p()
+        keys = (C.c_int32 * len(partitioning.key_cols))(*partitioning.key_cols)
+        seeds_arr = (C.c_uint64 * 4)(*seeds) if seeds is not None else None
+        nv.check(nv.lib().dfd_partitioner_create(ctx.handle, partitioning.partition_count, keys,
+                                                 len(partitioning.key_cols), seeds_arr, C.byref(self._h)))
+
+    @property
+    def num_partitions(self) -> int:
+        return self.partitioning.partition_count
+
+    def close(self):
+        if self._h:
+            nv.lib().dfd_partitioner_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def partition_ids(self, cols: Sequence[DeviceColumn], n_rows: int) -> np.ndarray:
+        """dest[i] = create_hashes(keys)[i] % N, computed on the GPU."""
+        out = self.ctx.alloc(max(n_rows * 4, 4))
+        nv.check(nv.lib().dfd_partition_ids_device(self._h, columns_to_c(cols), len(cols), n_rows, out.ptr))
+        return out.download(np.uint32, n_rows)
+
+    def partition(self, cols: Sequence[DeviceColumn], n_rows: int, out_cols: Optional[List[DeviceColumn]] = None,
+                  sync: bool = True):
+        """Partition device columns; returns (out_cols, part_starts[N+1] | None)."""
+        if out_cols is None:
+            out_cols = [DeviceColumn.empty_like(self.ctx, c, n_rows) for c in cols]
+        starts = (C.c_int64 * (self.num_partitions + 1))() if sync else None
+        nv.check(nv.lib().dfd_partition_device(self._h, columns_to_c(cols), len(cols), n_rows,
+                                               columns_to_c(out_cols), starts))
+        return out_cols, (np.frombuffer(starts, dtype=np.int64).copy() if sync else None)

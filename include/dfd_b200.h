@@ -1,0 +1,165 @@
+/*
+ * include/dfd_b200.h — C ABI of the B200-native hash-repartition shuffle.
+ *
+ * This is the drop-in boundary for ONE path of datafusion-distributed: the
+ * hash-repartition shuffle (producer `RepartitionExec(Hash(keys, P*T))` ->
+ * exchange -> consumer `NetworkShuffleExec`).  Plain C types only (pointers,
+ * sizes, Arrow C Data Interface structs); no torch / C++ types cross it.  A
+ * Rust `ExecutionPlan` shim binds these symbols with `extern "C"` (see
+ * INTEGRATION.md); tests and bench.py bind them with ctypes.
+ *
+ * Each entry point cites the reference interface it replaces
+ * (paths relative to the datafusion-distributed checkout @ f032463).
+ *
+ * Threading: every call may come from any thread.  A dfd_ctx owns one GPU's
+ * streams and scratch; calls on the same ctx are serialised internally.
+ * Errors: 0 == DFD_OK; otherwise a dfd_status code, with a human-readable
+ * message retrievable (per thread) through dfd_last_error().  Nothing aborts
+ * the process.  There is NO CPU fallback anywhere behind this ABI: if CUDA is
+ * unavailable every compute entry point returns DFD_ERR_CUDA.
+ */
+#ifndef DFD_B200_H
+#define DFD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "arrow_c_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFD_ABI_VERSION 1
+
+/* Maps onto DataFusionError in the Rust shim:
+ * INVALID_ARGUMENT/UNSUPPORTED -> Plan/NotImplemented, OOM/CAPACITY ->
+ * ResourcesExhausted, CUDA/NCCL -> Execution, INTERNAL -> Internal
+ * (reference error transport: src/protobuf/errors/mod.rs:22-69). */
+typedef enum {
+    DFD_OK = 0,
+    DFD_ERR_INVALID_ARGUMENT = 1,
+    DFD_ERR_OOM = 2,
+    DFD_ERR_CUDA = 3,
+    DFD_ERR_NCCL = 4,
+    DFD_ERR_INTERNAL = 5,
+    DFD_ERR_UNSUPPORTED = 6,
+    DFD_ERR_CAPACITY = 7
+} dfd_status;
+
+typedef struct dfd_ctx dfd_ctx;                 /* one per GPU / worker            */
+typedef struct dfd_partitioner dfd_partitioner; /* ≙ BatchPartitioner::Hash        */
+
+/* Physical layout of one column, device- or host-resident: the buffers of an
+ * Arrow array flattened (what ArrowArray.buffers[] holds for these types). */
+typedef enum {
+    DFD_COL_FIXED = 0,     /* primitive values, `width` bytes each (1,2,4,8,16)     */
+    DFD_COL_BOOL = 1,      /* bit-packed values                                     */
+    DFD_COL_UTF8 = 2,      /* int32 offsets + bytes; hashed as Rust `str`           */
+    DFD_COL_LARGE_UTF8 = 3,/* int64 offsets + bytes                                 */
+    DFD_COL_BINARY = 4     /* int32 offsets + bytes; hashed as Rust `[u8]`          */
+} dfd_col_kind;
+
+typedef struct {
+    int32_t kind;            /* dfd_col_kind                                         */
+    int32_t width;           /* DFD_COL_FIXED: bytes per value                       */
+    void* values;            /* values / bitmap / string bytes                       */
+    void* offsets;           /* var-width kinds only                                 */
+    uint8_t* validity;       /* Arrow validity bitmap (LSB first) or NULL = no nulls */
+    int64_t offset;          /* Arrow logical offset (rows) into the buffers         */
+} dfd_column;
+
+/* Counters of the shuffle path; the reference exposes the same quantities as
+ * DataFusion metrics on NetworkShuffleExec (`bytes_transferred`,
+ * `elapsed_compute`, output_rows; src/worker/worker_connection_pool.rs:160-181). */
+typedef struct {
+    uint64_t calls;          /* partition calls since creation / last reset          */
+    uint64_t rows;           /* rows partitioned                                      */
+    uint64_t bytes_in;       /* payload bytes read (algorithmic)                      */
+    uint64_t bytes_out;      /* payload bytes written (algorithmic)                   */
+    uint64_t kernel_launches;/* CUDA kernels launched by this library                 */
+    double hist_ms;          /* sums of CUDA-event durations (profiling mode only)    */
+    double scan_ms;
+    double scatter_ms;
+    double h2d_ms;
+    double d2h_ms;
+    uint64_t scatter_launches;
+} dfd_metrics;
+
+/* ---- library / context ------------------------------------------------ */
+
+int dfd_abi_version(void);
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* dfd_last_error(void);
+const char* dfd_status_name(int status);
+int dfd_device_count(int* out_count);
+
+/* One context per GPU == one worker (reference: `Worker`,
+ * src/worker/worker_service.rs:39-49; one process per GPU in this build). */
+int dfd_ctx_create(int device, dfd_ctx** out);
+void dfd_ctx_destroy(dfd_ctx* ctx);
+/* cudaStream_t the compute kernels are launched on (for external event timing). */
+void* dfd_ctx_stream(dfd_ctx* ctx);
+int dfd_ctx_synchronize(dfd_ctx* ctx);
+/* When on, every kernel is bracketed by CUDA events on its launch stream and
+ * the durations are accumulated into dfd_metrics (costs one sync per call). */
+int dfd_ctx_set_profiling(dfd_ctx* ctx, int on);
+
+/* Buffer helpers so a host language without CUDA bindings can own memory.
+ * Host allocations are pinned (page-locked). */
+int dfd_device_alloc(dfd_ctx* ctx, size_t bytes, void** out);
+int dfd_device_free(dfd_ctx* ctx, void* ptr);
+int dfd_host_alloc(dfd_ctx* ctx, size_t bytes, void** out);
+int dfd_host_free(dfd_ctx* ctx, void* ptr);
+int dfd_memcpy_h2d(dfd_ctx* ctx, void* dst_device, const void* src_host, size_t bytes);
+int dfd_memcpy_d2h(dfd_ctx* ctx, void* dst_host, const void* src_device, size_t bytes);
+int dfd_memset_device(dfd_ctx* ctx, void* dst_device, int value, size_t bytes);
+/* Writes >L2-size scratch so the next timed launch starts with a cold L2. */
+int dfd_flush_l2(dfd_ctx* ctx);
+
+/* CUDA-event stopwatch on the compute stream (bench.py's timed region). */
+int dfd_timer_start(dfd_ctx* ctx);
+int dfd_timer_stop(dfd_ctx* ctx, float* out_ms);
+
+/* ---- hash partitioner --------------------------------------------------
+ * Replaces DataFusion's `BatchPartitioner::try_new(Partitioning::Hash(exprs,
+ * n), ..)` + `partition()` as configured by the reference at
+ * src/execution_plans/network_shuffle.rs:126-134 (Hash(keys, P * task_count))
+ * and executed at src/worker/impl_execute_task.rs:77-86.
+ *   key_cols : indices of the key columns (`Column` exprs) in hashing order
+ *   seeds    : ahash RandomState::with_seeds arguments; NULL selects
+ *              DataFusion's REPARTITION_RANDOM_STATE = (0,0,0,0)
+ * num_partitions must be in [1, 65535]. */
+int dfd_partitioner_create(dfd_ctx* ctx, uint32_t num_partitions, const int32_t* key_cols,
+                           int n_keys, const uint64_t* seeds, dfd_partitioner** out);
+void dfd_partitioner_destroy(dfd_partitioner* p);
+uint32_t dfd_partitioner_num_partitions(const dfd_partitioner* p);
+
+/* dest[i] = create_hashes(key columns)[i] % num_partitions, for device
+ * columns; `dest_device` holds n_rows uint32.  (Debug/parity entry point for
+ * `create_hashes` + `hash % partitions`.) */
+int dfd_partition_ids_device(dfd_partitioner* p, const dfd_column* cols, int n_cols,
+                             int64_t n_rows, uint32_t* dest_device);
+
+/* The hot path, device-resident: partition `n_rows` rows of `n_cols` columns
+ * into num_partitions destinations.  Output column c is ONE buffer
+ * (out_cols[c].values, capacity n_rows) in which destination p occupies rows
+ * [part_starts[p], part_starts[p+1]) — N contiguous per-destination Arrow
+ * buffers, zero-copy sliceable.  Within a destination, rows keep input order
+ * (SURVEY.md §8a invariant iii; DataFusion pushes indices in row order).
+ * part_starts_host (N+1 int64, may be NULL) is filled after a stream sync;
+ * with NULL the call is fully asynchronous on dfd_ctx_stream() and the device
+ * copy is available through dfd_partitioner_part_starts_device().
+ * Nullable payload columns: out_cols[c].validity must point to a zeroed
+ * bitmap of ceil(n_rows/8) bytes (output offset is 0). */
+int dfd_partition_device(dfd_partitioner* p, const dfd_column* in_cols, int n_cols,
+                         int64_t n_rows, const dfd_column* out_cols, int64_t* part_starts_host);
+const int64_t* dfd_partitioner_part_starts_device(const dfd_partitioner* p);
+
+int dfd_metrics_get(dfd_ctx* ctx, dfd_metrics* out);
+int dfd_metrics_reset(dfd_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFD_B200_H */

@@ -1,0 +1,413 @@
+/*
+ * oracle/df_oracle.c — CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+ * See df_oracle.h for scope, parity status ("parity unpinned") and the
+ * reference call sites.  Each function names the upstream source it restates.
+ *
+ * Build: gcc -O2 -fPIC -shared -pthread oracle/df_oracle.c -o oracle/libdf_oracle.so
+ */
+#include "df_oracle.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned __int128 u128;
+
+/* ahash 0.8.12 src/random_state.rs: const PI2: [u64; 4] */
+static const uint64_t ORC_PI2[4] = {
+    0x452821e638d01377ULL, 0xbe5466cf34e90c6cULL, 0xc0ac29b7c97c50ddULL, 0x3f84d5b5b5470917ULL};
+
+/* ahash 0.8.12 src/fallback_hash.rs: MULTIPLE (Knuth's LCG constant), ROT */
+#define ORC_MULTIPLE 6364136223846793005ULL
+#define ORC_ROT 23
+
+static inline uint64_t rotl64(uint64_t x, unsigned r) {
+    r &= 63;
+    return r ? (x << r) | (x >> (64 - r)) : x;
+}
+
+/* ahash src/operations.rs folded_multiply (cfg folded_multiply: 64-bit targets) */
+static inline uint64_t folded_multiply(uint64_t s, uint64_t by) {
+    u128 r = (u128)s * (u128)by;
+    return (uint64_t)r ^ (uint64_t)(r >> 64);
+}
+
+/* RandomState::with_seeds (random_state.rs): each seed is XORed with PI2 */
+orc_random_state orc_state_with_seeds(uint64_t s0, uint64_t s1, uint64_t s2, uint64_t s3) {
+    orc_random_state st = {s0 ^ ORC_PI2[0], s1 ^ ORC_PI2[1], s2 ^ ORC_PI2[2], s3 ^ ORC_PI2[3]};
+    return st;
+}
+
+/* datafusion-physical-plan repartition/mod.rs: REPARTITION_RANDOM_STATE */
+orc_random_state orc_repartition_random_state(void) { return orc_state_with_seeds(0, 0, 0, 0); }
+
+typedef struct {
+    uint64_t buffer, pad, extra0, extra1;
+} orc_hasher;
+
+/* AHasher::from_random_state (fallback_hash.rs): buffer=k1, pad=k0, extra=[k2,k3] */
+static inline orc_hasher orc_hasher_from_state(const orc_random_state* st) {
+    orc_hasher h = {st->k1, st->k0, st->k2, st->k3};
+    return h;
+}
+
+/* AHasher::update */
+static inline void h_update(orc_hasher* h, uint64_t x) {
+    h->buffer = folded_multiply(x ^ h->buffer, ORC_MULTIPLE);
+}
+
+/* AHasher::large_update */
+static inline void h_large_update(orc_hasher* h, uint64_t lo, uint64_t hi) {
+    uint64_t combined = folded_multiply(lo ^ h->extra0, hi ^ h->extra1);
+    h->buffer = rotl64((h->buffer + h->pad) ^ combined, ORC_ROT);
+}
+
+/* AHasher::finish */
+static inline uint64_t h_finish(const orc_hasher* h) {
+    unsigned rot = (unsigned)(h->buffer & 63);
+    return rotl64(folded_multiply(h->buffer, h->pad), rot);
+}
+
+static inline uint64_t rd_le(const uint8_t* p, int n) {
+    uint64_t v = 0;
+    memcpy(&v, p, (size_t)n); /* little-endian host (x86_64), as the reference build */
+    return v;
+}
+
+/* AHasher::write(&[u8]) + operations.rs read_small */
+static void h_write(orc_hasher* h, const uint8_t* data, size_t len) {
+    h->buffer = (h->buffer + (uint64_t)len) * ORC_MULTIPLE;
+    if (len > 8) {
+        if (len > 16) {
+            h_large_update(h, rd_le(data + len - 16, 8), rd_le(data + len - 8, 8));
+            while (len > 16) {
+                h_large_update(h, rd_le(data, 8), rd_le(data + 8, 8));
+                data += 16;
+                len -= 16;
+            }
+        } else {
+            h_large_update(h, rd_le(data, 8), rd_le(data + len - 8, 8));
+        }
+    } else {
+        uint64_t a, b;
+        if (len >= 2) {
+            if (len >= 4) {
+                a = rd_le(data, 4);
+                b = rd_le(data + len - 4, 4);
+            } else {
+                a = rd_le(data, 2);
+                b = data[len - 1];
+            }
+        } else if (len > 0) {
+            a = data[0];
+            b = data[0];
+        } else {
+            a = 0;
+            b = 0;
+        }
+        h_large_update(h, a, b);
+    }
+}
+
+uint64_t orc_hash_one_u64(const orc_random_state* st, uint64_t x) {
+    orc_hasher h = orc_hasher_from_state(st);
+    h_update(&h, x);
+    return h_finish(&h);
+}
+
+uint64_t orc_hash_one_u128(const orc_random_state* st, uint64_t lo, uint64_t hi) {
+    orc_hasher h = orc_hasher_from_state(st);
+    h_large_update(&h, lo, hi);
+    return h_finish(&h);
+}
+
+uint64_t orc_hash_one_str(const orc_random_state* st, const uint8_t* p, size_t len) {
+    orc_hasher h = orc_hasher_from_state(st);
+    h_write(&h, p, len);
+    h_update(&h, 0xff); /* Hasher::write_str default: write(bytes); write_u8(0xff) */
+    return h_finish(&h);
+}
+
+uint64_t orc_hash_one_bytes(const orc_random_state* st, const uint8_t* p, size_t len) {
+    orc_hasher h = orc_hasher_from_state(st);
+    h_update(&h, (uint64_t)len); /* write_length_prefix -> write_usize */
+    h_write(&h, p, len);
+    return h_finish(&h);
+}
+
+/* datafusion-common hash_utils.rs combine_hashes */
+uint64_t orc_combine_hashes(uint64_t l, uint64_t r) {
+    uint64_t hash = (uint64_t)(17 * 37) + l;
+    return hash * 37 + r;
+}
+
+static inline int bit_get(const uint8_t* bm, int64_t i) { return (bm[i >> 3] >> (i & 7)) & 1; }
+
+static inline uint64_t hash_value_at(const orc_column* c, int64_t i, const orc_random_state* st) {
+    int64_t j = i + c->offset;
+    switch (c->kind) {
+        case ORC_FIXED: {
+            const uint8_t* p = (const uint8_t*)c->values + (size_t)j * (size_t)c->width;
+            if (c->width == 16) return orc_hash_one_u128(st, rd_le(p, 8), rd_le(p + 8, 8));
+            return orc_hash_one_u64(st, rd_le(p, c->width));
+        }
+        case ORC_BOOL:
+            return orc_hash_one_u64(st, (uint64_t)bit_get((const uint8_t*)c->values, j));
+        case ORC_UTF8:
+        case ORC_BINARY: {
+            const int32_t* off = (const int32_t*)c->offsets;
+            const uint8_t* d = (const uint8_t*)c->values + off[j];
+            size_t len = (size_t)(off[j + 1] - off[j]);
+            return c->kind == ORC_UTF8 ? orc_hash_one_str(st, d, len) : orc_hash_one_bytes(st, d, len);
+        }
+        case ORC_LARGE_UTF8: {
+            const int64_t* off = (const int64_t*)c->offsets;
+            return orc_hash_one_str(st, (const uint8_t*)c->values + off[j], (size_t)(off[j + 1] - off[j]));
+        }
+    }
+    return 0;
+}
+
+/* datafusion-common hash_utils.rs create_hashes / hash_array_primitive / hash_array:
+ * rehash = (column index >= 1); null rows are skipped. */
+void orc_create_hashes(const orc_column* cols, int n_cols, int64_t n_rows,
+                       const orc_random_state* st, uint64_t* hashes) {
+    for (int c = 0; c < n_cols; ++c) {
+        const orc_column* col = &cols[c];
+        int rehash = c >= 1;
+        for (int64_t i = 0; i < n_rows; ++i) {
+            if (col->validity && !bit_get(col->validity, i + col->offset)) continue;
+            uint64_t v = hash_value_at(col, i, st);
+            hashes[i] = rehash ? orc_combine_hashes(v, hashes[i]) : v;
+        }
+    }
+}
+
+/* datafusion-physical-plan repartition/mod.rs BatchPartitioner::partition_iter (Hash arm):
+ *   for (index, hash) in hash_buffer.iter().enumerate() { indices[(*hash % *partitions as u64)].push(index) } */
+void orc_partition_indices(const uint64_t* hashes, int64_t n_rows, uint32_t num_partitions,
+                           int64_t* counts, uint32_t* indices, int64_t* starts) {
+    for (uint32_t p = 0; p < num_partitions; ++p) counts[p] = 0;
+    for (int64_t i = 0; i < n_rows; ++i) counts[hashes[i] % num_partitions]++;
+    starts[0] = 0;
+    for (uint32_t p = 0; p < num_partitions; ++p) starts[p + 1] = starts[p] + counts[p];
+    int64_t* cur = (int64_t*)malloc(sizeof(int64_t) * num_partitions);
+    memcpy(cur, starts, sizeof(int64_t) * num_partitions);
+    for (int64_t i = 0; i < n_rows; ++i) indices[cur[hashes[i] % num_partitions]++] = (uint32_t)i;
+    free(cur);
+}
+
+/* arrow-select take (primitive): gather by u32 index */
+void orc_take_fixed(const void* values, int width, const uint32_t* idx, int64_t n, void* out) {
+    switch (width) {
+        case 8: {
+            const uint64_t* v = (const uint64_t*)values;
+            uint64_t* o = (uint64_t*)out;
+            for (int64_t i = 0; i < n; ++i) o[i] = v[idx[i]];
+            break;
+        }
+        case 4: {
+            const uint32_t* v = (const uint32_t*)values;
+            uint32_t* o = (uint32_t*)out;
+            for (int64_t i = 0; i < n; ++i) o[i] = v[idx[i]];
+            break;
+        }
+        default: {
+            const uint8_t* v = (const uint8_t*)values;
+            uint8_t* o = (uint8_t*)out;
+            for (int64_t i = 0; i < n; ++i) memcpy(o + (size_t)i * width, v + (size_t)idx[i] * width, (size_t)width);
+        }
+    }
+}
+
+void orc_partition_ids(const orc_column* key_cols, int n_keys, int64_t n_rows,
+                       uint32_t num_partitions, uint32_t* dest) {
+    orc_random_state st = orc_repartition_random_state();
+    const int64_t CH = 1 << 16;
+    uint64_t* h = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)CH);
+    orc_column* cols = (orc_column*)malloc(sizeof(orc_column) * (size_t)n_keys);
+    for (int64_t base = 0; base < n_rows; base += CH) {
+        int64_t n = n_rows - base < CH ? n_rows - base : CH;
+        for (int k = 0; k < n_keys; ++k) {
+            cols[k] = key_cols[k];
+            cols[k].offset += base;
+        }
+        memset(h, 0, sizeof(uint64_t) * (size_t)n);
+        orc_create_hashes(cols, n_keys, n, &st, h);
+        for (int64_t i = 0; i < n; ++i) dest[base + i] = (uint32_t)(h[i] % num_partitions);
+    }
+    free(h);
+    free(cols);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Whole-operator restatement (timed CPU baseline).                          */
+/* ------------------------------------------------------------------------- */
+
+/* One destination's LimitedBatchCoalescer + the list of batches it emitted. */
+typedef struct {
+    uint8_t*** batches; /* [n_batches][n_cols] completed (and the in-progress last) batches */
+    int64_t* batch_rows;
+    int64_t n_batches, cap_batches;
+    int64_t rows;       /* total rows sent to this destination */
+} part_out;
+
+typedef struct {
+    /* shared, read-only */
+    const void* const* cols;
+    const int32_t* widths;
+    int n_cols;
+    int64_t n_rows;
+    const int32_t* key_cols;
+    int n_keys;
+    uint32_t N;
+    int64_t batch_size;
+    int n_threads, tid;
+    /* per-thread result: per destination, everything this input partition sent */
+    part_out* outs; /* [N] */
+    int rc;
+} worker_arg;
+
+static int part_out_new_batch(part_out* o, int n_cols, const int32_t* widths, int64_t batch_size) {
+    if (o->n_batches == o->cap_batches) {
+        int64_t cap = o->cap_batches ? o->cap_batches * 2 : 16;
+        o->batches = (uint8_t***)realloc(o->batches, sizeof(uint8_t**) * (size_t)cap);
+        o->batch_rows = (int64_t*)realloc(o->batch_rows, sizeof(int64_t) * (size_t)cap);
+        if (!o->batches || !o->batch_rows) return -1;
+        o->cap_batches = cap;
+    }
+    uint8_t** b = (uint8_t**)calloc((size_t)n_cols, sizeof(uint8_t*));
+    if (!b) return -1;
+    for (int c = 0; c < n_cols; ++c) {
+        b[c] = (uint8_t*)malloc((size_t)batch_size * (size_t)widths[c]);
+        if (!b[c]) return -1;
+    }
+    o->batches[o->n_batches] = b;
+    o->batch_rows[o->n_batches] = 0;
+    o->n_batches++;
+    return 0;
+}
+
+/* LimitedBatchCoalescer::push_batch: copy `n` rows of a taken sub-batch column
+ * set into the in-progress batch, emitting a batch every `batch_size` rows. */
+static int part_out_push(part_out* o, int n_cols, const int32_t* widths, int64_t batch_size,
+                         uint8_t* const* taken, int64_t n) {
+    int64_t done = 0;
+    while (done < n) {
+        if (o->n_batches == 0 || o->batch_rows[o->n_batches - 1] == batch_size)
+            if (part_out_new_batch(o, n_cols, widths, batch_size)) return -1;
+        int64_t bi = o->n_batches - 1;
+        int64_t room = batch_size - o->batch_rows[bi];
+        int64_t m = n - done < room ? n - done : room;
+        for (int c = 0; c < n_cols; ++c)
+            memcpy(o->batches[bi][c] + (size_t)o->batch_rows[bi] * (size_t)widths[c],
+                   taken[c] + (size_t)done * (size_t)widths[c], (size_t)m * (size_t)widths[c]);
+        o->batch_rows[bi] += m;
+        done += m;
+    }
+    o->rows += n;
+    return 0;
+}
+
+static void* worker_main(void* vp) {
+    worker_arg* a = (worker_arg*)vp;
+    const orc_random_state st = orc_repartition_random_state();
+    const int64_t B = a->batch_size;
+    const uint32_t N = a->N;
+    uint64_t* hash_buffer = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)B);
+    uint32_t* indices = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)B);
+    int64_t* counts = (int64_t*)malloc(sizeof(int64_t) * N);
+    int64_t* starts = (int64_t*)malloc(sizeof(int64_t) * (N + 1));
+    orc_column* kc = (orc_column*)calloc((size_t)a->n_keys, sizeof(orc_column));
+    uint8_t** taken = (uint8_t**)calloc((size_t)a->n_cols, sizeof(uint8_t*));
+    int64_t n_batches = (a->n_rows + B - 1) / B;
+    for (int64_t b = a->tid; b < n_batches; b += a->n_threads) {
+        int64_t base = b * B;
+        int64_t n = a->n_rows - base < B ? a->n_rows - base : B;
+        for (int k = 0; k < a->n_keys; ++k) {
+            int c = a->key_cols[k];
+            kc[k].kind = ORC_FIXED;
+            kc[k].width = a->widths[c];
+            kc[k].values = (const uint8_t*)a->cols[c] + (size_t)base * (size_t)a->widths[c];
+            kc[k].validity = NULL;
+            kc[k].offset = 0;
+        }
+        memset(hash_buffer, 0, sizeof(uint64_t) * (size_t)n); /* hash_buffer.resize(n, 0) */
+        orc_create_hashes(kc, a->n_keys, n, &st, hash_buffer);
+        orc_partition_indices(hash_buffer, n, N, counts, indices, starts);
+        for (uint32_t p = 0; p < N; ++p) {
+            if (counts[p] == 0) continue; /* only non-empty partitions are emitted */
+            /* take_arrays(batch.columns(), indices[p]): one fresh array per column */
+            for (int c = 0; c < a->n_cols; ++c) {
+                int w = a->widths[c];
+                taken[c] = (uint8_t*)malloc((size_t)counts[p] * (size_t)w);
+                if (!taken[c]) { a->rc = -1; goto done; }
+                orc_take_fixed((const uint8_t*)a->cols[c] + (size_t)base * (size_t)w, w,
+                               indices + starts[p], counts[p], taken[c]);
+            }
+            /* per-output channel -> LimitedBatchCoalescer (target batch_size) */
+            int rc = part_out_push(&a->outs[p], a->n_cols, a->widths, B, taken, counts[p]);
+            for (int c = 0; c < a->n_cols; ++c) free(taken[c]);
+            if (rc) { a->rc = -1; goto done; }
+        }
+    }
+done:
+    free(hash_buffer); free(indices); free(counts); free(starts); free(kc); free(taken);
+    return NULL;
+}
+
+int orc_repartition_table(const void* const* cols, const int32_t* widths, int n_cols,
+                          int64_t n_rows, const int32_t* key_cols, int n_keys,
+                          uint32_t num_partitions, int64_t batch_size, int n_threads,
+                          void* const* out_cols, int64_t* out_counts, int64_t* out_starts) {
+    if (n_threads < 1) n_threads = 1;
+    const uint32_t N = num_partitions;
+    worker_arg* args = (worker_arg*)calloc((size_t)n_threads, sizeof(worker_arg));
+    pthread_t* th = (pthread_t*)calloc((size_t)n_threads, sizeof(pthread_t));
+    for (int t = 0; t < n_threads; ++t) {
+        worker_arg* a = &args[t];
+        a->cols = cols; a->widths = widths; a->n_cols = n_cols; a->n_rows = n_rows;
+        a->key_cols = key_cols; a->n_keys = n_keys; a->N = N; a->batch_size = batch_size;
+        a->n_threads = n_threads; a->tid = t;
+        a->outs = (part_out*)calloc(N, sizeof(part_out));
+    }
+    for (int t = 0; t < n_threads; ++t) pthread_create(&th[t], NULL, worker_main, &args[t]);
+    int rc = 0;
+    for (int t = 0; t < n_threads; ++t) { pthread_join(th[t], NULL); if (args[t].rc) rc = args[t].rc; }
+    /* (checker only, outside what the reference does) concatenate per
+     * destination in thread-major order so tests can compare buffers. */
+    out_starts[0] = 0;
+    for (uint32_t p = 0; p < N; ++p) {
+        int64_t cnt = 0;
+        for (int t = 0; t < n_threads; ++t) cnt += args[t].outs[p].rows;
+        out_counts[p] = cnt;
+        out_starts[p + 1] = out_starts[p] + cnt;
+    }
+    if (!rc && out_cols) {
+        for (uint32_t p = 0; p < N; ++p) {
+            int64_t pos = out_starts[p];
+            for (int t = 0; t < n_threads; ++t) {
+                part_out* o = &args[t].outs[p];
+                for (int64_t b = 0; b < o->n_batches; ++b) {
+                    for (int c = 0; c < n_cols; ++c)
+                        memcpy((uint8_t*)out_cols[c] + (size_t)pos * (size_t)widths[c], o->batches[b][c],
+                               (size_t)o->batch_rows[b] * (size_t)widths[c]);
+                    pos += o->batch_rows[b];
+                }
+            }
+        }
+    }
+    for (int t = 0; t < n_threads; ++t) {
+        for (uint32_t p = 0; p < N; ++p) {
+            part_out* o = &args[t].outs[p];
+            for (int64_t b = 0; b < o->n_batches; ++b) {
+                for (int c = 0; c < n_cols; ++c) free(o->batches[b][c]);
+                free(o->batches[b]);
+            }
+            free(o->batches); free(o->batch_rows);
+        }
+        free(args[t].outs);
+    }
+    free(args); free(th);
+    return rc;
+}
