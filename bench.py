@@ -1,0 +1,221 @@
+#!/usr/bin/env python
+"""bench.py — shuffle rows/sec on the BASELINE.json workload.
+
+Workload (config.workload = "cfg2"): 2^26 rows x 8 Int64 columns, col0 = uniform
+i64 key, cols 1-7 = row_id*8+j, Hash([col0], 8) — BASELINE.json configs[1].
+One "step" = one pass of the hot path over the whole table.
+
+  value     rows/s with inputs resident in HBM (CUDA events on the library's stream)
+  roofline  dominant kernel (k_scatter): algorithmic bytes (2*C*w per row) / its
+            CUDA-event duration inside the timed region, vs MEASURED_PEAKS.json
+  e2e       same metric through the C-ABI with HOST (pinned) buffers, H2D+D2H timed
+  cpu_baseline  the oracle port of DataFusion's RepartitionExec on the host cores
+
+`--impl reference` times the CPU path only (the oracle port, all host threads).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "shuffle rows/sec (64M rows, 8xi64, 8-way hash repartition)"
+N_ROWS = 1 << 26
+N_COLS = 8
+WIDTH = 8
+NUM_PARTITIONS = 8
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int = 0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_reference_arm(n_rows: int, threads: int, reps: int):
+    """The reference's CPU path for this workload: oracle port of RepartitionExec(Hash)."""
+    from oracle import oracle as orc
+    from tests.util import cfg2_columns
+
+    cols = cfg2_columns(n_rows, N_COLS)
+    orc.repartition_table(cols, [0], NUM_PARTITIONS, 8192, threads, materialize=False)  # warm allocator
+    best = None
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.repartition_table(cols, [0], NUM_PARTITIONS, 8192, threads, materialize=False)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return n_rows / best, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_rows = 1 << 23
+    vals = []
+    t_all = time.perf_counter()
+    from oracle import oracle as orc
+    from tests.util import cfg2_columns
+
+    cols = cfg2_columns(sample_rows, N_COLS)
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        orc.repartition_table(cols, [0], NUM_PARTITIONS, 8192, threads, materialize=False)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            vals.append(dt)
+        if time.perf_counter() - t_all > 150 and len(vals) >= 1:
+            break
+    ms = 1e3 * sum(vals) / len(vals)
+    v = sample_rows / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int64", "data": "synthetic",
+        "config": {"workload": "cfg2: 8xInt64, Hash([col0], 8), batch 8192; bounded sample", "rows_per_step": sample_rows},
+        "cpu_baseline": {"value": v, "unit": "rows/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample_rows} rows (1/8 of the 2^26-row workload) per step, oracle port of "
+                                   "DataFusion RepartitionExec(Hash) + LimitedBatchCoalescer, one thread per input partition"},
+        "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=N_ROWS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    import datafusion_distributed_b200 as dfd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != 1 or args.gpus != 1:
+        raise SystemExit("multi-GPU exchange bench not wired yet")
+    dev = 0
+    torch.cuda.set_device(dev)
+    n = args.rows
+    g = torch.Generator(device="cuda").manual_seed(42)
+    key = torch.randint(-(2**63), 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+    rid = torch.arange(n, dtype=torch.int64, device="cuda")
+    ins = [key] + [rid * 8 + j for j in range(1, N_COLS)]
+    outs = [torch.empty_like(t) for t in ins]
+    del rid
+    torch.cuda.synchronize()
+
+    ctx = dfd.WorkerContext(dev)
+    part = dfd.HashPartitioner(ctx, dfd.Partitioning.Hash([0], NUM_PARTITIONS))
+    in_cols = [dfd.DeviceColumn.from_torch(t) for t in ins]
+    out_cols = [dfd.DeviceColumn.from_torch(t) for t in outs]
+
+    for _ in range(max(args.warmup, 3)):
+        part.partition(in_cols, n, out_cols, sync=False)
+    ctx.synchronize()
+    ctx.reset_metrics()
+    ctx.set_profiling(True)
+    # inputs (4 GiB) + outputs (4 GiB) are far larger than the 126 MB L2: no flush needed between steps
+    with ClockSampler(dev) as clocks:
+        ctx.timer_start()
+        for _ in range(args.steps):
+            part.partition(in_cols, n, out_cols, sync=False)
+        ms_total = ctx.timer_stop()
+    m = ctx.metrics()
+    ctx.set_profiling(False)
+    ms_per_step = ms_total / args.steps
+    value = n / (ms_per_step / 1e3)
+
+    peak, peak_src = measured_peaks()
+    alg_bytes = 2.0 * N_COLS * WIDTH * n
+    scatter_ms = m["scatter_ms"] / max(m["scatter_launches"], 1)
+    achieved = alg_bytes / (scatter_ms / 1e3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int64", "data": "synthetic",
+        "config": {"workload": "cfg2: 2^26 rows x 8 Int64, Hash([col0], 8), device-resident table", "rows": n,
+                   "columns": N_COLS, "num_partitions": NUM_PARTITIONS, "l2": "inputs+outputs (8 GiB) >> L2, no flush"},
+        "roofline": {"bound": "hbm", "kernel": "k_scatter", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scatter_ms,
+                     "hist_ms": m["hist_ms"] / max(m["calls"], 1), "scan_ms": m["scan_ms"] / max(m["calls"], 1)},
+        "gpu_launches": int(m["kernel_launches"]),
+        "clocks": clocks.summary(),
+        "e2e": None,
+    }
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = 1 << 23
+        v, times = cpu_reference_arm(sample, threads, 2)
+        line["cpu_baseline"] = {"value": v, "unit": "rows/s", "cores": threads, "kind": "port",
+                                "sample": f"{sample} rows of the same workload (1/8), best of 2, oracle port of RepartitionExec(Hash)"}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -56,6 +56,24 @@ int Scratch::ensure(size_t need, int device) {
 
 }  // namespace dfd
 
+int dfd_ctx::drain_events() {
+    if (ev_pending == 0) return DFD_OK;
+    cudaError_t e = cudaEventSynchronize(ev_ring[4 * (ev_pending - 1) + 3]);
+    if (e != cudaSuccess) return dfd::cuda_error(e, "partition kernels");
+    for (size_t i = 0; i < ev_pending; ++i) {
+        cudaEvent_t* ev = &ev_ring[4 * i];
+        float a = 0, b = 0, d = 0;
+        cudaEventElapsedTime(&a, ev[0], ev[1]);
+        cudaEventElapsedTime(&b, ev[1], ev[2]);
+        cudaEventElapsedTime(&d, ev[2], ev[3]);
+        metrics.hist_ms += a;
+        metrics.scan_ms += b;
+        metrics.scatter_ms += d;
+    }
+    ev_pending = 0;
+    return DFD_OK;
+}
+
 using namespace dfd;
 
 static int build_keyset(const dfd_partitioner* p, const dfd_column* cols, int n_cols, KeySet* ks) {
@@ -175,18 +193,30 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
     int64_t* d_totals = (int64_t*)((char*)c->scratch.ptr + hist_bytes + base_bytes);
 
     const bool prof = c->profiling;
-    if (prof) cudaEventRecord(c->ev[0], stream);
+    cudaEvent_t* ev = nullptr;
+    if (prof) {
+        if (c->ev_ring.empty()) {
+            c->ev_ring.resize(4 * dfd_ctx::EV_RING_CALLS);
+            for (auto& e : c->ev_ring) cudaEventCreate(&e);
+        }
+        if (c->ev_pending == dfd_ctx::EV_RING_CALLS) {
+            rc = c->drain_events();
+            if (rc) return rc;
+        }
+        ev = &c->ev_ring[4 * c->ev_pending];
+        cudaEventRecord(ev[0], stream);
+    }
     {
         size_t smem = (size_t)N * 4;
         k_tile_hist<TILE_THREADS, TILE_K><<<(unsigned)n_tiles, TILE_THREADS, smem, stream>>>(ks, p->st, p->mod, n_rows, n_tiles, N, d_hist);
         LAUNCH_CHECK("k_tile_hist");
     }
-    if (prof) cudaEventRecord(c->ev[1], stream);
+    if (prof) cudaEventRecord(ev[1], stream);
     k_scan_tiles<1024><<<N, 1024, 0, stream>>>(d_hist, d_base, d_totals, n_tiles);
     LAUNCH_CHECK("k_scan_tiles");
     k_part_starts<<<1, 1024, 0, stream>>>(d_totals, p->d_part_starts, N);
     LAUNCH_CHECK("k_part_starts");
-    if (prof) cudaEventRecord(c->ev[2], stream);
+    if (prof) cudaEventRecord(ev[2], stream);
     c->metrics.kernel_launches += 3;
 
     size_t smem = scatter_smem_bytes<TILE_THREADS, TILE_K>(N, stage_width);
@@ -216,24 +246,16 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
         LAUNCH_CHECK("k_scatter");
         ++launches;
     }
-    if (prof) cudaEventRecord(c->ev[3], stream);
+    if (prof) {
+        cudaEventRecord(ev[3], stream);
+        c->ev_pending++;
+    }
     c->metrics.kernel_launches += launches;
     c->metrics.scatter_launches += launches;
     c->metrics.calls++;
     c->metrics.rows += (uint64_t)n_rows;
     c->metrics.bytes_in += bytes;
     c->metrics.bytes_out += bytes;
-    if (prof) {
-        cudaError_t e = cudaEventSynchronize(c->ev[3]);
-        if (e != cudaSuccess) return cuda_error(e, "partition kernels");
-        float a = 0, b = 0, d = 0;
-        cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
-        cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
-        cudaEventElapsedTime(&d, c->ev[2], c->ev[3]);
-        c->metrics.hist_ms += a;
-        c->metrics.scan_ms += b;
-        c->metrics.scatter_ms += d;
-    }
     return DFD_OK;
 }
 
@@ -290,7 +312,6 @@ int dfd_ctx_create(int device, dfd_ctx** out) {
         delete c;
         return cuda_error(e, "cudaStreamCreate");
     }
-    for (auto& ev : c->ev) cudaEventCreate(&ev);
     cudaEventCreate(&c->timer_a);
     cudaEventCreate(&c->timer_b);
     *out = c;
@@ -303,7 +324,7 @@ void dfd_ctx_destroy(dfd_ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->scratch.ptr) cudaFree(c->scratch.ptr);
     if (c->flush.ptr) cudaFree(c->flush.ptr);
-    for (auto& ev : c->ev) cudaEventDestroy(ev);
+    for (auto& ev : c->ev_ring) cudaEventDestroy(ev);
     cudaEventDestroy(c->timer_a);
     cudaEventDestroy(c->timer_b);
     cudaStreamDestroy(c->stream);
@@ -408,12 +429,15 @@ int dfd_timer_stop(dfd_ctx* c, float* out_ms) {
 int dfd_metrics_get(dfd_ctx* c, dfd_metrics* out) {
     CTX_GUARD(c);
     if (!out) return set_error(DFD_ERR_INVALID_ARGUMENT, "out is NULL");
+    int rc = c->drain_events();
+    if (rc) return rc;
     *out = c->metrics;
     return DFD_OK;
 }
 
 int dfd_metrics_reset(dfd_ctx* c) {
     CTX_GUARD(c);
+    c->drain_events();
     memset(&c->metrics, 0, sizeof c->metrics);
     return DFD_OK;
 }

@@ -29,7 +29,11 @@ struct dfd_ctx {
     int sm_count = 148;
     size_t l2_bytes = 0;
     cudaStream_t stream = nullptr;  // compute stream: K1/K1b/K2 launch here
-    cudaEvent_t ev[4] = {};
+    // profiling: ring of event quads recorded without syncing; drained lazily
+    std::vector<cudaEvent_t> ev_ring;  // 4 events per call
+    size_t ev_pending = 0;             // calls recorded, not yet accumulated
+    static constexpr size_t EV_RING_CALLS = 64;
+    int drain_events();                // sync + accumulate into metrics
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     bool profiling = false;
     dfd::Scratch scratch;  // tile histograms / cursors
