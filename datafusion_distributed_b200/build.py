@@ -31,7 +31,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_source():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+    extra = os.environ.get("DFD_NVCC_DEFS", "").split()  # e.g. "-DDFD_TILE_K=16" for tuning sweeps
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [
         "-I", os.path.join(ROOT, "include"), "-I", CSRC,
     ] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT, "-ldl"]
     subprocess.check_call(cmd)

@@ -37,8 +37,18 @@ int cuda_error(cudaError_t e, const char* what) {
 }
 
 // Tile geometry of K1/K2 (rows per CTA = THREADS * K).
-constexpr int TILE_THREADS = 256;
-constexpr int TILE_K = 8;
+#ifndef DFD_TILE_THREADS
+#define DFD_TILE_THREADS 256
+#endif
+#ifndef DFD_TILE_K
+#define DFD_TILE_K 8
+#endif
+#ifndef DFD_TILE_MIN_CTAS
+#define DFD_TILE_MIN_CTAS 4
+#endif
+constexpr int TILE_THREADS = DFD_TILE_THREADS;
+constexpr int TILE_K = DFD_TILE_K;
+constexpr int TILE_MIN_CTAS = DFD_TILE_MIN_CTAS;
 constexpr int TILE_ROWS = TILE_THREADS * TILE_K;
 
 int Scratch::ensure(size_t need, int device) {
@@ -120,6 +130,34 @@ static int build_keyset(const dfd_partitioner* p, const dfd_column* cols, int n_
         if (_e != cudaSuccess) return cuda_error(_e, what);            \
     }
 
+template <bool FAST, typename V>
+static int launch_scatter_t(const ScatterParams& sp, unsigned grid, size_t smem, cudaStream_t stream) {
+    auto kern = k_scatter<TILE_THREADS, TILE_K, TILE_MIN_CTAS, FAST, V>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(k_scatter)");
+    }
+    kern<<<grid, TILE_THREADS, smem, stream>>>(sp);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DFD_OK : cuda_error(e, "k_scatter");
+}
+
+template <bool FAST>
+static int launch_scatter_w(const ScatterParams& sp, int width, unsigned grid, size_t smem, cudaStream_t stream) {
+    switch (width) {
+        case 8: return launch_scatter_t<FAST, uint64_t>(sp, grid, smem, stream);
+        case 4: return launch_scatter_t<FAST, uint32_t>(sp, grid, smem, stream);
+        case 2: return launch_scatter_t<FAST, uint16_t>(sp, grid, smem, stream);
+        case 1: return launch_scatter_t<FAST, uint8_t>(sp, grid, smem, stream);
+        case 16: return launch_scatter_t<FAST, uint4>(sp, grid, smem, stream);
+        default: return launch_scatter_t<FAST, BitColumn>(sp, grid, smem, stream);
+    }
+}
+
+static int launch_scatter(const ScatterParams& sp, int width, bool fast, unsigned grid, size_t smem, cudaStream_t stream) {
+    return fast ? launch_scatter_w<true>(sp, width, grid, smem, stream) : launch_scatter_w<false>(sp, width, grid, smem, stream);
+}
+
 int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,
                                  const dfd_column* out_cols, cudaStream_t stream) {
     Ctx* c = p->ctx;
@@ -136,7 +174,7 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
 
     // payload passes: every column's values, plus a bit pass per validity bitmap
     std::vector<PayloadCol> passes;
-    int stage_width = 1;
+
     uint64_t bytes = 0;
     for (int i = 0; i < n_cols; ++i) {
         const dfd_column& ic = in_cols[i];
@@ -154,7 +192,7 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
             pc.out = oc.values;
             pc.in_offset = ic.offset;
             pc.width = ic.width;
-            if (ic.width > stage_width) stage_width = ic.width;
+
             bytes += (uint64_t)n_rows * ic.width;
         } else if (ic.kind == DFD_COL_BOOL) {
             if ((uintptr_t)oc.values & 3) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: output bitmap must be 4-byte aligned", i);
@@ -208,7 +246,10 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
     }
     {
         size_t smem = (size_t)N * 4;
-        k_tile_hist<TILE_THREADS, TILE_K><<<(unsigned)n_tiles, TILE_THREADS, smem, stream>>>(ks, p->st, p->mod, n_rows, n_tiles, N, d_hist);
+        if (ks.fast_i64)
+            k_tile_hist<TILE_THREADS, TILE_K, true><<<(unsigned)n_tiles, TILE_THREADS, smem, stream>>>(ks, p->st, p->mod, n_rows, n_tiles, N, d_hist);
+        else
+            k_tile_hist<TILE_THREADS, TILE_K, false><<<(unsigned)n_tiles, TILE_THREADS, smem, stream>>>(ks, p->st, p->mod, n_rows, n_tiles, N, d_hist);
         LAUNCH_CHECK("k_tile_hist");
     }
     if (prof) cudaEventRecord(ev[1], stream);
@@ -219,13 +260,6 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
     if (prof) cudaEventRecord(ev[2], stream);
     c->metrics.kernel_launches += 3;
 
-    size_t smem = scatter_smem_bytes<TILE_THREADS, TILE_K>(N, stage_width);
-    if (smem > 200 * 1024) return set_error(DFD_ERR_UNSUPPORTED, "num_partitions %u needs %zu B of shared memory per CTA", N, smem);
-    if (smem > 48 * 1024 && smem > p->smem_configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_scatter<TILE_THREADS, TILE_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(k_scatter)");
-        p->smem_configured = smem;
-    }
     ScatterParams sp{};
     sp.keys = ks;
     sp.st = p->st;
@@ -236,15 +270,27 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
     sp.tile_base = d_base;
     sp.part_starts = p->d_part_starts;
     sp.N = N;
-    sp.stage_width = stage_width;
     int launches = 0;
-    for (size_t first = 0; first < passes.size(); first += MAX_COLS_PER_LAUNCH) {
-        size_t n = passes.size() - first < (size_t)MAX_COLS_PER_LAUNCH ? passes.size() - first : (size_t)MAX_COLS_PER_LAUNCH;
-        for (size_t i = 0; i < n; ++i) sp.cols[i] = passes[first + i];
-        sp.n_cols = (int32_t)n;
-        k_scatter<TILE_THREADS, TILE_K><<<(unsigned)n_tiles, TILE_THREADS, smem, stream>>>(sp);
-        LAUNCH_CHECK("k_scatter");
-        ++launches;
+    // one launch per element width (0 = bit columns), columns of that width batched
+    static const int kWidths[6] = {8, 4, 16, 2, 1, 0};
+    for (int wi = 0; wi < 6; ++wi) {
+        const int width = kWidths[wi];
+        std::vector<PayloadCol> group;
+        for (const PayloadCol& pc : passes)
+            if (pc.width == width) group.push_back(pc);
+        if (group.empty()) continue;
+        sp.stage_width = width ? width : 1;
+        size_t smem = scatter_smem_bytes<TILE_THREADS, TILE_K>(N, sp.stage_width);
+        if (smem > 200 * 1024)
+            return set_error(DFD_ERR_UNSUPPORTED, "num_partitions %u needs %zu B of shared memory per CTA", N, smem);
+        for (size_t first = 0; first < group.size(); first += MAX_COLS_PER_LAUNCH) {
+            size_t n = group.size() - first < (size_t)MAX_COLS_PER_LAUNCH ? group.size() - first : (size_t)MAX_COLS_PER_LAUNCH;
+            for (size_t i = 0; i < n; ++i) sp.cols[i] = group[first + i];
+            sp.n_cols = (int32_t)n;
+            rc = launch_scatter(sp, width, ks.fast_i64 != 0, (unsigned)n_tiles, smem, stream);
+            if (rc) return rc;
+            ++launches;
+        }
     }
     if (prof) {
         cudaEventRecord(ev[3], stream);

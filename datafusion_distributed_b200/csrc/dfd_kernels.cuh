@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "dfd_hash.cuh"
 
@@ -78,24 +79,37 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     return res;
 }
 
+// Lanes of the warp holding the same destination id `d` (d < 2^nbits), from
+// nbits ballots — cheaper than MATCH.ANY for the small ids used here.
+__device__ __forceinline__ unsigned peers_of(uint32_t d, int nbits) {
+    unsigned peers = 0xffffffffu;
+    for (int b = 0; b < nbits; ++b) {
+        unsigned bit = (d >> b) & 1u;
+        unsigned bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+}
+
 // ---------------------------------------------------------------------------
 // K0 (debug / parity): destination id per row
 // ---------------------------------------------------------------------------
 __global__ void k_partition_ids(KeySet keys, HashState st, ModN mod, int64_t n_rows, uint32_t* __restrict__ dest) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x)
-        dest[r] = mod_n(row_hash(keys, r, st), mod);
+        dest[r] = mod_n(row_hash<false>(keys, r, st), mod);
 }
 
 // ---------------------------------------------------------------------------
 // K1: per-tile destination histogram.  Tile t covers rows [t*T, (t+1)*T).
 // hist is destination-major ([N][n_tiles]) so the tile scan reads contiguously.
 // ---------------------------------------------------------------------------
-template <int THREADS, int K>
+template <int THREADS, int K, bool FAST_I64>
 __global__ void __launch_bounds__(THREADS) k_tile_hist(KeySet keys, HashState st, ModN mod, int64_t n_rows,
                                                         int64_t n_tiles, uint32_t N, uint32_t* __restrict__ hist) {
     constexpr int T = THREADS * K;
     extern __shared__ uint32_t s_hist[];
     const int lane = threadIdx.x & 31;
+    const int nbits = 32 - __clz(N);  // ids 0..N (N = "no row")
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (uint32_t p = threadIdx.x; p < N; p += THREADS) s_hist[p] = 0;
         __syncthreads();
@@ -104,11 +118,11 @@ __global__ void __launch_bounds__(THREADS) k_tile_hist(KeySet keys, HashState st
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             int64_t r = row0 + j * THREADS + threadIdx.x;
-            d[j] = r < n_rows ? mod_n(row_hash(keys, r, st), mod) : N;
+            d[j] = r < n_rows ? mod_n(row_hash<FAST_I64>(keys, r, st), mod) : N;
         }
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            unsigned peers = __match_any_sync(0xffffffffu, d[j]);
+            unsigned peers = peers_of(d[j], nbits);
             if (d[j] < N && (peers & ((1u << lane) - 1)) == 0) atomicAdd(&s_hist[d[j]], __popc(peers));
         }
         __syncthreads();
@@ -190,60 +204,70 @@ struct StageIO {
     static __device__ __forceinline__ V ld(const void* base, int64_t i) { return ((const V*)base)[i]; }
 };
 
-template <int THREADS, int K, typename V>
-__device__ __forceinline__ void scatter_fixed_column(const PayloadCol& c, void* stage_raw, int64_t row0, int64_t n_rows,
-                                                     int tile_rows, const uint32_t (&pos)[K], const int64_t (&dst)[K],
-                                                     int w, int lane) {
+template <int THREADS, int K, typename V, int CHUNK = K>
+__device__ __forceinline__ void scatter_fixed_column(const PayloadCol& c, void* stage_raw, int64_t row0, int tile_rows,
+                                                     const uint32_t (&ps)[K], const int64_t* delta, int t0) {
+    static_assert(K % CHUNK == 0, "CHUNK must divide K");
     V* stage = (V*)stage_raw;
-    const V* in = (const V*)c.in + c.in_offset;
-    V* out = (V*)c.out;
-    V v[K];
+    const V* in = (const V*)c.in + (c.in_offset + row0);  // tile-relative indexing below is 32-bit
+    V* out = (V*)c.out + row0;                             // delta[] is relative to row0 as well
+    V v[CHUNK];
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-        int64_t r = row0 + (int64_t)w * (K * 32) + j * 32 + lane;
-        if (r < n_rows) v[j] = in[r];
+    for (int j = 0; j < CHUNK; ++j) {
+        int t = t0 + j * 32;
+        if (t < tile_rows) v[j] = in[t];
     }
     __syncthreads();  // staging buffer free (previous column fully written out)
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-        int64_t r = row0 + (int64_t)w * (K * 32) + j * 32 + lane;
-        if (r < n_rows) stage[pos[j]] = v[j];
+    for (int ch = 0; ch < K / CHUNK; ++ch) {
+        if (ch > 0) {
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) {
+                int t = t0 + (ch * CHUNK + j) * 32;
+                if (t < tile_rows) v[j] = in[t];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) {
+            int t = t0 + (ch * CHUNK + j) * 32;
+            if (t < tile_rows) stage[ps[ch * CHUNK + j] & 0xffffu] = v[j];
+        }
     }
     __syncthreads();  // staging buffer holds the tile in destination order
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         int i = k * THREADS + (int)threadIdx.x;
-        if (i < tile_rows) out[dst[k]] = stage[i];
+        if (i < tile_rows) out[(int64_t)i + delta[ps[k] >> 16]] = stage[i];
     }
 }
 
 // bit column (boolean values or a validity bitmap): staged as one byte per row,
 // written back with warp-aggregated atomicOr on 32-bit output words.
 template <int THREADS, int K>
-__device__ __forceinline__ void scatter_bit_column(const PayloadCol& c, void* stage_raw, int64_t row0, int64_t n_rows,
-                                                   int tile_rows, const uint32_t (&pos)[K], const int64_t (&dst)[K],
-                                                   int w, int lane) {
+__device__ __forceinline__ void scatter_bit_column(const PayloadCol& c, void* stage_raw, int64_t row0, int tile_rows,
+                                                   const uint32_t (&ps)[K], const int64_t* delta, int t0) {
     uint8_t* stage = (uint8_t*)stage_raw;
     const uint8_t* in = (const uint8_t*)c.in;
     unsigned* out = (unsigned*)c.out;
+    const int lane = threadIdx.x & 31;
     uint8_t v[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-        int64_t r = row0 + (int64_t)w * (K * 32) + j * 32 + lane;
-        v[j] = (r < n_rows) ? (uint8_t)bit_is_set(in, r + c.in_offset) : 0;
+        int t = t0 + j * 32;
+        v[j] = (t < tile_rows) ? (uint8_t)bit_is_set(in, row0 + t + c.in_offset) : 0;
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-        int64_t r = row0 + (int64_t)w * (K * 32) + j * 32 + lane;
-        if (r < n_rows) stage[pos[j]] = v[j];
+        int t = t0 + j * 32;
+        if (t < tile_rows) stage[ps[j] & 0xffffu] = v[j];
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         int i = k * THREADS + (int)threadIdx.x;
         bool active = i < tile_rows;
-        int64_t d = active ? dst[k] : -1;
+        int64_t d = active ? row0 + (int64_t)i + delta[ps[k] >> 16] : -1;
         unsigned bit = (active && stage[i]) ? (1u << (d & 31)) : 0u;
         int64_t word = active ? (d >> 5) : -1;
         unsigned peers = __match_any_sync(0xffffffffu, word);
@@ -252,57 +276,66 @@ __device__ __forceinline__ void scatter_bit_column(const PayloadCol& c, void* st
     }
 }
 
-template <int THREADS, int K>
-__global__ void __launch_bounds__(THREADS) k_scatter(const __grid_constant__ ScatterParams P) {
+struct BitColumn {};  // tag: bit-packed column (boolean values / validity bitmap)
+
+// One instantiation per element type V: a launch moves all columns of one
+// width (the host groups them), so the hot instantiation (8-byte values)
+// carries no code or registers for the other widths.
+template <int THREADS, int K, int MIN_CTAS, bool FAST_I64, typename V>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_constant__ ScatterParams P) {
     constexpr int T = THREADS * K;
     constexpr int W = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t N = P.N;
-    // layout: stage | warp_cnt[W][N] | tile_start[N+1] | delta[N] | scan scratch
+    // layout: stage | delta[N] | warp_cnt[W][N] | tile_start[N+1] | scan scratch
     unsigned char* stage = smem;
-    size_t off = ((size_t)T * P.stage_width + 15) & ~(size_t)15;
-    int64_t* delta = (int64_t*)(smem + off);
-    off += (size_t)N * 8;
-    uint32_t* warp_cnt = (uint32_t*)(smem + off);
-    off += (size_t)W * N * 4;
-    uint32_t* tile_start = (uint32_t*)(smem + off);
-    off += (size_t)(N + 1) * 4;
-    uint32_t* s_scan = (uint32_t*)(smem + off);  // [W + 1]
+    const uint32_t off_delta = ((uint32_t)T * (uint32_t)P.stage_width + 15u) & ~15u;
+    const uint32_t off_wc = off_delta + N * 8u;
+    const uint32_t off_ts = off_wc + (uint32_t)W * N * 4u;
+    const uint32_t off_scan = off_ts + (N + 1u) * 4u;
+#define DELTA ((int64_t*)(smem + off_delta))
+#define WARP_CNT ((uint32_t*)(smem + off_wc))
+#define TILE_START ((uint32_t*)(smem + off_ts))
+#define S_SCAN ((uint32_t*)(smem + off_scan))
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t tile = blockIdx.x;
     const int64_t row0 = tile * T;
     const int tile_rows = (int)((P.n_rows - row0) < T ? (P.n_rows - row0) : T);
+    const int t0 = w * (K * 32) + lane;  // this thread's first tile-relative row; rows t0 + 32*j
 
-    // ---- tile_start / delta from the K1 histogram (independent of phase 1)
+    // ---- tile_start / delta from the K1 histogram (independent of phase 1).
+    // delta[p] maps a staging slot i to its output row RELATIVE to row0:
+    //   out_row - row0 = i + delta[p]
     {
         uint32_t carry = 0;
         for (uint32_t p0 = 0; p0 < N; p0 += THREADS) {
             uint32_t p = p0 + threadIdx.x;
             uint32_t c = p < N ? P.hist[(int64_t)p * P.n_tiles + tile] : 0;
             uint32_t tot;
-            uint32_t ex = block_exclusive_scan<THREADS>(c, s_scan, tot);
+            uint32_t ex = block_exclusive_scan<THREADS>(c, S_SCAN, tot);
             if (p < N) {
                 uint32_t ts = carry + ex;
-                tile_start[p] = ts;
-                delta[p] = P.part_starts[p] + P.tile_base[(int64_t)p * P.n_tiles + tile] - (int64_t)ts;
+                TILE_START[p] = ts;
+                DELTA[p] = P.part_starts[p] + P.tile_base[(int64_t)p * P.n_tiles + tile] - (int64_t)ts - row0;
             }
             carry += tot;
         }
-        if (threadIdx.x == 0) tile_start[N] = carry;
+        if (threadIdx.x == 0) TILE_START[N] = carry;
     }
 
     // ---- phase 1: destination + stable rank of every row of the tile
-    uint32_t* wc = warp_cnt + (size_t)w * N;
+    uint32_t* wc = WARP_CNT + (uint32_t)w * N;
     for (uint32_t p = lane; p < N; p += 32) wc[p] = 0;
     __syncwarp();
+    const int nbits = 32 - __clz(N);
     uint32_t pos[K];  // first: (dest << 16 | rank) ; later: staging position
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-        int64_t r = row0 + (int64_t)w * (K * 32) + j * 32 + lane;
-        bool valid = r < P.n_rows;
-        uint32_t d = valid ? mod_n(row_hash(P.keys, r, P.st), P.mod) : N;
-        unsigned peers = __match_any_sync(0xffffffffu, d);
+        int t = t0 + j * 32;
+        bool valid = t < tile_rows;
+        uint32_t d = valid ? mod_n(row_hash<FAST_I64>(P.keys, row0 + t, P.st), P.mod) : N;
+        unsigned peers = peers_of(d, nbits);
         uint32_t rank = __popc(peers & ((1u << lane) - 1));
         uint32_t base = valid ? wc[d] : 0;
         __syncwarp();
@@ -313,11 +346,11 @@ __global__ void __launch_bounds__(THREADS) k_scatter(const __grid_constant__ Sca
     __syncthreads();
     // warp_cnt[w][p] -> staging base of (warp w, destination p)
     for (uint32_t p = threadIdx.x; p < N; p += THREADS) {
-        uint32_t run = tile_start[p];
+        uint32_t run = TILE_START[p];
 #pragma unroll
         for (int ww = 0; ww < W; ++ww) {
-            uint32_t c = warp_cnt[(size_t)ww * N + p];
-            warp_cnt[(size_t)ww * N + p] = run;
+            uint32_t c = WARP_CNT[(uint32_t)ww * N + p];
+            WARP_CNT[(uint32_t)ww * N + p] = run;
             run += c;
         }
     }
@@ -327,32 +360,32 @@ __global__ void __launch_bounds__(THREADS) k_scatter(const __grid_constant__ Sca
         uint32_t d = pos[j] >> 16;
         pos[j] = d < N ? wc[d] + (pos[j] & 0xffffu) : 0;
     }
-    // ---- destination row of every staging slot this thread will write out
-    int64_t dst[K];
+    // ---- destination of every staging slot this thread will write out
+    // (packed into the high half of pos[]: pos[k] = staging position | slot destination << 16)
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        int i = k * THREADS + (int)threadIdx.x;
-        // last p with tile_start[p] <= i
-        uint32_t lo = 0, hi = N;  // invariant: tile_start[lo] <= i < tile_start[hi] (when i < tile_rows)
+        uint32_t i = k * THREADS + threadIdx.x;
+        uint32_t lo = 0, hi = N;  // last p with tile_start[p] <= i
         while (hi - lo > 1) {
             uint32_t mid = (lo + hi) >> 1;
-            if (tile_start[mid] <= (uint32_t)i) lo = mid; else hi = mid;
+            if (TILE_START[mid] <= i) lo = mid; else hi = mid;
         }
-        dst[k] = (int64_t)i + delta[lo];
+        pos[k] |= lo << 16;
     }
 
     // ---- phase 2: every column through the staging buffer
+#pragma unroll 1
     for (int c = 0; c < P.n_cols; ++c) {
         const PayloadCol& col = P.cols[c];
-        switch (col.width) {
-            case 8: scatter_fixed_column<THREADS, K, uint64_t>(col, stage, row0, P.n_rows, tile_rows, pos, dst, w, lane); break;
-            case 4: scatter_fixed_column<THREADS, K, uint32_t>(col, stage, row0, P.n_rows, tile_rows, pos, dst, w, lane); break;
-            case 2: scatter_fixed_column<THREADS, K, uint16_t>(col, stage, row0, P.n_rows, tile_rows, pos, dst, w, lane); break;
-            case 1: scatter_fixed_column<THREADS, K, uint8_t>(col, stage, row0, P.n_rows, tile_rows, pos, dst, w, lane); break;
-            case 16: scatter_fixed_column<THREADS, K, uint4>(col, stage, row0, P.n_rows, tile_rows, pos, dst, w, lane); break;
-            default: scatter_bit_column<THREADS, K>(col, stage, row0, P.n_rows, tile_rows, pos, dst, w, lane); break;
-        }
+        if constexpr (std::is_same<V, BitColumn>::value)
+            scatter_bit_column<THREADS, K>(col, stage, row0, tile_rows, pos, DELTA, t0);
+        else
+            scatter_fixed_column<THREADS, K, V, (sizeof(V) == 16 && K >= 4 ? K / 4 : K)>(col, stage, row0, tile_rows, pos, DELTA, t0);
     }
+#undef DELTA
+#undef WARP_CNT
+#undef TILE_START
+#undef S_SCAN
 }
 
 template <int THREADS, int K>
