@@ -219,16 +219,23 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
     }
 
     const int64_t n_tiles = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
-    if (n_tiles > 0x7fffffffLL) return set_error(DFD_ERR_UNSUPPORTED, "n_rows too large for one call");
-    // scratch: hist u32 [N][n_tiles] | tile_base i64 [N][n_tiles] | totals i64 [N]
+    if (n_rows > 0xffffffffLL) return set_error(DFD_ERR_UNSUPPORTED, "n_rows must be < 2^32 per call");
+    // scratch: hist u32 [N][n_tiles] | tile_base u32 [N][n_tiles] | totals i64 [N] | done u32
     size_t hist_bytes = (((size_t)N * n_tiles * 4) + 255) & ~(size_t)255;
-    size_t base_bytes = (((size_t)N * n_tiles * 8) + 255) & ~(size_t)255;
-    size_t need = hist_bytes + base_bytes + (size_t)N * 8;
+    size_t tot_bytes = (((size_t)N * 8) + 255) & ~(size_t)255;
+    size_t need = 2 * hist_bytes + tot_bytes + 256;
+    bool fresh = need > c->scratch.bytes;
     rc = c->scratch.ensure(need, c->device);
     if (rc) return rc;
     uint32_t* d_hist = (uint32_t*)c->scratch.ptr;
-    int64_t* d_base = (int64_t*)((char*)c->scratch.ptr + hist_bytes);
-    int64_t* d_totals = (int64_t*)((char*)c->scratch.ptr + hist_bytes + base_bytes);
+    uint32_t* d_base = (uint32_t*)((char*)c->scratch.ptr + hist_bytes);
+    int64_t* d_totals = (int64_t*)((char*)c->scratch.ptr + 2 * hist_bytes);
+    unsigned* d_done = (unsigned*)((char*)c->scratch.ptr + 2 * hist_bytes + tot_bytes);
+    if (fresh || c->scratch_done != d_done) {
+        cudaError_t e = cudaMemsetAsync(d_done, 0, 256, stream);
+        if (e != cudaSuccess) return cuda_error(e, "cudaMemsetAsync(done)");
+        c->scratch_done = d_done;
+    }
 
     const bool prof = c->profiling;
     cudaEvent_t* ev = nullptr;
@@ -246,19 +253,22 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
     }
     {
         size_t smem = (size_t)N * 4;
-        if (ks.fast_i64)
-            k_tile_hist<TILE_THREADS, TILE_K, true><<<(unsigned)n_tiles, TILE_THREADS, smem, stream>>>(ks, p->st, p->mod, n_rows, n_tiles, N, d_hist);
-        else
-            k_tile_hist<TILE_THREADS, TILE_K, false><<<(unsigned)n_tiles, TILE_THREADS, smem, stream>>>(ks, p->st, p->mod, n_rows, n_tiles, N, d_hist);
+        const int nf = N <= 4 ? 1 : N <= 8 ? 2 : N <= 16 ? 4 : 0;
+        const unsigned grid = (unsigned)n_tiles;
+#define HIST(FAST, NF) k_tile_hist<TILE_THREADS, TILE_K, FAST, NF><<<grid, TILE_THREADS, smem, stream>>>(ks, p->st, p->mod, n_rows, n_tiles, N, d_hist)
+        if (ks.fast_i64) {
+            switch (nf) { case 1: HIST(true, 1); break; case 2: HIST(true, 2); break; case 4: HIST(true, 4); break; default: HIST(true, 0); }
+        } else {
+            switch (nf) { case 1: HIST(false, 1); break; case 2: HIST(false, 2); break; case 4: HIST(false, 4); break; default: HIST(false, 0); }
+        }
+#undef HIST
         LAUNCH_CHECK("k_tile_hist");
     }
     if (prof) cudaEventRecord(ev[1], stream);
-    k_scan_tiles<1024><<<N, 1024, 0, stream>>>(d_hist, d_base, d_totals, n_tiles);
+    k_scan_tiles<1024><<<N, 1024, 0, stream>>>(d_hist, d_base, d_totals, p->d_part_starts, d_done, n_tiles, N);
     LAUNCH_CHECK("k_scan_tiles");
-    k_part_starts<<<1, 1024, 0, stream>>>(d_totals, p->d_part_starts, N);
-    LAUNCH_CHECK("k_part_starts");
     if (prof) cudaEventRecord(ev[2], stream);
-    c->metrics.kernel_launches += 3;
+    c->metrics.kernel_launches += 2;
 
     ScatterParams sp{};
     sp.keys = ks;

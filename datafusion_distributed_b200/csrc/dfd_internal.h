@@ -37,6 +37,7 @@ struct dfd_ctx {
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     bool profiling = false;
     dfd::Scratch scratch;  // tile histograms / cursors
+    void* scratch_done = nullptr;  // zero-initialised "blocks done" counter inside scratch
     dfd::Scratch flush;    // L2 flush buffer
     dfd_metrics metrics = {};
     std::mutex mu;

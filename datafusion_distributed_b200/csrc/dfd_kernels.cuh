@@ -5,7 +5,7 @@
 //   create_hashes -> `hash % N` -> per-destination index vectors -> take per column
 // with three device passes over Arrow columnar buffers:
 //   K1 k_tile_hist     hash(keys) -> destination -> per-tile radix histogram
-//   K1b k_scan_tiles / k_part_starts   exclusive scans -> per-(tile,destination) write cursors
+//   K1b k_scan_tiles                   exclusive scans -> per-(tile,destination) write cursors
 //   K2 k_scatter       fused hash -> stable rank (warp match/ballot) -> shared-memory
 //                      staging of each column in destination order -> coalesced run writes
 // Integer / byte work bounded by HBM bandwidth; no tensor cores.
@@ -37,7 +37,7 @@ struct ScatterParams {
     int64_t n_rows;
     int64_t n_tiles;
     const uint32_t* hist;        // [N][n_tiles] per-tile destination counts (K1)
-    const int64_t* tile_base;    // [N][n_tiles] exclusive scan of hist along tiles
+    const uint32_t* tile_base;   // [N][n_tiles] exclusive scan of hist along tiles (rows < 2^32 per call)
     const int64_t* part_starts;  // [N+1] exclusive scan of destination totals
     PayloadCol cols[MAX_COLS_PER_LAUNCH];
     int32_t n_cols;
@@ -80,15 +80,31 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 }
 
 // Lanes of the warp holding the same destination id `d` (d < 2^nbits), from
-// nbits ballots — cheaper than MATCH.ANY for the small ids used here.
-__device__ __forceinline__ unsigned peers_of(uint32_t d, int nbits) {
+// nbits ballots (fully unrolled per bit count; nbits is warp-uniform).
+template <int NB>
+__device__ __forceinline__ unsigned peers_of_t(uint32_t d) {
     unsigned peers = 0xffffffffu;
-    for (int b = 0; b < nbits; ++b) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
         unsigned bit = (d >> b) & 1u;
         unsigned bal = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? bal : ~bal;
+        peers &= bal ^ (bit - 1u);  // bit ? bal : ~bal
     }
     return peers;
+}
+
+__device__ __forceinline__ unsigned peers_of(uint32_t d, int nbits) {
+    switch (nbits) {
+        case 1: return peers_of_t<1>(d);
+        case 2: return peers_of_t<2>(d);
+        case 3: return peers_of_t<3>(d);
+        case 4: return peers_of_t<4>(d);
+        case 5: return peers_of_t<5>(d);
+        case 6: return peers_of_t<6>(d);
+        case 7: return peers_of_t<7>(d);
+        case 8: return peers_of_t<8>(d);
+        default: return __match_any_sync(0xffffffffu, d);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -100,13 +116,20 @@ __global__ void k_partition_ids(KeySet keys, HashState st, ModN mod, int64_t n_r
 }
 
 // ---------------------------------------------------------------------------
-// K1: per-tile destination histogram.  Tile t covers rows [t*T, (t+1)*T).
-// hist is destination-major ([N][n_tiles]) so the tile scan reads contiguously.
+// K1: per-tile destination histogram.  Tile t covers rows [t*T, (t+1)*T) —
+// the same tiling K2 uses.  hist is destination-major ([N][n_tiles]) so the
+// tile scan reads contiguously.
+//   NF > 0 : N <= 4*NF.  Each thread counts its K rows into NF packed u64
+//            accumulators (four 16-bit fields each), one xor-shuffle tree per
+//            warp adds them up and lanes 0..N-1 publish the fields: ~6
+//            integer instructions per row instead of a ballot cascade.
+//   NF == 0: any N.  Warp-aggregated shared-memory atomics (ballot peers).
 // ---------------------------------------------------------------------------
-template <int THREADS, int K, bool FAST_I64>
+template <int THREADS, int K, bool FAST_I64, int NF>
 __global__ void __launch_bounds__(THREADS) k_tile_hist(KeySet keys, HashState st, ModN mod, int64_t n_rows,
                                                         int64_t n_tiles, uint32_t N, uint32_t* __restrict__ hist) {
     constexpr int T = THREADS * K;
+    static_assert(K * 32 < 65536, "16-bit packed counters");
     extern __shared__ uint32_t s_hist[];
     const int lane = threadIdx.x & 31;
     const int nbits = 32 - __clz(N);  // ids 0..N (N = "no row")
@@ -114,16 +137,41 @@ __global__ void __launch_bounds__(THREADS) k_tile_hist(KeySet keys, HashState st
         for (uint32_t p = threadIdx.x; p < N; p += THREADS) s_hist[p] = 0;
         __syncthreads();
         const int64_t row0 = tile * T;
+        const int tile_rows = (int)((n_rows - row0) < T ? (n_rows - row0) : T);
         uint32_t d[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            int64_t r = row0 + j * THREADS + threadIdx.x;
-            d[j] = r < n_rows ? mod_n(row_hash<FAST_I64>(keys, r, st), mod) : N;
+            int t = j * THREADS + (int)threadIdx.x;
+            d[j] = t < tile_rows ? mod_n(row_hash<FAST_I64>(keys, row0 + t, st), mod) : N;
         }
+        if constexpr (NF > 0) {
+            unsigned long long acc[NF];
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            unsigned peers = peers_of(d[j], nbits);
-            if (d[j] < N && (peers & ((1u << lane) - 1)) == 0) atomicAdd(&s_hist[d[j]], __popc(peers));
+            for (int q = 0; q < NF; ++q) acc[q] = 0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                unsigned long long inc = d[j] < N ? 1ULL << ((d[j] & 3u) * 16u) : 0ULL;
+#pragma unroll
+                for (int q = 0; q < NF; ++q) acc[q] += ((d[j] >> 2) == (uint32_t)q) ? inc : 0ULL;
+            }
+#pragma unroll
+            for (int q = 0; q < NF; ++q) {
+#pragma unroll
+                for (int sh = 16; sh >= 1; sh >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], sh);
+            }
+            if ((uint32_t)lane < N) {
+                unsigned long long a = acc[0];
+#pragma unroll
+                for (int q = 1; q < NF; ++q) a = ((lane >> 2) == q) ? acc[q] : a;
+                uint32_t c = (uint32_t)(a >> ((lane & 3) * 16)) & 0xffffu;
+                if (c) atomicAdd(&s_hist[lane], c);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                unsigned peers = peers_of(d[j], nbits);
+                if (d[j] < N && (peers & ((1u << lane) - 1)) == 0) atomicAdd(&s_hist[d[j]], __popc(peers));
+            }
         }
         __syncthreads();
         for (uint32_t p = threadIdx.x; p < N; p += THREADS) hist[(int64_t)p * n_tiles + tile] = s_hist[p];
@@ -132,59 +180,84 @@ __global__ void __launch_bounds__(THREADS) k_tile_hist(KeySet keys, HashState st
 }
 
 // ---------------------------------------------------------------------------
-// K1b: one block per destination: exclusive scan of its tile counts.
+// K1b: one block per destination: exclusive scan of its tile counts
+// (tile_base, relative to the destination's start), then the LAST block to
+// finish turns the N totals into part_starts[N+1].  `done` is a zeroed
+// counter the kernel resets for the next call.
 // ---------------------------------------------------------------------------
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_scan_tiles(const uint32_t* __restrict__ hist, int64_t* __restrict__ tile_base,
-                                                         int64_t* __restrict__ totals, int64_t n_tiles) {
-    __shared__ unsigned long long s_part[THREADS];
+__device__ __forceinline__ unsigned long long block_exclusive_scan_u64(unsigned long long v, unsigned long long* s_warp,
+                                                                       unsigned long long& total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        unsigned long long x = lane < THREADS / 32 ? s_warp[lane] : 0;
+        unsigned long long xi = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, xi, d);
+            if (lane >= d) xi += t;
+        }
+        if (lane < THREADS / 32) s_warp[lane] = xi - x;
+        if (lane == 31) s_warp[32] = xi;
+    }
+    __syncthreads();
+    unsigned long long res = s_warp[w] + inc - v;
+    total = s_warp[32];
+    __syncthreads();
+    return res;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_scan_tiles(const uint32_t* __restrict__ hist, uint32_t* __restrict__ tile_base,
+                                                         int64_t* __restrict__ totals, int64_t* __restrict__ part_starts,
+                                                         unsigned* __restrict__ done, int64_t n_tiles, uint32_t N) {
+    __shared__ unsigned long long s_warp[33];
+    __shared__ bool s_last;
     const uint32_t p = blockIdx.x;
     const uint32_t* h = hist + (int64_t)p * n_tiles;
-    int64_t* b = tile_base + (int64_t)p * n_tiles;
+    uint32_t* b = tile_base + (int64_t)p * n_tiles;
+    // each thread owns a contiguous run of tiles (lines are re-used from L1 across its loads)
     const int64_t per = (n_tiles + THREADS - 1) / THREADS;
     const int64_t lo = (int64_t)threadIdx.x * per;
     const int64_t hi = lo + per < n_tiles ? lo + per : n_tiles;
     unsigned long long sum = 0;
     for (int64_t i = lo; i < hi; ++i) sum += h[i];
-    s_part[threadIdx.x] = sum;
-    __syncthreads();
-    // simple Hillis-Steele over THREADS partial sums
-    for (int d = 1; d < THREADS; d <<= 1) {
-        unsigned long long t = threadIdx.x >= d ? s_part[threadIdx.x - d] : 0;
-        __syncthreads();
-        s_part[threadIdx.x] += t;
-        __syncthreads();
-    }
-    unsigned long long run = s_part[threadIdx.x] - sum;
+    unsigned long long total;
+    unsigned long long run = block_exclusive_scan_u64<THREADS>(sum, s_warp, total);
     for (int64_t i = lo; i < hi; ++i) {
-        b[i] = (int64_t)run;
+        b[i] = (uint32_t)run;
         run += h[i];
     }
-    if (threadIdx.x == THREADS - 1) totals[p] = (int64_t)s_part[THREADS - 1];
-}
-
-// part_starts[p] = sum(totals[0..p)), part_starts[N] = n_rows.  Single block.
-__global__ void k_part_starts(const int64_t* __restrict__ totals, int64_t* __restrict__ part_starts, uint32_t N) {
-    __shared__ unsigned long long s_part[1024];
-    const uint32_t per = (N + 1023) / 1024;
-    const uint32_t lo = threadIdx.x * per;
-    const uint32_t hi = lo + per < N ? lo + per : N;
-    unsigned long long sum = 0;
-    for (uint32_t i = lo; i < hi; ++i) sum += (unsigned long long)totals[i];
-    s_part[threadIdx.x] = sum;
+    if (threadIdx.x == 0) {
+        totals[p] = (int64_t)total;
+        __threadfence();
+        s_last = atomicAdd(done, 1u) == N - 1;
+    }
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        unsigned long long t = threadIdx.x >= d ? s_part[threadIdx.x - d] : 0;
-        __syncthreads();
-        s_part[threadIdx.x] += t;
-        __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last block: part_starts[q] = sum(totals[0..q)), part_starts[N] = n_rows
+    unsigned long long carry = 0;
+    for (uint32_t q0 = 0; q0 < N; q0 += THREADS) {
+        uint32_t q = q0 + threadIdx.x;
+        unsigned long long v = q < N ? (unsigned long long)((volatile int64_t*)totals)[q] : 0;
+        unsigned long long tot;
+        unsigned long long ex = block_exclusive_scan_u64<THREADS>(v, s_warp, tot);
+        if (q < N) part_starts[q] = (int64_t)(carry + ex);
+        carry += tot;
     }
-    unsigned long long run = s_part[threadIdx.x] - sum;
-    for (uint32_t i = lo; i < hi; ++i) {
-        part_starts[i] = (int64_t)run;
-        run += (unsigned long long)totals[i];
+    if (threadIdx.x == 0) {
+        part_starts[N] = (int64_t)carry;
+        *done = 0;
     }
-    if (threadIdx.x == 1023) part_starts[N] = (int64_t)s_part[1023];
 }
 
 // ---------------------------------------------------------------------------
@@ -317,7 +390,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
             if (p < N) {
                 uint32_t ts = carry + ex;
                 TILE_START[p] = ts;
-                DELTA[p] = P.part_starts[p] + P.tile_base[(int64_t)p * P.n_tiles + tile] - (int64_t)ts - row0;
+                DELTA[p] = P.part_starts[p] + (int64_t)P.tile_base[(int64_t)p * P.n_tiles + tile] - (int64_t)ts - row0;
             }
             carry += tot;
         }

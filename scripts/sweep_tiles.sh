@@ -2,7 +2,7 @@
 # Tuning sweep of the K1/K2 tile geometry on the GPU box (rebuilds the library per config).
 set -u
 mkdir -p gpurun_out
-for cfg in "256 8 4" "256 8 5" "256 16 2" "256 16 3" "512 8 2" "512 4 2" "256 4 8" "128 16 5" "1024 4 1" "1024 2 2"; do
+for cfg in "256 8 4" "256 8 5" "256 4 8" "512 4 4" "256 6 6" "128 8 8" "256 5 6" "512 8 2" "384 4 5" "128 16 6"; do
   set -- $cfg
   export DFD_NVCC_DEFS="-DDFD_TILE_THREADS=$1 -DDFD_TILE_K=$2 -DDFD_TILE_MIN_CTAS=$3"
   python datafusion_distributed_b200/build.py --force >/dev/null 2>&1 || { echo "build failed $cfg"; continue; }
