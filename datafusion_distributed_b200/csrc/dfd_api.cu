@@ -41,10 +41,10 @@ int cuda_error(cudaError_t e, const char* what) {
 #define DFD_TILE_THREADS 256
 #endif
 #ifndef DFD_TILE_K
-#define DFD_TILE_K 8
+#define DFD_TILE_K 6
 #endif
 #ifndef DFD_TILE_MIN_CTAS
-#define DFD_TILE_MIN_CTAS 4
+#define DFD_TILE_MIN_CTAS 6
 #endif
 constexpr int TILE_THREADS = DFD_TILE_THREADS;
 constexpr int TILE_K = DFD_TILE_K;
