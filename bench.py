@@ -139,6 +139,53 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_e2e(ctx, dfd, n, args):
+    """Same metric through the reference-facing operator (RepartitionExec over the C-ABI)
+    with HOST buffers: pinned Arrow record batches in, per-destination Arrow batches out,
+    H2D and D2H copies inside the timed region (wall clock around push..finish..drain)."""
+    import pyarrow as pa
+
+    names = [f"c{j}" for j in range(N_COLS)]
+    pt = dfd.PinnedTable(ctx, n, [np.int64] * N_COLS)
+    rng = np.random.Generator(np.random.PCG64(42))
+    step = 1 << 22
+    for lo in range(0, n, step):
+        hi = min(lo + step, n)
+        pt.columns[0][lo:hi] = rng.integers(-(2**63), 2**63 - 1, hi - lo, dtype=np.int64, endpoint=True)
+        rid = np.arange(lo, hi, dtype=np.int64)
+        for j in range(1, N_COLS):
+            pt.columns[j][lo:hi] = rid * 8 + j
+    batches = pt.record_batches(names, args.e2e_batch_rows)
+    schema = batches[0].schema
+    times = []
+    st = None
+    for it in range(2 + max(1, args.steps // 2)):
+        ex = dfd.RepartitionExec(ctx, schema, dfd.Partitioning.Hash([0], NUM_PARTITIONS), chunk_rows=args.e2e_chunk_rows,
+                                 pipeline_depth=3, pinned_pool_chunks=6)
+        readers = [ex.execute(p) for p in range(NUM_PARTITIONS)]
+        rows_out = 0
+        checksum = 0
+        t0 = time.perf_counter()
+        for b in batches:
+            ex.push_batch(b)
+        ex.finish()
+        for r in readers:  # consumer side: read every destination's stream (device->host result)
+            for rb in r:
+                rows_out += rb.num_rows
+        dt = time.perf_counter() - t0
+        assert rows_out == n, (rows_out, n)
+        st = ex.stats()
+        del readers
+        ex.close()
+        if it >= 2:
+            times.append(dt)
+    best = sum(times) / len(times)
+    pt.close()
+    return {"value": n / best, "unit": "rows/s", "h2d_bytes_per_step": int(st["bytes_h2d"]), "d2h_bytes_per_step": int(st["bytes_d2h"]),
+            "ms_per_step": best * 1e3, "steps": len(times), "batch_rows": args.e2e_batch_rows, "chunk_rows": args.e2e_chunk_rows,
+            "api": "RepartitionExec.push_batch/finish/execute(partition) over dfd_repartition_exec_* (Arrow C Data / C Stream)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -147,6 +194,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=N_ROWS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-batch-rows", type=int, default=1 << 20)
+    ap.add_argument("--e2e-chunk-rows", type=int, default=1 << 22)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -208,6 +258,9 @@ def main():
         "clocks": clocks.summary(),
         "e2e": None,
     }
+    if not args.no_e2e:
+        line["e2e"] = run_e2e(ctx, dfd, n, args)
+        line["gpu_launches"] = int(ctx.metrics()["kernel_launches"])
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         sample = 1 << 23

@@ -9,9 +9,10 @@ built `_lib/libdfd_b200.so` and a CUDA device.
 from . import _native
 from ._native import DfdError, LIB_PATH
 from .device import DeviceBuffer, DeviceColumn, WorkerContext
+from .execution_plans import PinnedTable, RepartitionExec
 from .partitioner import HashPartitioner, Partitioning, scale_partitioning
 
 __all__ = [
     "DfdError", "LIB_PATH", "DeviceBuffer", "DeviceColumn", "WorkerContext",
-    "HashPartitioner", "Partitioning", "scale_partitioning",
+    "HashPartitioner", "Partitioning", "scale_partitioning", "RepartitionExec", "PinnedTable",
 ]

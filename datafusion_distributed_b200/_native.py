@@ -58,6 +58,32 @@ class DfdMetrics(C.Structure):
         return {name: getattr(self, name) for name, _ in self._fields_}
 
 
+class DfdExecOptions(C.Structure):
+    _fields_ = [("chunk_rows", C.c_int64), ("pipeline_depth", C.c_int32), ("pinned_pool_chunks", C.c_int32)]
+
+
+class DfdExecStats(C.Structure):
+    _fields_ = [("rows_in", C.c_uint64), ("rows_out", C.c_uint64), ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64)]
+
+
+class ArrowSchemaStruct(C.Structure):
+    """struct ArrowSchema (Arrow C Data Interface), opaque storage for pyarrow's _export_to_c."""
+    _fields_ = [("format", C.c_char_p), ("name", C.c_char_p), ("metadata", C.c_char_p), ("flags", C.c_int64),
+                ("n_children", C.c_int64), ("children", C.c_void_p), ("dictionary", C.c_void_p),
+                ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+class ArrowArrayStruct(C.Structure):
+    _fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64),
+                ("n_children", C.c_int64), ("buffers", C.c_void_p), ("children", C.c_void_p),
+                ("dictionary", C.c_void_p), ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+class ArrowArrayStreamStruct(C.Structure):
+    _fields_ = [("get_schema", C.c_void_p), ("get_next", C.c_void_p), ("get_last_error", C.c_void_p),
+                ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
 # name -> (restype, argtypes).  Every symbol include/dfd_b200.h declares.
 _VP = C.c_void_p
 SIGNATURES = {
@@ -86,6 +112,14 @@ SIGNATURES = {
     "dfd_partition_ids_device": (C.c_int, [_VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, _VP]),
     "dfd_partition_device": (C.c_int, [_VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.POINTER(DfdColumn), C.POINTER(C.c_int64)]),
     "dfd_partitioner_part_starts_device": (_VP, [_VP]),
+    "dfd_repartition_exec_create": (C.c_int, [_VP, C.POINTER(ArrowSchemaStruct), C.POINTER(C.c_int32), C.c_int, C.c_uint32,
+                                              C.POINTER(DfdExecOptions), C.POINTER(_VP)]),
+    "dfd_repartition_exec_destroy": (None, [_VP]),
+    "dfd_repartition_exec_push": (C.c_int, [_VP, C.POINTER(ArrowArrayStruct)]),
+    "dfd_repartition_exec_finish": (C.c_int, [_VP]),
+    "dfd_repartition_exec_run": (C.c_int, [_VP, C.POINTER(ArrowArrayStreamStruct)]),
+    "dfd_repartition_exec_execute": (C.c_int, [_VP, C.c_uint32, C.POINTER(ArrowArrayStreamStruct)]),
+    "dfd_repartition_exec_stats": (C.c_int, [_VP, C.POINTER(DfdExecStats)]),
     "dfd_metrics_get": (C.c_int, [_VP, C.POINTER(DfdMetrics)]),
     "dfd_metrics_reset": (C.c_int, [_VP]),
 }

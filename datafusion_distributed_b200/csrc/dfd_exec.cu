@@ -1,0 +1,746 @@
+// dfd_exec.cu — host-side operator: RepartitionExec(Hash) with HOST Arrow batches.
+//
+// Mirrors the producer half of the reference's shuffle as an operator:
+//   RepartitionExec::try_new(input, Partitioning::Hash(exprs, P * task_count))
+//     (src/execution_plans/network_shuffle.rs:126-134)
+//   plan.execute(partition, ctx) -> SendableRecordBatchStream
+//     (src/worker/impl_execute_task.rs:77-86)
+// over the Arrow C Data / C Stream interfaces.  Input batches are copied to the
+// GPU in chunks (H2D stream), partitioned by K1/K1b/K2 (compute stream), copied
+// back into pooled pinned memory (D2H stream) and handed out as zero-copy
+// per-destination slices — the three stages of consecutive chunks overlap, so
+// end-to-end time approaches max(H2D, D2H) over PCIe.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "dfd_b200.h"
+#include "dfd_internal.h"
+
+using namespace dfd;
+
+namespace {
+
+struct FieldInfo {
+    std::string name, format;
+    int64_t flags = 0;
+    int32_t kind = DFD_COL_FIXED;
+    int32_t width = 0;
+};
+
+// Arrow format string -> physical layout (Arrow C data interface, "Data type description")
+bool parse_format(const char* f, int32_t* kind, int32_t* width) {
+    *kind = DFD_COL_FIXED;
+    switch (f[0]) {
+        case 'b': *kind = DFD_COL_BOOL; *width = 0; return f[1] == 0;
+        case 'c': case 'C': *width = 1; return f[1] == 0;
+        case 's': case 'S': *width = 2; return f[1] == 0;
+        case 'e': *width = 2; return f[1] == 0;
+        case 'i': case 'I': case 'f': *width = 4; return f[1] == 0;
+        case 'l': case 'L': case 'g': *width = 8; return f[1] == 0;
+        case 'u': *kind = DFD_COL_UTF8; *width = 0; return f[1] == 0;
+        case 'U': *kind = DFD_COL_LARGE_UTF8; *width = 0; return f[1] == 0;
+        case 'z': *kind = DFD_COL_BINARY; *width = 0; return f[1] == 0;
+        case 'd': {  // d:precision,scale[,bitwidth]
+            int p = 0, s = 0, bw = 128;
+            int n = sscanf(f, "d:%d,%d,%d", &p, &s, &bw);
+            if (n < 2) return false;
+            if (bw != 128 && bw != 64 && bw != 32) return false;
+            *width = bw / 8;
+            return true;
+        }
+        case 't':
+            if (f[1] == 'd') { *width = f[2] == 'D' ? 4 : 8; return f[2] == 'D' || f[2] == 'm'; }  // date32/date64
+            if (f[1] == 't') { *width = (f[2] == 's' || f[2] == 'm') ? 4 : 8; return true; }    // time32/time64
+            if (f[1] == 's' || f[1] == 'D') { *width = 8; return true; }                           // timestamp / duration
+            if (f[1] == 'i') { *width = f[2] == 'M' ? 4 : (f[2] == 'D' ? 8 : 16); return true; }   // intervals
+            return false;
+    }
+    return false;
+}
+
+struct PinnedPool;
+
+// One D2H landing buffer (pinned): all columns of one chunk, destination-sorted.
+struct OutChunk {
+    std::vector<void*> values;    // per column
+    std::vector<void*> validity;  // per column (may be null)
+    std::atomic<int> refs{0};
+    std::shared_ptr<PinnedPool> pool;
+};
+
+struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
+    int device = 0;
+    int64_t chunk_rows = 0;
+    std::vector<FieldInfo> fields;
+    std::mutex mu;
+    std::vector<OutChunk*> free_list;
+    std::vector<OutChunk*> all;
+
+    static size_t value_bytes(const FieldInfo& f, int64_t rows) {
+        return f.kind == DFD_COL_BOOL ? (size_t)((rows + 63) / 64 * 8 + 8) : (size_t)rows * (size_t)f.width;
+    }
+    static size_t bitmap_bytes(int64_t rows) { return (size_t)((rows + 63) / 64 * 8 + 8); }
+
+    OutChunk* acquire() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (!free_list.empty()) {
+                OutChunk* c = free_list.back();
+                free_list.pop_back();
+                return c;
+            }
+        }
+        OutChunk* c = new (std::nothrow) OutChunk();
+        if (!c) return nullptr;
+        cudaSetDevice(device);
+        for (const FieldInfo& f : fields) {
+            void* v = nullptr;
+            void* b = nullptr;
+            if (cudaHostAlloc(&v, value_bytes(f, chunk_rows), cudaHostAllocPortable) != cudaSuccess) return nullptr;
+            if ((f.flags & ARROW_FLAG_NULLABLE) && cudaHostAlloc(&b, bitmap_bytes(chunk_rows), cudaHostAllocPortable) != cudaSuccess)
+                return nullptr;
+            c->values.push_back(v);
+            c->validity.push_back(b);
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        all.push_back(c);
+        return c;
+    }
+    void give_back(OutChunk* c) {
+        std::lock_guard<std::mutex> lk(mu);
+        free_list.push_back(c);
+    }
+    ~PinnedPool() {
+        for (OutChunk* c : all) {
+            for (void* p : c->values) cudaFreeHost(p);
+            for (void* p : c->validity)
+                if (p) cudaFreeHost(p);
+            delete c;
+        }
+    }
+};
+
+void chunk_unref(OutChunk* c) {
+    if (c->refs.fetch_sub(1) == 1) {
+        std::shared_ptr<PinnedPool> pool = std::move(c->pool);  // keep the pool alive past give_back
+        pool->give_back(c);
+    }
+}
+
+// ---- Arrow C Data export of one destination's slice of a chunk -------------
+struct BatchPriv {
+    OutChunk* chunk;
+    std::vector<ArrowArray> children;
+    std::vector<ArrowArray*> child_ptrs;
+    std::vector<const void*> child_bufs;  // 2 per child
+    const void* struct_bufs[1] = {nullptr};
+};
+
+void child_release(ArrowArray* a) { a->release = nullptr; }
+
+void batch_release(ArrowArray* a) {
+    BatchPriv* p = (BatchPriv*)a->private_data;
+    for (ArrowArray& c : p->children)
+        if (c.release) c.release(&c);
+    chunk_unref(p->chunk);
+    delete p;
+    a->release = nullptr;
+}
+
+struct SchemaPriv {
+    std::vector<FieldInfo> fields;
+    std::vector<ArrowSchema> children;
+    std::vector<ArrowSchema*> child_ptrs;
+};
+
+void schema_child_release(ArrowSchema* s) { s->release = nullptr; }
+void schema_release(ArrowSchema* s) {
+    SchemaPriv* p = (SchemaPriv*)s->private_data;
+    for (ArrowSchema& c : p->children)
+        if (c.release) c.release(&c);
+    delete p;
+    s->release = nullptr;
+}
+
+int export_schema(const std::vector<FieldInfo>& fields, ArrowSchema* out) {
+    SchemaPriv* p = new (std::nothrow) SchemaPriv();
+    if (!p) return ENOMEM;
+    p->fields = fields;
+    p->children.resize(fields.size());
+    p->child_ptrs.resize(fields.size());
+    for (size_t i = 0; i < fields.size(); ++i) {
+        ArrowSchema& c = p->children[i];
+        memset(&c, 0, sizeof c);
+        c.format = p->fields[i].format.c_str();
+        c.name = p->fields[i].name.c_str();
+        c.flags = p->fields[i].flags;
+        c.release = schema_child_release;
+        p->child_ptrs[i] = &c;
+    }
+    memset(out, 0, sizeof *out);
+    out->format = "+s";
+    out->name = "";
+    out->n_children = (int64_t)fields.size();
+    out->children = p->child_ptrs.data();
+    out->release = schema_release;
+    out->private_data = p;
+    return 0;
+}
+
+struct PartQueue {
+    std::deque<ArrowArray> batches;
+};
+
+struct HeldInput {  // an input batch whose buffers an in-flight H2D still reads
+    ArrowArray array;
+};
+
+struct Slot {
+    std::vector<void*> d_in, d_in_valid, d_out, d_out_valid;  // per column device buffers
+    int64_t* h_part_starts = nullptr;                        // pinned [N+1]
+    cudaEvent_t e_h2d = nullptr, e_k = nullptr, e_d2h = nullptr;
+    bool k_recorded = false, d2h_recorded = false;
+    // state of the chunk currently in this slot
+    int64_t rows = 0;
+    bool plain = true;
+    std::vector<int64_t> in_offset;  // per column logical offset (bit columns / validity)
+    std::vector<bool> has_valid;
+    OutChunk* out = nullptr;
+    bool in_flight = false;
+    std::vector<HeldInput> held;
+};
+
+}  // namespace
+
+struct dfd_repartition_exec {
+    dfd_ctx* ctx = nullptr;
+    dfd_partitioner* part = nullptr;
+    std::vector<FieldInfo> fields;
+    uint32_t N = 0;
+    int64_t chunk_rows = 0;
+    int depth = 3;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<Slot> slots;
+    int cur = 0;              // slot being filled
+    bool cur_open = false;
+    std::shared_ptr<PinnedPool> pool;
+    // output side
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<PartQueue> queues;
+    bool finished = false;
+    int error_code = 0;
+    std::string error;
+    uint64_t rows_in = 0, rows_out = 0, bytes_h2d = 0, bytes_d2h = 0;
+};
+
+namespace {
+
+int fail(dfd_repartition_exec* x, int code, const std::string& msg) {
+    {
+        std::lock_guard<std::mutex> lk(x->mu);
+        if (!x->error_code) {
+            x->error_code = code;
+            x->error = msg;
+        }
+        x->finished = true;
+    }
+    x->cv.notify_all();
+    return set_error(code, "%s", msg.c_str());
+}
+
+#define XCUDA(x, call, what)                                                           \
+    {                                                                                  \
+        cudaError_t _e = (call);                                                       \
+        if (_e != cudaSuccess) return fail((x), DFD_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(_e)); \
+    }
+
+// hand the finished chunk in `s` to the per-destination queues
+int emit_slot(dfd_repartition_exec* x, Slot& s) {
+    if (!s.in_flight) return DFD_OK;
+    XCUDA(x, cudaEventSynchronize(s.e_d2h), "D2H");
+    for (HeldInput& h : s.held)
+        if (h.array.release) h.array.release(&h.array);
+    s.held.clear();
+    OutChunk* oc = s.out;
+    s.out = nullptr;
+    s.in_flight = false;
+    const size_t C = x->fields.size();
+    int made = 0;
+    oc->refs.store(1);  // guard while slicing
+    oc->pool = x->pool;
+    for (uint32_t p = 0; p < x->N; ++p) {
+        int64_t start = s.h_part_starts[p], cnt = s.h_part_starts[p + 1] - start;
+        if (cnt <= 0) continue;  // like the reference, only non-empty partitions are emitted
+        BatchPriv* bp = new (std::nothrow) BatchPriv();
+        if (!bp) return fail(x, DFD_ERR_OOM, "out of host memory");
+        bp->chunk = oc;
+        bp->children.resize(C);
+        bp->child_ptrs.resize(C);
+        bp->child_bufs.resize(2 * C);
+        for (size_t c = 0; c < C; ++c) {
+            ArrowArray& a = bp->children[c];
+            memset(&a, 0, sizeof a);
+            bool hv = s.has_valid[c];
+            bp->child_bufs[2 * c] = hv ? oc->validity[c] : nullptr;
+            bp->child_bufs[2 * c + 1] = oc->values[c];
+            a.length = cnt;
+            a.offset = start;  // zero-copy slice of the chunk-wide destination-sorted buffer
+            a.null_count = hv ? -1 : 0;
+            a.n_buffers = 2;
+            a.buffers = &bp->child_bufs[2 * c];
+            a.release = child_release;
+            bp->child_ptrs[c] = &a;
+        }
+        ArrowArray top;
+        memset(&top, 0, sizeof top);
+        top.length = cnt;
+        top.null_count = 0;
+        top.n_buffers = 1;
+        top.buffers = bp->struct_bufs;
+        top.n_children = (int64_t)C;
+        top.children = bp->child_ptrs.data();
+        top.release = batch_release;
+        top.private_data = bp;
+        oc->refs.fetch_add(1);
+        ++made;
+        {
+            std::lock_guard<std::mutex> lk(x->mu);
+            x->queues[p].batches.push_back(top);
+            x->rows_out += (uint64_t)cnt;
+        }
+    }
+    chunk_unref(oc);  // drop the guard (returns the chunk to the pool if nothing was emitted)
+    (void)made;
+    x->cv.notify_all();
+    return DFD_OK;
+}
+
+// run the kernels + D2H for the chunk accumulated in the current slot
+int flush_current(dfd_repartition_exec* x) {
+    if (!x->cur_open) return DFD_OK;
+    Slot& s = x->slots[x->cur];
+    dfd_ctx* c = x->ctx;
+    const size_t C = x->fields.size();
+    x->cur_open = false;
+    if (s.rows == 0) return DFD_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    XCUDA(x, cudaSetDevice(c->device), "cudaSetDevice");
+    XCUDA(x, cudaEventRecord(s.e_h2d, x->s_h2d), "record h2d");
+    XCUDA(x, cudaStreamWaitEvent(c->stream, s.e_h2d, 0), "wait h2d");
+    if (s.d2h_recorded) XCUDA(x, cudaStreamWaitEvent(c->stream, s.e_d2h, 0), "wait d2h");
+    std::vector<dfd_column> in(C), out(C);
+    for (size_t i = 0; i < C; ++i) {
+        const FieldInfo& f = x->fields[i];
+        in[i] = dfd_column{f.kind, f.width, s.d_in[i], nullptr, s.has_valid[i] ? (uint8_t*)s.d_in_valid[i] : nullptr, s.in_offset[i]};
+        out[i] = dfd_column{f.kind, f.width, s.d_out[i], nullptr, s.has_valid[i] ? (uint8_t*)s.d_out_valid[i] : nullptr, 0};
+        if (f.kind == DFD_COL_BOOL)
+            XCUDA(x, cudaMemsetAsync(s.d_out[i], 0, PinnedPool::bitmap_bytes(s.rows), c->stream), "memset");
+        if (s.has_valid[i]) XCUDA(x, cudaMemsetAsync(s.d_out_valid[i], 0, PinnedPool::bitmap_bytes(s.rows), c->stream), "memset");
+    }
+    int rc = partition_device_locked(x->part, in.data(), (int)C, s.rows, out.data(), c->stream);
+    if (rc) return fail(x, rc, dfd_last_error());
+    XCUDA(x, cudaMemcpyAsync(s.h_part_starts, x->part->d_part_starts, sizeof(int64_t) * (x->N + 1), cudaMemcpyDeviceToHost, c->stream),
+          "D2H part_starts");
+    XCUDA(x, cudaEventRecord(s.e_k, c->stream), "record k");
+    s.k_recorded = true;
+    // D2H of the destination-sorted chunk into a pooled pinned buffer
+    s.out = x->pool->acquire();
+    if (!s.out) return fail(x, DFD_ERR_OOM, "pinned host allocation failed");
+    XCUDA(x, cudaStreamWaitEvent(x->s_d2h, s.e_k, 0), "wait k");
+    for (size_t i = 0; i < C; ++i) {
+        const FieldInfo& f = x->fields[i];
+        size_t nb = f.kind == DFD_COL_BOOL ? (size_t)((s.rows + 7) / 8) : (size_t)s.rows * f.width;
+        XCUDA(x, cudaMemcpyAsync(s.out->values[i], s.d_out[i], nb, cudaMemcpyDeviceToHost, x->s_d2h), "D2H");
+        x->bytes_d2h += nb;
+        if (s.has_valid[i]) {
+            XCUDA(x, cudaMemcpyAsync(s.out->validity[i], s.d_out_valid[i], (size_t)((s.rows + 7) / 8), cudaMemcpyDeviceToHost, x->s_d2h), "D2H");
+            x->bytes_d2h += (size_t)((s.rows + 7) / 8);
+        }
+    }
+    XCUDA(x, cudaEventRecord(s.e_d2h, x->s_d2h), "record d2h");
+    s.d2h_recorded = true;
+    s.in_flight = true;
+    return DFD_OK;
+}
+
+// make the next slot current: emit whatever it still holds, fence its buffers
+int open_next_slot(dfd_repartition_exec* x) {
+    x->cur = (x->cur + 1) % x->depth;
+    Slot& s = x->slots[x->cur];
+    int rc = emit_slot(x, s);
+    if (rc) return rc;
+    // H2D into this slot must not overtake the kernels that last read it
+    if (s.k_recorded) {
+        std::lock_guard<std::mutex> lk(x->ctx->mu);
+        XCUDA(x, cudaSetDevice(x->ctx->device), "cudaSetDevice");
+        XCUDA(x, cudaStreamWaitEvent(x->s_h2d, s.e_k, 0), "wait k (h2d)");
+    }
+    s.rows = 0;
+    s.plain = true;
+    std::fill(s.in_offset.begin(), s.in_offset.end(), 0);
+    std::fill(s.has_valid.begin(), s.has_valid.end(), false);
+    x->cur_open = true;
+    return DFD_OK;
+}
+
+bool batch_is_plain(const dfd_repartition_exec* x, const ArrowArray* b) {
+    for (size_t i = 0; i < x->fields.size(); ++i) {
+        const ArrowArray* c = b->children[i];
+        if (x->fields[i].kind != DFD_COL_FIXED) return false;
+        if (c->null_count != 0 && c->n_buffers > 0 && c->buffers[0] != nullptr) return false;
+    }
+    return true;
+}
+
+// copy rows [start, start+n) of `b` into the current slot (appending for plain batches).
+// A non-plain batch (bit-packed values or validity bitmaps) is alone in its chunk:
+// its bitmaps keep their sub-byte bit offset (lo & 7) and the fixed-width values of the
+// same column are placed at that logical offset too, so one `offset` addresses both.
+int stage_rows(dfd_repartition_exec* x, const ArrowArray* b, int64_t start, int64_t n, bool plain) {
+    Slot& s = x->slots[x->cur];
+    const size_t C = x->fields.size();
+    std::lock_guard<std::mutex> lk(x->ctx->mu);
+    XCUDA(x, cudaSetDevice(x->ctx->device), "cudaSetDevice");
+    for (size_t i = 0; i < C; ++i) {
+        const FieldInfo& f = x->fields[i];
+        const ArrowArray* c = b->children[i];
+        const int64_t lo = c->offset + start;
+        const bool hv = !plain && c->null_count != 0 && c->n_buffers > 0 && c->buffers[0] != nullptr;
+        const int64_t bit_off = (hv || f.kind == DFD_COL_BOOL) ? (lo & 7) : 0;
+        const size_t bitmap_nb = (size_t)((bit_off + n + 7) >> 3);
+        if (f.kind == DFD_COL_FIXED) {
+            const char* src = (const char*)c->buffers[1] + (size_t)lo * f.width;
+            char* dst = (char*)s.d_in[i] + (size_t)(s.rows + bit_off) * f.width;
+            XCUDA(x, cudaMemcpyAsync(dst, src, (size_t)n * f.width, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
+            x->bytes_h2d += (size_t)n * f.width;
+        } else {  // bool values: copy the covering bytes
+            const char* src = (const char*)c->buffers[1] + (lo >> 3);
+            XCUDA(x, cudaMemcpyAsync(s.d_in[i], src, bitmap_nb, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
+            x->bytes_h2d += bitmap_nb;
+        }
+        if (hv) {
+            const char* src = (const char*)c->buffers[0] + (lo >> 3);
+            XCUDA(x, cudaMemcpyAsync(s.d_in_valid[i], src, bitmap_nb, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
+            x->bytes_h2d += bitmap_nb;
+        }
+        if (!plain) s.in_offset[i] = bit_off;
+        s.has_valid[i] = hv;
+    }
+    s.rows += n;
+    s.plain = plain;
+    return DFD_OK;
+}
+
+// emit every in-flight chunk (oldest first) whose D2H has already completed
+int emit_ready(dfd_repartition_exec* x) {
+    for (int i = 1; i <= x->depth; ++i) {
+        Slot& s = x->slots[(x->cur + i) % x->depth];
+        if (!s.in_flight) continue;
+        cudaError_t q = cudaEventQuery(s.e_d2h);
+        if (q == cudaErrorNotReady) break;  // keep emission in chunk order
+        if (q != cudaSuccess) return fail(x, DFD_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(q));
+        int rc = emit_slot(x, s);
+        if (rc) return rc;
+    }
+    return DFD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, const int32_t* key_cols, int n_keys,
+                                uint32_t num_partitions, const dfd_exec_options* opts, dfd_repartition_exec** out) {
+    if (!ctx || !schema || !out) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_repartition_exec_create: NULL argument");
+    *out = nullptr;
+    if (!schema->format || strcmp(schema->format, "+s") != 0)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "schema must be a struct (record batch) schema, got format '%s'",
+                         schema->format ? schema->format : "(null)");
+    std::unique_ptr<dfd_repartition_exec> x(new (std::nothrow) dfd_repartition_exec());
+    if (!x) return set_error(DFD_ERR_OOM, "out of host memory");
+    x->ctx = ctx;
+    x->N = num_partitions;
+    for (int64_t i = 0; i < schema->n_children; ++i) {
+        const ArrowSchema* c = schema->children[i];
+        FieldInfo f;
+        f.name = c->name ? c->name : "";
+        f.format = c->format ? c->format : "";
+        f.flags = c->flags;
+        if (c->dictionary) return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): dictionary arrays are not supported yet", (long long)i, f.name.c_str());
+        if (!parse_format(f.format.c_str(), &f.kind, &f.width))
+            return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): Arrow format '%s' is not supported", (long long)i, f.name.c_str(), f.format.c_str());
+        bool is_key = false;
+        for (int k = 0; k < n_keys; ++k) is_key |= key_cols && key_cols[k] == i;
+        if (f.kind != DFD_COL_FIXED && f.kind != DFD_COL_BOOL)
+            return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): variable-width columns are not supported by the host operator yet%s",
+                             (long long)i, f.name.c_str(), is_key ? " (use dfd_partition_ids_device for var-width keys)" : "");
+        x->fields.push_back(f);
+    }
+    for (int k = 0; k < n_keys; ++k)
+        if (!key_cols || key_cols[k] < 0 || key_cols[k] >= (int)x->fields.size())
+            return set_error(DFD_ERR_INVALID_ARGUMENT, "key column index out of range");
+    int rc = dfd_partitioner_create(ctx, num_partitions, key_cols, n_keys, nullptr, &x->part);
+    if (rc) return rc;  // (x has no CUDA resources yet; unique_ptr frees it)
+    x->chunk_rows = (opts && opts->chunk_rows > 0) ? opts->chunk_rows : (int64_t)(4 << 20);
+    x->chunk_rows = (x->chunk_rows + 63) / 64 * 64;
+    x->depth = (opts && opts->pipeline_depth > 0) ? opts->pipeline_depth : 3;
+    if (x->depth < 2) x->depth = 2;
+    int pool_chunks = (opts && opts->pinned_pool_chunks > 0) ? opts->pinned_pool_chunks : x->depth + 1;
+    x->queues.resize(num_partitions);
+
+    cudaError_t e;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        e = cudaSetDevice(ctx->device);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->s_h2d, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->s_d2h, cudaStreamNonBlocking);
+        const size_t C = x->fields.size();
+        x->slots.resize(x->depth);
+        for (Slot& s : x->slots) {
+            s.d_in.assign(C, nullptr); s.d_in_valid.assign(C, nullptr); s.d_out.assign(C, nullptr); s.d_out_valid.assign(C, nullptr);
+            s.in_offset.assign(C, 0);
+            s.has_valid.assign(C, false);
+            for (size_t i = 0; i < C && e == cudaSuccess; ++i) {
+                const FieldInfo& f = x->fields[i];
+                size_t vb = PinnedPool::value_bytes(f, x->chunk_rows) + 16 * (size_t)(f.width ? f.width : 1);
+                e = cudaMalloc(&s.d_in[i], vb);
+                if (e == cudaSuccess) e = cudaMalloc(&s.d_out[i], vb);
+                if (e == cudaSuccess && (f.flags & ARROW_FLAG_NULLABLE)) {
+                    e = cudaMalloc(&s.d_in_valid[i], PinnedPool::bitmap_bytes(x->chunk_rows) + 8);
+                    if (e == cudaSuccess) e = cudaMalloc(&s.d_out_valid[i], PinnedPool::bitmap_bytes(x->chunk_rows) + 8);
+                }
+            }
+            if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.h_part_starts, sizeof(int64_t) * (num_partitions + 1), cudaHostAllocPortable);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.e_h2d, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.e_k, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.e_d2h, cudaEventDisableTiming);
+        }
+    }
+    if (e != cudaSuccess) {
+        int code = cuda_error(e, "dfd_repartition_exec_create allocations");
+        dfd_repartition_exec_destroy(x.release());
+        return code;
+    }
+    x->pool = std::make_shared<PinnedPool>();
+    x->pool->device = ctx->device;
+    x->pool->chunk_rows = x->chunk_rows;
+    x->pool->fields = x->fields;
+    std::vector<OutChunk*> pre;
+    for (int i = 0; i < pool_chunks; ++i) {
+        OutChunk* c = x->pool->acquire();
+        if (!c) {
+            dfd_repartition_exec_destroy(x.release());
+            return set_error(DFD_ERR_OOM, "pinned pool allocation failed");
+        }
+        pre.push_back(c);
+    }
+    for (OutChunk* c : pre) x->pool->give_back(c);
+    x->cur = x->depth - 1;  // open_next_slot() starts at slot 0
+    *out = x.release();
+    return DFD_OK;
+}
+
+void dfd_repartition_exec_destroy(dfd_repartition_exec* x) {
+    if (!x) return;
+    {
+        std::lock_guard<std::mutex> lk(x->ctx->mu);
+        cudaSetDevice(x->ctx->device);
+        if (x->s_h2d) cudaStreamSynchronize(x->s_h2d);
+        if (x->s_d2h) cudaStreamSynchronize(x->s_d2h);
+        cudaStreamSynchronize(x->ctx->stream);
+        for (Slot& s : x->slots) {
+            for (HeldInput& h : s.held)
+                if (h.array.release) h.array.release(&h.array);
+            if (s.out) { s.out->refs.store(1); s.out->pool = x->pool; chunk_unref(s.out); }
+            for (void* p : s.d_in) cudaFree(p);
+            for (void* p : s.d_in_valid) cudaFree(p);
+            for (void* p : s.d_out) cudaFree(p);
+            for (void* p : s.d_out_valid) cudaFree(p);
+            if (s.h_part_starts) cudaFreeHost(s.h_part_starts);
+            if (s.e_h2d) cudaEventDestroy(s.e_h2d);
+            if (s.e_k) cudaEventDestroy(s.e_k);
+            if (s.e_d2h) cudaEventDestroy(s.e_d2h);
+        }
+        if (x->s_h2d) cudaStreamDestroy(x->s_h2d);
+        if (x->s_d2h) cudaStreamDestroy(x->s_d2h);
+    }
+    for (PartQueue& q : x->queues)
+        for (ArrowArray& a : q.batches)
+            if (a.release) a.release(&a);
+    if (x->part) dfd_partitioner_destroy(x->part);
+    delete x;
+}
+
+int dfd_repartition_exec_push(dfd_repartition_exec* x, struct ArrowArray* batch) {
+    if (!x || !batch) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_repartition_exec_push: NULL argument");
+    auto drop = [&]() { if (batch->release) batch->release(batch); };
+    if (x->finished) { drop(); return set_error(DFD_ERR_INVALID_ARGUMENT, "push after finish/error: %s", x->error.c_str()); }
+    if (batch->n_children != (int64_t)x->fields.size()) {
+        drop();
+        return fail(x, DFD_ERR_INVALID_ARGUMENT, "batch has " + std::to_string(batch->n_children) + " columns, schema has " + std::to_string(x->fields.size()));
+    }
+    const int64_t R = batch->length;
+    x->rows_in += (uint64_t)R;
+    if (R == 0) { drop(); return DFD_OK; }
+    for (int64_t i = 0; i < batch->n_children; ++i)
+        if (batch->children[i]->length < R || (batch->offset != 0)) {
+            drop();
+            return fail(x, DFD_ERR_INVALID_ARGUMENT, "record batch children shorter than the batch, or non-zero struct offset");
+        }
+    const bool plain = batch_is_plain(x, batch);
+    int rc = DFD_OK;
+    int64_t done = 0;
+    while (done < R) {
+        if (x->cur_open) {
+            Slot& s = x->slots[x->cur];
+            bool must_flush = s.rows > 0 && (!plain || !s.plain || s.rows == x->chunk_rows);
+            if (must_flush) {
+                if ((rc = flush_current(x))) { drop(); return rc; }
+            }
+        }
+        if (!x->cur_open && (rc = open_next_slot(x))) { drop(); return rc; }
+        Slot& s = x->slots[x->cur];
+        int64_t room = x->chunk_rows - s.rows;
+        int64_t n = R - done < room ? R - done : room;
+        if ((rc = stage_rows(x, batch, done, n, plain))) { drop(); return rc; }
+        done += n;
+        if (s.rows == x->chunk_rows || !plain) {
+            // keep the input alive until this chunk's H2D has completed (emit_slot releases it)
+            if (done == R) {
+                HeldInput h;
+                h.array = *batch;
+                batch->release = nullptr;  // ownership moved
+                s.held.push_back(h);
+            }
+            if ((rc = flush_current(x))) return rc;
+            if (done < R) {
+                // the same batch continues in the next slot: wait for this slot's H2D before moving on
+                // (the batch is released only after its last piece) — nothing to do, events order it
+            }
+        }
+    }
+    if (batch->release) {  // plain batch fully appended to a still-open chunk
+        HeldInput h;
+        h.array = *batch;
+        batch->release = nullptr;
+        x->slots[x->cur].held.push_back(h);
+    }
+    return emit_ready(x);
+}
+
+int dfd_repartition_exec_finish(dfd_repartition_exec* x) {
+    if (!x) return set_error(DFD_ERR_INVALID_ARGUMENT, "NULL exec");
+    if (x->finished) return x->error_code ? set_error(x->error_code, "%s", x->error.c_str()) : DFD_OK;
+    int rc = flush_current(x);
+    if (rc) return rc;
+    for (int i = 0; i < x->depth; ++i) {
+        int si = (x->cur + 1 + i) % x->depth;
+        if ((rc = emit_slot(x, x->slots[si]))) return rc;
+    }
+    {
+        std::lock_guard<std::mutex> lk(x->mu);
+        x->finished = true;
+    }
+    x->cv.notify_all();
+    return DFD_OK;
+}
+
+int dfd_repartition_exec_run(dfd_repartition_exec* x, struct ArrowArrayStream* input) {
+    if (!x || !input || !input->get_next) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_repartition_exec_run: NULL argument");
+    int rc = DFD_OK;
+    for (;;) {
+        ArrowArray a;
+        memset(&a, 0, sizeof a);
+        int e = input->get_next(input, &a);
+        if (e != 0) {
+            const char* m = input->get_last_error ? input->get_last_error(input) : nullptr;
+            rc = fail(x, DFD_ERR_INTERNAL, std::string("input stream error: ") + (m ? m : "unknown"));
+            break;
+        }
+        if (!a.release) break;  // end of stream
+        if ((rc = dfd_repartition_exec_push(x, &a))) break;
+    }
+    if (input->release) input->release(input);
+    if (rc) return rc;
+    return dfd_repartition_exec_finish(x);
+}
+
+/* ---- output streams (ArrowArrayStream per destination) ------------------- */
+
+namespace {
+struct OutStreamPriv {
+    dfd_repartition_exec* x;
+    uint32_t partition;
+    std::string last_error;
+};
+
+int os_get_schema(ArrowArrayStream* s, ArrowSchema* out) {
+    OutStreamPriv* p = (OutStreamPriv*)s->private_data;
+    return export_schema(p->x->fields, out);
+}
+
+int os_get_next(ArrowArrayStream* s, ArrowArray* out) {
+    OutStreamPriv* p = (OutStreamPriv*)s->private_data;
+    dfd_repartition_exec* x = p->x;
+    std::unique_lock<std::mutex> lk(x->mu);
+    PartQueue& q = x->queues[p->partition];
+    x->cv.wait(lk, [&] { return !q.batches.empty() || x->finished; });
+    if (!q.batches.empty()) {
+        *out = q.batches.front();
+        q.batches.pop_front();
+        return 0;
+    }
+    if (x->error_code) {  // errors fan out to every partition stream (worker_connection_pool.rs:393-397)
+        p->last_error = x->error;
+        return EIO;
+    }
+    memset(out, 0, sizeof *out);  // release == NULL: end of stream
+    return 0;
+}
+
+const char* os_last_error(ArrowArrayStream* s) {
+    OutStreamPriv* p = (OutStreamPriv*)s->private_data;
+    return p->last_error.empty() ? nullptr : p->last_error.c_str();
+}
+
+void os_release(ArrowArrayStream* s) {
+    delete (OutStreamPriv*)s->private_data;
+    s->release = nullptr;
+}
+}  // namespace
+
+int dfd_repartition_exec_execute(dfd_repartition_exec* x, uint32_t partition, struct ArrowArrayStream* out) {
+    if (!x || !out) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_repartition_exec_execute: NULL argument");
+    if (partition >= x->N) return set_error(DFD_ERR_INVALID_ARGUMENT, "partition %u out of range [0,%u)", partition, x->N);
+    OutStreamPriv* p = new (std::nothrow) OutStreamPriv{x, partition, {}};
+    if (!p) return set_error(DFD_ERR_OOM, "out of host memory");
+    out->get_schema = os_get_schema;
+    out->get_next = os_get_next;
+    out->get_last_error = os_last_error;
+    out->release = os_release;
+    out->private_data = p;
+    return DFD_OK;
+}
+
+int dfd_repartition_exec_stats(dfd_repartition_exec* x, dfd_exec_stats* out) {
+    if (!x || !out) return set_error(DFD_ERR_INVALID_ARGUMENT, "NULL argument");
+    std::lock_guard<std::mutex> lk(x->mu);
+    out->rows_in = x->rows_in;
+    out->rows_out = x->rows_out;
+    out->bytes_h2d = x->bytes_h2d;
+    out->bytes_d2h = x->bytes_d2h;
+    return DFD_OK;
+}
+
+}  // extern "C"

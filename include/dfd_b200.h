@@ -156,6 +156,49 @@ int dfd_partition_device(dfd_partitioner* p, const dfd_column* in_cols, int n_co
                          int64_t n_rows, const dfd_column* out_cols, int64_t* part_starts_host);
 const int64_t* dfd_partitioner_part_starts_device(const dfd_partitioner* p);
 
+/* ---- host operator: RepartitionExec(Hash) over Arrow C Data / C Stream ----
+ * Replaces, on one worker, `RepartitionExec::try_new(input,
+ * Partitioning::Hash(exprs, n))` (built by the reference at
+ * src/execution_plans/network_shuffle.rs:126-134) and
+ * `ExecutionPlan::execute(partition, ctx) -> SendableRecordBatchStream`
+ * (called at src/worker/impl_execute_task.rs:77-86).  Input and output are
+ * HOST record batches; host<->device copies happen inside.
+ *   schema    : struct ("+s") schema of the input batches (borrowed)
+ *   push      : feed one input RecordBatch (struct ArrowArray); ownership of
+ *               `batch` moves to the operator (released after its H2D copy).
+ *               Single producer thread; may block on the pipeline.
+ *   finish    : end of input; drains the pipeline.
+ *   run       : pull `input` (≙ child.execute()) to exhaustion, then finish.
+ *   execute   : stream of destination `partition`'s batches; get_next blocks
+ *               until a batch is ready or the input is finished.  Batches are
+ *               zero-copy slices of pooled pinned buffers; only non-empty
+ *               batches are emitted; an operator error is delivered to every
+ *               partition stream (EIO + get_last_error), like the reference
+ *               (src/worker/worker_connection_pool.rs:393-397).
+ * Rows inside (one input chunk, one destination) keep input order.
+ * Variable-width / dictionary columns: DFD_ERR_UNSUPPORTED. */
+typedef struct dfd_repartition_exec dfd_repartition_exec;
+
+typedef struct {
+    int64_t chunk_rows;         /* rows per device chunk; 0 = 4Mi                   */
+    int32_t pipeline_depth;     /* chunks in flight (H2D | kernels | D2H); 0 = 3    */
+    int32_t pinned_pool_chunks; /* pinned output chunks preallocated; 0 = depth + 1 */
+} dfd_exec_options;
+
+typedef struct {
+    uint64_t rows_in, rows_out, bytes_h2d, bytes_d2h;
+} dfd_exec_stats;
+
+int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, const int32_t* key_cols,
+                                int n_keys, uint32_t num_partitions, const dfd_exec_options* opts,
+                                dfd_repartition_exec** out);
+void dfd_repartition_exec_destroy(dfd_repartition_exec* x);
+int dfd_repartition_exec_push(dfd_repartition_exec* x, struct ArrowArray* batch);
+int dfd_repartition_exec_finish(dfd_repartition_exec* x);
+int dfd_repartition_exec_run(dfd_repartition_exec* x, struct ArrowArrayStream* input);
+int dfd_repartition_exec_execute(dfd_repartition_exec* x, uint32_t partition, struct ArrowArrayStream* out);
+int dfd_repartition_exec_stats(dfd_repartition_exec* x, dfd_exec_stats* out);
+
 int dfd_metrics_get(dfd_ctx* ctx, dfd_metrics* out);
 int dfd_metrics_reset(dfd_ctx* ctx);
 

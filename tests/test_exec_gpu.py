@@ -1,0 +1,136 @@
+"""GPU parity tests of the host operator (RepartitionExec over Arrow C Data /
+C Stream): HOST record batches in, per-destination HOST record batch streams
+out, compared bit-exactly (values AND order) with the CPU oracle."""
+import random
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+import datafusion_distributed_b200 as dfd
+from oracle import oracle as orc
+from tests.util import cfg2_columns, expected_partitions
+
+pytestmark = pytest.mark.gpu
+
+
+def collect(exec_, N):
+    return [exec_.execute(p).read_all() for p in range(N)]
+
+
+def batches_of(arrays, names, batch_rows):
+    t = pa.table(arrays, names=names)
+    return t.to_batches(max_chunksize=batch_rows)
+
+
+@pytest.mark.parametrize("batch_rows,chunk_rows", [(8192, 0), (1024, 10_000), (100_000, 65_536), (1_000_000, 0)])
+def test_cfg1_shape_matches_oracle_exactly(ctx, batch_rows, chunk_rows):
+    """cfg-1 shape (ShuffleBench defaults): 1M rows, (k: Int64, v: Int64), Hash([k], 8)."""
+    rng = np.random.Generator(np.random.PCG64(1))
+    n, N = 1_000_000, 8
+    k = rng.integers(0, 2**63 - 1, n, dtype=np.int64)
+    v = np.arange(n, dtype=np.int64)
+    ex = dfd.RepartitionExec(ctx, pa.schema([("k", pa.int64()), ("v", pa.int64())]), dfd.Partitioning.Hash([0], N),
+                             chunk_rows=chunk_rows)
+    for b in batches_of([k, v], ["k", "v"], batch_rows):
+        ex.push_batch(b)
+    ex.finish()
+    outs = collect(ex, N)
+    ref, counts, starts = orc.repartition_table([k, v], [0], N, 8192, 1)
+    st = ex.stats()
+    assert st["rows_in"] == n and st["rows_out"] == n
+    for p in range(N):
+        assert outs[p].num_rows == counts[p]
+        assert np.array_equal(outs[p].column("k").to_numpy(), ref[0][starts[p]:starts[p + 1]])
+        assert np.array_equal(outs[p].column("v").to_numpy(), ref[1][starts[p]:starts[p + 1]])
+    ex.close()
+
+
+def test_nullable_bool_mixed_widths_and_sliced_batches(ctx):
+    rnd = random.Random(4)
+    rng = np.random.Generator(np.random.PCG64(4))
+    n, N = 50_000, 12
+    key = pa.array([rnd.choice([None, rnd.getrandbits(40)]) for _ in range(n)], type=pa.int64())
+    i32 = pa.array([rnd.choice([None, rnd.getrandbits(31)]) for _ in range(n)], type=pa.int32())
+    u8 = pa.array(rng.integers(0, 255, n, dtype=np.uint8))
+    f64 = pa.array(rng.standard_normal(n))
+    bl = pa.array([rnd.choice([None, True, False]) for _ in range(n)])
+    ts = pa.array(rng.integers(0, 2**60, n, dtype=np.int64)).cast(pa.timestamp("ns"))
+    names = ["key", "i32", "u8", "f64", "bl", "ts"]
+    table = pa.table([key, i32, u8, f64, bl, ts], names=names)
+    ex = dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash([0, 1], N), chunk_rows=16_384)
+    # ragged, sliced batches: offsets that are not multiples of 8
+    cuts = [0, 13, 1000, 1003, 20_001, 20_001, 37_777, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        for rb in table.slice(a, b - a).to_batches():
+            ex.push_batch(rb)
+    ex.finish()
+    outs = collect(ex, N)
+    dest = orc.partition_ids([key, i32], n, N)
+    order, starts = expected_partitions(dest, N)
+    for p in range(N):
+        want = table.take(pa.array(order[starts[p]:starts[p + 1]]))
+        assert outs[p].num_rows == want.num_rows
+        assert outs[p].equals(want), p
+    ex.close()
+
+
+def test_run_from_reader_and_empty_inputs(ctx):
+    cols = cfg2_columns(30_000, 3)
+    names = ["a", "b", "c"]
+    table = pa.table(cols, names=names)
+    batches = table.to_batches(max_chunksize=7000)
+    batches.insert(2, table.slice(0, 0).to_batches()[0] if table.slice(0, 0).to_batches() else pa.RecordBatch.from_arrays(
+        [pa.array([], type=pa.int64())] * 3, names=names))
+    reader = pa.RecordBatchReader.from_batches(table.schema, batches)
+    ex = dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash([0], 3))
+    ex.run(reader)
+    outs = collect(ex, 3)
+    ref, counts, starts = orc.repartition_table(cols, [0], 3, 8192, 1)
+    for p in range(3):
+        assert np.array_equal(outs[p].column("b").to_numpy(), ref[1][starts[p]:starts[p + 1]])
+    ex.close()
+    # no input at all: every partition stream ends immediately, schema preserved (invariants ii, iv)
+    ex = dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash([0], 4))
+    ex.finish()
+    for p in range(4):
+        t = ex.execute(p).read_all()
+        assert t.num_rows == 0 and t.schema.names == names
+    ex.close()
+
+
+def test_single_partition_and_pinned_input(ctx):
+    n = 200_000
+    pt = dfd.PinnedTable(ctx, n, [np.int64, np.int64])
+    rng = np.random.Generator(np.random.PCG64(9))
+    pt.columns[0][:] = rng.integers(-(2**63), 2**63 - 1, n, dtype=np.int64)
+    pt.columns[1][:] = np.arange(n)
+    ex = dfd.RepartitionExec(ctx, pa.schema([("k", pa.int64()), ("v", pa.int64())]), dfd.Partitioning.Hash([0], 1))
+    for rb in pt.record_batches(["k", "v"], 50_000):
+        ex.push_batch(rb)
+    ex.finish()
+    out = ex.execute(0).read_all()
+    assert np.array_equal(out.column("v").to_numpy(), np.arange(n))
+    ex.close()
+
+
+def test_operator_errors(ctx):
+    with pytest.raises(dfd.DfdError) as e:
+        dfd.RepartitionExec(ctx, pa.schema([("s", pa.string())]), dfd.Partitioning.Hash([0], 4))
+    assert e.value.status == 6  # DFD_ERR_UNSUPPORTED: variable-width columns are a "next" row
+    sch = pa.schema([("k", pa.int64())])
+    with pytest.raises(dfd.DfdError):
+        dfd.RepartitionExec(ctx, sch, dfd.Partitioning.Hash([1], 4))
+    ex = dfd.RepartitionExec(ctx, sch, dfd.Partitioning.Hash([0], 4))
+    ex.finish()
+    with pytest.raises(dfd.DfdError):
+        ex.push_batch(pa.RecordBatch.from_arrays([pa.array([1, 2, 3])], names=["k"]))
+    ex.close()
+    # wrong column count: the error reaches every partition stream
+    ex = dfd.RepartitionExec(ctx, sch, dfd.Partitioning.Hash([0], 2))
+    with pytest.raises(dfd.DfdError):
+        ex.push_batch(pa.RecordBatch.from_arrays([pa.array([1]), pa.array([2])], names=["k", "x"]))
+    for p in range(2):
+        with pytest.raises(Exception):
+            ex.execute(p).read_all()
+    ex.close()
