@@ -163,16 +163,23 @@ def run_e2e(ctx, dfd, n, args):
         ex = dfd.RepartitionExec(ctx, schema, dfd.Partitioning.Hash([0], NUM_PARTITIONS), chunk_rows=args.e2e_chunk_rows,
                                  pipeline_depth=3, pinned_pool_chunks=6)
         readers = [ex.execute(p) for p in range(NUM_PARTITIONS)]
-        rows_out = 0
-        checksum = 0
+        counts = [0] * NUM_PARTITIONS
+
+        def consume(p):  # one consumer per destination stream, like the reference's per-partition pollers
+            for rb in readers[p]:
+                counts[p] += rb.num_rows
+
+        consumers = [threading.Thread(target=consume, args=(p,)) for p in range(NUM_PARTITIONS)]
         t0 = time.perf_counter()
+        for t in consumers:
+            t.start()
         for b in batches:
             ex.push_batch(b)
         ex.finish()
-        for r in readers:  # consumer side: read every destination's stream (device->host result)
-            for rb in r:
-                rows_out += rb.num_rows
+        for t in consumers:
+            t.join()
         dt = time.perf_counter() - t0
+        rows_out = sum(counts)
         assert rows_out == n, (rows_out, n)
         st = ex.stats()
         del readers
