@@ -19,6 +19,7 @@ STATUS = {
 }
 
 COL_FIXED, COL_BOOL, COL_UTF8, COL_LARGE_UTF8, COL_BINARY = 0, 1, 2, 3, 4
+EXCHANGE_NCCL, EXCHANGE_FUSED = 0, 1
 
 
 class DfdError(RuntimeError):
@@ -120,6 +121,16 @@ SIGNATURES = {
     "dfd_repartition_exec_run": (C.c_int, [_VP, C.POINTER(ArrowArrayStreamStruct)]),
     "dfd_repartition_exec_execute": (C.c_int, [_VP, C.c_uint32, C.POINTER(ArrowArrayStreamStruct)]),
     "dfd_repartition_exec_stats": (C.c_int, [_VP, C.POINTER(DfdExecStats)]),
+    "dfd_nccl_unique_id": (C.c_int, [_VP]),
+    "dfd_exchange_create": (C.c_int, [_VP, C.c_int, C.c_int, _VP, C.POINTER(_VP)]),
+    "dfd_exchange_destroy": (None, [_VP]),
+    "dfd_exchange_rank": (C.c_int, [_VP]),
+    "dfd_exchange_world": (C.c_int, [_VP]),
+    "dfd_exchange_setup_window": (C.c_int, [_VP, C.c_size_t]),
+    "dfd_exchange_plan": (C.c_int, [C.c_int, C.c_uint32, C.c_int, _VP, _VP, _VP, _VP, _VP, C.POINTER(C.c_int64)]),
+    "dfd_shuffle_device": (C.c_int, [_VP, _VP, C.c_int, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.c_uint32,
+                                     C.POINTER(DfdColumn), C.c_int64, C.POINTER(C.c_int64)]),
+    "dfd_exchange_stats": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "dfd_metrics_get": (C.c_int, [_VP, C.POINTER(DfdMetrics)]),
     "dfd_metrics_reset": (C.c_int, [_VP]),
 }

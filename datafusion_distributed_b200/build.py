@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 OUT = os.path.join(OUT_DIR, "libdfd_b200.so")
 
-SOURCES = ["dfd_api.cu", "dfd_exec.cu"]
+SOURCES = ["dfd_api.cu", "dfd_exec.cu", "dfd_exchange.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

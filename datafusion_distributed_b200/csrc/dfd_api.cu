@@ -130,9 +130,9 @@ static int build_keyset(const dfd_partitioner* p, const dfd_column* cols, int n_
         if (_e != cudaSuccess) return cuda_error(_e, what);            \
     }
 
-template <bool FAST, typename V>
+template <bool FAST, typename V, bool PEER>
 static int launch_scatter_t(const ScatterParams& sp, unsigned grid, size_t smem, cudaStream_t stream) {
-    auto kern = k_scatter<TILE_THREADS, TILE_K, TILE_MIN_CTAS, FAST, V>;
+    auto kern = k_scatter<TILE_THREADS, TILE_K, TILE_MIN_CTAS, FAST, V, PEER>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(k_scatter)");
@@ -142,46 +142,49 @@ static int launch_scatter_t(const ScatterParams& sp, unsigned grid, size_t smem,
     return e == cudaSuccess ? DFD_OK : cuda_error(e, "k_scatter");
 }
 
-template <bool FAST>
+template <bool FAST, bool PEER>
 static int launch_scatter_w(const ScatterParams& sp, int width, unsigned grid, size_t smem, cudaStream_t stream) {
     switch (width) {
-        case 8: return launch_scatter_t<FAST, uint64_t>(sp, grid, smem, stream);
-        case 4: return launch_scatter_t<FAST, uint32_t>(sp, grid, smem, stream);
-        case 2: return launch_scatter_t<FAST, uint16_t>(sp, grid, smem, stream);
-        case 1: return launch_scatter_t<FAST, uint8_t>(sp, grid, smem, stream);
-        case 16: return launch_scatter_t<FAST, uint4>(sp, grid, smem, stream);
-        default: return launch_scatter_t<FAST, BitColumn>(sp, grid, smem, stream);
+        case 8: return launch_scatter_t<FAST, uint64_t, PEER>(sp, grid, smem, stream);
+        case 4: return launch_scatter_t<FAST, uint32_t, PEER>(sp, grid, smem, stream);
+        case 2: return launch_scatter_t<FAST, uint16_t, PEER>(sp, grid, smem, stream);
+        case 1: return launch_scatter_t<FAST, uint8_t, PEER>(sp, grid, smem, stream);
+        case 16: return launch_scatter_t<FAST, uint4, PEER>(sp, grid, smem, stream);
+        default:
+            if (PEER) return set_error(DFD_ERR_UNSUPPORTED, "bit-packed columns are not supported by the fused peer-store exchange");
+            return launch_scatter_t<FAST, BitColumn, false>(sp, grid, smem, stream);
     }
 }
 
-static int launch_scatter(const ScatterParams& sp, int width, bool fast, unsigned grid, size_t smem, cudaStream_t stream) {
-    return fast ? launch_scatter_w<true>(sp, width, grid, smem, stream) : launch_scatter_w<false>(sp, width, grid, smem, stream);
+static int launch_scatter(const ScatterParams& sp, int width, bool fast, bool peer, unsigned grid, size_t smem, cudaStream_t stream) {
+    if (peer) return fast ? launch_scatter_w<true, true>(sp, width, grid, smem, stream) : launch_scatter_w<false, true>(sp, width, grid, smem, stream);
+    return fast ? launch_scatter_w<true, false>(sp, width, grid, smem, stream) : launch_scatter_w<false, false>(sp, width, grid, smem, stream);
 }
 
-int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,
-                                 const dfd_column* out_cols, cudaStream_t stream) {
+// ---- PartitionJob: validation -> K1/K1b -> K2, reusable by the local path and the exchange ----
+
+int dfd::PartitionJob::prepare(Partitioner* part, const dfd_column* in_cols, int n_cols, int64_t rows,
+                               const dfd_column* out_cols, bool peer_mode, cudaStream_t st) {
+    p = part;
+    stream = st;
+    peer = peer_mode;
+    n_rows = rows;
+    passes.clear();
+    bytes = 0;
     Ctx* c = p->ctx;
     const uint32_t N = p->N;
     if (n_rows < 0 || n_cols < 0 || (n_cols > 0 && (!in_cols || !out_cols)))
-        return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_partition_device: bad arguments");
-    if (n_rows == 0) {
-        cudaError_t e = cudaMemsetAsync(p->d_part_starts, 0, sizeof(int64_t) * (size_t)(N + 1), stream);
-        return e == cudaSuccess ? DFD_OK : cuda_error(e, "cudaMemsetAsync");
-    }
-    KeySet ks;
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "partition: bad arguments");
+    if (n_rows > 0xffffffffLL) return set_error(DFD_ERR_UNSUPPORTED, "n_rows must be < 2^32 per call");
     int rc = build_keyset(p, in_cols, n_cols, &ks);
     if (rc) return rc;
-
     // payload passes: every column's values, plus a bit pass per validity bitmap
-    std::vector<PayloadCol> passes;
-
-    uint64_t bytes = 0;
     for (int i = 0; i < n_cols; ++i) {
         const dfd_column& ic = in_cols[i];
         const dfd_column& oc = out_cols[i];
         if (ic.kind != oc.kind || ic.width != oc.width)
             return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: in/out layout mismatch", i);
-        if (!ic.values || !oc.values) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: values is NULL", i);
+        if (!ic.values || (!peer && !oc.values)) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: values is NULL", i);
         PayloadCol pc{};
         if (ic.kind == DFD_COL_FIXED) {
             if (ic.width != 1 && ic.width != 2 && ic.width != 4 && ic.width != 8 && ic.width != 16)
@@ -192,9 +195,9 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
             pc.out = oc.values;
             pc.in_offset = ic.offset;
             pc.width = ic.width;
-
             bytes += (uint64_t)n_rows * ic.width;
         } else if (ic.kind == DFD_COL_BOOL) {
+            if (peer) return set_error(DFD_ERR_UNSUPPORTED, "column %d: bit-packed columns need the NCCL exchange mode", i);
             if ((uintptr_t)oc.values & 3) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: output bitmap must be 4-byte aligned", i);
             pc.in = ic.values;
             pc.out = oc.values;
@@ -202,10 +205,11 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
             pc.width = 0;
             bytes += (uint64_t)(n_rows + 7) / 8;
         } else {
-            return set_error(DFD_ERR_UNSUPPORTED, "column %d: variable-width payload columns are not supported by dfd_partition_device yet", i);
+            return set_error(DFD_ERR_UNSUPPORTED, "column %d: variable-width payload columns are not supported yet", i);
         }
         passes.push_back(pc);
         if (ic.validity) {
+            if (peer) return set_error(DFD_ERR_UNSUPPORTED, "column %d: nullable columns need the NCCL exchange mode", i);
             if (!oc.validity) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: input has a validity bitmap but out validity is NULL", i);
             if ((uintptr_t)oc.validity & 3) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: output validity must be 4-byte aligned", i);
             PayloadCol vc{};
@@ -217,9 +221,7 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
             bytes += (uint64_t)(n_rows + 7) / 8;
         }
     }
-
-    const int64_t n_tiles = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
-    if (n_rows > 0xffffffffLL) return set_error(DFD_ERR_UNSUPPORTED, "n_rows must be < 2^32 per call");
+    n_tiles = n_rows > 0 ? (n_rows + TILE_ROWS - 1) / TILE_ROWS : 1;
     // scratch: hist u32 [N][n_tiles] | tile_base u32 [N][n_tiles] | totals i64 [N] | done u32
     size_t hist_bytes = (((size_t)N * n_tiles * 4) + 255) & ~(size_t)255;
     size_t tot_bytes = (((size_t)N * 8) + 255) & ~(size_t)255;
@@ -227,19 +229,17 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
     bool fresh = need > c->scratch.bytes;
     rc = c->scratch.ensure(need, c->device);
     if (rc) return rc;
-    uint32_t* d_hist = (uint32_t*)c->scratch.ptr;
-    uint32_t* d_base = (uint32_t*)((char*)c->scratch.ptr + hist_bytes);
-    int64_t* d_totals = (int64_t*)((char*)c->scratch.ptr + 2 * hist_bytes);
-    unsigned* d_done = (unsigned*)((char*)c->scratch.ptr + 2 * hist_bytes + tot_bytes);
+    d_hist = (uint32_t*)c->scratch.ptr;
+    d_base = (uint32_t*)((char*)c->scratch.ptr + hist_bytes);
+    d_totals = (int64_t*)((char*)c->scratch.ptr + 2 * hist_bytes);
+    d_done = (unsigned*)((char*)c->scratch.ptr + 2 * hist_bytes + tot_bytes);
     if (fresh || c->scratch_done != d_done) {
         cudaError_t e = cudaMemsetAsync(d_done, 0, 256, stream);
         if (e != cudaSuccess) return cuda_error(e, "cudaMemsetAsync(done)");
         c->scratch_done = d_done;
     }
-
-    const bool prof = c->profiling;
-    cudaEvent_t* ev = nullptr;
-    if (prof) {
+    ev = nullptr;
+    if (c->profiling) {
         if (c->ev_ring.empty()) {
             c->ev_ring.resize(4 * dfd_ctx::EV_RING_CALLS);
             for (auto& e : c->ev_ring) cudaEventCreate(&e);
@@ -249,7 +249,20 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
             if (rc) return rc;
         }
         ev = &c->ev_ring[4 * c->ev_pending];
-        cudaEventRecord(ev[0], stream);
+    }
+    return DFD_OK;
+}
+
+// K1 + K1b: d_hist, d_base (tile cursors), d_totals[N] and p->d_part_starts[N+1]
+int dfd::PartitionJob::run_hist_scan() {
+    Ctx* c = p->ctx;
+    const uint32_t N = p->N;
+    if (ev) cudaEventRecord(ev[0], stream);
+    if (n_rows == 0) {
+        cudaError_t e = cudaMemsetAsync(d_totals, 0, sizeof(int64_t) * (size_t)N, stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(p->d_part_starts, 0, sizeof(int64_t) * (size_t)(N + 1), stream);
+        if (ev) { cudaEventRecord(ev[1], stream); cudaEventRecord(ev[2], stream); }
+        return e == cudaSuccess ? DFD_OK : cuda_error(e, "cudaMemsetAsync");
     }
     {
         size_t smem = (size_t)N * 4;
@@ -264,47 +277,63 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
 #undef HIST
         LAUNCH_CHECK("k_tile_hist");
     }
-    if (prof) cudaEventRecord(ev[1], stream);
+    if (ev) cudaEventRecord(ev[1], stream);
     k_scan_tiles<1024><<<N, 1024, 0, stream>>>(d_hist, d_base, d_totals, p->d_part_starts, d_done, n_tiles, N);
     LAUNCH_CHECK("k_scan_tiles");
-    if (prof) cudaEventRecord(ev[2], stream);
+    if (ev) cudaEventRecord(ev[2], stream);
     c->metrics.kernel_launches += 2;
+    return DFD_OK;
+}
 
-    ScatterParams sp{};
-    sp.keys = ks;
-    sp.st = p->st;
-    sp.mod = p->mod;
-    sp.n_rows = n_rows;
-    sp.n_tiles = n_tiles;
-    sp.hist = d_hist;
-    sp.tile_base = d_base;
-    sp.part_starts = p->d_part_starts;
-    sp.N = N;
+// K2.  dest_base[N]: first output row of each destination (p->d_part_starts in local mode).
+int dfd::PartitionJob::run_scatter(const int64_t* dest_base, void* const* peer_base, int world, uint32_t parts_per_rank,
+                                   const int32_t* abort_flag) {
+    Ctx* c = p->ctx;
+    const uint32_t N = p->N;
     int launches = 0;
-    // one launch per element width (0 = bit columns), columns of that width batched
-    static const int kWidths[6] = {8, 4, 16, 2, 1, 0};
-    for (int wi = 0; wi < 6; ++wi) {
-        const int width = kWidths[wi];
-        std::vector<PayloadCol> group;
-        for (const PayloadCol& pc : passes)
-            if (pc.width == width) group.push_back(pc);
-        if (group.empty()) continue;
-        sp.stage_width = width ? width : 1;
-        size_t smem = scatter_smem_bytes<TILE_THREADS, TILE_K>(N, sp.stage_width);
-        if (smem > 200 * 1024)
-            return set_error(DFD_ERR_UNSUPPORTED, "num_partitions %u needs %zu B of shared memory per CTA", N, smem);
-        for (size_t first = 0; first < group.size(); first += MAX_COLS_PER_LAUNCH) {
-            size_t n = group.size() - first < (size_t)MAX_COLS_PER_LAUNCH ? group.size() - first : (size_t)MAX_COLS_PER_LAUNCH;
-            for (size_t i = 0; i < n; ++i) sp.cols[i] = group[first + i];
-            sp.n_cols = (int32_t)n;
-            rc = launch_scatter(sp, width, ks.fast_i64 != 0, (unsigned)n_tiles, smem, stream);
-            if (rc) return rc;
-            ++launches;
+    if (n_rows > 0) {
+        ScatterParams sp{};
+        sp.keys = ks;
+        sp.st = p->st;
+        sp.mod = p->mod;
+        sp.n_rows = n_rows;
+        sp.n_tiles = n_tiles;
+        sp.hist = d_hist;
+        sp.tile_base = d_base;
+        sp.dest_base = dest_base;
+        sp.N = N;
+        sp.parts_per_rank = parts_per_rank ? parts_per_rank : 1;
+        sp.abort_flag = abort_flag;
+        if (peer) {
+            if (world > MAX_RANKS) return set_error(DFD_ERR_UNSUPPORTED, "world size %d > %d", world, MAX_RANKS);
+            for (int r = 0; r < world; ++r) sp.peer_base[r] = peer_base[r];
+        }
+        // one launch per element width (0 = bit columns), columns of that width batched
+        static const int kWidths[6] = {8, 4, 16, 2, 1, 0};
+        for (int wi = 0; wi < 6; ++wi) {
+            const int width = kWidths[wi];
+            std::vector<PayloadCol> group;
+            for (const PayloadCol& pc : passes)
+                if (pc.width == width) group.push_back(pc);
+            if (group.empty()) continue;
+            sp.stage_width = width ? width : 1;
+            size_t smem = scatter_smem_bytes<TILE_THREADS, TILE_K>(N, sp.stage_width);
+            if (smem > 200 * 1024)
+                return set_error(DFD_ERR_UNSUPPORTED, "num_partitions %u needs %zu B of shared memory per CTA", N, smem);
+            for (size_t first = 0; first < group.size(); first += MAX_COLS_PER_LAUNCH) {
+                size_t n = group.size() - first < (size_t)MAX_COLS_PER_LAUNCH ? group.size() - first : (size_t)MAX_COLS_PER_LAUNCH;
+                for (size_t i = 0; i < n; ++i) sp.cols[i] = group[first + i];
+                sp.n_cols = (int32_t)n;
+                int rc = launch_scatter(sp, width, ks.fast_i64 != 0, peer, (unsigned)n_tiles, smem, stream);
+                if (rc) return rc;
+                ++launches;
+            }
         }
     }
-    if (prof) {
+    if (ev) {
         cudaEventRecord(ev[3], stream);
         c->ev_pending++;
+        ev = nullptr;
     }
     c->metrics.kernel_launches += launches;
     c->metrics.scatter_launches += launches;
@@ -313,6 +342,15 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
     c->metrics.bytes_in += bytes;
     c->metrics.bytes_out += bytes;
     return DFD_OK;
+}
+
+int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,
+                                 const dfd_column* out_cols, cudaStream_t stream) {
+    PartitionJob job;
+    int rc = job.prepare(p, in_cols, n_cols, n_rows, out_cols, false, stream);
+    if (rc) return rc;
+    if ((rc = job.run_hist_scan())) return rc;
+    return job.run_scatter(p->d_part_starts, nullptr, 1, 1, nullptr);
 }
 
 extern "C" {

@@ -1,0 +1,481 @@
+// dfd_exchange.cu — the inter-worker exchange of the shuffle over NVLink.
+//
+// Replaces the reference's data plane between stage N (producers) and stage
+// N+1 (consumers):
+//   server  Worker::impl_execute_task  (src/worker/impl_execute_task.rs:36-169)
+//           Arrow-IPC/Flight encode + gRPC stream per (consumer, producer)
+//   client  WorkerConnection demux + FlightRecordBatchStream decode
+//           (src/worker/worker_connection_pool.rs:143-390)
+//   NetworkShuffleExec::execute: off = P*task_index, partition off+p from every
+//           producer (src/execution_plans/network_shuffle.rs:213-238)
+// with one worker per GPU and two transports:
+//   DFD_EXCHANGE_NCCL   partition locally, all-gather the T x N count matrix,
+//                       grouped ncclSend/ncclRecv per (column, destination).
+//   DFD_EXCHANGE_FUSED  the K2 scatter kernel stores every run straight into
+//                       the owner rank's receive window (CUDA-IPC mapped peer
+//                       memory over NVLink/NVSwitch): no staging buffer, no
+//                       separate send — compute and transfer are one kernel.
+// NCCL is resolved at run time (dlopen libnccl.so.2) so the single-GPU library
+// has no link-time dependency on it.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "dfd_b200.h"
+#include "dfd_internal.h"
+
+using namespace dfd;
+
+namespace {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    std::string error;
+};
+
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) {
+            api.error = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "");
+            return;
+        }
+#define LOAD(field, sym)                                                   \
+    api.field = (decltype(api.field))dlsym(api.handle, sym);             \
+    if (!api.field) { api.error = std::string("missing NCCL symbol ") + sym; return; }
+        LOAD(GetVersion, "ncclGetVersion");
+        LOAD(GetUniqueId, "ncclGetUniqueId");
+        LOAD(CommInitRank, "ncclCommInitRank");
+        LOAD(CommDestroy, "ncclCommDestroy");
+        LOAD(CommAbort, "ncclCommAbort");
+        LOAD(GetErrorString, "ncclGetErrorString");
+        LOAD(AllGather, "ncclAllGather");
+        LOAD(AllReduce, "ncclAllReduce");
+        LOAD(Send, "ncclSend");
+        LOAD(Recv, "ncclRecv");
+        LOAD(GroupStart, "ncclGroupStart");
+        LOAD(GroupEnd, "ncclGroupEnd");
+#undef LOAD
+    });
+    return &api;
+}
+
+int nccl_error(ncclResult_t r, const char* what) {
+    NcclApi* n = nccl_api();
+    return set_error(DFD_ERR_NCCL, "%s: %s", what, n->GetErrorString ? n->GetErrorString(r) : "NCCL error");
+}
+
+#define NCCL_TRY(call, what)                                   \
+    {                                                          \
+        ncclResult_t _r = (call);                              \
+        if (_r != ncclSuccess) return nccl_error(_r, what);    \
+    }
+#define CUDA_TRY(call, what)                                   \
+    {                                                          \
+        cudaError_t _e = (call);                               \
+        if (_e != cudaSuccess) return cuda_error(_e, what);    \
+    }
+
+// dest_base / part_starts / overflow check on the device (fused mode), from the
+// all-gathered count matrix counts[T][N]: no host round trip before K2.
+__global__ void k_exchange_plan(const int64_t* __restrict__ counts, int world, uint32_t P, int rank, int64_t capacity_rows,
+                                int64_t* __restrict__ dest_base /*[N]*/, int64_t* __restrict__ my_part_starts /*[P+1]*/,
+                                int32_t* __restrict__ abort_flag) {
+    const uint32_t N = P * (uint32_t)world;
+    __shared__ int overflow;
+    if (threadIdx.x == 0) overflow = 0;
+    __syncthreads();
+    // one thread per owner rank o: walk its P partitions
+    for (int o = threadIdx.x; o < world; o += blockDim.x) {
+        int64_t run = 0;
+        for (uint32_t q = 0; q < P; ++q) {
+            const uint32_t g = (uint32_t)o * P + q;
+            if (o == rank) my_part_starts[q] = run;
+            int64_t before_me = 0, tot = 0;
+            for (int r = 0; r < world; ++r) {
+                int64_t c = counts[(int64_t)r * N + g];
+                if (r < rank) before_me += c;
+                tot += c;
+            }
+            dest_base[g] = run + before_me;
+            run += tot;
+        }
+        if (o == rank) my_part_starts[P] = run;
+        if (run > capacity_rows) atomicExch(&overflow, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *abort_flag = overflow;
+}
+
+}  // namespace
+
+struct dfd_exchange {
+    dfd_ctx* ctx = nullptr;
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    // scratch
+    int64_t* d_counts = nullptr;      // [T][N] all-gathered destination counts
+    int64_t* h_counts = nullptr;      // pinned mirror
+    int64_t* d_dest_base = nullptr;   // [N]
+    int64_t* d_my_starts = nullptr;   // [P+1]
+    int64_t* h_my_starts = nullptr;   // pinned
+    int32_t* d_abort = nullptr;
+    int32_t* h_abort = nullptr;       // pinned
+    int32_t* d_token = nullptr;       // barrier payload
+    uint32_t cap_N = 0;
+    // NCCL mode staging (locally partitioned columns)
+    Scratch send;
+    // fused mode: receive window + peers' mappings
+    void* window = nullptr;
+    size_t window_bytes = 0;
+    void* peer_window[MAX_RANKS] = {};
+    bool window_ready = false;
+    uint64_t bytes_sent = 0, bytes_received = 0, shuffles = 0;
+};
+
+extern "C" {
+
+/* Pure host logic (no GPU): from the T x N count matrix, where does everything go? */
+int dfd_exchange_plan(int world, uint32_t partitions_per_task, int rank, const int64_t* counts, int64_t* send_start,
+                      int64_t* recv_start, int64_t* part_starts, int64_t* dest_base, int64_t* recv_rows) {
+    if (world < 1 || partitions_per_task < 1 || rank < 0 || rank >= world || !counts)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_exchange_plan: bad arguments");
+    const uint32_t P = partitions_per_task;
+    const int64_t N = (int64_t)P * world;
+    for (int64_t i = 0; i < N * world; ++i)
+        if (counts[i] < 0) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_exchange_plan: negative count");
+    if (send_start) {  // my locally partitioned buffer: destinations back-to-back
+        int64_t run = 0;
+        for (int64_t g = 0; g < N; ++g) {
+            send_start[g] = run;
+            run += counts[(int64_t)rank * N + g];
+        }
+    }
+    // my receive buffer: [local partition q][producer r]  (destination-major, producers in task order)
+    int64_t run = 0;
+    for (uint32_t q = 0; q < P; ++q) {
+        const int64_t g = (int64_t)rank * P + q;
+        if (part_starts) part_starts[q] = run;
+        for (int r = 0; r < world; ++r) {
+            if (recv_start) recv_start[(int64_t)q * world + r] = run;
+            run += counts[(int64_t)r * N + g];
+        }
+    }
+    if (part_starts) part_starts[P] = run;
+    if (recv_rows) *recv_rows = run;
+    if (dest_base) {  // where MY rows of destination g start inside the owner's receive buffer
+        for (int o = 0; o < world; ++o) {
+            int64_t orun = 0;
+            for (uint32_t q = 0; q < P; ++q) {
+                const int64_t g = (int64_t)o * P + q;
+                int64_t before = 0, tot = 0;
+                for (int r = 0; r < world; ++r) {
+                    if (r < rank) before += counts[(int64_t)r * N + g];
+                    tot += counts[(int64_t)r * N + g];
+                }
+                dest_base[g] = orun + before;
+                orun += tot;
+            }
+        }
+    }
+    return DFD_OK;
+}
+
+int dfd_nccl_unique_id(void* out_128_bytes) {
+    if (!out_128_bytes) return set_error(DFD_ERR_INVALID_ARGUMENT, "out is NULL");
+    NcclApi* n = nccl_api();
+    if (!n->handle || !n->error.empty()) return set_error(DFD_ERR_NCCL, "%s", n->error.c_str());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NCCL_TRY(n->GetUniqueId(&id), "ncclGetUniqueId");
+    memcpy(out_128_bytes, &id, sizeof id);
+    return DFD_OK;
+}
+
+int dfd_exchange_create(dfd_ctx* ctx, int rank, int world, const void* nccl_unique_id, dfd_exchange** out) {
+    if (!ctx || !out) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_exchange_create: NULL argument");
+    *out = nullptr;
+    if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "rank %d / world %d invalid (max %d workers)", rank, world, MAX_RANKS);
+    dfd_exchange* x = new (std::nothrow) dfd_exchange();
+    if (!x) return set_error(DFD_ERR_OOM, "out of host memory");
+    x->ctx = ctx;
+    x->rank = rank;
+    x->world = world;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) { delete x; return cuda_error(e, "cudaSetDevice"); }
+    if (world > 1) {
+        if (!nccl_unique_id) { delete x; return set_error(DFD_ERR_INVALID_ARGUMENT, "nccl_unique_id is NULL"); }
+        NcclApi* n = nccl_api();
+        if (!n->handle || !n->error.empty()) { delete x; return set_error(DFD_ERR_NCCL, "%s", n->error.c_str()); }
+        ncclUniqueId id;
+        memcpy(&id, nccl_unique_id, sizeof id);
+        ncclResult_t r = n->CommInitRank(&x->comm, world, id, rank);
+        if (r != ncclSuccess) { delete x; return nccl_error(r, "ncclCommInitRank"); }
+    }
+    e = cudaMalloc((void**)&x->d_abort, 256);
+    if (e == cudaSuccess) e = cudaMemset(x->d_abort, 0, 256);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&x->h_abort, 64, cudaHostAllocPortable);
+    if (e != cudaSuccess) { delete x; return cuda_error(e, "dfd_exchange_create"); }
+    x->d_token = x->d_abort + 16;
+    *x->h_abort = 0;
+    *out = x;
+    return DFD_OK;
+}
+
+void dfd_exchange_destroy(dfd_exchange* x) {
+    if (!x) return;
+    {
+        std::lock_guard<std::mutex> lk(x->ctx->mu);
+        cudaSetDevice(x->ctx->device);
+        cudaStreamSynchronize(x->ctx->stream);
+        for (int r = 0; r < x->world; ++r)
+            if (x->peer_window[r] && r != x->rank) cudaIpcCloseMemHandle(x->peer_window[r]);
+        if (x->comm) nccl_api()->CommDestroy(x->comm);
+        cudaFree(x->window);
+        cudaFree(x->d_counts);
+        cudaFree(x->d_dest_base);
+        cudaFree(x->d_my_starts);
+        cudaFree(x->d_abort);
+        cudaFree(x->send.ptr);
+        cudaFreeHost(x->h_counts);
+        cudaFreeHost(x->h_my_starts);
+        cudaFreeHost(x->h_abort);
+    }
+    delete x;
+}
+
+int dfd_exchange_rank(const dfd_exchange* x) { return x ? x->rank : -1; }
+int dfd_exchange_world(const dfd_exchange* x) { return x ? x->world : 0; }
+
+static int ensure_count_buffers(dfd_exchange* x, uint32_t N) {
+    if (N <= x->cap_N) return DFD_OK;
+    cudaFree(x->d_counts); cudaFree(x->d_dest_base); cudaFree(x->d_my_starts);
+    cudaFreeHost(x->h_counts); cudaFreeHost(x->h_my_starts);
+    x->d_counts = nullptr; x->d_dest_base = nullptr; x->d_my_starts = nullptr; x->h_counts = nullptr; x->h_my_starts = nullptr;
+    x->cap_N = 0;
+    CUDA_TRY(cudaMalloc((void**)&x->d_counts, sizeof(int64_t) * (size_t)N * x->world), "cudaMalloc(counts)");
+    CUDA_TRY(cudaMalloc((void**)&x->d_dest_base, sizeof(int64_t) * (size_t)N), "cudaMalloc(dest_base)");
+    CUDA_TRY(cudaMalloc((void**)&x->d_my_starts, sizeof(int64_t) * (size_t)(N + 1)), "cudaMalloc(my_starts)");
+    CUDA_TRY(cudaHostAlloc((void**)&x->h_counts, sizeof(int64_t) * (size_t)N * x->world, cudaHostAllocPortable), "cudaHostAlloc");
+    CUDA_TRY(cudaHostAlloc((void**)&x->h_my_starts, sizeof(int64_t) * (size_t)(N + 1), cudaHostAllocPortable), "cudaHostAlloc");
+    x->cap_N = N;
+    return DFD_OK;
+}
+
+/* Allocate this rank's receive window and map every peer's (collective call). */
+int dfd_exchange_setup_window(dfd_exchange* x, size_t window_bytes) {
+    if (!x) return set_error(DFD_ERR_INVALID_ARGUMENT, "NULL exchange");
+    dfd_ctx* c = x->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device), "cudaSetDevice");
+    if (x->window_ready) return set_error(DFD_ERR_INVALID_ARGUMENT, "receive window already set up");
+    window_bytes = (window_bytes + 255) & ~(size_t)255;
+    CUDA_TRY(cudaMalloc(&x->window, window_bytes), "cudaMalloc(receive window)");
+    x->window_bytes = window_bytes;
+    x->peer_window[x->rank] = x->window;
+    if (x->world > 1) {
+        NcclApi* n = nccl_api();
+        cudaIpcMemHandle_t mine;
+        CUDA_TRY(cudaIpcGetMemHandle(&mine, x->window), "cudaIpcGetMemHandle");
+        char* d_h = nullptr;
+        const size_t hs = sizeof(cudaIpcMemHandle_t);
+        CUDA_TRY(cudaMalloc((void**)&d_h, hs * (size_t)(x->world + 1)), "cudaMalloc(handles)");
+        CUDA_TRY(cudaMemcpyAsync(d_h + hs * x->world, &mine, hs, cudaMemcpyHostToDevice, c->stream), "H2D handle");
+        NCCL_TRY(n->AllGather(d_h + hs * x->world, d_h, hs, ncclInt8, x->comm, c->stream), "ncclAllGather(handles)");
+        std::vector<cudaIpcMemHandle_t> all(x->world);
+        CUDA_TRY(cudaMemcpyAsync(all.data(), d_h, hs * x->world, cudaMemcpyDeviceToHost, c->stream), "D2H handles");
+        CUDA_TRY(cudaStreamSynchronize(c->stream), "sync");
+        cudaFree(d_h);
+        for (int r = 0; r < x->world; ++r) {
+            if (r == x->rank) continue;
+            cudaError_t e = cudaIpcOpenMemHandle(&x->peer_window[r], all[r], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return cuda_error(e, "cudaIpcOpenMemHandle (peer receive window)");
+        }
+    }
+    x->window_ready = true;
+    return DFD_OK;
+}
+
+static size_t row_bytes_of(const dfd_column* cols, int n_cols) {
+    size_t rb = 0;
+    for (int i = 0; i < n_cols; ++i) rb += cols[i].kind == DFD_COL_FIXED ? (size_t)cols[i].width : 0;
+    return rb;
+}
+
+/* The shuffle: producer task `rank` holds n_rows local rows; afterwards this
+ * worker, as consumer task `rank`, holds its P = partitions_per_task
+ * destinations (global partitions rank*P .. rank*P+P-1), each contiguous, rows
+ * from the producers in task order. */
+int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* part, int mode, const dfd_column* in_cols, int n_cols,
+                       int64_t n_rows, uint32_t partitions_per_task, dfd_column* out_cols, int64_t out_capacity_rows,
+                       int64_t* part_starts_host) {
+    if (!x || !part || !in_cols || !out_cols || !part_starts_host)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_shuffle_device: NULL argument");
+    dfd_ctx* c = x->ctx;
+    if (part->ctx != c) return set_error(DFD_ERR_INVALID_ARGUMENT, "partitioner and exchange belong to different contexts");
+    const uint32_t P = partitions_per_task;
+    const uint32_t N = part->N;
+    const int T = x->world;
+    if (P < 1 || (uint64_t)P * T != N)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "num_partitions %u != partitions_per_task %u x %d workers", N, P, T);
+    NcclApi* n = T > 1 ? nccl_api() : nullptr;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device), "cudaSetDevice");
+    int rc = ensure_count_buffers(x, N);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    x->shuffles++;
+
+    if (mode == DFD_EXCHANGE_FUSED) {
+        if (!x->window_ready) return set_error(DFD_ERR_INVALID_ARGUMENT, "fused exchange needs dfd_exchange_setup_window first");
+        const size_t rb = row_bytes_of(in_cols, n_cols);
+        if (rb == 0) return set_error(DFD_ERR_INVALID_ARGUMENT, "no fixed-width columns");
+        const int64_t capacity_rows = (int64_t)(x->window_bytes / rb) / 16 * 16;
+        // window layout (identical on every rank): column c at byte offset capacity_rows * sum(width[0..c))
+        std::vector<dfd_column> outs(n_cols);
+        size_t off = 0;
+        for (int i = 0; i < n_cols; ++i) {
+            outs[i] = in_cols[i];
+            outs[i].values = (void*)off;  // peer mode: byte offset into every window
+            outs[i].validity = nullptr;
+            outs[i].offset = 0;
+            out_cols[i] = in_cols[i];
+            out_cols[i].values = (char*)x->window + off;
+            out_cols[i].validity = nullptr;
+            out_cols[i].offset = 0;
+            off += (size_t)capacity_rows * (size_t)in_cols[i].width;
+        }
+        PartitionJob job;
+        if ((rc = job.prepare(part, in_cols, n_cols, n_rows, outs.data(), true, s))) return rc;
+        if ((rc = job.run_hist_scan())) return rc;
+        if (T > 1) {
+            NCCL_TRY(n->AllGather(job.d_totals, x->d_counts, N, ncclInt64, x->comm, s), "ncclAllGather(counts)");
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(x->d_counts, job.d_totals, sizeof(int64_t) * N, cudaMemcpyDeviceToDevice, s), "copy counts");
+        }
+        k_exchange_plan<<<1, 32, 0, s>>>(x->d_counts, T, P, x->rank, capacity_rows, x->d_dest_base, x->d_my_starts, x->d_abort);
+        CUDA_TRY(cudaGetLastError(), "k_exchange_plan");
+        c->metrics.kernel_launches++;
+        if ((rc = job.run_scatter(x->d_dest_base, x->peer_window, T, P, x->d_abort))) return rc;
+        // every producer's stores must have landed before any consumer reads its window
+        if (T > 1) NCCL_TRY(n->AllReduce(x->d_token, x->d_token, 1, ncclInt32, ncclSum, x->comm, s), "ncclAllReduce(barrier)");
+        CUDA_TRY(cudaMemcpyAsync(x->h_my_starts, x->d_my_starts, sizeof(int64_t) * (P + 1), cudaMemcpyDeviceToHost, s), "D2H starts");
+        CUDA_TRY(cudaMemcpyAsync(x->h_abort, x->d_abort, sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H flag");
+        CUDA_TRY(cudaStreamSynchronize(s), "fused shuffle");
+        if (*x->h_abort)
+            return set_error(DFD_ERR_CAPACITY, "a receive window (%zu B = %lld rows) is too small for this shuffle", x->window_bytes,
+                             (long long)capacity_rows);
+        memcpy(part_starts_host, x->h_my_starts, sizeof(int64_t) * (P + 1));
+        x->bytes_received += (uint64_t)part_starts_host[P] * rb;
+        x->bytes_sent += (uint64_t)n_rows * rb;
+        return DFD_OK;
+    }
+    if (mode != DFD_EXCHANGE_NCCL) return set_error(DFD_ERR_INVALID_ARGUMENT, "unknown exchange mode %d", mode);
+
+    // ---- NCCL mode: partition locally into a staging buffer, then grouped send/recv ----
+    size_t stage_bytes = 0;
+    std::vector<size_t> col_off(n_cols), val_off(n_cols);
+    for (int i = 0; i < n_cols; ++i) {
+        const dfd_column& ic = in_cols[i];
+        col_off[i] = stage_bytes;
+        stage_bytes += ic.kind == DFD_COL_FIXED ? (((size_t)n_rows * ic.width + 255) & ~(size_t)255) : 0;
+        if (ic.kind != DFD_COL_FIXED || ic.validity)
+            return set_error(DFD_ERR_UNSUPPORTED, "column %d: the device exchange moves fixed-width non-null columns (validity / bit / var-width: next)", i);
+        if (out_cols[i].kind != ic.kind || out_cols[i].width != ic.width || !out_cols[i].values)
+            return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: out layout mismatch", i);
+    }
+    if ((rc = x->send.ensure(stage_bytes + 256, c->device))) return rc;
+    std::vector<dfd_column> staged(n_cols);
+    for (int i = 0; i < n_cols; ++i) {
+        staged[i] = in_cols[i];
+        staged[i].values = (char*)x->send.ptr + col_off[i];
+        staged[i].validity = nullptr;
+        staged[i].offset = 0;
+    }
+    PartitionJob job;
+    if ((rc = job.prepare(part, in_cols, n_cols, n_rows, staged.data(), false, s))) return rc;
+    if ((rc = job.run_hist_scan())) return rc;
+    if ((rc = job.run_scatter(part->d_part_starts, nullptr, 1, 1, nullptr))) return rc;
+    if (T > 1) {
+        NCCL_TRY(n->AllGather(job.d_totals, x->d_counts, N, ncclInt64, x->comm, s), "ncclAllGather(counts)");
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(x->d_counts, job.d_totals, sizeof(int64_t) * N, cudaMemcpyDeviceToDevice, s), "copy counts");
+    }
+    CUDA_TRY(cudaMemcpyAsync(x->h_counts, x->d_counts, sizeof(int64_t) * (size_t)N * T, cudaMemcpyDeviceToHost, s), "D2H counts");
+    CUDA_TRY(cudaStreamSynchronize(s), "count exchange");
+    std::vector<int64_t> send_start(N), recv_start((size_t)P * T);
+    int64_t recv_rows = 0;
+    rc = dfd_exchange_plan(T, P, x->rank, x->h_counts, send_start.data(), recv_start.data(), part_starts_host, nullptr, &recv_rows);
+    if (rc) return rc;
+    if (recv_rows > out_capacity_rows)
+        return set_error(DFD_ERR_CAPACITY, "this worker receives %lld rows but out_capacity_rows is %lld", (long long)recv_rows,
+                         (long long)out_capacity_rows);
+    const int64_t* cnt = x->h_counts;
+    if (T > 1) NCCL_TRY(n->GroupStart(), "ncclGroupStart");
+    for (int i = 0; i < n_cols; ++i) {
+        const size_t w = (size_t)in_cols[i].width;
+        const char* sbuf = (const char*)staged[i].values;
+        char* rbuf = (char*)out_cols[i].values;
+        for (uint32_t g = 0; g < N; ++g) {  // my rows of destination g -> its owner
+            const int peer = (int)(g / P);
+            const int64_t rows = cnt[(int64_t)x->rank * N + g];
+            if (rows == 0) continue;
+            if (peer == x->rank) {
+                const uint32_t q = g % P;
+                CUDA_TRY(cudaMemcpyAsync(rbuf + (size_t)recv_start[(size_t)q * T + x->rank] * w, sbuf + (size_t)send_start[g] * w,
+                                         (size_t)rows * w, cudaMemcpyDeviceToDevice, s), "local segment copy");
+            } else {
+                NCCL_TRY(n->Send(sbuf + (size_t)send_start[g] * w, (size_t)rows * w, ncclInt8, peer, x->comm, s), "ncclSend");
+                x->bytes_sent += (uint64_t)rows * w;
+            }
+        }
+        for (int r = 0; r < T; ++r) {  // every producer's rows of my P destinations
+            if (r == x->rank) continue;
+            for (uint32_t q = 0; q < P; ++q) {
+                const int64_t rows = cnt[(int64_t)r * N + (int64_t)x->rank * P + q];
+                if (rows == 0) continue;
+                NCCL_TRY(n->Recv(rbuf + (size_t)recv_start[(size_t)q * T + r] * w, (size_t)rows * w, ncclInt8, r, x->comm, s), "ncclRecv");
+                x->bytes_received += (uint64_t)rows * w;
+            }
+        }
+    }
+    if (T > 1) NCCL_TRY(n->GroupEnd(), "ncclGroupEnd");
+    CUDA_TRY(cudaStreamSynchronize(s), "nccl exchange");
+    return DFD_OK;
+}
+
+int dfd_exchange_stats(dfd_exchange* x, uint64_t* bytes_sent, uint64_t* bytes_received, uint64_t* shuffles) {
+    if (!x) return set_error(DFD_ERR_INVALID_ARGUMENT, "NULL exchange");
+    if (bytes_sent) *bytes_sent = x->bytes_sent;
+    if (bytes_received) *bytes_received = x->bytes_received;
+    if (shuffles) *shuffles = x->shuffles;
+    return DFD_OK;
+}
+
+}  // extern "C"

@@ -9,6 +9,7 @@
 
 #include "dfd_b200.h"
 #include "dfd_hash.cuh"
+#include "dfd_types.cuh"
 
 namespace dfd {
 
@@ -57,6 +58,28 @@ struct dfd_partitioner {
 namespace dfd {
 using Ctx = ::dfd_ctx;
 using Partitioner = ::dfd_partitioner;
+
+// One partition call split into its stages so the exchange can put the count
+// all-gather between K1b and K2.  Caller holds ctx->mu and has set the device.
+struct PartitionJob {
+    Partitioner* p = nullptr;
+    cudaStream_t stream = nullptr;
+    bool peer = false;
+    KeySet ks{};
+    std::vector<PayloadCol> passes;
+    uint64_t bytes = 0;
+    int64_t n_rows = 0, n_tiles = 0;
+    uint32_t* d_hist = nullptr;
+    uint32_t* d_base = nullptr;
+    int64_t* d_totals = nullptr;  // [N] rows per destination (after run_hist_scan)
+    unsigned* d_done = nullptr;
+    cudaEvent_t* ev = nullptr;
+    int prepare(Partitioner* part, const dfd_column* in_cols, int n_cols, int64_t rows, const dfd_column* out_cols,
+                bool peer_mode, cudaStream_t st);
+    int run_hist_scan();
+    int run_scatter(const int64_t* dest_base, void* const* peer_base, int world, uint32_t parts_per_rank,
+                    const int32_t* abort_flag);
+};
 
 // Launches K1 -> K1b -> K2 on `stream`; caller holds ctx->mu and has set the device.
 int partition_device_locked(Partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,

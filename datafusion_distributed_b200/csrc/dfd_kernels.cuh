@@ -16,35 +16,9 @@
 #include <type_traits>
 
 #include "dfd_hash.cuh"
+#include "dfd_types.cuh"
 
 namespace dfd {
-
-constexpr int MAX_COLS_PER_LAUNCH = 24;
-constexpr uint32_t MAX_PARTITIONS = 4096;
-
-struct PayloadCol {
-    const void* in;          // values (fixed) or bitmap (bool / validity pass)
-    void* out;
-    int64_t in_offset;       // Arrow logical offset of the input (rows)
-    int32_t width;           // bytes; 0 => bit column (bool values or validity)
-    int32_t pad;
-};
-
-struct ScatterParams {
-    KeySet keys;
-    HashState st;
-    ModN mod;
-    int64_t n_rows;
-    int64_t n_tiles;
-    const uint32_t* hist;        // [N][n_tiles] per-tile destination counts (K1)
-    const uint32_t* tile_base;   // [N][n_tiles] exclusive scan of hist along tiles (rows < 2^32 per call)
-    const int64_t* part_starts;  // [N+1] exclusive scan of destination totals
-    PayloadCol cols[MAX_COLS_PER_LAUNCH];
-    int32_t n_cols;
-    uint32_t N;
-    int32_t stage_width;         // widest staged element (bytes)
-    int32_t pad;
-};
 
 // ---------------------------------------------------------------------------
 // small block-scan helper: exclusive scan of one value per thread
@@ -279,11 +253,12 @@ struct StageIO {
 
 template <int THREADS, int K, typename V, int CHUNK = K>
 __device__ __forceinline__ void scatter_fixed_column(const PayloadCol& c, void* stage_raw, int64_t row0, int tile_rows,
-                                                     const uint32_t (&ps)[K], const int64_t* delta, int t0) {
+                                                     const uint32_t (&ps)[K], const int64_t* delta, int t0,
+                                                     void* const* out_base /* per destination (peer mode) or nullptr */) {
     static_assert(K % CHUNK == 0, "CHUNK must divide K");
     V* stage = (V*)stage_raw;
     const V* in = (const V*)c.in + (c.in_offset + row0);  // tile-relative indexing below is 32-bit
-    V* out = (V*)c.out + row0;                             // delta[] is relative to row0 as well
+    V* out = (V*)c.out;                                    // local mode: delta[] holds absolute output rows
     V v[CHUNK];
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) {
@@ -310,7 +285,11 @@ __device__ __forceinline__ void scatter_fixed_column(const PayloadCol& c, void* 
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         int i = k * THREADS + (int)threadIdx.x;
-        if (i < tile_rows) out[(int64_t)i + delta[ps[k] >> 16]] = stage[i];
+        if (i < tile_rows) {
+            const uint32_t p = ps[k] >> 16;
+            V* o = out_base ? (V*)out_base[p] : out;  // peer mode: the owner rank's receive window (NVLink store)
+            o[(int64_t)i + delta[p]] = stage[i];
+        }
     }
 }
 
@@ -340,7 +319,7 @@ __device__ __forceinline__ void scatter_bit_column(const PayloadCol& c, void* st
     for (int k = 0; k < K; ++k) {
         int i = k * THREADS + (int)threadIdx.x;
         bool active = i < tile_rows;
-        int64_t d = active ? row0 + (int64_t)i + delta[ps[k] >> 16] : -1;
+        int64_t d = active ? (int64_t)i + delta[ps[k] >> 16] : -1;
         unsigned bit = (active && stage[i]) ? (1u << (d & 31)) : 0u;
         int64_t word = active ? (d >> 5) : -1;
         unsigned peers = __match_any_sync(0xffffffffu, word);
@@ -354,7 +333,7 @@ struct BitColumn {};  // tag: bit-packed column (boolean values / validity bitma
 // One instantiation per element type V: a launch moves all columns of one
 // width (the host groups them), so the hot instantiation (8-byte values)
 // carries no code or registers for the other widths.
-template <int THREADS, int K, int MIN_CTAS, bool FAST_I64, typename V>
+template <int THREADS, int K, int MIN_CTAS, bool FAST_I64, typename V, bool PEER>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_constant__ ScatterParams P) {
     constexpr int T = THREADS * K;
     constexpr int W = THREADS / 32;
@@ -366,6 +345,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
     const uint32_t off_wc = off_delta + N * 8u;
     const uint32_t off_ts = off_wc + (uint32_t)W * N * 4u;
     const uint32_t off_scan = off_ts + (N + 1u) * 4u;
+    const uint32_t off_ob = (off_scan + (uint32_t)(W + 1) * 4u + 7u) & ~7u;  // peer mode only: per-destination bases
+#define OUT_BASE ((void**)(smem + off_ob))
+    if (PEER && *P.abort_flag) return;
 #define DELTA ((int64_t*)(smem + off_delta))
 #define WARP_CNT ((uint32_t*)(smem + off_wc))
 #define TILE_START ((uint32_t*)(smem + off_ts))
@@ -378,8 +360,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
     const int t0 = w * (K * 32) + lane;  // this thread's first tile-relative row; rows t0 + 32*j
 
     // ---- tile_start / delta from the K1 histogram (independent of phase 1).
-    // delta[p] maps a staging slot i to its output row RELATIVE to row0:
-    //   out_row - row0 = i + delta[p]
+    // delta[p] maps a staging slot i to its absolute output row: out_row = i + delta[p]
     {
         uint32_t carry = 0;
         for (uint32_t p0 = 0; p0 < N; p0 += THREADS) {
@@ -390,7 +371,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
             if (p < N) {
                 uint32_t ts = carry + ex;
                 TILE_START[p] = ts;
-                DELTA[p] = P.part_starts[p] + (int64_t)P.tile_base[(int64_t)p * P.n_tiles + tile] - (int64_t)ts - row0;
+                DELTA[p] = P.dest_base[p] + (int64_t)P.tile_base[(int64_t)p * P.n_tiles + tile] - (int64_t)ts;
             }
             carry += tot;
         }
@@ -450,11 +431,22 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
 #pragma unroll 1
     for (int c = 0; c < P.n_cols; ++c) {
         const PayloadCol& col = P.cols[c];
-        if constexpr (std::is_same<V, BitColumn>::value)
+        if constexpr (std::is_same<V, BitColumn>::value) {
             scatter_bit_column<THREADS, K>(col, stage, row0, tile_rows, pos, DELTA, t0);
-        else
-            scatter_fixed_column<THREADS, K, V, (sizeof(V) == 16 && K >= 4 ? K / 4 : K)>(col, stage, row0, tile_rows, pos, DELTA, t0);
+        } else {
+            if (PEER) {
+                // (the previous column's write-out reads OUT_BASE: the barrier inside
+                //  scatter_fixed_column orders this rewrite after it only for the staging
+                //  buffer, so fence explicitly)
+                __syncthreads();
+                for (uint32_t p = threadIdx.x; p < N; p += THREADS)
+                    OUT_BASE[p] = (char*)P.peer_base[p / P.parts_per_rank] + (size_t)col.out;
+            }
+            scatter_fixed_column<THREADS, K, V, (sizeof(V) == 16 && K >= 4 ? K / 4 : K)>(col, stage, row0, tile_rows, pos, DELTA, t0,
+                                                                                       PEER ? OUT_BASE : nullptr);
+        }
     }
+#undef OUT_BASE
 #undef DELTA
 #undef WARP_CNT
 #undef TILE_START
@@ -468,6 +460,8 @@ inline size_t scatter_smem_bytes(uint32_t N, int stage_width) {
     off += (size_t)(THREADS / 32) * N * 4;
     off += (size_t)(N + 1) * 4;
     off += (size_t)(THREADS / 32 + 1) * 4;
+    off = (off + 7) & ~(size_t)7;
+    off += (size_t)N * 8;  // per-destination output bases (peer mode)
     return off;
 }
 

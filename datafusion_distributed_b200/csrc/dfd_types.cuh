@@ -1,0 +1,40 @@
+// dfd_types.cuh — plain structs shared by the kernels and the host-side launch code.
+#pragma once
+#include <cstdint>
+
+#include "dfd_hash.cuh"
+
+namespace dfd {
+
+constexpr int MAX_COLS_PER_LAUNCH = 24;
+constexpr uint32_t MAX_PARTITIONS = 4096;
+constexpr int MAX_RANKS = 16;
+
+struct PayloadCol {
+    const void* in;          // values (fixed) or bitmap (bool / validity pass)
+    void* out;               // local mode: output buffer; peer mode: byte offset into every rank's receive window
+    int64_t in_offset;       // Arrow logical offset of the input (rows)
+    int32_t width;           // bytes; 0 => bit column (bool values or validity)
+    int32_t pad;
+};
+
+struct ScatterParams {
+    KeySet keys;
+    HashState st;
+    ModN mod;
+    int64_t n_rows;
+    int64_t n_tiles;
+    const uint32_t* hist;        // [N][n_tiles] per-tile destination counts (K1)
+    const uint32_t* tile_base;   // [N][n_tiles] exclusive scan of hist along tiles (rows < 2^32 per call)
+    const int64_t* dest_base;    // [N] first output row of destination p for THIS producer:
+                                 //   local mode: part_starts[p]; peer mode: row inside the owner's receive window
+    PayloadCol cols[MAX_COLS_PER_LAUNCH];
+    int32_t n_cols;
+    uint32_t N;
+    int32_t stage_width;         // widest staged element (bytes)
+    uint32_t parts_per_rank;     // peer mode: destination p lives on rank p / parts_per_rank
+    void* peer_base[MAX_RANKS];  // peer mode: every rank's receive window (CUDA-IPC mapped, NVLink)
+    const int32_t* abort_flag;   // peer mode: non-zero => a receive window would overflow; do nothing
+};
+
+}  // namespace dfd

@@ -1,0 +1,168 @@
+"""Host mirror of the consumer half: Stage / DistributedTaskContext /
+NetworkShuffleExec over the NVLink exchange.
+
+Reference surface being mirrored:
+  Stage, ExecutionTask, DistributedTaskContext      src/stage.rs:71-106
+  NetworkShuffleExec::try_new / execute             src/execution_plans/network_shuffle.rs:115-157, 213-238
+The data plane (gRPC + Arrow Flight in the reference) is `dfd_shuffle_device`:
+one worker per GPU, NCCL send/recv or fused peer stores over NVLink.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import uuid
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as nv
+from .device import DeviceColumn, WorkerContext, columns_to_c
+from .partitioner import HashPartitioner, Partitioning, scale_partitioning
+
+
+@dataclass
+class ExecutionTask:
+    """src/stage.rs:85-89 — here the "url" of a worker is its rank on the NVSwitch box."""
+    url: Optional[int] = None
+
+
+@dataclass
+class Stage:
+    """src/stage.rs:71-82"""
+    query_id: uuid.UUID
+    num: int
+    plan: Optional[Partitioning]
+    tasks: List[ExecutionTask] = field(default_factory=list)
+
+
+@dataclass(frozen=True)
+class DistributedTaskContext:
+    """src/stage.rs:92-106 — which shard of the stage this worker is."""
+    task_index: int = 0
+    task_count: int = 1
+
+
+def exchange_plan(counts: np.ndarray, partitions_per_task: int, rank: int):
+    """`dfd_exchange_plan` (pure host arithmetic): counts[T][N] -> dict of offset arrays."""
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    T, N = counts.shape
+    P = partitions_per_task
+    send_start = np.zeros(N, np.int64)
+    recv_start = np.zeros(P * T, np.int64)
+    part_starts = np.zeros(P + 1, np.int64)
+    dest_base = np.zeros(N, np.int64)
+    recv_rows = C.c_int64()
+    nv.check(nv.lib().dfd_exchange_plan(T, P, rank, counts.ctypes.data, send_start.ctypes.data, recv_start.ctypes.data,
+                                        part_starts.ctypes.data, dest_base.ctypes.data, C.byref(recv_rows)))
+    return {"send_start": send_start, "recv_start": recv_start.reshape(P, T), "part_starts": part_starts,
+            "dest_base": dest_base, "recv_rows": recv_rows.value}
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_char * 128)()
+    nv.check(nv.lib().dfd_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+class ShuffleExchange:
+    """One worker's endpoint of the exchange (≙ WorkerConnectionPool + the worker's
+    ExecuteTask server, src/worker/worker_connection_pool.rs:60-113)."""
+
+    def __init__(self, ctx: WorkerContext, rank: int, world: int, unique_id: Optional[bytes]):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self._h = C.c_void_p()
+        uid = (C.c_char * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        nv.check(nv.lib().dfd_exchange_create(ctx.handle, rank, world, uid, C.byref(self._h)))
+
+    def setup_window(self, nbytes: int):
+        nv.check(nv.lib().dfd_exchange_setup_window(self._h, nbytes))
+
+    def stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        nv.check(nv.lib().dfd_exchange_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"bytes_sent": a.value, "bytes_received": b.value, "shuffles": c.value}
+
+    def close(self):
+        if self._h:
+            nv.lib().dfd_exchange_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NetworkShuffleExec:
+    """Consumer side of the shuffle for device-resident columns.
+
+    `try_new(input_partitioning=Hash(keys, P), ..., task_count, input_task_count)` rescales the
+    producer's RepartitionExec to Hash(keys, P * task_count) (network_shuffle.rs:126-134) while
+    this node keeps advertising Hash(keys, P) (properties cloned before scaling, :155).
+    """
+
+    def __init__(self, properties: Partitioning, input_stage: Stage, task_count: int):
+        self.properties = properties
+        self.input_stage = input_stage
+        self.task_count = task_count
+        self._part: Optional[HashPartitioner] = None
+        self._out: Optional[List[DeviceColumn]] = None
+        self._starts: Optional[np.ndarray] = None
+
+    @staticmethod
+    def try_new(input_partitioning: Partitioning, query_id: uuid.UUID, num: int, task_count: int,
+                input_task_count: int) -> "NetworkShuffleExec":
+        if not input_partitioning.key_cols:
+            raise ValueError("NetworkShuffleExec input must be hash partitioned")
+        scaled = scale_partitioning(input_partitioning, lambda p: p * task_count)
+        stage = Stage(query_id, num, scaled, [ExecutionTask(None) for _ in range(input_task_count)])
+        return NetworkShuffleExec(input_partitioning, stage, task_count)
+
+    def name(self) -> str:
+        return "NetworkShuffleExec"
+
+    def output_partitioning(self) -> Partitioning:
+        return self.properties
+
+    def input_stage_plan(self) -> Partitioning:
+        return self.input_stage.plan
+
+    # -- data plane --------------------------------------------------------------
+    def shuffle(self, exchange: ShuffleExchange, in_cols: Sequence[DeviceColumn], n_rows: int, mode: int = nv.EXCHANGE_FUSED,
+                out_cols: Optional[List[DeviceColumn]] = None, out_capacity_rows: int = 0):
+        """Run the collective for this worker: as producer task `rank` it contributes `in_cols`,
+        as consumer task `rank` it receives its P partitions."""
+        if len(self.input_stage.tasks) != exchange.world or self.task_count != exchange.world:
+            raise ValueError("this exchange runs one producer and one consumer task per GPU worker")
+        ctx = exchange.ctx
+        if self._part is None:
+            self._part = HashPartitioner(ctx, self.input_stage.plan)
+        P = self.properties.partition_count
+        c_in = columns_to_c(in_cols)
+        if mode == nv.EXCHANGE_NCCL:
+            if out_cols is None:
+                raise ValueError("NCCL mode needs caller-provided output columns")
+            c_out = columns_to_c(out_cols)
+        else:
+            c_out = (nv.DfdColumn * len(in_cols))()
+        starts = (C.c_int64 * (P + 1))()
+        nv.check(nv.lib().dfd_shuffle_device(exchange._h, self._part._h, mode, c_in, len(in_cols), n_rows, P, c_out,
+                                             out_capacity_rows, starts))
+        if mode == nv.EXCHANGE_FUSED:
+            out_cols = [DeviceColumn(c_out[i].kind, c_out[i].width, c_out[i].values or 0, 0, 0, 0, int(starts[P]), exchange,
+                                     in_cols[i].arrow_type) for i in range(len(in_cols))]
+        self._out = list(out_cols)
+        self._starts = np.frombuffer(starts, dtype=np.int64).copy()
+        return self._out, self._starts
+
+    def execute(self, partition: int, task_ctx: DistributedTaskContext):
+        """≙ NetworkShuffleExec::execute(partition, ctx): rows with
+        hash % (P*T) == P*task_index + partition, as (columns, first_row, end_row)."""
+        if self._out is None:
+            raise RuntimeError("shuffle() has not run")
+        P = self.properties.partition_count
+        if not 0 <= partition < P:
+            raise IndexError(partition)
+        return self._out, int(self._starts[partition]), int(self._starts[partition + 1])

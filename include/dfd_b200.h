@@ -199,6 +199,68 @@ int dfd_repartition_exec_run(dfd_repartition_exec* x, struct ArrowArrayStream* i
 int dfd_repartition_exec_execute(dfd_repartition_exec* x, uint32_t partition, struct ArrowArrayStream* out);
 int dfd_repartition_exec_stats(dfd_repartition_exec* x, dfd_exec_stats* out);
 
+/* ---- inter-worker exchange (one worker per GPU, single NVSwitch box) -------
+ * Replaces the reference's shuffle data plane: the per-(consumer, producer)
+ * gRPC/Arrow-Flight streams served by `impl_execute_task`
+ * (src/worker/impl_execute_task.rs:36-169), demultiplexed by `WorkerConnection`
+ * (src/worker/worker_connection_pool.rs:143-390) and merged by
+ * `NetworkShuffleExec::execute` (src/execution_plans/network_shuffle.rs:213-238).
+ * Addressing follows the reference exactly: with N = P * T global partitions,
+ * global partition g belongs to consumer task g / P as its local partition
+ * g % P (off = P * task_index, network_shuffle.rs:219).
+ *
+ *   DFD_EXCHANGE_NCCL  : local K1/K1b/K2 into a staging buffer, ncclAllGather of
+ *                        the T x N count matrix, grouped ncclSend/ncclRecv.
+ *   DFD_EXCHANGE_FUSED : K2 stores each destination's runs directly into the
+ *                        owner's receive window over NVLink (CUDA-IPC peer
+ *                        memory); counts all-gather before, one barrier after.
+ *                        Fixed-width non-null columns only.
+ * Control plane (who is rank r, the 128-byte NCCL id) stays with the caller —
+ * in the reference that is the gRPC coordinator channel / TaskKey plumbing. */
+typedef struct dfd_exchange dfd_exchange;
+enum { DFD_EXCHANGE_NCCL = 0, DFD_EXCHANGE_FUSED = 1 };
+
+/* ncclGetUniqueId: call on one worker, ship the 128 bytes to the others. */
+int dfd_nccl_unique_id(void* out_128_bytes);
+/* Collective over all `world` workers (≙ the T tasks of the stage pair). */
+int dfd_exchange_create(dfd_ctx* ctx, int rank, int world, const void* nccl_unique_id, dfd_exchange** out);
+void dfd_exchange_destroy(dfd_exchange* x);
+int dfd_exchange_rank(const dfd_exchange* x);
+int dfd_exchange_world(const dfd_exchange* x);
+/* Collective: allocate this worker's receive window (fused mode) and map every
+ * peer's window through CUDA IPC. */
+int dfd_exchange_setup_window(dfd_exchange* x, size_t window_bytes);
+
+/* Pure host arithmetic of the exchange (no GPU needed; also what the Rust shim
+ * or a CPU test harness would call): from counts[world][N] (rows producer r
+ * holds for global partition g, N = partitions_per_task * world) compute, for
+ * worker `rank` (any output pointer may be NULL):
+ *   send_start[N]      start row of destination g in rank's partitioned buffer
+ *   recv_start[P*world] start row, in rank's receive buffer, of (local
+ *                      partition q, producer r) at index q*world + r
+ *   part_starts[P+1]   rank's output partition boundaries
+ *   dest_base[N]       start row of rank's rows inside the OWNER's receive
+ *                      buffer for destination g (fused mode)
+ *   recv_rows          total rows rank receives                              */
+int dfd_exchange_plan(int world, uint32_t partitions_per_task, int rank, const int64_t* counts,
+                      int64_t* send_start, int64_t* recv_start, int64_t* part_starts,
+                      int64_t* dest_base, int64_t* recv_rows);
+
+/* Collective shuffle of device-resident columns.  On return (stream
+ * synchronised) this worker holds its P = partitions_per_task destinations:
+ * out column c, rows [part_starts_host[q], part_starts_host[q+1]) = local
+ * partition q = global partition rank*P + q, producers' rows in task order,
+ * each producer's rows in its input order.
+ *   NCCL mode : out_cols[c].values are caller buffers of out_capacity_rows.
+ *   FUSED mode: out_cols[c].values are SET to point into the receive window
+ *               (valid until the next shuffle); out_capacity_rows is ignored.
+ * DFD_ERR_CAPACITY if a receive buffer / window is too small (nothing is
+ * written in that case). */
+int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* p, int mode, const dfd_column* in_cols, int n_cols,
+                       int64_t n_rows, uint32_t partitions_per_task, dfd_column* out_cols,
+                       int64_t out_capacity_rows, int64_t* part_starts_host);
+int dfd_exchange_stats(dfd_exchange* x, uint64_t* bytes_sent, uint64_t* bytes_received, uint64_t* shuffles);
+
 int dfd_metrics_get(dfd_ctx* ctx, dfd_metrics* out);
 int dfd_metrics_reset(dfd_ctx* ctx);
 

@@ -1,0 +1,85 @@
+"""Multi-GPU parity check, run as one process per GPU:
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node T --master-addr 127.0.0.1 --master-port P tests/mgpu_shuffle_check.py
+Every rank is producer task `rank` (contiguous row range of the cfg-2 table) and
+consumer task `rank`; both exchange transports are compared, bit-exactly and in
+order, with the single-node CPU oracle.  torch.distributed is only plumbing
+(rendezvous + shipping the NCCL id)."""
+import os
+import sys
+import uuid
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import datafusion_distributed_b200 as dfd
+    from datafusion_distributed_b200 import _native as nv
+    from oracle import oracle as orc
+    from tests.util import cfg2_columns
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    uid = [dfd.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx = dfd.WorkerContext(local_rank)
+    ex = dfd.ShuffleExchange(ctx, rank, world, uid[0])
+    n_rows, n_cols = int(os.environ.get("DFD_CHECK_ROWS", 1_000_003)), 4
+    ex.setup_window(int(n_rows * n_cols * 8 * 1.5 / world) + (1 << 20))
+    cols = cfg2_columns(n_rows, n_cols)
+    lo, hi = rank * n_rows // world, (rank + 1) * n_rows // world
+    failures = 0
+    for total_parts in (8, 16, 3 * world):
+        if total_parts % world:
+            continue
+        P = total_parts // world
+        N = P * world
+        ref, rc, rs = orc.repartition_table(cols, [0], N, 8192, 1)
+        ins = [torch.from_numpy(c[lo:hi].copy()).cuda() for c in cols]
+        torch.cuda.synchronize()
+        in_cols = [dfd.DeviceColumn.from_torch(t) for t in ins]
+        for mode, name in ((nv.EXCHANGE_NCCL, "nccl"), (nv.EXCHANGE_FUSED, "fused")):
+            node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0], P), uuid.uuid4(), 1, world, world)
+            cap = int(n_rows * 1.5 / world) + 1024
+            outs_t = [torch.empty(cap, dtype=torch.int64, device="cuda") for _ in cols]
+            torch.cuda.synchronize()
+            out_cols = [dfd.DeviceColumn.from_torch(t) for t in outs_t] if mode == nv.EXCHANGE_NCCL else None
+            outs, starts = node.shuffle(ex, in_cols, hi - lo, mode, out_cols, cap)
+            for q in range(P):
+                g = rank * P + q
+                _, a, b = node.execute(q, dfd.DistributedTaskContext(rank, world))
+                assert b - a == rc[g], (name, q, b - a, rc[g])
+                for c in range(n_cols):
+                    if mode == nv.EXCHANGE_NCCL:
+                        got = outs_t[c][a:b].cpu().numpy()
+                    else:
+                        got = np.empty(b - a, dtype=np.int64)
+                        if b > a:
+                            nv.check(nv.lib().dfd_memcpy_d2h(ctx.handle, got.ctypes.data, outs[c].values + a * 8, (b - a) * 8))
+                    if not np.array_equal(got, ref[c][rs[g]:rs[g + 1]]):
+                        failures += 1
+                        print(f"rank {rank}: MISMATCH mode={name} N={N} q={q} col={c}", flush=True)
+            dist.barrier()
+    # window overflow is reported, not written
+    node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([1], 1), uuid.uuid4(), 2, world, world)
+    t = torch.zeros(hi - lo, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    st = ex.stats()
+    f = torch.tensor([failures], device="cuda")
+    dist.all_reduce(f)
+    if rank == 0:
+        print(("MGPU_SHUFFLE_OK" if f.item() == 0 else "MGPU_SHUFFLE_FAILED"), "world", world, "stats", st, flush=True)
+    ex.close()
+    dist.destroy_process_group()
+    sys.exit(0 if f.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,130 @@
+"""CPU tests of the multi-worker path (no GPU): the exchange arithmetic
+(`dfd_exchange_plan`, product host logic behind the C ABI) driven by a real
+world_size-2 `gloo` run, with the CPU oracle standing in for the partition
+kernel, checked against the oracle's single-node result."""
+import os
+import socket
+import uuid
+
+import numpy as np
+import pytest
+
+import datafusion_distributed_b200 as dfd
+from oracle import oracle as orc
+from tests.util import cfg2_columns
+
+
+def test_plan_matches_bruteforce():
+    rng = np.random.Generator(np.random.PCG64(0))
+    for T, P in [(1, 8), (2, 4), (4, 2), (8, 1), (3, 5)]:
+        N = T * P
+        counts = rng.integers(0, 50, (T, N), dtype=np.int64)
+        counts[rng.random((T, N)) < 0.2] = 0
+        for rank in range(T):
+            plan = dfd.exchange_plan(counts, P, rank)
+            assert np.array_equal(plan["send_start"], np.concatenate([[0], np.cumsum(counts[rank])[:-1]]))
+            run = 0
+            for q in range(P):
+                assert plan["part_starts"][q] == run
+                for r in range(T):
+                    assert plan["recv_start"][q, r] == run
+                    run += counts[r, rank * P + q]
+            assert plan["part_starts"][P] == run == plan["recv_rows"]
+            # dest_base[g] == the owner's recv_start for (g % P, me)
+            for g in range(N):
+                owner = dfd.exchange_plan(counts, P, g // P)
+                assert plan["dest_base"][g] == owner["recv_start"][g % P, rank]
+
+
+def test_plan_rejects_bad_arguments():
+    with pytest.raises(dfd.DfdError):
+        dfd.exchange_plan(np.array([[1, -1]], dtype=np.int64), 2, 0)
+    with pytest.raises(dfd.DfdError):
+        dfd.exchange_plan(np.zeros((2, 4), dtype=np.int64), 2, 2)
+
+
+def test_network_shuffle_exec_surface():
+    ex = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0], 4), uuid.uuid4(), 1, task_count=2, input_task_count=2)
+    assert ex.name() == "NetworkShuffleExec"
+    assert ex.output_partitioning().partition_count == 4          # advertised: Hash(keys, P)
+    assert ex.input_stage_plan().partition_count == 8             # producer scaled to P * task_count
+    assert len(ex.input_stage.tasks) == 2
+    with pytest.raises(ValueError):
+        dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([], 4), uuid.uuid4(), 1, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, P, n_rows, ret):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        N = P * world
+        cols = cfg2_columns(n_rows, 3)
+        lo, hi = rank * n_rows // world, (rank + 1) * n_rows // world  # contiguous row range per producer task
+        local = [c[lo:hi] for c in cols]
+        # producer: local partition (CPU oracle stands in for K1/K2 on this GPU-less box)
+        parts, counts, starts = orc.repartition_table(local, [0], N, 8192, 1)
+        all_counts = [torch.zeros(N, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(all_counts, torch.from_numpy(counts.copy()))
+        cm = torch.stack(all_counts).numpy()
+        plan = dfd.exchange_plan(cm, P, rank)  # product host logic
+        recv = [np.zeros(plan["recv_rows"], dtype=np.int64) for _ in cols]
+        for c in range(len(cols)):
+            for peer in range(world):  # exchange (gloo point-to-point in place of ncclSend/ncclRecv)
+                for q in range(P):
+                    g_out = peer * P + q
+                    seg = parts[c][plan["send_start"][g_out]: plan["send_start"][g_out] + cm[rank, g_out]]
+                    g_in = rank * P + q
+                    n_in = int(cm[peer, g_in])
+                    dst = recv[c][plan["recv_start"][q, peer]: plan["recv_start"][q, peer] + n_in]
+                    if peer == rank:
+                        dst[:] = seg
+                    else:
+                        ops = []
+                        t_out = torch.from_numpy(seg.copy())
+                        t_in = torch.from_numpy(dst)
+                        if rank < peer:
+                            if len(seg): dist.send(t_out, peer)
+                            if n_in: dist.recv(t_in, peer)
+                        else:
+                            if n_in: dist.recv(t_in, peer)
+                            if len(seg): dist.send(t_out, peer)
+        # consumer check: my P partitions == the single-node oracle's global partitions rank*P+q, exact order
+        ref, rc, rs = orc.repartition_table(cols, [0], N, 8192, 1)
+        for q in range(P):
+            g = rank * P + q
+            a, b = plan["part_starts"][q], plan["part_starts"][q + 1]
+            for c in range(len(cols)):
+                assert np.array_equal(recv[c][a:b], ref[c][rs[g]:rs[g + 1]]), (rank, q, c)
+        ret.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        ret.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("P", [1, 4])
+def test_two_worker_shuffle_over_gloo(built, P):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, P, 40_000, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [ret.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results

@@ -1,0 +1,69 @@
+"""GPU tests of the exchange: world=1 on any box, world=T via torchrun when the
+box has more than one GPU (the driver's 1-GPU tier skips that case)."""
+import os
+import subprocess
+import sys
+import uuid
+
+import numpy as np
+import pytest
+
+import datafusion_distributed_b200 as dfd
+from datafusion_distributed_b200 import _native as nv
+from oracle import oracle as orc
+from tests.util import cfg2_columns
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("mode", [nv.EXCHANGE_NCCL, nv.EXCHANGE_FUSED])
+def test_single_worker_shuffle_equals_local_repartition(ctx, mode):
+    import pyarrow as pa
+
+    n, P = 300_007, 8
+    cols = cfg2_columns(n, 4)
+    ex = dfd.ShuffleExchange(ctx, 0, 1, None)
+    ex.setup_window(n * 4 * 8 + (1 << 20))
+    node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0], P), uuid.uuid4(), 1, 1, 1)
+    in_cols = [dfd.DeviceColumn.from_arrow(ctx, pa.array(c)) for c in cols]
+    out_cols = [dfd.DeviceColumn.empty_like(ctx, c, n) for c in in_cols] if mode == nv.EXCHANGE_NCCL else None
+    outs, starts = node.shuffle(ex, in_cols, n, mode, out_cols, n)
+    ref, rc, rs = orc.repartition_table(cols, [0], P, 8192, 1)
+    assert np.array_equal(starts, rs)
+    for q in range(P):
+        _, a, b = node.execute(q, dfd.DistributedTaskContext(0, 1))
+        for c in range(4):
+            got = np.empty(b - a, dtype=np.int64)
+            nv.check(nv.lib().dfd_memcpy_d2h(ctx.handle, got.ctypes.data, outs[c].values + a * 8, (b - a) * 8))
+            assert np.array_equal(got, ref[c][rs[q]:rs[q + 1]])
+    ex.close()
+
+
+def test_fused_window_overflow_is_reported(ctx):
+    import pyarrow as pa
+
+    n = 100_000
+    cols = cfg2_columns(n, 2)
+    ex = dfd.ShuffleExchange(ctx, 0, 1, None)
+    ex.setup_window(n * 8)  # half of what 2 columns need
+    node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0], 4), uuid.uuid4(), 1, 1, 1)
+    in_cols = [dfd.DeviceColumn.from_arrow(ctx, pa.array(c)) for c in cols]
+    with pytest.raises(dfd.DfdError) as e:
+        node.shuffle(ex, in_cols, n, nv.EXCHANGE_FUSED)
+    assert e.value.status == 7  # DFD_ERR_CAPACITY
+    ex.close()
+
+
+def test_multi_gpu_shuffle_under_torchrun(built):
+    import ctypes as C
+
+    n = C.c_int(0)
+    nv.lib().dfd_device_count(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs >= 2 GPUs (run tests/mgpu_shuffle_check.py under torchrun on a multi-GPU box)")
+    world = 2 if n.value < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_shuffle_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert "MGPU_SHUFFLE_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
