@@ -193,6 +193,124 @@ def run_e2e(ctx, dfd, n, args):
             "api": "RepartitionExec.push_batch/finish/execute(partition) over dfd_repartition_exec_* (Arrow C Data / C Stream)"}
 
 
+NVLINK_PEAK_GBS = 770.0  # measured peer copy per direction per GPU on this pool (B200_PROFILING.md; nominal 900)
+
+
+def run_multi_gpu(args, torch, dfd, world):
+    """N workers = N GPUs of one NVSwitch box, one rank per GPU.  Strong scaling: the 2^26-row
+    table is split into `world` contiguous row ranges (producer tasks); N = 8 global partitions,
+    P = 8/world per consumer task.  One step = hist + count all-gather + fused peer-store scatter
+    (or NCCL send/recv) + barrier.  Timed with CUDA events on the library stream, max over ranks."""
+    import uuid
+
+    import torch.distributed as dist
+
+    from datafusion_distributed_b200 import _native as nv
+
+    rank = int(os.environ["RANK"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_total = args.rows
+    total_parts = NUM_PARTITIONS if NUM_PARTITIONS % world == 0 else NUM_PARTITIONS * world
+    P = total_parts // world
+    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    n = hi - lo
+    g = torch.Generator(device="cuda").manual_seed(42 + rank)
+    key = torch.randint(-(2**63), 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+    rid = torch.arange(lo, hi, dtype=torch.int64, device="cuda")
+    ins = [key] + [rid * 8 + j for j in range(1, N_COLS)]
+    del rid
+    cap = int(n * 1.25) + 4096
+    torch.cuda.synchronize()
+    uid = [dfd.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx = dfd.WorkerContext(local_rank)
+    ex = dfd.ShuffleExchange(ctx, rank, world, uid[0])
+    mode = nv.EXCHANGE_FUSED if args.exchange == "fused" else nv.EXCHANGE_NCCL
+    ex.setup_window(cap * N_COLS * WIDTH)
+    outs_t = [torch.empty(cap, dtype=torch.int64, device="cuda") for _ in range(N_COLS)] if mode == nv.EXCHANGE_NCCL else None
+    torch.cuda.synchronize()
+    in_cols = [dfd.DeviceColumn.from_torch(t) for t in ins]
+    out_cols = [dfd.DeviceColumn.from_torch(t) for t in outs_t] if outs_t else None
+    node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0], P), uuid.uuid4(), 1, world, world)
+
+    def step():
+        return node.shuffle(ex, in_cols, n, mode, out_cols, cap)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ctx.reset_metrics()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ctx.synchronize()
+    with ClockSampler(local_rank) as clocks:
+        ctx.timer_start()
+        for _ in range(args.steps):
+            outs, starts = step()
+        ms_local = ctx.timer_stop()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = t.item() / args.steps
+    recv_rows = torch.tensor([int(starts[-1])], dtype=torch.int64, device="cuda")
+    dist.all_reduce(recv_rows)
+    assert recv_rows.item() == n_total, (recv_rows.item(), n_total)
+    launches = torch.tensor([int(ctx.metrics()["kernel_launches"])], dtype=torch.int64, device="cuda")
+    dist.all_reduce(launches)
+
+    # e2e: host (pinned) rows in, host rows out, per worker: H2D local rows -> shuffle -> D2H my partitions
+    e2e = None
+    if not args.no_e2e:
+        pt_in = dfd.PinnedTable(ctx, n, [np.int64] * N_COLS)
+        pt_out = dfd.PinnedTable(ctx, cap, [np.int64] * N_COLS)
+        for j in range(N_COLS):
+            nv.check(nv.lib().dfd_memcpy_d2h(ctx.handle, pt_in.columns[j].ctypes.data, ins[j].data_ptr(), n * WIDTH))
+        e2e_times = []
+        for it in range(2 + max(1, args.steps // 2)):
+            dist.barrier()
+            t0 = time.perf_counter()
+            for j in range(N_COLS):
+                nv.check(nv.lib().dfd_memcpy_h2d(ctx.handle, ins[j].data_ptr(), pt_in.columns[j].ctypes.data, n * WIDTH))
+            o, st = step()
+            got = int(st[-1])
+            for j in range(N_COLS):
+                nv.check(nv.lib().dfd_memcpy_d2h(ctx.handle, pt_out.columns[j].ctypes.data, o[j].values, got * WIDTH))
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            if it >= 2:
+                e2e_times.append(dt.item())
+        e2e_s = sum(e2e_times) / len(e2e_times)
+        tot = torch.tensor([n * N_COLS * WIDTH, got * N_COLS * WIDTH], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tot)
+        e2e = {"value": n_total / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": int(tot[0].item()), "d2h_bytes_per_step": int(tot[1].item()),
+               "ms_per_step": e2e_s * 1e3, "steps": len(e2e_times),
+               "api": "per worker: dfd_memcpy_h2d(local rows) -> dfd_shuffle_device -> dfd_memcpy_d2h(received partitions); wall clock, max over ranks"}
+        pt_in.close()
+        pt_out.close()
+    if rank == 0:
+        alg = N_COLS * WIDTH * n * (world - 1) / world  # bytes each GPU must push through NVLink per direction
+        achieved = alg / (ms_per_step / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": n_total / (ms_per_step / 1e3), "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": f"cfg2: 2^26 rows x 8 Int64 split over {world} producer tasks, Hash([col0], {total_parts}), "
+                                   f"{P} partitions per consumer task, device-resident", "rows": n_total, "columns": N_COLS,
+                       "num_partitions": total_parts, "exchange": args.exchange,
+                       "l2": f"per-GPU inputs+window ({2 * n * N_COLS * WIDTH >> 20} MiB) > L2, no flush"},
+            "roofline": {"bound": "nvlink", "kernel": "k_scatter<PEER> (fused hash->rank->peer store)" if args.exchange == "fused" else "ncclSend/Recv",
+                         "achieved": achieved, "peak": NVLINK_PEAK_GBS, "unit": "GB/s", "frac": achieved / NVLINK_PEAK_GBS,
+                         "peak_source": "measured peer copy per direction (B200_PROFILING.md); nominal 900", "traffic": None,
+                         "algorithmic_bytes_per_gpu_per_direction": alg},
+            "gpu_launches": int(launches.item()), "clocks": clocks.summary(), "e2e": e2e,
+        }
+        print(json.dumps(line))
+    ex.close()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,7 +321,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-batch-rows", type=int, default=1 << 20)
-    ap.add_argument("--e2e-chunk-rows", type=int, default=1 << 22)
+    ap.add_argument("--e2e-chunk-rows", type=int, default=1 << 20)
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -213,8 +332,10 @@ def main():
     import datafusion_distributed_b200 as dfd
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world != 1 or args.gpus != 1:
-        raise SystemExit("multi-GPU exchange bench not wired yet")
+    if world > 1:
+        return run_multi_gpu(args, torch, dfd, world)
+    if args.gpus != 1:
+        raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     dev = 0
     torch.cuda.set_device(dev)
     n = args.rows
