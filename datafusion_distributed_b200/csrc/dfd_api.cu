@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -49,6 +50,9 @@ int cuda_error(cudaError_t e, const char* what) {
 constexpr int TILE_THREADS = DFD_TILE_THREADS;
 constexpr int TILE_K = DFD_TILE_K;
 constexpr int TILE_MIN_CTAS = DFD_TILE_MIN_CTAS;
+// aligned write-out (see k_scatter): used when N <= ALIGNED_MAX_N; each run wastes < 62 virtual slots
+constexpr uint32_t ALIGNED_MAX_N = 16;
+constexpr int TILE_KV = TILE_K + (62 * (int)ALIGNED_MAX_N + TILE_THREADS - 1) / TILE_THREADS;
 constexpr int TILE_ROWS = TILE_THREADS * TILE_K;
 
 int Scratch::ensure(size_t need, int device) {
@@ -130,9 +134,9 @@ static int build_keyset(const dfd_partitioner* p, const dfd_column* cols, int n_
         if (_e != cudaSuccess) return cuda_error(_e, what);            \
     }
 
-template <bool FAST, typename V, bool PEER>
-static int launch_scatter_t(const ScatterParams& sp, unsigned grid, size_t smem, cudaStream_t stream) {
-    auto kern = k_scatter<TILE_THREADS, TILE_K, TILE_MIN_CTAS, FAST, V, PEER>;
+template <bool FAST, typename V, bool PEER, int KV>
+static int launch_scatter_kv(const ScatterParams& sp, unsigned grid, size_t smem, cudaStream_t stream) {
+    auto kern = k_scatter<TILE_THREADS, TILE_K, KV, TILE_MIN_CTAS, FAST, V, PEER>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(k_scatter)");
@@ -140,6 +144,17 @@ static int launch_scatter_t(const ScatterParams& sp, unsigned grid, size_t smem,
     kern<<<grid, TILE_THREADS, smem, stream>>>(sp);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DFD_OK : cuda_error(e, "k_scatter");
+}
+
+static bool use_aligned(uint32_t N) {
+    static const bool enabled = [] { const char* e = getenv("DFD_ALIGNED_WRITEOUT"); return !e || atoi(e) != 0; }();
+    return enabled && N <= ALIGNED_MAX_N;
+}
+
+template <bool FAST, typename V, bool PEER>
+static int launch_scatter_t(const ScatterParams& sp, unsigned grid, size_t smem, cudaStream_t stream) {
+    if (use_aligned(sp.N)) return launch_scatter_kv<FAST, V, PEER, TILE_KV>(sp, grid, smem, stream);
+    return launch_scatter_kv<FAST, V, PEER, TILE_K>(sp, grid, smem, stream);
 }
 
 template <bool FAST, bool PEER>

@@ -251,10 +251,12 @@ struct StageIO {
     static __device__ __forceinline__ V ld(const void* base, int64_t i) { return ((const V*)base)[i]; }
 };
 
-template <int THREADS, int K, typename V, int CHUNK = K>
+constexpr uint32_t SLOT_NONE = 0xffffffffu;
+
+template <int THREADS, int K, int KV, typename V, int CHUNK = K>
 __device__ __forceinline__ void scatter_fixed_column(const PayloadCol& c, void* stage_raw, int64_t row0, int tile_rows,
-                                                     const uint32_t (&ps)[K], const int64_t* delta, int t0,
-                                                     void* const* out_base /* per destination (peer mode) or nullptr */) {
+                                                     const uint32_t (&ps)[K], const uint32_t (&slot)[KV], const int64_t* delta,
+                                                     int t0, void* const* out_base /* per destination (peer mode) or nullptr */) {
     static_assert(K % CHUNK == 0, "CHUNK must divide K");
     V* stage = (V*)stage_raw;
     const V* in = (const V*)c.in + (c.in_offset + row0);  // tile-relative indexing below is 32-bit
@@ -278,15 +280,14 @@ __device__ __forceinline__ void scatter_fixed_column(const PayloadCol& c, void* 
 #pragma unroll
         for (int j = 0; j < CHUNK; ++j) {
             int t = t0 + (ch * CHUNK + j) * 32;
-            if (t < tile_rows) stage[ps[ch * CHUNK + j] & 0xffffu] = v[j];
+            if (t < tile_rows) stage[ps[ch * CHUNK + j]] = v[j];
         }
     }
     __syncthreads();  // staging buffer holds the tile in destination order
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        int i = k * THREADS + (int)threadIdx.x;
-        if (i < tile_rows) {
-            const uint32_t p = ps[k] >> 16;
+    for (int k = 0; k < KV; ++k) {
+        if (slot[k] != SLOT_NONE) {
+            const uint32_t i = slot[k] & 0xffffu, p = slot[k] >> 16;
             V* o = out_base ? (V*)out_base[p] : out;  // peer mode: the owner rank's receive window (NVLink store)
             o[(int64_t)i + delta[p]] = stage[i];
         }
@@ -295,9 +296,9 @@ __device__ __forceinline__ void scatter_fixed_column(const PayloadCol& c, void* 
 
 // bit column (boolean values or a validity bitmap): staged as one byte per row,
 // written back with warp-aggregated atomicOr on 32-bit output words.
-template <int THREADS, int K>
+template <int THREADS, int K, int KV>
 __device__ __forceinline__ void scatter_bit_column(const PayloadCol& c, void* stage_raw, int64_t row0, int tile_rows,
-                                                   const uint32_t (&ps)[K], const int64_t* delta, int t0) {
+                                                   const uint32_t (&ps)[K], const uint32_t (&slot)[KV], const int64_t* delta, int t0) {
     uint8_t* stage = (uint8_t*)stage_raw;
     const uint8_t* in = (const uint8_t*)c.in;
     unsigned* out = (unsigned*)c.out;
@@ -312,14 +313,14 @@ __device__ __forceinline__ void scatter_bit_column(const PayloadCol& c, void* st
 #pragma unroll
     for (int j = 0; j < K; ++j) {
         int t = t0 + j * 32;
-        if (t < tile_rows) stage[ps[j] & 0xffffu] = v[j];
+        if (t < tile_rows) stage[ps[j]] = v[j];
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        int i = k * THREADS + (int)threadIdx.x;
-        bool active = i < tile_rows;
-        int64_t d = active ? (int64_t)i + delta[ps[k] >> 16] : -1;
+    for (int k = 0; k < KV; ++k) {
+        const bool active = slot[k] != SLOT_NONE;
+        const uint32_t i = slot[k] & 0xffffu;
+        int64_t d = active ? (int64_t)i + delta[slot[k] >> 16] : -1;
         unsigned bit = (active && stage[i]) ? (1u << (d & 31)) : 0u;
         int64_t word = active ? (d >> 5) : -1;
         unsigned peers = __match_any_sync(0xffffffffu, word);
@@ -333,7 +334,12 @@ struct BitColumn {};  // tag: bit-packed column (boolean values / validity bitma
 // One instantiation per element type V: a launch moves all columns of one
 // width (the host groups them), so the hot instantiation (8-byte values)
 // carries no code or registers for the other widths.
-template <int THREADS, int K, int MIN_CTAS, bool FAST_I64, typename V, bool PEER>
+// KV: write-out iterations per thread.  KV == K: staging slots are written out
+// linearly.  KV > K ("aligned" mode, small N): the write-out walks a virtual slot
+// space in which every destination's run is shifted so that each warp's 32 rows
+// start on a 32-row (256 B for 8-byte values) boundary of the OUTPUT buffer —
+// full-line stores to HBM and full-size write packets over NVLink.
+template <int THREADS, int K, int KV, int MIN_CTAS, bool FAST_I64, typename V, bool PEER>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_constant__ ScatterParams P) {
     constexpr int T = THREADS * K;
     constexpr int W = THREADS / 32;
@@ -346,7 +352,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
     const uint32_t off_ts = off_wc + (uint32_t)W * N * 4u;
     const uint32_t off_scan = off_ts + (N + 1u) * 4u;
     const uint32_t off_ob = (off_scan + (uint32_t)(W + 1) * 4u + 7u) & ~7u;  // peer mode only: per-destination bases
+    const uint32_t off_vs = off_ob + N * 8u;                                // aligned mode only: virtual run starts
 #define OUT_BASE ((void**)(smem + off_ob))
+#define VSTART ((uint32_t*)(smem + off_vs))
     if (PEER && *P.abort_flag) return;
 #define DELTA ((int64_t*)(smem + off_delta))
 #define WARP_CNT ((uint32_t*)(smem + off_wc))
@@ -414,17 +422,57 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
         uint32_t d = pos[j] >> 16;
         pos[j] = d < N ? wc[d] + (pos[j] & 0xffffu) : 0;
     }
-    // ---- destination of every staging slot this thread will write out
-    // (packed into the high half of pos[]: pos[k] = staging position | slot destination << 16)
+    // ---- which staging slot (and destination) each of this thread's write-out iterations handles
+    uint32_t slot[KV];
+    if constexpr (KV == K) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        uint32_t i = k * THREADS + threadIdx.x;
-        uint32_t lo = 0, hi = N;  // last p with tile_start[p] <= i
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (TILE_START[mid] <= i) lo = mid; else hi = mid;
+        for (int k = 0; k < K; ++k) {
+            uint32_t i = k * THREADS + threadIdx.x;
+            uint32_t lo = 0, hi = N;  // last p with tile_start[p] <= i
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (TILE_START[mid] <= i) lo = mid; else hi = mid;
+            }
+            slot[k] = i < (uint32_t)tile_rows ? (i | (lo << 16)) : SLOT_NONE;
         }
-        pos[k] |= lo << 16;
+    } else {
+        // virtual run of destination p: [VSTART[p], VSTART[p+1]) = m_p leading pad + its rows, rounded up to 32,
+        // where m_p = (first output row of the run) mod 32
+        {
+            uint32_t carry = 0;
+            for (uint32_t p0 = 0; p0 < N; p0 += THREADS) {
+                uint32_t p = p0 + threadIdx.x;
+                uint32_t len = 0;
+                if (p < N) {
+                    uint32_t ts = TILE_START[p], cnt = TILE_START[p + 1] - ts;
+                    uint32_t m = (uint32_t)((int64_t)ts + DELTA[p]) & 31u;
+                    len = cnt ? (m + cnt + 31u) & ~31u : 0u;
+                }
+                uint32_t tot;
+                uint32_t ex = block_exclusive_scan<THREADS>(len, S_SCAN, tot);
+                if (p < N) VSTART[p] = carry + ex;
+                carry += tot;
+            }
+            if (threadIdx.x == 0) VSTART[N] = carry;
+            __syncthreads();
+        }
+        const uint32_t vtotal = VSTART[N];
+#pragma unroll
+        for (int k = 0; k < KV; ++k) {
+            uint32_t vs = k * THREADS + threadIdx.x;
+            slot[k] = SLOT_NONE;
+            if (vs < vtotal) {
+                uint32_t lo = 0, hi = N;  // last p with VSTART[p] <= vs
+                while (hi - lo > 1) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (VSTART[mid] <= vs) lo = mid; else hi = mid;
+                }
+                uint32_t ts = TILE_START[lo], cnt = TILE_START[lo + 1] - ts;
+                uint32_t m = (uint32_t)((int64_t)ts + DELTA[lo]) & 31u;
+                uint32_t off = vs - VSTART[lo] - m;  // wraps for the leading pad
+                if (off < cnt) slot[k] = (ts + off) | (lo << 16);
+            }
+        }
     }
 
     // ---- phase 2: every column through the staging buffer
@@ -432,7 +480,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
     for (int c = 0; c < P.n_cols; ++c) {
         const PayloadCol& col = P.cols[c];
         if constexpr (std::is_same<V, BitColumn>::value) {
-            scatter_bit_column<THREADS, K>(col, stage, row0, tile_rows, pos, DELTA, t0);
+            scatter_bit_column<THREADS, K, KV>(col, stage, row0, tile_rows, pos, slot, DELTA, t0);
         } else {
             if (PEER) {
                 // (the previous column's write-out reads OUT_BASE: the barrier inside
@@ -442,11 +490,12 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
                 for (uint32_t p = threadIdx.x; p < N; p += THREADS)
                     OUT_BASE[p] = (char*)P.peer_base[p / P.parts_per_rank] + (size_t)col.out;
             }
-            scatter_fixed_column<THREADS, K, V, (sizeof(V) == 16 && K >= 4 ? K / 4 : K)>(col, stage, row0, tile_rows, pos, DELTA, t0,
-                                                                                       PEER ? OUT_BASE : nullptr);
+            scatter_fixed_column<THREADS, K, KV, V, (sizeof(V) == 16 && K % 2 == 0 ? K / 2 : K)>(col, stage, row0, tile_rows, pos, slot, DELTA, t0,
+                                                                                           PEER ? OUT_BASE : nullptr);
         }
     }
 #undef OUT_BASE
+#undef VSTART
 #undef DELTA
 #undef WARP_CNT
 #undef TILE_START
@@ -462,6 +511,7 @@ inline size_t scatter_smem_bytes(uint32_t N, int stage_width) {
     off += (size_t)(THREADS / 32 + 1) * 4;
     off = (off + 7) & ~(size_t)7;
     off += (size_t)N * 8;  // per-destination output bases (peer mode)
+    off += (size_t)(N + 1) * 4;  // virtual run starts (aligned mode)
     return off;
 }
 
