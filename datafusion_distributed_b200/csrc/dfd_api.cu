@@ -146,14 +146,18 @@ static int launch_scatter_kv(const ScatterParams& sp, unsigned grid, size_t smem
     return e == cudaSuccess ? DFD_OK : cuda_error(e, "k_scatter");
 }
 
-static bool use_aligned(uint32_t N) {
-    static const bool enabled = [] { const char* e = getenv("DFD_ALIGNED_WRITEOUT"); return !e || atoi(e) != 0; }();
-    return enabled && N <= ALIGNED_MAX_N;
+// Measured on B200 (profiles/): aligned write-out costs ~5% on local HBM stores (more write-out
+// iterations, L2 already merges partial lines) but gains ~15% on NVLink peer stores (full-size
+// write packets), so it is on for the fused exchange only.  DFD_ALIGNED_WRITEOUT=0/1 forces it.
+static bool use_aligned(uint32_t N, bool peer) {
+    static const int forced = [] { const char* e = getenv("DFD_ALIGNED_WRITEOUT"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+    if (N > ALIGNED_MAX_N) return false;
+    return forced >= 0 ? forced == 1 : peer;
 }
 
 template <bool FAST, typename V, bool PEER>
 static int launch_scatter_t(const ScatterParams& sp, unsigned grid, size_t smem, cudaStream_t stream) {
-    if (use_aligned(sp.N)) return launch_scatter_kv<FAST, V, PEER, TILE_KV>(sp, grid, smem, stream);
+    if (use_aligned(sp.N, PEER)) return launch_scatter_kv<FAST, V, PEER, TILE_KV>(sp, grid, smem, stream);
     return launch_scatter_kv<FAST, V, PEER, TILE_K>(sp, grid, smem, stream);
 }
 
