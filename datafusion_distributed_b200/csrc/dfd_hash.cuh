@@ -72,6 +72,9 @@ __device__ __forceinline__ uint64_t rotl64(uint64_t x, unsigned r) {
     return (x << r) | (x >> ((64 - r) & 63));
 }
 
+// lo64(s*by) ^ hi64(s*by).  nvcc lowers this to 3 IMAD (low half) + 4 IMAD.WIDE.U32 with
+// carry predicates (high half); a hand-split 32-bit-limb version was measured to be LONGER
+// (extra zero-extension moves), so the intrinsic form stays.
 __device__ __forceinline__ uint64_t folded_multiply(uint64_t s, uint64_t by) {
     return (s * by) ^ __umul64hi(s, by);
 }

@@ -113,10 +113,15 @@ __global__ void __launch_bounds__(THREADS) k_tile_hist(KeySet keys, HashState st
         const int64_t row0 = tile * T;
         const int tile_rows = (int)((n_rows - row0) < T ? (n_rows - row0) : T);
         uint32_t d[K];
+        if (tile_rows == T) {  // full tile (all but the last): no per-row bounds predicates
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            int t = j * THREADS + (int)threadIdx.x;
-            d[j] = t < tile_rows ? mod_n(row_hash<FAST_I64>(keys, row0 + t, st), mod) : N;
+            for (int j = 0; j < K; ++j) d[j] = mod_n(row_hash<FAST_I64>(keys, row0 + j * THREADS + (int)threadIdx.x, st), mod);
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                int t = j * THREADS + (int)threadIdx.x;
+                d[j] = t < tile_rows ? mod_n(row_hash<FAST_I64>(keys, row0 + t, st), mod) : N;
+            }
         }
         if constexpr (NF > 0) {
             unsigned long long acc[NF];
