@@ -37,6 +37,7 @@ class DfdColumn(C.Structure):
         ("offsets", C.c_void_p),
         ("validity", C.c_void_p),
         ("offset", C.c_int64),
+        ("values_bytes", C.c_int64),
     ]
 
 

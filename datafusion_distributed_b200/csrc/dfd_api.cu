@@ -189,6 +189,8 @@ int dfd::PartitionJob::prepare(Partitioner* part, const dfd_column* in_cols, int
     peer = peer_mode;
     n_rows = rows;
     passes.clear();
+    var_cols.clear();
+    d_src = nullptr;
     bytes = 0;
     Ctx* c = p->ctx;
     const uint32_t N = p->N;
@@ -203,7 +205,8 @@ int dfd::PartitionJob::prepare(Partitioner* part, const dfd_column* in_cols, int
         const dfd_column& oc = out_cols[i];
         if (ic.kind != oc.kind || ic.width != oc.width)
             return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: in/out layout mismatch", i);
-        if (!ic.values || (!peer && !oc.values)) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: values is NULL", i);
+        const bool var_kind = ic.kind == DFD_COL_UTF8 || ic.kind == DFD_COL_LARGE_UTF8 || ic.kind == DFD_COL_BINARY;
+        if (!var_kind && (!ic.values || (!peer && !oc.values))) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: values is NULL", i);
         PayloadCol pc{};
         if (ic.kind == DFD_COL_FIXED) {
             if (ic.width != 1 && ic.width != 2 && ic.width != 4 && ic.width != 8 && ic.width != 16)
@@ -223,10 +226,29 @@ int dfd::PartitionJob::prepare(Partitioner* part, const dfd_column* in_cols, int
             pc.in_offset = ic.offset;
             pc.width = 0;
             bytes += (uint64_t)(n_rows + 7) / 8;
+        } else if (ic.kind == DFD_COL_UTF8 || ic.kind == DFD_COL_LARGE_UTF8 || ic.kind == DFD_COL_BINARY) {
+            if (peer) return set_error(DFD_ERR_UNSUPPORTED, "column %d: variable-width columns need the NCCL exchange mode", i);
+            if (!ic.offsets || !oc.offsets) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: offsets is NULL", i);
+            // capacity check needs the input's byte count: two small D2H reads
+            const size_t ow = ic.kind == DFD_COL_LARGE_UTF8 ? 8 : 4;
+            int64_t first = 0, last = 0;
+            cudaError_t e = cudaMemcpyAsync(&first, (const char*)ic.offsets + (size_t)ic.offset * ow, ow, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&last, (const char*)ic.offsets + (size_t)(ic.offset + n_rows) * ow, ow, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) return cuda_error(e, "reading variable-width offsets");
+            if (ow == 4) { first = (int32_t)first; last = (int32_t)last; }
+            const int64_t nbytes = last - first;
+            if (nbytes < 0) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: offsets are not monotonic", i);
+            if (oc.values_bytes < nbytes)
+                return set_error(DFD_ERR_CAPACITY, "column %d: out values_bytes %lld < %lld bytes of input data", i,
+                                 (long long)oc.values_bytes, (long long)nbytes);
+            if (nbytes > 0 && (!ic.values || !oc.values)) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: values is NULL", i);
+            var_cols.push_back(VarCol{ic, oc});
+            bytes += (uint64_t)nbytes + (uint64_t)(n_rows + 1) * ow;
         } else {
-            return set_error(DFD_ERR_UNSUPPORTED, "column %d: variable-width payload columns are not supported yet", i);
+            return set_error(DFD_ERR_UNSUPPORTED, "column %d: unknown column kind %d", i, ic.kind);
         }
-        passes.push_back(pc);
+        if (ic.kind == DFD_COL_FIXED || ic.kind == DFD_COL_BOOL) passes.push_back(pc);
         if (ic.validity) {
             if (peer) return set_error(DFD_ERR_UNSUPPORTED, "column %d: nullable columns need the NCCL exchange mode", i);
             if (!oc.validity) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: input has a validity bitmap but out validity is NULL", i);
@@ -239,6 +261,25 @@ int dfd::PartitionJob::prepare(Partitioner* part, const dfd_column* in_cols, int
             passes.push_back(vc);
             bytes += (uint64_t)(n_rows + 7) / 8;
         }
+    }
+    if (!var_cols.empty() && n_rows > 0) {
+        // K4 needs the input row of every output row: scatter an iota column with the rest
+        const size_t nb = (((size_t)n_rows * 4) + 255) & ~(size_t)255;
+        const int64_t n_blocks = (n_rows + VAR_BLOCK * VAR_ITEMS - 1) / (VAR_BLOCK * VAR_ITEMS);
+        rc = c->var_scratch.ensure(2 * nb + (size_t)(n_blocks + 1) * 8 + 256, c->device);
+        if (rc) return rc;
+        uint32_t* d_iota = (uint32_t*)c->var_scratch.ptr;
+        d_src = (uint32_t*)((char*)c->var_scratch.ptr + nb);
+        d_block_sums = (unsigned long long*)((char*)c->var_scratch.ptr + 2 * nb);
+        k_iota_u32<<<(unsigned)(c->sm_count * 8), 256, 0, stream>>>(d_iota, n_rows);
+        LAUNCH_CHECK("k_iota_u32");
+        c->metrics.kernel_launches++;
+        PayloadCol ip{};
+        ip.in = d_iota;
+        ip.out = d_src;
+        ip.in_offset = 0;
+        ip.width = 4;
+        passes.push_back(ip);
     }
     n_tiles = n_rows > 0 ? (n_rows + TILE_ROWS - 1) / TILE_ROWS : 1;
     // scratch: hist u32 [N][n_tiles] | tile_base u32 [N][n_tiles] | totals i64 [N] | done u32
@@ -349,6 +390,10 @@ int dfd::PartitionJob::run_scatter(const int64_t* dest_base, void* const* peer_b
             }
         }
     }
+    if (!var_cols.empty()) {
+        int rc = run_varwidth();
+        if (rc) return rc;
+    }
     if (ev) {
         cudaEventRecord(ev[3], stream);
         c->ev_pending++;
@@ -360,6 +405,41 @@ int dfd::PartitionJob::run_scatter(const int64_t* dest_base, void* const* peer_b
     c->metrics.rows += (uint64_t)n_rows;
     c->metrics.bytes_in += bytes;
     c->metrics.bytes_out += bytes;
+    return DFD_OK;
+}
+
+template <typename OFF>
+static int launch_varwidth(const dfd::PartitionJob::VarCol& vc, const uint32_t* d_src, unsigned long long* d_block_sums,
+                           int64_t n_rows, int sm_count, cudaStream_t stream) {
+    const int64_t n_blocks = (n_rows + VAR_BLOCK * VAR_ITEMS - 1) / (VAR_BLOCK * VAR_ITEMS);
+    const OFF* in_off = (const OFF*)vc.in.offsets;
+    OFF* out_off = (OFF*)vc.out.offsets;
+    k_var_block_sums<OFF><<<(unsigned)n_blocks, VAR_BLOCK, 0, stream>>>(in_off, vc.in.offset, d_src, n_rows, d_block_sums);
+    LAUNCH_CHECK("k_var_block_sums");
+    k_var_scan_block_sums<<<1, 1024, 0, stream>>>(d_block_sums, n_blocks);
+    LAUNCH_CHECK("k_var_scan_block_sums");
+    k_var_write_offsets<OFF><<<(unsigned)n_blocks, VAR_BLOCK, 0, stream>>>(in_off, vc.in.offset, d_src, n_rows, d_block_sums, out_off);
+    LAUNCH_CHECK("k_var_write_offsets");
+    k_var_copy_bytes<OFF><<<(unsigned)(sm_count * 16), 256, 0, stream>>>(in_off, vc.in.offset, (const uint8_t*)vc.in.values, d_src, out_off,
+                                                                       (uint8_t*)vc.out.values, n_rows);
+    LAUNCH_CHECK("k_var_copy_bytes");
+    return DFD_OK;
+}
+
+int dfd::PartitionJob::run_varwidth() {
+    Ctx* c = p->ctx;
+    for (const VarCol& vc : var_cols) {
+        if (n_rows == 0) {
+            const size_t ow = vc.in.kind == DFD_COL_LARGE_UTF8 ? 8 : 4;
+            cudaError_t e = cudaMemsetAsync(vc.out.offsets, 0, ow, stream);
+            if (e != cudaSuccess) return cuda_error(e, "cudaMemsetAsync");
+            continue;
+        }
+        int rc = vc.in.kind == DFD_COL_LARGE_UTF8 ? launch_varwidth<int64_t>(vc, d_src, d_block_sums, n_rows, c->sm_count, stream)
+                                                  : launch_varwidth<int32_t>(vc, d_src, d_block_sums, n_rows, c->sm_count, stream);
+        if (rc) return rc;
+        c->metrics.kernel_launches += 4;
+    }
     return DFD_OK;
 }
 
@@ -437,6 +517,7 @@ void dfd_ctx_destroy(dfd_ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->scratch.ptr) cudaFree(c->scratch.ptr);
     if (c->flush.ptr) cudaFree(c->flush.ptr);
+    if (c->var_scratch.ptr) cudaFree(c->var_scratch.ptr);
     for (auto& ev : c->ev_ring) cudaEventDestroy(ev);
     cudaEventDestroy(c->timer_a);
     cudaEventDestroy(c->timer_b);

@@ -40,6 +40,7 @@ struct dfd_ctx {
     dfd::Scratch scratch;  // tile histograms / cursors
     void* scratch_done = nullptr;  // zero-initialised "blocks done" counter inside scratch
     dfd::Scratch flush;    // L2 flush buffer
+    dfd::Scratch var_scratch;  // K4: iota | src row ids | block sums
     dfd_metrics metrics = {};
     std::mutex mu;
 };
@@ -67,6 +68,10 @@ struct PartitionJob {
     bool peer = false;
     KeySet ks{};
     std::vector<PayloadCol> passes;
+    struct VarCol { dfd_column in, out; };
+    std::vector<VarCol> var_cols;        // K4: variable-width payload columns
+    uint32_t* d_src = nullptr;            // K4: input row of every output row (scattered iota)
+    unsigned long long* d_block_sums = nullptr;
     uint64_t bytes = 0;
     int64_t n_rows = 0, n_tiles = 0;
     uint32_t* d_hist = nullptr;
@@ -79,6 +84,7 @@ struct PartitionJob {
     int run_hist_scan();
     int run_scatter(const int64_t* dest_base, void* const* peer_base, int world, uint32_t parts_per_rank,
                     const int32_t* abort_flag);
+    int run_varwidth();  // called by run_scatter after the fixed-width launches
 };
 
 // Launches K1 -> K1b -> K2 on `stream`; caller holds ctx->mu and has set the device.

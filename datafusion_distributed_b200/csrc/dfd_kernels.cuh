@@ -507,6 +507,104 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
 #undef S_SCAN
 }
 
+// ---------------------------------------------------------------------------
+// K4: variable-width payload columns (Utf8 / LargeUtf8 / Binary).
+// K2 scatters an iota column, giving src[j] = input row of output row j.  Per
+// var-width column: gather the string lengths in output order, exclusive-scan
+// them into the output offsets (3-phase device scan), then copy the bytes.
+// ---------------------------------------------------------------------------
+constexpr int VAR_BLOCK = 256;
+constexpr int VAR_ITEMS = 8;  // rows per thread in the scan kernels (block = 2048 rows)
+
+__global__ void k_iota_u32(uint32_t* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (uint32_t)i;
+}
+
+template <typename OFF>
+__device__ __forceinline__ unsigned long long var_len(const OFF* __restrict__ in_off, int64_t in_offset, uint32_t src) {
+    const int64_t j = (int64_t)src + in_offset;
+    return (unsigned long long)(in_off[j + 1] - in_off[j]);
+}
+
+// phase a: per-block sum of the gathered lengths
+template <typename OFF>
+__global__ void __launch_bounds__(VAR_BLOCK) k_var_block_sums(const OFF* __restrict__ in_off, int64_t in_offset,
+                                                               const uint32_t* __restrict__ src, int64_t n,
+                                                               unsigned long long* __restrict__ block_sums) {
+    __shared__ unsigned long long s_warp[VAR_BLOCK / 32];
+    const int64_t base = (int64_t)blockIdx.x * (VAR_BLOCK * VAR_ITEMS) + (int64_t)threadIdx.x * VAR_ITEMS;
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int k = 0; k < VAR_ITEMS; ++k)
+        if (base + k < n) sum += var_len(in_off, in_offset, src[base + k]);
+#pragma unroll
+    for (int sh = 16; sh >= 1; sh >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sh);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < VAR_BLOCK / 32; ++w) t += s_warp[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// phase b: exclusive scan of the block sums in place (single CTA), total -> block_sums[n_blocks]
+__global__ void __launch_bounds__(1024) k_var_scan_block_sums(unsigned long long* __restrict__ block_sums, int64_t n_blocks) {
+    __shared__ unsigned long long s_warp[33];
+    unsigned long long carry = 0;
+    for (int64_t b0 = 0; b0 < n_blocks; b0 += 1024) {
+        int64_t b = b0 + threadIdx.x;
+        unsigned long long v = b < n_blocks ? block_sums[b] : 0, tot;
+        unsigned long long ex = block_exclusive_scan_u64<1024>(v, s_warp, tot);
+        if (b < n_blocks) block_sums[b] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) block_sums[n_blocks] = carry;
+}
+
+// phase c: output offsets = block base + block-local exclusive scan of the lengths
+template <typename OFF>
+__global__ void __launch_bounds__(VAR_BLOCK) k_var_write_offsets(const OFF* __restrict__ in_off, int64_t in_offset,
+                                                                  const uint32_t* __restrict__ src, int64_t n,
+                                                                  const unsigned long long* __restrict__ block_sums,
+                                                                  OFF* __restrict__ out_off) {
+    __shared__ unsigned long long s_warp[33];
+    const int64_t base = (int64_t)blockIdx.x * (VAR_BLOCK * VAR_ITEMS) + (int64_t)threadIdx.x * VAR_ITEMS;
+    unsigned long long len[VAR_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < VAR_ITEMS; ++k) {
+        len[k] = base + k < n ? var_len(in_off, in_offset, src[base + k]) : 0;
+        sum += len[k];
+    }
+    unsigned long long tot;
+    unsigned long long run = block_sums[blockIdx.x] + block_exclusive_scan_u64<VAR_BLOCK>(sum, s_warp, tot);
+#pragma unroll
+    for (int k = 0; k < VAR_ITEMS; ++k) {
+        if (base + k < n) out_off[base + k] = (OFF)run;
+        run += len[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out_off[n] = (OFF)block_sums[gridDim.x];
+}
+
+// bytes of output row j <- bytes of input row src[j]; one thread per row
+template <typename OFF>
+__global__ void __launch_bounds__(256) k_var_copy_bytes(const OFF* __restrict__ in_off, int64_t in_offset,
+                                                         const uint8_t* __restrict__ in_data, const uint32_t* __restrict__ src,
+                                                         const OFF* __restrict__ out_off, uint8_t* __restrict__ out_data, int64_t n) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = (int64_t)src[j] + in_offset;
+        const uint8_t* s = in_data + in_off[r];
+        const int64_t len = (int64_t)(in_off[r + 1] - in_off[r]);
+        uint8_t* d = out_data + out_off[j];
+        int64_t i = 0;
+        if ((((uintptr_t)s ^ (uintptr_t)d) & 7) == 0) {  // co-aligned: byte head, 8-byte body
+            for (; i < len && ((uintptr_t)(s + i) & 7); ++i) d[i] = s[i];
+            for (; i + 8 <= len; i += 8) *(uint64_t*)(d + i) = *(const uint64_t*)(s + i);
+        }
+        for (; i < len; ++i) d[i] = s[i];
+    }
+}
+
 template <int THREADS, int K>
 inline size_t scatter_smem_bytes(uint32_t N, int stage_width) {
     size_t off = ((size_t)THREADS * K * stage_width + 15) & ~(size_t)15;

@@ -130,10 +130,11 @@ class DeviceColumn:
     length: int = 0
     keep: Any = field(default=None, repr=False)  # owners of the memory
     arrow_type: Any = None
+    values_bytes: int = 0  # var-width kinds: size (capacity for outputs) of `values`
 
     def as_c(self) -> nv.DfdColumn:
         return nv.DfdColumn(self.kind, self.width, self.values or None, self.offsets or None,
-                            self.validity or None, self.offset)
+                            self.validity or None, self.offset, self.values_bytes)
 
     @staticmethod
     def from_torch(t, validity=None) -> "DeviceColumn":
@@ -166,7 +167,8 @@ class DeviceColumn:
             ob = ctx.upload_raw(bufs[1].address, bufs[1].size)
             db = ctx.upload_raw(bufs[2].address if bufs[2] is not None else 0, bufs[2].size if bufs[2] is not None else 0)
             keep += [ob, db]
-            return DeviceColumn(kind, 0, db.ptr, ob.ptr, validity, arr.offset, len(arr), keep, t)
+            return DeviceColumn(kind, 0, db.ptr, ob.ptr, validity, arr.offset, len(arr), keep, t,
+                                bufs[2].size if bufs[2] is not None else 0)
         width = t.bit_width // 8
         b = ctx.upload_raw(bufs[1].address, bufs[1].size, pad_to=max(width, 4))
         keep.append(b)
@@ -185,8 +187,12 @@ class DeviceColumn:
             b = ctx.alloc(max((n_rows + 31) // 32 * 4, 4)).zero()
         elif col.kind == nv.COL_FIXED:
             b = ctx.alloc(max(n_rows * col.width, 16))
-        else:
-            raise NotImplementedError("variable-width payload columns")
+        else:  # variable width: offsets (n+1) + a byte buffer as large as the input's
+            ow = 8 if col.kind == nv.COL_LARGE_UTF8 else 4
+            ob = ctx.alloc((n_rows + 1) * ow)
+            b = ctx.alloc(max(col.values_bytes, 16))
+            keep += [ob, b]
+            return DeviceColumn(col.kind, 0, b.ptr, ob.ptr, validity, 0, n_rows, keep, col.arrow_type, max(col.values_bytes, 16))
         keep.append(b)
         return DeviceColumn(col.kind, col.width, b.ptr, 0, validity, 0, n_rows, keep, col.arrow_type)
 
@@ -212,7 +218,14 @@ class DeviceColumn:
             raw = self.keep[-1].download(np.uint8, self.length * self.width)
             data = pa.py_buffer(raw[start * self.width: stop * self.width].tobytes())
             return pa.Array.from_buffers(self.arrow_type, n, [validity_buf, data], null_count=null_count)
-        raise NotImplementedError
+        # variable width: rebase the offsets of rows [start, stop) to zero
+        odt = np.int64 if self.kind == nv.COL_LARGE_UTF8 else np.int32
+        off = self.keep[-2].download(odt, self.length + 1)[start:stop + 1]
+        lo, hi = (int(off[0]), int(off[-1])) if n or len(off) else (0, 0)
+        raw = self.keep[-1].download(np.uint8, max(hi, 1))
+        data = pa.py_buffer(raw[lo:hi].tobytes())
+        offs = pa.py_buffer((off - lo).astype(odt).tobytes())
+        return pa.Array.from_buffers(self.arrow_type, n, [validity_buf, offs, data], null_count=null_count)
 
 
 def columns_to_c(cols: Sequence[DeviceColumn]):

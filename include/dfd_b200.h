@@ -67,6 +67,8 @@ typedef struct {
     void* offsets;           /* var-width kinds only                                 */
     uint8_t* validity;       /* Arrow validity bitmap (LSB first) or NULL = no nulls */
     int64_t offset;          /* Arrow logical offset (rows) into the buffers         */
+    int64_t values_bytes;    /* var-width kinds: size of `values` in bytes (for an OUTPUT
+                                column: its capacity); ignored for fixed / bool       */
 } dfd_column;
 
 /* Counters of the shuffle path; the reference exposes the same quantities as
@@ -151,7 +153,12 @@ int dfd_partition_ids_device(dfd_partitioner* p, const dfd_column* cols, int n_c
  * with NULL the call is fully asynchronous on dfd_ctx_stream() and the device
  * copy is available through dfd_partitioner_part_starts_device().
  * Nullable payload columns: out_cols[c].validity must point to a zeroed
- * bitmap of ceil(n_rows/8) bytes (output offset is 0). */
+ * bitmap of ceil(n_rows/8) bytes (output offset is 0).
+ * Variable-width payload columns (Utf8 / LargeUtf8 / Binary; K4): out_cols[c]
+ * carries `offsets` (n_rows + 1 entries of the input's offset width) and
+ * `values` with `values_bytes` >= the input's byte count; the output is one
+ * offsets buffer + one byte buffer in destination order, so destination p is
+ * again the zero-copy slice [part_starts[p], part_starts[p+1]). */
 int dfd_partition_device(dfd_partitioner* p, const dfd_column* in_cols, int n_cols,
                          int64_t n_rows, const dfd_column* out_cols, int64_t* part_starts_host);
 const int64_t* dfd_partitioner_part_starts_device(const dfd_partitioner* p);

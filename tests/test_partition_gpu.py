@@ -246,3 +246,66 @@ def test_full_size_cfg2_properties(ctx):
     # (5) first 1M rows of partition 0 equal the oracle's order exactly
     want = np.nonzero(dest == 0)[0][:1_000_000]
     assert np.array_equal(rid_out[starts[0]:starts[0] + len(want)].cpu().numpy(), want)
+
+
+# ------------------------------------------- variable-width payload (K4) ----
+
+def _rand_strings(rnd, n, null_frac=0.1, empty_frac=0.3, max_len=40):
+    out = []
+    for _ in range(n):
+        x = rnd.random()
+        if x < null_frac:
+            out.append(None)
+        elif x < null_frac + empty_frac:
+            out.append("")
+        else:
+            out.append("".join(rnd.choice("abcdefghijklmnopqrstuvwxyzäß0123456789 ") for _ in range(rnd.randint(1, max_len))))
+    return out
+
+
+@pytest.mark.parametrize("N", [1, 6, 8, 48])
+def test_scatter_variable_width_payload_and_keys(ctx, N):
+    """cfg-5 shape in small: Hash([UserID: Int64, SearchPhrase: Utf8], N) with Utf8/LargeUtf8/Binary payload."""
+    rnd = random.Random(29)
+    n = 30_011
+    uid = pa.array([rnd.choice([rnd.getrandbits(20), rnd.getrandbits(62)]) for _ in range(n)], type=pa.int64())
+    phrase = pa.array(_rand_strings(rnd, n, 0.05, 0.7, 60), type=pa.string())
+    big = pa.array(_rand_strings(rnd, n, 0.2, 0.1, 100), type=pa.large_string())
+    binv = pa.array([None if s is None else s.encode() for s in _rand_strings(rnd, n, 0.1, 0.1, 17)], type=pa.binary())
+    cnt = pa.array(np.arange(n, dtype=np.int32))
+    arrays = [uid, phrase, big, binv, cnt]
+    outs, starts = run_partition(ctx, arrays, [0, 1], N)
+    dest = orc.partition_ids([uid, phrase], n, N)
+    order, ref_starts = expected_partitions(dest, N)
+    assert np.array_equal(starts, ref_starts)
+    for p in range(N):
+        idx = pa.array(order[starts[p]:starts[p + 1]])
+        for c, arr in enumerate(arrays):
+            got = outs[c].to_arrow(ctx, int(starts[p]), int(starts[p + 1]))
+            assert got.equals(arr.take(idx)), (N, p, c)
+
+
+def test_variable_width_sliced_input_and_empty(ctx):
+    rnd = random.Random(5)
+    s = pa.array(_rand_strings(rnd, 5000, 0.1, 0.2, 30), type=pa.string())
+    k = pa.array(np.arange(5000, dtype=np.int64))
+    sl = [k.slice(77, 3001), s.slice(77, 3001)]
+    outs, starts = run_partition(ctx, sl, [0], 5)
+    dest = orc.partition_ids([sl[0]], 3001, 5)
+    order, ref_starts = expected_partitions(dest, 5)
+    assert np.array_equal(starts, ref_starts)
+    assert outs[1].to_arrow(ctx, 0, 3001).equals(sl[1].take(pa.array(order)))
+    outs, starts = run_partition(ctx, [k.slice(0, 0), s.slice(0, 0)], [0], 4)
+    assert not starts.any()
+
+
+def test_variable_width_capacity_error(ctx):
+    s = pa.array(["hello", "world", "x" * 100], type=pa.string())
+    k = pa.array([1, 2, 3], type=pa.int64())
+    cols = dev_cols(ctx, [k, s])
+    outs = [dfd.DeviceColumn.empty_like(ctx, c, 3) for c in cols]
+    outs[1].values_bytes = 8  # too small
+    part = dfd.HashPartitioner(ctx, dfd.Partitioning.Hash([0], 2))
+    with pytest.raises(dfd.DfdError) as e:
+        part.partition(cols, 3, outs)
+    assert e.value.status == 7
