@@ -9,6 +9,7 @@ uploaded from pyarrow arrays.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass, field
 from typing import Any, Optional, Sequence
 
@@ -24,6 +25,11 @@ class WorkerContext:
         self._h = C.c_void_p()
         nv.check(nv.lib().dfd_ctx_create(device, C.byref(self._h)))
         self.device = device
+        # native objects created on this context; they must be destroyed BEFORE the context
+        self._children = weakref.WeakSet()
+
+    def _adopt(self, child):
+        self._children.add(child)
 
     @property
     def handle(self):
@@ -31,6 +37,11 @@ class WorkerContext:
 
     def close(self):
         if self._h:
+            for child in list(self._children):
+                try:
+                    child.close()
+                except Exception:
+                    pass
             nv.lib().dfd_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -95,6 +106,12 @@ class DeviceBuffer:
         p = C.c_void_p()
         nv.check(nv.lib().dfd_device_alloc(ctx.handle, nbytes, C.byref(p)))
         self.ptr = p.value
+        ctx._adopt(self)
+
+    def close(self):
+        if self.ptr and self.ctx.handle:
+            nv.lib().dfd_device_free(self.ctx.handle, self.ptr)
+        self.ptr = None
 
     def zero(self):
         nv.check(nv.lib().dfd_memset_device(self.ctx.handle, self.ptr, 0, self.nbytes))
@@ -110,11 +127,9 @@ class DeviceBuffer:
 
     def __del__(self):
         try:
-            if self.ptr and self.ctx.handle:
-                nv.lib().dfd_device_free(self.ctx.handle, self.ptr)
+            self.close()
         except Exception:
             pass
-        self.ptr = None
 
 
 @dataclass

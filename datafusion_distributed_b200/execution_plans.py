@@ -27,6 +27,7 @@ class PinnedTable:
         self.n_rows = n_rows
         self._ptrs = []
         self.columns = []
+        ctx._adopt(self)
         for dt in dtypes:
             dt = np.dtype(dt)
             nbytes = max(n_rows * dt.itemsize, 16)
@@ -83,6 +84,7 @@ class RepartitionExec:
         finally:
             if cs.release:  # the operator only borrows the schema
                 C.CFUNCTYPE(None, C.c_void_p)(cs.release)(C.addressof(cs))
+        ctx._adopt(self)
 
     def name(self) -> str:
         return "RepartitionExec"
@@ -119,9 +121,9 @@ class RepartitionExec:
         return {k: getattr(st, k) for k, _ in st._fields_}
 
     def close(self):
-        if self._h:
+        if self._h and self.ctx.handle:
             nv.lib().dfd_repartition_exec_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:

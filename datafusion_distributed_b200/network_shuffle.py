@@ -74,6 +74,7 @@ class ShuffleExchange:
         self._h = C.c_void_p()
         uid = (C.c_char * 128).from_buffer_copy(unique_id) if unique_id is not None else None
         nv.check(nv.lib().dfd_exchange_create(ctx.handle, rank, world, uid, C.byref(self._h)))
+        ctx._adopt(self)
 
     def setup_window(self, nbytes: int):
         nv.check(nv.lib().dfd_exchange_setup_window(self._h, nbytes))
@@ -84,9 +85,9 @@ class ShuffleExchange:
         return {"bytes_sent": a.value, "bytes_received": b.value, "shuffles": c.value}
 
     def close(self):
-        if self._h:
+        if self._h and self.ctx.handle:
             nv.lib().dfd_exchange_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:

@@ -45,15 +45,16 @@ class HashPartitioner:
         seeds_arr = (C.c_uint64 * 4)(*seeds) if seeds is not None else None
         nv.check(nv.lib().dfd_partitioner_create(ctx.handle, partitioning.partition_count, keys,
                                                  len(partitioning.key_cols), seeds_arr, C.byref(self._h)))
+        ctx._adopt(self)
 
     @property
     def num_partitions(self) -> int:
         return self.partitioning.partition_count
 
     def close(self):
-        if self._h:
+        if self._h and self.ctx.handle:  # (the context destroys its children first)
             nv.lib().dfd_partitioner_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:

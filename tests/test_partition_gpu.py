@@ -309,3 +309,17 @@ def test_variable_width_capacity_error(ctx):
     with pytest.raises(dfd.DfdError) as e:
         part.partition(cols, 3, outs)
     assert e.value.status == 7
+
+
+def test_context_closes_its_children_first(built):
+    """Destroy order must not matter to the caller: closing the worker context first
+    tears down the partitioners / buffers / operators created on it."""
+    import gc
+
+    c2 = dfd.WorkerContext(0)
+    part = dfd.HashPartitioner(c2, dfd.Partitioning.Hash([0], 4))
+    buf = c2.alloc(1024)
+    ex = dfd.RepartitionExec(c2, pa.schema([("k", pa.int64())]), dfd.Partitioning.Hash([0], 2), chunk_rows=1024)
+    c2.close()
+    del part, buf, ex
+    gc.collect()
