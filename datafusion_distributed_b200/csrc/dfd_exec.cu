@@ -35,6 +35,8 @@ struct FieldInfo {
     int64_t flags = 0;
     int32_t kind = DFD_COL_FIXED;
     int32_t width = 0;
+    bool var() const { return kind == DFD_COL_UTF8 || kind == DFD_COL_LARGE_UTF8 || kind == DFD_COL_BINARY; }
+    size_t ow() const { return kind == DFD_COL_LARGE_UTF8 ? 8 : 4; }  // offset width of var-width kinds
 };
 
 // Arrow format string -> physical layout (Arrow C data interface, "Data type description")
@@ -72,8 +74,10 @@ struct PinnedPool;
 
 // One D2H landing buffer (pinned): all columns of one chunk, destination-sorted.
 struct OutChunk {
-    std::vector<void*> values;    // per column
+    std::vector<void*> values;    // per column: values (fixed / bool) or string bytes (var-width, grown on demand)
     std::vector<void*> validity;  // per column (may be null)
+    std::vector<void*> offsets;   // per column (var-width only)
+    std::vector<size_t> data_cap; // per column: capacity of `values` for var-width columns
     std::atomic<int> refs{0};
     std::shared_ptr<PinnedPool> pool;
 };
@@ -87,6 +91,7 @@ struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
     std::vector<OutChunk*> all;
 
     static size_t value_bytes(const FieldInfo& f, int64_t rows) {
+        if (f.var()) return 0;  // string bytes are sized per chunk
         return f.kind == DFD_COL_BOOL ? (size_t)((rows + 63) / 64 * 8 + 8) : (size_t)rows * (size_t)f.width;
     }
     static size_t bitmap_bytes(int64_t rows) { return (size_t)((rows + 63) / 64 * 8 + 8); }
@@ -106,11 +111,15 @@ struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
         for (const FieldInfo& f : fields) {
             void* v = nullptr;
             void* b = nullptr;
-            if (cudaHostAlloc(&v, value_bytes(f, chunk_rows), cudaHostAllocPortable) != cudaSuccess) return nullptr;
+            void* o = nullptr;
+            if (!f.var() && cudaHostAlloc(&v, value_bytes(f, chunk_rows), cudaHostAllocPortable) != cudaSuccess) return nullptr;
             if ((f.flags & ARROW_FLAG_NULLABLE) && cudaHostAlloc(&b, bitmap_bytes(chunk_rows), cudaHostAllocPortable) != cudaSuccess)
                 return nullptr;
+            if (f.var() && cudaHostAlloc(&o, (size_t)(chunk_rows + 16) * f.ow(), cudaHostAllocPortable) != cudaSuccess) return nullptr;
             c->values.push_back(v);
             c->validity.push_back(b);
+            c->offsets.push_back(o);
+            c->data_cap.push_back(0);
         }
         std::lock_guard<std::mutex> lk(mu);
         all.push_back(c);
@@ -122,8 +131,11 @@ struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
     }
     ~PinnedPool() {
         for (OutChunk* c : all) {
-            for (void* p : c->values) cudaFreeHost(p);
+            for (void* p : c->values)
+                if (p) cudaFreeHost(p);
             for (void* p : c->validity)
+                if (p) cudaFreeHost(p);
+            for (void* p : c->offsets)
                 if (p) cudaFreeHost(p);
             delete c;
         }
@@ -142,7 +154,7 @@ struct BatchPriv {
     OutChunk* chunk;
     std::vector<ArrowArray> children;
     std::vector<ArrowArray*> child_ptrs;
-    std::vector<const void*> child_bufs;  // 2 per child
+    std::vector<const void*> child_bufs;  // 3 per child (validity, values|offsets, string bytes)
     const void* struct_bufs[1] = {nullptr};
 };
 
@@ -207,6 +219,9 @@ struct HeldInput {  // an input batch whose buffers an in-flight H2D still reads
 
 struct Slot {
     std::vector<void*> d_in, d_in_valid, d_out, d_out_valid;  // per column device buffers
+    std::vector<void*> d_in_off, d_out_off;                   // var-width: offsets buffers
+    std::vector<size_t> in_cap, out_cap;                      // var-width: capacity of d_in / d_out (string bytes)
+    std::vector<int64_t> first_off, data_bytes;               // var-width: first input offset / byte count of the chunk
     int64_t* h_part_starts = nullptr;                        // pinned [N+1]
     cudaEvent_t e_h2d = nullptr, e_k = nullptr, e_d2h = nullptr;
     bool k_recorded = false, d2h_recorded = false;
@@ -287,18 +302,20 @@ int emit_slot(dfd_repartition_exec* x, Slot& s) {
         bp->chunk = oc;
         bp->children.resize(C);
         bp->child_ptrs.resize(C);
-        bp->child_bufs.resize(2 * C);
+        bp->child_bufs.resize(3 * C);
         for (size_t c = 0; c < C; ++c) {
             ArrowArray& a = bp->children[c];
             memset(&a, 0, sizeof a);
             bool hv = s.has_valid[c];
-            bp->child_bufs[2 * c] = hv ? oc->validity[c] : nullptr;
-            bp->child_bufs[2 * c + 1] = oc->values[c];
+            const bool var = x->fields[c].var();
+            bp->child_bufs[3 * c] = hv ? oc->validity[c] : nullptr;
+            bp->child_bufs[3 * c + 1] = var ? oc->offsets[c] : oc->values[c];
+            bp->child_bufs[3 * c + 2] = var ? oc->values[c] : nullptr;
             a.length = cnt;
             a.offset = start;  // zero-copy slice of the chunk-wide destination-sorted buffer
             a.null_count = hv ? -1 : 0;
-            a.n_buffers = 2;
-            a.buffers = &bp->child_bufs[2 * c];
+            a.n_buffers = var ? 3 : 2;
+            a.buffers = &bp->child_bufs[3 * c];
             a.release = child_release;
             bp->child_ptrs[c] = &a;
         }
@@ -342,8 +359,15 @@ int flush_current(dfd_repartition_exec* x) {
     std::vector<dfd_column> in(C), out(C);
     for (size_t i = 0; i < C; ++i) {
         const FieldInfo& f = x->fields[i];
-        in[i] = dfd_column{f.kind, f.width, s.d_in[i], nullptr, s.has_valid[i] ? (uint8_t*)s.d_in_valid[i] : nullptr, s.in_offset[i], 0};
-        out[i] = dfd_column{f.kind, f.width, s.d_out[i], nullptr, s.has_valid[i] ? (uint8_t*)s.d_out_valid[i] : nullptr, 0, 0};
+        if (f.var()) {
+            // offsets stay absolute: point `values` so that values + first_off is the first copied byte
+            in[i] = dfd_column{f.kind, 0, (char*)s.d_in[i] - s.first_off[i], s.d_in_off[i], s.has_valid[i] ? (uint8_t*)s.d_in_valid[i] : nullptr,
+                               s.in_offset[i], (int64_t)s.in_cap[i]};
+            out[i] = dfd_column{f.kind, 0, s.d_out[i], s.d_out_off[i], s.has_valid[i] ? (uint8_t*)s.d_out_valid[i] : nullptr, 0, (int64_t)s.out_cap[i]};
+        } else {
+            in[i] = dfd_column{f.kind, f.width, s.d_in[i], nullptr, s.has_valid[i] ? (uint8_t*)s.d_in_valid[i] : nullptr, s.in_offset[i], 0};
+            out[i] = dfd_column{f.kind, f.width, s.d_out[i], nullptr, s.has_valid[i] ? (uint8_t*)s.d_out_valid[i] : nullptr, 0, 0};
+        }
         if (f.kind == DFD_COL_BOOL)
             XCUDA(x, cudaMemsetAsync(s.d_out[i], 0, PinnedPool::bitmap_bytes(s.rows), c->stream), "memset");
         if (s.has_valid[i]) XCUDA(x, cudaMemsetAsync(s.d_out_valid[i], 0, PinnedPool::bitmap_bytes(s.rows), c->stream), "memset");
@@ -361,7 +385,20 @@ int flush_current(dfd_repartition_exec* x) {
     for (size_t i = 0; i < C; ++i) {
         const FieldInfo& f = x->fields[i];
         size_t nb = f.kind == DFD_COL_BOOL ? (size_t)((s.rows + 7) / 8) : (size_t)s.rows * f.width;
-        XCUDA(x, cudaMemcpyAsync(s.out->values[i], s.d_out[i], nb, cudaMemcpyDeviceToHost, x->s_d2h), "D2H");
+        if (f.var()) {
+            nb = (size_t)s.data_bytes[i];
+            if (s.out->data_cap[i] < nb) {  // grow this pinned chunk's string buffer
+                if (s.out->values[i]) cudaFreeHost(s.out->values[i]);
+                s.out->values[i] = nullptr;
+                s.out->data_cap[i] = 0;
+                size_t want = nb + nb / 4 + 64;
+                XCUDA(x, cudaHostAlloc(&s.out->values[i], want, cudaHostAllocPortable), "cudaHostAlloc(string bytes)");
+                s.out->data_cap[i] = want;
+            }
+            XCUDA(x, cudaMemcpyAsync(s.out->offsets[i], s.d_out_off[i], (size_t)(s.rows + 1) * f.ow(), cudaMemcpyDeviceToHost, x->s_d2h), "D2H offsets");
+            x->bytes_d2h += (size_t)(s.rows + 1) * f.ow();
+        }
+        if (nb) XCUDA(x, cudaMemcpyAsync(s.out->values[i], s.d_out[i], nb, cudaMemcpyDeviceToHost, x->s_d2h), "D2H");
         x->bytes_d2h += nb;
         if (s.has_valid[i]) {
             XCUDA(x, cudaMemcpyAsync(s.out->validity[i], s.d_out_valid[i], (size_t)((s.rows + 7) / 8), cudaMemcpyDeviceToHost, x->s_d2h), "D2H");
@@ -419,7 +456,31 @@ int stage_rows(dfd_repartition_exec* x, const ArrowArray* b, int64_t start, int6
         const bool hv = !plain && c->null_count != 0 && c->n_buffers > 0 && c->buffers[0] != nullptr;
         const int64_t bit_off = (hv || f.kind == DFD_COL_BOOL) ? (lo & 7) : 0;
         const size_t bitmap_nb = (size_t)((bit_off + n + 7) >> 3);
-        if (f.kind == DFD_COL_FIXED) {
+        if (f.var()) {
+            // offsets (n + 1 entries, kept absolute) at logical index bit_off; the bytes they span at d_in
+            const size_t ow = f.ow();
+            const char* offs = (const char*)c->buffers[1];
+            int64_t first, last;
+            if (ow == 4) { first = ((const int32_t*)offs)[lo]; last = ((const int32_t*)offs)[lo + n]; }
+            else { first = ((const int64_t*)offs)[lo]; last = ((const int64_t*)offs)[lo + n]; }
+            const int64_t nbytes = last - first;
+            if (nbytes < 0) return fail(x, DFD_ERR_INVALID_ARGUMENT, "column " + f.name + ": offsets are not monotonic");
+            if ((size_t)nbytes > s.in_cap[i]) {  // grow (the slot is idle: it was emitted before being reopened)
+                cudaFree(s.d_in[i]); cudaFree(s.d_out[i]);
+                s.d_in[i] = s.d_out[i] = nullptr;
+                s.in_cap[i] = s.out_cap[i] = 0;
+                size_t want = (size_t)nbytes + (size_t)nbytes / 4 + 256;
+                XCUDA(x, cudaMalloc(&s.d_in[i], want), "cudaMalloc(string bytes)");
+                XCUDA(x, cudaMalloc(&s.d_out[i], want), "cudaMalloc(string bytes)");
+                s.in_cap[i] = s.out_cap[i] = want;
+            }
+            XCUDA(x, cudaMemcpyAsync((char*)s.d_in_off[i] + (size_t)bit_off * ow, offs + (size_t)lo * ow, (size_t)(n + 1) * ow,
+                                     cudaMemcpyHostToDevice, x->s_h2d), "H2D offsets");
+            if (nbytes) XCUDA(x, cudaMemcpyAsync(s.d_in[i], (const char*)c->buffers[2] + first, (size_t)nbytes, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
+            s.first_off[i] = first;
+            s.data_bytes[i] = nbytes;
+            x->bytes_h2d += (size_t)nbytes + (size_t)(n + 1) * ow;
+        } else if (f.kind == DFD_COL_FIXED) {
             const char* src = (const char*)c->buffers[1] + (size_t)lo * f.width;
             char* dst = (char*)s.d_in[i] + (size_t)(s.rows + bit_off) * f.width;
             XCUDA(x, cudaMemcpyAsync(dst, src, (size_t)n * f.width, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
@@ -482,9 +543,7 @@ int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, 
             return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): Arrow format '%s' is not supported", (long long)i, f.name.c_str(), f.format.c_str());
         bool is_key = false;
         for (int k = 0; k < n_keys; ++k) is_key |= key_cols && key_cols[k] == i;
-        if (f.kind != DFD_COL_FIXED && f.kind != DFD_COL_BOOL)
-            return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): variable-width columns are not supported by the host operator yet%s",
-                             (long long)i, f.name.c_str(), is_key ? " (use dfd_partition_ids_device for var-width keys)" : "");
+        (void)is_key;
         x->fields.push_back(f);
     }
     for (int k = 0; k < n_keys; ++k)
@@ -511,8 +570,20 @@ int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, 
             s.d_in.assign(C, nullptr); s.d_in_valid.assign(C, nullptr); s.d_out.assign(C, nullptr); s.d_out_valid.assign(C, nullptr);
             s.in_offset.assign(C, 0);
             s.has_valid.assign(C, false);
+            s.d_in_off.assign(C, nullptr); s.d_out_off.assign(C, nullptr);
+            s.in_cap.assign(C, 0); s.out_cap.assign(C, 0);
+            s.first_off.assign(C, 0); s.data_bytes.assign(C, 0);
             for (size_t i = 0; i < C && e == cudaSuccess; ++i) {
                 const FieldInfo& f = x->fields[i];
+                if (f.var()) {  // offsets now, string bytes on demand
+                    e = cudaMalloc(&s.d_in_off[i], (size_t)(x->chunk_rows + 16) * f.ow());
+                    if (e == cudaSuccess) e = cudaMalloc(&s.d_out_off[i], (size_t)(x->chunk_rows + 16) * f.ow());
+                    if (e == cudaSuccess && (f.flags & ARROW_FLAG_NULLABLE)) {
+                        e = cudaMalloc(&s.d_in_valid[i], PinnedPool::bitmap_bytes(x->chunk_rows) + 8);
+                        if (e == cudaSuccess) e = cudaMalloc(&s.d_out_valid[i], PinnedPool::bitmap_bytes(x->chunk_rows) + 8);
+                    }
+                    continue;
+                }
                 size_t vb = PinnedPool::value_bytes(f, x->chunk_rows) + 16 * (size_t)(f.width ? f.width : 1);
                 e = cudaMalloc(&s.d_in[i], vb);
                 if (e == cudaSuccess) e = cudaMalloc(&s.d_out[i], vb);
@@ -567,6 +638,8 @@ void dfd_repartition_exec_destroy(dfd_repartition_exec* x) {
             for (void* p : s.d_in_valid) cudaFree(p);
             for (void* p : s.d_out) cudaFree(p);
             for (void* p : s.d_out_valid) cudaFree(p);
+            for (void* p : s.d_in_off) cudaFree(p);
+            for (void* p : s.d_out_off) cudaFree(p);
             if (s.h_part_starts) cudaFreeHost(s.h_part_starts);
             if (s.e_h2d) cudaEventDestroy(s.e_h2d);
             if (s.e_k) cudaEventDestroy(s.e_k);

@@ -183,7 +183,9 @@ const int64_t* dfd_partitioner_part_starts_device(const dfd_partitioner* p);
  *               partition stream (EIO + get_last_error), like the reference
  *               (src/worker/worker_connection_pool.rs:393-397).
  * Rows inside (one input chunk, one destination) keep input order.
- * Variable-width / dictionary columns: DFD_ERR_UNSUPPORTED. */
+ * Supported columns: fixed-width primitives (incl. Decimal128, timestamps,
+ * dates), Boolean, Utf8 / LargeUtf8 / Binary, all nullable.  Dictionary, view
+ * and nested types: DFD_ERR_UNSUPPORTED (remaining part). */
 typedef struct dfd_repartition_exec dfd_repartition_exec;
 
 typedef struct {

@@ -116,8 +116,8 @@ def test_single_partition_and_pinned_input(ctx):
 
 def test_operator_errors(ctx):
     with pytest.raises(dfd.DfdError) as e:
-        dfd.RepartitionExec(ctx, pa.schema([("s", pa.string())]), dfd.Partitioning.Hash([0], 4))
-    assert e.value.status == 6  # DFD_ERR_UNSUPPORTED: variable-width columns are a "next" row
+        dfd.RepartitionExec(ctx, pa.schema([("s", pa.dictionary(pa.int32(), pa.string()))]), dfd.Partitioning.Hash([0], 4))
+    assert e.value.status == 6  # DFD_ERR_UNSUPPORTED: dictionary arrays are a "next" row
     sch = pa.schema([("k", pa.int64())])
     with pytest.raises(dfd.DfdError):
         dfd.RepartitionExec(ctx, sch, dfd.Partitioning.Hash([1], 4))
@@ -133,4 +133,32 @@ def test_operator_errors(ctx):
     for p in range(2):
         with pytest.raises(Exception):
             ex.execute(p).read_all()
+    ex.close()
+
+
+def test_utf8_keys_and_payload_through_the_operator(ctx):
+    """cfg-3 / cfg-5 shapes through the host operator: Utf8 keys, Utf8 / LargeUtf8 / Binary payload, nulls, slices."""
+    rnd = random.Random(12)
+    n, N = 40_000, 6
+    words = ["", "a", "N", "O", "F", "R", "search phrase", "x" * 70, "päö"]
+    uid = pa.array([rnd.getrandbits(18) for _ in range(n)], type=pa.int64())
+    phrase = pa.array([rnd.choice([None] + words) if rnd.random() < 0.8 else "q%d" % rnd.getrandbits(30) for _ in range(n)], type=pa.string())
+    big = pa.array([rnd.choice([None, "big" * rnd.randint(0, 20)]) for _ in range(n)], type=pa.large_string())
+    binv = pa.array([rnd.choice([None, b"", bytes(rnd.getrandbits(8) for _ in range(rnd.randint(0, 12)))]) for _ in range(n)], type=pa.binary())
+    val = pa.array(np.arange(n, dtype=np.int32))
+    names = ["uid", "phrase", "big", "bin", "val"]
+    table = pa.table([uid, phrase, big, binv, val], names=names)
+    ex = dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash([0, 1], N), chunk_rows=8192)
+    cuts = [0, 5, 9000, 9003, 25_001, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        for rb in table.slice(a, b - a).to_batches(max_chunksize=7000):
+            ex.push_batch(rb)
+    ex.finish()
+    outs = collect(ex, N)
+    dest = orc.partition_ids([uid, phrase], n, N)
+    order, starts = expected_partitions(dest, N)
+    for p in range(N):
+        want = table.take(pa.array(order[starts[p]:starts[p + 1]]))
+        assert outs[p].num_rows == want.num_rows
+        assert outs[p].equals(want), p
     ex.close()
