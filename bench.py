@@ -45,7 +45,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks + throttle reasons sampled (one `nvidia-smi -lms 100` process) while the GPU is
+    under load: started before an untimed soak of the same step and stopped after the timed region."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -54,37 +55,59 @@ class ClockSampler:
     def __init__(self, index: int = 0):
         self.index = index
         self.samples = []
-        self._stop = threading.Event()
+        self._p = None
         self._t = None
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        for line in self._p.stdout:
+            parts = [x.strip() for x in line.strip().split(",")]
+            if len(parts) >= 7:
+                self.samples.append(parts)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self._p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                                        "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        except Exception:
+            self._p = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self._p is not None:
+            self._p.terminate()
+            try:
+                self._p.wait(timeout=5)
+            except Exception:
+                self._p.kill()
+            self._t.join(timeout=5)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+
+        sm = sorted(v for v in (num(s[0]) for s in self.samples) if v is not None)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
-                "reasons": reasons, "samples": len(self.samples)}
+        pw = [v for v in (num(s[2]) for s in self.samples) if v is not None]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": num(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples), "power_w_max": max(pw) if pw else None}
+
+
+def soak(step, seconds: float, sync):
+    """Untimed repetitions of the step so clocks/thermals are at steady state and the sampler sees load."""
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(20):
+            step()
+        sync()
 
 
 def cpu_reference_arm(n_rows: int, threads: int, reps: int):
@@ -245,6 +268,12 @@ def run_multi_gpu(args, torch, dfd, world):
     torch.cuda.synchronize()
     ctx.synchronize()
     with ClockSampler(local_rank) as clocks:
+        for _ in range(0 if args.no_soak else 100):  # untimed soak (collective: same count on every rank)
+            step()
+        ctx.reset_metrics()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
         ctx.timer_start()
         for _ in range(args.steps):
             outs, starts = step()
@@ -320,6 +349,7 @@ def main():
     ap.add_argument("--rows", type=int, default=N_ROWS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-soak", action="store_true", help="skip the untimed clock soak (use under ncu)")
     ap.add_argument("--e2e-batch-rows", type=int, default=1 << 20)
     ap.add_argument("--e2e-chunk-rows", type=int, default=1 << 20)
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"])
@@ -359,6 +389,9 @@ def main():
     ctx.set_profiling(True)
     # inputs (4 GiB) + outputs (4 GiB) are far larger than the 126 MB L2: no flush needed between steps
     with ClockSampler(dev) as clocks:
+        if not args.no_soak:
+            soak(lambda: part.partition(in_cols, n, out_cols, sync=False), 1.0, ctx.synchronize)
+        ctx.reset_metrics()
         ctx.timer_start()
         for _ in range(args.steps):
             part.partition(in_cols, n, out_cols, sync=False)
