@@ -412,7 +412,11 @@ def main():
         "config": {"workload": "cfg2: 2^26 rows x 8 Int64, Hash([col0], 8), device-resident table", "rows": n,
                    "columns": N_COLS, "num_partitions": NUM_PARTITIONS, "l2": "inputs+outputs (8 GiB) >> L2, no flush"},
         "roofline": {"bound": "hbm", "kernel": "k_scatter", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                     "frac": achieved / peak, "peak_source": peak_src,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one k_scatter launch at this exact workload,
+                     # from the committed `ncu --set full` capture profiles/r01c_ncu_summary.md (8.59 GB algorithmic)
+                     "traffic": 8.576116e9 if n == N_ROWS else None, "traffic_unit": "bytes/launch",
+                     "traffic_source": "profiles/r01c_ncu_summary.md",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scatter_ms,
                      "hist_ms": m["hist_ms"] / max(m["calls"], 1), "scan_ms": m["scan_ms"] / max(m["calls"], 1)},
         "gpu_launches": int(m["kernel_launches"]),

@@ -377,8 +377,8 @@ int dfd::PartitionJob::run_scatter(const int64_t* dest_base, void* const* peer_b
                 if (pc.width == width) group.push_back(pc);
             if (group.empty()) continue;
             sp.stage_width = width ? width : 1;
-            size_t smem = scatter_smem_bytes<TILE_THREADS, TILE_K>(N, sp.stage_width);
-            if (smem > 200 * 1024)
+            size_t smem = scatter_smem_bytes<TILE_THREADS, TILE_K>(N, sp.stage_width, peer, use_aligned(N, peer));
+            if (smem > 227 * 1024)
                 return set_error(DFD_ERR_UNSUPPORTED, "num_partitions %u needs %zu B of shared memory per CTA", N, smem);
             for (size_t first = 0; first < group.size(); first += MAX_COLS_PER_LAUNCH) {
                 size_t n = group.size() - first < (size_t)MAX_COLS_PER_LAUNCH ? group.size() - first : (size_t)MAX_COLS_PER_LAUNCH;

@@ -198,22 +198,43 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_scan_tiles(const uint32_t* __restrict__ hist, uint32_t* __restrict__ tile_base,
                                                          int64_t* __restrict__ totals, int64_t* __restrict__ part_starts,
                                                          unsigned* __restrict__ done, int64_t n_tiles, uint32_t N) {
+    constexpr int W = THREADS / 32;
     __shared__ unsigned long long s_warp[33];
+    __shared__ unsigned long long s_wsum[W];
     __shared__ bool s_last;
     const uint32_t p = blockIdx.x;
     const uint32_t* h = hist + (int64_t)p * n_tiles;
     uint32_t* b = tile_base + (int64_t)p * n_tiles;
-    // each thread owns a contiguous run of tiles (lines are re-used from L1 across its loads)
-    const int64_t per = (n_tiles + THREADS - 1) / THREADS;
-    const int64_t lo = (int64_t)threadIdx.x * per;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // warp w owns the contiguous tiles [lo, hi); every access is a coalesced 32-wide row
+    const int64_t per = ((n_tiles + W - 1) / W + 31) & ~(int64_t)31;
+    const int64_t lo = (int64_t)w * per;
     const int64_t hi = lo + per < n_tiles ? lo + per : n_tiles;
     unsigned long long sum = 0;
-    for (int64_t i = lo; i < hi; ++i) sum += h[i];
-    unsigned long long total;
-    unsigned long long run = block_exclusive_scan_u64<THREADS>(sum, s_warp, total);
-    for (int64_t i = lo; i < hi; ++i) {
-        b[i] = (uint32_t)run;
-        run += h[i];
+    for (int64_t i = lo + lane; i < hi; i += 32) sum += h[i];
+#pragma unroll
+    for (int sh = 16; sh >= 1; sh >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sh);
+    if (lane == 0) s_wsum[w] = sum;
+    __syncthreads();
+    unsigned long long total = 0, base = 0;
+#pragma unroll
+    for (int ww = 0; ww < W; ++ww) {
+        unsigned long long v = s_wsum[ww];
+        if (ww < w) base += v;
+        total += v;
+    }
+    unsigned long long run = base;
+    for (int64_t i0 = lo; i0 < hi; i0 += 32) {
+        const int64_t i = i0 + lane;
+        const uint32_t v = i < hi ? h[i] : 0;
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (i < hi) b[i] = (uint32_t)(run + inc - v);
+        run += __shfl_sync(0xffffffffu, inc, 31);
     }
     if (threadIdx.x == 0) {
         totals[p] = (int64_t)total;
@@ -605,16 +626,18 @@ __global__ void __launch_bounds__(256) k_var_copy_bytes(const OFF* __restrict__ 
     }
 }
 
+// must mirror the offsets computed at the top of k_scatter (the peer / aligned tables are last,
+// so launches that do not use them simply do not allocate them)
 template <int THREADS, int K>
-inline size_t scatter_smem_bytes(uint32_t N, int stage_width) {
+inline size_t scatter_smem_bytes(uint32_t N, int stage_width, bool peer, bool aligned) {
     size_t off = ((size_t)THREADS * K * stage_width + 15) & ~(size_t)15;
     off += (size_t)N * 8;
     off += (size_t)(THREADS / 32) * N * 4;
     off += (size_t)(N + 1) * 4;
     off += (size_t)(THREADS / 32 + 1) * 4;
     off = (off + 7) & ~(size_t)7;
-    off += (size_t)N * 8;  // per-destination output bases (peer mode)
-    off += (size_t)(N + 1) * 4;  // virtual run starts (aligned mode)
+    if (peer || aligned) off += (size_t)N * 8;  // per-destination output bases (peer mode)
+    if (aligned) off += (size_t)(N + 1) * 4;    // virtual run starts (aligned mode)
     return off;
 }
 
