@@ -154,6 +154,10 @@ struct dfd_exchange {
     size_t window_bytes = 0;
     void* peer_window[MAX_RANKS] = {};
     bool window_ready = false;
+    // host pipeline (dfd_shuffle_host): H2D | shuffle | D2H of consecutive chunks overlap
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t e_h2d[2] = {}, e_k[2] = {}, e_d2h[2] = {};
+    Scratch in_stage[2];
     uint64_t bytes_sent = 0, bytes_received = 0, shuffles = 0;
 };
 
@@ -263,6 +267,15 @@ void dfd_exchange_destroy(dfd_exchange* x) {
         cudaFree(x->d_my_starts);
         cudaFree(x->d_abort);
         cudaFree(x->send.ptr);
+        cudaFree(x->in_stage[0].ptr);
+        cudaFree(x->in_stage[1].ptr);
+        for (int i = 0; i < 2; ++i) {
+            if (x->e_h2d[i]) cudaEventDestroy(x->e_h2d[i]);
+            if (x->e_k[i]) cudaEventDestroy(x->e_k[i]);
+            if (x->e_d2h[i]) cudaEventDestroy(x->e_d2h[i]);
+        }
+        if (x->s_h2d) cudaStreamDestroy(x->s_h2d);
+        if (x->s_d2h) cudaStreamDestroy(x->s_d2h);
         cudaFreeHost(x->h_counts);
         cudaFreeHost(x->h_my_starts);
         cudaFreeHost(x->h_abort);
@@ -328,6 +341,65 @@ static size_t row_bytes_of(const dfd_column* cols, int n_cols) {
     return rb;
 }
 
+// Fused shuffle of device columns into window slot `slot` of `n_slots` (the window is split so
+// that a chunked host pipeline can drain one slot while the next chunk lands in the other).
+// Ends with a stream synchronize: x->h_my_starts holds this worker's part_starts[P+1].
+// `e_k`, if given, is recorded right after the last kernel / barrier of this shuffle.
+static int fused_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const dfd_column* in_cols, int n_cols, int64_t n_rows,
+                                uint32_t P, int slot, int n_slots, dfd_column* out_cols, cudaEvent_t e_k) {
+    dfd_ctx* c = x->ctx;
+    const uint32_t N = part->N;
+    const int T = x->world;
+    NcclApi* n = T > 1 ? nccl_api() : nullptr;
+    cudaStream_t s = c->stream;
+    if (!x->window_ready) return set_error(DFD_ERR_INVALID_ARGUMENT, "fused exchange needs dfd_exchange_setup_window first");
+    const size_t rb = row_bytes_of(in_cols, n_cols);
+    if (rb == 0) return set_error(DFD_ERR_INVALID_ARGUMENT, "no fixed-width columns");
+    const size_t slot_bytes = (x->window_bytes / (size_t)n_slots) & ~(size_t)255;
+    const int64_t capacity_rows = (int64_t)(slot_bytes / rb) / 16 * 16;
+    void* peer_base[MAX_RANKS];
+    for (int r = 0; r < T; ++r) peer_base[r] = (char*)x->peer_window[r] + (size_t)slot * slot_bytes;
+    // slot layout (identical on every rank): column c at byte offset capacity_rows * sum(width[0..c))
+    std::vector<dfd_column> outs(n_cols);
+    size_t off = 0;
+    for (int i = 0; i < n_cols; ++i) {
+        outs[i] = in_cols[i];
+        outs[i].values = (void*)off;  // peer mode: byte offset into every window slot
+        outs[i].validity = nullptr;
+        outs[i].offset = 0;
+        out_cols[i] = in_cols[i];
+        out_cols[i].values = (char*)peer_base[x->rank] + off;
+        out_cols[i].validity = nullptr;
+        out_cols[i].offset = 0;
+        off += (size_t)capacity_rows * (size_t)in_cols[i].width;
+    }
+    int rc;
+    PartitionJob job;
+    if ((rc = job.prepare(part, in_cols, n_cols, n_rows, outs.data(), true, s))) return rc;
+    if ((rc = job.run_hist_scan())) return rc;
+    if (T > 1) {
+        NCCL_TRY(n->AllGather(job.d_totals, x->d_counts, N, ncclInt64, x->comm, s), "ncclAllGather(counts)");
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(x->d_counts, job.d_totals, sizeof(int64_t) * N, cudaMemcpyDeviceToDevice, s), "copy counts");
+    }
+    k_exchange_plan<<<1, 32, 0, s>>>(x->d_counts, T, P, x->rank, capacity_rows, x->d_dest_base, x->d_my_starts, x->d_abort);
+    CUDA_TRY(cudaGetLastError(), "k_exchange_plan");
+    c->metrics.kernel_launches++;
+    if ((rc = job.run_scatter(x->d_dest_base, peer_base, T, P, x->d_abort))) return rc;
+    // every producer's stores must have landed before any consumer reads its window
+    if (T > 1) NCCL_TRY(n->AllReduce(x->d_token, x->d_token, 1, ncclInt32, ncclSum, x->comm, s), "ncclAllReduce(barrier)");
+    if (e_k) CUDA_TRY(cudaEventRecord(e_k, s), "record");
+    CUDA_TRY(cudaMemcpyAsync(x->h_my_starts, x->d_my_starts, sizeof(int64_t) * (P + 1), cudaMemcpyDeviceToHost, s), "D2H starts");
+    CUDA_TRY(cudaMemcpyAsync(x->h_abort, x->d_abort, sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H flag");
+    CUDA_TRY(cudaStreamSynchronize(s), "fused shuffle");
+    if (*x->h_abort)
+        return set_error(DFD_ERR_CAPACITY, "a receive window slot (%zu B = %lld rows) is too small for this shuffle", slot_bytes,
+                         (long long)capacity_rows);
+    x->bytes_received += (uint64_t)x->h_my_starts[P] * rb;
+    x->bytes_sent += (uint64_t)n_rows * rb;
+    return DFD_OK;
+}
+
 /* The shuffle: producer task `rank` holds n_rows local rows; afterwards this
  * worker, as consumer task `rank`, holds its P = partitions_per_task
  * destinations (global partitions rank*P .. rank*P+P-1), each contiguous, rows
@@ -353,47 +425,9 @@ int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* part, int mode, const d
     x->shuffles++;
 
     if (mode == DFD_EXCHANGE_FUSED) {
-        if (!x->window_ready) return set_error(DFD_ERR_INVALID_ARGUMENT, "fused exchange needs dfd_exchange_setup_window first");
-        const size_t rb = row_bytes_of(in_cols, n_cols);
-        if (rb == 0) return set_error(DFD_ERR_INVALID_ARGUMENT, "no fixed-width columns");
-        const int64_t capacity_rows = (int64_t)(x->window_bytes / rb) / 16 * 16;
-        // window layout (identical on every rank): column c at byte offset capacity_rows * sum(width[0..c))
-        std::vector<dfd_column> outs(n_cols);
-        size_t off = 0;
-        for (int i = 0; i < n_cols; ++i) {
-            outs[i] = in_cols[i];
-            outs[i].values = (void*)off;  // peer mode: byte offset into every window
-            outs[i].validity = nullptr;
-            outs[i].offset = 0;
-            out_cols[i] = in_cols[i];
-            out_cols[i].values = (char*)x->window + off;
-            out_cols[i].validity = nullptr;
-            out_cols[i].offset = 0;
-            off += (size_t)capacity_rows * (size_t)in_cols[i].width;
-        }
-        PartitionJob job;
-        if ((rc = job.prepare(part, in_cols, n_cols, n_rows, outs.data(), true, s))) return rc;
-        if ((rc = job.run_hist_scan())) return rc;
-        if (T > 1) {
-            NCCL_TRY(n->AllGather(job.d_totals, x->d_counts, N, ncclInt64, x->comm, s), "ncclAllGather(counts)");
-        } else {
-            CUDA_TRY(cudaMemcpyAsync(x->d_counts, job.d_totals, sizeof(int64_t) * N, cudaMemcpyDeviceToDevice, s), "copy counts");
-        }
-        k_exchange_plan<<<1, 32, 0, s>>>(x->d_counts, T, P, x->rank, capacity_rows, x->d_dest_base, x->d_my_starts, x->d_abort);
-        CUDA_TRY(cudaGetLastError(), "k_exchange_plan");
-        c->metrics.kernel_launches++;
-        if ((rc = job.run_scatter(x->d_dest_base, x->peer_window, T, P, x->d_abort))) return rc;
-        // every producer's stores must have landed before any consumer reads its window
-        if (T > 1) NCCL_TRY(n->AllReduce(x->d_token, x->d_token, 1, ncclInt32, ncclSum, x->comm, s), "ncclAllReduce(barrier)");
-        CUDA_TRY(cudaMemcpyAsync(x->h_my_starts, x->d_my_starts, sizeof(int64_t) * (P + 1), cudaMemcpyDeviceToHost, s), "D2H starts");
-        CUDA_TRY(cudaMemcpyAsync(x->h_abort, x->d_abort, sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H flag");
-        CUDA_TRY(cudaStreamSynchronize(s), "fused shuffle");
-        if (*x->h_abort)
-            return set_error(DFD_ERR_CAPACITY, "a receive window (%zu B = %lld rows) is too small for this shuffle", x->window_bytes,
-                             (long long)capacity_rows);
+        rc = fused_shuffle_locked(x, part, in_cols, n_cols, n_rows, P, 0, 1, out_cols, nullptr);
+        if (rc) return rc;
         memcpy(part_starts_host, x->h_my_starts, sizeof(int64_t) * (P + 1));
-        x->bytes_received += (uint64_t)part_starts_host[P] * rb;
-        x->bytes_sent += (uint64_t)n_rows * rb;
         return DFD_OK;
     }
     if (mode != DFD_EXCHANGE_NCCL) return set_error(DFD_ERR_INVALID_ARGUMENT, "unknown exchange mode %d", mode);
@@ -467,6 +501,95 @@ int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* part, int mode, const d
     }
     if (T > 1) NCCL_TRY(n->GroupEnd(), "ncclGroupEnd");
     CUDA_TRY(cudaStreamSynchronize(s), "nccl exchange");
+    return DFD_OK;
+}
+
+/* Host-to-host shuffle (the end-to-end path of the multi-worker exchange): this worker's rows live in
+ * HOST column buffers, its received destinations are delivered into HOST (ideally pinned) buffers.
+ * The rows are cut into `n_chunks` equal pieces (every worker must pass the same n_chunks: each chunk
+ * is one collective fused shuffle) and pipelined: H2D of chunk i+1 and D2H of chunk i-1 overlap the
+ * shuffle of chunk i (two input stages, two receive-window slots).  Output: chunk-major — chunk i's
+ * destination q occupies rows [chunk_part_starts[i*(P+1)+q], chunk_part_starts[i*(P+1)+q+1]) of
+ * every out column (absolute row offsets), exactly like a stream of per-destination record batches. */
+int dfd_shuffle_host(dfd_exchange* x, dfd_partitioner* part, const dfd_column* in_cols, int n_cols, int64_t n_rows,
+                     uint32_t partitions_per_task, int n_chunks, const dfd_column* out_cols, int64_t out_capacity_rows,
+                     int64_t* chunk_part_starts) {
+    if (!x || !part || !in_cols || !out_cols || !chunk_part_starts || n_chunks < 1 || n_rows < 0)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_shuffle_host: bad arguments");
+    dfd_ctx* c = x->ctx;
+    const uint32_t P = partitions_per_task;
+    if ((uint64_t)P * x->world != part->N)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "num_partitions %u != partitions_per_task %u x %d workers", part->N, P, x->world);
+    for (int i = 0; i < n_cols; ++i)
+        if (in_cols[i].kind != DFD_COL_FIXED || in_cols[i].validity || in_cols[i].offset != 0 || out_cols[i].kind != DFD_COL_FIXED ||
+            out_cols[i].width != in_cols[i].width || !in_cols[i].values || !out_cols[i].values)
+            return set_error(DFD_ERR_UNSUPPORTED, "column %d: dfd_shuffle_host moves fixed-width non-null columns", i);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device), "cudaSetDevice");
+    int rc = ensure_count_buffers(x, part->N);
+    if (rc) return rc;
+    if (!x->s_h2d) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&x->s_h2d, cudaStreamNonBlocking), "stream");
+        CUDA_TRY(cudaStreamCreateWithFlags(&x->s_d2h, cudaStreamNonBlocking), "stream");
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&x->e_h2d[i], cudaEventDisableTiming), "event");
+            CUDA_TRY(cudaEventCreateWithFlags(&x->e_k[i], cudaEventDisableTiming), "event");
+            CUDA_TRY(cudaEventCreateWithFlags(&x->e_d2h[i], cudaEventDisableTiming), "event");
+        }
+    }
+    const int64_t max_chunk = (n_rows + n_chunks - 1) / n_chunks + 1;
+    std::vector<size_t> col_off(n_cols);
+    size_t stage_bytes = 0;
+    for (int i = 0; i < n_cols; ++i) {
+        col_off[i] = stage_bytes;
+        stage_bytes += ((size_t)max_chunk * in_cols[i].width + 255) & ~(size_t)255;
+    }
+    for (int k = 0; k < 2; ++k)
+        if ((rc = x->in_stage[k].ensure(stage_bytes + 256, c->device))) return rc;
+    auto chunk_lo = [&](int i) { return (int64_t)((__int128)n_rows * i / n_chunks); };
+    auto issue_h2d = [&](int i) -> int {
+        const int k = i & 1;
+        const int64_t lo = chunk_lo(i), rows = chunk_lo(i + 1) - lo;
+        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(x->s_h2d, x->e_k[k], 0), "wait");  // kernels of chunk i-2 read this stage
+        for (int cidx = 0; cidx < n_cols; ++cidx) {
+            const size_t w = (size_t)in_cols[cidx].width;
+            if (rows)
+                CUDA_TRY(cudaMemcpyAsync((char*)x->in_stage[k].ptr + col_off[cidx], (const char*)in_cols[cidx].values + (size_t)lo * w,
+                                         (size_t)rows * w, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
+        }
+        CUDA_TRY(cudaEventRecord(x->e_h2d[k], x->s_h2d), "record");
+        return DFD_OK;
+    };
+    int64_t out_row = 0;
+    if ((rc = issue_h2d(0))) return rc;
+    std::vector<dfd_column> dev_in(n_cols), win(n_cols);
+    for (int i = 0; i < n_chunks; ++i) {
+        const int k = i & 1;
+        if (i + 1 < n_chunks && (rc = issue_h2d(i + 1))) return rc;
+        const int64_t rows = chunk_lo(i + 1) - chunk_lo(i);
+        for (int cidx = 0; cidx < n_cols; ++cidx) {
+            dev_in[cidx] = in_cols[cidx];
+            dev_in[cidx].values = (char*)x->in_stage[k].ptr + col_off[cidx];
+        }
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, x->e_h2d[k], 0), "wait");
+        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, x->e_d2h[k], 0), "wait");  // my window slot k has been drained
+        x->shuffles++;
+        if ((rc = fused_shuffle_locked(x, part, dev_in.data(), n_cols, rows, P, k, 2, win.data(), x->e_k[k]))) return rc;
+        const int64_t got = x->h_my_starts[P];
+        if (out_row + got > out_capacity_rows)
+            return set_error(DFD_ERR_CAPACITY, "dfd_shuffle_host: out buffers hold %lld rows, need more than %lld", (long long)out_capacity_rows,
+                             (long long)(out_row + got));
+        for (uint32_t q = 0; q <= P; ++q) chunk_part_starts[(size_t)i * (P + 1) + q] = out_row + x->h_my_starts[q];
+        for (int cidx = 0; cidx < n_cols; ++cidx) {
+            const size_t w = (size_t)in_cols[cidx].width;
+            if (got)
+                CUDA_TRY(cudaMemcpyAsync((char*)out_cols[cidx].values + (size_t)out_row * w, win[cidx].values, (size_t)got * w,
+                                         cudaMemcpyDeviceToHost, x->s_d2h), "D2H");
+        }
+        CUDA_TRY(cudaEventRecord(x->e_d2h[k], x->s_d2h), "record");
+        out_row += got;
+    }
+    CUDA_TRY(cudaStreamSynchronize(x->s_d2h), "D2H drain");
     return DFD_OK;
 }
 

@@ -158,6 +158,18 @@ class NetworkShuffleExec:
         self._starts = np.frombuffer(starts, dtype=np.int64).copy()
         return self._out, self._starts
 
+    def shuffle_host(self, exchange: ShuffleExchange, host_in: Sequence[DeviceColumn], n_rows: int, n_chunks: int,
+                     host_out: Sequence[DeviceColumn], out_capacity_rows: int) -> np.ndarray:
+        """Host-to-host pipelined shuffle (`dfd_shuffle_host`): `host_in` / `host_out` describe HOST (pinned)
+        column buffers.  Returns chunk_part_starts[n_chunks][P+1] (absolute row offsets into host_out)."""
+        if self._part is None:
+            self._part = HashPartitioner(exchange.ctx, self.input_stage.plan)
+        P = self.properties.partition_count
+        starts = (C.c_int64 * (n_chunks * (P + 1)))()
+        nv.check(nv.lib().dfd_shuffle_host(exchange._h, self._part._h, columns_to_c(host_in), len(host_in), n_rows, P, n_chunks,
+                                           columns_to_c(host_out), out_capacity_rows, starts))
+        return np.frombuffer(starts, dtype=np.int64).reshape(n_chunks, P + 1).copy()
+
     def execute(self, partition: int, task_ctx: DistributedTaskContext):
         """≙ NetworkShuffleExec::execute(partition, ctx): rows with
         hash % (P*T) == P*task_index + partition, as (columns, first_row, end_row)."""

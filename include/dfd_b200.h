@@ -268,6 +268,19 @@ int dfd_exchange_plan(int world, uint32_t partitions_per_task, int rank, const i
 int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* p, int mode, const dfd_column* in_cols, int n_cols,
                        int64_t n_rows, uint32_t partitions_per_task, dfd_column* out_cols,
                        int64_t out_capacity_rows, int64_t* part_starts_host);
+/* Host-to-host collective shuffle (end-to-end path of the multi-worker exchange; replaces, per
+ * worker, "execute the producer plan, Flight-encode, stream, decode" of
+ * src/worker/impl_execute_task.rs:36-169 + src/worker/worker_connection_pool.rs:143-390 for
+ * fixed-width non-null columns).  HOST in_cols (n_rows) -> HOST out_cols (out_capacity_rows;
+ * pinned memory from dfd_host_alloc gives full PCIe rate).  The rows are cut into n_chunks
+ * equal pieces — one fused collective shuffle each, so every worker must pass the same
+ * n_chunks — and H2D(i+1) | shuffle(i) | D2H(i-1) overlap (needs a receive window of
+ * at least 2 x the per-chunk receive size).  Output is chunk-major, like a stream of
+ * per-destination batches: chunk i / local partition q = rows
+ * [chunk_part_starts[i*(P+1)+q], chunk_part_starts[i*(P+1)+q+1]) of every out column. */
+int dfd_shuffle_host(dfd_exchange* x, dfd_partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,
+                     uint32_t partitions_per_task, int n_chunks, const dfd_column* out_cols,
+                     int64_t out_capacity_rows, int64_t* chunk_part_starts);
 int dfd_exchange_stats(dfd_exchange* x, uint64_t* bytes_sent, uint64_t* bytes_received, uint64_t* shuffles);
 
 int dfd_metrics_get(dfd_ctx* ctx, dfd_metrics* out);

@@ -67,6 +67,31 @@ def main():
                         failures += 1
                         print(f"rank {rank}: MISMATCH mode={name} N={N} q={q} col={c}", flush=True)
             dist.barrier()
+    # host-to-host pipelined shuffle: row-set equality per destination (chunk-major output)
+    P, N = 8 // world if 8 % world == 0 else 1, (8 // world if 8 % world == 0 else 1) * world
+    ref, rc, rs = orc.repartition_table(cols, [0], N, 8192, 1)
+    node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0], P), uuid.uuid4(), 3, world, world)
+    cap = int(n_rows * 1.5 / world) + 1024
+    pin_in = dfd.PinnedTable(ctx, hi - lo, [np.int64] * n_cols)
+    pin_out = dfd.PinnedTable(ctx, cap, [np.int64] * n_cols)
+    for c in range(n_cols):
+        pin_in.columns[c][:] = cols[c][lo:hi]
+    h_in = [dfd.DeviceColumn(nv.COL_FIXED, 8, a.ctypes.data, length=hi - lo) for a in pin_in.columns]
+    h_out = [dfd.DeviceColumn(nv.COL_FIXED, 8, a.ctypes.data, length=cap) for a in pin_out.columns]
+    for n_chunks in (1, 5):
+        cps = node.shuffle_host(ex, h_in, hi - lo, n_chunks, h_out, cap)
+        for q in range(P):
+            g = rank * P + q
+            segs = [np.arange(cps[i, q], cps[i, q + 1]) for i in range(n_chunks)]
+            idx = np.concatenate(segs) if segs else np.zeros(0, dtype=np.int64)
+            got = [pin_out.columns[c][idx] for c in range(n_cols)]
+            order = np.argsort(got[1], kind="stable")  # col1 = row_id*8+1: canonical order
+            want_order = np.argsort(ref[1][rs[g]:rs[g + 1]], kind="stable")
+            for c in range(n_cols):
+                if not np.array_equal(got[c][order], ref[c][rs[g]:rs[g + 1]][want_order]):
+                    failures += 1
+                    print(f"rank {rank}: MISMATCH shuffle_host n_chunks={n_chunks} q={q} col={c}", flush=True)
+        dist.barrier()
     # window overflow is reported, not written
     node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([1], 1), uuid.uuid4(), 2, world, world)
     t = torch.zeros(hi - lo, dtype=torch.int64, device="cuda")
