@@ -268,7 +268,7 @@ def run_multi_gpu(args, torch, dfd, world):
     torch.cuda.synchronize()
     ctx.synchronize()
     with ClockSampler(local_rank) as clocks:
-        for _ in range(0 if args.no_soak else 100):  # untimed soak (collective: same count on every rank)
+        for _ in range(0 if args.no_soak else 400):  # untimed soak (collective: same count on every rank)
             step()
         ctx.reset_metrics()
         dist.barrier()

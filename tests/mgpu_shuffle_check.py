@@ -32,7 +32,7 @@ def main():
     ctx = dfd.WorkerContext(local_rank)
     ex = dfd.ShuffleExchange(ctx, rank, world, uid[0])
     n_rows, n_cols = int(os.environ.get("DFD_CHECK_ROWS", 1_000_003)), 4
-    ex.setup_window(int(n_rows * n_cols * 8 * 1.5 / world) + (1 << 20))
+    ex.setup_window(int(n_rows * n_cols * 8 * 3.2 / world) + (1 << 20))  # two slots of 1.6x the fair share
     cols = cfg2_columns(n_rows, n_cols)
     lo, hi = rank * n_rows // world, (rank + 1) * n_rows // world
     failures = 0
