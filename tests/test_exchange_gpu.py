@@ -67,3 +67,31 @@ def test_multi_gpu_shuffle_under_torchrun(built):
            "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_shuffle_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "MGPU_SHUFFLE_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n_chunks", [1, 3, 7])
+def test_single_worker_host_to_host_shuffle(ctx, n_chunks):
+    """dfd_shuffle_host at world=1: pinned host columns in, chunk-major host segments out."""
+    n, P = 250_003, 8
+    cols = cfg2_columns(n, 3)
+    ex = dfd.ShuffleExchange(ctx, 0, 1, None)
+    ex.setup_window(2 * (n * 3 * 8 + (1 << 16)))
+    node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0], P), uuid.uuid4(), 1, 1, 1)
+    pin_in = dfd.PinnedTable(ctx, n, [np.int64] * 3)
+    pin_out = dfd.PinnedTable(ctx, n, [np.int64] * 3)
+    for c in range(3):
+        pin_in.columns[c][:] = cols[c]
+    h_in = [dfd.DeviceColumn(nv.COL_FIXED, 8, a.ctypes.data, length=n) for a in pin_in.columns]
+    h_out = [dfd.DeviceColumn(nv.COL_FIXED, 8, a.ctypes.data, length=n) for a in pin_out.columns]
+    cps = node.shuffle_host(ex, h_in, n, n_chunks, h_out, n)
+    assert cps[-1, -1] == n
+    ref, rc, rs = orc.repartition_table(cols, [0], P, 8192, 1)
+    for q in range(P):
+        # one producer: concatenating the chunks of destination q reproduces the oracle's order exactly
+        idx = np.concatenate([np.arange(cps[i, q], cps[i, q + 1]) for i in range(n_chunks)])
+        for c in range(3):
+            assert np.array_equal(pin_out.columns[c][idx], ref[c][rs[q]:rs[q + 1]]), (q, c)
+    with pytest.raises(dfd.DfdError) as e:
+        node.shuffle_host(ex, h_in, n, n_chunks, h_out, n // 2)
+    assert e.value.status == 7
+    ex.close()
