@@ -128,10 +128,16 @@ def cpu_reference_arm(n_rows: int, threads: int, reps: int):
 
 
 def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path on the host cores.
+    N = 1: local `RepartitionExec(Hash)` (BASELINE configs[1]: "vs CPU RepartitionExec").
+    N > 1: N producer tasks -> N consumer tasks: CPU repartition + Arrow Flight (IPC + LZ4, localhost gRPC)
+           exchange — `oracle/flight_proxy.py`, the stand-in for impl_execute_task + WorkerConnectionPool.
+    The real crate cannot be built here (no Rust toolchain), so both are the oracle port ("kind": "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    world = max(1, args.gpus)
     sample_rows = 1 << 23
     vals = []
     t_all = time.perf_counter()
@@ -139,14 +145,41 @@ def run_reference(args):
     from tests.util import cfg2_columns
 
     cols = cfg2_columns(sample_rows, N_COLS)
-    for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        orc.repartition_table(cols, [0], NUM_PARTITIONS, 8192, threads, materialize=False)
-        dt = time.perf_counter() - t0
-        if i >= args.warmup:
-            vals.append(dt)
-        if time.perf_counter() - t_all > 150 and len(vals) >= 1:
-            break
+    extra = {}
+    if world == 1:
+        what = ("oracle port of DataFusion RepartitionExec(Hash) + LimitedBatchCoalescer, one thread per input partition")
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            orc.repartition_table(cols, [0], NUM_PARTITIONS, 8192, threads, materialize=False)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                vals.append(dt)
+            if time.perf_counter() - t_all > 150 and len(vals) >= 1:
+                break
+    else:
+        from oracle.flight_proxy import FlightShuffleProxy
+
+        total_parts = NUM_PARTITIONS if NUM_PARTITIONS % world == 0 else NUM_PARTITIONS * world
+        P = total_parts // world
+        names = [f"c{j}" for j in range(N_COLS)]
+        prod = [[c[r * sample_rows // world:(r + 1) * sample_rows // world] for c in cols] for r in range(world)]
+        tpp = max(1, threads // world)
+        what = (f"{world} producer tasks -> {world} consumer tasks in one process: oracle port of RepartitionExec(Hash, {total_parts}) "
+                f"({tpp} threads per producer) + pyarrow.flight localhost gRPC exchange, Arrow IPC with LZ4_FRAME (the reference default)")
+        px = FlightShuffleProxy(names, world, world, P, "lz4")
+        for i in range(args.warmup + args.steps):
+            dt, rows, _ = px.run(prod, tpp)
+            assert rows == sample_rows
+            if i >= args.warmup:
+                vals.append(dt)
+            if time.perf_counter() - t_all > 120 and len(vals) >= 1:
+                break
+        px.close()
+        px = FlightShuffleProxy(names, world, world, P, None)  # uncompressed, for context
+        px.run(prod, tpp)
+        dt_nc, _, _ = px.run(prod, tpp)
+        px.close()
+        extra["uncompressed_rows_per_s"] = sample_rows / dt_nc
     ms = 1e3 * sum(vals) / len(vals)
     v = sample_rows / (ms / 1e3)
     line = {
@@ -154,9 +187,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int64", "data": "synthetic",
         "config": {"workload": "cfg2: 8xInt64, Hash([col0], 8), batch 8192; bounded sample", "rows_per_step": sample_rows},
-        "cpu_baseline": {"value": v, "unit": "rows/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample_rows} rows (1/8 of the 2^26-row workload) per step, oracle port of "
-                                   "DataFusion RepartitionExec(Hash) + LimitedBatchCoalescer, one thread per input partition"},
+        "cpu_baseline": dict({"value": v, "unit": "rows/s", "cores": threads, "kind": "port",
+                              "sample": f"{sample_rows} rows (1/8 of the 2^26-row workload) per step; {what}"}, **extra),
         "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))

@@ -114,3 +114,24 @@ def test_distribution_sanity():
     dest = orc.partition_ids([np.arange(100_000, dtype=np.int64)], 100_000, 8)
     counts = np.bincount(dest, minlength=8)
     assert counts.min() >= 12_300 and counts.max() <= 12_700
+
+
+def test_flight_proxy_reference_arm_is_a_correct_shuffle():
+    """The CPU+Flight stand-in used by `bench.py --impl reference --gpus N` delivers the right row sets."""
+    import pyarrow as pa
+
+    from oracle.flight_proxy import FlightShuffleProxy
+
+    n, T, P = 30_000, 2, 4
+    cols = cfg2_columns(n, 3)
+    px = FlightShuffleProxy(["c0", "c1", "c2"], T, T, P, "lz4")
+    try:
+        prod = [[c[r * n // T:(r + 1) * n // T] for c in cols] for r in range(T)]
+        dt, rows, tables = px.run(prod, 1)
+        assert rows == n
+        dest = orc.partition_ids([cols[0]], n, P * T)
+        for ci in range(T):
+            got = np.sort(pa.concat_tables(tables[ci]).column("c1").to_numpy())
+            assert np.array_equal(got, np.sort(cols[1][(dest // P) == ci]))
+    finally:
+        px.close()
