@@ -443,6 +443,54 @@ int dfd::PartitionJob::run_varwidth() {
     return DFD_OK;
 }
 
+int dfd::launch_bits_to_bytes(const uint8_t* bits, int64_t bit_offset, int64_t n, uint8_t* out, cudaStream_t s) {
+    if (n <= 0) return DFD_OK;
+    k_bits_to_bytes<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(bits, bit_offset, n, out);
+    LAUNCH_CHECK("k_bits_to_bytes");
+    return DFD_OK;
+}
+
+int dfd::launch_bytes_to_bits(const uint8_t* in, int64_t n, void* out_words, cudaStream_t s) {
+    if (n <= 0) return DFD_OK;
+    k_bytes_to_bits<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(in, n, (unsigned*)out_words);
+    LAUNCH_CHECK("k_bytes_to_bits");
+    return DFD_OK;
+}
+
+int dfd::launch_offsets_to_lengths(const void* off, int ow, int64_t n, void* len, cudaStream_t s) {
+    if (n <= 0) return DFD_OK;
+    const unsigned grid = (unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256);
+    if (ow == 8) k_offsets_to_lengths<int64_t><<<grid, 256, 0, s>>>((const int64_t*)off, n, (int64_t*)len);
+    else k_offsets_to_lengths<int32_t><<<grid, 256, 0, s>>>((const int32_t*)off, n, (int32_t*)len);
+    LAUNCH_CHECK("k_offsets_to_lengths");
+    return DFD_OK;
+}
+
+int dfd::launch_var_dest_bytes(const void* off, int ow, const int64_t* part_starts, uint32_t N, int64_t* bytes, int64_t* first, cudaStream_t s) {
+    const unsigned grid = (N + 255) / 256;
+    if (ow == 8) k_var_dest_bytes<int64_t><<<grid, 256, 0, s>>>((const int64_t*)off, part_starts, N, bytes, first);
+    else k_var_dest_bytes<int32_t><<<grid, 256, 0, s>>>((const int32_t*)off, part_starts, N, bytes, first);
+    LAUNCH_CHECK("k_var_dest_bytes");
+    return DFD_OK;
+}
+
+int dfd::launch_lengths_to_offsets(const void* len, int ow, int64_t n, unsigned long long* block_sums, void* out_off, cudaStream_t s) {
+    if (n <= 0) {
+        cudaError_t e = cudaMemsetAsync(out_off, 0, (size_t)ow, s);
+        return e == cudaSuccess ? DFD_OK : cuda_error(e, "cudaMemsetAsync");
+    }
+    const int64_t n_blocks = (n + VAR_BLOCK * VAR_ITEMS - 1) / (VAR_BLOCK * VAR_ITEMS);
+    if (ow == 8) k_len_block_sums<int64_t><<<(unsigned)n_blocks, VAR_BLOCK, 0, s>>>((const int64_t*)len, n, block_sums);
+    else k_len_block_sums<int32_t><<<(unsigned)n_blocks, VAR_BLOCK, 0, s>>>((const int32_t*)len, n, block_sums);
+    LAUNCH_CHECK("k_len_block_sums");
+    k_var_scan_block_sums<<<1, 1024, 0, s>>>(block_sums, n_blocks);
+    LAUNCH_CHECK("k_var_scan_block_sums");
+    if (ow == 8) k_len_write_offsets<int64_t><<<(unsigned)n_blocks, VAR_BLOCK, 0, s>>>((const int64_t*)len, n, block_sums, (int64_t*)out_off);
+    else k_len_write_offsets<int32_t><<<(unsigned)n_blocks, VAR_BLOCK, 0, s>>>((const int32_t*)len, n, block_sums, (int32_t*)out_off);
+    LAUNCH_CHECK("k_len_write_offsets");
+    return DFD_OK;
+}
+
 int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,
                                  const dfd_column* out_cols, cudaStream_t stream) {
     PartitionJob job;

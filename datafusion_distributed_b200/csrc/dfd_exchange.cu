@@ -149,6 +149,7 @@ struct dfd_exchange {
     uint32_t cap_N = 0;
     // NCCL mode staging (locally partitioned columns)
     Scratch send;
+    Scratch recv_tmp;  // receiver-side temporaries (u8 images of bitmaps, string lengths)
     // fused mode: receive window + peers' mappings
     void* window = nullptr;
     size_t window_bytes = 0;
@@ -267,6 +268,7 @@ void dfd_exchange_destroy(dfd_exchange* x) {
         cudaFree(x->d_my_starts);
         cudaFree(x->d_abort);
         cudaFree(x->send.ptr);
+        cudaFree(x->recv_tmp.ptr);
         cudaFree(x->in_stage[0].ptr);
         cudaFree(x->in_stage[1].ptr);
         for (int i = 0; i < 2; ++i) {
@@ -433,24 +435,65 @@ int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* part, int mode, const d
     if (mode != DFD_EXCHANGE_NCCL) return set_error(DFD_ERR_INVALID_ARGUMENT, "unknown exchange mode %d", mode);
 
     // ---- NCCL mode: partition locally into a staging buffer, then grouped send/recv ----
+    // Every column kind the local partitioner supports travels: fixed-width values as they are,
+    // bitmaps (validity, booleans) as one byte per row, strings as (lengths, bytes); the receiver
+    // rebuilds bitmaps and offsets (k_bytes_to_bits, lengths -> offsets scan).
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    struct XCol {
+        int kind, width, ow;
+        bool has_valid;
+        size_t st_values, st_valid, st_off;        // staging offsets (destination-sorted local output)
+        size_t cv_valid, cv_values, cv_len;        // sender-side conversions (u8 per row / lengths)
+        size_t rv_valid, rv_values, rv_len;        // receiver-side temporaries
+        int64_t cap_bytes;                          // var-width: staging byte capacity
+    };
+    std::vector<XCol> xc(n_cols);
     size_t stage_bytes = 0;
-    std::vector<size_t> col_off(n_cols), val_off(n_cols);
     for (int i = 0; i < n_cols; ++i) {
         const dfd_column& ic = in_cols[i];
-        col_off[i] = stage_bytes;
-        stage_bytes += ic.kind == DFD_COL_FIXED ? (((size_t)n_rows * ic.width + 255) & ~(size_t)255) : 0;
-        if (ic.kind != DFD_COL_FIXED || ic.validity)
-            return set_error(DFD_ERR_UNSUPPORTED, "column %d: the device exchange moves fixed-width non-null columns (validity / bit / var-width: next)", i);
+        XCol& c0 = xc[i];
+        c0 = XCol{};
+        c0.kind = ic.kind; c0.width = ic.width; c0.ow = ic.kind == DFD_COL_LARGE_UTF8 ? 8 : 4;
+        c0.has_valid = ic.validity != nullptr;
         if (out_cols[i].kind != ic.kind || out_cols[i].width != ic.width || !out_cols[i].values)
             return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: out layout mismatch", i);
+        if (c0.has_valid && !out_cols[i].validity) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: out validity is NULL", i);
+        const size_t bm = al((size_t)((n_rows + 63) / 64 * 8 + 8));
+        if (ic.kind == DFD_COL_FIXED) {
+            c0.st_values = stage_bytes; stage_bytes += al((size_t)n_rows * ic.width + 16);
+        } else if (ic.kind == DFD_COL_BOOL) {
+            c0.st_values = stage_bytes; stage_bytes += bm;
+            c0.cv_values = stage_bytes; stage_bytes += al((size_t)n_rows + 16);
+        } else if (ic.kind == DFD_COL_UTF8 || ic.kind == DFD_COL_LARGE_UTF8 || ic.kind == DFD_COL_BINARY) {
+            if (!out_cols[i].offsets) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: out offsets is NULL", i);
+            c0.cap_bytes = ic.values_bytes > 0 ? ic.values_bytes : 16;
+            c0.st_off = stage_bytes; stage_bytes += al((size_t)(n_rows + 1) * c0.ow + 16);
+            c0.st_values = stage_bytes; stage_bytes += al((size_t)c0.cap_bytes + 16);
+            c0.cv_len = stage_bytes; stage_bytes += al((size_t)(n_rows + 1) * c0.ow + 16);
+        } else {
+            return set_error(DFD_ERR_UNSUPPORTED, "column %d: unknown column kind %d", i, ic.kind);
+        }
+        if (c0.has_valid) {
+            c0.st_valid = stage_bytes; stage_bytes += bm;
+            c0.cv_valid = stage_bytes; stage_bytes += al((size_t)n_rows + 16);
+        }
     }
+    const size_t meta_off = stage_bytes;               // per var column: bytes[N] | first[N] (device)
+    stage_bytes += al((size_t)n_cols * 2 * N * 8 + 64);
     if ((rc = x->send.ensure(stage_bytes + 256, c->device))) return rc;
+    char* sb = (char*)x->send.ptr;
     std::vector<dfd_column> staged(n_cols);
     for (int i = 0; i < n_cols; ++i) {
+        const XCol& c0 = xc[i];
         staged[i] = in_cols[i];
-        staged[i].values = (char*)x->send.ptr + col_off[i];
-        staged[i].validity = nullptr;
+        staged[i].values = sb + c0.st_values;
+        staged[i].offsets = c0.kind >= DFD_COL_UTF8 ? (void*)(sb + c0.st_off) : nullptr;
+        staged[i].validity = c0.has_valid ? (uint8_t*)(sb + c0.st_valid) : nullptr;
         staged[i].offset = 0;
+        staged[i].values_bytes = c0.cap_bytes;
+        const size_t bm = (size_t)((n_rows + 63) / 64 * 8 + 8);
+        if (c0.kind == DFD_COL_BOOL) CUDA_TRY(cudaMemsetAsync(sb + c0.st_values, 0, bm, s), "memset");
+        if (c0.has_valid) CUDA_TRY(cudaMemsetAsync(sb + c0.st_valid, 0, bm, s), "memset");
     }
     PartitionJob job;
     if ((rc = job.prepare(part, in_cols, n_cols, n_rows, staged.data(), false, s))) return rc;
@@ -462,7 +505,40 @@ int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* part, int mode, const d
         CUDA_TRY(cudaMemcpyAsync(x->d_counts, job.d_totals, sizeof(int64_t) * N, cudaMemcpyDeviceToDevice, s), "copy counts");
     }
     CUDA_TRY(cudaMemcpyAsync(x->h_counts, x->d_counts, sizeof(int64_t) * (size_t)N * T, cudaMemcpyDeviceToHost, s), "D2H counts");
-    CUDA_TRY(cudaStreamSynchronize(s), "count exchange");
+    // sender-side conversions + per-destination byte counts of the string columns
+    std::vector<int> var_cols;
+    for (int i = 0; i < n_cols; ++i) {
+        const XCol& c0 = xc[i];
+        if (c0.has_valid && (rc = launch_bits_to_bytes((const uint8_t*)(sb + c0.st_valid), 0, n_rows, (uint8_t*)(sb + c0.cv_valid), s))) return rc;
+        if (c0.kind == DFD_COL_BOOL && (rc = launch_bits_to_bytes((const uint8_t*)(sb + c0.st_values), 0, n_rows, (uint8_t*)(sb + c0.cv_values), s))) return rc;
+        if (c0.kind >= DFD_COL_UTF8) {
+            if ((rc = launch_offsets_to_lengths(sb + c0.st_off, c0.ow, n_rows, sb + c0.cv_len, s))) return rc;
+            int64_t* d_meta = (int64_t*)(sb + meta_off) + (size_t)var_cols.size() * 2 * N;
+            if ((rc = launch_var_dest_bytes(sb + c0.st_off, c0.ow, part->d_part_starts, N, d_meta, d_meta + N, s))) return rc;
+            var_cols.push_back(i);
+        }
+    }
+    // byte-count matrices of the string columns: all-gather [T][N] per column
+    const size_t V = var_cols.size();
+    std::vector<int64_t> h_first(V * N), h_bytes(V * (size_t)T * N);
+    int64_t* d_bytes_all = nullptr;
+    if (V) {
+        CUDA_TRY(cudaMalloc((void**)&d_bytes_all, sizeof(int64_t) * V * (size_t)T * N), "cudaMalloc(byte counts)");
+        for (size_t v = 0; v < V; ++v) {
+            int64_t* d_meta = (int64_t*)(sb + meta_off) + v * 2 * N;
+            if (T > 1) {
+                ncclResult_t r = n->AllGather(d_meta, d_bytes_all + v * (size_t)T * N, N, ncclInt64, x->comm, s);
+                if (r != ncclSuccess) { cudaFree(d_bytes_all); return nccl_error(r, "ncclAllGather(byte counts)"); }
+            } else {
+                cudaMemcpyAsync(d_bytes_all + v * N, d_meta, sizeof(int64_t) * N, cudaMemcpyDeviceToDevice, s);
+            }
+            cudaMemcpyAsync(h_first.data() + v * N, d_meta + N, sizeof(int64_t) * N, cudaMemcpyDeviceToHost, s);
+        }
+        cudaMemcpyAsync(h_bytes.data(), d_bytes_all, sizeof(int64_t) * V * (size_t)T * N, cudaMemcpyDeviceToHost, s);
+    }
+    cudaError_t se = cudaStreamSynchronize(s);
+    if (d_bytes_all) cudaFree(d_bytes_all);
+    if (se != cudaSuccess) return cuda_error(se, "count exchange");
     std::vector<int64_t> send_start(N), recv_start((size_t)P * T);
     int64_t recv_rows = 0;
     rc = dfd_exchange_plan(T, P, x->rank, x->h_counts, send_start.data(), recv_start.data(), part_starts_host, nullptr, &recv_rows);
@@ -470,23 +546,52 @@ int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* part, int mode, const d
     if (recv_rows > out_capacity_rows)
         return set_error(DFD_ERR_CAPACITY, "this worker receives %lld rows but out_capacity_rows is %lld", (long long)recv_rows,
                          (long long)out_capacity_rows);
-    const int64_t* cnt = x->h_counts;
-    if (T > 1) NCCL_TRY(n->GroupStart(), "ncclGroupStart");
+    // receive-side byte layout of every string column (same [q][r] order as the rows)
+    std::vector<std::vector<int64_t>> brecv_start(V);
+    for (size_t v = 0; v < V; ++v) {
+        brecv_start[v].resize((size_t)P * T);
+        int64_t total = 0;
+        rc = dfd_exchange_plan(T, P, x->rank, h_bytes.data() + v * (size_t)T * N, nullptr, brecv_start[v].data(), nullptr, nullptr, &total);
+        if (rc) return rc;
+        if (total > out_cols[var_cols[v]].values_bytes)
+            return set_error(DFD_ERR_CAPACITY, "column %d: receives %lld string bytes but out values_bytes is %lld", var_cols[v],
+                             (long long)total, (long long)out_cols[var_cols[v]].values_bytes);
+    }
+    // receiver temporaries: u8-per-row images of bitmaps, lengths of strings
+    size_t rtmp = 0;
     for (int i = 0; i < n_cols; ++i) {
-        const size_t w = (size_t)in_cols[i].width;
-        const char* sbuf = (const char*)staged[i].values;
-        char* rbuf = (char*)out_cols[i].values;
+        XCol& c0 = xc[i];
+        if (c0.has_valid) { c0.rv_valid = rtmp; rtmp += al((size_t)recv_rows + 64); }
+        if (c0.kind == DFD_COL_BOOL) { c0.rv_values = rtmp; rtmp += al((size_t)recv_rows + 64); }
+        if (c0.kind >= DFD_COL_UTF8) { c0.rv_len = rtmp; rtmp += al((size_t)(recv_rows + 1) * c0.ow + 64); }
+    }
+    const size_t rsums = rtmp;
+    rtmp += al((size_t)(recv_rows / (256 * 8) + 4) * 8);
+    if ((rc = x->recv_tmp.ensure(rtmp + 256, c->device))) return rc;
+    char* rt = (char*)x->recv_tmp.ptr;
+    const int64_t* cnt = x->h_counts;
+    // one "lane" = one fixed-stride row stream to move with the row count matrix
+    struct Lane { const char* src; char* dst; size_t w; };
+    std::vector<Lane> lanes;
+    for (int i = 0; i < n_cols; ++i) {
+        const XCol& c0 = xc[i];
+        if (c0.kind == DFD_COL_FIXED) lanes.push_back({sb + c0.st_values, (char*)out_cols[i].values, (size_t)c0.width});
+        if (c0.kind == DFD_COL_BOOL) lanes.push_back({sb + c0.cv_values, rt + c0.rv_values, 1});
+        if (c0.kind >= DFD_COL_UTF8) lanes.push_back({sb + c0.cv_len, rt + c0.rv_len, (size_t)c0.ow});
+        if (c0.has_valid) lanes.push_back({sb + c0.cv_valid, rt + c0.rv_valid, 1});
+    }
+    if (T > 1) NCCL_TRY(n->GroupStart(), "ncclGroupStart");
+    for (const Lane& ln : lanes) {
         for (uint32_t g = 0; g < N; ++g) {  // my rows of destination g -> its owner
             const int peer = (int)(g / P);
             const int64_t rows = cnt[(int64_t)x->rank * N + g];
             if (rows == 0) continue;
             if (peer == x->rank) {
-                const uint32_t q = g % P;
-                CUDA_TRY(cudaMemcpyAsync(rbuf + (size_t)recv_start[(size_t)q * T + x->rank] * w, sbuf + (size_t)send_start[g] * w,
-                                         (size_t)rows * w, cudaMemcpyDeviceToDevice, s), "local segment copy");
+                CUDA_TRY(cudaMemcpyAsync(ln.dst + (size_t)recv_start[(size_t)(g % P) * T + x->rank] * ln.w, ln.src + (size_t)send_start[g] * ln.w,
+                                         (size_t)rows * ln.w, cudaMemcpyDeviceToDevice, s), "local segment copy");
             } else {
-                NCCL_TRY(n->Send(sbuf + (size_t)send_start[g] * w, (size_t)rows * w, ncclInt8, peer, x->comm, s), "ncclSend");
-                x->bytes_sent += (uint64_t)rows * w;
+                NCCL_TRY(n->Send(ln.src + (size_t)send_start[g] * ln.w, (size_t)rows * ln.w, ncclInt8, peer, x->comm, s), "ncclSend");
+                x->bytes_sent += (uint64_t)rows * ln.w;
             }
         }
         for (int r = 0; r < T; ++r) {  // every producer's rows of my P destinations
@@ -494,12 +599,48 @@ int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* part, int mode, const d
             for (uint32_t q = 0; q < P; ++q) {
                 const int64_t rows = cnt[(int64_t)r * N + (int64_t)x->rank * P + q];
                 if (rows == 0) continue;
-                NCCL_TRY(n->Recv(rbuf + (size_t)recv_start[(size_t)q * T + r] * w, (size_t)rows * w, ncclInt8, r, x->comm, s), "ncclRecv");
-                x->bytes_received += (uint64_t)rows * w;
+                NCCL_TRY(n->Recv(ln.dst + (size_t)recv_start[(size_t)q * T + r] * ln.w, (size_t)rows * ln.w, ncclInt8, r, x->comm, s), "ncclRecv");
+                x->bytes_received += (uint64_t)rows * ln.w;
+            }
+        }
+    }
+    for (size_t v = 0; v < V; ++v) {  // string bytes, with their own count matrix
+        const int i = var_cols[v];
+        const int64_t* bc = h_bytes.data() + v * (size_t)T * N;
+        const char* src = sb + xc[i].st_values;
+        char* dst = (char*)out_cols[i].values;
+        for (uint32_t g = 0; g < N; ++g) {
+            const int peer = (int)(g / P);
+            const int64_t nb = bc[(int64_t)x->rank * N + g];
+            if (nb == 0) continue;
+            if (peer == x->rank) {
+                CUDA_TRY(cudaMemcpyAsync(dst + brecv_start[v][(size_t)(g % P) * T + x->rank], src + h_first[v * N + g], (size_t)nb,
+                                         cudaMemcpyDeviceToDevice, s), "local bytes copy");
+            } else {
+                NCCL_TRY(n->Send(src + h_first[v * N + g], (size_t)nb, ncclInt8, peer, x->comm, s), "ncclSend(bytes)");
+                x->bytes_sent += (uint64_t)nb;
+            }
+        }
+        for (int r = 0; r < T; ++r) {
+            if (r == x->rank) continue;
+            for (uint32_t q = 0; q < P; ++q) {
+                const int64_t nb = bc[(int64_t)r * N + (int64_t)x->rank * P + q];
+                if (nb == 0) continue;
+                NCCL_TRY(n->Recv(dst + brecv_start[v][(size_t)q * T + r], (size_t)nb, ncclInt8, r, x->comm, s), "ncclRecv(bytes)");
+                x->bytes_received += (uint64_t)nb;
             }
         }
     }
     if (T > 1) NCCL_TRY(n->GroupEnd(), "ncclGroupEnd");
+    // receiver-side rebuild of bitmaps and offsets
+    for (int i = 0; i < n_cols; ++i) {
+        const XCol& c0 = xc[i];
+        if (c0.has_valid && (rc = launch_bytes_to_bits((const uint8_t*)(rt + c0.rv_valid), recv_rows, out_cols[i].validity, s))) return rc;
+        if (c0.kind == DFD_COL_BOOL && (rc = launch_bytes_to_bits((const uint8_t*)(rt + c0.rv_values), recv_rows, out_cols[i].values, s))) return rc;
+        if (c0.kind >= DFD_COL_UTF8 &&
+            (rc = launch_lengths_to_offsets(rt + c0.rv_len, c0.ow, recv_rows, (unsigned long long*)(rt + rsums), out_cols[i].offsets, s)))
+            return rc;
+    }
     CUDA_TRY(cudaStreamSynchronize(s), "nccl exchange");
     return DFD_OK;
 }

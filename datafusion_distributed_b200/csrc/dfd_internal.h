@@ -87,6 +87,13 @@ struct PartitionJob {
     int run_varwidth();  // called by run_scatter after the fixed-width launches
 };
 
+// Small conversion kernels the exchange uses for bit-packed / variable-width columns (defined in dfd_api.cu).
+int launch_bits_to_bytes(const uint8_t* bits, int64_t bit_offset, int64_t n, uint8_t* out, cudaStream_t s);
+int launch_bytes_to_bits(const uint8_t* in, int64_t n, void* out_words, cudaStream_t s);
+int launch_offsets_to_lengths(const void* off, int ow, int64_t n, void* len, cudaStream_t s);
+int launch_var_dest_bytes(const void* off, int ow, const int64_t* part_starts, uint32_t N, int64_t* bytes, int64_t* first, cudaStream_t s);
+int launch_lengths_to_offsets(const void* len, int ow, int64_t n, unsigned long long* block_sums /*[n/2048 + 2]*/, void* out_off, cudaStream_t s);
+
 // Launches K1 -> K1b -> K2 on `stream`; caller holds ctx->mu and has set the device.
 int partition_device_locked(Partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,
                             const dfd_column* out_cols, cudaStream_t stream);

@@ -628,6 +628,81 @@ __global__ void __launch_bounds__(256) k_var_copy_bytes(const OFF* __restrict__ 
 
 // must mirror the offsets computed at the top of k_scatter (the peer / aligned tables are last,
 // so launches that do not use them simply do not allocate them)
+// ---------------------------------------------------------------------------
+// Exchange helpers for bit-packed and variable-width columns (NCCL mode): bitmaps travel as one
+// byte per row, strings as (lengths, bytes); the receiver rebuilds bitmaps and offsets.
+// ---------------------------------------------------------------------------
+__global__ void k_bits_to_bytes(const uint8_t* __restrict__ bits, int64_t bit_offset, int64_t n, uint8_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = bit_is_set(bits, i + bit_offset) ? 1 : 0;
+}
+
+// out bitmap words are fully written (n rounded up to 32 rows per warp): no pre-zeroing, no atomics
+__global__ void k_bytes_to_bits(const uint8_t* __restrict__ in, int64_t n, unsigned* __restrict__ out_words) {
+    const int64_t n32 = (n + 31) & ~(int64_t)31;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned b = __ballot_sync(0xffffffffu, i < n && in[i] != 0);
+        if ((threadIdx.x & 31) == 0) out_words[i >> 5] = b;
+    }
+}
+
+template <typename OFF>
+__global__ void k_offsets_to_lengths(const OFF* __restrict__ off, int64_t n, OFF* __restrict__ len) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) len[i] = off[i + 1] - off[i];
+}
+
+// bytes[g] / first[g] of every destination's run of a destination-sorted var-width column
+template <typename OFF>
+__global__ void k_var_dest_bytes(const OFF* __restrict__ off, const int64_t* __restrict__ part_starts, uint32_t N,
+                                 int64_t* __restrict__ bytes, int64_t* __restrict__ first) {
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x) {
+        const int64_t a = (int64_t)off[part_starts[g]], b = (int64_t)off[part_starts[g + 1]];
+        bytes[g] = b - a;
+        first[g] = a;
+    }
+}
+
+// lengths -> exclusive offsets, same 3-phase scan as K4 (phase b is k_var_scan_block_sums)
+template <typename OFF>
+__global__ void __launch_bounds__(VAR_BLOCK) k_len_block_sums(const OFF* __restrict__ len, int64_t n, unsigned long long* __restrict__ block_sums) {
+    __shared__ unsigned long long s_warp[VAR_BLOCK / 32];
+    const int64_t base = (int64_t)blockIdx.x * (VAR_BLOCK * VAR_ITEMS) + (int64_t)threadIdx.x * VAR_ITEMS;
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int k = 0; k < VAR_ITEMS; ++k)
+        if (base + k < n) sum += (unsigned long long)len[base + k];
+#pragma unroll
+    for (int sh = 16; sh >= 1; sh >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sh);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < VAR_BLOCK / 32; ++w) t += s_warp[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+template <typename OFF>
+__global__ void __launch_bounds__(VAR_BLOCK) k_len_write_offsets(const OFF* __restrict__ len, int64_t n,
+                                                                  const unsigned long long* __restrict__ block_sums, OFF* __restrict__ out_off) {
+    __shared__ unsigned long long s_warp[33];
+    const int64_t base = (int64_t)blockIdx.x * (VAR_BLOCK * VAR_ITEMS) + (int64_t)threadIdx.x * VAR_ITEMS;
+    unsigned long long l[VAR_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < VAR_ITEMS; ++k) {
+        l[k] = base + k < n ? (unsigned long long)len[base + k] : 0;
+        sum += l[k];
+    }
+    unsigned long long tot;
+    unsigned long long run = block_sums[blockIdx.x] + block_exclusive_scan_u64<VAR_BLOCK>(sum, s_warp, tot);
+#pragma unroll
+    for (int k = 0; k < VAR_ITEMS; ++k) {
+        if (base + k < n) out_off[base + k] = (OFF)run;
+        run += l[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out_off[n] = (OFF)block_sums[gridDim.x];
+}
+
 template <int THREADS, int K>
 inline size_t scatter_smem_bytes(uint32_t N, int stage_width, bool peer, bool aligned) {
     size_t off = ((size_t)THREADS * K * stage_width + 15) & ~(size_t)15;

@@ -67,6 +67,37 @@ def main():
                         failures += 1
                         print(f"rank {rank}: MISMATCH mode={name} N={N} q={q} col={c}", flush=True)
             dist.barrier()
+    # NCCL mode with nullable / boolean / string columns: per destination, rows from the producers in task order
+    import pyarrow as pa
+    from tests.test_exchange_gpu import _mixed_table
+    from tests.util import expected_partitions
+
+    m = 60_013
+    arrays = _mixed_table(m, 23)
+    mlo, mhi = rank * m // world, (rank + 1) * m // world
+    P2 = 3
+    N2 = P2 * world
+    node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0, 1], P2), uuid.uuid4(), 4, world, world)
+    in_cols2 = [dfd.DeviceColumn.from_arrow(ctx, a.slice(mlo, mhi - mlo)) for a in arrays]
+    cap2 = int(m * 2.0 / world) + 64
+    out_cols2 = []
+    for c in in_cols2:
+        if c.values_bytes:
+            c.values_bytes = max(c.values_bytes, 1)
+        oc = dfd.DeviceColumn.empty_like(ctx, dfd.DeviceColumn(c.kind, c.width, c.values, c.offsets, c.validity or 1, 0, cap2, None, c.arrow_type,
+                                                               c.values_bytes * 4 + 1024), cap2)
+        out_cols2.append(oc)
+    outs2, starts2 = node.shuffle(ex, in_cols2, mhi - mlo, nv.EXCHANGE_NCCL, out_cols2, cap2)
+    dest2 = orc.partition_ids([arrays[0], arrays[1]], m, N2)
+    for q in range(P2):
+        g = rank * P2 + q
+        want_idx = np.concatenate([np.nonzero(dest2[r * m // world:(r + 1) * m // world] == g)[0] + r * m // world for r in range(world)])
+        for c, arr in enumerate(arrays):
+            got = outs2[c].to_arrow(ctx, int(starts2[q]), int(starts2[q + 1]))
+            if not got.equals(arr.take(pa.array(want_idx))):
+                failures += 1
+                print(f"rank {rank}: MISMATCH nccl mixed q={q} col={c} {arr.type}", flush=True)
+    dist.barrier()
     # host-to-host pipelined shuffle: row-set equality per destination (chunk-major output)
     P, N = 8 // world if 8 % world == 0 else 1, (8 // world if 8 % world == 0 else 1) * world
     ref, rc, rs = orc.repartition_table(cols, [0], N, 8192, 1)

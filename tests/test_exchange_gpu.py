@@ -95,3 +95,41 @@ def test_single_worker_host_to_host_shuffle(ctx, n_chunks):
         node.shuffle_host(ex, h_in, n, n_chunks, h_out, n // 2)
     assert e.value.status == 7
     ex.close()
+
+
+def _mixed_table(n, seed):
+    import random
+
+    import pyarrow as pa
+
+    rnd = random.Random(seed)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    key = pa.array([rnd.choice([None, rnd.getrandbits(30)]) for _ in range(n)], type=pa.int64())
+    s = pa.array([rnd.choice([None, "", "N", "O", "phrase %d" % rnd.getrandbits(16), "x" * rnd.randint(0, 50)]) for _ in range(n)], type=pa.string())
+    ls = pa.array([rnd.choice([None, "L" * rnd.randint(0, 9)]) for _ in range(n)], type=pa.large_string())
+    bl = pa.array([rnd.choice([None, True, False]) for _ in range(n)])
+    i32 = pa.array([rnd.choice([None, rnd.getrandbits(31)]) for _ in range(n)], type=pa.int32())
+    f64 = pa.array(rng.standard_normal(n))
+    return [key, s, ls, bl, i32, f64]
+
+
+def test_single_worker_nccl_mode_moves_every_column_kind(ctx):
+    """NCCL-mode exchange with nullable, boolean and string columns (keys: Int64 + Utf8) at world=1."""
+    import pyarrow as pa
+
+    from tests.util import expected_partitions
+
+    n, P = 20_011, 6
+    arrays = _mixed_table(n, 17)
+    ex = dfd.ShuffleExchange(ctx, 0, 1, None)
+    node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0, 1], P), uuid.uuid4(), 1, 1, 1)
+    in_cols = [dfd.DeviceColumn.from_arrow(ctx, a) for a in arrays]
+    out_cols = [dfd.DeviceColumn.empty_like(ctx, c, n) for c in in_cols]
+    outs, starts = node.shuffle(ex, in_cols, n, nv.EXCHANGE_NCCL, out_cols, n)
+    dest = orc.partition_ids([arrays[0], arrays[1]], n, P)
+    order, ref_starts = expected_partitions(dest, P)
+    assert np.array_equal(starts, ref_starts)
+    idx = pa.array(order)
+    for c, arr in enumerate(arrays):
+        assert outs[c].to_arrow(ctx, 0, n).equals(arr.take(idx)), (c, arr.type)
+    ex.close()
