@@ -441,7 +441,9 @@ int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* part, int mode, const d
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     struct XCol {
         int kind, width, ow;
-        bool has_valid;
+        bool has_valid;   // the column travels with a validity lane (decided by the OUTPUT descriptor, i.e. the schema,
+                          // so that every worker agrees even if its own rows happen to contain no nulls)
+        bool in_valid;    // this worker's input actually carries a validity bitmap
         size_t st_values, st_valid, st_off;        // staging offsets (destination-sorted local output)
         size_t cv_valid, cv_values, cv_len;        // sender-side conversions (u8 per row / lengths)
         size_t rv_valid, rv_values, rv_len;        // receiver-side temporaries
@@ -454,10 +456,13 @@ int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* part, int mode, const d
         XCol& c0 = xc[i];
         c0 = XCol{};
         c0.kind = ic.kind; c0.width = ic.width; c0.ow = ic.kind == DFD_COL_LARGE_UTF8 ? 8 : 4;
-        c0.has_valid = ic.validity != nullptr;
+        c0.in_valid = ic.validity != nullptr;
+        c0.has_valid = out_cols[i].validity != nullptr;
         if (out_cols[i].kind != ic.kind || out_cols[i].width != ic.width || !out_cols[i].values)
             return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: out layout mismatch", i);
-        if (c0.has_valid && !out_cols[i].validity) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: out validity is NULL", i);
+        if (c0.in_valid && !c0.has_valid)
+            return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: input has nulls but out validity is NULL (nullable columns need a validity "
+                                                       "buffer on EVERY worker)", i);
         const size_t bm = al((size_t)((n_rows + 63) / 64 * 8 + 8));
         if (ic.kind == DFD_COL_FIXED) {
             c0.st_values = stage_bytes; stage_bytes += al((size_t)n_rows * ic.width + 16);
@@ -473,10 +478,8 @@ int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* part, int mode, const d
         } else {
             return set_error(DFD_ERR_UNSUPPORTED, "column %d: unknown column kind %d", i, ic.kind);
         }
-        if (c0.has_valid) {
-            c0.st_valid = stage_bytes; stage_bytes += bm;
-            c0.cv_valid = stage_bytes; stage_bytes += al((size_t)n_rows + 16);
-        }
+        if (c0.in_valid) { c0.st_valid = stage_bytes; stage_bytes += bm; }
+        if (c0.has_valid) { c0.cv_valid = stage_bytes; stage_bytes += al((size_t)n_rows + 16); }
     }
     const size_t meta_off = stage_bytes;               // per var column: bytes[N] | first[N] (device)
     stage_bytes += al((size_t)n_cols * 2 * N * 8 + 64);
@@ -488,12 +491,12 @@ int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* part, int mode, const d
         staged[i] = in_cols[i];
         staged[i].values = sb + c0.st_values;
         staged[i].offsets = c0.kind >= DFD_COL_UTF8 ? (void*)(sb + c0.st_off) : nullptr;
-        staged[i].validity = c0.has_valid ? (uint8_t*)(sb + c0.st_valid) : nullptr;
+        staged[i].validity = c0.in_valid ? (uint8_t*)(sb + c0.st_valid) : nullptr;
         staged[i].offset = 0;
         staged[i].values_bytes = c0.cap_bytes;
         const size_t bm = (size_t)((n_rows + 63) / 64 * 8 + 8);
         if (c0.kind == DFD_COL_BOOL) CUDA_TRY(cudaMemsetAsync(sb + c0.st_values, 0, bm, s), "memset");
-        if (c0.has_valid) CUDA_TRY(cudaMemsetAsync(sb + c0.st_valid, 0, bm, s), "memset");
+        if (c0.in_valid) CUDA_TRY(cudaMemsetAsync(sb + c0.st_valid, 0, bm, s), "memset");
     }
     PartitionJob job;
     if ((rc = job.prepare(part, in_cols, n_cols, n_rows, staged.data(), false, s))) return rc;
@@ -509,7 +512,9 @@ int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* part, int mode, const d
     std::vector<int> var_cols;
     for (int i = 0; i < n_cols; ++i) {
         const XCol& c0 = xc[i];
-        if (c0.has_valid && (rc = launch_bits_to_bytes((const uint8_t*)(sb + c0.st_valid), 0, n_rows, (uint8_t*)(sb + c0.cv_valid), s))) return rc;
+        if (c0.in_valid && (rc = launch_bits_to_bytes((const uint8_t*)(sb + c0.st_valid), 0, n_rows, (uint8_t*)(sb + c0.cv_valid), s))) return rc;
+        if (c0.has_valid && !c0.in_valid && n_rows > 0)  // no nulls among my rows: all-valid lane
+            CUDA_TRY(cudaMemsetAsync(sb + c0.cv_valid, 1, (size_t)n_rows, s), "memset");
         if (c0.kind == DFD_COL_BOOL && (rc = launch_bits_to_bytes((const uint8_t*)(sb + c0.st_values), 0, n_rows, (uint8_t*)(sb + c0.cv_values), s))) return rc;
         if (c0.kind >= DFD_COL_UTF8) {
             if ((rc = launch_offsets_to_lengths(sb + c0.st_off, c0.ow, n_rows, sb + c0.cv_len, s))) return rc;

@@ -260,7 +260,12 @@ int dfd_exchange_plan(int world, uint32_t partitions_per_task, int rank, const i
  * out column c, rows [part_starts_host[q], part_starts_host[q+1]) = local
  * partition q = global partition rank*P + q, producers' rows in task order,
  * each producer's rows in its input order.
- *   NCCL mode : out_cols[c].values are caller buffers of out_capacity_rows.
+ *   NCCL mode : out_cols[c].values (/offsets/validity) are caller buffers of
+ *               out_capacity_rows; every column kind of dfd_partition_device
+ *               is supported.  A column travels with a validity lane iff
+ *               out_cols[c].validity != NULL — set it from the SCHEMA's
+ *               nullable flag so that every worker agrees, whether or not its
+ *               own rows contain nulls; string outputs need values_bytes.
  *   FUSED mode: out_cols[c].values are SET to point into the receive window
  *               (valid until the next shuffle); out_capacity_rows is ignored.
  * DFD_ERR_CAPACITY if a receive buffer / window is too small (nothing is
