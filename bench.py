@@ -101,6 +101,34 @@ class ClockSampler:
                 "samples": len(self.samples), "power_w_max": max(pw) if pw else None}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this worker process to the CPU cores of its GPU's NUMA node BEFORE any pinned allocation, so that the
+    page-locked staging buffers are node-local to the GPU's PCIe root (standard one-worker-per-GPU deployment).
+    Returns (original affinity, description); a no-op when sysfs / nvidia-smi do not expose the topology."""
+    try:
+        orig = os.sched_getaffinity(0)
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if not bus:
+            return None, "numa: unknown (no nvidia-smi)"
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None, "numa: single node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= orig
+        if not cpus:
+            return None, f"numa: node {node} has no allowed cpus"
+        os.sched_setaffinity(0, cpus)
+        return orig, f"numa: bound to node {node} ({len(cpus)} cpus) of GPU {index}"
+    except Exception as e:  # pragma: no cover - topology files missing
+        return None, f"numa: not bound ({type(e).__name__})"
+
+
 def soak(step, seconds: float, sync):
     """Untimed repetitions of the step so clocks/thermals are at steady state and the sampler sees load."""
     t0 = time.perf_counter()
@@ -362,7 +390,7 @@ def run_multi_gpu(args, torch, dfd, world):
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": {"workload": f"cfg2: 2^26 rows x 8 Int64 split over {world} producer tasks, Hash([col0], {total_parts}), "
                                    f"{P} partitions per consumer task, device-resident", "rows": n_total, "columns": N_COLS,
-                       "num_partitions": total_parts, "exchange": args.exchange,
+                       "num_partitions": total_parts, "exchange": args.exchange, "host": args.numa_note,
                        "l2": f"per-GPU inputs+window ({2 * n * N_COLS * WIDTH >> 20} MiB) > L2, no flush"},
             "roofline": {"bound": "nvlink", "kernel": "k_scatter<PEER> (fused hash->rank->peer store)" if args.exchange == "fused" else "ncclSend/Recv",
                          "achieved": achieved, "peak": NVLINK_PEAK_GBS, "unit": "GB/s", "frac": achieved / NVLINK_PEAK_GBS,
@@ -385,12 +413,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-soak", action="store_true", help="skip the untimed clock soak (use under ncu)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the worker to its GPU's NUMA node")
     ap.add_argument("--e2e-batch-rows", type=int, default=1 << 20)
     ap.add_argument("--e2e-chunk-rows", type=int, default=1 << 20)
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    orig_affinity, numa_note = (None, "numa: binding disabled") if args.no_numa_bind else bind_to_gpu_numa_node(local_rank)
+    args.numa_note = numa_note
+    args.orig_affinity = orig_affinity
 
     import torch
 
@@ -461,7 +495,10 @@ def main():
     if not args.no_e2e:
         line["e2e"] = run_e2e(ctx, dfd, n, args)
         line["gpu_launches"] = int(ctx.metrics()["kernel_launches"])
+    line["config"]["host"] = args.numa_note
     if not args.no_cpu_baseline:
+        if args.orig_affinity:
+            os.sched_setaffinity(0, args.orig_affinity)  # the CPU baseline uses every host core
         threads = os.cpu_count() or 1
         sample = 1 << 23
         v, times = cpu_reference_arm(sample, threads, 2)
