@@ -321,6 +321,18 @@ def run_multi_gpu(args, torch, dfd, world):
     def step():
         return node.shuffle(ex, in_cols, n, mode, out_cols, cap)
 
+    def timed_steps(k):
+        """K back-to-back shuffles; the fused transport is enqueued asynchronously (like the 1-GPU path's launches)
+        and synchronised once at the end, the NCCL transport needs the host count exchange every step."""
+        if mode == nv.EXCHANGE_FUSED:
+            for _ in range(k):
+                node.shuffle_async(ex, in_cols, n)
+            return node.wait(ex)
+        r = None
+        for _ in range(k):
+            r = step()
+        return r
+
     for _ in range(max(args.warmup, 3)):
         step()
     ctx.reset_metrics()
@@ -335,8 +347,7 @@ def run_multi_gpu(args, torch, dfd, world):
         torch.cuda.synchronize()
         ctx.synchronize()
         ctx.timer_start()
-        for _ in range(args.steps):
-            outs, starts = step()
+        outs, starts = timed_steps(args.steps)
         ms_local = ctx.timer_stop()
     torch.cuda.synchronize()
     dist.barrier()

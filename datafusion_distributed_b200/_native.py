@@ -131,6 +131,8 @@ SIGNATURES = {
     "dfd_exchange_plan": (C.c_int, [C.c_int, C.c_uint32, C.c_int, _VP, _VP, _VP, _VP, _VP, C.POINTER(C.c_int64)]),
     "dfd_shuffle_device": (C.c_int, [_VP, _VP, C.c_int, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.c_uint32,
                                      C.POINTER(DfdColumn), C.c_int64, C.POINTER(C.c_int64)]),
+    "dfd_shuffle_device_async": (C.c_int, [_VP, _VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.c_uint32, C.POINTER(DfdColumn)]),
+    "dfd_exchange_wait": (C.c_int, [_VP, C.POINTER(C.c_int64)]),
     "dfd_shuffle_host": (C.c_int, [_VP, _VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.c_uint32, C.c_int, C.POINTER(DfdColumn),
                                    C.c_int64, C.POINTER(C.c_int64)]),
     "dfd_exchange_stats": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

@@ -155,6 +155,9 @@ struct dfd_exchange {
     size_t window_bytes = 0;
     void* peer_window[MAX_RANKS] = {};
     bool window_ready = false;
+    bool pending_async = false;       // a fused shuffle has been enqueued but not waited for
+    size_t pending_row_bytes = 0;
+    uint32_t pending_P = 0;
     // host pipeline (dfd_shuffle_host): H2D | shuffle | D2H of consecutive chunks overlap
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t e_h2d[2] = {}, e_k[2] = {}, e_d2h[2] = {};
@@ -347,8 +350,18 @@ static size_t row_bytes_of(const dfd_column* cols, int n_cols) {
 // that a chunked host pipeline can drain one slot while the next chunk lands in the other).
 // Ends with a stream synchronize: x->h_my_starts holds this worker's part_starts[P+1].
 // `e_k`, if given, is recorded right after the last kernel / barrier of this shuffle.
+static int fused_shuffle_finish(dfd_exchange* x, uint32_t P) {
+    dfd_ctx* c = x->ctx;
+    CUDA_TRY(cudaStreamSynchronize(c->stream), "fused shuffle");
+    x->pending_async = false;
+    if (*x->h_abort)
+        return set_error(DFD_ERR_CAPACITY, "a receive window slot is too small for this shuffle (window %zu B)", x->window_bytes);
+    x->bytes_received += (uint64_t)x->h_my_starts[P] * x->pending_row_bytes;
+    return DFD_OK;
+}
+
 static int fused_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const dfd_column* in_cols, int n_cols, int64_t n_rows,
-                                uint32_t P, int slot, int n_slots, dfd_column* out_cols, cudaEvent_t e_k) {
+                                uint32_t P, int slot, int n_slots, dfd_column* out_cols, cudaEvent_t e_k, bool sync = true) {
     dfd_ctx* c = x->ctx;
     const uint32_t N = part->N;
     const int T = x->world;
@@ -393,13 +406,12 @@ static int fused_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const df
     if (e_k) CUDA_TRY(cudaEventRecord(e_k, s), "record");
     CUDA_TRY(cudaMemcpyAsync(x->h_my_starts, x->d_my_starts, sizeof(int64_t) * (P + 1), cudaMemcpyDeviceToHost, s), "D2H starts");
     CUDA_TRY(cudaMemcpyAsync(x->h_abort, x->d_abort, sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H flag");
-    CUDA_TRY(cudaStreamSynchronize(s), "fused shuffle");
-    if (*x->h_abort)
-        return set_error(DFD_ERR_CAPACITY, "a receive window slot (%zu B = %lld rows) is too small for this shuffle", slot_bytes,
-                         (long long)capacity_rows);
-    x->bytes_received += (uint64_t)x->h_my_starts[P] * rb;
     x->bytes_sent += (uint64_t)n_rows * rb;
-    return DFD_OK;
+    x->pending_row_bytes = rb;
+    x->pending_async = true;
+    x->pending_P = P;
+    (void)capacity_rows;
+    return sync ? fused_shuffle_finish(x, P) : DFD_OK;
 }
 
 /* The shuffle: producer task `rank` holds n_rows local rows; afterwards this
@@ -736,6 +748,38 @@ int dfd_shuffle_host(dfd_exchange* x, dfd_partitioner* part, const dfd_column* i
         out_row += got;
     }
     CUDA_TRY(cudaStreamSynchronize(x->s_d2h), "D2H drain");
+    return DFD_OK;
+}
+
+/* Fused shuffle without the final host synchronisation: everything is enqueued on the context's
+ * stream and the call returns; out_cols are set (window pointers) immediately.  Completion,
+ * the capacity check and part_starts are delivered by dfd_exchange_wait.  Back-to-back calls
+ * pipeline on the stream (each overwrites the window, so consume or wait in between if the data
+ * matters). */
+int dfd_shuffle_device_async(dfd_exchange* x, dfd_partitioner* part, const dfd_column* in_cols, int n_cols, int64_t n_rows,
+                             uint32_t partitions_per_task, dfd_column* out_cols) {
+    if (!x || !part || !in_cols || !out_cols) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_shuffle_device_async: NULL argument");
+    dfd_ctx* c = x->ctx;
+    if (part->ctx != c) return set_error(DFD_ERR_INVALID_ARGUMENT, "partitioner and exchange belong to different contexts");
+    if (partitions_per_task < 1 || (uint64_t)partitions_per_task * x->world != part->N)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "num_partitions %u != partitions_per_task %u x %d workers", part->N, partitions_per_task, x->world);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device), "cudaSetDevice");
+    int rc = ensure_count_buffers(x, part->N);
+    if (rc) return rc;
+    x->shuffles++;
+    return fused_shuffle_locked(x, part, in_cols, n_cols, n_rows, partitions_per_task, 0, 1, out_cols, nullptr, /*sync=*/false);
+}
+
+int dfd_exchange_wait(dfd_exchange* x, int64_t* part_starts_host) {
+    if (!x) return set_error(DFD_ERR_INVALID_ARGUMENT, "NULL exchange");
+    dfd_ctx* c = x->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device), "cudaSetDevice");
+    if (!x->pending_async) return set_error(DFD_ERR_INVALID_ARGUMENT, "no asynchronous shuffle is pending");
+    int rc = fused_shuffle_finish(x, x->pending_P);
+    if (rc) return rc;
+    if (part_starts_host) memcpy(part_starts_host, x->h_my_starts, sizeof(int64_t) * (x->pending_P + 1));
     return DFD_OK;
 }
 

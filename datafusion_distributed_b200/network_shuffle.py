@@ -158,6 +158,26 @@ class NetworkShuffleExec:
         self._starts = np.frombuffer(starts, dtype=np.int64).copy()
         return self._out, self._starts
 
+    def shuffle_async(self, exchange: ShuffleExchange, in_cols: Sequence[DeviceColumn], n_rows: int):
+        """Fused shuffle enqueued on the worker's stream without a host sync (`dfd_shuffle_device_async`)."""
+        if self._part is None:
+            self._part = HashPartitioner(exchange.ctx, self.input_stage.plan)
+        P = self.properties.partition_count
+        c_out = (nv.DfdColumn * len(in_cols))()
+        nv.check(nv.lib().dfd_shuffle_device_async(exchange._h, self._part._h, columns_to_c(in_cols), len(in_cols), n_rows, P, c_out))
+        self._pending = (c_out, [c.arrow_type for c in in_cols], exchange)
+
+    def wait(self, exchange: ShuffleExchange):
+        """Complete the last `shuffle_async`: returns (out columns, part_starts[P+1])."""
+        P = self.properties.partition_count
+        starts = (C.c_int64 * (P + 1))()
+        nv.check(nv.lib().dfd_exchange_wait(exchange._h, starts))
+        c_out, types, _ = self._pending
+        self._out = [DeviceColumn(c_out[i].kind, c_out[i].width, c_out[i].values or 0, 0, 0, 0, int(starts[P]), exchange, types[i])
+                     for i in range(len(types))]
+        self._starts = np.frombuffer(starts, dtype=np.int64).copy()
+        return self._out, self._starts
+
     def shuffle_host(self, exchange: ShuffleExchange, host_in: Sequence[DeviceColumn], n_rows: int, n_chunks: int,
                      host_out: Sequence[DeviceColumn], out_capacity_rows: int) -> np.ndarray:
         """Host-to-host pipelined shuffle (`dfd_shuffle_host`): `host_in` / `host_out` describe HOST (pinned)

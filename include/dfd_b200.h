@@ -273,6 +273,14 @@ int dfd_exchange_plan(int world, uint32_t partitions_per_task, int rank, const i
 int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* p, int mode, const dfd_column* in_cols, int n_cols,
                        int64_t n_rows, uint32_t partitions_per_task, dfd_column* out_cols,
                        int64_t out_capacity_rows, int64_t* part_starts_host);
+/* DFD_EXCHANGE_FUSED without the final host synchronisation: the whole shuffle is enqueued on
+ * dfd_ctx_stream() and the call returns (out_cols already point into the receive window).
+ * dfd_exchange_wait() synchronises, reports DFD_ERR_CAPACITY if a window overflowed and fills
+ * part_starts_host[P+1] (may be NULL).  Lets consecutive collectives pipeline on the stream. */
+int dfd_shuffle_device_async(dfd_exchange* x, dfd_partitioner* p, const dfd_column* in_cols, int n_cols,
+                             int64_t n_rows, uint32_t partitions_per_task, dfd_column* out_cols);
+int dfd_exchange_wait(dfd_exchange* x, int64_t* part_starts_host);
+
 /* Host-to-host collective shuffle (end-to-end path of the multi-worker exchange; replaces, per
  * worker, "execute the producer plan, Flight-encode, stream, decode" of
  * src/worker/impl_execute_task.rs:36-169 + src/worker/worker_connection_pool.rs:143-390 for

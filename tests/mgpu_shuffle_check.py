@@ -52,6 +52,10 @@ def main():
             torch.cuda.synchronize()
             out_cols = [dfd.DeviceColumn.from_torch(t) for t in outs_t] if mode == nv.EXCHANGE_NCCL else None
             outs, starts = node.shuffle(ex, in_cols, hi - lo, mode, out_cols, cap)
+            if mode == nv.EXCHANGE_FUSED:  # asynchronous form: three pipelined collectives, one wait
+                for _ in range(3):
+                    node.shuffle_async(ex, in_cols, hi - lo)
+                outs, starts = node.wait(ex)
             for q in range(P):
                 g = rank * P + q
                 _, a, b = node.execute(q, dfd.DistributedTaskContext(rank, world))

@@ -29,6 +29,10 @@ def test_single_worker_shuffle_equals_local_repartition(ctx, mode):
     in_cols = [dfd.DeviceColumn.from_arrow(ctx, pa.array(c)) for c in cols]
     out_cols = [dfd.DeviceColumn.empty_like(ctx, c, n) for c in in_cols] if mode == nv.EXCHANGE_NCCL else None
     outs, starts = node.shuffle(ex, in_cols, n, mode, out_cols, n)
+    if mode == nv.EXCHANGE_FUSED:  # the asynchronous form (two pipelined shuffles, one wait) gives the same result
+        node.shuffle_async(ex, in_cols, n)
+        node.shuffle_async(ex, in_cols, n)
+        outs, starts = node.wait(ex)
     ref, rc, rs = orc.repartition_table(cols, [0], P, 8192, 1)
     assert np.array_equal(starts, rs)
     for q in range(P):
