@@ -86,6 +86,11 @@ class ArrowArrayStreamStruct(C.Structure):
                 ("release", C.c_void_p), ("private_data", C.c_void_p)]
 
 
+class ArrowDeviceArrayStruct(C.Structure):
+    _fields_ = [("array", ArrowArrayStruct), ("device_id", C.c_int64), ("device_type", C.c_int32), ("sync_event", C.c_void_p),
+                ("reserved", C.c_int64 * 3)]
+
+
 # name -> (restype, argtypes).  Every symbol include/dfd_b200.h declares.
 _VP = C.c_void_p
 SIGNATURES = {
@@ -136,6 +141,7 @@ SIGNATURES = {
     "dfd_shuffle_host": (C.c_int, [_VP, _VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.c_uint32, C.c_int, C.POINTER(DfdColumn),
                                    C.c_int64, C.POINTER(C.c_int64)]),
     "dfd_exchange_stats": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "dfd_export_partition_device": (C.c_int, [_VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.c_int64, C.POINTER(ArrowDeviceArrayStruct)]),
     "dfd_metrics_get": (C.c_int, [_VP, C.POINTER(DfdMetrics)]),
     "dfd_metrics_reset": (C.c_int, [_VP]),
 }

@@ -806,6 +806,81 @@ int dfd_repartition_exec_execute(dfd_repartition_exec* x, uint32_t partition, st
     return DFD_OK;
 }
 
+namespace {
+struct DevExportPriv {
+    std::vector<ArrowArray> children;
+    std::vector<ArrowArray*> child_ptrs;
+    std::vector<const void*> bufs;  // 3 per child
+    const void* struct_bufs[1] = {nullptr};
+    cudaEvent_t event = nullptr;
+    int device = 0;
+};
+void dev_child_release(ArrowArray* a) { a->release = nullptr; }
+void dev_export_release(ArrowArray* a) {
+    DevExportPriv* p = (DevExportPriv*)a->private_data;
+    for (ArrowArray& c : p->children)
+        if (c.release) c.release(&c);
+    if (p->event) {
+        cudaSetDevice(p->device);
+        cudaEventDestroy(p->event);
+    }
+    delete p;
+    a->release = nullptr;
+}
+}  // namespace
+
+int dfd_export_partition_device(dfd_ctx* ctx, const dfd_column* cols, int n_cols, int64_t first_row, int64_t n_rows,
+                                struct ArrowDeviceArray* out) {
+    if (!ctx || !out || n_cols < 0 || (n_cols > 0 && !cols) || first_row < 0 || n_rows < 0)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_export_partition_device: bad arguments");
+    DevExportPriv* p = new (std::nothrow) DevExportPriv();
+    if (!p) return set_error(DFD_ERR_OOM, "out of host memory");
+    p->device = ctx->device;
+    p->children.resize(n_cols);
+    p->child_ptrs.resize(n_cols);
+    p->bufs.resize(3 * (size_t)n_cols);
+    for (int i = 0; i < n_cols; ++i) {
+        const dfd_column& c = cols[i];
+        ArrowArray& a = p->children[i];
+        memset(&a, 0, sizeof a);
+        const bool var = c.kind == DFD_COL_UTF8 || c.kind == DFD_COL_LARGE_UTF8 || c.kind == DFD_COL_BINARY;
+        p->bufs[3 * i] = c.validity;
+        p->bufs[3 * i + 1] = var ? c.offsets : c.values;
+        p->bufs[3 * i + 2] = var ? c.values : nullptr;
+        a.length = n_rows;
+        a.offset = c.offset + first_row;
+        a.null_count = c.validity ? -1 : 0;
+        a.n_buffers = var ? 3 : 2;
+        a.buffers = &p->bufs[3 * i];
+        a.release = dev_child_release;
+        p->child_ptrs[i] = &a;
+    }
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->event, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(p->event, ctx->stream);
+        if (e != cudaSuccess) {
+            if (p->event) cudaEventDestroy(p->event);
+            delete p;
+            return cuda_error(e, "dfd_export_partition_device");
+        }
+    }
+    memset(out, 0, sizeof *out);
+    out->array.length = n_rows;
+    out->array.null_count = 0;
+    out->array.n_buffers = 1;
+    out->array.buffers = p->struct_bufs;
+    out->array.n_children = n_cols;
+    out->array.children = p->child_ptrs.data();
+    out->array.release = dev_export_release;
+    out->array.private_data = p;
+    out->device_id = ctx->device;
+    out->device_type = ARROW_DEVICE_CUDA;
+    out->sync_event = &p->event;
+    return DFD_OK;
+}
+
 int dfd_repartition_exec_stats(dfd_repartition_exec* x, dfd_exec_stats* out) {
     if (!x || !out) return set_error(DFD_ERR_INVALID_ARGUMENT, "NULL argument");
     std::lock_guard<std::mutex> lk(x->mu);

@@ -296,6 +296,16 @@ int dfd_shuffle_host(dfd_exchange* x, dfd_partitioner* p, const dfd_column* in_c
                      int64_t out_capacity_rows, int64_t* chunk_part_starts);
 int dfd_exchange_stats(dfd_exchange* x, uint64_t* bytes_sent, uint64_t* bytes_received, uint64_t* shuffles);
 
+/* Arrow C Device Data Interface export of ONE destination of a dfd_partition_device /
+ * dfd_shuffle_device result: a struct array (record batch) of `n_cols` children whose buffers are
+ * the device buffers of `cols` (no copy), sliced with `offset = first_row`, `length = n_rows`.
+ * device_type = ARROW_DEVICE_CUDA, device_id = the context's GPU, sync_event = a cudaEvent_t*
+ * recorded on dfd_ctx_stream() (the consumer waits on it before reading).  The export does not
+ * own the column buffers: keep them alive until out->array.release has been called.
+ * (≙ handing a RecordBatch of `NetworkShuffleExec::execute(partition)` to a device-side consumer.) */
+int dfd_export_partition_device(dfd_ctx* ctx, const dfd_column* cols, int n_cols, int64_t first_row, int64_t n_rows,
+                                struct ArrowDeviceArray* out);
+
 int dfd_metrics_get(dfd_ctx* ctx, dfd_metrics* out);
 int dfd_metrics_reset(dfd_ctx* ctx);
 

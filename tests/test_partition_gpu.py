@@ -323,3 +323,31 @@ def test_context_closes_its_children_first(built):
     c2.close()
     del part, buf, ex
     gc.collect()
+
+
+def test_arrow_c_device_export_of_one_destination(ctx):
+    """dfd_export_partition_device: ArrowDeviceArray (CUDA) slice of a partition result, read back through its buffers."""
+    import ctypes as C
+
+    from datafusion_distributed_b200 import _native as nv
+    from datafusion_distributed_b200.device import columns_to_c
+
+    n, N = 10_000, 4
+    cols = cfg2_columns(n, 2)
+    outs, starts = run_partition(ctx, cols, [0], N)
+    ref, _, rs = orc.repartition_table(cols, [0], N, 8192, 1)
+    p = 2
+    dev = nv.ArrowDeviceArrayStruct()
+    nv.check(nv.lib().dfd_export_partition_device(ctx.handle, columns_to_c(outs), 2, int(starts[p]), int(starts[p + 1] - starts[p]), C.byref(dev)))
+    assert dev.device_type == 2 and dev.device_id == 0 and dev.sync_event  # ARROW_DEVICE_CUDA
+    assert dev.array.length == starts[p + 1] - starts[p] and dev.array.n_children == 2
+    children = C.cast(dev.array.children, C.POINTER(C.POINTER(nv.ArrowArrayStruct)))
+    for c in range(2):
+        ch = children[c].contents
+        assert ch.offset == starts[p] and ch.length == dev.array.length and ch.n_buffers == 2
+        bufs = C.cast(ch.buffers, C.POINTER(C.c_void_p))
+        got = np.empty(ch.length, dtype=np.int64)
+        nv.check(nv.lib().dfd_memcpy_d2h(ctx.handle, got.ctypes.data, bufs[1] + ch.offset * 8, ch.length * 8))
+        assert np.array_equal(got, ref[c][rs[p]:rs[p + 1]])
+    C.CFUNCTYPE(None, C.c_void_p)(dev.array.release)(C.addressof(dev.array))
+    assert not dev.array.release
