@@ -185,8 +185,14 @@ def run_reference(args):
             if time.perf_counter() - t_all > 150 and len(vals) >= 1:
                 break
     else:
+        import pyarrow as pa
+
         from oracle.flight_proxy import FlightShuffleProxy
 
+        # torchrun exports OMP_NUM_THREADS=1, which Arrow would take as its CPU pool size (IPC/LZ4 threads):
+        # give the reference arm every host core, as the tokio runtime of the real workers would have
+        pa.set_cpu_count(threads)
+        pa.set_io_thread_count(max(8, min(64, threads)))
         total_parts = NUM_PARTITIONS if NUM_PARTITIONS % world == 0 else NUM_PARTITIONS * world
         P = total_parts // world
         names = [f"c{j}" for j in range(N_COLS)]
