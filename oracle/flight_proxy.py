@@ -85,7 +85,9 @@ class FlightShuffleProxy:
 
     # -- one shuffle -------------------------------------------------------------------------
     def run(self, producer_cols: List[List[np.ndarray]], threads_per_producer: int = 1):
-        """producer_cols[r] = producer r's columns.  Returns (seconds, rows_received, per-consumer tables|None)."""
+        """producer_cols[r] = producer r's columns.  Returns (seconds, rows_received, per-consumer tables).
+        `self.last_phases` = (repartition seconds, exchange seconds): the real reference overlaps the two
+        (consumers poll while producers are still partitioning), so callers may charge max() instead of the sum."""
         t0 = time.perf_counter()
         # stage N: every producer repartitions its rows (concurrently, like T worker processes)
         results = [None] * self.T_prod
@@ -100,6 +102,7 @@ class FlightShuffleProxy:
             t.join()
         for r in range(self.T_prod):
             self.servers[r].set_output(results[r])
+        t1 = time.perf_counter()
         # stage N+1: every consumer task pulls its partition range from every producer
         rows = [0] * self.T_cons
         tables = [None] * self.T_cons
@@ -121,5 +124,6 @@ class FlightShuffleProxy:
             t.start()
         for t in ct:
             t.join()
-        dt = time.perf_counter() - t0
-        return dt, sum(rows), tables
+        t2 = time.perf_counter()
+        self.last_phases = (t1 - t0, t2 - t1)
+        return t2 - t0, sum(rows), tables
