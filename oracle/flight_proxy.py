@@ -105,21 +105,19 @@ class FlightShuffleProxy:
         t1 = time.perf_counter()
         # stage N+1: every consumer task pulls its partition range from every producer
         rows = [0] * self.T_cons
-        tables = [None] * self.T_cons
 
-        def consume(ci):
+        def pull(ci, r):  # one Flight stream per (consumer, producer) pair, all pairs concurrently (select_all)
             off = self.P * ci
-            got = []
-            for r in range(self.T_prod):
-                client = fl.connect(f"grpc://127.0.0.1:{self.ports[r]}")
-                reader = client.do_get(fl.Ticket(f"{off},{off + self.P}".encode()))
-                t = reader.read_all()
-                got.append(t)
+            client = fl.connect(f"grpc://127.0.0.1:{self.ports[r]}")
+            t = client.do_get(fl.Ticket(f"{off},{off + self.P}".encode())).read_all()
+            client.close()
+            with lock:
                 rows[ci] += t.num_rows
-                client.close()
-            tables[ci] = got
+                tables[ci][r] = t
 
-        ct = [threading.Thread(target=consume, args=(ci,)) for ci in range(self.T_cons)]
+        lock = threading.Lock()
+        tables = [[None] * self.T_prod for _ in range(self.T_cons)]
+        ct = [threading.Thread(target=pull, args=(ci, r)) for ci in range(self.T_cons) for r in range(self.T_prod)]
         for t in ct:
             t.start()
         for t in ct:
