@@ -387,7 +387,7 @@ int flush_current(dfd_repartition_exec* x) {
         size_t nb = f.kind == DFD_COL_BOOL ? (size_t)((s.rows + 7) / 8) : (size_t)s.rows * f.width;
         if (f.var()) {
             nb = (size_t)s.data_bytes[i];
-            if (s.out->data_cap[i] < nb) {  // grow this pinned chunk's string buffer
+            if (s.out->data_cap[i] < nb || !s.out->values[i]) {  // grow this pinned chunk's string buffer (never NULL, even for 0 bytes)
                 if (s.out->values[i]) cudaFreeHost(s.out->values[i]);
                 s.out->values[i] = nullptr;
                 s.out->data_cap[i] = 0;

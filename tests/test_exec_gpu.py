@@ -162,3 +162,20 @@ def test_utf8_keys_and_payload_through_the_operator(ctx):
         assert outs[p].num_rows == want.num_rows
         assert outs[p].equals(want), p
     ex.close()
+
+
+def test_all_empty_strings_chunk(ctx):
+    """A chunk whose string column has zero bytes still yields valid Arrow arrays."""
+    n = 1000
+    t = pa.table([pa.array(np.arange(n, dtype=np.int64)), pa.array([""] * n, type=pa.string())], names=["k", "s"])
+    ex = dfd.RepartitionExec(ctx, t.schema, dfd.Partitioning.Hash([0], 3))
+    for rb in t.to_batches():
+        ex.push_batch(rb)
+    ex.finish()
+    total = 0
+    for p in range(3):
+        out = ex.execute(p).read_all()
+        assert out.column("s").to_pylist() == [""] * out.num_rows
+        total += out.num_rows
+    assert total == n
+    ex.close()
