@@ -344,15 +344,14 @@ def run_multi_gpu(args, torch, dfd, world):
             r = step()
         return r
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    ctx.reset_metrics()
-    dist.barrier()
-    torch.cuda.synchronize()
-    ctx.synchronize()
-    with ClockSampler(local_rank) as clocks:
-        for _ in range(0 if args.no_soak else 400):  # untimed soak (collective: same count on every rank)
+    with ClockSampler(local_rank) as clocks:  # started before warm-up: nvidia-smi needs ~1 s to deliver its first sample
+        for _ in range(max(args.warmup, 3)):
             step()
+        # untimed soak (collective: the same count on every rank), sized for >= ~2 s under load
+        for _ in range(0 if args.no_soak else (2500 if mode == nv.EXCHANGE_FUSED else 300)):
+            node.shuffle_async(ex, in_cols, n) if mode == nv.EXCHANGE_FUSED else step()
+        if mode == nv.EXCHANGE_FUSED and not args.no_soak:
+            node.wait(ex)
         ctx.reset_metrics()
         dist.barrier()
         torch.cuda.synchronize()
