@@ -119,6 +119,8 @@ SIGNATURES = {
     "dfd_partition_ids_device": (C.c_int, [_VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, _VP]),
     "dfd_partition_device": (C.c_int, [_VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.POINTER(DfdColumn), C.POINTER(C.c_int64)]),
     "dfd_partitioner_part_starts_device": (_VP, [_VP]),
+    "dfd_arrow_format_layout": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "dfd_schema_supported": (C.c_int, [C.POINTER(ArrowSchemaStruct)]),
     "dfd_repartition_exec_create": (C.c_int, [_VP, C.POINTER(ArrowSchemaStruct), C.POINTER(C.c_int32), C.c_int, C.c_uint32,
                                               C.POINTER(DfdExecOptions), C.POINTER(_VP)]),
     "dfd_repartition_exec_destroy": (None, [_VP]),

@@ -521,6 +521,30 @@ int emit_ready(dfd_repartition_exec* x) {
 
 extern "C" {
 
+int dfd_arrow_format_layout(const char* format, int32_t* kind, int32_t* width) {
+    int32_t k = 0, w = 0;
+    if (!format || !parse_format(format, &k, &w))
+        return set_error(DFD_ERR_UNSUPPORTED, "Arrow format '%s' is not supported by the GPU shuffle path", format ? format : "(null)");
+    if (kind) *kind = k;
+    if (width) *width = w;
+    return DFD_OK;
+}
+
+int dfd_schema_supported(const struct ArrowSchema* schema) {
+    if (!schema || !schema->format || strcmp(schema->format, "+s") != 0)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "schema must be a struct (record batch) schema");
+    for (int64_t i = 0; i < schema->n_children; ++i) {
+        const ArrowSchema* c = schema->children[i];
+        int32_t k, w;
+        if (c->dictionary)
+            return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): dictionary arrays are not supported yet", (long long)i, c->name ? c->name : "");
+        if (!c->format || !parse_format(c->format, &k, &w))
+            return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): Arrow format '%s' is not supported", (long long)i, c->name ? c->name : "",
+                             c->format ? c->format : "(null)");
+    }
+    return DFD_OK;
+}
+
 int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, const int32_t* key_cols, int n_keys,
                                 uint32_t num_partitions, const dfd_exec_options* opts, dfd_repartition_exec** out) {
     if (!ctx || !schema || !out) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_repartition_exec_create: NULL argument");

@@ -188,6 +188,19 @@ const int64_t* dfd_partitioner_part_starts_device(const dfd_partitioner* p);
  * and nested types: DFD_ERR_UNSUPPORTED (remaining part). */
 typedef struct dfd_repartition_exec dfd_repartition_exec;
 
+/* Pure host helpers (no GPU needed) for the plan hook that decides whether a stage-head
+ * `RepartitionExec(Hash)` can be swapped for the GPU operator
+ * (`Worker::add_on_plan_hook`, src/worker/worker_service.rs:91-96):
+ *   dfd_arrow_format_layout : Arrow C format string -> (dfd_col_kind, value width);
+ *                             DFD_ERR_UNSUPPORTED for dictionary-less types this path does
+ *                             not move yet (views, lists, structs, 256-bit decimals ...).
+ *   dfd_schema_supported    : DFD_OK iff every column of the record-batch schema is
+ *                             supported (and no column is dictionary-encoded);
+ *                             otherwise DFD_ERR_UNSUPPORTED with the reason in
+ *                             dfd_last_error(). */
+int dfd_arrow_format_layout(const char* format, int32_t* kind, int32_t* width);
+int dfd_schema_supported(const struct ArrowSchema* schema);
+
 typedef struct {
     int64_t chunk_rows;         /* rows per device chunk; 0 = 4Mi                   */
     int32_t pipeline_depth;     /* chunks in flight (H2D | kernels | D2H); 0 = 3    */

@@ -72,3 +72,40 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 assert "oracle" not in open(os.path.join(dp, f)).read().lower(), os.path.join(dp, f)
+
+
+def test_schema_support_helpers_run_without_a_gpu(built):
+    """dfd_arrow_format_layout / dfd_schema_supported: the pure-host predicates the plan hook uses."""
+    import ctypes as C
+
+    import pyarrow as pa
+
+    from datafusion_distributed_b200 import _native as nv
+
+    L = nv.lib()
+    expect = {b"l": (0, 8), b"L": (0, 8), b"i": (0, 4), b"s": (0, 2), b"c": (0, 1), b"g": (0, 8), b"f": (0, 4), b"e": (0, 2), b"b": (1, 0),
+              b"u": (2, 0), b"U": (3, 0), b"z": (4, 0), b"d:38,10": (0, 16), b"d:9,2,32": (0, 4), b"tsn:": (0, 8), b"tsu:UTC": (0, 8),
+              b"tdD": (0, 4), b"tdm": (0, 8), b"ttu": (0, 8), b"tts": (0, 4), b"tDn": (0, 8), b"tiM": (0, 4), b"tiD": (0, 8), b"tin": (0, 16)}
+    for fmt, (kind, width) in expect.items():
+        k, w = C.c_int32(-1), C.c_int32(-1)
+        assert L.dfd_arrow_format_layout(fmt, C.byref(k), C.byref(w)) == 0, fmt
+        assert (k.value, w.value) == (kind, width), fmt
+    for fmt in (b"+l", b"+s", b"vu", b"d:76,0,256", b"w:16", b"n", b"Z"):
+        assert L.dfd_arrow_format_layout(fmt, None, None) == 6, fmt  # DFD_ERR_UNSUPPORTED
+
+    def supported(schema):
+        cs = nv.ArrowSchemaStruct()
+        schema._export_to_c(C.addressof(cs))
+        try:
+            return L.dfd_schema_supported(C.byref(cs)), L.dfd_last_error().decode()
+        finally:
+            C.CFUNCTYPE(None, C.c_void_p)(cs.release)(C.addressof(cs))
+
+    ok = pa.schema([("id", pa.int64()), ("metric", pa.float64()), ("flag", pa.bool_()), ("label", pa.string()), ("raw", pa.uint8()),
+                    ("ts", pa.timestamp("ns")), ("count", pa.int32()), ("price", pa.decimal128(15, 2)), ("blob", pa.binary())])
+    assert supported(ok)[0] == 0
+    # the two columns of the reference's bench fixture (src/execution_plans/benchmarks/fixture.rs:13-33) that are still "next"
+    st, why = supported(pa.schema([("id", pa.int64()), ("category", pa.dictionary(pa.int32(), pa.string()))]))
+    assert st == 6 and "dictionary" in why
+    st, why = supported(pa.schema([("id", pa.int64()), ("tags", pa.list_(pa.string()))]))
+    assert st == 6 and "tags" in why
