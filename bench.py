@@ -287,6 +287,7 @@ def run_e2e(ctx, dfd, n, args):
             "api": "RepartitionExec.push_batch/finish/execute(partition) over dfd_repartition_exec_* (Arrow C Data / C Stream)"}
 
 
+TRAFFIC_ONEPASS = None  # dram bytes of one k_scatter<ONEPASS> launch at cfg-2 (ncu --set full), filled from profiles/r02a
 NVLINK_PEAK_GBS = 770.0  # measured peer copy per direction per GPU on this pool (B200_PROFILING.md; nominal 900)
 
 
@@ -438,6 +439,8 @@ def main():
     ap.add_argument("--e2e-batch-rows", type=int, default=1 << 20)
     ap.add_argument("--e2e-chunk-rows", type=int, default=1 << 20)
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"])
+    ap.add_argument("--kernel", default="onepass", choices=["onepass", "twopass"],
+                    help="1-GPU partition path: single-pass k_scatter<ONEPASS> (regions) or K1/K1b/K2 (dense)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -463,30 +466,40 @@ def main():
     key = torch.randint(-(2**63), 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
     rid = torch.arange(n, dtype=torch.int64, device="cuda")
     ins = [key] + [rid * 8 + j for j in range(1, N_COLS)]
-    outs = [torch.empty_like(t) for t in ins]
     del rid
-    torch.cuda.synchronize()
-
     ctx = dfd.WorkerContext(dev)
     part = dfd.HashPartitioner(ctx, dfd.Partitioning.Hash([0], NUM_PARTITIONS))
+    onepass = args.kernel == "onepass"
+    region_rows = part.default_region_rows(n) if onepass else 0  # fair share + 25 % per destination
+    outs = [torch.empty(NUM_PARTITIONS * region_rows if onepass else n, dtype=torch.int64, device="cuda") for _ in ins]
+    torch.cuda.synchronize()
     in_cols = [dfd.DeviceColumn.from_torch(t) for t in ins]
     out_cols = [dfd.DeviceColumn.from_torch(t) for t in outs]
 
+    def one_step():
+        if onepass:
+            part.partition_onepass(in_cols, n, region_rows, out_cols, sync=False)
+        else:
+            part.partition(in_cols, n, out_cols, sync=False)
+
     for _ in range(max(args.warmup, 3)):
-        part.partition(in_cols, n, out_cols, sync=False)
+        one_step()
     ctx.synchronize()
     ctx.reset_metrics()
     ctx.set_profiling(True)
     # inputs (4 GiB) + outputs (4 GiB) are far larger than the 126 MB L2: no flush needed between steps
     with ClockSampler(dev) as clocks:
         if not args.no_soak:
-            soak(lambda: part.partition(in_cols, n, out_cols, sync=False), 1.0, ctx.synchronize)
+            soak(one_step, 1.0, ctx.synchronize)
         ctx.reset_metrics()
         ctx.timer_start()
         for _ in range(args.steps):
-            part.partition(in_cols, n, out_cols, sync=False)
+            one_step()
         ms_total = ctx.timer_stop()
     m = ctx.metrics()
+    if onepass:
+        _, counts = part.collect()
+        assert int(counts.sum()) == n and ctx.metrics()["onepass_reruns"] == 0, "a destination region overflowed inside the timed loop"
     ctx.set_profiling(False)
     ms_per_step = ms_total / args.steps
     value = n / (ms_per_step / 1e3)
@@ -500,13 +513,15 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int64", "data": "synthetic",
         "config": {"workload": "cfg2: 2^26 rows x 8 Int64, Hash([col0], 8), device-resident table", "rows": n,
-                   "columns": N_COLS, "num_partitions": NUM_PARTITIONS, "l2": "inputs+outputs (8 GiB) >> L2, no flush"},
-        "roofline": {"bound": "hbm", "kernel": "k_scatter", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                   "columns": N_COLS, "num_partitions": NUM_PARTITIONS, "l2": "inputs+outputs (8 GiB) >> L2, no flush",
+                   "kernel_path": ("single pass: k_scatter<ONEPASS> (hash once, decoupled look-back, per-destination regions of "
+                                   f"{region_rows} rows)") if onepass else "two pass: k_tile_hist -> k_scan_tiles -> k_scatter (dense)"},
+        "roofline": {"bound": "hbm", "kernel": "k_scatter<ONEPASS>" if onepass else "k_scatter", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one k_scatter launch at this exact workload,
                      # from the committed `ncu --set full` capture profiles/r01c_ncu_summary.md (8.59 GB algorithmic)
-                     "traffic": 8.576116e9 if n == N_ROWS else None, "traffic_unit": "bytes/launch",
-                     "traffic_source": "profiles/r01c_ncu_summary.md",
+                     "traffic": (TRAFFIC_ONEPASS if onepass else 8.576116e9) if n == N_ROWS else None, "traffic_unit": "bytes/launch",
+                     "traffic_source": "profiles/r02a_ncu_summary.md" if onepass else "profiles/r01c_ncu_summary.md",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scatter_ms,
                      "hist_ms": m["hist_ms"] / max(m["calls"], 1), "scan_ms": m["scan_ms"] / max(m["calls"], 1)},
         "gpu_launches": int(m["kernel_launches"]),

@@ -54,6 +54,7 @@ class DfdMetrics(C.Structure):
         ("h2d_ms", C.c_double),
         ("d2h_ms", C.c_double),
         ("scatter_launches", C.c_uint64),
+        ("onepass_reruns", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -119,6 +120,9 @@ SIGNATURES = {
     "dfd_partition_ids_device": (C.c_int, [_VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, _VP]),
     "dfd_partition_device": (C.c_int, [_VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.POINTER(DfdColumn), C.POINTER(C.c_int64)]),
     "dfd_partitioner_part_starts_device": (_VP, [_VP]),
+    "dfd_partition_device_onepass": (C.c_int, [_VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.POINTER(DfdColumn), C.c_int64,
+                                               C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "dfd_partitioner_collect": (C.c_int, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dfd_arrow_format_layout": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "dfd_schema_supported": (C.c_int, [C.POINTER(ArrowSchemaStruct)]),
     "dfd_repartition_exec_create": (C.c_int, [_VP, C.POINTER(ArrowSchemaStruct), C.POINTER(C.c_int32), C.c_int, C.c_uint32,

@@ -134,9 +134,9 @@ static int build_keyset(const dfd_partitioner* p, const dfd_column* cols, int n_
         if (_e != cudaSuccess) return cuda_error(_e, what);            \
     }
 
-template <bool FAST, typename V, bool PEER, int KV>
+template <bool FAST, typename V, bool PEER, int KV, bool ONEPASS>
 static int launch_scatter_kv(const ScatterParams& sp, unsigned grid, size_t smem, cudaStream_t stream) {
-    auto kern = k_scatter<TILE_THREADS, TILE_K, KV, TILE_MIN_CTAS, FAST, V, PEER>;
+    auto kern = k_scatter<TILE_THREADS, TILE_K, KV, TILE_MIN_CTAS, FAST, V, PEER, ONEPASS>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(k_scatter)");
@@ -155,29 +155,39 @@ static bool use_aligned(uint32_t N, bool peer) {
     return forced >= 0 ? forced == 1 : peer;
 }
 
-template <bool FAST, typename V, bool PEER>
+template <bool FAST, typename V, bool PEER, bool ONEPASS>
 static int launch_scatter_t(const ScatterParams& sp, unsigned grid, size_t smem, cudaStream_t stream) {
-    if (use_aligned(sp.N, PEER)) return launch_scatter_kv<FAST, V, PEER, TILE_KV>(sp, grid, smem, stream);
-    return launch_scatter_kv<FAST, V, PEER, TILE_K>(sp, grid, smem, stream);
+    if (use_aligned(sp.N, PEER)) return launch_scatter_kv<FAST, V, PEER, TILE_KV, ONEPASS>(sp, grid, smem, stream);
+    return launch_scatter_kv<FAST, V, PEER, TILE_K, ONEPASS>(sp, grid, smem, stream);
 }
 
-template <bool FAST, bool PEER>
+template <bool FAST, bool PEER, bool ONEPASS>
 static int launch_scatter_w(const ScatterParams& sp, int width, unsigned grid, size_t smem, cudaStream_t stream) {
     switch (width) {
-        case 8: return launch_scatter_t<FAST, uint64_t, PEER>(sp, grid, smem, stream);
-        case 4: return launch_scatter_t<FAST, uint32_t, PEER>(sp, grid, smem, stream);
-        case 2: return launch_scatter_t<FAST, uint16_t, PEER>(sp, grid, smem, stream);
-        case 1: return launch_scatter_t<FAST, uint8_t, PEER>(sp, grid, smem, stream);
-        case 16: return launch_scatter_t<FAST, uint4, PEER>(sp, grid, smem, stream);
+        case 8: return launch_scatter_t<FAST, uint64_t, PEER, ONEPASS>(sp, grid, smem, stream);
+        case 4: return launch_scatter_t<FAST, uint32_t, PEER, ONEPASS>(sp, grid, smem, stream);
+        case 2: return launch_scatter_t<FAST, uint16_t, PEER, ONEPASS>(sp, grid, smem, stream);
+        case 1: return launch_scatter_t<FAST, uint8_t, PEER, ONEPASS>(sp, grid, smem, stream);
+        case 16: return launch_scatter_t<FAST, uint4, PEER, ONEPASS>(sp, grid, smem, stream);
         default:
-            if (PEER) return set_error(DFD_ERR_UNSUPPORTED, "bit-packed columns are not supported by the fused peer-store exchange");
-            return launch_scatter_t<FAST, BitColumn, false>(sp, grid, smem, stream);
+            if constexpr (PEER || ONEPASS) {
+                return set_error(DFD_ERR_INTERNAL, "bit-packed columns take the two-pass local k_scatter instantiation");
+            } else {
+                return launch_scatter_t<FAST, BitColumn, false, false>(sp, grid, smem, stream);
+            }
     }
 }
 
-static int launch_scatter(const ScatterParams& sp, int width, bool fast, bool peer, unsigned grid, size_t smem, cudaStream_t stream) {
-    if (peer) return fast ? launch_scatter_w<true, true>(sp, width, grid, smem, stream) : launch_scatter_w<false, true>(sp, width, grid, smem, stream);
-    return fast ? launch_scatter_w<true, false>(sp, width, grid, smem, stream) : launch_scatter_w<false, false>(sp, width, grid, smem, stream);
+static int launch_scatter(const ScatterParams& sp, int width, bool fast, bool peer, bool onepass, unsigned grid, size_t smem,
+                          cudaStream_t stream) {
+#define DFD_LS(F, PE, OP) return launch_scatter_w<F, PE, OP>(sp, width, grid, smem, stream)
+    if (onepass) {
+        if (peer) { if (fast) DFD_LS(true, true, true); else DFD_LS(false, true, true); }
+        if (fast) DFD_LS(true, false, true); else DFD_LS(false, false, true);
+    }
+    if (peer) { if (fast) DFD_LS(true, true, false); else DFD_LS(false, true, false); }
+    if (fast) DFD_LS(true, false, false); else DFD_LS(false, false, false);
+#undef DFD_LS
 }
 
 // ---- PartitionJob: validation -> K1/K1b -> K2, reusable by the local path and the exchange ----
@@ -384,7 +394,7 @@ int dfd::PartitionJob::run_scatter(const int64_t* dest_base, void* const* peer_b
                 size_t n = group.size() - first < (size_t)MAX_COLS_PER_LAUNCH ? group.size() - first : (size_t)MAX_COLS_PER_LAUNCH;
                 for (size_t i = 0; i < n; ++i) sp.cols[i] = group[first + i];
                 sp.n_cols = (int32_t)n;
-                int rc = launch_scatter(sp, width, ks.fast_i64 != 0, peer, (unsigned)n_tiles, smem, stream);
+                int rc = launch_scatter(sp, width, ks.fast_i64 != 0, peer, false, (unsigned)n_tiles, smem, stream);
                 if (rc) return rc;
                 ++launches;
             }
@@ -393,6 +403,108 @@ int dfd::PartitionJob::run_scatter(const int64_t* dest_base, void* const* peer_b
     if (!var_cols.empty()) {
         int rc = run_varwidth();
         if (rc) return rc;
+    }
+    if (ev) {
+        cudaEventRecord(ev[3], stream);
+        c->ev_pending++;
+        ev = nullptr;
+    }
+    c->metrics.kernel_launches += launches;
+    c->metrics.scatter_launches += launches;
+    c->metrics.calls++;
+    c->metrics.rows += (uint64_t)n_rows;
+    c->metrics.bytes_in += bytes;
+    c->metrics.bytes_out += bytes;
+    return DFD_OK;
+}
+
+// Single-pass partition: ONE k_scatter<ONEPASS> launch hashes, ranks, resolves the tile cursors by
+// decoupled look-back and scatters the first width group; further width groups (and bit columns) reuse
+// the per-tile counts / cursors it leaves in d_hist / d_base through the two-pass code path.
+int dfd::PartitionJob::run_onepass(const OnePassLayout& L) {
+    Ctx* c = p->ctx;
+    const uint32_t N = p->N;
+    if (ev) { cudaEventRecord(ev[0], stream); cudaEventRecord(ev[1], stream); cudaEventRecord(ev[2], stream); }
+    if (!var_cols.empty()) return set_error(DFD_ERR_INTERNAL, "single-pass mode does not move variable-width columns");
+    int launches = 0;
+    if (n_rows == 0) {
+        cudaError_t e = cudaMemsetAsync(L.d_totals, 0, sizeof(int64_t) * (size_t)N, stream);
+        if (e != cudaSuccess) return cuda_error(e, "cudaMemsetAsync");
+    } else {
+        const size_t need = 256 + (size_t)N * (size_t)n_tiles * 8;
+        bool clear = false;
+        if (need > c->lb.bytes) {
+            int rc = c->lb.ensure(need, c->device);
+            if (rc) return rc;
+            clear = true;
+        }
+        if (++c->lb_epoch >= (1u << 30)) { c->lb_epoch = 1; clear = true; }
+        if (clear) {
+            cudaError_t e = cudaMemsetAsync(c->lb.ptr, 0, c->lb.bytes, stream);
+            if (e != cudaSuccess) return cuda_error(e, "cudaMemsetAsync(look-back table)");
+        }
+        ScatterParams sp{};
+        sp.keys = ks;
+        sp.st = p->st;
+        sp.mod = p->mod;
+        sp.n_rows = n_rows;
+        sp.n_tiles = n_tiles;
+        sp.N = N;
+        sp.parts_per_rank = L.parts_per_rank ? L.parts_per_rank : 1;
+        sp.dest_base = L.d_dest_base;
+        sp.dest_cap = L.d_dest_cap;
+        sp.region_stride = L.region_stride;
+        sp.rank = L.rank;
+        sp.world = L.world;
+        sp.lb_ticket = (unsigned*)c->lb.ptr;
+        sp.lb_desc = (unsigned long long*)((char*)c->lb.ptr + 256);
+        sp.lb_epoch = c->lb_epoch;
+        sp.totals_out = L.d_totals;
+        sp.overflow_out = L.d_overflow;
+        if (peer) {
+            if (L.world > MAX_RANKS) return set_error(DFD_ERR_UNSUPPORTED, "world size %d > %d", L.world, MAX_RANKS);
+            for (int r = 0; r < L.world; ++r) sp.peer_base[r] = L.peer_base[r];
+        }
+        static const int kWidths[6] = {8, 4, 16, 2, 1, 0};
+        int n_groups = 0;
+        for (int wi = 0; wi < 6; ++wi)
+            for (const PayloadCol& pc : passes)
+                if (pc.width == kWidths[wi]) { ++n_groups; break; }
+        if (passes.size() > 0 && passes.size() > (size_t)MAX_COLS_PER_LAUNCH) n_groups += 1;  // more than one launch for sure
+        bool first = true;
+        for (int wi = 0; wi < 6; ++wi) {
+            const int width = kWidths[wi];
+            std::vector<PayloadCol> group;
+            for (const PayloadCol& pc : passes)
+                if (pc.width == width) group.push_back(pc);
+            if (group.empty()) continue;
+            if (first && width == 0) return set_error(DFD_ERR_INTERNAL, "single-pass mode needs a fixed-width column");
+            sp.stage_width = width ? width : 1;
+            size_t smem = scatter_smem_bytes<TILE_THREADS, TILE_K>(N, sp.stage_width, peer, use_aligned(N, peer));
+            if (smem > 227 * 1024)
+                return set_error(DFD_ERR_UNSUPPORTED, "num_partitions %u needs %zu B of shared memory per CTA", N, smem);
+            for (size_t f0 = 0; f0 < group.size(); f0 += MAX_COLS_PER_LAUNCH) {
+                size_t n = group.size() - f0 < (size_t)MAX_COLS_PER_LAUNCH ? group.size() - f0 : (size_t)MAX_COLS_PER_LAUNCH;
+                for (size_t i = 0; i < n; ++i) sp.cols[i] = group[f0 + i];
+                sp.n_cols = (int32_t)n;
+                int rc;
+                if (first) {
+                    const bool more = n_groups > 1 || group.size() > (size_t)MAX_COLS_PER_LAUNCH;
+                    sp.hist_out = more ? d_hist : nullptr;
+                    sp.base_out = more ? d_base : nullptr;
+                    rc = launch_scatter(sp, width, ks.fast_i64 != 0, peer, true, (unsigned)n_tiles, smem, stream);
+                    first = false;
+                    // the follow-up launches take the two-pass code path over the counts / cursors just written
+                    sp.hist = d_hist;
+                    sp.tile_base = d_base;
+                    sp.abort_flag = L.d_overflow;
+                } else {
+                    rc = launch_scatter(sp, width, ks.fast_i64 != 0, peer, false, (unsigned)n_tiles, smem, stream);
+                }
+                if (rc) return rc;
+                ++launches;
+            }
+        }
     }
     if (ev) {
         cudaEventRecord(ev[3], stream);
@@ -566,6 +678,7 @@ void dfd_ctx_destroy(dfd_ctx* c) {
     if (c->scratch.ptr) cudaFree(c->scratch.ptr);
     if (c->flush.ptr) cudaFree(c->flush.ptr);
     if (c->var_scratch.ptr) cudaFree(c->var_scratch.ptr);
+    if (c->lb.ptr) cudaFree(c->lb.ptr);
     for (auto& ev : c->ev_ring) cudaEventDestroy(ev);
     cudaEventDestroy(c->timer_a);
     cudaEventDestroy(c->timer_b);
@@ -713,7 +826,12 @@ int dfd_partitioner_create(dfd_ctx* c, uint32_t num_partitions, const int32_t* k
     {
         CTX_GUARD(c);
         cudaError_t e = cudaMalloc((void**)&p->d_part_starts, sizeof(int64_t) * (size_t)(num_partitions + 1));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_counts, sizeof(int64_t) * (size_t)(3 * num_partitions + 1));
+        if (e == cudaSuccess) e = cudaMemset(p->d_counts, 0, sizeof(int64_t) * (size_t)(3 * num_partitions + 1));
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&p->h_pin, sizeof(int64_t) * (size_t)(num_partitions + 1), cudaHostAllocPortable);
         if (e != cudaSuccess) {
+            cudaFree(p->d_part_starts);
+            cudaFree(p->d_counts);
             delete p;
             return cuda_error(e, "cudaMalloc(part_starts)");
         }
@@ -729,6 +847,8 @@ void dfd_partitioner_destroy(dfd_partitioner* p) {
         cudaSetDevice(p->ctx->device);
         cudaStreamSynchronize(p->ctx->stream);
         cudaFree(p->d_part_starts);
+        cudaFree(p->d_counts);
+        cudaFreeHost(p->h_pin);
     }
     delete p;
 }
@@ -770,6 +890,120 @@ int dfd_partition_device(dfd_partitioner* p, const dfd_column* in_cols, int n_co
         if (e != cudaSuccess) return cuda_error(e, "dfd_partition_device");
     }
     return DFD_OK;
+}
+
+/* ---- single-pass partition (region layout) ---------------------------------- */
+
+static int onepass_launch_locked(dfd_partitioner* p, const int64_t* d_base, const int64_t* d_cap, int64_t stride) {
+    dfd_ctx* c = p->ctx;
+    const uint32_t N = p->N;
+    int32_t* d_flag = (int32_t*)(p->d_counts + 3 * (size_t)N);
+    cudaError_t e = cudaMemsetAsync(d_flag, 0, sizeof(int64_t), c->stream);
+    if (e != cudaSuccess) return cuda_error(e, "cudaMemsetAsync(overflow flag)");
+    PartitionJob job;
+    int rc = job.prepare(p, p->last_in.data(), (int)p->last_in.size(), p->last_rows, p->last_out.data(), false, c->stream);
+    if (rc) return rc;
+    PartitionJob::OnePassLayout L;
+    L.d_dest_base = d_base;
+    L.d_dest_cap = d_cap;
+    L.region_stride = stride;
+    L.d_totals = p->d_counts;
+    L.d_overflow = d_flag;
+    if ((rc = job.run_onepass(L))) return rc;
+    e = cudaMemcpyAsync(p->h_pin, p->d_counts, sizeof(int64_t) * (size_t)N, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->h_pin + N, d_flag, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream);
+    return e == cudaSuccess ? DFD_OK : cuda_error(e, "D2H counts");
+}
+
+static int collect_locked(dfd_partitioner* p, int64_t* starts, int64_t* counts) {
+    dfd_ctx* c = p->ctx;
+    const uint32_t N = p->N;
+    if (p->last == dfd_partitioner::LAST_NONE) return set_error(DFD_ERR_INVALID_ARGUMENT, "no partition call to collect");
+    if (p->last == dfd_partitioner::LAST_DENSE) {
+        std::vector<int64_t> ps(N + 1);
+        cudaError_t e = cudaMemcpyAsync(ps.data(), p->d_part_starts, sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return cuda_error(e, "dfd_partitioner_collect");
+        for (uint32_t q = 0; q < N; ++q) {
+            if (starts) starts[q] = ps[q];
+            if (counts) counts[q] = ps[q + 1] - ps[q];
+        }
+        return DFD_OK;
+    }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cuda_error(e, "single-pass partition");
+    if (p->h_pin[N] != 0) {
+        // a destination outgrew its region (skewed keys): the counts are exact, so re-run with exact,
+        // dense regions (dest_base = prefix of the counts) — always fits in N * region_rows >= n_rows rows
+        std::vector<int64_t> reg(2 * (size_t)N);
+        int64_t run = 0;
+        for (uint32_t q = 0; q < N; ++q) {
+            reg[q] = run;
+            reg[N + q] = p->h_pin[q];
+            run += p->h_pin[q];
+        }
+        e = cudaMemcpyAsync(p->d_counts + N, reg.data(), sizeof(int64_t) * 2 * (size_t)N, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // `reg` is pageable
+        if (e != cudaSuccess) return cuda_error(e, "H2D exact regions");
+        int rc = onepass_launch_locked(p, p->d_counts + N, p->d_counts + 2 * (size_t)N, 0);
+        if (rc) return rc;
+        e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return cuda_error(e, "single-pass partition (exact re-run)");
+        if (p->h_pin[N] != 0) return set_error(DFD_ERR_INTERNAL, "exact re-run overflowed");
+        c->metrics.onepass_reruns++;
+        for (uint32_t q = 0; q < N; ++q) {
+            if (starts) starts[q] = reg[q];
+            if (counts) counts[q] = p->h_pin[q];
+        }
+        p->last_stride = -1;  // dense now
+        return DFD_OK;
+    }
+    for (uint32_t q = 0; q < N; ++q) {
+        if (starts) starts[q] = (int64_t)q * p->last_stride;
+        if (counts) counts[q] = p->h_pin[q];
+    }
+    return DFD_OK;
+}
+
+int dfd_partition_device_onepass(dfd_partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,
+                                 const dfd_column* out_cols, int64_t region_rows, int64_t* part_starts_host,
+                                 int64_t* part_counts_host) {
+    if (!p) return set_error(DFD_ERR_INVALID_ARGUMENT, "partitioner is NULL");
+    dfd_ctx* c = p->ctx;
+    CTX_GUARD(c);
+    if (n_rows < 0 || n_cols < 0 || (n_cols > 0 && (!in_cols || !out_cols)))
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "partition: bad arguments");
+    const uint32_t N = p->N;
+    bool has_fixed = false, has_var = false;
+    for (int i = 0; i < n_cols; ++i) {
+        has_fixed |= in_cols[i].kind == DFD_COL_FIXED;
+        has_var |= in_cols[i].kind == DFD_COL_UTF8 || in_cols[i].kind == DFD_COL_LARGE_UTF8 || in_cols[i].kind == DFD_COL_BINARY;
+    }
+    p->last_in.assign(in_cols, in_cols + n_cols);
+    p->last_out.assign(out_cols, out_cols + n_cols);
+    p->last_rows = n_rows;
+    int rc;
+    if (!has_fixed || has_var || N > ONEPASS_MAX_N) {
+        // dense two-pass path (K1 -> K1b -> K2 [-> K4]); same (start, count) contract
+        if ((rc = partition_device_locked(p, in_cols, n_cols, n_rows, out_cols, c->stream))) return rc;
+        p->last = dfd_partitioner::LAST_DENSE;
+    } else {
+        if (region_rows < 1 || (__int128)region_rows * N < n_rows)
+            return set_error(DFD_ERR_INVALID_ARGUMENT, "region_rows %lld x %u partitions < n_rows %lld", (long long)region_rows, N,
+                             (long long)n_rows);
+        p->last_stride = region_rows;
+        if ((rc = onepass_launch_locked(p, nullptr, nullptr, region_rows))) return rc;
+        p->last = dfd_partitioner::LAST_REGIONS;
+    }
+    if (part_starts_host || part_counts_host) return collect_locked(p, part_starts_host, part_counts_host);
+    return DFD_OK;
+}
+
+int dfd_partitioner_collect(dfd_partitioner* p, int64_t* part_starts_host, int64_t* part_counts_host) {
+    if (!p) return set_error(DFD_ERR_INVALID_ARGUMENT, "partitioner is NULL");
+    dfd_ctx* c = p->ctx;
+    CTX_GUARD(c);
+    return collect_locked(p, part_starts_host, part_counts_host);
 }
 
 }  // extern "C"

@@ -41,6 +41,8 @@ struct dfd_ctx {
     void* scratch_done = nullptr;  // zero-initialised "blocks done" counter inside scratch
     dfd::Scratch flush;    // L2 flush buffer
     dfd::Scratch var_scratch;  // K4: iota | src row ids | block sums
+    dfd::Scratch lb;           // single-pass mode: [ticket, done | 256 B] [look-back descriptors u64 [N][n_tiles]]
+    uint32_t lb_epoch = 0;     // epoch of the last single-pass launch (30 bits; descriptors of older epochs are stale)
     dfd_metrics metrics = {};
     std::mutex mu;
 };
@@ -54,6 +56,12 @@ struct dfd_partitioner {
     dfd::ModN mod{};
     int64_t* d_part_starts = nullptr;  // [N+1]
     size_t smem_configured = 0;
+    // single-pass (region layout) state: results of the last dfd_partition_device_onepass
+    int64_t* d_counts = nullptr;       // [N] rows per destination | [N] dest_base | [N] dest_cap (exact re-run) | overflow flag
+    int64_t* h_pin = nullptr;          // pinned: [N] counts, then the overflow flag
+    enum { LAST_NONE = 0, LAST_DENSE = 1, LAST_REGIONS = 2 } last = LAST_NONE;
+    std::vector<dfd_column> last_in, last_out;
+    int64_t last_rows = 0, last_stride = 0;
 };
 
 namespace dfd {
@@ -85,7 +93,21 @@ struct PartitionJob {
     int run_scatter(const int64_t* dest_base, void* const* peer_base, int world, uint32_t parts_per_rank,
                     const int32_t* abort_flag);
     int run_varwidth();  // called by run_scatter after the fixed-width launches
+    // Single-pass K2 (no K1/K1b): destinations live in fixed regions; see k_scatter<..., ONEPASS>.
+    struct OnePassLayout {
+        const int64_t* d_dest_base = nullptr;  // device [N] region starts (rows); nullptr: region_stride formula
+        const int64_t* d_dest_cap = nullptr;   // device [N] region capacities; nullptr: region_stride
+        int64_t region_stride = 0;
+        void* const* peer_base = nullptr;      // peer mode: every rank's window slot
+        int world = 1, rank = 0;
+        uint32_t parts_per_rank = 1;
+        int64_t* d_totals = nullptr;           // device [N] out: rows per destination
+        int32_t* d_overflow = nullptr;         // device out: set to 1 if a region is too small (caller zeroes it)
+    };
+    int run_onepass(const OnePassLayout& L);
 };
+
+constexpr uint32_t ONEPASS_MAX_N = 256;  // above this the per-tile look-back costs more than the K1 pass it replaces
 
 // Small conversion kernels the exchange uses for bit-packed / variable-width columns (defined in dfd_api.cu).
 int launch_bits_to_bytes(const uint8_t* bits, int64_t bit_offset, int64_t n, uint8_t* out, cudaStream_t s);

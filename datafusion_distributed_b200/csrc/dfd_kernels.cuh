@@ -357,6 +357,34 @@ __device__ __forceinline__ void scatter_bit_column(const PayloadCol& c, void* st
 
 struct BitColumn {};  // tag: bit-packed column (boolean values / validity bitmap)
 
+// ---- decoupled look-back descriptors (single-pass mode) --------------------
+// One 64-bit word per (destination, tile): high half = (call epoch << 2) | state, low half = rows.
+// Status and value travel in ONE word, so relaxed loads/stores suffice (Merrill & Garland's
+// single-word trick); a word whose epoch is not the current call's reads as "not published", so
+// the table never needs clearing between calls.
+constexpr uint32_t LB_AGG = 1u;     // value = rows of this tile for the destination
+constexpr uint32_t LB_PREFIX = 2u;  // value = rows of tiles 0..this for the destination (inclusive)
+
+__device__ __forceinline__ unsigned long long lb_pack(uint32_t epoch, uint32_t state, uint32_t value) {
+    return ((unsigned long long)((epoch << 2) | state) << 32) | value;
+}
+__device__ __forceinline__ void lb_store(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long lb_load(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// first output row of destination p's region (single-pass mode without an explicit dest_base[])
+template <bool PEER>
+__device__ __forceinline__ int64_t region_base_of(const ScatterParams& P, uint32_t p) {
+    if (P.dest_base) return P.dest_base[p];
+    if (PEER) return ((int64_t)(p % P.parts_per_rank) * P.world + P.rank) * P.region_stride;
+    return (int64_t)p * P.region_stride;
+}
+
 // One instantiation per element type V: a launch moves all columns of one
 // width (the host groups them), so the hot instantiation (8-byte values)
 // carries no code or registers for the other widths.
@@ -365,37 +393,55 @@ struct BitColumn {};  // tag: bit-packed column (boolean values / validity bitma
 // space in which every destination's run is shifted so that each warp's 32 rows
 // start on a 32-row (256 B for 8-byte values) boundary of the OUTPUT buffer —
 // full-line stores to HBM and full-size write packets over NVLink.
-template <int THREADS, int K, int KV, int MIN_CTAS, bool FAST_I64, typename V, bool PEER>
+// ONEPASS: no K1/K1b.  CTAs take tile tickets in launch order, count their own
+// destinations while ranking (phase 1), publish the counts and resolve their
+// write cursors by decoupled look-back over the predecessors' descriptors
+// (warp w looks back for destinations w, w+W, ... 32 predecessors at a time):
+// every row is hashed once and the key column is read once.  Order is stable
+// (cursor = sum over lower tiles).  Destinations live in fixed regions
+// (dest_base / region_stride); a tile that would overflow a region sets
+// overflow_out and writes nothing (the host re-runs with exact regions).
+template <int THREADS, int K, int KV, int MIN_CTAS, bool FAST_I64, typename V, bool PEER, bool ONEPASS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_constant__ ScatterParams P) {
     constexpr int T = THREADS * K;
     constexpr int W = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t N = P.N;
-    // layout: stage | delta[N] | warp_cnt[W][N] | tile_start[N+1] | scan scratch
+    // layout: stage | delta[N] | warp_cnt[W][N] | tile_start[N+1] | scan scratch | misc[2]
     unsigned char* stage = smem;
     const uint32_t off_delta = ((uint32_t)T * (uint32_t)P.stage_width + 15u) & ~15u;
     const uint32_t off_wc = off_delta + N * 8u;
     const uint32_t off_ts = off_wc + (uint32_t)W * N * 4u;
     const uint32_t off_scan = off_ts + (N + 1u) * 4u;
-    const uint32_t off_ob = (off_scan + (uint32_t)(W + 1) * 4u + 7u) & ~7u;  // peer mode only: per-destination bases
+    const uint32_t off_misc = off_scan + (uint32_t)(W + 1) * 4u;          // [0] tile ticket, [1] tile overflow
+    const uint32_t off_ob = (off_misc + 2u * 4u + 7u) & ~7u;               // peer mode only: per-destination bases
     const uint32_t off_vs = off_ob + N * 8u;                                // aligned mode only: virtual run starts
 #define OUT_BASE ((void**)(smem + off_ob))
 #define VSTART ((uint32_t*)(smem + off_vs))
-    if (PEER && *P.abort_flag) return;
+    if (!ONEPASS && P.abort_flag && *P.abort_flag) return;  // a window / region overflowed: write nothing
 #define DELTA ((int64_t*)(smem + off_delta))
 #define WARP_CNT ((uint32_t*)(smem + off_wc))
 #define TILE_START ((uint32_t*)(smem + off_ts))
 #define S_SCAN ((uint32_t*)(smem + off_scan))
+#define S_MISC ((uint32_t*)(smem + off_misc))
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t tile = blockIdx.x;
+    int64_t tile = blockIdx.x;
+    if constexpr (ONEPASS) {
+        if (threadIdx.x == 0) {
+            S_MISC[0] = atomicAdd(P.lb_ticket, 1u);
+            S_MISC[1] = 0;
+        }
+        __syncthreads();
+        tile = S_MISC[0];
+    }
     const int64_t row0 = tile * T;
     const int tile_rows = (int)((P.n_rows - row0) < T ? (P.n_rows - row0) : T);
     const int t0 = w * (K * 32) + lane;  // this thread's first tile-relative row; rows t0 + 32*j
 
-    // ---- tile_start / delta from the K1 histogram (independent of phase 1).
+    // ---- two-pass mode: tile_start / delta from the K1 histogram (independent of phase 1).
     // delta[p] maps a staging slot i to its absolute output row: out_row = i + delta[p]
-    {
+    if constexpr (!ONEPASS) {
         uint32_t carry = 0;
         for (uint32_t p0 = 0; p0 < N; p0 += THREADS) {
             uint32_t p = p0 + threadIdx.x;
@@ -405,7 +451,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
             if (p < N) {
                 uint32_t ts = carry + ex;
                 TILE_START[p] = ts;
-                DELTA[p] = P.dest_base[p] + (int64_t)P.tile_base[(int64_t)p * P.n_tiles + tile] - (int64_t)ts;
+                DELTA[p] = region_base_of<PEER>(P, p) + (int64_t)P.tile_base[(int64_t)p * P.n_tiles + tile] - (int64_t)ts;
             }
             carry += tot;
         }
@@ -432,14 +478,43 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
         pos[j] = (d << 16) | (base + rank);
     }
     __syncthreads();
-    // warp_cnt[w][p] -> staging base of (warp w, destination p)
-    for (uint32_t p = threadIdx.x; p < N; p += THREADS) {
-        uint32_t run = TILE_START[p];
+    if constexpr (ONEPASS) {
+        // tile counts = sum of the warps' counts; publish them, then turn warp_cnt into staging bases
+        uint32_t carry = 0;
+        for (uint32_t p0 = 0; p0 < N; p0 += THREADS) {
+            uint32_t p = p0 + threadIdx.x;
+            uint32_t c = 0;
+            if (p < N) {
 #pragma unroll
-        for (int ww = 0; ww < W; ++ww) {
-            uint32_t c = WARP_CNT[(uint32_t)ww * N + p];
-            WARP_CNT[(uint32_t)ww * N + p] = run;
-            run += c;
+                for (int ww = 0; ww < W; ++ww) c += WARP_CNT[(uint32_t)ww * N + p];
+                // tile 0 has no predecessor: its aggregate IS its inclusive prefix
+                lb_store(P.lb_desc + (int64_t)p * P.n_tiles + tile, lb_pack(P.lb_epoch, tile == 0 ? LB_PREFIX : LB_AGG, c));
+            }
+            uint32_t tot;
+            uint32_t ex = block_exclusive_scan<THREADS>(c, S_SCAN, tot);
+            if (p < N) {
+                uint32_t run = carry + ex;
+                TILE_START[p] = run;
+#pragma unroll
+                for (int ww = 0; ww < W; ++ww) {
+                    uint32_t cc = WARP_CNT[(uint32_t)ww * N + p];
+                    WARP_CNT[(uint32_t)ww * N + p] = run;
+                    run += cc;
+                }
+            }
+            carry += tot;
+        }
+        if (threadIdx.x == 0) TILE_START[N] = carry;
+    } else {
+        // warp_cnt[w][p] -> staging base of (warp w, destination p)
+        for (uint32_t p = threadIdx.x; p < N; p += THREADS) {
+            uint32_t run = TILE_START[p];
+#pragma unroll
+            for (int ww = 0; ww < W; ++ww) {
+                uint32_t c = WARP_CNT[(uint32_t)ww * N + p];
+                WARP_CNT[(uint32_t)ww * N + p] = run;
+                run += c;
+            }
         }
     }
     __syncthreads();
@@ -447,6 +522,57 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
     for (int j = 0; j < K; ++j) {
         uint32_t d = pos[j] >> 16;
         pos[j] = d < N ? wc[d] + (pos[j] & 0xffffu) : 0;
+    }
+    if constexpr (ONEPASS) {
+        // ---- decoupled look-back: exclusive prefix of every destination over the lower tiles
+        for (uint32_t p = (uint32_t)w; p < N; p += W) {
+            const uint32_t cnt = TILE_START[p + 1] - TILE_START[p];
+            uint32_t excl = 0;
+            if (tile > 0) {
+                const unsigned long long* d = P.lb_desc + (int64_t)p * P.n_tiles;
+                int64_t j = tile - 1;  // lane 0 looks at the nearest predecessor
+                for (;;) {
+                    const int64_t idx = j - lane;
+                    uint32_t st = LB_PREFIX, val = 0;
+                    if (idx >= 0) {
+                        unsigned long long v;
+                        uint32_t hi;
+                        do {
+                            v = lb_load(d + idx);
+                            hi = (uint32_t)(v >> 32);
+                        } while ((hi >> 2) != P.lb_epoch || (hi & 3u) == 0u);
+                        st = hi & 3u;
+                        val = (uint32_t)v;
+                    }
+                    const unsigned pm = __ballot_sync(0xffffffffu, st == LB_PREFIX);
+                    const int first = __ffs(pm) - 1;  // nearest predecessor with an inclusive prefix (-1: none)
+                    excl += __reduce_add_sync(0xffffffffu, (first < 0 || lane <= first) ? val : 0u);
+                    if (pm) break;
+                    j -= 32;
+                }
+                if (lane == 0) lb_store(P.lb_desc + (int64_t)p * P.n_tiles + tile, lb_pack(P.lb_epoch, LB_PREFIX, excl + cnt));
+            }
+            if (lane == 0) {
+                const int64_t cap = P.dest_cap ? P.dest_cap[p] : P.region_stride;
+                if ((int64_t)excl + (int64_t)cnt > cap) S_MISC[1] = 1;
+                DELTA[p] = region_base_of<PEER>(P, p) + (int64_t)excl - (int64_t)TILE_START[p];
+                if (P.hist_out) {
+                    P.hist_out[(int64_t)p * P.n_tiles + tile] = cnt;
+                    P.base_out[(int64_t)p * P.n_tiles + tile] = excl;
+                }
+                if (tile == P.n_tiles - 1) P.totals_out[p] = (int64_t)excl + (int64_t)cnt;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (S_MISC[1]) *P.overflow_out = 1;
+            // every CTA has its ticket once `n_tiles` CTAs are past this point: the last one re-arms the counters
+            if (atomicAdd(P.lb_ticket + 1, 1u) == (unsigned)(P.n_tiles - 1)) {
+                P.lb_ticket[0] = 0;
+                P.lb_ticket[1] = 0;
+            }
+        }
+        if (S_MISC[1]) return;  // a region is too small: this tile writes nothing
     }
     // ---- which staging slot (and destination) each of this thread's write-out iterations handles
     uint32_t slot[KV];
@@ -526,6 +652,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
 #undef WARP_CNT
 #undef TILE_START
 #undef S_SCAN
+#undef S_MISC
 }
 
 // ---------------------------------------------------------------------------
@@ -710,6 +837,7 @@ inline size_t scatter_smem_bytes(uint32_t N, int stage_width, bool peer, bool al
     off += (size_t)(THREADS / 32) * N * 4;
     off += (size_t)(N + 1) * 4;
     off += (size_t)(THREADS / 32 + 1) * 4;
+    off += 2 * 4;  // misc: tile ticket, tile overflow (single-pass mode)
     off = (off + 7) & ~(size_t)7;
     if (peer || aligned) off += (size_t)N * 8;  // per-destination output bases (peer mode)
     if (aligned) off += (size_t)(N + 1) * 4;    // virtual run starts (aligned mode)

@@ -35,6 +35,19 @@ struct ScatterParams {
     uint32_t parts_per_rank;     // peer mode: destination p lives on rank p / parts_per_rank
     void* peer_base[MAX_RANKS];  // peer mode: every rank's receive window (CUDA-IPC mapped, NVLink)
     const int32_t* abort_flag;   // peer mode: non-zero => a receive window would overflow; do nothing
+    // ---- single-pass mode (k_scatter<..., ONEPASS>): no K1/K1b; tile cursors by decoupled look-back ----
+    unsigned long long* lb_desc; // [N][n_tiles] look-back descriptors: (epoch<<2 | state) << 32 | rows
+    unsigned* lb_ticket;         // [0] next tile ticket, [1] finished CTAs (both reset by the last CTA)
+    uint32_t lb_epoch;           // call epoch (30 bits): descriptors of older calls read as "not published"
+    int32_t rank;                // peer mode: this producer's task index
+    int32_t world;               // peer mode: number of workers
+    int64_t region_stride;       // rows per destination region when dest_base == nullptr:
+                                 //   local: region p starts at row p*stride; peer: (p % parts_per_rank)*world + rank
+    const int64_t* dest_cap;     // [N] rows each region can hold (nullptr: region_stride)
+    int64_t* totals_out;         // [N] rows per destination (written by the last tile)
+    int32_t* overflow_out;       // set to 1 when a region is too small (that tile writes nothing)
+    uint32_t* hist_out;          // optional [N][n_tiles]: per-tile counts / cursors for follow-up launches
+    uint32_t* base_out;          //   (other column widths) that run the two-pass k_scatter code path
 };
 
 }  // namespace dfd

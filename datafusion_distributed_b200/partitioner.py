@@ -77,3 +77,37 @@ class HashPartitioner:
         nv.check(nv.lib().dfd_partition_device(self._h, columns_to_c(cols), len(cols), n_rows,
                                                columns_to_c(out_cols), starts))
         return out_cols, (np.frombuffer(starts, dtype=np.int64).copy() if sync else None)
+
+    # -- single-pass form (region layout) ------------------------------------------
+    def default_region_rows(self, n_rows: int, slack: float = 0.25) -> int:
+        """Rows reserved per destination: the fair share plus `slack`, rounded up to 32 rows
+        (aligned region starts).  A destination that outgrows it triggers the exact re-run."""
+        N = self.num_partitions
+        fair = -(-max(n_rows, 1) // N)
+        return (int(fair * (1.0 + slack)) + 32 + 31) // 32 * 32
+
+    def partition_onepass(self, cols: Sequence[DeviceColumn], n_rows: int, region_rows: Optional[int] = None,
+                          out_cols: Optional[List[DeviceColumn]] = None, sync: bool = True):
+        """`dfd_partition_device_onepass`: one kernel, no histogram pass.  Destination p is rows
+        [starts[p], starts[p] + counts[p]) of every output column (starts[p] = p * region_rows unless the
+        call fell back to / re-ran with the dense layout).  Returns (out_cols, starts[N], counts[N]);
+        with sync=False the arrays are None and `collect()` fetches them."""
+        N = self.num_partitions
+        if region_rows is None:
+            region_rows = self.default_region_rows(n_rows)
+        if out_cols is None:
+            out_cols = [DeviceColumn.empty_like(self.ctx, c, N * region_rows) for c in cols]
+        starts = (C.c_int64 * N)() if sync else None
+        counts = (C.c_int64 * N)() if sync else None
+        nv.check(nv.lib().dfd_partition_device_onepass(self._h, columns_to_c(cols), len(cols), n_rows, columns_to_c(out_cols),
+                                                       region_rows, starts, counts))
+        if not sync:
+            return out_cols, None, None
+        return out_cols, np.frombuffer(starts, dtype=np.int64).copy(), np.frombuffer(counts, dtype=np.int64).copy()
+
+    def collect(self):
+        """Complete an asynchronous `partition_onepass(sync=False)`: (starts[N], counts[N])."""
+        N = self.num_partitions
+        starts, counts = (C.c_int64 * N)(), (C.c_int64 * N)()
+        nv.check(nv.lib().dfd_partitioner_collect(self._h, starts, counts))
+        return np.frombuffer(starts, dtype=np.int64).copy(), np.frombuffer(counts, dtype=np.int64).copy()

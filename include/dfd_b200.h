@@ -86,6 +86,7 @@ typedef struct {
     double h2d_ms;
     double d2h_ms;
     uint64_t scatter_launches;
+    uint64_t onepass_reruns; /* single-pass calls that overflowed a region and re-ran exactly */
 } dfd_metrics;
 
 /* ---- library / context ------------------------------------------------ */
@@ -162,6 +163,27 @@ int dfd_partition_ids_device(dfd_partitioner* p, const dfd_column* cols, int n_c
 int dfd_partition_device(dfd_partitioner* p, const dfd_column* in_cols, int n_cols,
                          int64_t n_rows, const dfd_column* out_cols, int64_t* part_starts_host);
 const int64_t* dfd_partitioner_part_starts_device(const dfd_partitioner* p);
+
+/* Single-pass form of the hot path (same reference interface as dfd_partition_device:
+ * BatchPartitioner::partition, src/worker/impl_execute_task.rs:77-86).  ONE kernel hashes every
+ * row once, ranks it, resolves the per-tile write cursors by decoupled look-back and scatters —
+ * there is no histogram pass, so destination totals are not known before the first store.
+ * Destination p therefore owns a fixed REGION of every output column: rows
+ * [part_starts[p], part_starts[p] + part_counts[p]) with part_starts[p] = p * region_rows — still
+ * N contiguous, zero-copy sliceable per-destination buffers, in input order.
+ *   out_cols[c] must hold N * region_rows rows, and N * region_rows >= n_rows.
+ *   If a destination outgrows its region (skewed keys) nothing is lost: collection re-runs
+ *   the kernel with exact regions (part_starts = prefix sums of the now-known counts, dense).
+ *   Variable-width payload columns, boolean-only schemas and N > 256 take the two-pass
+ *   path internally and return the dense layout through the same (start, count) contract.
+ * part_starts_host / part_counts_host (N int64 each): both NULL = asynchronous on
+ * dfd_ctx_stream(); fetch the result later with dfd_partitioner_collect (which synchronises
+ * and performs the exact re-run if needed).  Bit-packed outputs follow the rules of
+ * dfd_partition_device with n_rows replaced by N * region_rows. */
+int dfd_partition_device_onepass(dfd_partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,
+                                 const dfd_column* out_cols, int64_t region_rows, int64_t* part_starts_host,
+                                 int64_t* part_counts_host);
+int dfd_partitioner_collect(dfd_partitioner* p, int64_t* part_starts_host, int64_t* part_counts_host);
 
 /* ---- host operator: RepartitionExec(Hash) over Arrow C Data / C Stream ----
  * Replaces, on one worker, `RepartitionExec::try_new(input,
