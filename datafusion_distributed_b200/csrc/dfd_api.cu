@@ -47,6 +47,15 @@ int cuda_error(cudaError_t e, const char* what) {
 #ifndef DFD_TILE_MIN_CTAS
 #define DFD_TILE_MIN_CTAS 6
 #endif
+// single-pass kernel: ring depth (tiles in flight per CTA) and resident CTAs per SM
+#ifndef DFD_ONEPASS_NB
+#define DFD_ONEPASS_NB 3
+#endif
+#ifndef DFD_ONEPASS_MIN_CTAS
+#define DFD_ONEPASS_MIN_CTAS 4
+#endif
+constexpr int ONEPASS_NB = DFD_ONEPASS_NB;
+constexpr int ONEPASS_MIN_CTAS = DFD_ONEPASS_MIN_CTAS;
 constexpr int TILE_THREADS = DFD_TILE_THREADS;
 constexpr int TILE_K = DFD_TILE_K;
 constexpr int TILE_MIN_CTAS = DFD_TILE_MIN_CTAS;
@@ -134,18 +143,6 @@ static int build_keyset(const dfd_partitioner* p, const dfd_column* cols, int n_
         if (_e != cudaSuccess) return cuda_error(_e, what);            \
     }
 
-template <bool FAST, typename V, bool PEER, int KV, bool ONEPASS>
-static int launch_scatter_kv(const ScatterParams& sp, unsigned grid, size_t smem, cudaStream_t stream) {
-    auto kern = k_scatter<TILE_THREADS, TILE_K, KV, TILE_MIN_CTAS, FAST, V, PEER, ONEPASS>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(k_scatter)");
-    }
-    kern<<<grid, TILE_THREADS, smem, stream>>>(sp);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? DFD_OK : cuda_error(e, "k_scatter");
-}
-
 // Measured on B200 (profiles/): aligned write-out costs ~5% on local HBM stores (more write-out
 // iterations, L2 already merges partial lines) but gains ~15% on NVLink peer stores (full-size
 // write packets), so it is on for the fused exchange only.  DFD_ALIGNED_WRITEOUT=0/1 forces it.
@@ -155,32 +152,70 @@ static bool use_aligned(uint32_t N, bool peer) {
     return forced >= 0 ? forced == 1 : peer;
 }
 
+// grid < 0: two-pass k_scatter (one CTA per tile).  ONEPASS: persistent k_scatter_onepass, one CTA per resident slot.
+template <bool FAST, typename V, bool PEER, int KV, bool ONEPASS>
+static int launch_scatter_kv(const ScatterParams& sp, int sm_count, size_t smem, cudaStream_t stream) {
+    cudaError_t e;
+    if constexpr (ONEPASS) {
+        if constexpr (std::is_same<V, BitColumn>::value) {
+            return set_error(DFD_ERR_INTERNAL, "bit-packed columns take the two-pass k_scatter");
+        } else {
+            auto kern = k_scatter_onepass<TILE_THREADS, TILE_K, KV, ONEPASS_NB, ONEPASS_MIN_CTAS, FAST, V, PEER>;
+            smem = onepass_smem_bytes<TILE_THREADS, TILE_K, ONEPASS_NB>(sp.N, (int)sizeof(V), PEER, KV != TILE_K);
+            if (smem > 227 * 1024) return set_error(DFD_ERR_UNSUPPORTED, "single-pass kernel needs %zu B of shared memory per CTA", smem);
+            // (static per instantiation: the attribute and the occupancy are properties of the kernel + smem size)
+            static thread_local size_t cfg_smem = 0;
+            static thread_local int cfg_per_sm = 0;
+            if (cfg_smem != smem) {
+                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+                    return cuda_error(e, "cudaFuncSetAttribute(k_scatter_onepass)");
+                if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_per_sm, kern, TILE_THREADS + 32, smem)) != cudaSuccess)
+                    return cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+                if (cfg_per_sm < 1) cfg_per_sm = 1;
+                cfg_smem = smem;
+            }
+            int64_t grid = (int64_t)cfg_per_sm * sm_count;
+            if (grid > sp.n_tiles) grid = sp.n_tiles;
+            kern<<<(unsigned)grid, TILE_THREADS + 32, smem, stream>>>(sp);
+        }
+    } else {
+        auto kern = k_scatter<TILE_THREADS, TILE_K, KV, TILE_MIN_CTAS, FAST, V, PEER>;
+        if (smem > 48 * 1024) {
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+                return cuda_error(e, "cudaFuncSetAttribute(k_scatter)");
+        }
+        kern<<<(unsigned)sp.n_tiles, TILE_THREADS, smem, stream>>>(sp);
+    }
+    e = cudaGetLastError();
+    return e == cudaSuccess ? DFD_OK : cuda_error(e, "k_scatter");
+}
+
 template <bool FAST, typename V, bool PEER, bool ONEPASS>
-static int launch_scatter_t(const ScatterParams& sp, unsigned grid, size_t smem, cudaStream_t stream) {
-    if (use_aligned(sp.N, PEER)) return launch_scatter_kv<FAST, V, PEER, TILE_KV, ONEPASS>(sp, grid, smem, stream);
-    return launch_scatter_kv<FAST, V, PEER, TILE_K, ONEPASS>(sp, grid, smem, stream);
+static int launch_scatter_t(const ScatterParams& sp, int sm_count, size_t smem, cudaStream_t stream) {
+    if (use_aligned(sp.N, PEER)) return launch_scatter_kv<FAST, V, PEER, TILE_KV, ONEPASS>(sp, sm_count, smem, stream);
+    return launch_scatter_kv<FAST, V, PEER, TILE_K, ONEPASS>(sp, sm_count, smem, stream);
 }
 
 template <bool FAST, bool PEER, bool ONEPASS>
-static int launch_scatter_w(const ScatterParams& sp, int width, unsigned grid, size_t smem, cudaStream_t stream) {
+static int launch_scatter_w(const ScatterParams& sp, int width, int sm_count, size_t smem, cudaStream_t stream) {
     switch (width) {
-        case 8: return launch_scatter_t<FAST, uint64_t, PEER, ONEPASS>(sp, grid, smem, stream);
-        case 4: return launch_scatter_t<FAST, uint32_t, PEER, ONEPASS>(sp, grid, smem, stream);
-        case 2: return launch_scatter_t<FAST, uint16_t, PEER, ONEPASS>(sp, grid, smem, stream);
-        case 1: return launch_scatter_t<FAST, uint8_t, PEER, ONEPASS>(sp, grid, smem, stream);
-        case 16: return launch_scatter_t<FAST, uint4, PEER, ONEPASS>(sp, grid, smem, stream);
+        case 8: return launch_scatter_t<FAST, uint64_t, PEER, ONEPASS>(sp, sm_count, smem, stream);
+        case 4: return launch_scatter_t<FAST, uint32_t, PEER, ONEPASS>(sp, sm_count, smem, stream);
+        case 2: return launch_scatter_t<FAST, uint16_t, PEER, ONEPASS>(sp, sm_count, smem, stream);
+        case 1: return launch_scatter_t<FAST, uint8_t, PEER, ONEPASS>(sp, sm_count, smem, stream);
+        case 16: return launch_scatter_t<FAST, uint4, PEER, ONEPASS>(sp, sm_count, smem, stream);
         default:
             if constexpr (PEER || ONEPASS) {
                 return set_error(DFD_ERR_INTERNAL, "bit-packed columns take the two-pass local k_scatter instantiation");
             } else {
-                return launch_scatter_t<FAST, BitColumn, false, false>(sp, grid, smem, stream);
+                return launch_scatter_t<FAST, BitColumn, false, false>(sp, sm_count, smem, stream);
             }
     }
 }
 
-static int launch_scatter(const ScatterParams& sp, int width, bool fast, bool peer, bool onepass, unsigned grid, size_t smem,
+static int launch_scatter(const ScatterParams& sp, int width, bool fast, bool peer, bool onepass, int sm_count, size_t smem,
                           cudaStream_t stream) {
-#define DFD_LS(F, PE, OP) return launch_scatter_w<F, PE, OP>(sp, width, grid, smem, stream)
+#define DFD_LS(F, PE, OP) return launch_scatter_w<F, PE, OP>(sp, width, sm_count, smem, stream)
     if (onepass) {
         if (peer) { if (fast) DFD_LS(true, true, true); else DFD_LS(false, true, true); }
         if (fast) DFD_LS(true, false, true); else DFD_LS(false, false, true);
@@ -394,7 +429,7 @@ int dfd::PartitionJob::run_scatter(const int64_t* dest_base, void* const* peer_b
                 size_t n = group.size() - first < (size_t)MAX_COLS_PER_LAUNCH ? group.size() - first : (size_t)MAX_COLS_PER_LAUNCH;
                 for (size_t i = 0; i < n; ++i) sp.cols[i] = group[first + i];
                 sp.n_cols = (int32_t)n;
-                int rc = launch_scatter(sp, width, ks.fast_i64 != 0, peer, false, (unsigned)n_tiles, smem, stream);
+                int rc = launch_scatter(sp, width, ks.fast_i64 != 0, peer, false, c->sm_count, smem, stream);
                 if (rc) return rc;
                 ++launches;
             }
@@ -480,7 +515,7 @@ int dfd::PartitionJob::run_onepass(const OnePassLayout& L) {
             if (group.empty()) continue;
             if (first && width == 0) return set_error(DFD_ERR_INTERNAL, "single-pass mode needs a fixed-width column");
             sp.stage_width = width ? width : 1;
-            size_t smem = scatter_smem_bytes<TILE_THREADS, TILE_K>(N, sp.stage_width, peer, use_aligned(N, peer));
+            size_t smem = scatter_smem_bytes<TILE_THREADS, TILE_K>(N, sp.stage_width, peer, use_aligned(N, peer), first);
             if (smem > 227 * 1024)
                 return set_error(DFD_ERR_UNSUPPORTED, "num_partitions %u needs %zu B of shared memory per CTA", N, smem);
             for (size_t f0 = 0; f0 < group.size(); f0 += MAX_COLS_PER_LAUNCH) {
@@ -492,14 +527,14 @@ int dfd::PartitionJob::run_onepass(const OnePassLayout& L) {
                     const bool more = n_groups > 1 || group.size() > (size_t)MAX_COLS_PER_LAUNCH;
                     sp.hist_out = more ? d_hist : nullptr;
                     sp.base_out = more ? d_base : nullptr;
-                    rc = launch_scatter(sp, width, ks.fast_i64 != 0, peer, true, (unsigned)n_tiles, smem, stream);
+                    rc = launch_scatter(sp, width, ks.fast_i64 != 0 && width == 8, peer, true, c->sm_count, smem, stream);
                     first = false;
                     // the follow-up launches take the two-pass code path over the counts / cursors just written
                     sp.hist = d_hist;
                     sp.tile_base = d_base;
                     sp.abort_flag = L.d_overflow;
                 } else {
-                    rc = launch_scatter(sp, width, ks.fast_i64 != 0, peer, false, (unsigned)n_tiles, smem, stream);
+                    rc = launch_scatter(sp, width, ks.fast_i64 != 0, peer, false, c->sm_count, smem, stream);
                 }
                 if (rc) return rc;
                 ++launches;
@@ -991,6 +1026,8 @@ int dfd_partition_device_onepass(dfd_partitioner* p, const dfd_column* in_cols, 
         if (region_rows < 1 || (__int128)region_rows * N < n_rows)
             return set_error(DFD_ERR_INVALID_ARGUMENT, "region_rows %lld x %u partitions < n_rows %lld", (long long)region_rows, N,
                              (long long)n_rows);
+        if ((__int128)region_rows * N >= 0xffffffffLL)
+            return set_error(DFD_ERR_UNSUPPORTED, "region_rows x partitions must be < 2^32 - 1 rows per call (32-bit output rows)");
         p->last_stride = region_rows;
         if ((rc = onepass_launch_locked(p, nullptr, nullptr, region_rows))) return rc;
         p->last = dfd_partitioner::LAST_REGIONS;

@@ -23,7 +23,15 @@ namespace dfd {
 // ---------------------------------------------------------------------------
 // small block-scan helper: exclusive scan of one value per thread
 // ---------------------------------------------------------------------------
-template <int THREADS>
+// BAR == 0: __syncthreads(); BAR > 0: named barrier BAR over the first THREADS threads of the CTA (the
+// consumer warps of a warp-specialised kernel; the producer warp never joins it)
+template <int THREADS, int BAR>
+__device__ __forceinline__ void block_sync() {
+    if constexpr (BAR == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(THREADS) : "memory");
+}
+
+template <int THREADS, int BAR = 0>
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp /*[THREADS/32 + 1]*/,
                                                          uint32_t& block_total) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -34,7 +42,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
         if (lane >= d) inc += t;
     }
     if (lane == 31) s_warp[w] = inc;
-    __syncthreads();
+    block_sync<THREADS, BAR>();
     if (w == 0) {
         uint32_t x = lane < THREADS / 32 ? s_warp[lane] : 0;
         uint32_t xi = x;
@@ -46,10 +54,10 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
         if (lane < THREADS / 32) s_warp[lane] = xi - x;
         if (lane == 31) s_warp[THREADS / 32] = xi;
     }
-    __syncthreads();
+    block_sync<THREADS, BAR>();
     uint32_t res = s_warp[w] + inc - v;
     block_total = s_warp[THREADS / 32];
-    __syncthreads();
+    block_sync<THREADS, BAR>();
     return res;
 }
 
@@ -279,7 +287,15 @@ struct StageIO {
 
 constexpr uint32_t SLOT_NONE = 0xffffffffu;
 
-template <int THREADS, int K, int KV, typename V, int CHUNK = K>
+// Payload columns are streamed exactly once: evict-first loads / stores keep the L2 for what is reused
+// (the key tiles between phase 1 and the scatter of the same tile, the look-back descriptors).
+template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
+template <typename V> __device__ __forceinline__ void st_stream(V* p, V v) { __stcs(p, v); }
+
+// ROWS == false: slot[k] = (destination << 16 | staging index) for write-out iteration k (or SLOT_NONE)
+// ROWS == true : slot[k] = absolute output row of staging index k*THREADS + threadIdx.x (or SLOT_NONE) — local
+//                mode with KV == K: no per-store delta lookup, 4 instructions per stored element
+template <int THREADS, int K, int KV, typename V, int CHUNK = K, bool ROWS = false>
 __device__ __forceinline__ void scatter_fixed_column(const PayloadCol& c, void* stage_raw, int64_t row0, int tile_rows,
                                                      const uint32_t (&ps)[K], const uint32_t (&slot)[KV], const int64_t* delta,
                                                      int t0, void* const* out_base /* per destination (peer mode) or nullptr */) {
@@ -291,7 +307,7 @@ __device__ __forceinline__ void scatter_fixed_column(const PayloadCol& c, void* 
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) {
         int t = t0 + j * 32;
-        if (t < tile_rows) v[j] = in[t];
+        if (t < tile_rows) v[j] = ld_stream(in + t);
     }
     __syncthreads();  // staging buffer free (previous column fully written out)
 #pragma unroll
@@ -300,7 +316,7 @@ __device__ __forceinline__ void scatter_fixed_column(const PayloadCol& c, void* 
 #pragma unroll
             for (int j = 0; j < CHUNK; ++j) {
                 int t = t0 + (ch * CHUNK + j) * 32;
-                if (t < tile_rows) v[j] = in[t];
+                if (t < tile_rows) v[j] = ld_stream(in + t);
             }
         }
 #pragma unroll
@@ -310,12 +326,19 @@ __device__ __forceinline__ void scatter_fixed_column(const PayloadCol& c, void* 
         }
     }
     __syncthreads();  // staging buffer holds the tile in destination order
+    if constexpr (ROWS) {
+        static_assert(KV == K, "row mode walks the staging buffer linearly");
 #pragma unroll
-    for (int k = 0; k < KV; ++k) {
-        if (slot[k] != SLOT_NONE) {
-            const uint32_t i = slot[k] & 0xffffu, p = slot[k] >> 16;
-            V* o = out_base ? (V*)out_base[p] : out;  // peer mode: the owner rank's receive window (NVLink store)
-            o[(int64_t)i + delta[p]] = stage[i];
+        for (int k = 0; k < K; ++k)
+            if (slot[k] != SLOT_NONE) st_stream(out + slot[k], stage[k * THREADS + (int)threadIdx.x]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < KV; ++k) {
+            if (slot[k] != SLOT_NONE) {
+                const uint32_t i = slot[k] & 0xffffu, p = slot[k] >> 16;
+                V* o = out_base ? (V*)out_base[p] : out;  // peer mode: the owner rank's receive window (NVLink store)
+                st_stream(o + ((int64_t)i + delta[p]), stage[i]);
+            }
         }
     }
 }
@@ -393,55 +416,155 @@ __device__ __forceinline__ int64_t region_base_of(const ScatterParams& P, uint32
 // space in which every destination's run is shifted so that each warp's 32 rows
 // start on a 32-row (256 B for 8-byte values) boundary of the OUTPUT buffer —
 // full-line stores to HBM and full-size write packets over NVLink.
-// ONEPASS: no K1/K1b.  CTAs take tile tickets in launch order, count their own
-// destinations while ranking (phase 1), publish the counts and resolve their
-// write cursors by decoupled look-back over the predecessors' descriptors
-// (warp w looks back for destinations w, w+W, ... 32 predecessors at a time):
-// every row is hashed once and the key column is read once.  Order is stable
-// (cursor = sum over lower tiles).  Destinations live in fixed regions
-// (dest_base / region_stride); a tile that would overflow a region sets
-// overflow_out and writes nothing (the host re-runs with exact regions).
-template <int THREADS, int K, int KV, int MIN_CTAS, bool FAST_I64, typename V, bool PEER, bool ONEPASS>
+struct ScatterSmem {
+    // layout: stage | delta[N] | warp_cnt[W][N] | tile_start[2][N+1] | scan scratch | misc[4] | pos16[2][T] | dest8[2][T] | out_base[N] | vstart[N+1]
+    uint32_t off_delta, off_wc, off_ts, off_scan, off_misc, off_pos, off_d8, off_ob, off_vs;
+};
+template <int THREADS, int K>
+__host__ __device__ __forceinline__ ScatterSmem scatter_smem_layout(uint32_t N, uint32_t stage_width, bool onepass) {
+    constexpr uint32_t T = THREADS * K, W = THREADS / 32;
+    ScatterSmem L;
+    L.off_delta = (T * stage_width + 15u) & ~15u;
+    L.off_wc = L.off_delta + N * 8u;
+    L.off_ts = L.off_wc + W * N * 4u;
+    L.off_scan = L.off_ts + (onepass ? 2u : 1u) * (N + 1u) * 4u;
+    L.off_misc = L.off_scan + (W + 1u) * 4u;
+    L.off_pos = (L.off_misc + 4u * 4u + 3u) & ~3u;
+    L.off_d8 = L.off_pos + (onepass ? 2u * T * 2u : 0u);                  // single-pass mode: destination of every staging slot
+    L.off_ob = (L.off_d8 + (onepass ? 2u * T : 0u) + 7u) & ~7u;            // peer mode only: per-destination bases
+    L.off_vs = L.off_ob + N * 8u;                                          // aligned mode only: virtual run starts
+    return L;
+}
+
+// which staging slot (and destination) each of this thread's write-out iterations handles
+template <int THREADS, int K, int KV, int BAR = 0>
+__device__ __forceinline__ void compute_slots(uint32_t (&slot)[KV], uint32_t N, int tile_rows, const uint32_t* tile_start,
+                                              const int64_t* delta, uint32_t* vstart, uint32_t* s_scan) {
+    if constexpr (KV == K) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            uint32_t i = k * THREADS + threadIdx.x;
+            uint32_t lo = 0, hi = N;  // last p with tile_start[p] <= i
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (tile_start[mid] <= i) lo = mid; else hi = mid;
+            }
+            slot[k] = i < (uint32_t)tile_rows ? (i | (lo << 16)) : SLOT_NONE;
+        }
+    } else {
+        // virtual run of destination p: [vstart[p], vstart[p+1]) = m_p leading pad + its rows, rounded up to 32,
+        // where m_p = (first output row of the run) mod 32
+        {
+            uint32_t carry = 0;
+            for (uint32_t p0 = 0; p0 < N; p0 += THREADS) {
+                uint32_t p = p0 + threadIdx.x;
+                uint32_t len = 0;
+                if (p < N) {
+                    uint32_t ts = tile_start[p], cnt = tile_start[p + 1] - ts;
+                    uint32_t m = (uint32_t)((int64_t)ts + delta[p]) & 31u;
+                    len = cnt ? (m + cnt + 31u) & ~31u : 0u;
+                }
+                uint32_t tot;
+                uint32_t ex = block_exclusive_scan<THREADS, BAR>(len, s_scan, tot);
+                if (p < N) vstart[p] = carry + ex;
+                carry += tot;
+            }
+            if (threadIdx.x == 0) vstart[N] = carry;
+            block_sync<THREADS, BAR>();
+        }
+        const uint32_t vtotal = vstart[N];
+#pragma unroll
+        for (int k = 0; k < KV; ++k) {
+            uint32_t vs = k * THREADS + threadIdx.x;
+            slot[k] = SLOT_NONE;
+            if (vs < vtotal) {
+                uint32_t lo = 0, hi = N;  // last p with vstart[p] <= vs
+                while (hi - lo > 1) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (vstart[mid] <= vs) lo = mid; else hi = mid;
+                }
+                uint32_t ts = tile_start[lo], cnt = tile_start[lo + 1] - ts;
+                uint32_t m = (uint32_t)((int64_t)ts + delta[lo]) & 31u;
+                uint32_t off = vs - vstart[lo] - m;  // wraps for the leading pad
+                if (off < cnt) slot[k] = (ts + off) | (lo << 16);
+            }
+        }
+    }
+}
+
+// phase 2: every column of the launch through the staging buffer
+template <int THREADS, int K, int KV, typename V, bool PEER, bool ROWS = false>
+__device__ __forceinline__ void scatter_all_columns(const ScatterParams& P, unsigned char* stage, int64_t row0, int tile_rows,
+                                                    const uint32_t (&pos)[K], const uint32_t (&slot)[KV], const int64_t* delta, int t0,
+                                                    void** out_base) {
+#pragma unroll 1
+    for (int c = 0; c < P.n_cols; ++c) {
+        const PayloadCol& col = P.cols[c];
+        if constexpr (std::is_same<V, BitColumn>::value) {
+            scatter_bit_column<THREADS, K, KV>(col, stage, row0, tile_rows, pos, slot, delta, t0);
+        } else {
+            if (PEER) {
+                // (the previous column's write-out reads out_base: the barrier inside
+                //  scatter_fixed_column orders this rewrite after it only for the staging
+                //  buffer, so fence explicitly)
+                __syncthreads();
+                for (uint32_t p = threadIdx.x; p < P.N; p += THREADS)
+                    out_base[p] = (char*)P.peer_base[p / P.parts_per_rank] + (size_t)col.out;
+            }
+            scatter_fixed_column<THREADS, K, KV, V, (sizeof(V) == 16 && K % 2 == 0 ? K / 2 : K), ROWS>(col, stage, row0, tile_rows, pos, slot, delta,
+                                                                                                 t0, PEER ? out_base : nullptr);
+        }
+    }
+}
+
+// phase 1 of one tile: destination + stable rank of every row.  Returns (dest << 16 | rank in (warp, dest)) per row
+// and leaves the per-(warp, destination) counts in warp_cnt[W][N].
+template <int THREADS, int K, bool FAST_I64>
+__device__ __forceinline__ void rank_rows(const ScatterParams& P, int64_t row0, int tile_rows, int t0, uint32_t* warp_cnt, uint32_t (&pos)[K]) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t N = P.N;
+    uint32_t* wc = warp_cnt + (uint32_t)w * N;
+    for (uint32_t p = lane; p < N; p += 32) wc[p] = 0;
+    __syncwarp();
+    const int nbits = 32 - __clz(N);
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        int t = t0 + j * 32;
+        bool valid = t < tile_rows;
+        uint32_t d = valid ? mod_n(row_hash<FAST_I64>(P.keys, row0 + t, P.st), P.mod) : N;
+        unsigned peers = peers_of(d, nbits);
+        uint32_t rank = __popc(peers & ((1u << lane) - 1));
+        uint32_t base = valid ? wc[d] : 0;
+        __syncwarp();
+        if (valid && rank == 0) wc[d] = base + __popc(peers);
+        __syncwarp();
+        pos[j] = (d << 16) | (base + rank);
+    }
+}
+
+template <int THREADS, int K, int KV, int MIN_CTAS, bool FAST_I64, typename V, bool PEER>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_constant__ ScatterParams P) {
     constexpr int T = THREADS * K;
     constexpr int W = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t N = P.N;
-    // layout: stage | delta[N] | warp_cnt[W][N] | tile_start[N+1] | scan scratch | misc[2]
+    const ScatterSmem L = scatter_smem_layout<THREADS, K>(N, (uint32_t)P.stage_width, false);
     unsigned char* stage = smem;
-    const uint32_t off_delta = ((uint32_t)T * (uint32_t)P.stage_width + 15u) & ~15u;
-    const uint32_t off_wc = off_delta + N * 8u;
-    const uint32_t off_ts = off_wc + (uint32_t)W * N * 4u;
-    const uint32_t off_scan = off_ts + (N + 1u) * 4u;
-    const uint32_t off_misc = off_scan + (uint32_t)(W + 1) * 4u;          // [0] tile ticket, [1] tile overflow
-    const uint32_t off_ob = (off_misc + 2u * 4u + 7u) & ~7u;               // peer mode only: per-destination bases
-    const uint32_t off_vs = off_ob + N * 8u;                                // aligned mode only: virtual run starts
-#define OUT_BASE ((void**)(smem + off_ob))
-#define VSTART ((uint32_t*)(smem + off_vs))
-    if (!ONEPASS && P.abort_flag && *P.abort_flag) return;  // a window / region overflowed: write nothing
-#define DELTA ((int64_t*)(smem + off_delta))
-#define WARP_CNT ((uint32_t*)(smem + off_wc))
-#define TILE_START ((uint32_t*)(smem + off_ts))
-#define S_SCAN ((uint32_t*)(smem + off_scan))
-#define S_MISC ((uint32_t*)(smem + off_misc))
+    int64_t* const DELTA = (int64_t*)(smem + L.off_delta);
+    uint32_t* const WARP_CNT = (uint32_t*)(smem + L.off_wc);
+    uint32_t* const TILE_START = (uint32_t*)(smem + L.off_ts);
+    uint32_t* const S_SCAN = (uint32_t*)(smem + L.off_scan);
+    if (P.abort_flag && *P.abort_flag) return;  // a receive window / region overflowed: write nothing
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int64_t tile = blockIdx.x;
-    if constexpr (ONEPASS) {
-        if (threadIdx.x == 0) {
-            S_MISC[0] = atomicAdd(P.lb_ticket, 1u);
-            S_MISC[1] = 0;
-        }
-        __syncthreads();
-        tile = S_MISC[0];
-    }
+    const int64_t tile = blockIdx.x;
     const int64_t row0 = tile * T;
     const int tile_rows = (int)((P.n_rows - row0) < T ? (P.n_rows - row0) : T);
     const int t0 = w * (K * 32) + lane;  // this thread's first tile-relative row; rows t0 + 32*j
 
-    // ---- two-pass mode: tile_start / delta from the K1 histogram (independent of phase 1).
+    // ---- tile_start / delta from the K1 histogram (independent of phase 1).
     // delta[p] maps a staging slot i to its absolute output row: out_row = i + delta[p]
-    if constexpr (!ONEPASS) {
+    {
         uint32_t carry = 0;
         for (uint32_t p0 = 0; p0 < N; p0 += THREADS) {
             uint32_t p = p0 + threadIdx.x;
@@ -459,30 +582,282 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
     }
 
     // ---- phase 1: destination + stable rank of every row of the tile
-    uint32_t* wc = WARP_CNT + (uint32_t)w * N;
-    for (uint32_t p = lane; p < N; p += 32) wc[p] = 0;
-    __syncwarp();
-    const int nbits = 32 - __clz(N);
     uint32_t pos[K];  // first: (dest << 16 | rank) ; later: staging position
+    rank_rows<THREADS, K, FAST_I64>(P, row0, tile_rows, t0, WARP_CNT, pos);
+    __syncthreads();
+    // warp_cnt[w][p] -> staging base of (warp w, destination p)
+    for (uint32_t p = threadIdx.x; p < N; p += THREADS) {
+        uint32_t run = TILE_START[p];
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-        int t = t0 + j * 32;
-        bool valid = t < tile_rows;
-        uint32_t d = valid ? mod_n(row_hash<FAST_I64>(P.keys, row0 + t, P.st), P.mod) : N;
-        unsigned peers = peers_of(d, nbits);
-        uint32_t rank = __popc(peers & ((1u << lane) - 1));
-        uint32_t base = valid ? wc[d] : 0;
-        __syncwarp();
-        if (valid && rank == 0) wc[d] = base + __popc(peers);
-        __syncwarp();
-        pos[j] = (d << 16) | (base + rank);
+        for (int ww = 0; ww < W; ++ww) {
+            uint32_t c = WARP_CNT[(uint32_t)ww * N + p];
+            WARP_CNT[(uint32_t)ww * N + p] = run;
+            run += c;
+        }
     }
     __syncthreads();
-    if constexpr (ONEPASS) {
+    {
+        const uint32_t* wc = WARP_CNT + (uint32_t)w * N;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            uint32_t d = pos[j] >> 16;
+            pos[j] = d < N ? wc[d] + (pos[j] & 0xffffu) : 0;
+        }
+    }
+    uint32_t slot[KV];
+    compute_slots<THREADS, K, KV>(slot, N, tile_rows, TILE_START, DELTA, (uint32_t*)(smem + L.off_vs), S_SCAN);
+    scatter_all_columns<THREADS, K, KV, V, PEER>(P, stage, row0, tile_rows, pos, slot, DELTA, t0, (void**)(smem + L.off_ob));
+}
+
+// ---------------------------------------------------------------------------
+// mbarrier + TMA bulk-copy primitives (sm_90+/sm_100a): the producer warp of the single-pass kernel
+// streams contiguous column tiles global -> shared with cp.async.bulk (UBLKCP in SASS); completion is
+// signalled on an mbarrier by transaction bytes, so no register ever stages a payload load.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* b, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(b)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must fail the launch (trap -> CUDA error), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
+    if (mbar_try_wait(b, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(b, parity)) {
+        if (clock64() - t0 > (1LL << 33)) __trap();  // ~4 s at 2 GHz
+    }
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, unsigned long long* bar, unsigned long long pol,
+                                         bool hint) {
+    if (hint)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                         smem_u32(dst_smem)),
+                     "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                     : "memory");
+    else
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src),
+                     "r"(bytes), "r"(smem_u32(bar))
+                     : "memory");
+}
+
+// shared-memory layout of k_scatter_onepass
+struct OnePassSmem {
+    uint32_t off_bars, off_tix, off_delta, off_ob, off_wc, off_ts, off_scan, off_misc, off_vs, off_src, off_d8, total;
+};
+template <int THREADS, int K, int NB>
+__host__ __device__ __forceinline__ OnePassSmem onepass_smem_layout(uint32_t N, uint32_t width, bool peer, bool aligned) {
+    constexpr uint32_t T = THREADS * K, W = THREADS / 32;
+    OnePassSmem L;
+    const uint32_t slot_bytes = (T * width + 127u) & ~127u;  // ring of NB input tiles first (128-B aligned bulk-copy destinations)
+    L.off_bars = NB * slot_bytes;                             // full[NB] | empty[NB]
+    L.off_tix = L.off_bars + 2u * NB * 8u;                    // tile of the header item in each slot (int64)
+    L.off_delta = L.off_tix + NB * 8u;
+    L.off_ob = L.off_delta + N * 8u;                          // peer mode: window of every destination's owner
+    L.off_wc = L.off_ob + (peer ? N * 8u : 0u);
+    L.off_ts = L.off_wc + W * N * 4u;
+    L.off_scan = L.off_ts + 2u * (N + 1u) * 4u;
+    L.off_misc = L.off_scan + (W + 1u) * 4u;
+    L.off_vs = L.off_misc + 4u * 4u;                          // aligned mode: virtual run starts
+    L.off_src = (L.off_vs + (aligned ? (N + 1u) * 4u : 0u) + 3u) & ~3u;
+    L.off_d8 = L.off_src + 2u * T * 2u;
+    L.total = L.off_d8 + 2u * T;
+    return L;
+}
+
+// ---------------------------------------------------------------------------
+// K2', single pass: no K1/K1b; every row is hashed once and every column read once.
+//
+// Warp-specialised persistent kernel (one CTA per resident slot): THREADS consumer threads + one producer warp.
+//  * producer warp: draws tile tickets (atomic, launch order) and streams, per tile, a header item (the key
+//    tile when the key is a single non-null 8-byte column) and one item per payload column into a ring of NB
+//    shared-memory slots with TMA bulk copies; per-slot full/empty mbarriers — loads run NB-1 items ahead of
+//    their use and never occupy registers.
+//  * consumers, per tile:
+//      phase 1 (on the header item of the NEXT tile): hash -> destination -> stable rank (ballot peers +
+//        per-warp counters); the tile's per-destination counts are published as look-back aggregates and
+//        the inverse permutation (source row of every destination-ordered slot) is left in shared memory;
+//      look-back (current tile): warp w resolves destinations w, w+W, ...: exclusive prefix over the lower
+//        tiles' descriptors, 32 predecessors per step.  Because phase 1 of a tile runs a whole tile-time
+//        before its look-back, the aggregates below it are always published already;
+//      scatter: per column item, slot i of the destination order is gathered from the ring (src row) and
+//        stored to its output row — consecutive threads write consecutive rows of a destination's run.
+// Order is stable (cursor = sum over lower tiles).  Destinations live in fixed regions (dest_base /
+// region_stride); a tile that would overflow a region sets overflow_out and writes nothing — the counts stay
+// exact and the host re-runs with exact regions.
+// ---------------------------------------------------------------------------
+template <int THREADS, int K, int KV, int NB, int MIN_CTAS, bool FAST_I64, typename V, bool PEER>
+__global__ void __launch_bounds__(THREADS + 32, MIN_CTAS) k_scatter_onepass(const __grid_constant__ ScatterParams P) {
+    constexpr int T = THREADS * K;
+    constexpr int W = THREADS / 32;
+    constexpr int BAR = 1;  // named barrier of the consumer warps
+    constexpr bool ROWS = (KV == K) && !PEER;
+    static_assert(!std::is_same<V, BitColumn>::value, "bit columns take the two-pass kernel");
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t N = P.N;
+    const OnePassSmem L = onepass_smem_layout<THREADS, K, NB>(N, (uint32_t)sizeof(V), PEER, KV != K);
+    const uint32_t slot_bytes = ((uint32_t)T * (uint32_t)sizeof(V) + 127u) & ~127u;
+    unsigned long long* const FULL = (unsigned long long*)(smem + L.off_bars);
+    unsigned long long* const EMPTY = FULL + NB;
+    long long* const TIX = (long long*)(smem + L.off_tix);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NB; ++i) {
+            mbar_init(FULL + i, 1);   // the producer's arrive (+ the bulk copy's transaction bytes)
+            mbar_init(EMPTY + i, W);  // one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (w == W) {
+        // =========================== producer warp ===========================
+        const unsigned long long pol = l2_policy_evict_first();
+        uint32_t seq = 0;
+        auto acquire_slot = [&]() -> int {
+            const int slot = (int)(seq % NB);
+            if (lane == 0) mbar_wait(EMPTY + slot, ((seq / NB) & 1u) ^ 1u);
+            __syncwarp();
+            return slot;
+        };
+        // rows [row0, row0 + rows) of a column of `width`-byte values -> ring slot
+        auto fill = [&](int slot, const void* base, int64_t first_row, int rows, uint32_t width, bool stream) {
+            const char* src = (const char*)base + first_row * (int64_t)width;
+            const uint32_t bytes = (uint32_t)rows * width;
+            unsigned char* dst = smem + (uint32_t)slot * slot_bytes;
+            if ((((uintptr_t)src | (uintptr_t)bytes) & 15u) == 0) {
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(FULL + slot, bytes);
+                    bulk_g2s(dst, src, bytes, FULL + slot, pol, stream);
+                }
+            } else {  // unaligned Arrow offset / ragged last tile: element-wise copy by the producer lanes
+                if (width == 8) for (int e = lane; e < rows; e += 32) ((uint64_t*)dst)[e] = ((const uint64_t*)src)[e];
+                else if (width == 4) for (int e = lane; e < rows; e += 32) ((uint32_t*)dst)[e] = ((const uint32_t*)src)[e];
+                else if (width == 16) for (int e = lane; e < 2 * rows; e += 32) ((uint64_t*)dst)[e] = ((const uint64_t*)src)[e];
+                else for (uint32_t e = lane; e < bytes; e += 32) dst[e] = ((const unsigned char*)src)[e];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(FULL + slot);
+            }
+            ++seq;
+        };
+        auto draw = [&]() -> int64_t {
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(P.lb_ticket, 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            return (int64_t)t < P.n_tiles ? (int64_t)t : -1;
+        };
+        auto emit_header = [&](int64_t tile) {
+            const int slot = acquire_slot();
+            if (lane == 0) TIX[slot] = tile;
+            if (FAST_I64 && tile >= 0) {
+                const int64_t row0 = tile * T;
+                const int rows = (int)((P.n_rows - row0) < T ? (P.n_rows - row0) : T);
+                fill(slot, P.keys.col[0].values, row0, rows, 8, false);  // key tile: default L2 policy (re-read as a payload column)
+            } else {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(FULL + slot);
+                ++seq;
+            }
+        };
+        int64_t cur = draw();
+        emit_header(cur);
+        while (cur >= 0) {
+            const int64_t nxt = draw();
+            emit_header(nxt);
+            const int64_t row0 = cur * T;
+            const int rows = (int)((P.n_rows - row0) < T ? (P.n_rows - row0) : T);
+            for (int c = 0; c < P.n_cols; ++c) {
+                const int slot = acquire_slot();
+                fill(slot, P.cols[c].in, P.cols[c].in_offset + row0, rows, (uint32_t)sizeof(V), true);
+            }
+            cur = nxt;
+        }
+        return;
+    }
+
+    // ============================== consumer warps ==============================
+    int64_t* const DELTA = (int64_t*)(smem + L.off_delta);
+    void** const OUT_BASE = (void**)(smem + L.off_ob);
+    uint32_t* const WARP_CNT = (uint32_t*)(smem + L.off_wc);
+    uint32_t* const S_SCAN = (uint32_t*)(smem + L.off_scan);
+    uint32_t* const S_MISC = (uint32_t*)(smem + L.off_misc);  // [0] tile overflow
+    const int t0 = w * (K * 32) + lane;  // this thread's first tile-relative row; rows t0 + 32*j
+    if (PEER)
+        for (uint32_t p = threadIdx.x; p < N; p += THREADS) OUT_BASE[p] = P.peer_base[p / P.parts_per_rank];
+    uint32_t cseq = 0;
+    auto wait_item = [&]() -> int {
+        const int slot = (int)(cseq % NB);
+        mbar_wait(FULL + slot, (cseq / NB) & 1u);
+        return slot;
+    };
+    auto release_item = [&](int slot) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(EMPTY + slot);
+        ++cseq;
+    };
+
+    // phase 1 of the tile announced by the next header item, into buffer `buf`; returns the tile (or -1: end of stream)
+    auto rank_tile = [&](int buf) -> int64_t {
+        const int slot = wait_item();
+        const int64_t tile = TIX[slot];
+        if (tile < 0) {
+            release_item(slot);
+            return -1;
+        }
+        const int64_t row0 = tile * T;
+        const int tile_rows = (int)((P.n_rows - row0) < T ? (P.n_rows - row0) : T);
+        uint32_t* const TS = (uint32_t*)(smem + L.off_ts) + (uint32_t)buf * (N + 1u);
+        uint16_t* const SRC16 = (uint16_t*)(smem + L.off_src) + (uint32_t)buf * T;
+        uint8_t* const DEST8 = smem + L.off_d8 + (uint32_t)buf * T;
+        uint32_t* wc = WARP_CNT + (uint32_t)w * N;
+        for (uint32_t p = lane; p < N; p += 32) wc[p] = 0;
+        __syncwarp();
+        const int nbits = 32 - __clz(N);
+        const uint64_t* keys = (const uint64_t*)(smem + (uint32_t)slot * slot_bytes);
+        uint32_t pos[K];  // (dest << 16 | rank within (warp, dest))
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int t = t0 + j * 32;
+            const bool valid = t < tile_rows;
+            uint32_t d = N;
+            if (valid) {
+                const uint64_t h = FAST_I64 ? hash_one_u64(P.st, keys[t]) : row_hash<false>(P.keys, row0 + t, P.st);
+                d = mod_n(h, P.mod);
+            }
+            const unsigned peers = peers_of(d, nbits);
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+            const uint32_t base = valid ? wc[d] : 0;
+            __syncwarp();
+            if (valid && rank == 0) wc[d] = base + __popc(peers);
+            __syncwarp();
+            pos[j] = (d << 16) | (base + rank);
+        }
+        release_item(slot);  // key tile consumed
+        block_sync<THREADS, BAR>();
         // tile counts = sum of the warps' counts; publish them, then turn warp_cnt into staging bases
         uint32_t carry = 0;
         for (uint32_t p0 = 0; p0 < N; p0 += THREADS) {
-            uint32_t p = p0 + threadIdx.x;
+            const uint32_t p = p0 + threadIdx.x;
             uint32_t c = 0;
             if (p < N) {
 #pragma unroll
@@ -491,42 +866,45 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
                 lb_store(P.lb_desc + (int64_t)p * P.n_tiles + tile, lb_pack(P.lb_epoch, tile == 0 ? LB_PREFIX : LB_AGG, c));
             }
             uint32_t tot;
-            uint32_t ex = block_exclusive_scan<THREADS>(c, S_SCAN, tot);
+            const uint32_t ex = block_exclusive_scan<THREADS, BAR>(c, S_SCAN, tot);
             if (p < N) {
                 uint32_t run = carry + ex;
-                TILE_START[p] = run;
+                TS[p] = run;
 #pragma unroll
                 for (int ww = 0; ww < W; ++ww) {
-                    uint32_t cc = WARP_CNT[(uint32_t)ww * N + p];
+                    const uint32_t cc = WARP_CNT[(uint32_t)ww * N + p];
                     WARP_CNT[(uint32_t)ww * N + p] = run;
                     run += cc;
                 }
             }
             carry += tot;
         }
-        if (threadIdx.x == 0) TILE_START[N] = carry;
-    } else {
-        // warp_cnt[w][p] -> staging base of (warp w, destination p)
-        for (uint32_t p = threadIdx.x; p < N; p += THREADS) {
-            uint32_t run = TILE_START[p];
+        if (threadIdx.x == 0) TS[N] = carry;
+        block_sync<THREADS, BAR>();
 #pragma unroll
-            for (int ww = 0; ww < W; ++ww) {
-                uint32_t c = WARP_CNT[(uint32_t)ww * N + p];
-                WARP_CNT[(uint32_t)ww * N + p] = run;
-                run += c;
+        for (int j = 0; j < K; ++j) {
+            const uint32_t d = pos[j] >> 16;
+            if (d < N) {
+                const uint32_t sp = wc[d] + (pos[j] & 0xffffu);  // slot of this row in destination order
+                SRC16[sp] = (uint16_t)(t0 + j * 32);
+                DEST8[sp] = (uint8_t)d;  // N <= 256 in single-pass mode
             }
         }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-        uint32_t d = pos[j] >> 16;
-        pos[j] = d < N ? wc[d] + (pos[j] & 0xffffu) : 0;
-    }
-    if constexpr (ONEPASS) {
+        return tile;
+    };
+
+    int buf = 0;
+    int64_t tile = rank_tile(0);
+    while (tile >= 0) {
+        const int64_t next = rank_tile(buf ^ 1);
+        const uint32_t* const TS = (const uint32_t*)(smem + L.off_ts) + (uint32_t)buf * (N + 1u);
+        const int64_t row0 = tile * T;
+        const int tile_rows = (int)((P.n_rows - row0) < T ? (P.n_rows - row0) : T);
+        if (threadIdx.x == 0) S_MISC[0] = 0;
+        block_sync<THREADS, BAR>();  // (also: SRC16 / DEST8 of this tile are visible, DELTA is free)
         // ---- decoupled look-back: exclusive prefix of every destination over the lower tiles
         for (uint32_t p = (uint32_t)w; p < N; p += W) {
-            const uint32_t cnt = TILE_START[p + 1] - TILE_START[p];
+            const uint32_t cnt = TS[p + 1] - TS[p];
             uint32_t excl = 0;
             if (tile > 0) {
                 const unsigned long long* d = P.lb_desc + (int64_t)p * P.n_tiles;
@@ -554,8 +932,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
             }
             if (lane == 0) {
                 const int64_t cap = P.dest_cap ? P.dest_cap[p] : P.region_stride;
-                if ((int64_t)excl + (int64_t)cnt > cap) S_MISC[1] = 1;
-                DELTA[p] = region_base_of<PEER>(P, p) + (int64_t)excl - (int64_t)TILE_START[p];
+                if ((int64_t)excl + (int64_t)cnt > cap) S_MISC[0] = 1;
+                DELTA[p] = region_base_of<PEER>(P, p) + (int64_t)excl - (int64_t)TS[p];
                 if (P.hist_out) {
                     P.hist_out[(int64_t)p * P.n_tiles + tile] = cnt;
                     P.base_out[(int64_t)p * P.n_tiles + tile] = excl;
@@ -563,96 +941,58 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_cons
                 if (tile == P.n_tiles - 1) P.totals_out[p] = (int64_t)excl + (int64_t)cnt;
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (S_MISC[1]) *P.overflow_out = 1;
-            // every CTA has its ticket once `n_tiles` CTAs are past this point: the last one re-arms the counters
-            if (atomicAdd(P.lb_ticket + 1, 1u) == (unsigned)(P.n_tiles - 1)) {
-                P.lb_ticket[0] = 0;
-                P.lb_ticket[1] = 0;
-            }
-        }
-        if (S_MISC[1]) return;  // a region is too small: this tile writes nothing
-    }
-    // ---- which staging slot (and destination) each of this thread's write-out iterations handles
-    uint32_t slot[KV];
-    if constexpr (KV == K) {
+        block_sync<THREADS, BAR>();
+        const bool overflow = S_MISC[0] != 0;
+        if (overflow && threadIdx.x == 0) *P.overflow_out = 1;  // a region is too small: this tile writes nothing
+        const uint16_t* const SRC16 = (const uint16_t*)(smem + L.off_src) + (uint32_t)buf * T;
+        const uint8_t* const DEST8 = smem + L.off_d8 + (uint32_t)buf * T;
+        if constexpr (ROWS) {
+            // absolute output row (< 2^32: host-checked) and source row of every slot this thread writes
+            uint32_t orow[K], src[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            uint32_t i = k * THREADS + threadIdx.x;
-            uint32_t lo = 0, hi = N;  // last p with tile_start[p] <= i
-            while (hi - lo > 1) {
-                uint32_t mid = (lo + hi) >> 1;
-                if (TILE_START[mid] <= i) lo = mid; else hi = mid;
+            for (int k = 0; k < K; ++k) {
+                const uint32_t i = k * THREADS + threadIdx.x;
+                const bool on = i < (uint32_t)tile_rows && !overflow;
+                orow[k] = on ? i + (uint32_t)DELTA[DEST8[i]] : SLOT_NONE;
+                src[k] = on ? SRC16[i] : 0;
             }
-            slot[k] = i < (uint32_t)tile_rows ? (i | (lo << 16)) : SLOT_NONE;
-        }
-    } else {
-        // virtual run of destination p: [VSTART[p], VSTART[p+1]) = m_p leading pad + its rows, rounded up to 32,
-        // where m_p = (first output row of the run) mod 32
-        {
-            uint32_t carry = 0;
-            for (uint32_t p0 = 0; p0 < N; p0 += THREADS) {
-                uint32_t p = p0 + threadIdx.x;
-                uint32_t len = 0;
-                if (p < N) {
-                    uint32_t ts = TILE_START[p], cnt = TILE_START[p + 1] - ts;
-                    uint32_t m = (uint32_t)((int64_t)ts + DELTA[p]) & 31u;
-                    len = cnt ? (m + cnt + 31u) & ~31u : 0u;
-                }
-                uint32_t tot;
-                uint32_t ex = block_exclusive_scan<THREADS>(len, S_SCAN, tot);
-                if (p < N) VSTART[p] = carry + ex;
-                carry += tot;
-            }
-            if (threadIdx.x == 0) VSTART[N] = carry;
-            __syncthreads();
-        }
-        const uint32_t vtotal = VSTART[N];
-#pragma unroll
-        for (int k = 0; k < KV; ++k) {
-            uint32_t vs = k * THREADS + threadIdx.x;
-            slot[k] = SLOT_NONE;
-            if (vs < vtotal) {
-                uint32_t lo = 0, hi = N;  // last p with VSTART[p] <= vs
-                while (hi - lo > 1) {
-                    uint32_t mid = (lo + hi) >> 1;
-                    if (VSTART[mid] <= vs) lo = mid; else hi = mid;
-                }
-                uint32_t ts = TILE_START[lo], cnt = TILE_START[lo + 1] - ts;
-                uint32_t m = (uint32_t)((int64_t)ts + DELTA[lo]) & 31u;
-                uint32_t off = vs - VSTART[lo] - m;  // wraps for the leading pad
-                if (off < cnt) slot[k] = (ts + off) | (lo << 16);
-            }
-        }
-    }
-
-    // ---- phase 2: every column through the staging buffer
 #pragma unroll 1
-    for (int c = 0; c < P.n_cols; ++c) {
-        const PayloadCol& col = P.cols[c];
-        if constexpr (std::is_same<V, BitColumn>::value) {
-            scatter_bit_column<THREADS, K, KV>(col, stage, row0, tile_rows, pos, slot, DELTA, t0);
-        } else {
-            if (PEER) {
-                // (the previous column's write-out reads OUT_BASE: the barrier inside
-                //  scatter_fixed_column orders this rewrite after it only for the staging
-                //  buffer, so fence explicitly)
-                __syncthreads();
-                for (uint32_t p = threadIdx.x; p < N; p += THREADS)
-                    OUT_BASE[p] = (char*)P.peer_base[p / P.parts_per_rank] + (size_t)col.out;
+            for (int c = 0; c < P.n_cols; ++c) {
+                const int slot = wait_item();
+                const V* in = (const V*)(smem + (uint32_t)slot * slot_bytes);
+                V* out = (V*)P.cols[c].out;
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (orow[k] != SLOT_NONE) st_stream(out + orow[k], in[src[k]]);
+                release_item(slot);
             }
-            scatter_fixed_column<THREADS, K, KV, V, (sizeof(V) == 16 && K % 2 == 0 ? K / 2 : K)>(col, stage, row0, tile_rows, pos, slot, DELTA, t0,
-                                                                                           PEER ? OUT_BASE : nullptr);
+        } else {
+            uint32_t slot_of[KV];
+            compute_slots<THREADS, K, KV, BAR>(slot_of, N, tile_rows, TS, DELTA, (uint32_t*)(smem + L.off_vs), S_SCAN);
+#pragma unroll 1
+            for (int c = 0; c < P.n_cols; ++c) {
+                const int slot = wait_item();
+                const V* in = (const V*)(smem + (uint32_t)slot * slot_bytes);
+                const size_t col_out = (size_t)P.cols[c].out;  // local: pointer; peer: byte offset into every window
+#pragma unroll
+                for (int k = 0; k < KV; ++k) {
+                    if (slot_of[k] != SLOT_NONE && !overflow) {
+                        const uint32_t i = slot_of[k] & 0xffffu, p = slot_of[k] >> 16;
+                        V* o = PEER ? (V*)((char*)OUT_BASE[p] + col_out) : (V*)col_out;  // peer: the owner's window (NVLink store)
+                        st_stream(o + ((int64_t)i + DELTA[p]), in[SRC16[i]]);
+                    }
+                }
+                release_item(slot);
+            }
         }
+        tile = next;
+        buf ^= 1;
     }
-#undef OUT_BASE
-#undef VSTART
-#undef DELTA
-#undef WARP_CNT
-#undef TILE_START
-#undef S_SCAN
-#undef S_MISC
+    // every CTA draws exactly one ticket >= n_tiles; the last CTA out re-arms the counters for the next launch
+    if (threadIdx.x == 0 && atomicAdd(P.lb_ticket + 1, 1u) == gridDim.x - 1) {
+        P.lb_ticket[0] = 0;
+        P.lb_ticket[1] = 0;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -753,8 +1093,7 @@ __global__ void __launch_bounds__(256) k_var_copy_bytes(const OFF* __restrict__ 
     }
 }
 
-// must mirror the offsets computed at the top of k_scatter (the peer / aligned tables are last,
-// so launches that do not use them simply do not allocate them)
+// (the peer / aligned tables are last in scatter_smem_layout, so launches that do not use them do not allocate them)
 // ---------------------------------------------------------------------------
 // Exchange helpers for bit-packed and variable-width columns (NCCL mode): bitmaps travel as one
 // byte per row, strings as (lengths, bytes); the receiver rebuilds bitmaps and offsets.
@@ -831,17 +1170,17 @@ __global__ void __launch_bounds__(VAR_BLOCK) k_len_write_offsets(const OFF* __re
 }
 
 template <int THREADS, int K>
-inline size_t scatter_smem_bytes(uint32_t N, int stage_width, bool peer, bool aligned) {
-    size_t off = ((size_t)THREADS * K * stage_width + 15) & ~(size_t)15;
-    off += (size_t)N * 8;
-    off += (size_t)(THREADS / 32) * N * 4;
-    off += (size_t)(N + 1) * 4;
-    off += (size_t)(THREADS / 32 + 1) * 4;
-    off += 2 * 4;  // misc: tile ticket, tile overflow (single-pass mode)
-    off = (off + 7) & ~(size_t)7;
+inline size_t scatter_smem_bytes(uint32_t N, int stage_width, bool peer, bool aligned, bool onepass = false) {
+    const ScatterSmem L = scatter_smem_layout<THREADS, K>(N, (uint32_t)stage_width, onepass);
+    size_t off = L.off_ob;
     if (peer || aligned) off += (size_t)N * 8;  // per-destination output bases (peer mode)
     if (aligned) off += (size_t)(N + 1) * 4;    // virtual run starts (aligned mode)
     return off;
+}
+
+template <int THREADS, int K, int NB>
+inline size_t onepass_smem_bytes(uint32_t N, int width, bool peer, bool aligned) {
+    return onepass_smem_layout<THREADS, K, NB>(N, (uint32_t)width, peer, aligned).total;
 }
 
 }  // namespace dfd
