@@ -10,7 +10,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libdfd_b200.so")
+# DFD_LIB_TAG selects a tuning-sweep build (_lib/libdfd_b200_<tag>.so, see build.py); default = the product library
+_TAG = os.environ.get("DFD_LIB_TAG", "")
+LIB_PATH = os.path.join(_HERE, "_lib", f"libdfd_b200{('_' + _TAG) if _TAG else ''}.so")
 
 DFD_OK = 0
 STATUS = {

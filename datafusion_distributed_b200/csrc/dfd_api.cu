@@ -17,6 +17,7 @@
 #include "dfd_b200.h"
 #include "dfd_internal.h"
 #include "dfd_kernels.cuh"
+#include "dfd_launch.cuh"
 
 namespace dfd {
 
@@ -36,33 +37,6 @@ int cuda_error(cudaError_t e, const char* what) {
     int code = (e == cudaErrorMemoryAllocation) ? DFD_ERR_OOM : DFD_ERR_CUDA;
     return set_error(code, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
 }
-
-// Tile geometry of K1/K2 (rows per CTA = THREADS * K).
-#ifndef DFD_TILE_THREADS
-#define DFD_TILE_THREADS 256
-#endif
-#ifndef DFD_TILE_K
-#define DFD_TILE_K 6
-#endif
-#ifndef DFD_TILE_MIN_CTAS
-#define DFD_TILE_MIN_CTAS 6
-#endif
-// single-pass kernel: ring depth (tiles in flight per CTA) and resident CTAs per SM
-#ifndef DFD_ONEPASS_NB
-#define DFD_ONEPASS_NB 3
-#endif
-#ifndef DFD_ONEPASS_MIN_CTAS
-#define DFD_ONEPASS_MIN_CTAS 4
-#endif
-constexpr int ONEPASS_NB = DFD_ONEPASS_NB;
-constexpr int ONEPASS_MIN_CTAS = DFD_ONEPASS_MIN_CTAS;
-constexpr int TILE_THREADS = DFD_TILE_THREADS;
-constexpr int TILE_K = DFD_TILE_K;
-constexpr int TILE_MIN_CTAS = DFD_TILE_MIN_CTAS;
-// aligned write-out (see k_scatter): used when N <= ALIGNED_MAX_N; each run wastes < 62 virtual slots
-constexpr uint32_t ALIGNED_MAX_N = 16;
-constexpr int TILE_KV = TILE_K + (62 * (int)ALIGNED_MAX_N + TILE_THREADS - 1) / TILE_THREADS;
-constexpr int TILE_ROWS = TILE_THREADS * TILE_K;
 
 int Scratch::ensure(size_t need, int device) {
     if (need <= bytes) return DFD_OK;
@@ -146,83 +120,18 @@ static int build_keyset(const dfd_partitioner* p, const dfd_column* cols, int n_
 // Measured on B200 (profiles/): aligned write-out costs ~5% on local HBM stores (more write-out
 // iterations, L2 already merges partial lines) but gains ~15% on NVLink peer stores (full-size
 // write packets), so it is on for the fused exchange only.  DFD_ALIGNED_WRITEOUT=0/1 forces it.
-static bool use_aligned(uint32_t N, bool peer) {
+bool dfd::use_aligned(uint32_t N, bool peer) {
     static const int forced = [] { const char* e = getenv("DFD_ALIGNED_WRITEOUT"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
     if (N > ALIGNED_MAX_N) return false;
     return forced >= 0 ? forced == 1 : peer;
 }
 
-// grid < 0: two-pass k_scatter (one CTA per tile).  ONEPASS: persistent k_scatter_onepass, one CTA per resident slot.
-template <bool FAST, typename V, bool PEER, int KV, bool ONEPASS>
-static int launch_scatter_kv(const ScatterParams& sp, int sm_count, size_t smem, cudaStream_t stream) {
-    cudaError_t e;
-    if constexpr (ONEPASS) {
-        if constexpr (std::is_same<V, BitColumn>::value) {
-            return set_error(DFD_ERR_INTERNAL, "bit-packed columns take the two-pass k_scatter");
-        } else {
-            auto kern = k_scatter_onepass<TILE_THREADS, TILE_K, KV, ONEPASS_NB, ONEPASS_MIN_CTAS, FAST, V, PEER>;
-            smem = onepass_smem_bytes<TILE_THREADS, TILE_K, ONEPASS_NB>(sp.N, (int)sizeof(V), PEER, KV != TILE_K);
-            if (smem > 227 * 1024) return set_error(DFD_ERR_UNSUPPORTED, "single-pass kernel needs %zu B of shared memory per CTA", smem);
-            // (static per instantiation: the attribute and the occupancy are properties of the kernel + smem size)
-            static thread_local size_t cfg_smem = 0;
-            static thread_local int cfg_per_sm = 0;
-            if (cfg_smem != smem) {
-                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
-                    return cuda_error(e, "cudaFuncSetAttribute(k_scatter_onepass)");
-                if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_per_sm, kern, TILE_THREADS + 32, smem)) != cudaSuccess)
-                    return cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-                if (cfg_per_sm < 1) cfg_per_sm = 1;
-                cfg_smem = smem;
-            }
-            int64_t grid = (int64_t)cfg_per_sm * sm_count;
-            if (grid > sp.n_tiles) grid = sp.n_tiles;
-            kern<<<(unsigned)grid, TILE_THREADS + 32, smem, stream>>>(sp);
-        }
-    } else {
-        auto kern = k_scatter<TILE_THREADS, TILE_K, KV, TILE_MIN_CTAS, FAST, V, PEER>;
-        if (smem > 48 * 1024) {
-            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
-                return cuda_error(e, "cudaFuncSetAttribute(k_scatter)");
-        }
-        kern<<<(unsigned)sp.n_tiles, TILE_THREADS, smem, stream>>>(sp);
-    }
-    e = cudaGetLastError();
-    return e == cudaSuccess ? DFD_OK : cuda_error(e, "k_scatter");
-}
-
-template <bool FAST, typename V, bool PEER, bool ONEPASS>
-static int launch_scatter_t(const ScatterParams& sp, int sm_count, size_t smem, cudaStream_t stream) {
-    if (use_aligned(sp.N, PEER)) return launch_scatter_kv<FAST, V, PEER, TILE_KV, ONEPASS>(sp, sm_count, smem, stream);
-    return launch_scatter_kv<FAST, V, PEER, TILE_K, ONEPASS>(sp, sm_count, smem, stream);
-}
-
-template <bool FAST, bool PEER, bool ONEPASS>
-static int launch_scatter_w(const ScatterParams& sp, int width, int sm_count, size_t smem, cudaStream_t stream) {
-    switch (width) {
-        case 8: return launch_scatter_t<FAST, uint64_t, PEER, ONEPASS>(sp, sm_count, smem, stream);
-        case 4: return launch_scatter_t<FAST, uint32_t, PEER, ONEPASS>(sp, sm_count, smem, stream);
-        case 2: return launch_scatter_t<FAST, uint16_t, PEER, ONEPASS>(sp, sm_count, smem, stream);
-        case 1: return launch_scatter_t<FAST, uint8_t, PEER, ONEPASS>(sp, sm_count, smem, stream);
-        case 16: return launch_scatter_t<FAST, uint4, PEER, ONEPASS>(sp, sm_count, smem, stream);
-        default:
-            if constexpr (PEER || ONEPASS) {
-                return set_error(DFD_ERR_INTERNAL, "bit-packed columns take the two-pass local k_scatter instantiation");
-            } else {
-                return launch_scatter_t<FAST, BitColumn, false, false>(sp, sm_count, smem, stream);
-            }
-    }
-}
-
 static int launch_scatter(const ScatterParams& sp, int width, bool fast, bool peer, bool onepass, int sm_count, size_t smem,
                           cudaStream_t stream) {
-#define DFD_LS(F, PE, OP) return launch_scatter_w<F, PE, OP>(sp, width, sm_count, smem, stream)
-    if (onepass) {
-        if (peer) { if (fast) DFD_LS(true, true, true); else DFD_LS(false, true, true); }
-        if (fast) DFD_LS(true, false, true); else DFD_LS(false, false, true);
-    }
-    if (peer) { if (fast) DFD_LS(true, true, false); else DFD_LS(false, true, false); }
-    if (fast) DFD_LS(true, false, false); else DFD_LS(false, false, false);
-#undef DFD_LS
+    if (onepass) return peer ? launch_scatter_onepass_peer(sp, width, fast, sm_count, smem, stream)
+                             : launch_scatter_onepass_local(sp, width, fast, sm_count, smem, stream);
+    return peer ? launch_scatter_twopass_peer(sp, width, fast, sm_count, smem, stream)
+                : launch_scatter_twopass_local(sp, width, fast, sm_count, smem, stream);
 }
 
 // ---- PartitionJob: validation -> K1/K1b -> K2, reusable by the local path and the exchange ----

@@ -92,7 +92,7 @@ __device__ __forceinline__ unsigned peers_of(uint32_t d, int nbits) {
 // ---------------------------------------------------------------------------
 // K0 (debug / parity): destination id per row
 // ---------------------------------------------------------------------------
-__global__ void k_partition_ids(KeySet keys, HashState st, ModN mod, int64_t n_rows, uint32_t* __restrict__ dest) {
+static __global__ void k_partition_ids(KeySet keys, HashState st, ModN mod, int64_t n_rows, uint32_t* __restrict__ dest) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x)
         dest[r] = mod_n(row_hash<false>(keys, r, st), mod);
 }
@@ -546,7 +546,7 @@ template <int THREADS, int K, int KV, int MIN_CTAS, bool FAST_I64, typename V, b
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_scatter(const __grid_constant__ ScatterParams P) {
     constexpr int T = THREADS * K;
     constexpr int W = THREADS / 32;
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t N = P.N;
     const ScatterSmem L = scatter_smem_layout<THREADS, K>(N, (uint32_t)P.stage_width, false);
     unsigned char* stage = smem;
@@ -1004,7 +1004,7 @@ __global__ void __launch_bounds__(THREADS + 32, MIN_CTAS) k_scatter_onepass(cons
 constexpr int VAR_BLOCK = 256;
 constexpr int VAR_ITEMS = 8;  // rows per thread in the scan kernels (block = 2048 rows)
 
-__global__ void k_iota_u32(uint32_t* __restrict__ out, int64_t n) {
+static __global__ void k_iota_u32(uint32_t* __restrict__ out, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (uint32_t)i;
 }
 
@@ -1037,7 +1037,7 @@ __global__ void __launch_bounds__(VAR_BLOCK) k_var_block_sums(const OFF* __restr
 }
 
 // phase b: exclusive scan of the block sums in place (single CTA), total -> block_sums[n_blocks]
-__global__ void __launch_bounds__(1024) k_var_scan_block_sums(unsigned long long* __restrict__ block_sums, int64_t n_blocks) {
+static __global__ void __launch_bounds__(1024) k_var_scan_block_sums(unsigned long long* __restrict__ block_sums, int64_t n_blocks) {
     __shared__ unsigned long long s_warp[33];
     unsigned long long carry = 0;
     for (int64_t b0 = 0; b0 < n_blocks; b0 += 1024) {
@@ -1098,13 +1098,13 @@ __global__ void __launch_bounds__(256) k_var_copy_bytes(const OFF* __restrict__ 
 // Exchange helpers for bit-packed and variable-width columns (NCCL mode): bitmaps travel as one
 // byte per row, strings as (lengths, bytes); the receiver rebuilds bitmaps and offsets.
 // ---------------------------------------------------------------------------
-__global__ void k_bits_to_bytes(const uint8_t* __restrict__ bits, int64_t bit_offset, int64_t n, uint8_t* __restrict__ out) {
+static __global__ void k_bits_to_bytes(const uint8_t* __restrict__ bits, int64_t bit_offset, int64_t n, uint8_t* __restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = bit_is_set(bits, i + bit_offset) ? 1 : 0;
 }
 
 // out bitmap words are fully written (n rounded up to 32 rows per warp): no pre-zeroing, no atomics
-__global__ void k_bytes_to_bits(const uint8_t* __restrict__ in, int64_t n, unsigned* __restrict__ out_words) {
+static __global__ void k_bytes_to_bits(const uint8_t* __restrict__ in, int64_t n, unsigned* __restrict__ out_words) {
     const int64_t n32 = (n + 31) & ~(int64_t)31;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += (int64_t)gridDim.x * blockDim.x) {
         unsigned b = __ballot_sync(0xffffffffu, i < n && in[i] != 0);

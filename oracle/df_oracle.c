@@ -411,3 +411,216 @@ int orc_repartition_table(const void* const* cols, const int32_t* widths, int n_
     free(args); free(th);
     return rc;
 }
+
+
+/* ------------------------------------------------------------------------- */
+/* Streaming operator restatement on a PERSISTENT thread pool (timed CPU arm). */
+/*                                                                             */
+/* Same per-batch work as orc_repartition_table — create_hashes -> per-        */
+/* destination index vectors -> take_arrays per (destination, column) ->       */
+/* LimitedBatchCoalescer (target batch_size) — but the way a long-running      */
+/* worker does it (reference worker: tokio multi-thread runtime + mimalloc,    */
+/* benchmarks/cdk/bin/worker.rs:32): threads are created once, every thread    */
+/* keeps its hash/index/take buffers and its per-destination coalescer batch,  */
+/* and a completed output batch is handed to a consumer that drops it, so its  */
+/* memory is reused (no fresh pages per step).                                 */
+/* ------------------------------------------------------------------------- */
+
+typedef struct {
+    uint64_t* hash_buffer;
+    uint32_t* indices;
+    int64_t *counts, *starts;
+    uint8_t** taken;      /* [n_cols] batch_size * width */
+    uint8_t*** coal;      /* [N][n_cols] in-progress coalescer batch */
+    int64_t* coal_rows;   /* [N] */
+    int64_t* sent_rows;   /* [N] rows emitted to each destination by this thread */
+    int64_t batches_out;  /* completed output batches */
+    uint64_t checksum;    /* xor of the first column's last value of every emitted batch (keeps the copies observable) */
+    /* shape the buffers were allocated for */
+    int n_cols; uint32_t N; int64_t batch_size; int64_t row_bytes;
+} pool_thread_state;
+
+struct orc_pool {
+    int n_threads;
+    pthread_t* th;
+    pool_thread_state* ts;
+    pthread_mutex_t mu;
+    pthread_cond_t cv_job, cv_done;
+    uint64_t generation;
+    int remaining;
+    int shutdown;
+    /* current job */
+    const void* const* cols; const int32_t* widths; int n_cols; int64_t n_rows;
+    const int32_t* key_cols; int n_keys; uint32_t N; int64_t batch_size; int active_threads;
+    int rc;
+};
+
+typedef struct { struct orc_pool* pool; int tid; } pool_arg;
+
+static void pts_free(pool_thread_state* t) {
+    free(t->hash_buffer); free(t->indices); free(t->counts); free(t->starts);
+    if (t->taken) { for (int c = 0; c < t->n_cols; ++c) free(t->taken[c]); free(t->taken); }
+    if (t->coal) {
+        for (uint32_t p = 0; p < t->N; ++p) { for (int c = 0; c < t->n_cols; ++c) free(t->coal[p][c]); free(t->coal[p]); }
+        free(t->coal);
+    }
+    free(t->coal_rows); free(t->sent_rows);
+    memset(t, 0, sizeof *t);
+}
+
+static int pts_ensure(pool_thread_state* t, const int32_t* widths, int n_cols, uint32_t N, int64_t B) {
+    int64_t rb = 0;
+    for (int c = 0; c < n_cols; ++c) rb = rb * 31 + widths[c];
+    if (t->hash_buffer && t->n_cols == n_cols && t->N == N && t->batch_size == B && t->row_bytes == rb) return 0;
+    pts_free(t);
+    t->n_cols = n_cols; t->N = N; t->batch_size = B; t->row_bytes = rb;
+    t->hash_buffer = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)B);
+    t->indices = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)B);
+    t->counts = (int64_t*)malloc(sizeof(int64_t) * N);
+    t->starts = (int64_t*)malloc(sizeof(int64_t) * (N + 1));
+    t->taken = (uint8_t**)calloc((size_t)n_cols, sizeof(uint8_t*));
+    t->coal = (uint8_t***)calloc(N, sizeof(uint8_t**));
+    t->coal_rows = (int64_t*)calloc(N, sizeof(int64_t));
+    t->sent_rows = (int64_t*)calloc(N, sizeof(int64_t));
+    if (!t->hash_buffer || !t->indices || !t->counts || !t->starts || !t->taken || !t->coal || !t->coal_rows || !t->sent_rows) return -1;
+    for (int c = 0; c < n_cols; ++c)
+        if (!(t->taken[c] = (uint8_t*)malloc((size_t)B * (size_t)widths[c]))) return -1;
+    for (uint32_t p = 0; p < N; ++p) {
+        if (!(t->coal[p] = (uint8_t**)calloc((size_t)n_cols, sizeof(uint8_t*)))) return -1;
+        for (int c = 0; c < n_cols; ++c)
+            if (!(t->coal[p][c] = (uint8_t*)malloc((size_t)B * (size_t)widths[c]))) return -1;
+    }
+    return 0;
+}
+
+static void pool_run_job(struct orc_pool* P, int tid) {
+    pool_thread_state* t = &P->ts[tid];
+    if (tid >= P->active_threads) return;
+    if (pts_ensure(t, P->widths, P->n_cols, P->N, P->batch_size)) { P->rc = -1; return; }
+    const orc_random_state st = orc_repartition_random_state();
+    const int64_t B = P->batch_size;
+    const uint32_t N = P->N;
+    const int C = P->n_cols;
+    memset(t->coal_rows, 0, sizeof(int64_t) * N);
+    memset(t->sent_rows, 0, sizeof(int64_t) * N);
+    t->batches_out = 0;
+    t->checksum = 0;
+    orc_column kc[8];
+    const int64_t n_batches = (P->n_rows + B - 1) / B;
+    for (int64_t b = tid; b < n_batches; b += P->active_threads) { /* input partition `tid`: batches dealt round-robin */
+        const int64_t base = b * B;
+        const int64_t n = P->n_rows - base < B ? P->n_rows - base : B;
+        for (int k = 0; k < P->n_keys; ++k) {
+            const int c = P->key_cols[k];
+            kc[k].kind = ORC_FIXED; kc[k].width = P->widths[c];
+            kc[k].values = (const uint8_t*)P->cols[c] + (size_t)base * (size_t)P->widths[c];
+            kc[k].offsets = NULL; kc[k].validity = NULL; kc[k].offset = 0;
+        }
+        memset(t->hash_buffer, 0, sizeof(uint64_t) * (size_t)n);
+        orc_create_hashes(kc, P->n_keys, n, &st, t->hash_buffer);
+        orc_partition_indices(t->hash_buffer, n, N, t->counts, t->indices, t->starts);
+        for (uint32_t p = 0; p < N; ++p) {
+            const int64_t cnt = t->counts[p];
+            if (cnt == 0) continue;
+            for (int c = 0; c < C; ++c) /* take_arrays(batch.columns(), indices[p]) */
+                orc_take_fixed((const uint8_t*)P->cols[c] + (size_t)base * (size_t)P->widths[c], P->widths[c], t->indices + t->starts[p], cnt,
+                               t->taken[c]);
+            /* LimitedBatchCoalescer::push_batch: append, emit a batch every batch_size rows */
+            int64_t done = 0;
+            while (done < cnt) {
+                const int64_t room = B - t->coal_rows[p];
+                const int64_t m = cnt - done < room ? cnt - done : room;
+                for (int c = 0; c < C; ++c)
+                    memcpy(t->coal[p][c] + (size_t)t->coal_rows[p] * (size_t)P->widths[c], t->taken[c] + (size_t)done * (size_t)P->widths[c],
+                           (size_t)m * (size_t)P->widths[c]);
+                t->coal_rows[p] += m;
+                done += m;
+                if (t->coal_rows[p] == B) { /* batch complete: sent downstream, consumer drops it, memory is reused */
+                    t->checksum ^= *(const uint64_t*)(t->coal[p][0] + (size_t)(B - 1) * (size_t)P->widths[0] - (P->widths[0] >= 8 ? 0 : 0));
+                    t->batches_out++;
+                    t->coal_rows[p] = 0;
+                }
+            }
+            t->sent_rows[p] += cnt;
+        }
+    }
+    for (uint32_t p = 0; p < N; ++p) /* finish(): flush the partial batches */
+        if (t->coal_rows[p]) { t->batches_out++; t->coal_rows[p] = 0; }
+}
+
+static void* pool_main(void* vp) {
+    pool_arg* a = (pool_arg*)vp;
+    struct orc_pool* P = a->pool;
+    const int tid = a->tid;
+    free(a);
+    uint64_t seen = 0;
+    for (;;) {
+        pthread_mutex_lock(&P->mu);
+        while (!P->shutdown && P->generation == seen) pthread_cond_wait(&P->cv_job, &P->mu);
+        if (P->shutdown) { pthread_mutex_unlock(&P->mu); return NULL; }
+        seen = P->generation;
+        pthread_mutex_unlock(&P->mu);
+        pool_run_job(P, tid);
+        pthread_mutex_lock(&P->mu);
+        if (--P->remaining == 0) pthread_cond_signal(&P->cv_done);
+        pthread_mutex_unlock(&P->mu);
+    }
+}
+
+orc_pool* orc_pool_create(int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    struct orc_pool* P = (struct orc_pool*)calloc(1, sizeof *P);
+    if (!P) return NULL;
+    P->n_threads = n_threads;
+    P->th = (pthread_t*)calloc((size_t)n_threads, sizeof(pthread_t));
+    P->ts = (pool_thread_state*)calloc((size_t)n_threads, sizeof(pool_thread_state));
+    pthread_mutex_init(&P->mu, NULL);
+    pthread_cond_init(&P->cv_job, NULL);
+    pthread_cond_init(&P->cv_done, NULL);
+    for (int t = 0; t < n_threads; ++t) {
+        pool_arg* a = (pool_arg*)malloc(sizeof *a);
+        a->pool = P; a->tid = t;
+        pthread_create(&P->th[t], NULL, pool_main, a);
+    }
+    return P;
+}
+
+void orc_pool_destroy(orc_pool* P) {
+    if (!P) return;
+    pthread_mutex_lock(&P->mu);
+    P->shutdown = 1;
+    pthread_cond_broadcast(&P->cv_job);
+    pthread_mutex_unlock(&P->mu);
+    for (int t = 0; t < P->n_threads; ++t) { pthread_join(P->th[t], NULL); pts_free(&P->ts[t]); }
+    free(P->th); free(P->ts);
+    pthread_mutex_destroy(&P->mu); pthread_cond_destroy(&P->cv_job); pthread_cond_destroy(&P->cv_done);
+    free(P);
+}
+
+int orc_pool_threads(const orc_pool* P) { return P ? P->n_threads : 0; }
+
+int orc_repartition_stream(orc_pool* P, const void* const* cols, const int32_t* widths, int n_cols, int64_t n_rows,
+                           const int32_t* key_cols, int n_keys, uint32_t num_partitions, int64_t batch_size, int use_threads,
+                           int64_t* out_counts, int64_t* out_batches, uint64_t* out_checksum) {
+    if (!P || n_keys > 8 || n_keys < 1 || batch_size < 1) return -1;
+    if (use_threads < 1 || use_threads > P->n_threads) use_threads = P->n_threads;
+    pthread_mutex_lock(&P->mu);
+    P->cols = cols; P->widths = widths; P->n_cols = n_cols; P->n_rows = n_rows; P->key_cols = key_cols; P->n_keys = n_keys;
+    P->N = num_partitions; P->batch_size = batch_size; P->active_threads = use_threads; P->rc = 0;
+    P->remaining = P->n_threads;
+    P->generation++;
+    pthread_cond_broadcast(&P->cv_job);
+    while (P->remaining) pthread_cond_wait(&P->cv_done, &P->mu);
+    pthread_mutex_unlock(&P->mu);
+    int64_t batches = 0;
+    uint64_t cs = 0;
+    for (uint32_t p = 0; p < num_partitions; ++p) out_counts[p] = 0;
+    for (int t = 0; t < use_threads; ++t) {
+        for (uint32_t p = 0; p < num_partitions; ++p) out_counts[p] += P->ts[t].sent_rows[p];
+        batches += P->ts[t].batches_out;
+        cs ^= P->ts[t].checksum;
+    }
+    if (out_batches) *out_batches = batches;
+    if (out_checksum) *out_checksum = cs;
+    return P->rc;
+}

@@ -114,6 +114,21 @@ int orc_repartition_table(const void* const* cols, const int32_t* widths, int n_
                           void* const* out_cols, int64_t* out_counts /*[N]*/,
                           int64_t* out_starts /*[N+1]*/);
 
+/* ---- The same operator as a long-running worker runs it (timed CPU arm) ----
+ * Persistent thread pool (threads created once; reference workers: tokio multi-thread runtime + mimalloc,
+ * benchmarks/cdk/bin/worker.rs:32), per-thread reusable hash / index / take buffers and per-destination
+ * coalescer batches; a completed output batch is handed to a consumer that drops it (its memory is reused).
+ * Per batch the arithmetic and the copies are exactly those of orc_repartition_table.
+ *   use_threads : input partitions == threads used for this call (<= pool size; 0 = all)
+ *   out_counts[N], *out_batches (output batches emitted), *out_checksum (observable side effect of the copies) */
+typedef struct orc_pool orc_pool;
+orc_pool* orc_pool_create(int n_threads);
+void orc_pool_destroy(orc_pool* pool);
+int orc_pool_threads(const orc_pool* pool);
+int orc_repartition_stream(orc_pool* pool, const void* const* cols, const int32_t* widths, int n_cols, int64_t n_rows,
+                           const int32_t* key_cols, int n_keys, uint32_t num_partitions, int64_t batch_size, int use_threads,
+                           int64_t* out_counts, int64_t* out_batches, uint64_t* out_checksum);
+
 /* Lightweight version for big parity checks: destination id per row only. */
 void orc_partition_ids(const orc_column* key_cols, int n_keys, int64_t n_rows,
                        uint32_t num_partitions, uint32_t* dest /*[n_rows]*/);

@@ -77,7 +77,45 @@ def lib():
             C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int, C.c_int64, C.POINTER(C.c_int32), C.c_int,
             C.c_uint32, C.c_int64, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
         ]
+        L.orc_pool_create.restype = C.c_void_p
+        L.orc_pool_create.argtypes = [C.c_int]
+        L.orc_pool_destroy.restype = None
+        L.orc_pool_destroy.argtypes = [C.c_void_p]
+        L.orc_repartition_stream.restype = C.c_int
+        L.orc_repartition_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int, C.c_int64, C.POINTER(C.c_int32),
+                                             C.c_int, C.c_uint32, C.c_int64, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]
     return _lib
+
+
+class WorkerPool:
+    """Persistent CPU worker pool for the timed reference arm (`orc_repartition_stream`)."""
+
+    def __init__(self, n_threads: int):
+        self.n_threads = n_threads
+        self._h = lib().orc_pool_create(n_threads)
+
+    def close(self):
+        if self._h:
+            lib().orc_pool_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def repartition(self, columns, key_cols, num_partitions: int, batch_size: int = 8192, use_threads: int = 0):
+        """RepartitionExec(Hash) + LimitedBatchCoalescer over the whole table; returns (counts[N], output batches)."""
+        n_rows = columns[0].shape[0]
+        n_cols = len(columns)
+        ptrs = (C.c_void_p * n_cols)(*[c.ctypes.data for c in columns])
+        widths = (C.c_int32 * n_cols)(*[c.dtype.itemsize for c in columns])
+        keys = (C.c_int32 * len(key_cols))(*key_cols)
+        counts = np.zeros(num_partitions, dtype=np.int64)
+        batches, cs = C.c_int64(), C.c_uint64()
+        rc = lib().orc_repartition_stream(self._h, ptrs, widths, n_cols, n_rows, keys, len(key_cols), num_partitions, batch_size,
+                                          use_threads, counts.ctypes.data, C.byref(batches), C.byref(cs))
+        if rc != 0:
+            raise MemoryError("orc_repartition_stream failed")
+        return counts, batches.value
 
 
 def _state(seeds=(0, 0, 0, 0)) -> OrcState:
