@@ -325,11 +325,81 @@ TRAFFIC_ONEPASS = None  # dram bytes of one k_scatter<ONEPASS> launch at cfg-2 (
 NVLINK_PEAK_GBS = 770.0  # measured peer copy per direction per GPU on this pool (B200_PROFILING.md; nominal 900)
 
 
+def multi_gpu_parity(args, torch, dist, dfd, nv, ctx, ex, world, rank, P, total_parts):
+    """Bit-parity of the multi-GPU shuffle against the single-node CPU oracle, run by EVERY rank before the timed
+    region (the reference's correctness bar is distributed == single node, tests/tpch_correctness_test.rs:137-146).
+    A seeded cfg-2 table of `parity_rows` rows is split into contiguous producer ranges; every consumer compares each
+    of its partitions — per producer segment, values AND order — with the oracle's rows for that (destination, producer).
+    Returns the number of mismatching segments summed over ranks (0 == parity)."""
+    import uuid
+
+    from oracle import oracle as orc
+    from tests.util import cfg2_columns
+
+    n_chk = args.parity_rows
+    cols = cfg2_columns(n_chk, N_COLS, seed=1234)
+    lo, hi = rank * n_chk // world, (rank + 1) * n_chk // world
+    ins = [torch.from_numpy(c[lo:hi].copy()).cuda() for c in cols]
+    torch.cuda.synchronize()
+    in_cols = [dfd.DeviceColumn.from_torch(t) for t in ins]
+    dest = orc.partition_ids([cols[0]], n_chk, total_parts)
+    node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0], P), uuid.uuid4(), 99, world, world)
+    bad = 0
+
+    def fetch(col, a, cnt):
+        got = np.empty(cnt, dtype=np.int64)
+        if cnt:
+            nv.check(nv.lib().dfd_memcpy_d2h(ctx.handle, got.ctypes.data, col.values + a * 8, cnt * 8))
+        return got
+
+    if args.exchange == "onepass":
+        node.shuffle_onepass(ex, in_cols, hi - lo)
+        node.shuffle_onepass(ex, in_cols, hi - lo)  # twice: window reuse is ordered by the ready/done flags
+        outs, seg_starts, seg_counts = node.collect(ex)
+        segs = lambda q, r: (int(seg_starts[q, r]), int(seg_counts[q, r]))
+    else:
+        cap = int((hi - lo) * 1.5) + 4096
+        mode = nv.EXCHANGE_FUSED if args.exchange == "fused" else nv.EXCHANGE_NCCL
+        outs_t = [torch.empty(cap, dtype=torch.int64, device="cuda") for _ in range(N_COLS)] if mode == nv.EXCHANGE_NCCL else None
+        out_cols = [dfd.DeviceColumn.from_torch(t) for t in outs_t] if outs_t else None
+        outs, starts = node.shuffle(ex, in_cols, hi - lo, mode, out_cols, cap)
+        per = {}
+        for q in range(P):
+            run = int(starts[q])
+            for r in range(world):
+                cnt = int(np.count_nonzero(dest[r * n_chk // world:(r + 1) * n_chk // world] == rank * P + q))
+                per[(q, r)] = (run, cnt)
+                run += cnt
+            if run != int(starts[q + 1]):
+                bad += 1
+        segs = lambda q, r: per[(q, r)]
+    for q in range(P):
+        g = rank * P + q
+        for r in range(world):
+            rlo, rhi = r * n_chk // world, (r + 1) * n_chk // world
+            want = np.nonzero(dest[rlo:rhi] == g)[0] + rlo
+            a, cnt = segs(q, r)
+            if cnt != len(want):
+                bad += 1
+                continue
+            for c in range(N_COLS):
+                if not np.array_equal(fetch(outs[c], a, cnt), cols[c][want]):
+                    bad += 1
+    t = torch.tensor([bad], dtype=torch.int64, device="cuda")
+    dist.all_reduce(t)
+    return int(t.item())
+
+
 def run_multi_gpu(args, torch, dfd, world):
     """N workers = N GPUs of one NVSwitch box, one rank per GPU.  Strong scaling: the 2^26-row
     table is split into `world` contiguous row ranges (producer tasks); N = 8 global partitions,
-    P = 8/world per consumer task.  One step = hist + count all-gather + fused peer-store scatter
-    (or NCCL send/recv) + barrier.  Timed with CUDA events on the library stream, max over ranks."""
+    P = 8/world per consumer task.  One step = one collective shuffle:
+      onepass : k_xchg_signal_ready -> k_scatter_onepass<PEER> (hash once, look-back, peer stores) -> k_xchg_publish_wait
+      fused   : hist + count all-gather + two-pass peer-store scatter + NCCL barrier
+      nccl    : local partition + grouped ncclSend/ncclRecv
+    Timed with CUDA events on the library stream, max over ranks.  Before the timed region every rank checks
+    bit-parity against the CPU oracle on a seeded slice (parity_checked / parity_rows in the JSON line); a mismatch
+    fails the run."""
     import uuid
 
     import torch.distributed as dist
@@ -356,7 +426,7 @@ def run_multi_gpu(args, torch, dfd, world):
     dist.broadcast_object_list(uid, src=0)
     ctx = dfd.WorkerContext(local_rank)
     ex = dfd.ShuffleExchange(ctx, rank, world, uid[0])
-    mode = nv.EXCHANGE_FUSED if args.exchange == "fused" else nv.EXCHANGE_NCCL
+    mode = {"onepass": None, "fused": nv.EXCHANGE_FUSED, "nccl": nv.EXCHANGE_NCCL}[args.exchange]
     ex.setup_window(cap * N_COLS * WIDTH)
     outs_t = [torch.empty(cap, dtype=torch.int64, device="cuda") for _ in range(N_COLS)] if mode == nv.EXCHANGE_NCCL else None
     torch.cuda.synchronize()
@@ -364,46 +434,62 @@ def run_multi_gpu(args, torch, dfd, world):
     out_cols = [dfd.DeviceColumn.from_torch(t) for t in outs_t] if outs_t else None
     node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0], P), uuid.uuid4(), 1, world, world)
 
+    parity_bad = multi_gpu_parity(args, torch, dist, dfd, nv, ctx, ex, world, rank, P, total_parts)
+    if parity_bad:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "n_gpus": world, "parity_checked": False, "parity_mismatching_segments": parity_bad,
+                              "error": "multi-GPU shuffle differs from the CPU oracle"}))
+        ex.close()
+        dist.destroy_process_group()
+        sys.exit(3)
+
     def step():
+        if mode is None:
+            node.shuffle_onepass(ex, in_cols, n)
+            return node.collect(ex)
         return node.shuffle(ex, in_cols, n, mode, out_cols, cap)
 
     def timed_steps(k):
-        """K back-to-back shuffles; the fused transport is enqueued asynchronously (like the 1-GPU path's launches)
+        """K back-to-back shuffles; the fused transports are enqueued asynchronously (like the 1-GPU path's launches)
         and synchronised once at the end, the NCCL transport needs the host count exchange every step."""
+        if mode is None:
+            for _ in range(k):
+                node.shuffle_onepass(ex, in_cols, n)
+            _, _, seg_counts = node.collect(ex)
+            return int(seg_counts.sum())
         if mode == nv.EXCHANGE_FUSED:
             for _ in range(k):
                 node.shuffle_async(ex, in_cols, n)
-            return node.wait(ex)
+            return int(node.wait(ex)[1][-1])
         r = None
         for _ in range(k):
             r = step()
-        return r
+        return int(r[1][-1])
 
     with ClockSampler(local_rank) as clocks:  # started before warm-up: nvidia-smi needs ~1 s to deliver its first sample
         for _ in range(max(args.warmup, 3)):
             step()
         # untimed soak (collective: the same count on every rank), sized for >= ~2 s under load
-        for _ in range(0 if args.no_soak else (2500 if mode == nv.EXCHANGE_FUSED else 300)):
-            node.shuffle_async(ex, in_cols, n) if mode == nv.EXCHANGE_FUSED else step()
-        if mode == nv.EXCHANGE_FUSED and not args.no_soak:
-            node.wait(ex)
+        if not args.no_soak:
+            timed_steps(2500 if mode != nv.EXCHANGE_NCCL else 300)
         ctx.reset_metrics()
         dist.barrier()
         torch.cuda.synchronize()
         ctx.synchronize()
         ctx.timer_start()
-        outs, starts = timed_steps(args.steps)
+        got_rows = timed_steps(args.steps)
         ms_local = ctx.timer_stop()
     torch.cuda.synchronize()
     dist.barrier()
     t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = t.item() / args.steps
-    recv_rows = torch.tensor([int(starts[-1])], dtype=torch.int64, device="cuda")
+    recv_rows = torch.tensor([got_rows], dtype=torch.int64, device="cuda")
     dist.all_reduce(recv_rows)
     assert recv_rows.item() == n_total, (recv_rows.item(), n_total)
     launches = torch.tensor([int(ctx.metrics()["kernel_launches"])], dtype=torch.int64, device="cuda")
     dist.all_reduce(launches)
+    fallbacks = int(nv.lib().dfd_exchange_onepass_fallbacks(ex._h))
 
     # e2e: host (pinned) rows in, host rows out, per worker, through dfd_shuffle_host: chunked
     # H2D | fused shuffle | D2H pipeline (every chunk is one collective), wall clock, max over ranks
@@ -448,7 +534,12 @@ def run_multi_gpu(args, torch, dfd, world):
                                    f"{P} partitions per consumer task, device-resident", "rows": n_total, "columns": N_COLS,
                        "num_partitions": total_parts, "exchange": args.exchange, "host": args.numa_note,
                        "l2": f"per-GPU inputs+window ({2 * n * N_COLS * WIDTH >> 20} MiB) > L2, no flush"},
-            "roofline": {"bound": "nvlink", "kernel": "k_scatter<PEER> (fused hash->rank->peer store)" if args.exchange == "fused" else "ncclSend/Recv",
+            "parity_checked": True, "parity_rows": args.parity_rows,
+            "parity": "every rank compared each (partition, producer) segment — values and order — with the single-node CPU oracle before the timed region",
+            "onepass_fallbacks": fallbacks,
+            "roofline": {"bound": "nvlink", "kernel": {"onepass": "k_scatter_onepass<PEER> (hash once -> look-back -> peer stores; flags over peer memory)",
+                                                        "fused": "k_scatter<PEER> (two-pass; ncclAllGather(counts) + ncclAllReduce barrier)",
+                                                        "nccl": "ncclSend/Recv"}[args.exchange],
                          "achieved": achieved, "peak": NVLINK_PEAK_GBS, "unit": "GB/s", "frac": achieved / NVLINK_PEAK_GBS,
                          "peak_source": "measured peer copy per direction (B200_PROFILING.md); nominal 900", "traffic": None,
                          "algorithmic_bytes_per_gpu_per_direction": alg},
@@ -459,121 +550,3 @@ def run_multi_gpu(args, torch, dfd, world):
     dist.destroy_process_group()
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=int, default=N_ROWS)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-soak", action="store_true", help="skip the untimed clock soak (use under ncu)")
-    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the worker to its GPU's NUMA node")
-    ap.add_argument("--e2e-batch-rows", type=int, default=1 << 20)
-    ap.add_argument("--e2e-chunk-rows", type=int, default=1 << 20)
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"])
-    ap.add_argument("--kernel", default="onepass", choices=["onepass", "twopass"],
-                    help="1-GPU partition path: single-pass k_scatter<ONEPASS> (regions) or K1/K1b/K2 (dense)")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    orig_affinity, numa_note = (None, "numa: binding disabled") if args.no_numa_bind else bind_to_gpu_numa_node(local_rank)
-    args.numa_note = numa_note
-    args.orig_affinity = orig_affinity
-
-    import torch
-
-    import datafusion_distributed_b200 as dfd
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
-        return run_multi_gpu(args, torch, dfd, world)
-    if args.gpus != 1:
-        raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
-    dev = 0
-    torch.cuda.set_device(dev)
-    n = args.rows
-    g = torch.Generator(device="cuda").manual_seed(42)
-    key = torch.randint(-(2**63), 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
-    rid = torch.arange(n, dtype=torch.int64, device="cuda")
-    ins = [key] + [rid * 8 + j for j in range(1, N_COLS)]
-    del rid
-    ctx = dfd.WorkerContext(dev)
-    part = dfd.HashPartitioner(ctx, dfd.Partitioning.Hash([0], NUM_PARTITIONS))
-    onepass = args.kernel == "onepass"
-    region_rows = part.default_region_rows(n) if onepass else 0  # fair share + 25 % per destination
-    outs = [torch.empty(NUM_PARTITIONS * region_rows if onepass else n, dtype=torch.int64, device="cuda") for _ in ins]
-    torch.cuda.synchronize()
-    in_cols = [dfd.DeviceColumn.from_torch(t) for t in ins]
-    out_cols = [dfd.DeviceColumn.from_torch(t) for t in outs]
-
-    def one_step():
-        if onepass:
-            part.partition_onepass(in_cols, n, region_rows, out_cols, sync=False)
-        else:
-            part.partition(in_cols, n, out_cols, sync=False)
-
-    for _ in range(max(args.warmup, 3)):
-        one_step()
-    ctx.synchronize()
-    ctx.reset_metrics()
-    ctx.set_profiling(True)
-    # inputs (4 GiB) + outputs (4 GiB) are far larger than the 126 MB L2: no flush needed between steps
-    with ClockSampler(dev) as clocks:
-        if not args.no_soak:
-            soak(one_step, 1.0, ctx.synchronize)
-        ctx.reset_metrics()
-        ctx.timer_start()
-        for _ in range(args.steps):
-            one_step()
-        ms_total = ctx.timer_stop()
-    m = ctx.metrics()
-    if onepass:
-        _, counts = part.collect()
-        assert int(counts.sum()) == n and ctx.metrics()["onepass_reruns"] == 0, "a destination region overflowed inside the timed loop"
-    ctx.set_profiling(False)
-    ms_per_step = ms_total / args.steps
-    value = n / (ms_per_step / 1e3)
-
-    peak, peak_src = measured_peaks()
-    alg_bytes = 2.0 * N_COLS * WIDTH * n
-    scatter_ms = m["scatter_ms"] / max(m["scatter_launches"], 1)
-    achieved = alg_bytes / (scatter_ms / 1e3) / 1e9
-    line = {
-        "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "int64", "data": "synthetic",
-        "config": {"workload": "cfg2: 2^26 rows x 8 Int64, Hash([col0], 8), device-resident table", "rows": n,
-                   "columns": N_COLS, "num_partitions": NUM_PARTITIONS, "l2": "inputs+outputs (8 GiB) >> L2, no flush",
-                   "kernel_path": ("single pass: k_scatter<ONEPASS> (hash once, decoupled look-back, per-destination regions of "
-                                   f"{region_rows} rows)") if onepass else "two pass: k_tile_hist -> k_scan_tiles -> k_scatter (dense)"},
-        "roofline": {"bound": "hbm", "kernel": "k_scatter<ONEPASS>" if onepass else "k_scatter", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "peak_source": peak_src,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one k_scatter launch at this exact workload,
-                     # from the committed `ncu --set full` capture profiles/r01c_ncu_summary.md (8.59 GB algorithmic)
-                     "traffic": (TRAFFIC_ONEPASS if onepass else 8.576116e9) if n == N_ROWS else None, "traffic_unit": "bytes/launch",
-                     "traffic_source": "profiles/r02a_ncu_summary.md" if onepass else "profiles/r01c_ncu_summary.md",
-                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scatter_ms,
-                     "hist_ms": m["hist_ms"] / max(m["calls"], 1), "scan_ms": m["scan_ms"] / max(m["calls"], 1)},
-        "gpu_launches": int(m["kernel_launches"]),
-        "clocks": clocks.summary(),
-        "e2e": None,
-    }
-    if not args.no_e2e:
-        line["e2e"] = run_e2e(ctx, dfd, n, args)
-        line["gpu_launches"] = int(ctx.metrics()["kernel_launches"])
-    line["config"]["host"] = args.numa_note
-    if not args.no_cpu_baseline:
-        if args.orig_affinity:
-            os.sched_setaffinity(0, args.orig_affinity)  # the CPU baseline uses every host core
-        v, ms_cpu, steps_cpu, info = cpu_pool_arm(n, 3, 1, 25.0)
-        line["cpu_baseline"] = dict({"value": v, "unit": "rows/s", "cores": info["threads_used"], "host_cores": os.cpu_count() or 1, "kind": "port",
-                                     "sample": f"full {n}-row table, mean of {steps_cpu} passes after 1 warm-up; {CPU_WHAT}"}, **info)
-    print(json.dumps(line))
-
-
-if __name__ == "__main__":
-    main()

@@ -22,6 +22,7 @@ STATUS = {
 
 COL_FIXED, COL_BOOL, COL_UTF8, COL_LARGE_UTF8, COL_BINARY = 0, 1, 2, 3, 4
 EXCHANGE_NCCL, EXCHANGE_FUSED = 0, 1
+KEY_HASH_PLAIN, KEY_HASH_INTERVAL_DAY_TIME, KEY_HASH_INTERVAL_MONTH_DAY_NANO = 0, 1, 2
 
 
 class DfdError(RuntimeError):
@@ -119,6 +120,7 @@ SIGNATURES = {
     "dfd_partitioner_create": (C.c_int, [_VP, C.c_uint32, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_uint64), C.POINTER(_VP)]),
     "dfd_partitioner_destroy": (None, [_VP]),
     "dfd_partitioner_num_partitions": (C.c_uint32, [_VP]),
+    "dfd_partitioner_set_key_hash_mode": (C.c_int, [_VP, C.c_int, C.c_int]),
     "dfd_partition_ids_device": (C.c_int, [_VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, _VP]),
     "dfd_partition_device": (C.c_int, [_VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.POINTER(DfdColumn), C.POINTER(C.c_int64)]),
     "dfd_partitioner_part_starts_device": (_VP, [_VP]),
@@ -146,6 +148,9 @@ SIGNATURES = {
                                      C.POINTER(DfdColumn), C.c_int64, C.POINTER(C.c_int64)]),
     "dfd_shuffle_device_async": (C.c_int, [_VP, _VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.c_uint32, C.POINTER(DfdColumn)]),
     "dfd_exchange_wait": (C.c_int, [_VP, C.POINTER(C.c_int64)]),
+    "dfd_shuffle_device_onepass": (C.c_int, [_VP, _VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.c_uint32, C.POINTER(DfdColumn)]),
+    "dfd_exchange_collect": (C.c_int, [_VP, C.POINTER(DfdColumn), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "dfd_exchange_onepass_fallbacks": (C.c_uint64, [_VP]),
     "dfd_shuffle_host": (C.c_int, [_VP, _VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.c_uint32, C.c_int, C.POINTER(DfdColumn),
                                    C.c_int64, C.POINTER(C.c_int64)]),
     "dfd_exchange_stats": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

@@ -86,11 +86,14 @@ static int build_keyset(const dfd_partitioner* p, const dfd_column* cols, int n_
         kc.validity = c.validity;
         kc.offset = c.offset;
         kc.kind = c.kind;
-        kc.width = c.width;
+        kc.width = (int16_t)c.width;
+        kc.mode = (int16_t)p->key_modes[k];
         switch (c.kind) {
             case DFD_COL_FIXED:
                 if (c.width != 1 && c.width != 2 && c.width != 4 && c.width != 8 && c.width != 16)
                     return set_error(DFD_ERR_UNSUPPORTED, "key column %d: fixed width %d not in {1,2,4,8,16}", ci, c.width);
+                if ((kc.mode == KEY_HASH_INTERVAL_DAY_TIME && c.width != 8) || (kc.mode == KEY_HASH_INTERVAL_MONTH_DAY_NANO && c.width != 16))
+                    return set_error(DFD_ERR_INVALID_ARGUMENT, "key column %d: key hash mode %d does not match value width %d", ci, kc.mode, c.width);
                 if (!c.values) return set_error(DFD_ERR_INVALID_ARGUMENT, "key column %d: values is NULL", ci);
                 break;
             case DFD_COL_BOOL:
@@ -105,7 +108,7 @@ static int build_keyset(const dfd_partitioner* p, const dfd_column* cols, int n_
         }
     }
     ks->fast_i64 = (ks->n == 1 && ks->col[0].kind == COL_FIXED && ks->col[0].width == 8 && !ks->col[0].validity &&
-                    ks->col[0].offset == 0)
+                    ks->col[0].offset == 0 && ks->col[0].mode == KEY_HASH_PLAIN)
                        ? 1
                        : 0;
     return DFD_OK;
@@ -215,6 +218,16 @@ int dfd::PartitionJob::prepare(Partitioner* part, const dfd_column* in_cols, int
             passes.push_back(vc);
             bytes += (uint64_t)(n_rows + 7) / 8;
         }
+    }
+    // bit-packed outputs (boolean values, validity bitmaps) are produced with 32-bit atomicOr: zero them here, in whole
+    // words (the header requires capacities of ceil(rows / 32) * 4 bytes), so callers need not pre-clear them
+    if (!peer) {
+        const int64_t orows = out_rows >= 0 ? out_rows : n_rows;
+        for (const PayloadCol& pc : passes)
+            if (pc.width == 0 && orows > 0) {
+                cudaError_t e = cudaMemsetAsync(pc.out, 0, (size_t)((orows + 31) / 32) * 4, stream);
+                if (e != cudaSuccess) return cuda_error(e, "cudaMemsetAsync(bit-packed output)");
+            }
     }
     if (!var_cols.empty() && n_rows > 0) {
         // K4 needs the input row of every output row: scatter an iota column with the rest
@@ -405,6 +418,8 @@ int dfd::PartitionJob::run_onepass(const OnePassLayout& L) {
         sp.lb_epoch = c->lb_epoch;
         sp.totals_out = L.d_totals;
         sp.overflow_out = L.d_overflow;
+        sp.ready_flags = L.ready_flags;
+        sp.ready_epoch = L.ready_epoch;
         if (peer) {
             if (L.world > MAX_RANKS) return set_error(DFD_ERR_UNSUPPORTED, "world size %d > %d", L.world, MAX_RANKS);
             for (int r = 0; r < L.world; ++r) sp.peer_base[r] = L.peer_base[r];
@@ -759,6 +774,7 @@ int dfd_partitioner_create(dfd_ctx* c, uint32_t num_partitions, const int32_t* k
     p->ctx = c;
     p->N = num_partitions;
     p->key_cols.assign(key_cols, key_cols + n_keys);
+    p->key_modes.assign((size_t)n_keys, DFD_KEY_HASH_PLAIN);
     // ahash RandomState::with_seeds: seed ^ PI2 (random_state.rs); DataFusion's
     // REPARTITION_RANDOM_STATE uses seeds (0,0,0,0).
     static const uint64_t PI2[4] = {0x452821e638d01377ULL, 0xbe5466cf34e90c6cULL, 0xc0ac29b7c97c50ddULL,
@@ -798,6 +814,16 @@ void dfd_partitioner_destroy(dfd_partitioner* p) {
 }
 
 uint32_t dfd_partitioner_num_partitions(const dfd_partitioner* p) { return p ? p->N : 0; }
+
+int dfd_partitioner_set_key_hash_mode(dfd_partitioner* p, int key_index, int mode) {
+    if (!p) return set_error(DFD_ERR_INVALID_ARGUMENT, "partitioner is NULL");
+    if (key_index < 0 || key_index >= (int)p->key_cols.size()) return set_error(DFD_ERR_INVALID_ARGUMENT, "key index %d out of range", key_index);
+    if (mode != DFD_KEY_HASH_PLAIN && mode != DFD_KEY_HASH_INTERVAL_DAY_TIME && mode != DFD_KEY_HASH_INTERVAL_MONTH_DAY_NANO)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "unknown key hash mode %d", mode);
+    std::lock_guard<std::mutex> lk(p->ctx->mu);
+    p->key_modes[(size_t)key_index] = mode;
+    return DFD_OK;
+}
 const int64_t* dfd_partitioner_part_starts_device(const dfd_partitioner* p) { return p ? p->d_part_starts : nullptr; }
 
 int dfd_partition_ids_device(dfd_partitioner* p, const dfd_column* cols, int n_cols, int64_t n_rows,
@@ -845,6 +871,7 @@ static int onepass_launch_locked(dfd_partitioner* p, const int64_t* d_base, cons
     cudaError_t e = cudaMemsetAsync(d_flag, 0, sizeof(int64_t), c->stream);
     if (e != cudaSuccess) return cuda_error(e, "cudaMemsetAsync(overflow flag)");
     PartitionJob job;
+    job.out_rows = stride > 0 ? stride * (int64_t)N : p->last_rows;  // region layout spans N * region_rows output rows
     int rc = job.prepare(p, p->last_in.data(), (int)p->last_in.size(), p->last_rows, p->last_out.data(), false, c->stream);
     if (rc) return rc;
     PartitionJob::OnePassLayout L;

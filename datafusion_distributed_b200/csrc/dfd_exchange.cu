@@ -131,6 +131,42 @@ __global__ void k_exchange_plan(const int64_t* __restrict__ counts, int world, u
     if (threadIdx.x == 0) *abort_flag = overflow;
 }
 
+// ---------------------------------------------------------------------------
+// Peer-memory flags of the single-pass exchange (replace ncclAllGather(counts) + ncclAllReduce(barrier)).
+// ---------------------------------------------------------------------------
+// consumer side, start of a shuffle: "my window is free" -> every producer's header
+__global__ void k_xchg_signal_ready(ExchangeHeader* const* __restrict__ peer_hdr, int rank, int world, unsigned long long epoch) {
+    const int o = threadIdx.x;
+    if (o < world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&peer_hdr[o]->ready[rank]), "l"(epoch) : "memory");
+    }
+}
+
+// producer side, end of a shuffle (stream-ordered after the scatter kernels): publish my per-destination counts and my
+// overflow flag into every consumer's header, then the "landed" flag; then, as consumer, wait for every producer's flag.
+__global__ void __launch_bounds__(256) k_xchg_publish_wait(ExchangeHeader* __restrict__ local, ExchangeHeader* const* __restrict__ peer_hdr, int rank, int world,
+                                                           uint32_t P, unsigned long long epoch, const int64_t* __restrict__ totals /*[P*world]*/,
+                                                           const int32_t* __restrict__ overflow, int32_t* __restrict__ timed_out) {
+    const uint32_t N = P * (uint32_t)world;
+    for (uint32_t g = threadIdx.x; g < N; g += blockDim.x) peer_hdr[g / P]->counts[rank][g % P] = totals[g];
+    if ((int)threadIdx.x < world) peer_hdr[threadIdx.x]->overflow[rank] = *overflow;
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&peer_hdr[threadIdx.x]->done[rank]), "l"(epoch) : "memory");
+        const long long t_start = clock64();
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(&local->done[threadIdx.x]) : "memory");
+            if (v < epoch && clock64() - t_start > (1LL << 34)) {  // ~8 s: a peer never arrived (it failed before launching)
+                *timed_out = 1;
+                break;
+            }
+        } while (v < epoch);
+    }
+}
+
 }  // namespace
 
 struct dfd_exchange {
@@ -155,6 +191,19 @@ struct dfd_exchange {
     size_t window_bytes = 0;
     void* peer_window[MAX_RANKS] = {};
     bool window_ready = false;
+    // single-pass exchange: window header flags (no NCCL on the critical path)
+    ExchangeHeader** d_peer_hdr = nullptr;  // device array [T]: every worker's window header
+    unsigned long long epoch = 0;           // shuffle counter (flag value)
+    int32_t* d_flags = nullptr;             // [0] my scatter overflowed a sub-window, [1] a peer never arrived
+    int64_t* h_seg_counts = nullptr;        // pinned [T][P] rows producer r sent to my partition q
+    int32_t* h_seg_flags = nullptr;         // pinned [T] overflow flags of the producers + [T] timed-out flag
+    bool pending_onepass = false;
+    int64_t pending_sub_cap = 0;
+    std::vector<dfd_column> last_in;        // retained for the exact (two-pass) re-run after an overflow
+    std::vector<dfd_column> last_out;
+    dfd_partitioner* last_part = nullptr;
+    int64_t last_rows = 0;
+    uint64_t onepass_fallbacks = 0;
     bool pending_async = false;       // a fused shuffle has been enqueued but not waited for
     size_t pending_row_bytes = 0;
     uint32_t pending_P = 0;
@@ -266,6 +315,10 @@ void dfd_exchange_destroy(dfd_exchange* x) {
             if (x->peer_window[r] && r != x->rank) cudaIpcCloseMemHandle(x->peer_window[r]);
         if (x->comm) nccl_api()->CommDestroy(x->comm);
         cudaFree(x->window);
+        cudaFree(x->d_peer_hdr);
+        cudaFree(x->d_flags);
+        cudaFreeHost(x->h_seg_counts);
+        cudaFreeHost(x->h_seg_flags);
         cudaFree(x->d_counts);
         cudaFree(x->d_dest_base);
         cudaFree(x->d_my_starts);
@@ -314,27 +367,57 @@ int dfd_exchange_setup_window(dfd_exchange* x, size_t window_bytes) {
     CUDA_TRY(cudaSetDevice(c->device), "cudaSetDevice");
     if (x->window_ready) return set_error(DFD_ERR_INVALID_ARGUMENT, "receive window already set up");
     window_bytes = (window_bytes + 255) & ~(size_t)255;
-    CUDA_TRY(cudaMalloc(&x->window, window_bytes), "cudaMalloc(receive window)");
+    // [ExchangeHeader | XCHG_HEADER_BYTES][window_bytes of row data]
+    CUDA_TRY(cudaMalloc(&x->window, window_bytes + XCHG_HEADER_BYTES), "cudaMalloc(receive window)");
+    CUDA_TRY(cudaMemset(x->window, 0, XCHG_HEADER_BYTES), "cudaMemset(window header)");
     x->window_bytes = window_bytes;
     x->peer_window[x->rank] = x->window;
     if (x->world > 1) {
         NcclApi* n = nccl_api();
-        cudaIpcMemHandle_t mine;
-        CUDA_TRY(cudaIpcGetMemHandle(&mine, x->window), "cudaIpcGetMemHandle");
+        // every worker derives slot sizes, column offsets and overflow checks from ITS window_bytes and applies
+        // them to every peer's window: the sizes must agree, so they travel with the IPC handles
+        struct Rec { cudaIpcMemHandle_t handle; unsigned long long bytes; } mine;
+        memset(&mine, 0, sizeof mine);
+        CUDA_TRY(cudaIpcGetMemHandle(&mine.handle, x->window), "cudaIpcGetMemHandle");
+        mine.bytes = (unsigned long long)window_bytes;
         char* d_h = nullptr;
-        const size_t hs = sizeof(cudaIpcMemHandle_t);
+        const size_t hs = sizeof(Rec);
         CUDA_TRY(cudaMalloc((void**)&d_h, hs * (size_t)(x->world + 1)), "cudaMalloc(handles)");
         CUDA_TRY(cudaMemcpyAsync(d_h + hs * x->world, &mine, hs, cudaMemcpyHostToDevice, c->stream), "H2D handle");
         NCCL_TRY(n->AllGather(d_h + hs * x->world, d_h, hs, ncclInt8, x->comm, c->stream), "ncclAllGather(handles)");
-        std::vector<cudaIpcMemHandle_t> all(x->world);
+        std::vector<Rec> all(x->world);
         CUDA_TRY(cudaMemcpyAsync(all.data(), d_h, hs * x->world, cudaMemcpyDeviceToHost, c->stream), "D2H handles");
         CUDA_TRY(cudaStreamSynchronize(c->stream), "sync");
         cudaFree(d_h);
+        for (int r = 0; r < x->world; ++r)
+            if (all[r].bytes != (unsigned long long)window_bytes) {
+                cudaFree(x->window);
+                x->window = nullptr;
+                x->peer_window[x->rank] = nullptr;
+                return set_error(DFD_ERR_INVALID_ARGUMENT, "receive windows must have the same size on every worker: rank %d has %llu B, rank %d has %zu B",
+                                 r, all[r].bytes, x->rank, window_bytes);
+            }
         for (int r = 0; r < x->world; ++r) {
             if (r == x->rank) continue;
-            cudaError_t e = cudaIpcOpenMemHandle(&x->peer_window[r], all[r], cudaIpcMemLazyEnablePeerAccess);
+            cudaError_t e = cudaIpcOpenMemHandle(&x->peer_window[r], all[r].handle, cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess) return cuda_error(e, "cudaIpcOpenMemHandle (peer receive window)");
         }
+    }
+    {
+        std::vector<ExchangeHeader*> hdrs(x->world);
+        for (int r = 0; r < x->world; ++r) hdrs[r] = (ExchangeHeader*)x->peer_window[r];
+        CUDA_TRY(cudaMalloc((void**)&x->d_peer_hdr, sizeof(ExchangeHeader*) * (size_t)x->world), "cudaMalloc(peer headers)");
+        CUDA_TRY(cudaMemcpy(x->d_peer_hdr, hdrs.data(), sizeof(ExchangeHeader*) * (size_t)x->world, cudaMemcpyHostToDevice), "H2D peer headers");
+        CUDA_TRY(cudaMalloc((void**)&x->d_flags, 64), "cudaMalloc(flags)");
+        CUDA_TRY(cudaMemset(x->d_flags, 0, 64), "cudaMemset(flags)");
+        CUDA_TRY(cudaHostAlloc((void**)&x->h_seg_counts, sizeof(int64_t) * MAX_RANKS * XCHG_MAX_P, cudaHostAllocPortable), "cudaHostAlloc");
+        CUDA_TRY(cudaHostAlloc((void**)&x->h_seg_flags, sizeof(int32_t) * (MAX_RANKS + 16), cudaHostAllocPortable), "cudaHostAlloc");
+    }
+    if (x->world > 1) {
+        // the header memset above must be complete on every worker before anyone's first flag store can arrive
+        NcclApi* n = nccl_api();
+        NCCL_TRY(n->AllReduce(x->d_token, x->d_token, 1, ncclInt32, ncclSum, x->comm, c->stream), "ncclAllReduce(window barrier)");
+        CUDA_TRY(cudaStreamSynchronize(c->stream), "sync");
     }
     x->window_ready = true;
     return DFD_OK;
@@ -373,7 +456,7 @@ static int fused_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const df
     const size_t slot_bytes = (x->window_bytes / (size_t)n_slots) & ~(size_t)255;
     const int64_t capacity_rows = (int64_t)(slot_bytes / rb) / 16 * 16;
     void* peer_base[MAX_RANKS];
-    for (int r = 0; r < T; ++r) peer_base[r] = (char*)x->peer_window[r] + (size_t)slot * slot_bytes;
+    for (int r = 0; r < T; ++r) peer_base[r] = (char*)x->peer_window[r] + XCHG_HEADER_BYTES + (size_t)slot * slot_bytes;
     // slot layout (identical on every rank): column c at byte offset capacity_rows * sum(width[0..c))
     std::vector<dfd_column> outs(n_cols);
     size_t off = 0;
@@ -412,6 +495,83 @@ static int fused_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const df
     x->pending_P = P;
     (void)capacity_rows;
     return sync ? fused_shuffle_finish(x, P) : DFD_OK;
+}
+
+// ---- single-pass fused shuffle ------------------------------------------------------------------
+// Every (consumer partition q, producer r) pair owns a fixed sub-window of the consumer's receive window, so a producer
+// needs no global counts before its first store: ONE k_scatter_onepass<PEER> launch hashes, ranks, resolves its tile
+// cursors by look-back and stores straight into the owners' windows over NVLink.  Counts, overflow and completion
+// travel as peer-memory flags (window headers) written by two tiny kernels — no NCCL call on the critical path.
+// The reference makes the same promise: a consumer partition is the MERGE of one stream per producer, in no
+// particular inter-producer order (src/execution_plans/network_shuffle.rs:230-237 `select_all`).
+static bool onepass_supported(const dfd_exchange* x, const dfd_partitioner* part, const dfd_column* cols, int n_cols, uint32_t P) {
+    if (part->N > ONEPASS_MAX_N || P > XCHG_MAX_P || n_cols < 1) return false;
+    for (int i = 0; i < n_cols; ++i)
+        if (cols[i].kind != DFD_COL_FIXED || cols[i].validity) return false;
+    (void)x;
+    return true;
+}
+
+static int onepass_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const dfd_column* in_cols, int n_cols, int64_t n_rows, uint32_t P,
+                                  int slot, int n_slots, dfd_column* out_cols) {
+    dfd_ctx* c = x->ctx;
+    const int T = x->world;
+    cudaStream_t s = c->stream;
+    if (!x->window_ready) return set_error(DFD_ERR_INVALID_ARGUMENT, "fused exchange needs dfd_exchange_setup_window first");
+    const size_t rb = row_bytes_of(in_cols, n_cols);
+    const size_t slot_bytes = (x->window_bytes / (size_t)n_slots) & ~(size_t)255;
+    const int64_t capacity_rows = (int64_t)(slot_bytes / rb) / 32 * 32;
+    const int64_t sub_cap = capacity_rows / ((int64_t)P * T) / 32 * 32;  // rows per (partition, producer) sub-window
+    if (sub_cap < 32) return set_error(DFD_ERR_CAPACITY, "receive window (%zu B) too small for %u x %d sub-windows", x->window_bytes, P, T);
+    void* peer_base[MAX_RANKS];
+    for (int r = 0; r < T; ++r) peer_base[r] = (char*)x->peer_window[r] + XCHG_HEADER_BYTES + (size_t)slot * slot_bytes;
+    std::vector<dfd_column> outs(n_cols);
+    size_t off = 0;
+    for (int i = 0; i < n_cols; ++i) {
+        outs[i] = in_cols[i];
+        outs[i].values = (void*)off;  // peer mode: byte offset into every window slot
+        outs[i].validity = nullptr;
+        outs[i].offset = 0;
+        out_cols[i] = in_cols[i];
+        out_cols[i].values = (char*)peer_base[x->rank] + off;
+        out_cols[i].validity = nullptr;
+        out_cols[i].offset = 0;
+        off += (size_t)capacity_rows * (size_t)in_cols[i].width;
+    }
+    const unsigned long long epoch = ++x->epoch;
+    ExchangeHeader* hdr = (ExchangeHeader*)x->window;
+    // consumer half: my window is free (everything enqueued on my stream so far — i.e. my reads of the previous shuffle — is ordered before)
+    k_xchg_signal_ready<<<1, 32, 0, s>>>(x->d_peer_hdr, x->rank, T, epoch);
+    CUDA_TRY(cudaGetLastError(), "k_xchg_signal_ready");
+    CUDA_TRY(cudaMemsetAsync(x->d_flags, 0, 8, s), "memset flags");
+    int rc;
+    PartitionJob job;
+    if ((rc = job.prepare(part, in_cols, n_cols, n_rows, outs.data(), true, s))) return rc;
+    PartitionJob::OnePassLayout L;
+    L.region_stride = sub_cap;
+    L.peer_base = peer_base;
+    L.world = T;
+    L.rank = x->rank;
+    L.parts_per_rank = P;
+    L.d_totals = x->d_counts;
+    L.d_overflow = x->d_flags;
+    L.ready_flags = hdr->ready;
+    L.ready_epoch = epoch;
+    if ((rc = job.run_onepass(L))) return rc;
+    // producer half: counts + overflow + "landed" flag into every consumer's header; consumer half: wait for all producers
+    k_xchg_publish_wait<<<1, 256, 0, s>>>(hdr, x->d_peer_hdr, x->rank, T, P, epoch, x->d_counts, x->d_flags, x->d_flags + 1);
+    CUDA_TRY(cudaGetLastError(), "k_xchg_publish_wait");
+    c->metrics.kernel_launches += 2;
+    CUDA_TRY(cudaMemcpy2DAsync(x->h_seg_counts, sizeof(int64_t) * P, hdr->counts, sizeof(long long) * XCHG_MAX_P, sizeof(int64_t) * P, (size_t)T,
+                               cudaMemcpyDeviceToHost, s), "D2H counts");
+    CUDA_TRY(cudaMemcpyAsync(x->h_seg_flags, hdr->overflow, sizeof(int32_t) * (size_t)T, cudaMemcpyDeviceToHost, s), "D2H overflow flags");
+    CUDA_TRY(cudaMemcpyAsync(x->h_seg_flags + MAX_RANKS, x->d_flags + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H timeout flag");
+    x->bytes_sent += (uint64_t)n_rows * rb;
+    x->pending_row_bytes = rb;
+    x->pending_onepass = true;
+    x->pending_P = P;
+    x->pending_sub_cap = sub_cap;
+    return DFD_OK;
 }
 
 /* The shuffle: producer task `rank` holds n_rows local rows; afterwards this
@@ -783,12 +943,104 @@ int dfd_exchange_wait(dfd_exchange* x, int64_t* part_starts_host) {
     return DFD_OK;
 }
 
+/* Single-pass fused shuffle (asynchronous): see onepass_shuffle_locked.  Falls back to the two-pass fused path
+ * (dense layout) when the schema / partition count is outside the single-pass kernel's envelope. */
+int dfd_shuffle_device_onepass(dfd_exchange* x, dfd_partitioner* part, const dfd_column* in_cols, int n_cols, int64_t n_rows,
+                               uint32_t partitions_per_task, dfd_column* out_cols) {
+    if (!x || !part || !in_cols || !out_cols) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_shuffle_device_onepass: NULL argument");
+    dfd_ctx* c = x->ctx;
+    if (part->ctx != c) return set_error(DFD_ERR_INVALID_ARGUMENT, "partitioner and exchange belong to different contexts");
+    const uint32_t P = partitions_per_task;
+    if (P < 1 || (uint64_t)P * x->world != part->N)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "num_partitions %u != partitions_per_task %u x %d workers", part->N, P, x->world);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device), "cudaSetDevice");
+    int rc = ensure_count_buffers(x, part->N);
+    if (rc) return rc;
+    x->shuffles++;
+    x->last_in.assign(in_cols, in_cols + n_cols);
+    x->last_part = part;
+    x->last_rows = n_rows;
+    if (!onepass_supported(x, part, in_cols, n_cols, P)) {
+        x->pending_onepass = false;
+        return fused_shuffle_locked(x, part, in_cols, n_cols, n_rows, P, 0, 1, out_cols, nullptr, /*sync=*/false);
+    }
+    rc = onepass_shuffle_locked(x, part, in_cols, n_cols, n_rows, P, 0, 1, out_cols);
+    if (rc == DFD_OK) x->last_out.assign(out_cols, out_cols + n_cols);
+    return rc;
+}
+
+/* Complete the last dfd_shuffle_device_onepass: per local partition q and producer r, rows
+ * [seg_starts[q*T + r], +seg_counts[q*T + r]) of every out column.  If a sub-window overflowed on ANY worker
+ * (every worker sees every producer's flag, so all take the same branch) the shuffle is re-run through the two-pass
+ * fused path with exact counts; the segments then describe its dense layout. */
+int dfd_exchange_collect(dfd_exchange* x, dfd_column* out_cols, int64_t* seg_starts, int64_t* seg_counts) {
+    if (!x) return set_error(DFD_ERR_INVALID_ARGUMENT, "NULL exchange");
+    dfd_ctx* c = x->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device), "cudaSetDevice");
+    const int T = x->world;
+    const uint32_t P = x->pending_P;
+    if (!x->pending_onepass) {
+        if (!x->pending_async) return set_error(DFD_ERR_INVALID_ARGUMENT, "no shuffle is pending");
+        int rc = fused_shuffle_finish(x, P);  // dense two-pass layout: producers contiguous per partition
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpy(x->h_counts, x->d_counts, sizeof(int64_t) * (size_t)P * T * T, cudaMemcpyDeviceToHost), "D2H counts");
+        for (uint32_t q = 0; q < P; ++q) {
+            int64_t run = x->h_my_starts[q];
+            for (int r = 0; r < T; ++r) {
+                const int64_t cnt = x->h_counts[(size_t)r * P * T + (size_t)x->rank * P + q];
+                if (seg_starts) seg_starts[(size_t)q * T + r] = run;
+                if (seg_counts) seg_counts[(size_t)q * T + r] = cnt;
+                run += cnt;
+            }
+        }
+        return DFD_OK;
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream), "single-pass shuffle");
+    x->pending_onepass = false;
+    if (x->h_seg_flags[MAX_RANKS]) return set_error(DFD_ERR_INTERNAL, "a peer worker never signalled completion of the shuffle (did it fail?)");
+    bool overflow = false;
+    for (int r = 0; r < T; ++r) overflow |= x->h_seg_flags[r] != 0;
+    if (overflow) {
+        // exact re-run: counts all-gather -> plan -> two-pass peer scatter (every worker takes this branch)
+        x->onepass_fallbacks++;
+        std::vector<dfd_column> outs(x->last_in.size());
+        int rc = fused_shuffle_locked(x, x->last_part, x->last_in.data(), (int)x->last_in.size(), x->last_rows, P, 0, 1, outs.data(), nullptr, /*sync=*/true);
+        if (rc) return rc;
+        if (out_cols) for (size_t i = 0; i < outs.size(); ++i) out_cols[i] = outs[i];
+        for (uint32_t q = 0; q < P; ++q) {
+            int64_t run = x->h_my_starts[q];
+            for (int r = 0; r < T; ++r) {
+                const int64_t cnt = x->h_seg_counts[(size_t)r * P + q];
+                if (seg_starts) seg_starts[(size_t)q * T + r] = run;
+                if (seg_counts) seg_counts[(size_t)q * T + r] = cnt;
+                run += cnt;
+            }
+        }
+        return DFD_OK;
+    }
+    uint64_t rows = 0;
+    for (uint32_t q = 0; q < P; ++q)
+        for (int r = 0; r < T; ++r) {
+            const int64_t cnt = x->h_seg_counts[(size_t)r * P + q];
+            if (seg_starts) seg_starts[(size_t)q * T + r] = ((int64_t)q * T + r) * x->pending_sub_cap;
+            if (seg_counts) seg_counts[(size_t)q * T + r] = cnt;
+            rows += (uint64_t)cnt;
+        }
+    x->bytes_received += rows * x->pending_row_bytes;
+    return DFD_OK;
+}
+
 int dfd_exchange_stats(dfd_exchange* x, uint64_t* bytes_sent, uint64_t* bytes_received, uint64_t* shuffles) {
     if (!x) return set_error(DFD_ERR_INVALID_ARGUMENT, "NULL exchange");
     if (bytes_sent) *bytes_sent = x->bytes_sent;
     if (bytes_received) *bytes_received = x->bytes_received;
     if (shuffles) *shuffles = x->shuffles;
     return DFD_OK;
+}
+
+uint64_t dfd_exchange_onepass_fallbacks(const dfd_exchange* x) { return x ? x->onepass_fallbacks : 0;
 }
 
 }  // extern "C"

@@ -575,6 +575,15 @@ int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, 
             return set_error(DFD_ERR_INVALID_ARGUMENT, "key column index out of range");
     int rc = dfd_partitioner_create(ctx, num_partitions, key_cols, n_keys, nullptr, &x->part);
     if (rc) return rc;  // (x has no CUDA resources yet; unique_ptr frees it)
+    for (int k = 0; k < n_keys; ++k) {  // interval keys hash field by field (arrow's derived Hash), not as one integer
+        const std::string& fmt = x->fields[(size_t)key_cols[k]].format;
+        const int mode = fmt == "tiD" ? DFD_KEY_HASH_INTERVAL_DAY_TIME : fmt == "tin" ? DFD_KEY_HASH_INTERVAL_MONTH_DAY_NANO : DFD_KEY_HASH_PLAIN;
+        if (mode != DFD_KEY_HASH_PLAIN && (rc = dfd_partitioner_set_key_hash_mode(x->part, k, mode))) {
+            dfd_partitioner_destroy(x->part);
+            x->part = nullptr;
+            return rc;
+        }
+    }
     x->chunk_rows = (opts && opts->chunk_rows > 0) ? opts->chunk_rows : (int64_t)(4 << 20);
     x->chunk_rows = (x->chunk_rows + 63) / 64 * 64;
     x->depth = (opts && opts->pipeline_depth > 0) ? opts->pipeline_depth : 3;

@@ -31,8 +31,14 @@ struct KeyCol {
     const uint8_t* validity;
     int64_t offset;
     int32_t kind;
-    int32_t width;
+    int16_t width;
+    int16_t mode;  // KEY_HASH_*: how a fixed-width value is fed to the hasher
 };
+
+// A fixed-width key is normally ONE write_u{8..128}.  Arrow's interval structs derive `Hash`, i.e. one write
+// per field (arrow-buffer IntervalDayTime {i32, i32}, IntervalMonthDayNano {i32, i32, i64}; DataFusion hash_utils
+// `hash_value!(.., IntervalDayTime, IntervalMonthDayNano)` -> `state.hash_one(self)`).
+enum KeyHashMode : int16_t { KEY_HASH_PLAIN = 0, KEY_HASH_INTERVAL_DAY_TIME = 1, KEY_HASH_INTERVAL_MONTH_DAY_NANO = 2 };
 
 struct KeySet {
     KeyCol col[MAX_KEYS];
@@ -40,7 +46,7 @@ struct KeySet {
     int32_t fast_i64;  // 1: exactly one non-null 8-byte fixed key with offset 0
 };
 
-// `h % n` for n in [1, 65535]: mask for powers of two, otherwise one Barrett
+// `h % n` for n in [1, 2^32) (the ABI caps n at DFD_MAX_PARTITIONS = 4096): mask for powers of two, otherwise one Barrett
 // step (q = mulhi(h, floor(2^64/n)) is off by at most one) — replaces the
 // ~100-instruction generic 64-bit remainder.
 struct ModN {
@@ -150,14 +156,29 @@ __device__ __forceinline__ uint64_t hash_key_value(const KeyCol& c, int64_t j, c
     switch (c.kind) {
         case COL_FIXED: {
             switch (c.width) {
-                case 8: return hash_one_u64(st, ((const uint64_t*)c.values)[j]);
+                case 8: {
+                    const uint64_t v = ((const uint64_t*)c.values)[j];
+                    if (c.mode == KEY_HASH_INTERVAL_DAY_TIME) {  // {days: i32, milliseconds: i32}: two write_i32
+                        AHasher h(st);
+                        h.update(v & 0xffffffffULL);
+                        h.update(v >> 32);
+                        return h.finish();
+                    }
+                    return hash_one_u64(st, v);
+                }
                 case 4: return hash_one_u64(st, ((const uint32_t*)c.values)[j]);
                 case 2: return hash_one_u64(st, ((const uint16_t*)c.values)[j]);
                 case 1: return hash_one_u64(st, ((const uint8_t*)c.values)[j]);
                 default: {  // 16: write_u128 -> large_update
                     const uint64_t* p = (const uint64_t*)c.values + 2 * j;
                     AHasher h(st);
-                    h.large_update(p[0], p[1]);
+                    if (c.mode == KEY_HASH_INTERVAL_MONTH_DAY_NANO) {  // {months: i32, days: i32, nanoseconds: i64}
+                        h.update(p[0] & 0xffffffffULL);
+                        h.update(p[0] >> 32);
+                        h.update(p[1]);
+                    } else {
+                        h.large_update(p[0], p[1]);
+                    }
                     return h.finish();
                 }
             }

@@ -52,6 +52,7 @@ struct dfd_partitioner {
     dfd_ctx* ctx = nullptr;
     uint32_t N = 0;
     std::vector<int32_t> key_cols;
+    std::vector<int32_t> key_modes;  // dfd_key_hash_mode per key column
     dfd::HashState st{};
     dfd::ModN mod{};
     int64_t* d_part_starts = nullptr;  // [N+1]
@@ -82,6 +83,7 @@ struct PartitionJob {
     unsigned long long* d_block_sums = nullptr;
     uint64_t bytes = 0;
     int64_t n_rows = 0, n_tiles = 0;
+    int64_t out_rows = -1;               // rows of the OUTPUT row space (-1: n_rows; single-pass regions: N * region_rows)
     uint32_t* d_hist = nullptr;
     uint32_t* d_base = nullptr;
     int64_t* d_totals = nullptr;  // [N] rows per destination (after run_hist_scan)
@@ -103,6 +105,8 @@ struct PartitionJob {
         uint32_t parts_per_rank = 1;
         int64_t* d_totals = nullptr;           // device [N] out: rows per destination
         int32_t* d_overflow = nullptr;         // device out: set to 1 if a region is too small (caller zeroes it)
+        const unsigned long long* ready_flags = nullptr;  // peer mode: "window free" flags in my header (see ExchangeHeader)
+        unsigned long long ready_epoch = 0;
     };
     int run_onepass(const OnePassLayout& L);
 };

@@ -895,6 +895,20 @@ __global__ void __launch_bounds__(THREADS + 32, MIN_CTAS) k_scatter_onepass(cons
 
     int buf = 0;
     int64_t tile = rank_tile(0);
+    if (PEER && P.ready_flags) {
+        // every consumer must have released its window (previous shuffle fully read) before the first peer store;
+        // the flags were signalled before this kernel started, so this normally falls through — after phase 1 of
+        // the first tile, i.e. off the critical path
+        if ((int)threadIdx.x < P.world) {
+            const long long t_start = clock64();
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(P.ready_flags + threadIdx.x) : "memory");
+                if (v < P.ready_epoch && clock64() - t_start > (1LL << 33)) __trap();
+            } while (v < P.ready_epoch);
+        }
+        block_sync<THREADS, BAR>();
+    }
     while (tile >= 0) {
         const int64_t next = rank_tile(buf ^ 1);
         const uint32_t* const TS = (const uint32_t*)(smem + L.off_ts) + (uint32_t)buf * (N + 1u);

@@ -48,6 +48,24 @@ struct ScatterParams {
     int32_t* overflow_out;       // set to 1 when a region is too small (that tile writes nothing)
     uint32_t* hist_out;          // optional [N][n_tiles]: per-tile counts / cursors for follow-up launches
     uint32_t* base_out;          //   (other column widths) that run the two-pass k_scatter code path
+    // peer mode: "window free" flags in THIS worker's window header, ready_flags[o] >= ready_epoch once consumer o has
+    // finished reading the previous shuffle's rows (checked by every CTA before its first store to a peer)
+    const unsigned long long* ready_flags;
+    unsigned long long ready_epoch;
 };
+
+// Header at the start of every worker's receive window (peer-memory flags of the single-pass exchange; no NCCL on the
+// critical path).  ready[o]  : written by consumer o into every PRODUCER's header: "my window may be overwritten, epoch e"
+//                   done[r]   : written by producer r into every CONSUMER's header: "my rows of shuffle e have landed"
+//                   counts[r][q], overflow[r] : what producer r sent to this consumer's partition q / whether it overflowed
+constexpr uint32_t XCHG_MAX_P = 256;
+constexpr size_t XCHG_HEADER_BYTES = 64 * 1024;
+struct ExchangeHeader {
+    unsigned long long ready[MAX_RANKS];
+    unsigned long long done[MAX_RANKS];
+    int overflow[MAX_RANKS];
+    long long counts[MAX_RANKS][XCHG_MAX_P];
+};
+static_assert(sizeof(ExchangeHeader) <= XCHG_HEADER_BYTES, "exchange header must fit its reservation");
 
 }  // namespace dfd

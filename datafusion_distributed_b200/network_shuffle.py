@@ -178,6 +178,42 @@ class NetworkShuffleExec:
         self._starts = np.frombuffer(starts, dtype=np.int64).copy()
         return self._out, self._starts
 
+    # -- single-pass fused shuffle (segments) -------------------------------------------------
+    def shuffle_onepass(self, exchange: ShuffleExchange, in_cols: Sequence[DeviceColumn], n_rows: int):
+        """`dfd_shuffle_device_onepass`: enqueue the single-pass fused shuffle (no NCCL on the critical path).
+        Complete it with `collect()`."""
+        if len(self.input_stage.tasks) != exchange.world or self.task_count != exchange.world:
+            raise ValueError("this exchange runs one producer and one consumer task per GPU worker")
+        if self._part is None:
+            self._part = HashPartitioner(exchange.ctx, self.input_stage.plan)
+        P = self.properties.partition_count
+        c_out = (nv.DfdColumn * len(in_cols))()
+        nv.check(nv.lib().dfd_shuffle_device_onepass(exchange._h, self._part._h, columns_to_c(in_cols), len(in_cols), n_rows, P, c_out))
+        self._pending = (c_out, [c.arrow_type for c in in_cols], exchange)
+
+    def collect(self, exchange: ShuffleExchange):
+        """Complete `shuffle_onepass`: returns (out columns, seg_starts[P][T], seg_counts[P][T]) — partition q is the
+        merge of its T per-producer segments (rows [seg_starts[q][r], +seg_counts[q][r]) of every column)."""
+        P, T = self.properties.partition_count, exchange.world
+        starts, counts = (C.c_int64 * (P * T))(), (C.c_int64 * (P * T))()
+        c_out, types, _ = self._pending
+        nv.check(nv.lib().dfd_exchange_collect(exchange._h, c_out, starts, counts))
+        self._seg_starts = np.frombuffer(starts, dtype=np.int64).reshape(P, T).copy()
+        self._seg_counts = np.frombuffer(counts, dtype=np.int64).reshape(P, T).copy()
+        self._out = [DeviceColumn(c_out[i].kind, c_out[i].width, c_out[i].values or 0, 0, 0, 0, 0, exchange, types[i]) for i in range(len(types))]
+        self._starts = None
+        return self._out, self._seg_starts, self._seg_counts
+
+    def execute_segments(self, partition: int, task_ctx: DistributedTaskContext):
+        """≙ NetworkShuffleExec::execute(partition, ctx) after `collect()`: the partition's per-producer streams as
+        (columns, [(first_row, n_rows) per producer task])."""
+        if self._out is None or getattr(self, "_seg_starts", None) is None:
+            raise RuntimeError("shuffle_onepass()/collect() has not run")
+        P = self.properties.partition_count
+        if not 0 <= partition < P:
+            raise IndexError(partition)
+        return self._out, [(int(a), int(n)) for a, n in zip(self._seg_starts[partition], self._seg_counts[partition])]
+
     def shuffle_host(self, exchange: ShuffleExchange, host_in: Sequence[DeviceColumn], n_rows: int, n_chunks: int,
                      host_out: Sequence[DeviceColumn], out_capacity_rows: int) -> np.ndarray:
         """Host-to-host pipelined shuffle (`dfd_shuffle_host`): `host_in` / `host_out` describe HOST (pinned)

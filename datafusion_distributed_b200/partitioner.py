@@ -47,6 +47,10 @@ class HashPartitioner:
                                                  len(partitioning.key_cols), seeds_arr, C.byref(self._h)))
         ctx._adopt(self)
 
+    def set_key_hash_mode(self, key_index: int, mode: int):
+        """Interval(DayTime) / Interval(MonthDayNano) keys hash field by field (`dfd_partitioner_set_key_hash_mode`)."""
+        nv.check(nv.lib().dfd_partitioner_set_key_hash_mode(self._h, key_index, mode))
+
     @property
     def num_partitions(self) -> int:
         return self.partitioning.partition_count

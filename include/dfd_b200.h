@@ -132,11 +132,21 @@ int dfd_timer_stop(dfd_ctx* ctx, float* out_ms);
  *   key_cols : indices of the key columns (`Column` exprs) in hashing order
  *   seeds    : ahash RandomState::with_seeds arguments; NULL selects
  *              DataFusion's REPARTITION_RANDOM_STATE = (0,0,0,0)
- * num_partitions must be in [1, 65535]. */
+ * num_partitions must be in [1, 4096] (DFD_MAX_PARTITIONS; DataFusion stages use target_partitions x tasks,
+ * typically tens to hundreds). */
+#define DFD_MAX_PARTITIONS 4096
 int dfd_partitioner_create(dfd_ctx* ctx, uint32_t num_partitions, const int32_t* key_cols,
                            int n_keys, const uint64_t* seeds, dfd_partitioner** out);
 void dfd_partitioner_destroy(dfd_partitioner* p);
 uint32_t dfd_partitioner_num_partitions(const dfd_partitioner* p);
+/* How a FIXED key column is fed to the hasher.  Primitive values are one `write_u{8,16,32,64,128}` (PLAIN).
+ * Arrow's interval structs `#[derive(Hash)]`, i.e. one write per field, and DataFusion hashes them through that
+ * impl (datafusion-common hash_utils `hash_value!(.., IntervalDayTime, IntervalMonthDayNano)`), so an
+ * Interval(DayTime) key (format "tiD", 8 bytes {days: i32, milliseconds: i32}) and an Interval(MonthDayNano)
+ * key ("tin", 16 bytes {months: i32, days: i32, nanoseconds: i64}) must be declared here; as PAYLOAD they are
+ * plain 8 / 16-byte values.  dfd_repartition_exec_create does this from the schema's format strings. */
+typedef enum { DFD_KEY_HASH_PLAIN = 0, DFD_KEY_HASH_INTERVAL_DAY_TIME = 1, DFD_KEY_HASH_INTERVAL_MONTH_DAY_NANO = 2 } dfd_key_hash_mode;
+int dfd_partitioner_set_key_hash_mode(dfd_partitioner* p, int key_index, int mode);
 
 /* dest[i] = create_hashes(key columns)[i] % num_partitions, for device
  * columns; `dest_device` holds n_rows uint32.  (Debug/parity entry point for
@@ -153,8 +163,10 @@ int dfd_partition_ids_device(dfd_partitioner* p, const dfd_column* cols, int n_c
  * part_starts_host (N+1 int64, may be NULL) is filled after a stream sync;
  * with NULL the call is fully asynchronous on dfd_ctx_stream() and the device
  * copy is available through dfd_partitioner_part_starts_device().
- * Nullable payload columns: out_cols[c].validity must point to a zeroed
- * bitmap of ceil(n_rows/8) bytes (output offset is 0).
+ * Bit-packed outputs — out_cols[c].validity of a nullable column and the `values` of a
+ * DFD_COL_BOOL column — are written with 32-bit atomic ORs: each must be 4-byte aligned and
+ * hold ceil(n_rows / 32) * 4 bytes (whole words; output offset is 0).  The library zeroes
+ * them itself at the start of the call.
  * Variable-width payload columns (Utf8 / LargeUtf8 / Binary; K4): out_cols[c]
  * carries `offsets` (n_rows + 1 entries of the input's offset width) and
  * `values` with `values_bytes` >= the input's byte count; the output is one
@@ -272,7 +284,9 @@ void dfd_exchange_destroy(dfd_exchange* x);
 int dfd_exchange_rank(const dfd_exchange* x);
 int dfd_exchange_world(const dfd_exchange* x);
 /* Collective: allocate this worker's receive window (fused mode) and map every
- * peer's window through CUDA IPC. */
+ * peer's window through CUDA IPC.  window_bytes must be the SAME on every worker (slot sizes, column
+ * offsets and capacity checks are derived from it on each producer); a mismatch fails with
+ * DFD_ERR_INVALID_ARGUMENT on every worker. */
 int dfd_exchange_setup_window(dfd_exchange* x, size_t window_bytes);
 
 /* Pure host arithmetic of the exchange (no GPU needed; also what the Rust shim
@@ -315,6 +329,25 @@ int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* p, int mode, const dfd_
 int dfd_shuffle_device_async(dfd_exchange* x, dfd_partitioner* p, const dfd_column* in_cols, int n_cols,
                              int64_t n_rows, uint32_t partitions_per_task, dfd_column* out_cols);
 int dfd_exchange_wait(dfd_exchange* x, int64_t* part_starts_host);
+
+/* Single-pass fused shuffle (the fast path; collective, asynchronous on dfd_ctx_stream()).  Every (consumer partition
+ * q, producer r) pair owns a FIXED sub-window of the consumer's receive window, so producers need no global counts
+ * before their first store: one k_scatter_onepass launch per worker hashes every row once and stores straight into
+ * the owners' windows over NVLink; counts, overflow and completion are peer-memory flags in the window headers —
+ * no NCCL call on the critical path.  This is the reference's own contract: a consumer partition is the merge of
+ * one stream per producer, unordered across producers (src/execution_plans/network_shuffle.rs:230-237 `select_all`);
+ * within a segment rows keep the producer's input order.
+ *   out_cols[c].values are SET to point into this worker's receive window (valid until the next shuffle).
+ *   dfd_exchange_collect synchronises and returns, for local partition q and producer r, the segment
+ *   rows [seg_starts[q*T + r], +seg_counts[q*T + r]) of every out column (T = workers).  If any sub-window
+ *   overflowed on any worker (skew), collect re-runs the shuffle through the exact two-pass fused path on every
+ *   worker (all see the same flags) and rewrites out_cols (may be NULL if the caller keeps the originals) — the
+ *   segments then describe that dense layout.  Fixed-width non-null columns and <= 256 partitions take the
+ *   single-pass kernel; anything else is routed to the two-pass fused path with the same (segments) result. */
+int dfd_shuffle_device_onepass(dfd_exchange* x, dfd_partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,
+                               uint32_t partitions_per_task, dfd_column* out_cols);
+int dfd_exchange_collect(dfd_exchange* x, dfd_column* out_cols, int64_t* seg_starts, int64_t* seg_counts);
+uint64_t dfd_exchange_onepass_fallbacks(const dfd_exchange* x);
 
 /* Host-to-host collective shuffle (end-to-end path of the multi-worker exchange; replaces, per
  * worker, "execute the producer plan, Flight-encode, stream, decode" of

@@ -164,6 +164,21 @@ static inline uint64_t hash_value_at(const orc_column* c, int64_t i, const orc_r
             const int64_t* off = (const int64_t*)c->offsets;
             return orc_hash_one_str(st, (const uint8_t*)c->values + off[j], (size_t)(off[j + 1] - off[j]));
         }
+        case ORC_INTERVAL_DAY_TIME: { /* #[derive(Hash)] struct IntervalDayTime { days: i32, milliseconds: i32 } */
+            const uint8_t* p = (const uint8_t*)c->values + (size_t)j * 8;
+            orc_hasher h = orc_hasher_from_state(st);
+            h_update(&h, rd_le(p, 4));
+            h_update(&h, rd_le(p + 4, 4));
+            return h_finish(&h);
+        }
+        case ORC_INTERVAL_MONTH_DAY_NANO: { /* { months: i32, days: i32, nanoseconds: i64 } */
+            const uint8_t* p = (const uint8_t*)c->values + (size_t)j * 16;
+            orc_hasher h = orc_hasher_from_state(st);
+            h_update(&h, rd_le(p, 4));
+            h_update(&h, rd_le(p + 4, 4));
+            h_update(&h, rd_le(p + 8, 8));
+            return h_finish(&h);
+        }
     }
     return 0;
 }

@@ -69,6 +69,8 @@ enum {
     ORC_UTF8 = 2,    /* int32 offsets + data (Utf8; hashed as str)                */
     ORC_LARGE_UTF8 = 3, /* int64 offsets                                          */
     ORC_BINARY = 4,  /* int32 offsets, hashed as [u8]                             */
+    ORC_INTERVAL_DAY_TIME = 5,       /* 8 B {days: i32, milliseconds: i32}: derived Hash, one write_i32 per field   */
+    ORC_INTERVAL_MONTH_DAY_NANO = 6, /* 16 B {months: i32, days: i32, nanoseconds: i64}: write_i32, write_i32, write_i64 */
 };
 
 typedef struct {

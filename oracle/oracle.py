@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libdf_oracle.so")
 _SRC = os.path.join(_HERE, "df_oracle.c")
 
-ORC_FIXED, ORC_BOOL, ORC_UTF8, ORC_LARGE_UTF8, ORC_BINARY = 0, 1, 2, 3, 4
+ORC_FIXED, ORC_BOOL, ORC_UTF8, ORC_LARGE_UTF8, ORC_BINARY, ORC_INTERVAL_DAY_TIME, ORC_INTERVAL_MONTH_DAY_NANO = 0, 1, 2, 3, 4, 5, 6
 
 
 class OrcState(C.Structure):
@@ -157,6 +157,14 @@ class _Cols:
     def _fill(self, d: OrcColumn, col):
         import pyarrow as pa
 
+        if isinstance(col, tuple):  # ("interval_day_time" | "interval_month_day_nano", raw little-endian values as a uint8 array)
+            tag, raw = col
+            raw = np.ascontiguousarray(raw, dtype=np.uint8)
+            self.keep.append(raw)
+            d.kind = ORC_INTERVAL_DAY_TIME if tag == "interval_day_time" else ORC_INTERVAL_MONTH_DAY_NANO
+            d.width = 8 if tag == "interval_day_time" else 16
+            d.values, d.offsets, d.validity, d.offset = raw.ctypes.data, None, None, 0
+            return
         if isinstance(col, np.ndarray):
             col = np.ascontiguousarray(col)
             self.keep.append(col)
@@ -177,6 +185,8 @@ class _Cols:
             d.kind = ORC_UTF8 if pa.types.is_string(t) else ORC_BINARY
             d.width, d.offsets = 0, bufs[1].address
             d.values = bufs[2].address if bufs[2] is not None else None
+        elif pa.types.is_interval(t):  # month_day_nano_interval: 16 B {months: i32, days: i32, nanoseconds: i64}
+            d.kind, d.width, d.values, d.offsets = ORC_INTERVAL_MONTH_DAY_NANO, 16, bufs[1].address, None
         elif pa.types.is_large_string(t):
             d.kind, d.width, d.offsets = ORC_LARGE_UTF8, 0, bufs[1].address
             d.values = bufs[2].address if bufs[2] is not None else None

@@ -94,6 +94,24 @@ def hash_one_int(x: int, width: int = 8, st=REPARTITION_RANDOM_STATE) -> int:
     return h.finish()
 
 
+def hash_one_interval_day_time(days: int, millis: int, st=REPARTITION_RANDOM_STATE) -> int:
+    """arrow-buffer IntervalDayTime {days: i32, milliseconds: i32} #[derive(Hash)]: write_i32 per field
+    (DataFusion hash_utils: hash_value!(.., IntervalDayTime, IntervalMonthDayNano) -> state.hash_one(self))."""
+    h = AHasher(st)
+    h.update(days & 0xFFFFFFFF)
+    h.update(millis & 0xFFFFFFFF)
+    return h.finish()
+
+
+def hash_one_interval_month_day_nano(months: int, days: int, nanos: int, st=REPARTITION_RANDOM_STATE) -> int:
+    """IntervalMonthDayNano {months: i32, days: i32, nanoseconds: i64} #[derive(Hash)]: write_i32, write_i32, write_i64."""
+    h = AHasher(st)
+    h.update(months & 0xFFFFFFFF)
+    h.update(days & 0xFFFFFFFF)
+    h.update(nanos & M64)
+    return h.finish()
+
+
 def hash_one_str(s: bytes, st=REPARTITION_RANDOM_STATE) -> int:
     h = AHasher(st)
     h.write(s)

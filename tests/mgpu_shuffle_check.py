@@ -71,6 +71,73 @@ def main():
                         failures += 1
                         print(f"rank {rank}: MISMATCH mode={name} N={N} q={q} col={c}", flush=True)
             dist.barrier()
+        # single-pass fused exchange: partition q = T per-producer segments, each bit-exact and in the producer's input order
+        node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0], P), uuid.uuid4(), 1, world, world)
+        for rep in range(3):  # back-to-back shuffles reuse the window: ready/done flags must order them
+            node.shuffle_onepass(ex, in_cols, hi - lo)
+        outs, seg_starts, seg_counts = node.collect(ex)
+        dest_all = orc.partition_ids([cols[0]], n_rows, N)
+        for q in range(P):
+            g = rank * P + q
+            for r in range(world):
+                rlo, rhi = r * n_rows // world, (r + 1) * n_rows // world
+                want_idx = np.nonzero(dest_all[rlo:rhi] == g)[0] + rlo
+                a, cnt = int(seg_starts[q, r]), int(seg_counts[q, r])
+                if cnt != len(want_idx):
+                    failures += 1
+                    print(f"rank {rank}: COUNT MISMATCH onepass N={N} q={q} r={r}: {cnt} != {len(want_idx)}", flush=True)
+                    continue
+                for c in range(n_cols):
+                    got = np.empty(cnt, dtype=np.int64)
+                    if cnt:
+                        nv.check(nv.lib().dfd_memcpy_d2h(ctx.handle, got.ctypes.data, outs[c].values + a * 8, cnt * 8))
+                    if not np.array_equal(got, cols[c][want_idx]):
+                        failures += 1
+                        print(f"rank {rank}: MISMATCH onepass N={N} q={q} r={r} col={c}", flush=True)
+        dist.barrier()
+    # skew: one hot key overflows its sub-window on the producers -> every worker re-runs through the exact two-pass path
+    hot = [np.full(hi - lo, 777, dtype=np.int64), np.arange(lo, hi, dtype=np.int64)]
+    hot[0][::97] = np.arange(lo, hi, 97)
+    hot_t = [torch.from_numpy(c).cuda() for c in hot]
+    torch.cuda.synchronize()
+    hot_cols = [dfd.DeviceColumn.from_torch(t) for t in hot_t]
+    P = 2
+    node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0], P), uuid.uuid4(), 5, world, world)
+    fb0 = nv.lib().dfd_exchange_onepass_fallbacks(ex._h)
+    try:
+        node.shuffle_onepass(ex, hot_cols, hi - lo)
+        outs, seg_starts, seg_counts = node.collect(ex)
+        got_rows = 0
+        for q in range(P):
+            for r in range(world):
+                a, cnt = int(seg_starts[q, r]), int(seg_counts[q, r])
+                got_rows += cnt
+                if cnt:
+                    k = np.empty(cnt, dtype=np.int64)
+                    v = np.empty(cnt, dtype=np.int64)
+                    nv.check(nv.lib().dfd_memcpy_d2h(ctx.handle, k.ctypes.data, outs[0].values + a * 8, cnt * 8))
+                    nv.check(nv.lib().dfd_memcpy_d2h(ctx.handle, v.ctypes.data, outs[1].values + a * 8, cnt * 8))
+                    rlo = r * n_rows // world
+                    ok = bool((np.diff(v) > 0).all()) and bool((orc.partition_ids([k], cnt, P * world) == rank * P + q).all())
+                    # v is the global row id: the key stored there must be what the producer held
+                    exp_k = np.where((v - rlo) % 97 == 0, v, 777)
+                    ok = ok and np.array_equal(k, exp_k)
+                    if not ok:
+                        failures += 1
+                        print(f"rank {rank}: MISMATCH skew fallback q={q} r={r}", flush=True)
+        tot = torch.tensor([got_rows], device="cuda")
+        dist.all_reduce(tot)
+        if tot.item() != n_rows:
+            failures += 1
+            print(f"rank {rank}: skew fallback lost rows: {tot.item()} != {n_rows}", flush=True)
+        if world > 1 and nv.lib().dfd_exchange_onepass_fallbacks(ex._h) != fb0 + 1:
+            failures += 1
+            print(f"rank {rank}: expected exactly one exact re-run for the skewed shuffle", flush=True)
+    except dfd.DfdError as e:  # the dense window may legitimately be too small for a fully skewed destination
+        if e.status != 7:
+            raise
+        print(f"rank {rank}: skewed shuffle reported DFD_ERR_CAPACITY (window too small for the hot destination)", flush=True)
+    dist.barrier()
     # NCCL mode with nullable / boolean / string columns: per destination, rows from the producers in task order
     import pyarrow as pa
     from tests.test_exchange_gpu import _mixed_table

@@ -135,3 +135,25 @@ def test_flight_proxy_reference_arm_is_a_correct_shuffle():
             assert np.array_equal(got, np.sort(cols[1][(dest // P) == ci]))
     finally:
         px.close()
+
+
+def test_interval_keys_hash_field_by_field():
+    """Arrow's IntervalDayTime / IntervalMonthDayNano derive `Hash` (one write per field); DataFusion hashes them through
+    that impl (hash_utils `hash_value!(.., IntervalDayTime, IntervalMonthDayNano)`), NOT as one 64/128-bit integer."""
+    import struct
+
+    from oracle import oracle_py as op
+
+    g = golden()["intervals"]
+    dt = [e for e in g if e["type"] == "day_time"]
+    raw = b"".join(struct.pack("<ii", e["days"], e["millis"]) for e in dt)
+    h = orc.create_hashes([("interval_day_time", np.frombuffer(raw, dtype=np.uint8))], len(dt))
+    assert [format(int(x), "016x") for x in h] == [e["hash"] for e in dt]
+    mdn = [e for e in g if e["type"] == "month_day_nano"]
+    raw = b"".join(struct.pack("<iiq", e["months"], e["days"], int(e["nanos"])) for e in mdn)
+    h = orc.create_hashes([("interval_month_day_nano", np.frombuffer(raw, dtype=np.uint8))], len(mdn))
+    assert [format(int(x), "016x") for x in h] == [e["hash"] for e in mdn]
+    # and it differs from hashing the same bytes as one integer
+    e = dt[0]
+    as_int = int.from_bytes(struct.pack("<ii", e["days"], e["millis"]), "little")
+    assert format(op.hash_one_int(as_int, 8), "016x") != e["hash"]

@@ -351,3 +351,38 @@ def test_arrow_c_device_export_of_one_destination(ctx):
         assert np.array_equal(got, ref[c][rs[p]:rs[p + 1]])
     C.CFUNCTYPE(None, C.c_void_p)(dev.array.release)(C.addressof(dev.array))
     assert not dev.array.release
+
+
+def test_interval_keys_hash_field_by_field_on_gpu(ctx):
+    """Interval(DayTime) / Interval(MonthDayNano) KEY columns: one hasher write per struct field (arrow's derived Hash)."""
+    import struct
+
+    from datafusion_distributed_b200 import _native as nv
+
+    rng = np.random.Generator(np.random.PCG64(99))
+    n = 20_000
+    days = rng.integers(-2**31, 2**31 - 1, n, dtype=np.int32)
+    ms = rng.integers(-2**31, 2**31 - 1, n, dtype=np.int32)
+    raw_dt = np.stack([days, ms], axis=1).copy().view(np.int64).reshape(n)  # {days: i32, milliseconds: i32}
+    months = rng.integers(-2**31, 2**31 - 1, n, dtype=np.int32)
+    nanos = rng.integers(-2**63, 2**63 - 1, n, dtype=np.int64)
+    raw_mdn = np.zeros(n, dtype=[("m", "<i4"), ("d", "<i4"), ("n", "<i8")])
+    raw_mdn["m"], raw_mdn["d"], raw_mdn["n"] = months, days, nanos
+    mdn = pa.Array.from_buffers(pa.decimal128(38, 0), n, [None, pa.py_buffer(raw_mdn.tobytes())])  # any 16-byte fixed layout
+    cols = dev_cols(ctx, [raw_dt, mdn])
+    for N in (8, 48, 1000):
+        part = dfd.HashPartitioner(ctx, dfd.Partitioning.Hash([0], N))
+        part.set_key_hash_mode(0, nv.KEY_HASH_INTERVAL_DAY_TIME)
+        want = orc.partition_ids([("interval_day_time", raw_dt.view(np.uint8))], n, N)
+        assert np.array_equal(part.partition_ids(cols, n), want)
+        part = dfd.HashPartitioner(ctx, dfd.Partitioning.Hash([1, 0], N))
+        part.set_key_hash_mode(0, nv.KEY_HASH_INTERVAL_MONTH_DAY_NANO)
+        part.set_key_hash_mode(1, nv.KEY_HASH_INTERVAL_DAY_TIME)
+        want = orc.partition_ids([("interval_month_day_nano", np.frombuffer(raw_mdn.tobytes(), dtype=np.uint8)),
+                                  ("interval_day_time", raw_dt.view(np.uint8))], n, N)
+        assert np.array_equal(part.partition_ids(cols, n), want)
+    # plain hashing of the same bytes gives different placements: the mode matters
+    plain = dfd.HashPartitioner(ctx, dfd.Partitioning.Hash([0], 1000)).partition_ids(cols, n)
+    assert not np.array_equal(plain, orc.partition_ids([("interval_day_time", raw_dt.view(np.uint8))], n, 1000))
+    with pytest.raises(dfd.DfdError):
+        dfd.HashPartitioner(ctx, dfd.Partitioning.Hash([0], 8)).set_key_hash_mode(0, 7)
