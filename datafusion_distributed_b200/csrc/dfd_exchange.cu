@@ -167,6 +167,144 @@ __global__ void __launch_bounds__(256) k_xchg_publish_wait(ExchangeHeader* __res
     }
 }
 
+// ---- push transport: flag-based all-gather of per-producer metadata, then contiguous peer-store pushes ----
+// Every worker writes its `n_meta` int64 counts into EVERY worker's header (meta[rank][..]), raises meta_flag[rank] = epoch
+// there, and waits until all workers' flags have arrived in its own header: an all-gather over NVLink stores.
+__global__ void __launch_bounds__(256) k_xchg_allgather_meta(ExchangeHeader* __restrict__ local, ExchangeHeader* const* __restrict__ peer_hdr, int rank,
+                                                             int world, unsigned long long epoch, const int64_t* __restrict__ my_meta, uint32_t n_meta,
+                                                             int32_t* __restrict__ timed_out) {
+    for (int o = 0; o < world; ++o)
+        for (uint32_t i = threadIdx.x; i < n_meta; i += blockDim.x) peer_hdr[o]->meta[rank][i] = my_meta[i];
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&peer_hdr[threadIdx.x]->meta_flag[rank]), "l"(epoch) : "memory");
+        const long long t_start = clock64();
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(&local->meta_flag[threadIdx.x]) : "memory");
+            if (v < epoch && clock64() - t_start > (1LL << 34)) {
+                *timed_out = 1;
+                break;
+            }
+        } while (v < epoch);
+    }
+}
+
+// end-of-push barrier: "my pushes have landed" into every consumer's header; wait for every producer's flag
+__global__ void k_xchg_done_barrier(ExchangeHeader* __restrict__ local, ExchangeHeader* const* __restrict__ peer_hdr, int rank, int world,
+                                    unsigned long long epoch, int32_t* __restrict__ timed_out) {
+    if ((int)threadIdx.x < world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&peer_hdr[threadIdx.x]->done[rank]), "l"(epoch) : "memory");
+        const long long t_start = clock64();
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(&local->done[threadIdx.x]) : "memory");
+            if (v < epoch && clock64() - t_start > (1LL << 34)) {
+                *timed_out = 1;
+                break;
+            }
+        } while (v < epoch);
+    }
+}
+
+// One contiguous run of a destination-sorted local column -> its segment in the owner's window.
+struct PushRun {
+    const char* src;
+    char* dst;
+    long long n;       // RUN_BYTES: bytes; RUN_BITS / RUN_ONES: rows (bits); RUN_OFF32 / RUN_OFF64: entries
+    long long a, b;    // RUN_BITS: a = first source bit; RUN_OFF*: dst[k] = src[k] - a + b
+    int kind;
+    int first_block;   // first CTA of this run in the launch (prefix over the runs)
+};
+enum { RUN_BYTES = 0, RUN_BITS = 1, RUN_OFF32 = 2, RUN_OFF64 = 3, RUN_ONES = 4 };
+constexpr int PUSH_THREADS = 256;
+constexpr long long PUSH_CHUNK = 64 * 1024;  // bytes (RUN_BYTES) / output bytes (others) per CTA
+
+__host__ __device__ inline long long push_run_out_bytes(const PushRun& r) {
+    switch (r.kind) {
+        case RUN_BYTES: return r.n;
+        case RUN_BITS: case RUN_ONES: return (r.n + 31) / 32 * 4;
+        case RUN_OFF32: return r.n * 4;
+        default: return r.n * 8;
+    }
+}
+
+__global__ void __launch_bounds__(PUSH_THREADS) k_push_runs(const PushRun* __restrict__ runs, int n_runs) {
+    // which run does this CTA serve?  (binary search over first_block)
+    int lo = 0, hi = n_runs;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (runs[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid;
+    }
+    const PushRun r = runs[lo];
+    const long long c0 = (long long)((int)blockIdx.x - r.first_block) * PUSH_CHUNK;  // first OUTPUT byte of this CTA's chunk
+    const long long total = push_run_out_bytes(r);
+    const long long c1 = c0 + PUSH_CHUNK < total ? c0 + PUSH_CHUNK : total;
+    if (r.kind == RUN_BYTES) {
+        const char* s = r.src + c0;
+        char* d = r.dst + c0;
+        const long long n = c1 - c0;
+        const unsigned mis = (unsigned)(((uintptr_t)s ^ (uintptr_t)d) & 15u);
+        if (mis == 0) {  // co-aligned: 16-byte body
+            long long head = (16 - ((uintptr_t)d & 15u)) & 15u;
+            if (head > n) head = n;
+            for (long long i = threadIdx.x; i < head; i += PUSH_THREADS) d[i] = s[i];
+            const long long body = (n - head) / 16;
+            const uint4* s4 = (const uint4*)(s + head);
+            uint4* d4 = (uint4*)(d + head);
+            for (long long i = threadIdx.x; i < body; i += PUSH_THREADS) __stcs(d4 + i, __ldcs(s4 + i));
+            for (long long i = head + body * 16 + threadIdx.x; i < n; i += PUSH_THREADS) d[i] = s[i];
+        } else if ((mis & 7u) == 0) {  // 8-byte co-aligned (8-byte values at an odd row distance)
+            long long head = (8 - ((uintptr_t)d & 7u)) & 7u;
+            if (head > n) head = n;
+            for (long long i = threadIdx.x; i < head; i += PUSH_THREADS) d[i] = s[i];
+            const long long body = (n - head) / 8;
+            const unsigned long long* s8 = (const unsigned long long*)(s + head);
+            unsigned long long* d8 = (unsigned long long*)(d + head);
+            for (long long i = threadIdx.x; i < body; i += PUSH_THREADS) __stcs(d8 + i, __ldcs(s8 + i));
+            for (long long i = head + body * 8 + threadIdx.x; i < n; i += PUSH_THREADS) d[i] = s[i];
+        } else if ((mis & 3u) == 0) {
+            long long head = (4 - ((uintptr_t)d & 3u)) & 3u;
+            if (head > n) head = n;
+            for (long long i = threadIdx.x; i < head; i += PUSH_THREADS) d[i] = s[i];
+            const long long body = (n - head) / 4;
+            const unsigned* s4 = (const unsigned*)(s + head);
+            unsigned* d4 = (unsigned*)(d + head);
+            for (long long i = threadIdx.x; i < body; i += PUSH_THREADS) d4[i] = s4[i];
+            for (long long i = head + body * 4 + threadIdx.x; i < n; i += PUSH_THREADS) d[i] = s[i];
+        } else {
+            for (long long i = threadIdx.x; i < n; i += PUSH_THREADS) d[i] = s[i];
+        }
+    } else if (r.kind == RUN_BITS) {
+        // destination words are 32-row aligned (segments start on multiples of 32 rows); source starts at bit r.a
+        const unsigned* sw = (const unsigned*)r.src;
+        unsigned* dw = (unsigned*)r.dst;
+        for (long long w = c0 / 4 + threadIdx.x; w < c1 / 4; w += PUSH_THREADS) {
+            const long long bit = r.a + w * 32;
+            const long long wi = bit >> 5;
+            const unsigned sh = (unsigned)(bit & 31);
+            const unsigned lo32 = sw[wi];
+            // (the word after the last one may lie outside the bitmap: only read it when bits of it are needed)
+            const bool need_hi = sh != 0 && (w * 32 + (32 - sh)) < r.n;
+            const unsigned hi32 = need_hi ? sw[wi + 1] : 0u;
+            dw[w] = sh ? __funnelshift_r(lo32, hi32, sh) : lo32;
+        }
+    } else if (r.kind == RUN_ONES) {
+        unsigned* dw = (unsigned*)r.dst;
+        for (long long w = c0 / 4 + threadIdx.x; w < c1 / 4; w += PUSH_THREADS) dw[w] = 0xffffffffu;
+    } else if (r.kind == RUN_OFF32) {
+        const int* so = (const int*)r.src;
+        int* d = (int*)r.dst;
+        for (long long k = c0 / 4 + threadIdx.x; k < c1 / 4; k += PUSH_THREADS) d[k] = (int)((long long)so[k] - r.a + r.b);
+    } else {
+        const long long* so = (const long long*)r.src;
+        long long* d = (long long*)r.dst;
+        for (long long k = c0 / 8 + threadIdx.x; k < c1 / 8; k += PUSH_THREADS) d[k] = so[k] - r.a + r.b;
+    }
+}
+
 }  // namespace
 
 struct dfd_exchange {
@@ -198,6 +336,14 @@ struct dfd_exchange {
     int64_t* h_seg_counts = nullptr;        // pinned [T][P] rows producer r sent to my partition q
     int32_t* h_seg_flags = nullptr;         // pinned [T] overflow flags of the producers + [T] timed-out flag
     bool pending_onepass = false;
+    bool pending_push = false;              // the last shuffle went through the push transport (already complete)
+    std::vector<int64_t> push_seg_starts, push_seg_counts;  // [P][T] result of the last push shuffle
+    int64_t* d_meta = nullptr;              // device [XCHG_META_MAX] my metadata for the flag all-gather
+    int64_t* h_meta = nullptr;              // pinned [MAX_RANKS][XCHG_META_MAX] gathered metadata
+    void* d_runs = nullptr;                 // device PushRun array
+    void* h_runs = nullptr;                 // pinned staging of the same
+    size_t runs_cap = 0;
+    uint64_t push_shuffles = 0;
     int64_t pending_sub_cap = 0;
     std::vector<dfd_column> last_in;        // retained for the exact (two-pass) re-run after an overflow
     std::vector<dfd_column> last_out;
@@ -317,6 +463,10 @@ void dfd_exchange_destroy(dfd_exchange* x) {
         cudaFree(x->window);
         cudaFree(x->d_peer_hdr);
         cudaFree(x->d_flags);
+        cudaFree(x->d_meta);
+        cudaFree(x->d_runs);
+        cudaFreeHost(x->h_meta);
+        cudaFreeHost(x->h_runs);
         cudaFreeHost(x->h_seg_counts);
         cudaFreeHost(x->h_seg_flags);
         cudaFree(x->d_counts);
@@ -412,6 +562,8 @@ int dfd_exchange_setup_window(dfd_exchange* x, size_t window_bytes) {
         CUDA_TRY(cudaMemset(x->d_flags, 0, 64), "cudaMemset(flags)");
         CUDA_TRY(cudaHostAlloc((void**)&x->h_seg_counts, sizeof(int64_t) * MAX_RANKS * XCHG_MAX_P, cudaHostAllocPortable), "cudaHostAlloc");
         CUDA_TRY(cudaHostAlloc((void**)&x->h_seg_flags, sizeof(int32_t) * (MAX_RANKS + 16), cudaHostAllocPortable), "cudaHostAlloc");
+        CUDA_TRY(cudaMalloc((void**)&x->d_meta, sizeof(int64_t) * XCHG_META_MAX), "cudaMalloc(meta)");
+        CUDA_TRY(cudaHostAlloc((void**)&x->h_meta, sizeof(int64_t) * MAX_RANKS * XCHG_META_MAX, cudaHostAllocPortable), "cudaHostAlloc");
     }
     if (x->world > 1) {
         // the header memset above must be complete on every worker before anyone's first flag store can arrive
@@ -571,6 +723,245 @@ static int onepass_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const 
     x->pending_onepass = true;
     x->pending_P = P;
     x->pending_sub_cap = sub_cap;
+    return DFD_OK;
+}
+
+// ---- push transport: every column kind over NVLink, no NCCL --------------------------------------
+// 1. partition locally (K1/K1b/K2 + K4) into a destination-sorted staging buffer — any column kind;
+// 2. all-gather the per-destination row / byte counts through the window headers (k_xchg_allgather_meta); its flag
+//    also tells the producers that this worker's window is free again;
+// 3. every worker derives EVERY consumer's window layout from the same count matrices: partition q of consumer o is T
+//    segments (one per producer, task order), each starting on a 32-row boundary (bitmaps are pushed word-aligned,
+//    no atomics) with >= 1 spare row (a segment's n+1 string offsets never touch its neighbour);
+// 4. k_push_runs stores each destination's contiguous runs — values, shifted bitmaps, re-based string offsets, string
+//    bytes — straight into the owner's segments (16-byte vectors when co-aligned), then k_xchg_done_barrier.
+// The consumer reads Arrow-shaped buffers in place: one values / offsets / bitmap buffer per column, segment (q, r)
+// = rows [seg_start, +seg_count).
+static int push_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const dfd_column* in_cols, int n_cols, int64_t n_rows, uint32_t P,
+                               dfd_column* out_cols) {
+    dfd_ctx* c = x->ctx;
+    const uint32_t N = part->N;
+    const int T = x->world;
+    cudaStream_t s = c->stream;
+    if (!x->window_ready) return set_error(DFD_ERR_INVALID_ARGUMENT, "fused exchange needs dfd_exchange_setup_window first");
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    struct PCol {
+        int kind, width, ow, var_index;
+        bool nullable, in_valid;
+        size_t st_values, st_off, st_valid;
+        int64_t cap_bytes;
+    };
+    std::vector<PCol> pc(n_cols);
+    int V = 0;
+    size_t stage_bytes = 0;
+    const size_t bm = al((size_t)((n_rows + 63) / 64 * 8 + 16));
+    for (int i = 0; i < n_cols; ++i) {
+        const dfd_column& ic = in_cols[i];
+        PCol& q = pc[i];
+        q = PCol{};
+        q.kind = ic.kind; q.width = ic.width; q.ow = ic.kind == DFD_COL_LARGE_UTF8 ? 8 : 4; q.var_index = -1;
+        q.in_valid = ic.validity != nullptr;
+        q.nullable = out_cols[i].validity != nullptr || q.in_valid;  // (the schema's flag: every worker passes the same)
+        if (ic.kind == DFD_COL_FIXED) {
+            q.st_values = stage_bytes; stage_bytes += al((size_t)n_rows * ic.width + 16);
+        } else if (ic.kind == DFD_COL_BOOL) {
+            q.st_values = stage_bytes; stage_bytes += bm;
+        } else if (ic.kind == DFD_COL_UTF8 || ic.kind == DFD_COL_LARGE_UTF8 || ic.kind == DFD_COL_BINARY) {
+            q.var_index = V++;
+            q.cap_bytes = ic.values_bytes > 0 ? ic.values_bytes : 16;
+            q.st_off = stage_bytes; stage_bytes += al((size_t)(n_rows + 1) * q.ow + 16);
+            q.st_values = stage_bytes; stage_bytes += al((size_t)q.cap_bytes + 16);
+        } else {
+            return set_error(DFD_ERR_UNSUPPORTED, "column %d: unknown column kind %d", i, ic.kind);
+        }
+        if (q.in_valid) { q.st_valid = stage_bytes; stage_bytes += bm; }
+    }
+    const uint32_t n_meta = (uint32_t)(1 + V) * N;
+    if (n_meta > XCHG_META_MAX)
+        return set_error(DFD_ERR_UNSUPPORTED, "push transport: (1 + %d string columns) x %u partitions exceeds %u metadata entries", V, N, XCHG_META_MAX);
+    const size_t first_off = stage_bytes;  // device: first[V][N] byte offset of every destination's run in the staged bytes
+    stage_bytes += al((size_t)(V ? V : 1) * N * 8);
+    int rc;
+    if ((rc = x->send.ensure(stage_bytes + 256, c->device))) return rc;
+    char* sb = (char*)x->send.ptr;
+    std::vector<dfd_column> staged(n_cols);
+    for (int i = 0; i < n_cols; ++i) {
+        const PCol& q = pc[i];
+        staged[i] = in_cols[i];
+        staged[i].values = sb + q.st_values;
+        staged[i].offsets = q.var_index >= 0 ? (void*)(sb + q.st_off) : nullptr;
+        staged[i].validity = q.in_valid ? (uint8_t*)(sb + q.st_valid) : nullptr;
+        staged[i].offset = 0;
+        staged[i].values_bytes = q.cap_bytes;
+    }
+    PartitionJob job;
+    if ((rc = job.prepare(part, in_cols, n_cols, n_rows, staged.data(), false, s))) return rc;
+    if ((rc = job.run_hist_scan())) return rc;
+    if ((rc = job.run_scatter(part->d_part_starts, nullptr, 1, 1, nullptr))) return rc;
+    // my metadata: rows per destination, then bytes per destination of every string column
+    CUDA_TRY(cudaMemcpyAsync(x->d_meta, job.d_totals, sizeof(int64_t) * N, cudaMemcpyDeviceToDevice, s), "copy counts");
+    int64_t* d_first = (int64_t*)(sb + first_off);
+    for (int i = 0; i < n_cols; ++i)
+        if (pc[i].var_index >= 0 &&
+            (rc = launch_var_dest_bytes(sb + pc[i].st_off, pc[i].ow, part->d_part_starts, N, x->d_meta + (size_t)N * (1 + pc[i].var_index),
+                                        d_first + (size_t)N * pc[i].var_index, s)))
+            return rc;
+    const unsigned long long epoch = ++x->epoch;
+    ExchangeHeader* hdr = (ExchangeHeader*)x->window;
+    CUDA_TRY(cudaMemsetAsync(x->d_flags, 0, 8, s), "memset flags");
+    k_xchg_allgather_meta<<<1, 256, 0, s>>>(hdr, x->d_peer_hdr, x->rank, T, epoch, x->d_meta, n_meta, x->d_flags + 1);
+    CUDA_TRY(cudaGetLastError(), "k_xchg_allgather_meta");
+    CUDA_TRY(cudaMemcpy2DAsync(x->h_meta, sizeof(int64_t) * XCHG_META_MAX, hdr->meta, sizeof(long long) * XCHG_META_MAX, sizeof(int64_t) * n_meta,
+                               (size_t)T, cudaMemcpyDeviceToHost, s), "D2H meta");
+    std::vector<int64_t> h_first((size_t)(V ? V : 1) * N);
+    if (V) CUDA_TRY(cudaMemcpyAsync(h_first.data(), d_first, sizeof(int64_t) * (size_t)V * N, cudaMemcpyDeviceToHost, s), "D2H first");
+    CUDA_TRY(cudaMemcpyAsync(x->h_seg_flags + MAX_RANKS, x->d_flags + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H timeout flag");
+    CUDA_TRY(cudaStreamSynchronize(s), "push shuffle: metadata exchange");
+    if (x->h_seg_flags[MAX_RANKS]) return set_error(DFD_ERR_INTERNAL, "a peer worker never published its shuffle metadata (did it fail?)");
+    auto rows_of = [&](int r, uint32_t g) { return x->h_meta[(size_t)r * XCHG_META_MAX + g]; };
+    auto bytes_of = [&](int r, int v, uint32_t g) { return x->h_meta[(size_t)r * XCHG_META_MAX + (size_t)N * (1 + v) + g]; };
+    // ---- every consumer's layout, from the same matrices on every worker
+    struct Layout {
+        std::vector<int64_t> seg_start;               // [P][T] rows
+        std::vector<std::vector<int64_t>> bseg_start; // [V][P][T] bytes
+        int64_t rows_cap = 0;
+        std::vector<size_t> reg_values, reg_off, reg_valid;  // byte offsets of the column regions in the window
+    };
+    std::vector<Layout> lay(T);
+    for (int o = 0; o < T; ++o) {
+        Layout& Lo = lay[o];
+        Lo.seg_start.assign((size_t)P * T, 0);
+        Lo.bseg_start.assign(V, std::vector<int64_t>((size_t)P * T, 0));
+        int64_t run = 0;
+        std::vector<int64_t> brun(V, 0);
+        for (uint32_t q = 0; q < P; ++q)
+            for (int r = 0; r < T; ++r) {
+                const uint32_t g = (uint32_t)o * P + q;
+                Lo.seg_start[(size_t)q * T + r] = run;
+                run = (run + rows_of(r, g) + 1 + 31) / 32 * 32;  // 32-row aligned, >= 1 spare row
+                for (int v = 0; v < V; ++v) {
+                    Lo.bseg_start[v][(size_t)q * T + r] = brun[v];
+                    brun[v] = (brun[v] + bytes_of(r, v, g) + 15) / 16 * 16;
+                }
+            }
+        Lo.rows_cap = run;
+        Lo.reg_values.assign(n_cols, 0); Lo.reg_off.assign(n_cols, 0); Lo.reg_valid.assign(n_cols, 0);
+        size_t off = 0;
+        for (int i = 0; i < n_cols; ++i) {
+            const PCol& q = pc[i];
+            if (q.kind == DFD_COL_FIXED) { Lo.reg_values[i] = off; off += al((size_t)run * q.width + 16); }
+            else if (q.kind == DFD_COL_BOOL) { Lo.reg_values[i] = off; off += al((size_t)run / 8 + 16); }
+            else {
+                Lo.reg_off[i] = off; off += al((size_t)(run + 1) * q.ow + 16);
+                Lo.reg_values[i] = off; off += al((size_t)brun[q.var_index] + 16);
+            }
+            if (q.nullable) { Lo.reg_valid[i] = off; off += al((size_t)run / 8 + 16); }
+        }
+        if (off > x->window_bytes)
+            return set_error(DFD_ERR_CAPACITY, "consumer %d needs %zu B of receive window for this shuffle, windows hold %zu B", o, off, x->window_bytes);
+    }
+    // ---- my runs as producer
+    std::vector<PushRun> runs;
+    int64_t send_start = 0;
+    for (uint32_t g = 0; g < N; ++g) {
+        const int o = (int)(g / P);
+        const uint32_t q = g % P;
+        const int64_t cnt = rows_of(x->rank, g);
+        const Layout& Lo = lay[o];
+        const int64_t seg = Lo.seg_start[(size_t)q * T + x->rank];
+        char* dst_base = (char*)x->peer_window[o] + XCHG_HEADER_BYTES;
+        if (cnt > 0) {
+            for (int i = 0; i < n_cols; ++i) {
+                const PCol& qc = pc[i];
+                PushRun r{};
+                if (qc.kind == DFD_COL_FIXED) {
+                    r.kind = RUN_BYTES; r.src = sb + qc.st_values + (size_t)send_start * qc.width;
+                    r.dst = dst_base + Lo.reg_values[i] + (size_t)seg * qc.width; r.n = cnt * qc.width;
+                    runs.push_back(r);
+                } else if (qc.kind == DFD_COL_BOOL) {
+                    r.kind = RUN_BITS; r.src = sb + qc.st_values; r.a = send_start; r.dst = dst_base + Lo.reg_values[i] + (size_t)seg / 8; r.n = cnt;
+                    runs.push_back(r);
+                } else {
+                    const int v = qc.var_index;
+                    const int64_t first = h_first[(size_t)v * N + g], nb = bytes_of(x->rank, v, g);
+                    const int64_t bseg = Lo.bseg_start[v][(size_t)q * T + x->rank];
+                    r.kind = qc.ow == 8 ? RUN_OFF64 : RUN_OFF32; r.src = sb + qc.st_off + (size_t)send_start * qc.ow; r.a = first; r.b = bseg;
+                    r.dst = dst_base + Lo.reg_off[i] + (size_t)seg * qc.ow; r.n = cnt + 1;
+                    runs.push_back(r);
+                    if (nb > 0) {
+                        PushRun b{};
+                        b.kind = RUN_BYTES; b.src = sb + qc.st_values + first; b.dst = dst_base + Lo.reg_values[i] + bseg; b.n = nb;
+                        runs.push_back(b);
+                        x->bytes_sent += o == x->rank ? 0 : (uint64_t)nb;
+                    }
+                }
+                if (qc.nullable) {
+                    PushRun vr{};
+                    vr.kind = qc.in_valid ? RUN_BITS : RUN_ONES; vr.src = qc.in_valid ? sb + qc.st_valid : nullptr; vr.a = send_start;
+                    vr.dst = dst_base + Lo.reg_valid[i] + (size_t)seg / 8; vr.n = cnt;
+                    runs.push_back(vr);
+                }
+            }
+        }
+        send_start += cnt;
+    }
+    int blocks = 0;
+    for (PushRun& r : runs) {
+        r.first_block = blocks;
+        blocks += (int)((push_run_out_bytes(r) + PUSH_CHUNK - 1) / PUSH_CHUNK);
+    }
+    if (!runs.empty()) {
+        const size_t need = runs.size() * sizeof(PushRun);
+        if (need > x->runs_cap) {
+            cudaFree(x->d_runs); cudaFreeHost(x->h_runs);
+            x->d_runs = nullptr; x->h_runs = nullptr; x->runs_cap = 0;
+            CUDA_TRY(cudaMalloc(&x->d_runs, need * 2), "cudaMalloc(push runs)");
+            CUDA_TRY(cudaHostAlloc(&x->h_runs, need * 2, cudaHostAllocPortable), "cudaHostAlloc(push runs)");
+            x->runs_cap = need * 2;
+        }
+        memcpy(x->h_runs, runs.data(), need);
+        CUDA_TRY(cudaMemcpyAsync(x->d_runs, x->h_runs, need, cudaMemcpyHostToDevice, s), "H2D push runs");
+        k_push_runs<<<(unsigned)blocks, PUSH_THREADS, 0, s>>>((const PushRun*)x->d_runs, (int)runs.size());
+        CUDA_TRY(cudaGetLastError(), "k_push_runs");
+        c->metrics.kernel_launches++;
+    }
+    k_xchg_done_barrier<<<1, 32, 0, s>>>(hdr, x->d_peer_hdr, x->rank, T, epoch, x->d_flags + 1);
+    CUDA_TRY(cudaGetLastError(), "k_xchg_done_barrier");
+    c->metrics.kernel_launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(x->h_seg_flags + MAX_RANKS, x->d_flags + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H timeout flag");
+    CUDA_TRY(cudaStreamSynchronize(s), "push shuffle");
+    if (x->h_seg_flags[MAX_RANKS]) return set_error(DFD_ERR_INTERNAL, "a peer worker never finished its pushes (did it fail?)");
+    // ---- my view as consumer
+    const Layout& Me = lay[x->rank];
+    char* my_base = (char*)x->window + XCHG_HEADER_BYTES;
+    for (int i = 0; i < n_cols; ++i) {
+        const PCol& q = pc[i];
+        out_cols[i] = in_cols[i];
+        out_cols[i].offset = 0;
+        out_cols[i].values = my_base + Me.reg_values[i];
+        out_cols[i].offsets = q.var_index >= 0 ? (void*)(my_base + Me.reg_off[i]) : nullptr;
+        out_cols[i].validity = q.nullable ? (uint8_t*)(my_base + Me.reg_valid[i]) : nullptr;
+        out_cols[i].values_bytes = 0;
+    }
+    x->push_seg_starts.assign((size_t)P * T, 0);
+    x->push_seg_counts.assign((size_t)P * T, 0);
+    uint64_t rows = 0;
+    for (uint32_t q = 0; q < P; ++q)
+        for (int r = 0; r < T; ++r) {
+            x->push_seg_starts[(size_t)q * T + r] = Me.seg_start[(size_t)q * T + r];
+            x->push_seg_counts[(size_t)q * T + r] = rows_of(r, (uint32_t)x->rank * P + q);
+            rows += (uint64_t)x->push_seg_counts[(size_t)q * T + r];
+        }
+    for (int i = 0; i < n_cols; ++i)
+        if (pc[i].kind == DFD_COL_FIXED) {
+            x->bytes_sent += (uint64_t)n_rows * pc[i].width;
+            x->bytes_received += rows * (uint64_t)pc[i].width;
+        }
+    x->push_shuffles++;
+    x->pending_push = true;
+    x->pending_onepass = false;
+    x->pending_async = false;
+    x->pending_P = P;
     return DFD_OK;
 }
 
@@ -961,9 +1352,11 @@ int dfd_shuffle_device_onepass(dfd_exchange* x, dfd_partitioner* part, const dfd
     x->last_in.assign(in_cols, in_cols + n_cols);
     x->last_part = part;
     x->last_rows = n_rows;
+    x->pending_push = false;
     if (!onepass_supported(x, part, in_cols, n_cols, P)) {
+        // nullable / boolean / string columns (or > 256 partitions): the push transport moves every column kind
         x->pending_onepass = false;
-        return fused_shuffle_locked(x, part, in_cols, n_cols, n_rows, P, 0, 1, out_cols, nullptr, /*sync=*/false);
+        return push_shuffle_locked(x, part, in_cols, n_cols, n_rows, P, out_cols);
     }
     rc = onepass_shuffle_locked(x, part, in_cols, n_cols, n_rows, P, 0, 1, out_cols);
     if (rc == DFD_OK) x->last_out.assign(out_cols, out_cols + n_cols);
@@ -981,6 +1374,13 @@ int dfd_exchange_collect(dfd_exchange* x, dfd_column* out_cols, int64_t* seg_sta
     CUDA_TRY(cudaSetDevice(c->device), "cudaSetDevice");
     const int T = x->world;
     const uint32_t P = x->pending_P;
+    if (x->pending_push) {  // the push transport completes inside the call: hand out its segments
+        for (size_t i = 0; i < (size_t)P * T; ++i) {
+            if (seg_starts) seg_starts[i] = x->push_seg_starts[i];
+            if (seg_counts) seg_counts[i] = x->push_seg_counts[i];
+        }
+        return DFD_OK;
+    }
     if (!x->pending_onepass) {
         if (!x->pending_async) return set_error(DFD_ERR_INVALID_ARGUMENT, "no shuffle is pending");
         int rc = fused_shuffle_finish(x, P);  // dense two-pass layout: producers contiguous per partition

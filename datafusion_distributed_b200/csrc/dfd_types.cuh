@@ -59,12 +59,17 @@ struct ScatterParams {
 //                   done[r]   : written by producer r into every CONSUMER's header: "my rows of shuffle e have landed"
 //                   counts[r][q], overflow[r] : what producer r sent to this consumer's partition q / whether it overflowed
 constexpr uint32_t XCHG_MAX_P = 256;
-constexpr size_t XCHG_HEADER_BYTES = 64 * 1024;
+constexpr uint32_t XCHG_META_MAX = 2048;  // push transport: int64 metadata entries per producer ((1 + var columns) x N)
+constexpr size_t XCHG_HEADER_BYTES = 320 * 1024;
 struct ExchangeHeader {
     unsigned long long ready[MAX_RANKS];
     unsigned long long done[MAX_RANKS];
     int overflow[MAX_RANKS];
     long long counts[MAX_RANKS][XCHG_MAX_P];
+    // push transport (all column kinds): meta_flag[r] = e once producer r's row / byte counts of shuffle e are in meta[r][]
+    // (it is sent only after r's stream has finished reading r's own window, so it doubles as the "window free" signal)
+    unsigned long long meta_flag[MAX_RANKS];
+    long long meta[MAX_RANKS][XCHG_META_MAX];
 };
 static_assert(sizeof(ExchangeHeader) <= XCHG_HEADER_BYTES, "exchange header must fit its reservation");
 

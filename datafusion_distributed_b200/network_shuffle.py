@@ -179,17 +179,58 @@ class NetworkShuffleExec:
         return self._out, self._starts
 
     # -- single-pass fused shuffle (segments) -------------------------------------------------
-    def shuffle_onepass(self, exchange: ShuffleExchange, in_cols: Sequence[DeviceColumn], n_rows: int):
-        """`dfd_shuffle_device_onepass`: enqueue the single-pass fused shuffle (no NCCL on the critical path).
-        Complete it with `collect()`."""
+    def shuffle_onepass(self, exchange: ShuffleExchange, in_cols: Sequence[DeviceColumn], n_rows: int,
+                        nullable: Optional[Sequence[bool]] = None):
+        """`dfd_shuffle_device_onepass`: the NCCL-free fused shuffle.  Fixed-width non-null columns take the single-pass
+        kernel (asynchronous); nullable / boolean / string columns take the push transport.  `nullable[i]` is the
+        SCHEMA's nullable flag of column i (every worker must pass the same; default: this worker's columns that
+        carry a validity bitmap).  Complete it with `collect()`."""
         if len(self.input_stage.tasks) != exchange.world or self.task_count != exchange.world:
             raise ValueError("this exchange runs one producer and one consumer task per GPU worker")
         if self._part is None:
             self._part = HashPartitioner(exchange.ctx, self.input_stage.plan)
         P = self.properties.partition_count
         c_out = (nv.DfdColumn * len(in_cols))()
+        for i, c in enumerate(in_cols):
+            if (nullable[i] if nullable is not None else bool(c.validity)):
+                c_out[i].validity = 1  # (flag only: the library replaces it with the bitmap's address)
         nv.check(nv.lib().dfd_shuffle_device_onepass(exchange._h, self._part._h, columns_to_c(in_cols), len(in_cols), n_rows, P, c_out))
         self._pending = (c_out, [c.arrow_type for c in in_cols], exchange)
+
+    @staticmethod
+    def segment_to_arrow(ctx: WorkerContext, col: DeviceColumn, start: int, count: int):
+        """Download rows [start, start+count) of a window-resident output column as a pyarrow Array (test / debug helper)."""
+        import pyarrow as pa
+
+        def grab(ptr, nbytes):
+            buf = np.empty(max(nbytes, 1), dtype=np.uint8)
+            if nbytes:
+                nv.check(nv.lib().dfd_memcpy_d2h(ctx.handle, buf.ctypes.data, ptr, nbytes))
+            return buf[:nbytes]
+
+        def bits(ptr):  # bitmap rows [start, start+count) re-based to bit 0
+            lo = start // 8
+            raw = grab(ptr + lo, (start % 8 + count + 7) // 8)
+            b = np.unpackbits(raw, bitorder="little")[start % 8: start % 8 + count]
+            return b
+
+        validity_buf, null_count = None, 0
+        if col.validity:
+            vb = bits(col.validity)
+            null_count = int(count - vb.sum())
+            validity_buf = pa.py_buffer(np.packbits(vb, bitorder="little").tobytes())
+        if col.kind == nv.COL_BOOL:
+            data = pa.py_buffer(np.packbits(bits(col.values), bitorder="little").tobytes())
+            return pa.Array.from_buffers(pa.bool_(), count, [validity_buf, data], null_count=null_count)
+        if col.kind == nv.COL_FIXED:
+            data = pa.py_buffer(grab(col.values + start * col.width, count * col.width).tobytes())
+            return pa.Array.from_buffers(col.arrow_type, count, [validity_buf, data], null_count=null_count)
+        ow = 8 if col.kind == nv.COL_LARGE_UTF8 else 4
+        off = grab(col.offsets + start * ow, (count + 1) * ow).view(np.int64 if ow == 8 else np.int32)
+        lo, hi = (int(off[0]), int(off[-1])) if count else (0, 0)
+        data = pa.py_buffer(grab(col.values + lo, hi - lo).tobytes())
+        offs = pa.py_buffer((off - lo).astype(off.dtype).tobytes()) if count else pa.py_buffer(np.zeros(1, dtype=off.dtype if count else np.int32).tobytes())
+        return pa.Array.from_buffers(col.arrow_type, count, [validity_buf, offs, data], null_count=null_count)
 
     def collect(self, exchange: ShuffleExchange):
         """Complete `shuffle_onepass`: returns (out columns, seg_starts[P][T], seg_counts[P][T]) — partition q is the
@@ -200,7 +241,8 @@ class NetworkShuffleExec:
         nv.check(nv.lib().dfd_exchange_collect(exchange._h, c_out, starts, counts))
         self._seg_starts = np.frombuffer(starts, dtype=np.int64).reshape(P, T).copy()
         self._seg_counts = np.frombuffer(counts, dtype=np.int64).reshape(P, T).copy()
-        self._out = [DeviceColumn(c_out[i].kind, c_out[i].width, c_out[i].values or 0, 0, 0, 0, 0, exchange, types[i]) for i in range(len(types))]
+        self._out = [DeviceColumn(c_out[i].kind, c_out[i].width, c_out[i].values or 0, c_out[i].offsets or 0, c_out[i].validity or 0, 0, 0,
+                                  exchange, types[i]) for i in range(len(types))]
         self._starts = None
         return self._out, self._seg_starts, self._seg_counts
 

@@ -342,8 +342,15 @@ int dfd_exchange_wait(dfd_exchange* x, int64_t* part_starts_host);
  *   rows [seg_starts[q*T + r], +seg_counts[q*T + r]) of every out column (T = workers).  If any sub-window
  *   overflowed on any worker (skew), collect re-runs the shuffle through the exact two-pass fused path on every
  *   worker (all see the same flags) and rewrites out_cols (may be NULL if the caller keeps the originals) — the
- *   segments then describe that dense layout.  Fixed-width non-null columns and <= 256 partitions take the
- *   single-pass kernel; anything else is routed to the two-pass fused path with the same (segments) result. */
+ *   segments then describe that dense layout.
+ * Column kinds: fixed-width non-null columns with <= 256 partitions take the single-pass kernel.  Nullable, boolean and
+ * Utf8 / LargeUtf8 / Binary columns (every kind dfd_partition_device moves) take the PUSH transport, also NCCL-free:
+ * local partition -> flag-based all-gather of the row / byte counts -> each destination's contiguous runs (values,
+ * shifted bitmaps, re-based string offsets, string bytes) are stored into the owner's window by k_push_runs.  There a
+ * segment starts on a 32-row boundary; out_cols[c].offsets / .validity are set like .values, and the string offsets
+ * of a segment index the column's single `values` byte buffer directly (Arrow layout, zero-copy sliceable).  ON
+ * ENTRY out_cols[c].validity != NULL marks column c as nullable in the SCHEMA (all workers must agree), whether or
+ * not this worker's rows contain nulls; in_cols[c].values_bytes must hold the byte size of a string column's data. */
 int dfd_shuffle_device_onepass(dfd_exchange* x, dfd_partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,
                                uint32_t partitions_per_task, dfd_column* out_cols);
 int dfd_exchange_collect(dfd_exchange* x, dfd_column* out_cols, int64_t* seg_starts, int64_t* seg_counts);

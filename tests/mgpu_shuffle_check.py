@@ -169,6 +169,26 @@ def main():
                 failures += 1
                 print(f"rank {rank}: MISMATCH nccl mixed q={q} col={c} {arr.type}", flush=True)
     dist.barrier()
+    # push transport (NCCL-free) with the same nullable / boolean / string table: per (partition, producer) segment, in place
+    node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0, 1], P2), uuid.uuid4(), 6, world, world)
+    for rep in range(2):
+        node.shuffle_onepass(ex, in_cols2, mhi - mlo, nullable=[True] * len(arrays))
+        outs3, seg_starts, seg_counts = node.collect(ex)
+        for q in range(P2):
+            g = rank * P2 + q
+            for r in range(world):
+                rlo, rhi = r * m // world, (r + 1) * m // world
+                want_idx = np.nonzero(dest2[rlo:rhi] == g)[0] + rlo
+                if int(seg_counts[q, r]) != len(want_idx):
+                    failures += 1
+                    print(f"rank {rank}: COUNT MISMATCH push q={q} r={r}", flush=True)
+                    continue
+                for c, arr in enumerate(arrays):
+                    got = dfd.NetworkShuffleExec.segment_to_arrow(ctx, outs3[c], int(seg_starts[q, r]), int(seg_counts[q, r]))
+                    if not got.equals(arr.take(pa.array(want_idx))):
+                        failures += 1
+                        print(f"rank {rank}: MISMATCH push rep={rep} q={q} r={r} col={c} {arr.type}", flush=True)
+        dist.barrier()
     # host-to-host pipelined shuffle: row-set equality per destination (chunk-major output)
     P, N = 8 // world if 8 % world == 0 else 1, (8 // world if 8 % world == 0 else 1) * world
     ref, rc, rs = orc.repartition_table(cols, [0], N, 8192, 1)

@@ -180,3 +180,51 @@ def test_single_worker_nccl_mode_moves_every_column_kind(ctx):
     for c, arr in enumerate(arrays):
         assert outs[c].to_arrow(ctx, 0, n).equals(arr.take(idx)), (c, arr.type)
     ex.close()
+
+
+def test_single_worker_push_transport_moves_every_column_kind(ctx):
+    """NCCL-free push transport (nullable / boolean / string columns; keys Int64 + Utf8) at world=1: every partition's
+    single segment equals the oracle's rows in order, read in place from the window as Arrow buffers."""
+    import pyarrow as pa
+
+    from tests.util import expected_partitions
+
+    n, P = 20_011, 6
+    arrays = _mixed_table(n, 17)
+    ex = dfd.ShuffleExchange(ctx, 0, 1, None)
+    ex.setup_window(8 << 20)
+    node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0, 1], P), uuid.uuid4(), 1, 1, 1)
+    in_cols = [dfd.DeviceColumn.from_arrow(ctx, a) for a in arrays]
+    dest = orc.partition_ids([arrays[0], arrays[1]], n, P)
+    order, ref_starts = expected_partitions(dest, P)
+    for rep in range(2):
+        node.shuffle_onepass(ex, in_cols, n, nullable=[True] * len(arrays))
+        outs, seg_starts, seg_counts = node.collect(ex)
+        assert np.array_equal(seg_counts[:, 0], np.diff(ref_starts))
+        assert (seg_starts % 32 == 0).all()
+        for q in range(P):
+            idx = pa.array(order[ref_starts[q]:ref_starts[q + 1]])
+            for c, arr in enumerate(arrays):
+                got = dfd.NetworkShuffleExec.segment_to_arrow(ctx, outs[c], int(seg_starts[q, 0]), int(seg_counts[q, 0]))
+                assert got.equals(arr.take(idx)), (rep, q, c, arr.type)
+    # sliced inputs (Arrow offset != 0) and an empty worker
+    sl = [a.slice(13, 9000) for a in arrays]
+    node.shuffle_onepass(ex, [dfd.DeviceColumn.from_arrow(ctx, a) for a in sl], 9000, nullable=[True] * len(arrays))
+    outs, seg_starts, seg_counts = node.collect(ex)
+    d2 = orc.partition_ids([sl[0], sl[1]], 9000, P)
+    o2, s2 = expected_partitions(d2, P)
+    for q in range(P):
+        for c, arr in enumerate(sl):
+            got = dfd.NetworkShuffleExec.segment_to_arrow(ctx, outs[c], int(seg_starts[q, 0]), int(seg_counts[q, 0]))
+            assert got.equals(arr.take(pa.array(o2[s2[q]:s2[q + 1]]))), (q, c)
+    node.shuffle_onepass(ex, [dfd.DeviceColumn.from_arrow(ctx, a.slice(0, 0)) for a in arrays], 0, nullable=[True] * len(arrays))
+    outs, seg_starts, seg_counts = node.collect(ex)
+    assert not seg_counts.any()
+    # window too small: reported, consistent on every worker
+    ex2 = dfd.ShuffleExchange(ctx, 0, 1, None)
+    ex2.setup_window(64 << 10)
+    with pytest.raises(dfd.DfdError) as e:
+        node.shuffle_onepass(ex2, in_cols, n, nullable=[True] * len(arrays))
+    assert e.value.status == 7
+    ex.close()
+    ex2.close()
