@@ -550,3 +550,133 @@ def run_multi_gpu(args, torch, dfd, world):
     dist.destroy_process_group()
 
 
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=N_ROWS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-soak", action="store_true", help="skip the untimed clock soak (use under ncu)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the worker to its GPU's NUMA node")
+    ap.add_argument("--e2e-batch-rows", type=int, default=1 << 20)
+    ap.add_argument("--e2e-chunk-rows", type=int, default=1 << 20)
+    ap.add_argument("--exchange", default="onepass", choices=["onepass", "fused", "nccl"],
+                    help="multi-GPU transport: single-pass fused (peer stores + peer-memory flags), two-pass fused, or NCCL send/recv")
+    ap.add_argument("--parity-rows", type=int, default=1 << 21, help="rows of the multi-GPU bit-parity check run before the timed region")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="cfg2 = the BASELINE.json headline (default; what the driver runs); cfg3/4/5 = the other configs (bench_workloads.py)")
+    ap.add_argument("--kernel", default="onepass", choices=["onepass", "twopass"],
+                    help="1-GPU partition path: single-pass k_scatter<ONEPASS> (regions) or K1/K1b/K2 (dense)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.workload == "cfg4":
+            import bench_workloads
+
+            return bench_workloads.run_reference_cfg4(args)
+        return run_reference(args)
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    orig_affinity, numa_note = (None, "numa: binding disabled") if args.no_numa_bind else bind_to_gpu_numa_node(local_rank)
+    args.numa_note = numa_note
+    args.orig_affinity = orig_affinity
+
+    import torch
+
+    import datafusion_distributed_b200 as dfd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload != "cfg2":
+        import bench_workloads
+
+        return bench_workloads.run(args, torch, dfd, world)
+    if world > 1:
+        return run_multi_gpu(args, torch, dfd, world)
+    if args.gpus != 1:
+        raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    dev = 0
+    torch.cuda.set_device(dev)
+    n = args.rows
+    g = torch.Generator(device="cuda").manual_seed(42)
+    key = torch.randint(-(2**63), 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+    rid = torch.arange(n, dtype=torch.int64, device="cuda")
+    ins = [key] + [rid * 8 + j for j in range(1, N_COLS)]
+    del rid
+    ctx = dfd.WorkerContext(dev)
+    part = dfd.HashPartitioner(ctx, dfd.Partitioning.Hash([0], NUM_PARTITIONS))
+    onepass = args.kernel == "onepass"
+    region_rows = part.default_region_rows(n) if onepass else 0  # fair share + 25 % per destination
+    outs = [torch.empty(NUM_PARTITIONS * region_rows if onepass else n, dtype=torch.int64, device="cuda") for _ in ins]
+    torch.cuda.synchronize()
+    in_cols = [dfd.DeviceColumn.from_torch(t) for t in ins]
+    out_cols = [dfd.DeviceColumn.from_torch(t) for t in outs]
+
+    def one_step():
+        if onepass:
+            part.partition_onepass(in_cols, n, region_rows, out_cols, sync=False)
+        else:
+            part.partition(in_cols, n, out_cols, sync=False)
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    ctx.synchronize()
+    ctx.reset_metrics()
+    ctx.set_profiling(True)
+    # inputs (4 GiB) + outputs (4 GiB) are far larger than the 126 MB L2: no flush needed between steps
+    with ClockSampler(dev) as clocks:
+        if not args.no_soak:
+            soak(one_step, 1.0, ctx.synchronize)
+        ctx.reset_metrics()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            one_step()
+        ms_total = ctx.timer_stop()
+    m = ctx.metrics()
+    if onepass:
+        _, counts = part.collect()
+        assert int(counts.sum()) == n and ctx.metrics()["onepass_reruns"] == 0, "a destination region overflowed inside the timed loop"
+    ctx.set_profiling(False)
+    ms_per_step = ms_total / args.steps
+    value = n / (ms_per_step / 1e3)
+
+    peak, peak_src = measured_peaks()
+    alg_bytes = 2.0 * N_COLS * WIDTH * n
+    scatter_ms = m["scatter_ms"] / max(m["scatter_launches"], 1)
+    achieved = alg_bytes / (scatter_ms / 1e3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int64", "data": "synthetic",
+        "config": {"workload": "cfg2: 2^26 rows x 8 Int64, Hash([col0], 8), device-resident table", "rows": n,
+                   "columns": N_COLS, "num_partitions": NUM_PARTITIONS, "l2": "inputs+outputs (8 GiB) >> L2, no flush",
+                   "kernel_path": ("single pass: k_scatter<ONEPASS> (hash once, decoupled look-back, per-destination regions of "
+                                   f"{region_rows} rows)") if onepass else "two pass: k_tile_hist -> k_scan_tiles -> k_scatter (dense)"},
+        "roofline": {"bound": "hbm", "kernel": "k_scatter<ONEPASS>" if onepass else "k_scatter", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_source": peak_src,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one k_scatter launch at this exact workload,
+                     # from the committed `ncu --set full` capture profiles/r01c_ncu_summary.md (8.59 GB algorithmic)
+                     "traffic": (TRAFFIC_ONEPASS if onepass else 8.576116e9) if n == N_ROWS else None, "traffic_unit": "bytes/launch",
+                     "traffic_source": "profiles/r02a_ncu_summary.md" if onepass else "profiles/r01c_ncu_summary.md",
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scatter_ms,
+                     "hist_ms": m["hist_ms"] / max(m["calls"], 1), "scan_ms": m["scan_ms"] / max(m["calls"], 1)},
+        "gpu_launches": int(m["kernel_launches"]),
+        "clocks": clocks.summary(),
+        "e2e": None,
+    }
+    if not args.no_e2e:
+        line["e2e"] = run_e2e(ctx, dfd, n, args)
+        line["gpu_launches"] = int(ctx.metrics()["kernel_launches"])
+    line["config"]["host"] = args.numa_note
+    if not args.no_cpu_baseline:
+        if args.orig_affinity:
+            os.sched_setaffinity(0, args.orig_affinity)  # the CPU baseline uses every host core
+        v, ms_cpu, steps_cpu, info = cpu_pool_arm(n, 3, 1, 25.0)
+        line["cpu_baseline"] = dict({"value": v, "unit": "rows/s", "cores": info["threads_used"], "host_cores": os.cpu_count() or 1, "kind": "port",
+                                     "sample": f"full {n}-row table, mean of {steps_cpu} passes after 1 warm-up; {CPU_WHAT}"}, **info)
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

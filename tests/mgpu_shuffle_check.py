@@ -101,7 +101,7 @@ def main():
     hot_t = [torch.from_numpy(c).cuda() for c in hot]
     torch.cuda.synchronize()
     hot_cols = [dfd.DeviceColumn.from_torch(t) for t in hot_t]
-    P = 2
+    P = 8  # 8 x world sub-windows per consumer: the hot destination's sub-window (1/(8 x world) of the rows) overflows
     node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0], P), uuid.uuid4(), 5, world, world)
     fb0 = nv.lib().dfd_exchange_onepass_fallbacks(ex._h)
     try:
