@@ -321,7 +321,7 @@ def run_e2e(ctx, dfd, n, args):
             "api": "RepartitionExec.push_batch/finish/execute(partition) over dfd_repartition_exec_* (Arrow C Data / C Stream)"}
 
 
-TRAFFIC_ONEPASS = None  # dram bytes of one k_scatter<ONEPASS> launch at cfg-2 (ncu --set full), filled from profiles/r02a
+TRAFFIC_ONEPASS = 8.564484e9  # dram__bytes_read.sum + dram__bytes_write.sum of one k_scatter_onepass launch at cfg-2 (profiles/r02c_ncu_summary.md)
 NVLINK_PEAK_GBS = 770.0  # measured peer copy per direction per GPU on this pool (B200_PROFILING.md; nominal 900)
 
 
@@ -651,14 +651,14 @@ def main():
         "dtype": "int64", "data": "synthetic",
         "config": {"workload": "cfg2: 2^26 rows x 8 Int64, Hash([col0], 8), device-resident table", "rows": n,
                    "columns": N_COLS, "num_partitions": NUM_PARTITIONS, "l2": "inputs+outputs (8 GiB) >> L2, no flush",
-                   "kernel_path": ("single pass: k_scatter<ONEPASS> (hash once, decoupled look-back, per-destination regions of "
+                   "kernel_path": ("single pass: k_scatter_onepass (TMA-fed ring, hash once, decoupled look-back, per-destination regions of "
                                    f"{region_rows} rows)") if onepass else "two pass: k_tile_hist -> k_scan_tiles -> k_scatter (dense)"},
-        "roofline": {"bound": "hbm", "kernel": "k_scatter<ONEPASS>" if onepass else "k_scatter", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_scatter_onepass" if onepass else "k_scatter", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one k_scatter launch at this exact workload,
                      # from the committed `ncu --set full` capture profiles/r01c_ncu_summary.md (8.59 GB algorithmic)
                      "traffic": (TRAFFIC_ONEPASS if onepass else 8.576116e9) if n == N_ROWS else None, "traffic_unit": "bytes/launch",
-                     "traffic_source": "profiles/r02a_ncu_summary.md" if onepass else "profiles/r01c_ncu_summary.md",
+                     "traffic_source": "profiles/r02c_ncu_summary.md" if onepass else "profiles/r01c_ncu_summary.md",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scatter_ms,
                      "hist_ms": m["hist_ms"] / max(m["calls"], 1), "scan_ms": m["scan_ms"] / max(m["calls"], 1)},
         "gpu_launches": int(m["kernel_launches"]),

@@ -18,7 +18,7 @@ OUT_DIR = os.path.join(HERE, "_lib")
 OBJ_DIR = os.environ.get("DFD_OBJ_DIR", "/tmp/dfd_b200_obj")  # object cache lives outside the repo (gpurun ships the tree)
 
 SOURCES = ["dfd_api.cu", "dfd_exec.cu", "dfd_exchange.cu", "dfd_scatter_twopass_local.cu", "dfd_scatter_twopass_peer.cu",
-           "dfd_scatter_onepass_local.cu", "dfd_scatter_onepass_peer.cu"]
+           "dfd_scatter_onepass_local.cu", "dfd_scatter_onepass_peer.cu", "dfd_scatter_follow_local.cu", "dfd_scatter_follow_peer.cu"]
 TUNABLE = {s for s in SOURCES if s.startswith("dfd_scatter_") or s == "dfd_api.cu"}  # sources that see the tile-geometry macros
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False, defs: str | None = None, t
     inc = ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
 
     def compile_one(src: str) -> str:
-        flags = NVCC_FLAGS + (extra if src in TUNABLE else []) + (extra_onepass if "onepass" in src else []) + (["-Xptxas", "-v"] if verbose else [])
+        flags = NVCC_FLAGS + (extra if src in TUNABLE else []) + (extra_onepass if ("onepass" in src or "follow" in src or src == "dfd_api.cu") else []) + (["-Xptxas", "-v"] if verbose else [])
         key = hashlib.sha1(" ".join(flags).encode()).hexdigest()[:10]
         obj = os.path.join(OBJ_DIR, f"{os.path.splitext(src)[0]}.{key}.o")
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < newest:

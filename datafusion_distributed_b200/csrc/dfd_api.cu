@@ -129,10 +129,13 @@ bool dfd::use_aligned(uint32_t N, bool peer) {
     return forced >= 0 ? forced == 1 : peer;
 }
 
-static int launch_scatter(const ScatterParams& sp, int width, bool fast, bool peer, bool onepass, int sm_count, size_t smem,
+// mode: 0 two-pass, 1 single-pass, 2 follow-up of a single-pass launch (see dfd_launch.cuh)
+static int launch_scatter(const ScatterParams& sp, int width, bool fast, bool peer, int mode, int sm_count, size_t smem,
                           cudaStream_t stream) {
-    if (onepass) return peer ? launch_scatter_onepass_peer(sp, width, fast, sm_count, smem, stream)
-                             : launch_scatter_onepass_local(sp, width, fast, sm_count, smem, stream);
+    if (mode == 1) return peer ? launch_scatter_onepass_peer(sp, width, fast, sm_count, smem, stream)
+                               : launch_scatter_onepass_local(sp, width, fast, sm_count, smem, stream);
+    if (mode == 2) return peer ? launch_scatter_follow_peer(sp, width, fast, sm_count, smem, stream)
+                               : launch_scatter_follow_local(sp, width, fast, sm_count, smem, stream);
     return peer ? launch_scatter_twopass_peer(sp, width, fast, sm_count, smem, stream)
                 : launch_scatter_twopass_local(sp, width, fast, sm_count, smem, stream);
 }
@@ -248,7 +251,8 @@ int dfd::PartitionJob::prepare(Partitioner* part, const dfd_column* in_cols, int
         ip.width = 4;
         passes.push_back(ip);
     }
-    n_tiles = n_rows > 0 ? (n_rows + TILE_ROWS - 1) / TILE_ROWS : 1;
+    const int64_t tile_rows = onepass_tiling ? ONEPASS_ROWS : TILE_ROWS;
+    n_tiles = n_rows > 0 ? (n_rows + tile_rows - 1) / tile_rows : 1;
     // scratch: hist u32 [N][n_tiles] | tile_base u32 [N][n_tiles] | totals i64 [N] | done u32
     size_t hist_bytes = (((size_t)N * n_tiles * 4) + 255) & ~(size_t)255;
     size_t tot_bytes = (((size_t)N * 8) + 255) & ~(size_t)255;
@@ -351,7 +355,7 @@ int dfd::PartitionJob::run_scatter(const int64_t* dest_base, void* const* peer_b
                 size_t n = group.size() - first < (size_t)MAX_COLS_PER_LAUNCH ? group.size() - first : (size_t)MAX_COLS_PER_LAUNCH;
                 for (size_t i = 0; i < n; ++i) sp.cols[i] = group[first + i];
                 sp.n_cols = (int32_t)n;
-                int rc = launch_scatter(sp, width, ks.fast_i64 != 0, peer, false, c->sm_count, smem, stream);
+                int rc = launch_scatter(sp, width, ks.fast_i64 != 0, peer, 0, c->sm_count, smem, stream);
                 if (rc) return rc;
                 ++launches;
             }
@@ -451,14 +455,14 @@ int dfd::PartitionJob::run_onepass(const OnePassLayout& L) {
                     const bool more = n_groups > 1 || group.size() > (size_t)MAX_COLS_PER_LAUNCH;
                     sp.hist_out = more ? d_hist : nullptr;
                     sp.base_out = more ? d_base : nullptr;
-                    rc = launch_scatter(sp, width, ks.fast_i64 != 0 && width == 8, peer, true, c->sm_count, smem, stream);
+                    rc = launch_scatter(sp, width, ks.fast_i64 != 0 && width == 8, peer, 1, c->sm_count, smem, stream);
                     first = false;
                     // the follow-up launches take the two-pass code path over the counts / cursors just written
                     sp.hist = d_hist;
                     sp.tile_base = d_base;
                     sp.abort_flag = L.d_overflow;
                 } else {
-                    rc = launch_scatter(sp, width, ks.fast_i64 != 0, peer, false, c->sm_count, smem, stream);
+                    rc = launch_scatter(sp, width, ks.fast_i64 != 0, peer, 2, c->sm_count, smem, stream);
                 }
                 if (rc) return rc;
                 ++launches;
@@ -871,6 +875,7 @@ static int onepass_launch_locked(dfd_partitioner* p, const int64_t* d_base, cons
     cudaError_t e = cudaMemsetAsync(d_flag, 0, sizeof(int64_t), c->stream);
     if (e != cudaSuccess) return cuda_error(e, "cudaMemsetAsync(overflow flag)");
     PartitionJob job;
+    job.onepass_tiling = true;
     job.out_rows = stride > 0 ? stride * (int64_t)N : p->last_rows;  // region layout spans N * region_rows output rows
     int rc = job.prepare(p, p->last_in.data(), (int)p->last_in.size(), p->last_rows, p->last_out.data(), false, c->stream);
     if (rc) return rc;

@@ -698,6 +698,7 @@ static int onepass_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const 
     CUDA_TRY(cudaMemsetAsync(x->d_flags, 0, 8, s), "memset flags");
     int rc;
     PartitionJob job;
+    job.onepass_tiling = true;
     if ((rc = job.prepare(part, in_cols, n_cols, n_rows, outs.data(), true, s))) return rc;
     PartitionJob::OnePassLayout L;
     L.region_stride = sub_cap;

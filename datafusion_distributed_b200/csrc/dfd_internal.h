@@ -83,6 +83,7 @@ struct PartitionJob {
     unsigned long long* d_block_sums = nullptr;
     uint64_t bytes = 0;
     int64_t n_rows = 0, n_tiles = 0;
+    bool onepass_tiling = false;         // set before prepare(): tile the rows for the single-pass kernel (ONEPASS_K rows per thread)
     int64_t out_rows = -1;               // rows of the OUTPUT row space (-1: n_rows; single-pass regions: N * region_rows)
     uint32_t* d_hist = nullptr;
     uint32_t* d_base = nullptr;
@@ -127,6 +128,8 @@ int launch_scatter_twopass_local(const ScatterParams& sp, int width, bool fast, 
 int launch_scatter_twopass_peer(const ScatterParams& sp, int width, bool fast, int sm_count, size_t smem, cudaStream_t stream);
 int launch_scatter_onepass_local(const ScatterParams& sp, int width, bool fast, int sm_count, size_t smem, cudaStream_t stream);
 int launch_scatter_onepass_peer(const ScatterParams& sp, int width, bool fast, int sm_count, size_t smem, cudaStream_t stream);
+int launch_scatter_follow_local(const ScatterParams& sp, int width, bool fast, int sm_count, size_t smem, cudaStream_t stream);
+int launch_scatter_follow_peer(const ScatterParams& sp, int width, bool fast, int sm_count, size_t smem, cudaStream_t stream);
 
 // Launches K1 -> K1b -> K2 on `stream`; caller holds ctx->mu and has set the device.
 int partition_device_locked(Partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,

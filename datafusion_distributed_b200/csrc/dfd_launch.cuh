@@ -24,11 +24,16 @@ namespace dfd {
 #endif
 // single-pass kernel: ring depth (tiles in flight per CTA) and resident CTAs per SM
 #ifndef DFD_ONEPASS_NB
-#define DFD_ONEPASS_NB 3
+#define DFD_ONEPASS_NB 2
 #endif
 #ifndef DFD_ONEPASS_MIN_CTAS
 #define DFD_ONEPASS_MIN_CTAS 4
 #endif
+#ifndef DFD_ONEPASS_K
+#define DFD_ONEPASS_K 10  // rows per consumer thread per tile (tile = 256 x K rows): larger tiles amortise ranking / look-back
+#endif
+constexpr int ONEPASS_K = DFD_ONEPASS_K;
+constexpr int FOLLOW_MIN_CTAS = 4;  // follow-up k_scatter launches on the single-pass tiling
 constexpr int ONEPASS_NB = DFD_ONEPASS_NB;
 constexpr int ONEPASS_MIN_CTAS = DFD_ONEPASS_MIN_CTAS;
 constexpr int TILE_THREADS = DFD_TILE_THREADS;
@@ -38,17 +43,23 @@ constexpr int TILE_MIN_CTAS = DFD_TILE_MIN_CTAS;
 constexpr uint32_t ALIGNED_MAX_N = 16;
 constexpr int TILE_KV = TILE_K + (62 * (int)ALIGNED_MAX_N + TILE_THREADS - 1) / TILE_THREADS;
 constexpr int TILE_ROWS = TILE_THREADS * TILE_K;
+constexpr int ONEPASS_KV = ONEPASS_K + (62 * (int)ALIGNED_MAX_N + TILE_THREADS - 1) / TILE_THREADS;
+constexpr int ONEPASS_ROWS = TILE_THREADS * ONEPASS_K;
 
 
-template <bool FAST, typename V, bool PEER, int KV, bool ONEPASS>
+// MODE: 0 = two-pass k_scatter on the K1 tiling (TILE_K); 1 = single-pass k_scatter_onepass (ONEPASS_K);
+//       2 = "follow-up" k_scatter on the SINGLE-PASS tiling: further column-width groups / bit columns of a single-pass
+//           call, driven by the per-tile counts and cursors the single-pass launch left in hist_out / base_out
+template <bool FAST, typename V, bool PEER, bool ALIGNED, int MODE>
 static int launch_scatter_kv(const ScatterParams& sp, int sm_count, size_t smem, cudaStream_t stream) {
     cudaError_t e;
-    if constexpr (ONEPASS) {
+    if constexpr (MODE == 1) {
         if constexpr (std::is_same<V, BitColumn>::value) {
             return set_error(DFD_ERR_INTERNAL, "bit-packed columns take the two-pass k_scatter");
         } else {
-            auto kern = k_scatter_onepass<TILE_THREADS, TILE_K, KV, ONEPASS_NB, ONEPASS_MIN_CTAS, FAST, V, PEER>;
-            smem = onepass_smem_bytes<TILE_THREADS, TILE_K, ONEPASS_NB>(sp.N, (int)sizeof(V), PEER, KV != TILE_K);
+            constexpr int KV = ALIGNED ? ONEPASS_KV : ONEPASS_K;
+            auto kern = k_scatter_onepass<TILE_THREADS, ONEPASS_K, KV, ONEPASS_NB, ONEPASS_MIN_CTAS, FAST, V, PEER>;
+            smem = onepass_smem_bytes<TILE_THREADS, ONEPASS_K, ONEPASS_NB>(sp.N, (int)sizeof(V), PEER, ALIGNED);
             if (smem > 227 * 1024) return set_error(DFD_ERR_UNSUPPORTED, "single-pass kernel needs %zu B of shared memory per CTA", smem);
             // (static per instantiation: the attribute and the occupancy are properties of the kernel + smem size)
             static thread_local size_t cfg_smem = 0;
@@ -66,7 +77,12 @@ static int launch_scatter_kv(const ScatterParams& sp, int sm_count, size_t smem,
             kern<<<(unsigned)grid, TILE_THREADS + 32, smem, stream>>>(sp);
         }
     } else {
-        auto kern = k_scatter<TILE_THREADS, TILE_K, KV, TILE_MIN_CTAS, FAST, V, PEER>;
+        constexpr int K = MODE == 2 ? ONEPASS_K : TILE_K;
+        constexpr int KV = ALIGNED ? (MODE == 2 ? ONEPASS_KV : TILE_KV) : K;
+        constexpr int CTAS = MODE == 2 ? FOLLOW_MIN_CTAS : TILE_MIN_CTAS;
+        auto kern = k_scatter<TILE_THREADS, K, KV, CTAS, FAST, V, PEER>;
+        if (MODE == 2) smem = scatter_smem_bytes<TILE_THREADS, ONEPASS_K>(sp.N, sp.stage_width, PEER, ALIGNED);
+        if (smem > 227 * 1024) return set_error(DFD_ERR_UNSUPPORTED, "k_scatter needs %zu B of shared memory per CTA", smem);
         if (smem > 48 * 1024) {
             if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
                 return cuda_error(e, "cudaFuncSetAttribute(k_scatter)");
@@ -77,34 +93,34 @@ static int launch_scatter_kv(const ScatterParams& sp, int sm_count, size_t smem,
     return e == cudaSuccess ? DFD_OK : cuda_error(e, "k_scatter");
 }
 
-template <bool FAST, typename V, bool PEER, bool ONEPASS>
+template <bool FAST, typename V, bool PEER, int MODE>
 static int launch_scatter_t(const ScatterParams& sp, int sm_count, size_t smem, cudaStream_t stream) {
-    if (use_aligned(sp.N, PEER)) return launch_scatter_kv<FAST, V, PEER, TILE_KV, ONEPASS>(sp, sm_count, smem, stream);
-    return launch_scatter_kv<FAST, V, PEER, TILE_K, ONEPASS>(sp, sm_count, smem, stream);
+    if (use_aligned(sp.N, PEER)) return launch_scatter_kv<FAST, V, PEER, true, MODE>(sp, sm_count, smem, stream);
+    return launch_scatter_kv<FAST, V, PEER, false, MODE>(sp, sm_count, smem, stream);
 }
 
-template <bool FAST, bool PEER, bool ONEPASS>
+template <bool FAST, bool PEER, int MODE>
 static int launch_scatter_w(const ScatterParams& sp, int width, int sm_count, size_t smem, cudaStream_t stream) {
     switch (width) {
-        case 8: return launch_scatter_t<FAST, uint64_t, PEER, ONEPASS>(sp, sm_count, smem, stream);
-        case 4: return launch_scatter_t<FAST, uint32_t, PEER, ONEPASS>(sp, sm_count, smem, stream);
-        case 2: return launch_scatter_t<FAST, uint16_t, PEER, ONEPASS>(sp, sm_count, smem, stream);
-        case 1: return launch_scatter_t<FAST, uint8_t, PEER, ONEPASS>(sp, sm_count, smem, stream);
-        case 16: return launch_scatter_t<FAST, uint4, PEER, ONEPASS>(sp, sm_count, smem, stream);
+        case 8: return launch_scatter_t<FAST, uint64_t, PEER, MODE>(sp, sm_count, smem, stream);
+        case 4: return launch_scatter_t<FAST, uint32_t, PEER, MODE>(sp, sm_count, smem, stream);
+        case 2: return launch_scatter_t<FAST, uint16_t, PEER, MODE>(sp, sm_count, smem, stream);
+        case 1: return launch_scatter_t<FAST, uint8_t, PEER, MODE>(sp, sm_count, smem, stream);
+        case 16: return launch_scatter_t<FAST, uint4, PEER, MODE>(sp, sm_count, smem, stream);
         default:
-            if constexpr (PEER || ONEPASS) {
-                return set_error(DFD_ERR_INTERNAL, "bit-packed columns take the two-pass local k_scatter instantiation");
+            if constexpr (PEER || MODE == 1) {
+                return set_error(DFD_ERR_INTERNAL, "bit-packed columns take the local k_scatter instantiation");
             } else {
-                return launch_scatter_t<FAST, BitColumn, false, false>(sp, sm_count, smem, stream);
+                return launch_scatter_t<FAST, BitColumn, false, MODE>(sp, sm_count, smem, stream);
             }
     }
 }
 
 // one definition per translation unit (dfd_scatter_*.cu)
-template <bool PEER, bool ONEPASS>
+template <bool PEER, int MODE>
 int launch_scatter_impl(const ScatterParams& sp, int width, bool fast, int sm_count, size_t smem, cudaStream_t stream) {
-    return fast ? launch_scatter_w<true, PEER, ONEPASS>(sp, width, sm_count, smem, stream)
-                : launch_scatter_w<false, PEER, ONEPASS>(sp, width, sm_count, smem, stream);
+    return fast ? launch_scatter_w<true, PEER, MODE>(sp, width, sm_count, smem, stream)
+                : launch_scatter_w<false, PEER, MODE>(sp, width, sm_count, smem, stream);
 }
 
 }  // namespace dfd
