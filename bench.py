@@ -129,6 +129,27 @@ def bind_to_gpu_numa_node(index: int):
         return None, f"numa: not bound ({type(e).__name__})"
 
 
+def nvlink_bytes(index: int):
+    """(tx_bytes, rx_bytes) summed over the NVLink links of GPU `index`, from `nvidia-smi nvlink -gt d`; None if unavailable."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
+        tx = rx = 0
+        seen = False
+        for line in out.splitlines():
+            line = line.strip()
+            if "Data Tx:" in line or "Data Rx:" in line:
+                val = line.split(":")[-1].strip().split()
+                n = float(val[0]) * {"KiB": 1024, "MiB": 1 << 20, "GiB": 1 << 30, "B": 1}.get(val[1] if len(val) > 1 else "KiB", 1024)
+                seen = True
+                if "Tx" in line:
+                    tx += n
+                else:
+                    rx += n
+        return (tx, rx) if seen else None
+    except Exception:
+        return None
+
+
 def soak(step, seconds: float, sync):
     """Untimed repetitions of the step so clocks/thermals are at steady state and the sampler sees load."""
     t0 = time.perf_counter()
@@ -490,6 +511,29 @@ def run_multi_gpu(args, torch, dfd, world):
     launches = torch.tensor([int(ctx.metrics()["kernel_launches"])], dtype=torch.int64, device="cuda")
     dist.all_reduce(launches)
     fallbacks = int(nv.lib().dfd_exchange_onepass_fallbacks(ex._h))
+    # phase split of the step (separate, untimed loop with per-phase CUDA events) + NVLink byte counters around it
+    phases = None
+    nvl = None
+    if mode is None:
+        import ctypes as C
+
+        nv0 = nvlink_bytes(local_rank)
+        ctx.set_profiling(True)
+        k_prof = 50
+        timed_steps(k_prof)
+        out3, cnt = (C.c_double * 3)(), C.c_uint64()
+        nv.check(nv.lib().dfd_exchange_phase_ms(ex._h, out3, C.byref(cnt)))
+        ctx.set_profiling(False)
+        nv1 = nvlink_bytes(local_rank)
+        ph = torch.tensor(list(out3), dtype=torch.float64, device="cuda")
+        ph_max = ph.clone()
+        dist.all_reduce(ph_max, op=dist.ReduceOp.MAX)
+        phases = {"signal_ready_ms": ph_max[0].item(), "scatter_ms": ph_max[1].item(), "publish_wait_ms": ph_max[2].item(),
+                  "rank0": {"signal_ready_ms": out3[0], "scatter_ms": out3[1], "publish_wait_ms": out3[2]},
+                  "how": f"CUDA events around the three stream phases of {int(cnt.value)} untimed shuffles; max over ranks"}
+        if nv0 and nv1:
+            nvl = {"tx_bytes_per_shuffle": (nv1[0] - nv0[0]) / k_prof, "rx_bytes_per_shuffle": (nv1[1] - nv0[1]) / k_prof,
+                   "source": "nvidia-smi nvlink -gt d (sum over links of this GPU), rank 0, around the untimed phase-timing loop"}
 
     # e2e: host (pinned) rows in, host rows out, per worker, through dfd_shuffle_host: chunked
     # H2D | fused shuffle | D2H pipeline (every chunk is one collective), wall clock, max over ranks
@@ -541,7 +585,9 @@ def run_multi_gpu(args, torch, dfd, world):
                                                         "fused": "k_scatter<PEER> (two-pass; ncclAllGather(counts) + ncclAllReduce barrier)",
                                                         "nccl": "ncclSend/Recv"}[args.exchange],
                          "achieved": achieved, "peak": NVLINK_PEAK_GBS, "unit": "GB/s", "frac": achieved / NVLINK_PEAK_GBS,
-                         "peak_source": "measured peer copy per direction (B200_PROFILING.md); nominal 900", "traffic": None,
+                         "peak_source": "measured peer copy per direction (B200_PROFILING.md); nominal 900",
+                         "traffic": (nvl["tx_bytes_per_shuffle"] if nvl else None), "traffic_unit": "NVLink Tx bytes per shuffle (rank 0)",
+                         "nvlink_counters": nvl, "phases": phases,
                          "algorithmic_bytes_per_gpu_per_direction": alg},
             "gpu_launches": int(launches.item()), "clocks": clocks.summary(), "e2e": e2e,
         }

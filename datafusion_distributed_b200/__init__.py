@@ -10,12 +10,13 @@ from . import _native
 from ._native import DfdError, LIB_PATH
 from .device import DeviceBuffer, DeviceColumn, WorkerContext
 from .execution_plans import PinnedTable, RepartitionExec
-from .network_shuffle import (DistributedTaskContext, ExecutionTask, NetworkShuffleExec, ShuffleExchange, Stage,
-                              exchange_plan, nccl_unique_id)
+from .network_shuffle import (DistributedTaskContext, ExecutionTask, NetworkBroadcastExec, NetworkCoalesceExec, NetworkShuffleExec,
+                              ShuffleExchange, Stage, exchange_plan, nccl_unique_id, task_group)
 from .partitioner import HashPartitioner, Partitioning, scale_partitioning
 
 __all__ = [
     "DfdError", "LIB_PATH", "DeviceBuffer", "DeviceColumn", "WorkerContext",
     "HashPartitioner", "Partitioning", "scale_partitioning", "RepartitionExec", "PinnedTable",
     "DistributedTaskContext", "ExecutionTask", "NetworkShuffleExec", "ShuffleExchange", "Stage", "exchange_plan", "nccl_unique_id",
+    "NetworkCoalesceExec", "NetworkBroadcastExec", "task_group",
 ]

@@ -22,6 +22,7 @@ STATUS = {
 
 COL_FIXED, COL_BOOL, COL_UTF8, COL_LARGE_UTF8, COL_BINARY = 0, 1, 2, 3, 4
 EXCHANGE_NCCL, EXCHANGE_FUSED = 0, 1
+ROUTE_SHUFFLE, ROUTE_COALESCE, ROUTE_BROADCAST = 0, 1, 2
 KEY_HASH_PLAIN, KEY_HASH_INTERVAL_DAY_TIME, KEY_HASH_INTERVAL_MONTH_DAY_NANO = 0, 1, 2
 
 
@@ -151,6 +152,10 @@ SIGNATURES = {
     "dfd_shuffle_device_onepass": (C.c_int, [_VP, _VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.c_uint32, C.POINTER(DfdColumn)]),
     "dfd_exchange_collect": (C.c_int, [_VP, C.POINTER(DfdColumn), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dfd_exchange_onepass_fallbacks": (C.c_uint64, [_VP]),
+    "dfd_exchange_phase_ms": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "dfd_coalesce_task_group": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dfd_exchange_gather": (C.c_int, [_VP, C.c_int, C.POINTER(DfdColumn), C.c_int, C.POINTER(C.c_int64), C.c_uint32, C.c_int, C.POINTER(DfdColumn)]),
+    "dfd_exchange_pending_segments": (C.c_uint32, [_VP]),
     "dfd_shuffle_host": (C.c_int, [_VP, _VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.c_uint32, C.c_int, C.POINTER(DfdColumn),
                                    C.c_int64, C.POINTER(C.c_int64)]),
     "dfd_exchange_stats": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

@@ -344,6 +344,11 @@ struct dfd_exchange {
     void* h_runs = nullptr;                 // pinned staging of the same
     size_t runs_cap = 0;
     uint64_t push_shuffles = 0;
+    // phase timing of the single-pass shuffle (profiling mode): 4 events per shuffle, drained by dfd_exchange_phase_ms
+    std::vector<cudaEvent_t> pev;
+    size_t pev_pending = 0;
+    double phase_ms[3] = {0, 0, 0};
+    uint64_t phase_shuffles = 0;
     int64_t pending_sub_cap = 0;
     std::vector<dfd_column> last_in;        // retained for the exact (two-pass) re-run after an overflow
     std::vector<dfd_column> last_out;
@@ -462,6 +467,7 @@ void dfd_exchange_destroy(dfd_exchange* x) {
         if (x->comm) nccl_api()->CommDestroy(x->comm);
         cudaFree(x->window);
         cudaFree(x->d_peer_hdr);
+        for (auto& e : x->pev) cudaEventDestroy(e);
         cudaFree(x->d_flags);
         cudaFree(x->d_meta);
         cudaFree(x->d_runs);
@@ -692,8 +698,30 @@ static int onepass_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const 
     }
     const unsigned long long epoch = ++x->epoch;
     ExchangeHeader* hdr = (ExchangeHeader*)x->window;
+    cudaEvent_t* pe = nullptr;
+    if (c->profiling) {
+        constexpr size_t RING = 64;
+        if (x->pev.empty()) {
+            x->pev.resize(4 * RING);
+            for (auto& e : x->pev) cudaEventCreate(&e);
+        }
+        if (x->pev_pending == RING) {  // drain
+            cudaEventSynchronize(x->pev[4 * RING - 1]);
+            for (size_t i = 0; i < RING; ++i)
+                for (int k = 0; k < 3; ++k) {
+                    float ms = 0;
+                    cudaEventElapsedTime(&ms, x->pev[4 * i + k], x->pev[4 * i + k + 1]);
+                    x->phase_ms[k] += ms;
+                }
+            x->phase_shuffles += RING;
+            x->pev_pending = 0;
+        }
+        pe = &x->pev[4 * x->pev_pending++];
+        cudaEventRecord(pe[0], s);
+    }
     // consumer half: my window is free (everything enqueued on my stream so far — i.e. my reads of the previous shuffle — is ordered before)
     k_xchg_signal_ready<<<1, 32, 0, s>>>(x->d_peer_hdr, x->rank, T, epoch);
+    if (pe) cudaEventRecord(pe[1], s);
     CUDA_TRY(cudaGetLastError(), "k_xchg_signal_ready");
     CUDA_TRY(cudaMemsetAsync(x->d_flags, 0, 8, s), "memset flags");
     int rc;
@@ -711,9 +739,11 @@ static int onepass_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const 
     L.ready_flags = hdr->ready;
     L.ready_epoch = epoch;
     if ((rc = job.run_onepass(L))) return rc;
+    if (pe) cudaEventRecord(pe[2], s);
     // producer half: counts + overflow + "landed" flag into every consumer's header; consumer half: wait for all producers
     k_xchg_publish_wait<<<1, 256, 0, s>>>(hdr, x->d_peer_hdr, x->rank, T, P, epoch, x->d_counts, x->d_flags, x->d_flags + 1);
     CUDA_TRY(cudaGetLastError(), "k_xchg_publish_wait");
+    if (pe) cudaEventRecord(pe[3], s);
     c->metrics.kernel_launches += 2;
     CUDA_TRY(cudaMemcpy2DAsync(x->h_seg_counts, sizeof(int64_t) * P, hdr->counts, sizeof(long long) * XCHG_MAX_P, sizeof(int64_t) * P, (size_t)T,
                                cudaMemcpyDeviceToHost, s), "D2H counts");
@@ -728,84 +758,96 @@ static int onepass_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const 
 }
 
 // ---- push transport: every column kind over NVLink, no NCCL --------------------------------------
-// 1. partition locally (K1/K1b/K2 + K4) into a destination-sorted staging buffer — any column kind;
-// 2. all-gather the per-destination row / byte counts through the window headers (k_xchg_allgather_meta); its flag
+// 1. (shuffle only) partition locally (K1/K1b/K2 + K4) into a destination-sorted staging buffer — any column kind;
+// 2. all-gather the per-slice row / byte counts through the window headers (k_xchg_allgather_meta); its flag
 //    also tells the producers that this worker's window is free again;
-// 3. every worker derives EVERY consumer's window layout from the same count matrices: partition q of consumer o is T
-//    segments (one per producer, task order), each starting on a 32-row boundary (bitmaps are pushed word-aligned,
-//    no atomics) with >= 1 spare row (a segment's n+1 string offsets never touch its neighbour);
-// 4. k_push_runs stores each destination's contiguous runs — values, shifted bitmaps, re-based string offsets, string
-//    bytes — straight into the owner's segments (16-byte vectors when co-aligned), then k_xchg_done_barrier.
-// The consumer reads Arrow-shaped buffers in place: one values / offsets / bitmap buffer per column, segment (q, r)
-// = rows [seg_start, +seg_count).
-static int push_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const dfd_column* in_cols, int n_cols, int64_t n_rows, uint32_t P,
-                               dfd_column* out_cols) {
-    dfd_ctx* c = x->ctx;
-    const uint32_t N = part->N;
-    const int T = x->world;
-    cudaStream_t s = c->stream;
-    if (!x->window_ready) return set_error(DFD_ERR_INVALID_ARGUMENT, "fused exchange needs dfd_exchange_setup_window first");
-    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    struct PCol {
-        int kind, width, ow, var_index;
-        bool nullable, in_valid;
-        size_t st_values, st_off, st_valid;
-        int64_t cap_bytes;
-    };
-    std::vector<PCol> pc(n_cols);
-    int V = 0;
-    size_t stage_bytes = 0;
-    const size_t bm = al((size_t)((n_rows + 63) / 64 * 8 + 16));
-    for (int i = 0; i < n_cols; ++i) {
-        const dfd_column& ic = in_cols[i];
-        PCol& q = pc[i];
-        q = PCol{};
-        q.kind = ic.kind; q.width = ic.width; q.ow = ic.kind == DFD_COL_LARGE_UTF8 ? 8 : 4; q.var_index = -1;
-        q.in_valid = ic.validity != nullptr;
-        q.nullable = out_cols[i].validity != nullptr || q.in_valid;  // (the schema's flag: every worker passes the same)
-        if (ic.kind == DFD_COL_FIXED) {
-            q.st_values = stage_bytes; stage_bytes += al((size_t)n_rows * ic.width + 16);
-        } else if (ic.kind == DFD_COL_BOOL) {
-            q.st_values = stage_bytes; stage_bytes += bm;
-        } else if (ic.kind == DFD_COL_UTF8 || ic.kind == DFD_COL_LARGE_UTF8 || ic.kind == DFD_COL_BINARY) {
-            q.var_index = V++;
-            q.cap_bytes = ic.values_bytes > 0 ? ic.values_bytes : 16;
-            q.st_off = stage_bytes; stage_bytes += al((size_t)(n_rows + 1) * q.ow + 16);
-            q.st_values = stage_bytes; stage_bytes += al((size_t)q.cap_bytes + 16);
-        } else {
-            return set_error(DFD_ERR_UNSUPPORTED, "column %d: unknown column kind %d", i, ic.kind);
+// 3. every worker derives EVERY consumer's window layout from the same count matrices: a consumer's window is a list
+//    of segments (which (producer, slice) lands where is the ROUTE: shuffle / coalesce / broadcast), each starting on a
+//    32-row boundary (bitmaps are pushed word-aligned, no atomics) with >= 1 spare row (a segment's n+1 string
+//    offsets never touch its neighbour);
+// 4. k_push_runs stores each slice's contiguous runs — values, shifted bitmaps, re-based string offsets, string
+//    bytes — straight into the owners' segments (16-byte vectors when co-aligned), then k_xchg_done_barrier.
+// The consumer reads Arrow-shaped buffers in place: one values / offsets / bitmap buffer per column, segment s
+// = rows [seg_start[s], +seg_count[s]).
+namespace {
+
+// Which (producer task, local slice) feeds which consumer segment.
+//   SHUFFLE   (NetworkShuffleExec, src/execution_plans/network_shuffle.rs:213-238): producer r holds N = P*T slices
+//             (global partitions); slice g goes to consumer g / P as segment (g % P) * T + r.
+//   COALESCE  (NetworkCoalesceExec, src/execution_plans/network_coalesce.rs:170-240): producer r holds P slices (its own
+//             partitions, no repartition); consumer c reads the contiguous group of producers task_group(T, c, C):
+//             segment (r - group.start) * P + g; groups shorter than the longest are padded with empty segments.
+//   BROADCAST (NetworkBroadcastExec, src/execution_plans/network_broadcast.rs:224-249): every consumer receives every
+//             producer's P slices: segment g * T + r on each of the C consumers.
+struct Route {
+    int kind;
+    uint32_t P;
+    int T;  // producer tasks == workers
+    int C;  // consumer tasks (<= workers)
+    uint32_t n_slices() const { return kind == DFD_ROUTE_SHUFFLE ? P * (uint32_t)T : P; }
+    void group(int c, int* start, int* len, int* max_len) const {  // task_group(input_task_count = T, task_index = c, task_count = C)
+        const int base = T / C, extra = T % C;
+        *len = base + (c < extra ? 1 : 0);
+        *start = c * base + (c < extra ? c : extra);
+        *max_len = base + (extra > 0 ? 1 : 0);
+    }
+    uint32_t n_segments(int o) const {
+        if (o >= C) return 0;
+        if (kind == DFD_ROUTE_COALESCE) { int s, l, m; group(o, &s, &l, &m); return (uint32_t)m * P; }
+        return P * (uint32_t)T;
+    }
+    // source of consumer o's segment s: producer r and its slice g (r = -1: padding segment)
+    void source(int o, uint32_t s, int* r, uint32_t* g) const {
+        if (kind == DFD_ROUTE_SHUFFLE) { *r = (int)(s % (uint32_t)T); *g = (uint32_t)o * P + s / (uint32_t)T; }
+        else if (kind == DFD_ROUTE_BROADCAST) { *r = (int)(s % (uint32_t)T); *g = s / (uint32_t)T; }
+        else {
+            int st, l, m;
+            group(o, &st, &l, &m);
+            const int off = (int)(s / P);
+            *r = off < l ? st + off : -1;
+            *g = s % P;
         }
-        if (q.in_valid) { q.st_valid = stage_bytes; stage_bytes += bm; }
     }
-    const uint32_t n_meta = (uint32_t)(1 + V) * N;
+};
+
+struct PushCol {
+    int kind, width, ow, var_index;
+    bool nullable, in_valid;
+    const char* values;
+    const char* offsets;
+    const char* validity;
+    int64_t offset;  // Arrow logical offset of the source column
+};
+
+__global__ void k_slice_rows(const int64_t* __restrict__ starts, uint32_t n, int64_t* __restrict__ rows) {
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) rows[g] = starts[g + 1] - starts[g];
+}
+
+}  // namespace
+
+// Steps 2-4 for `n_slices` consecutive row ranges [starts[g], starts[g+1]) of device columns `pc` (d_starts: device copy).
+static int push_slices_locked(dfd_exchange* x, const std::vector<PushCol>& pc, const dfd_column* proto_cols, const Route& R,
+                              const int64_t* d_starts, char* scratch /* >= (V+1) * n_slices * 8 B, device */, dfd_column* out_cols) {
+    dfd_ctx* c = x->ctx;
+    const int T = x->world;
+    const int n_cols = (int)pc.size();
+    cudaStream_t s = c->stream;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    int V = 0;
+    for (const PushCol& q : pc) V += q.var_index >= 0;
+    const uint32_t NS = R.n_slices();
+    const uint32_t n_meta = (uint32_t)(1 + V) * NS;
     if (n_meta > XCHG_META_MAX)
-        return set_error(DFD_ERR_UNSUPPORTED, "push transport: (1 + %d string columns) x %u partitions exceeds %u metadata entries", V, N, XCHG_META_MAX);
-    const size_t first_off = stage_bytes;  // device: first[V][N] byte offset of every destination's run in the staged bytes
-    stage_bytes += al((size_t)(V ? V : 1) * N * 8);
+        return set_error(DFD_ERR_UNSUPPORTED, "push transport: (1 + %d string columns) x %u slices exceeds %u metadata entries", V, NS, XCHG_META_MAX);
     int rc;
-    if ((rc = x->send.ensure(stage_bytes + 256, c->device))) return rc;
-    char* sb = (char*)x->send.ptr;
-    std::vector<dfd_column> staged(n_cols);
-    for (int i = 0; i < n_cols; ++i) {
-        const PCol& q = pc[i];
-        staged[i] = in_cols[i];
-        staged[i].values = sb + q.st_values;
-        staged[i].offsets = q.var_index >= 0 ? (void*)(sb + q.st_off) : nullptr;
-        staged[i].validity = q.in_valid ? (uint8_t*)(sb + q.st_valid) : nullptr;
-        staged[i].offset = 0;
-        staged[i].values_bytes = q.cap_bytes;
-    }
-    PartitionJob job;
-    if ((rc = job.prepare(part, in_cols, n_cols, n_rows, staged.data(), false, s))) return rc;
-    if ((rc = job.run_hist_scan())) return rc;
-    if ((rc = job.run_scatter(part->d_part_starts, nullptr, 1, 1, nullptr))) return rc;
-    // my metadata: rows per destination, then bytes per destination of every string column
-    CUDA_TRY(cudaMemcpyAsync(x->d_meta, job.d_totals, sizeof(int64_t) * N, cudaMemcpyDeviceToDevice, s), "copy counts");
-    int64_t* d_first = (int64_t*)(sb + first_off);
-    for (int i = 0; i < n_cols; ++i)
-        if (pc[i].var_index >= 0 &&
-            (rc = launch_var_dest_bytes(sb + pc[i].st_off, pc[i].ow, part->d_part_starts, N, x->d_meta + (size_t)N * (1 + pc[i].var_index),
-                                        d_first + (size_t)N * pc[i].var_index, s)))
+    // my metadata: rows per slice, then bytes per slice of every string column (+ local: first byte of every slice)
+    k_slice_rows<<<(NS + 255) / 256, 256, 0, s>>>(d_starts, NS, x->d_meta);
+    CUDA_TRY(cudaGetLastError(), "k_slice_rows");
+    int64_t* d_first = (int64_t*)scratch;
+    for (const PushCol& q : pc)
+        if (q.var_index >= 0 &&
+            (rc = launch_var_dest_bytes(q.offsets + (size_t)q.offset * q.ow, q.ow, d_starts, NS, x->d_meta + (size_t)NS * (1 + q.var_index),
+                                        d_first + (size_t)NS * q.var_index, s)))
             return rc;
     const unsigned long long epoch = ++x->epoch;
     ExchangeHeader* hdr = (ExchangeHeader*)x->window;
@@ -814,42 +856,43 @@ static int push_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const dfd
     CUDA_TRY(cudaGetLastError(), "k_xchg_allgather_meta");
     CUDA_TRY(cudaMemcpy2DAsync(x->h_meta, sizeof(int64_t) * XCHG_META_MAX, hdr->meta, sizeof(long long) * XCHG_META_MAX, sizeof(int64_t) * n_meta,
                                (size_t)T, cudaMemcpyDeviceToHost, s), "D2H meta");
-    std::vector<int64_t> h_first((size_t)(V ? V : 1) * N);
-    if (V) CUDA_TRY(cudaMemcpyAsync(h_first.data(), d_first, sizeof(int64_t) * (size_t)V * N, cudaMemcpyDeviceToHost, s), "D2H first");
+    std::vector<int64_t> h_first((size_t)(V ? V : 1) * NS), h_starts(NS + 1);
+    if (V) CUDA_TRY(cudaMemcpyAsync(h_first.data(), d_first, sizeof(int64_t) * (size_t)V * NS, cudaMemcpyDeviceToHost, s), "D2H first");
+    CUDA_TRY(cudaMemcpyAsync(h_starts.data(), d_starts, sizeof(int64_t) * (NS + 1), cudaMemcpyDeviceToHost, s), "D2H starts");
     CUDA_TRY(cudaMemcpyAsync(x->h_seg_flags + MAX_RANKS, x->d_flags + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H timeout flag");
-    CUDA_TRY(cudaStreamSynchronize(s), "push shuffle: metadata exchange");
-    if (x->h_seg_flags[MAX_RANKS]) return set_error(DFD_ERR_INTERNAL, "a peer worker never published its shuffle metadata (did it fail?)");
+    CUDA_TRY(cudaStreamSynchronize(s), "push: metadata exchange");
+    if (x->h_seg_flags[MAX_RANKS]) return set_error(DFD_ERR_INTERNAL, "a peer worker never published its metadata (did it fail?)");
     auto rows_of = [&](int r, uint32_t g) { return x->h_meta[(size_t)r * XCHG_META_MAX + g]; };
-    auto bytes_of = [&](int r, int v, uint32_t g) { return x->h_meta[(size_t)r * XCHG_META_MAX + (size_t)N * (1 + v) + g]; };
+    auto bytes_of = [&](int r, int v, uint32_t g) { return x->h_meta[(size_t)r * XCHG_META_MAX + (size_t)NS * (1 + v) + g]; };
     // ---- every consumer's layout, from the same matrices on every worker
     struct Layout {
-        std::vector<int64_t> seg_start;               // [P][T] rows
-        std::vector<std::vector<int64_t>> bseg_start; // [V][P][T] bytes
-        int64_t rows_cap = 0;
+        std::vector<int64_t> seg_start;               // [n_segments] rows
+        std::vector<std::vector<int64_t>> bseg_start; // [V][n_segments] bytes
         std::vector<size_t> reg_values, reg_off, reg_valid;  // byte offsets of the column regions in the window
     };
     std::vector<Layout> lay(T);
     for (int o = 0; o < T; ++o) {
         Layout& Lo = lay[o];
-        Lo.seg_start.assign((size_t)P * T, 0);
-        Lo.bseg_start.assign(V, std::vector<int64_t>((size_t)P * T, 0));
+        const uint32_t nseg = R.n_segments(o);
+        Lo.seg_start.assign(nseg, 0);
+        Lo.bseg_start.assign(V, std::vector<int64_t>(nseg, 0));
         int64_t run = 0;
         std::vector<int64_t> brun(V, 0);
-        for (uint32_t q = 0; q < P; ++q)
-            for (int r = 0; r < T; ++r) {
-                const uint32_t g = (uint32_t)o * P + q;
-                Lo.seg_start[(size_t)q * T + r] = run;
-                run = (run + rows_of(r, g) + 1 + 31) / 32 * 32;  // 32-row aligned, >= 1 spare row
-                for (int v = 0; v < V; ++v) {
-                    Lo.bseg_start[v][(size_t)q * T + r] = brun[v];
-                    brun[v] = (brun[v] + bytes_of(r, v, g) + 15) / 16 * 16;
-                }
+        for (uint32_t sg = 0; sg < nseg; ++sg) {
+            int r;
+            uint32_t g;
+            R.source(o, sg, &r, &g);
+            Lo.seg_start[sg] = run;
+            run = (run + (r >= 0 ? rows_of(r, g) : 0) + 1 + 31) / 32 * 32;  // 32-row aligned, >= 1 spare row
+            for (int v = 0; v < V; ++v) {
+                Lo.bseg_start[v][sg] = brun[v];
+                brun[v] = (brun[v] + (r >= 0 ? bytes_of(r, v, g) : 0) + 15) / 16 * 16;
             }
-        Lo.rows_cap = run;
+        }
         Lo.reg_values.assign(n_cols, 0); Lo.reg_off.assign(n_cols, 0); Lo.reg_valid.assign(n_cols, 0);
         size_t off = 0;
         for (int i = 0; i < n_cols; ++i) {
-            const PCol& q = pc[i];
+            const PushCol& q = pc[i];
             if (q.kind == DFD_COL_FIXED) { Lo.reg_values[i] = off; off += al((size_t)run * q.width + 16); }
             else if (q.kind == DFD_COL_BOOL) { Lo.reg_values[i] = off; off += al((size_t)run / 8 + 16); }
             else {
@@ -859,52 +902,52 @@ static int push_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const dfd
             if (q.nullable) { Lo.reg_valid[i] = off; off += al((size_t)run / 8 + 16); }
         }
         if (off > x->window_bytes)
-            return set_error(DFD_ERR_CAPACITY, "consumer %d needs %zu B of receive window for this shuffle, windows hold %zu B", o, off, x->window_bytes);
+            return set_error(DFD_ERR_CAPACITY, "consumer %d needs %zu B of receive window for this exchange, windows hold %zu B", o, off, x->window_bytes);
     }
-    // ---- my runs as producer
+    // ---- my runs as producer: walk every consumer's segments and emit the ones I feed
     std::vector<PushRun> runs;
-    int64_t send_start = 0;
-    for (uint32_t g = 0; g < N; ++g) {
-        const int o = (int)(g / P);
-        const uint32_t q = g % P;
-        const int64_t cnt = rows_of(x->rank, g);
+    for (int o = 0; o < T; ++o) {
         const Layout& Lo = lay[o];
-        const int64_t seg = Lo.seg_start[(size_t)q * T + x->rank];
         char* dst_base = (char*)x->peer_window[o] + XCHG_HEADER_BYTES;
-        if (cnt > 0) {
+        for (uint32_t sg = 0; sg < R.n_segments(o); ++sg) {
+            int r;
+            uint32_t g;
+            R.source(o, sg, &r, &g);
+            if (r != x->rank) continue;
+            const int64_t cnt = rows_of(r, g), seg = Lo.seg_start[sg], first_row = h_starts[g];
+            if (cnt <= 0) continue;
             for (int i = 0; i < n_cols; ++i) {
-                const PCol& qc = pc[i];
-                PushRun r{};
+                const PushCol& qc = pc[i];
+                PushRun pr{};
                 if (qc.kind == DFD_COL_FIXED) {
-                    r.kind = RUN_BYTES; r.src = sb + qc.st_values + (size_t)send_start * qc.width;
-                    r.dst = dst_base + Lo.reg_values[i] + (size_t)seg * qc.width; r.n = cnt * qc.width;
-                    runs.push_back(r);
+                    pr.kind = RUN_BYTES; pr.src = qc.values + (size_t)(qc.offset + first_row) * qc.width;
+                    pr.dst = dst_base + Lo.reg_values[i] + (size_t)seg * qc.width; pr.n = cnt * qc.width;
+                    runs.push_back(pr);
+                    if (o != x->rank) x->bytes_sent += (uint64_t)pr.n;
                 } else if (qc.kind == DFD_COL_BOOL) {
-                    r.kind = RUN_BITS; r.src = sb + qc.st_values; r.a = send_start; r.dst = dst_base + Lo.reg_values[i] + (size_t)seg / 8; r.n = cnt;
-                    runs.push_back(r);
+                    pr.kind = RUN_BITS; pr.src = qc.values; pr.a = qc.offset + first_row; pr.dst = dst_base + Lo.reg_values[i] + (size_t)seg / 8; pr.n = cnt;
+                    runs.push_back(pr);
                 } else {
                     const int v = qc.var_index;
-                    const int64_t first = h_first[(size_t)v * N + g], nb = bytes_of(x->rank, v, g);
-                    const int64_t bseg = Lo.bseg_start[v][(size_t)q * T + x->rank];
-                    r.kind = qc.ow == 8 ? RUN_OFF64 : RUN_OFF32; r.src = sb + qc.st_off + (size_t)send_start * qc.ow; r.a = first; r.b = bseg;
-                    r.dst = dst_base + Lo.reg_off[i] + (size_t)seg * qc.ow; r.n = cnt + 1;
-                    runs.push_back(r);
+                    const int64_t first = h_first[(size_t)v * NS + g], nb = bytes_of(r, v, g), bseg = Lo.bseg_start[v][sg];
+                    pr.kind = qc.ow == 8 ? RUN_OFF64 : RUN_OFF32; pr.src = qc.offsets + (size_t)(qc.offset + first_row) * qc.ow; pr.a = first; pr.b = bseg;
+                    pr.dst = dst_base + Lo.reg_off[i] + (size_t)seg * qc.ow; pr.n = cnt + 1;
+                    runs.push_back(pr);
                     if (nb > 0) {
                         PushRun b{};
-                        b.kind = RUN_BYTES; b.src = sb + qc.st_values + first; b.dst = dst_base + Lo.reg_values[i] + bseg; b.n = nb;
+                        b.kind = RUN_BYTES; b.src = qc.values + first; b.dst = dst_base + Lo.reg_values[i] + bseg; b.n = nb;
                         runs.push_back(b);
-                        x->bytes_sent += o == x->rank ? 0 : (uint64_t)nb;
+                        if (o != x->rank) x->bytes_sent += (uint64_t)nb;
                     }
                 }
                 if (qc.nullable) {
                     PushRun vr{};
-                    vr.kind = qc.in_valid ? RUN_BITS : RUN_ONES; vr.src = qc.in_valid ? sb + qc.st_valid : nullptr; vr.a = send_start;
+                    vr.kind = qc.in_valid ? RUN_BITS : RUN_ONES; vr.src = qc.in_valid ? qc.validity : nullptr; vr.a = qc.offset + first_row;
                     vr.dst = dst_base + Lo.reg_valid[i] + (size_t)seg / 8; vr.n = cnt;
                     runs.push_back(vr);
                 }
             }
         }
-        send_start += cnt;
     }
     int blocks = 0;
     for (PushRun& r : runs) {
@@ -928,42 +971,103 @@ static int push_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const dfd
     }
     k_xchg_done_barrier<<<1, 32, 0, s>>>(hdr, x->d_peer_hdr, x->rank, T, epoch, x->d_flags + 1);
     CUDA_TRY(cudaGetLastError(), "k_xchg_done_barrier");
-    c->metrics.kernel_launches += 2;
+    c->metrics.kernel_launches += 3;
     CUDA_TRY(cudaMemcpyAsync(x->h_seg_flags + MAX_RANKS, x->d_flags + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H timeout flag");
-    CUDA_TRY(cudaStreamSynchronize(s), "push shuffle");
+    CUDA_TRY(cudaStreamSynchronize(s), "push exchange");
     if (x->h_seg_flags[MAX_RANKS]) return set_error(DFD_ERR_INTERNAL, "a peer worker never finished its pushes (did it fail?)");
     // ---- my view as consumer
     const Layout& Me = lay[x->rank];
     char* my_base = (char*)x->window + XCHG_HEADER_BYTES;
     for (int i = 0; i < n_cols; ++i) {
-        const PCol& q = pc[i];
-        out_cols[i] = in_cols[i];
+        const PushCol& q = pc[i];
+        out_cols[i] = proto_cols[i];
         out_cols[i].offset = 0;
         out_cols[i].values = my_base + Me.reg_values[i];
         out_cols[i].offsets = q.var_index >= 0 ? (void*)(my_base + Me.reg_off[i]) : nullptr;
         out_cols[i].validity = q.nullable ? (uint8_t*)(my_base + Me.reg_valid[i]) : nullptr;
         out_cols[i].values_bytes = 0;
     }
-    x->push_seg_starts.assign((size_t)P * T, 0);
-    x->push_seg_counts.assign((size_t)P * T, 0);
+    const uint32_t nseg = R.n_segments(x->rank);
+    x->push_seg_starts.assign(nseg, 0);
+    x->push_seg_counts.assign(nseg, 0);
     uint64_t rows = 0;
-    for (uint32_t q = 0; q < P; ++q)
-        for (int r = 0; r < T; ++r) {
-            x->push_seg_starts[(size_t)q * T + r] = Me.seg_start[(size_t)q * T + r];
-            x->push_seg_counts[(size_t)q * T + r] = rows_of(r, (uint32_t)x->rank * P + q);
-            rows += (uint64_t)x->push_seg_counts[(size_t)q * T + r];
-        }
+    for (uint32_t sg = 0; sg < nseg; ++sg) {
+        int r;
+        uint32_t g;
+        R.source(x->rank, sg, &r, &g);
+        x->push_seg_starts[sg] = Me.seg_start[sg];
+        x->push_seg_counts[sg] = r >= 0 ? rows_of(r, g) : 0;
+        rows += (uint64_t)x->push_seg_counts[sg];
+    }
     for (int i = 0; i < n_cols; ++i)
-        if (pc[i].kind == DFD_COL_FIXED) {
-            x->bytes_sent += (uint64_t)n_rows * pc[i].width;
-            x->bytes_received += rows * (uint64_t)pc[i].width;
-        }
+        if (pc[i].kind == DFD_COL_FIXED) x->bytes_received += rows * (uint64_t)pc[i].width;
     x->push_shuffles++;
     x->pending_push = true;
     x->pending_onepass = false;
     x->pending_async = false;
-    x->pending_P = P;
     return DFD_OK;
+}
+
+static int push_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const dfd_column* in_cols, int n_cols, int64_t n_rows, uint32_t P,
+                               dfd_column* out_cols) {
+    dfd_ctx* c = x->ctx;
+    const uint32_t N = part->N;
+    cudaStream_t s = c->stream;
+    if (!x->window_ready) return set_error(DFD_ERR_INVALID_ARGUMENT, "fused exchange needs dfd_exchange_setup_window first");
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    std::vector<PushCol> pc(n_cols);
+    std::vector<size_t> st_values(n_cols), st_off(n_cols), st_valid(n_cols);
+    std::vector<int64_t> cap_bytes(n_cols, 0);
+    int V = 0;
+    size_t stage_bytes = 0;
+    const size_t bm = al((size_t)((n_rows + 63) / 64 * 8 + 16));
+    for (int i = 0; i < n_cols; ++i) {
+        const dfd_column& ic = in_cols[i];
+        PushCol& q = pc[i];
+        q = PushCol{};
+        q.kind = ic.kind; q.width = ic.width; q.ow = ic.kind == DFD_COL_LARGE_UTF8 ? 8 : 4; q.var_index = -1;
+        q.in_valid = ic.validity != nullptr;
+        q.nullable = out_cols[i].validity != nullptr || q.in_valid;  // (the schema's flag: every worker passes the same)
+        if (ic.kind == DFD_COL_FIXED) {
+            st_values[i] = stage_bytes; stage_bytes += al((size_t)n_rows * ic.width + 16);
+        } else if (ic.kind == DFD_COL_BOOL) {
+            st_values[i] = stage_bytes; stage_bytes += bm;
+        } else if (ic.kind == DFD_COL_UTF8 || ic.kind == DFD_COL_LARGE_UTF8 || ic.kind == DFD_COL_BINARY) {
+            q.var_index = V++;
+            cap_bytes[i] = ic.values_bytes > 0 ? ic.values_bytes : 16;
+            st_off[i] = stage_bytes; stage_bytes += al((size_t)(n_rows + 1) * q.ow + 16);
+            st_values[i] = stage_bytes; stage_bytes += al((size_t)cap_bytes[i] + 16);
+        } else {
+            return set_error(DFD_ERR_UNSUPPORTED, "column %d: unknown column kind %d", i, ic.kind);
+        }
+        if (q.in_valid) { st_valid[i] = stage_bytes; stage_bytes += bm; }
+    }
+    const size_t scratch_off = stage_bytes;
+    stage_bytes += al((size_t)(V + 1) * N * 8 + 64);
+    int rc;
+    if ((rc = x->send.ensure(stage_bytes + 256, c->device))) return rc;
+    char* sb = (char*)x->send.ptr;
+    std::vector<dfd_column> staged(n_cols);
+    for (int i = 0; i < n_cols; ++i) {
+        PushCol& q = pc[i];
+        staged[i] = in_cols[i];
+        staged[i].values = sb + st_values[i];
+        staged[i].offsets = q.var_index >= 0 ? (void*)(sb + st_off[i]) : nullptr;
+        staged[i].validity = q.in_valid ? (uint8_t*)(sb + st_valid[i]) : nullptr;
+        staged[i].offset = 0;
+        staged[i].values_bytes = cap_bytes[i];
+        q.values = sb + st_values[i];
+        q.offsets = q.var_index >= 0 ? sb + st_off[i] : nullptr;
+        q.validity = q.in_valid ? sb + st_valid[i] : nullptr;
+        q.offset = 0;
+    }
+    PartitionJob job;
+    if ((rc = job.prepare(part, in_cols, n_cols, n_rows, staged.data(), false, s))) return rc;
+    if ((rc = job.run_hist_scan())) return rc;
+    if ((rc = job.run_scatter(part->d_part_starts, nullptr, 1, 1, nullptr))) return rc;
+    Route R{DFD_ROUTE_SHUFFLE, P, x->world, x->world};
+    x->pending_P = P;
+    return push_slices_locked(x, pc, in_cols, R, part->d_part_starts, sb + scratch_off, out_cols);
 }
 
 /* The shuffle: producer task `rank` holds n_rows local rows; afterwards this
@@ -1376,7 +1480,7 @@ int dfd_exchange_collect(dfd_exchange* x, dfd_column* out_cols, int64_t* seg_sta
     const int T = x->world;
     const uint32_t P = x->pending_P;
     if (x->pending_push) {  // the push transport completes inside the call: hand out its segments
-        for (size_t i = 0; i < (size_t)P * T; ++i) {
+        for (size_t i = 0; i < x->push_seg_starts.size(); ++i) {
             if (seg_starts) seg_starts[i] = x->push_seg_starts[i];
             if (seg_counts) seg_counts[i] = x->push_seg_counts[i];
         }
@@ -1433,6 +1537,62 @@ int dfd_exchange_collect(dfd_exchange* x, dfd_column* out_cols, int64_t* seg_sta
     return DFD_OK;
 }
 
+/* Pure host arithmetic of NetworkCoalesceExec's task grouping (src/execution_plans/network_coalesce.rs:264-289 `task_group`). */
+int dfd_coalesce_task_group(int input_task_count, int task_index, int task_count, int* start_task, int* len, int* max_len) {
+    if (input_task_count < 0 || task_index < 0 || task_count < 0 || !start_task || !len || !max_len)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_coalesce_task_group: bad arguments");
+    if (task_count == 0) { *start_task = 0; *len = 0; *max_len = 0; return DFD_OK; }
+    Route R{DFD_ROUTE_COALESCE, 1, input_task_count, task_count};
+    R.group(task_index, start_task, len, max_len);
+    if (task_index >= task_count) *len = 0;
+    return DFD_OK;
+}
+
+/* Coalesce / broadcast over the same NVLink transport (no repartition): this worker, as producer task `rank`, holds
+ * `P` partitions = the row slices [slice_starts[j], slice_starts[j+1]) of in_cols. */
+int dfd_exchange_gather(dfd_exchange* x, int route, const dfd_column* in_cols, int n_cols, const int64_t* slice_starts, uint32_t P,
+                        int consumer_tasks, dfd_column* out_cols) {
+    if (!x || !in_cols || !out_cols || !slice_starts || P < 1 || n_cols < 1)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_exchange_gather: bad arguments");
+    if (route != DFD_ROUTE_COALESCE && route != DFD_ROUTE_BROADCAST) return set_error(DFD_ERR_INVALID_ARGUMENT, "unknown route %d", route);
+    if (consumer_tasks < 1 || consumer_tasks > x->world)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "consumer_tasks %d not in [1, %d workers]", consumer_tasks, x->world);
+    dfd_ctx* c = x->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device), "cudaSetDevice");
+    if (!x->window_ready) return set_error(DFD_ERR_INVALID_ARGUMENT, "the exchange needs dfd_exchange_setup_window first");
+    cudaStream_t s = c->stream;
+    std::vector<PushCol> pc(n_cols);
+    int V = 0;
+    for (int i = 0; i < n_cols; ++i) {
+        const dfd_column& ic = in_cols[i];
+        PushCol& q = pc[i];
+        q = PushCol{};
+        q.kind = ic.kind; q.width = ic.width; q.ow = ic.kind == DFD_COL_LARGE_UTF8 ? 8 : 4; q.var_index = -1;
+        if (ic.kind == DFD_COL_UTF8 || ic.kind == DFD_COL_LARGE_UTF8 || ic.kind == DFD_COL_BINARY) q.var_index = V++;
+        else if (ic.kind != DFD_COL_FIXED && ic.kind != DFD_COL_BOOL) return set_error(DFD_ERR_UNSUPPORTED, "column %d: unknown column kind %d", i, ic.kind);
+        q.in_valid = ic.validity != nullptr;
+        q.nullable = out_cols[i].validity != nullptr || q.in_valid;
+        q.values = (const char*)ic.values; q.offsets = (const char*)ic.offsets; q.validity = (const char*)ic.validity; q.offset = ic.offset;
+    }
+    // device copy of the slice boundaries + scratch for the per-slice byte offsets
+    const size_t need = ((size_t)(P + 1) * 8 + 255) / 256 * 256 + (size_t)(V + 1) * P * 8 + 256;
+    int rc;
+    if ((rc = x->recv_tmp.ensure(need, c->device))) return rc;
+    int64_t* d_starts = (int64_t*)x->recv_tmp.ptr;
+    char* scratch = (char*)x->recv_tmp.ptr + ((size_t)(P + 1) * 8 + 255) / 256 * 256;
+    for (uint32_t j = 0; j < P; ++j)
+        if (slice_starts[j + 1] < slice_starts[j]) return set_error(DFD_ERR_INVALID_ARGUMENT, "slice_starts must be non-decreasing");
+    CUDA_TRY(cudaMemcpyAsync(d_starts, slice_starts, sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice, s), "H2D slice starts");
+    CUDA_TRY(cudaStreamSynchronize(s), "sync");  // (slice_starts is caller memory)
+    Route R{route, P, x->world, consumer_tasks};
+    x->shuffles++;
+    x->pending_P = P;
+    return push_slices_locked(x, pc, in_cols, R, d_starts, scratch, out_cols);
+}
+
+uint32_t dfd_exchange_pending_segments(const dfd_exchange* x) { return x && x->pending_push ? (uint32_t)x->push_seg_starts.size() : 0; }
+
 int dfd_exchange_stats(dfd_exchange* x, uint64_t* bytes_sent, uint64_t* bytes_received, uint64_t* shuffles) {
     if (!x) return set_error(DFD_ERR_INVALID_ARGUMENT, "NULL exchange");
     if (bytes_sent) *bytes_sent = x->bytes_sent;
@@ -1441,7 +1601,30 @@ int dfd_exchange_stats(dfd_exchange* x, uint64_t* bytes_sent, uint64_t* bytes_re
     return DFD_OK;
 }
 
-uint64_t dfd_exchange_onepass_fallbacks(const dfd_exchange* x) { return x ? x->onepass_fallbacks : 0;
+uint64_t dfd_exchange_onepass_fallbacks(const dfd_exchange* x) { return x ? x->onepass_fallbacks : 0; }
+
+/* Mean CUDA-event durations (ms) of the three stream phases of the single-pass shuffles recorded while the context was in
+ * profiling mode: [0] k_xchg_signal_ready, [1] k_scatter_onepass<PEER> (+ follow-up launches), [2] k_xchg_publish_wait
+ * (flag stores + waiting for the slowest producer).  Synchronises; resets the accumulators. */
+int dfd_exchange_phase_ms(dfd_exchange* x, double* out3, uint64_t* n_shuffles) {
+    if (!x || !out3) return set_error(DFD_ERR_INVALID_ARGUMENT, "NULL argument");
+    dfd_ctx* c = x->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device), "cudaSetDevice");
+    CUDA_TRY(cudaStreamSynchronize(c->stream), "sync");
+    for (size_t i = 0; i < x->pev_pending; ++i)
+        for (int k = 0; k < 3; ++k) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, x->pev[4 * i + k], x->pev[4 * i + k + 1]);
+            x->phase_ms[k] += ms;
+        }
+    x->phase_shuffles += x->pev_pending;
+    x->pev_pending = 0;
+    for (int k = 0; k < 3; ++k) out3[k] = x->phase_shuffles ? x->phase_ms[k] / (double)x->phase_shuffles : 0.0;
+    if (n_shuffles) *n_shuffles = x->phase_shuffles;
+    x->phase_ms[0] = x->phase_ms[1] = x->phase_ms[2] = 0;
+    x->phase_shuffles = 0;
+    return DFD_OK;
 }
 
 }  // extern "C"

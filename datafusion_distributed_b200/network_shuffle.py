@@ -277,3 +277,101 @@ class NetworkShuffleExec:
         if not 0 <= partition < P:
             raise IndexError(partition)
         return self._out, int(self._starts[partition]), int(self._starts[partition + 1])
+
+
+# ---------------------------------------------------------------------------------------------
+# Sibling exchanges over the same transport: NetworkCoalesceExec / NetworkBroadcastExec
+# ---------------------------------------------------------------------------------------------
+
+def task_group(input_task_count: int, task_index: int, task_count: int):
+    """src/execution_plans/network_coalesce.rs:264-289 — the contiguous group of input tasks consumer `task_index` reads:
+    (start_task, len, max_len)."""
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    nv.check(nv.lib().dfd_coalesce_task_group(input_task_count, task_index, task_count, C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
+
+
+class _GatherExec:
+    ROUTE = None
+
+    def __init__(self, partitions: int, input_stage: Stage, task_count: int):
+        self.partitions = partitions          # P: partitions of every producer task
+        self.input_stage = input_stage
+        self.task_count = task_count          # consumer tasks
+        self._out = None
+        self._starts = self._counts = None
+
+    def gather(self, exchange: ShuffleExchange, in_cols: Sequence[DeviceColumn], slice_starts: Sequence[int],
+               nullable: Optional[Sequence[bool]] = None):
+        """Collective: this worker (producer task `rank`) contributes its P partitions = row slices of `in_cols`."""
+        if len(self.input_stage.tasks) != exchange.world:
+            raise ValueError("one producer task per GPU worker")
+        P = self.partitions
+        starts = (C.c_int64 * (P + 1))(*[int(v) for v in slice_starts])
+        c_out = (nv.DfdColumn * len(in_cols))()
+        for i, c in enumerate(in_cols):
+            if (nullable[i] if nullable is not None else bool(c.validity)):
+                c_out[i].validity = 1
+        nv.check(nv.lib().dfd_exchange_gather(exchange._h, self.ROUTE, columns_to_c(in_cols), len(in_cols), starts, P, self.task_count, c_out))
+        n = nv.lib().dfd_exchange_pending_segments(exchange._h)
+        ss, sc = (C.c_int64 * max(n, 1))(), (C.c_int64 * max(n, 1))()
+        nv.check(nv.lib().dfd_exchange_collect(exchange._h, c_out, ss, sc))
+        self._starts = np.frombuffer(ss, dtype=np.int64)[:n].copy()
+        self._counts = np.frombuffer(sc, dtype=np.int64)[:n].copy()
+        self._out = [DeviceColumn(c_out[i].kind, c_out[i].width, c_out[i].values or 0, c_out[i].offsets or 0, c_out[i].validity or 0, 0, 0,
+                                  exchange, in_cols[i].arrow_type) for i in range(len(in_cols))]
+        return self._out, self._starts, self._counts
+
+
+class NetworkCoalesceExec(_GatherExec):
+    """src/execution_plans/network_coalesce.rs — coalesce the partitions of T_in tasks into task_count tasks without
+    repartitioning.  Output partitions per consumer task = P x max group size; partition i reads partition i % P of
+    input task group.start + i / P (empty when the group is shorter than the longest one)."""
+    ROUTE = nv.ROUTE_COALESCE
+
+    @staticmethod
+    def try_new(input_partitions: int, query_id: uuid.UUID, num: int, task_count: int, input_task_count: int) -> "NetworkCoalesceExec":
+        if task_count == 0:
+            raise ValueError("NetworkCoalesceExec cannot be executed with task_count=0")
+        return NetworkCoalesceExec(input_partitions, Stage(query_id, num, None, [ExecutionTask(None) for _ in range(input_task_count)]), task_count)
+
+    def name(self) -> str:
+        return "NetworkCoalesceExec"
+
+    def output_partition_count(self) -> int:
+        return self.partitions * max(-(-len(self.input_stage.tasks) // self.task_count), 1)
+
+    def execute(self, partition: int, task_ctx: DistributedTaskContext):
+        """-> (columns, first_row, n_rows) of output `partition` on consumer task task_ctx.task_index (n_rows 0: padding)."""
+        if task_ctx.task_index >= task_ctx.task_count:
+            raise ValueError(f"NetworkCoalesceExec invalid task context: task_index={task_ctx.task_index} >= task_count={task_ctx.task_count}")
+        if not 0 <= partition < self.output_partition_count():
+            raise IndexError(partition)
+        if self._out is None:
+            raise RuntimeError("gather() has not run")
+        start, length, _ = task_group(len(self.input_stage.tasks), task_ctx.task_index, task_ctx.task_count)
+        if partition // self.partitions >= length:
+            return self._out, 0, 0
+        return self._out, int(self._starts[partition]), int(self._counts[partition])
+
+
+class NetworkBroadcastExec(_GatherExec):
+    """src/execution_plans/network_broadcast.rs — every consumer task reads all P partitions of every input task;
+    output partition p is the merge of one stream per input task."""
+    ROUTE = nv.ROUTE_BROADCAST
+
+    @staticmethod
+    def try_new(input_partitions: int, query_id: uuid.UUID, num: int, task_count: int, input_task_count: int) -> "NetworkBroadcastExec":
+        return NetworkBroadcastExec(input_partitions, Stage(query_id, num, None, [ExecutionTask(None) for _ in range(input_task_count)]), task_count)
+
+    def name(self) -> str:
+        return "NetworkBroadcastExec"
+
+    def execute(self, partition: int, task_ctx: DistributedTaskContext):
+        """-> (columns, [(first_row, n_rows) per input task]) of output `partition`."""
+        if not 0 <= partition < self.partitions:
+            raise IndexError(partition)
+        if self._out is None:
+            raise RuntimeError("gather() has not run")
+        T = len(self.input_stage.tasks)
+        return self._out, [(int(self._starts[partition * T + r]), int(self._counts[partition * T + r])) for r in range(T)]

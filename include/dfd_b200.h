@@ -355,6 +355,28 @@ int dfd_shuffle_device_onepass(dfd_exchange* x, dfd_partitioner* p, const dfd_co
                                uint32_t partitions_per_task, dfd_column* out_cols);
 int dfd_exchange_collect(dfd_exchange* x, dfd_column* out_cols, int64_t* seg_starts, int64_t* seg_counts);
 uint64_t dfd_exchange_onepass_fallbacks(const dfd_exchange* x);
+/* Profiling (dfd_ctx_set_profiling): mean CUDA-event milliseconds of the three stream phases of the single-pass shuffles
+ * since the last call: [0] k_xchg_signal_ready, [1] k_scatter_onepass<PEER> (+ follow-ups), [2] k_xchg_publish_wait. */
+int dfd_exchange_phase_ms(dfd_exchange* x, double* out3, uint64_t* n_shuffles);
+
+/* ---- sibling exchanges over the same transport (no repartition) ---------------------------------------------
+ * NetworkCoalesceExec (src/execution_plans/network_coalesce.rs:75-120, execute :170-240) and NetworkBroadcastExec
+ * (src/execution_plans/network_broadcast.rs:119-254) move whole partitions between stages; here they ride the push
+ * transport of the shuffle (flag-based count all-gather + k_push_runs peer stores; every column kind; NCCL-free).
+ * Every worker is producer task `rank` and holds P partitions = the row slices [slice_starts[j], slice_starts[j+1])
+ * of in_cols; workers 0 .. consumer_tasks-1 are the consumer tasks.
+ *   DFD_ROUTE_COALESCE : consumer c receives the P partitions of each producer in its contiguous group
+ *                        (dfd_coalesce_task_group == the reference's task_group); its output partition
+ *                        i = (producer - group.start) * P + j; groups shorter than the longest get empty partitions.
+ *   DFD_ROUTE_BROADCAST: every consumer receives every producer's P partitions; output partition j is the merge of
+ *                        segments j * T + r (r = producer task).
+ * Collective and synchronous.  dfd_exchange_collect then returns dfd_exchange_pending_segments() (start, count)
+ * pairs in the order above; out_cols are set like in dfd_shuffle_device_onepass (same nullable convention). */
+enum { DFD_ROUTE_SHUFFLE = 0, DFD_ROUTE_COALESCE = 1, DFD_ROUTE_BROADCAST = 2 };
+int dfd_coalesce_task_group(int input_task_count, int task_index, int task_count, int* start_task, int* len, int* max_len);
+int dfd_exchange_gather(dfd_exchange* x, int route, const dfd_column* in_cols, int n_cols, const int64_t* slice_starts,
+                        uint32_t partitions, int consumer_tasks, dfd_column* out_cols);
+uint32_t dfd_exchange_pending_segments(const dfd_exchange* x);
 
 /* Host-to-host collective shuffle (end-to-end path of the multi-worker exchange; replaces, per
  * worker, "execute the producer plan, Flight-encode, stream, decode" of

@@ -189,6 +189,47 @@ def main():
                         failures += 1
                         print(f"rank {rank}: MISMATCH push rep={rep} q={q} r={r} col={c} {arr.type}", flush=True)
         dist.barrier()
+    # NetworkCoalesceExec / NetworkBroadcastExec over the same transport (mixed table, per-producer partitions = row slices)
+    my = [a.slice(mlo, mhi - mlo) for a in arrays]
+    Pn = 3
+    cuts = [0, (mhi - mlo) // 5, (mhi - mlo) // 2, mhi - mlo]
+    for consumers in sorted({1, 2 if world >= 2 else 1, world}):
+        co = dfd.NetworkCoalesceExec.try_new(Pn, uuid.uuid4(), 7, consumers, world)
+        outs4, ss4, sc4 = co.gather(ex, in_cols2, cuts, nullable=[True] * len(arrays))
+        if rank < consumers:
+            gs, gl, gm = dfd.task_group(world, rank, consumers)
+            for part_i in range(co.output_partition_count()):
+                _, a, cnt = co.execute(part_i, dfd.DistributedTaskContext(rank, consumers))
+                off, j = divmod(part_i, Pn)
+                if off >= gl:
+                    if cnt != 0:
+                        failures += 1
+                        print(f"rank {rank}: coalesce padding partition {part_i} not empty", flush=True)
+                    continue
+                r = gs + off
+                rlo, rhi = r * m // world, (r + 1) * m // world
+                rc_ = [0, (rhi - rlo) // 5, (rhi - rlo) // 2, rhi - rlo]
+                for c, arr in enumerate(arrays):
+                    want = arr.slice(rlo + rc_[j], rc_[j + 1] - rc_[j])
+                    got = dfd.NetworkShuffleExec.segment_to_arrow(ctx, outs4[c], a, cnt)
+                    if not got.equals(want):
+                        failures += 1
+                        print(f"rank {rank}: MISMATCH coalesce consumers={consumers} partition={part_i} col={c}", flush=True)
+        dist.barrier()
+    bc = dfd.NetworkBroadcastExec.try_new(Pn, uuid.uuid4(), 8, world, world)
+    outs5, ss5, sc5 = bc.gather(ex, in_cols2, cuts, nullable=[True] * len(arrays))
+    for j in range(Pn):
+        _, segs = bc.execute(j, dfd.DistributedTaskContext(rank, world))
+        for r, (a, cnt) in enumerate(segs):
+            rlo, rhi = r * m // world, (r + 1) * m // world
+            rc_ = [0, (rhi - rlo) // 5, (rhi - rlo) // 2, rhi - rlo]
+            for c, arr in enumerate(arrays):
+                want = arr.slice(rlo + rc_[j], rc_[j + 1] - rc_[j])
+                got = dfd.NetworkShuffleExec.segment_to_arrow(ctx, outs5[c], a, cnt)
+                if not got.equals(want):
+                    failures += 1
+                    print(f"rank {rank}: MISMATCH broadcast partition={j} producer={r} col={c}", flush=True)
+    dist.barrier()
     # host-to-host pipelined shuffle: row-set equality per destination (chunk-major output)
     P, N = 8 // world if 8 % world == 0 else 1, (8 // world if 8 % world == 0 else 1) * world
     ref, rc, rs = orc.repartition_table(cols, [0], N, 8192, 1)

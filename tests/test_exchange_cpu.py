@@ -128,3 +128,28 @@ def test_two_worker_shuffle_over_gloo(built, P):
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, "ok"), (1, "ok")], results
+
+
+def test_coalesce_task_groups_match_the_reference(built):
+    """NetworkCoalesceExec's task grouping (reference: src/execution_plans/network_coalesce.rs:264-289 and its unit tests
+    :300-420): contiguous groups, the first `input % consumers` groups get one extra task, max_len sizes the output."""
+    import datafusion_distributed_b200 as dfd
+
+    for input_tasks, consumers in [(9, 3), (9, 2), (3, 3), (3, 5), (1, 1), (7, 3), (8, 8), (16, 4), (5, 1), (0, 2)]:
+        base, extra = divmod(input_tasks, consumers)
+        start = 0
+        covered = []
+        for t in range(consumers):
+            want_len = base + (1 if t < extra else 0)
+            s, l, m = dfd.task_group(input_tasks, t, consumers)
+            assert (s, l) == (start, want_len), (input_tasks, consumers, t)
+            assert m == base + (1 if extra else 0)
+            covered += list(range(s, s + l))
+            start += want_len
+        assert covered == list(range(input_tasks))
+    assert dfd.task_group(4, 0, 0) == (0, 0, 0)
+    node = dfd.NetworkCoalesceExec.try_new(3, __import__("uuid").uuid4(), 1, 2, 9)  # 9 input tasks x 3 partitions -> 2 consumers
+    assert node.output_partition_count() == 3 * 5
+    import pytest as _pt
+    with _pt.raises(ValueError):
+        dfd.NetworkCoalesceExec.try_new(3, __import__("uuid").uuid4(), 1, 0, 9)

@@ -228,3 +228,39 @@ def test_single_worker_push_transport_moves_every_column_kind(ctx):
     assert e.value.status == 7
     ex.close()
     ex2.close()
+
+
+def test_single_worker_coalesce_and_broadcast(ctx):
+    """NetworkCoalesceExec / NetworkBroadcastExec over the push transport at world=1: the consumer sees the producer's
+    partitions unchanged (every column kind), read in place from the window."""
+    import pyarrow as pa
+
+    n, P = 9_001, 4
+    arrays = _mixed_table(n, 5)
+    ex = dfd.ShuffleExchange(ctx, 0, 1, None)
+    ex.setup_window(8 << 20)
+    cols = [dfd.DeviceColumn.from_arrow(ctx, a) for a in arrays]
+    starts = [0, 100, 100, 5000, n]  # one empty partition
+    co = dfd.NetworkCoalesceExec.try_new(P, uuid.uuid4(), 1, 1, 1)
+    outs, ss, sc = co.gather(ex, cols, starts, nullable=[True] * len(arrays))
+    assert co.output_partition_count() == P and sc.tolist() == [100, 0, 4900, n - 5000]
+    for p in range(P):
+        _, a, cnt = co.execute(p, dfd.DistributedTaskContext(0, 1))
+        for c, arr in enumerate(arrays):
+            got = dfd.NetworkShuffleExec.segment_to_arrow(ctx, outs[c], a, cnt)
+            assert got.equals(arr.slice(starts[p], starts[p + 1] - starts[p])), (p, c)
+    bc = dfd.NetworkBroadcastExec.try_new(P, uuid.uuid4(), 2, 1, 1)
+    outs, ss, sc = bc.gather(ex, cols, starts, nullable=[True] * len(arrays))
+    for p in range(P):
+        _, segs = bc.execute(p, dfd.DistributedTaskContext(0, 1))
+        (a, cnt), = segs
+        for c, arr in enumerate(arrays):
+            got = dfd.NetworkShuffleExec.segment_to_arrow(ctx, outs[c], a, cnt)
+            assert got.equals(arr.slice(starts[p], starts[p + 1] - starts[p])), (p, c)
+    # sliced inputs (Arrow offset != 0)
+    sl = [a.slice(17, 4000) for a in arrays]
+    outs, ss, sc = co.gather(ex, [dfd.DeviceColumn.from_arrow(ctx, a) for a in sl], [0, 1, 2, 3000, 4000], nullable=[True] * len(arrays))
+    for c, arr in enumerate(sl):
+        got = dfd.NetworkShuffleExec.segment_to_arrow(ctx, outs[c], int(ss[2]), int(sc[2]))
+        assert got.equals(arr.slice(2, 2998)), c
+    ex.close()
