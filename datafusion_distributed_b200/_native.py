@@ -153,6 +153,10 @@ SIGNATURES = {
     "dfd_exchange_collect": (C.c_int, [_VP, C.POINTER(DfdColumn), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dfd_exchange_onepass_fallbacks": (C.c_uint64, [_VP]),
     "dfd_exchange_phase_ms": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "dfd_shuffle_stream_begin": (C.c_int, [_VP, _VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.c_uint32, C.POINTER(C.c_uint8), C.POINTER(_VP)]),
+    "dfd_shuffle_stream_next": (C.c_int, [_VP, C.POINTER(DfdColumn), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    "dfd_shuffle_stream_stats": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "dfd_shuffle_stream_end": (None, [_VP]),
     "dfd_coalesce_task_group": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dfd_exchange_gather": (C.c_int, [_VP, C.c_int, C.POINTER(DfdColumn), C.c_int, C.POINTER(C.c_int64), C.c_uint32, C.c_int, C.POINTER(DfdColumn)]),
     "dfd_exchange_pending_segments": (C.c_uint32, [_VP]),

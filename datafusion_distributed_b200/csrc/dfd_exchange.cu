@@ -662,10 +662,13 @@ static int fused_shuffle_locked(dfd_exchange* x, dfd_partitioner* part, const df
 // travel as peer-memory flags (window headers) written by two tiny kernels — no NCCL call on the critical path.
 // The reference makes the same promise: a consumer partition is the MERGE of one stream per producer, in no
 // particular inter-producer order (src/execution_plans/network_shuffle.rs:230-237 `select_all`).
-static bool onepass_supported(const dfd_exchange* x, const dfd_partitioner* part, const dfd_column* cols, int n_cols, uint32_t P) {
+// (decided from the SCHEMA — column kinds and the nullable flags the caller passes in out_cols[].validity — so that every
+//  worker takes the same transport whether or not its own rows contain nulls)
+static bool onepass_supported(const dfd_exchange* x, const dfd_partitioner* part, const dfd_column* cols, const dfd_column* out_cols, int n_cols,
+                              uint32_t P) {
     if (part->N > ONEPASS_MAX_N || P > XCHG_MAX_P || n_cols < 1) return false;
     for (int i = 0; i < n_cols; ++i)
-        if (cols[i].kind != DFD_COL_FIXED || cols[i].validity) return false;
+        if (cols[i].kind != DFD_COL_FIXED || cols[i].validity || out_cols[i].validity) return false;
     (void)x;
     return true;
 }
@@ -1458,7 +1461,7 @@ int dfd_shuffle_device_onepass(dfd_exchange* x, dfd_partitioner* part, const dfd
     x->last_part = part;
     x->last_rows = n_rows;
     x->pending_push = false;
-    if (!onepass_supported(x, part, in_cols, n_cols, P)) {
+    if (!onepass_supported(x, part, in_cols, out_cols, n_cols, P)) {
         // nullable / boolean / string columns (or > 256 partitions): the push transport moves every column kind
         x->pending_onepass = false;
         return push_shuffle_locked(x, part, in_cols, n_cols, n_rows, P, out_cols);
@@ -1535,6 +1538,86 @@ int dfd_exchange_collect(dfd_exchange* x, dfd_column* out_cols, int64_t* seg_sta
         }
     x->bytes_received += rows * x->pending_row_bytes;
     return DFD_OK;
+}
+
+/* ---- back-pressure: a shuffle delivered in rounds -------------------------------------------------------------
+ * The reference throttles producers with a per-connection byte budget (src/worker/worker_connection_pool.rs:151-153,
+ * 251-257): a consumer that cannot take more data yet slows its producers down, it never fails the query.  Here the
+ * bounded resource is the consumer's receive window: when a round does not fit (DFD_ERR_CAPACITY, detected from the
+ * same global count matrices on every worker, so all workers agree), the remaining rows of EVERY producer are cut
+ * into finer row ranges and the round is retried with less data; the consumer drains the window between rounds. */
+struct dfd_shuffle_stream {
+    dfd_exchange* x = nullptr;
+    dfd_partitioner* part = nullptr;
+    std::vector<dfd_column> in_cols;
+    std::vector<uint8_t> nullable;
+    int64_t n_rows = 0;
+    uint32_t P = 0;
+    // progress as a fraction num / den of every producer's rows (identical on all workers)
+    uint64_t num = 0, den = 1;
+    uint64_t rounds = 0, splits = 0;
+};
+
+int dfd_shuffle_stream_begin(dfd_exchange* x, dfd_partitioner* part, const dfd_column* in_cols, int n_cols, int64_t n_rows,
+                             uint32_t partitions_per_task, const uint8_t* nullable, dfd_shuffle_stream** out) {
+    if (!x || !part || !in_cols || !out || n_rows < 0 || n_cols < 1) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_shuffle_stream_begin: bad arguments");
+    if (partitions_per_task < 1 || (uint64_t)partitions_per_task * x->world != part->N)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "num_partitions %u != partitions_per_task %u x %d workers", part->N, partitions_per_task, x->world);
+    dfd_shuffle_stream* st = new (std::nothrow) dfd_shuffle_stream();
+    if (!st) return set_error(DFD_ERR_OOM, "out of host memory");
+    st->x = x; st->part = part; st->n_rows = n_rows; st->P = partitions_per_task;
+    st->in_cols.assign(in_cols, in_cols + n_cols);
+    st->nullable.assign((size_t)n_cols, 0);
+    for (int i = 0; i < n_cols; ++i) st->nullable[i] = (nullable ? nullable[i] != 0 : false) || in_cols[i].validity != nullptr;
+    *out = st;
+    return DFD_OK;
+}
+
+void dfd_shuffle_stream_end(dfd_shuffle_stream* st) { delete st; }
+
+int dfd_shuffle_stream_stats(const dfd_shuffle_stream* st, uint64_t* rounds, uint64_t* splits) {
+    if (!st) return set_error(DFD_ERR_INVALID_ARGUMENT, "NULL stream");
+    if (rounds) *rounds = st->rounds;
+    if (splits) *splits = st->splits;
+    return DFD_OK;
+}
+
+/* Collective.  Delivers the next round into the receive window: out_cols / segments (P x T) are valid until the next call.
+ * *done is set to 1 when every row has been delivered (this call then delivered nothing). */
+int dfd_shuffle_stream_next(dfd_shuffle_stream* st, dfd_column* out_cols, int64_t* seg_starts, int64_t* seg_counts, int* done) {
+    if (!st || !out_cols || !done) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_shuffle_stream_next: NULL argument");
+    dfd_exchange* x = st->x;
+    const int n_cols = (int)st->in_cols.size();
+    const size_t nseg = (size_t)st->P * x->world;
+    if (st->num == st->den) {
+        *done = 1;
+        for (size_t i = 0; i < nseg; ++i) { if (seg_starts) seg_starts[i] = 0; if (seg_counts) seg_counts[i] = 0; }
+        return DFD_OK;
+    }
+    *done = 0;
+    for (;;) {
+        const int64_t lo = (int64_t)((unsigned __int128)st->n_rows * st->num / st->den);
+        const int64_t hi = (int64_t)((unsigned __int128)st->n_rows * (st->num + 1) / st->den);
+        std::vector<dfd_column> cols(st->in_cols);
+        for (int i = 0; i < n_cols; ++i) {
+            cols[i].offset += lo;
+            out_cols[i] = dfd_column{};
+            out_cols[i].validity = st->nullable[i] ? (uint8_t*)1 : nullptr;  // the schema's nullable flag (see dfd_shuffle_device_onepass)
+        }
+        int rc = dfd_shuffle_device_onepass(x, st->part, cols.data(), n_cols, hi - lo, st->P, out_cols);
+        if (rc == DFD_OK) rc = dfd_exchange_collect(x, out_cols, seg_starts, seg_counts);
+        if (rc == DFD_OK) {
+            st->num += 1;
+            st->rounds++;
+            return DFD_OK;
+        }
+        if (rc != DFD_ERR_CAPACITY) return rc;
+        // the round does not fit some consumer's window: every worker saw the same counts and splits the same way
+        if (st->den > (uint64_t)1 << 40) return set_error(DFD_ERR_CAPACITY, "receive windows too small even for single-row rounds");
+        st->num *= 2;
+        st->den *= 2;
+        st->splits++;
+    }
 }
 
 /* Pure host arithmetic of NetworkCoalesceExec's task grouping (src/execution_plans/network_coalesce.rs:264-289 `task_group`). */

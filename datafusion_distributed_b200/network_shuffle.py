@@ -256,6 +256,33 @@ class NetworkShuffleExec:
             raise IndexError(partition)
         return self._out, [(int(a), int(n)) for a, n in zip(self._seg_starts[partition], self._seg_counts[partition])]
 
+    def shuffle_rounds(self, exchange: ShuffleExchange, in_cols: Sequence[DeviceColumn], n_rows: int,
+                       nullable: Optional[Sequence[bool]] = None):
+        """Back-pressured shuffle (`dfd_shuffle_stream_*`): a generator of rounds (out columns, seg_starts[P][T],
+        seg_counts[P][T]); a round's buffers are valid until the next one is requested.  Rounds shrink automatically
+        when a consumer's receive window cannot hold one (skew / small windows) instead of failing."""
+        if self._part is None:
+            self._part = HashPartitioner(exchange.ctx, self.input_stage.plan)
+        P, T = self.properties.partition_count, exchange.world
+        h = C.c_void_p()
+        nl = (C.c_uint8 * len(in_cols))(*[1 if (nullable[i] if nullable is not None else bool(c.validity)) else 0 for i, c in enumerate(in_cols)])
+        nv.check(nv.lib().dfd_shuffle_stream_begin(exchange._h, self._part._h, columns_to_c(in_cols), len(in_cols), n_rows, P, nl, C.byref(h)))
+        try:
+            while True:
+                c_out = (nv.DfdColumn * len(in_cols))()
+                starts, counts, done = (C.c_int64 * (P * T))(), (C.c_int64 * (P * T))(), C.c_int(0)
+                nv.check(nv.lib().dfd_shuffle_stream_next(h, c_out, starts, counts, C.byref(done)))
+                if done.value:
+                    break
+                outs = [DeviceColumn(c_out[i].kind, c_out[i].width, c_out[i].values or 0, c_out[i].offsets or 0, c_out[i].validity or 0, 0, 0,
+                                     exchange, in_cols[i].arrow_type) for i in range(len(in_cols))]
+                yield outs, np.frombuffer(starts, dtype=np.int64).reshape(P, T).copy(), np.frombuffer(counts, dtype=np.int64).reshape(P, T).copy()
+            r, sp = C.c_uint64(), C.c_uint64()
+            nv.lib().dfd_shuffle_stream_stats(h, C.byref(r), C.byref(sp))
+            self.last_stream_stats = {"rounds": r.value, "splits": sp.value}
+        finally:
+            nv.lib().dfd_shuffle_stream_end(h)
+
     def shuffle_host(self, exchange: ShuffleExchange, host_in: Sequence[DeviceColumn], n_rows: int, n_chunks: int,
                      host_out: Sequence[DeviceColumn], out_capacity_rows: int) -> np.ndarray:
         """Host-to-host pipelined shuffle (`dfd_shuffle_host`): `host_in` / `host_out` describe HOST (pinned)

@@ -359,6 +359,22 @@ uint64_t dfd_exchange_onepass_fallbacks(const dfd_exchange* x);
  * since the last call: [0] k_xchg_signal_ready, [1] k_scatter_onepass<PEER> (+ follow-ups), [2] k_xchg_publish_wait. */
 int dfd_exchange_phase_ms(dfd_exchange* x, double* out3, uint64_t* n_shuffles);
 
+/* ---- back-pressure: a shuffle delivered in rounds ----------------------------------------------------------------
+ * Replaces the reference's byte-budget back-pressure between WorkerConnection and its consumers
+ * (src/worker/worker_connection_pool.rs:151-153, 251-257): a consumer that cannot hold more data throttles its producers,
+ * it never fails the query.  Here the bounded resource is the consumer's receive window.  dfd_shuffle_stream_next
+ * delivers the next ROUND of the shuffle (out_cols + P x T segments, valid until the following call — the consumer
+ * drains in between).  When a round does not fit some consumer's window — skew, a window smaller than the data — every
+ * worker sees the same global counts, cuts the remaining rows of every producer into finer ranges and retries with
+ * less data; nothing fails unless a single row cannot fit.  Collective: every worker calls begin / next / end alike.
+ * `nullable[c]` (may be NULL) is the schema's nullable flag of column c. */
+typedef struct dfd_shuffle_stream dfd_shuffle_stream;
+int dfd_shuffle_stream_begin(dfd_exchange* x, dfd_partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,
+                             uint32_t partitions_per_task, const uint8_t* nullable, dfd_shuffle_stream** out);
+int dfd_shuffle_stream_next(dfd_shuffle_stream* s, dfd_column* out_cols, int64_t* seg_starts, int64_t* seg_counts, int* done);
+int dfd_shuffle_stream_stats(const dfd_shuffle_stream* s, uint64_t* rounds, uint64_t* splits);
+void dfd_shuffle_stream_end(dfd_shuffle_stream* s);
+
 /* ---- sibling exchanges over the same transport (no repartition) ---------------------------------------------
  * NetworkCoalesceExec (src/execution_plans/network_coalesce.rs:75-120, execute :170-240) and NetworkBroadcastExec
  * (src/execution_plans/network_broadcast.rs:119-254) move whole partitions between stages; here they ride the push

@@ -264,3 +264,46 @@ def test_single_worker_coalesce_and_broadcast(ctx):
         got = dfd.NetworkShuffleExec.segment_to_arrow(ctx, outs[c], int(ss[2]), int(sc[2]))
         assert got.equals(arr.slice(2, 2998)), c
     ex.close()
+
+
+def test_back_pressure_rounds_instead_of_capacity_error(ctx):
+    """A window far smaller than the data (and a single hot key): the shuffle is delivered in rounds that shrink until they
+    fit; the union of the rounds equals the oracle, per partition and in order (one producer)."""
+    import pyarrow as pa
+
+    n, P = 200_000, 4
+    k = np.full(n, 42, dtype=np.int64)
+    k[::7] = np.arange(0, n, 7)
+    v = np.arange(n, dtype=np.int64)
+    s = pa.array([("s%d" % (i % 1000)) if i % 3 else None for i in range(n)], type=pa.string())
+    arrays = [pa.array(k), pa.array(v), s]
+    ex = dfd.ShuffleExchange(ctx, 0, 1, None)
+    ex.setup_window(1 << 20)  # ~ 1/6 of what one round of everything would need
+    node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0], P), uuid.uuid4(), 1, 1, 1)
+    cols = [dfd.DeviceColumn.from_arrow(ctx, a) for a in arrays]
+    got = [[[] for _ in arrays] for _ in range(P)]
+    for outs, ss, sc in node.shuffle_rounds(ex, cols, n, nullable=[False, False, True]):
+        for q in range(P):
+            for c in range(len(arrays)):
+                got[q][c].append(dfd.NetworkShuffleExec.segment_to_arrow(ctx, outs[c], int(ss[q, 0]), int(sc[q, 0])))
+    assert node.last_stream_stats["rounds"] > 1 and node.last_stream_stats["splits"] >= 1
+    dest = orc.partition_ids([k], n, P)
+    for q in range(P):
+        idx = pa.array(np.nonzero(dest == q)[0])
+        for c, arr in enumerate(arrays):
+            assert pa.concat_arrays(got[q][c]).equals(arr.take(idx)), (q, c)
+    # the same data through the single-pass path (fixed-width, non-null) with a small window: overflow -> exact re-run -> rounds
+    ex2 = dfd.ShuffleExchange(ctx, 0, 1, None)
+    ex2.setup_window(1 << 20)
+    cols2 = cols[:2]
+    rows = 0
+    parts = [[] for _ in range(P)]
+    for outs, ss, sc in node.shuffle_rounds(ex2, cols2, n):
+        for q in range(P):
+            parts[q].append(dfd.NetworkShuffleExec.segment_to_arrow(ctx, outs[1], int(ss[q, 0]), int(sc[q, 0])))
+            rows += int(sc[q, 0])
+    assert rows == n and node.last_stream_stats["rounds"] > 1
+    for q in range(P):
+        assert pa.concat_arrays(parts[q]).equals(arrays[1].take(pa.array(np.nonzero(dest == q)[0])))
+    ex.close()
+    ex2.close()
