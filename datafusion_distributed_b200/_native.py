@@ -23,6 +23,7 @@ STATUS = {
 COL_FIXED, COL_BOOL, COL_UTF8, COL_LARGE_UTF8, COL_BINARY = 0, 1, 2, 3, 4
 EXCHANGE_NCCL, EXCHANGE_FUSED = 0, 1
 ROUTE_SHUFFLE, ROUTE_COALESCE, ROUTE_BROADCAST = 0, 1, 2
+AGG_SUM_I64, AGG_SUM_F64, AGG_MIN_I64, AGG_MAX_I64, AGG_SUM_I128, AGG_MIN_F64, AGG_MAX_F64 = 0, 1, 2, 3, 4, 5, 6
 KEY_HASH_PLAIN, KEY_HASH_INTERVAL_DAY_TIME, KEY_HASH_INTERVAL_MONTH_DAY_NANO = 0, 1, 2
 
 
@@ -153,6 +154,8 @@ SIGNATURES = {
     "dfd_exchange_collect": (C.c_int, [_VP, C.POINTER(DfdColumn), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dfd_exchange_onepass_fallbacks": (C.c_uint64, [_VP]),
     "dfd_exchange_phase_ms": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "dfd_partial_reduce_device": (C.c_int, [_VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32), _VP,
+                                            C.c_uint32, C.POINTER(DfdColumn), C.POINTER(C.c_int64), _VP]),
     "dfd_shuffle_stream_begin": (C.c_int, [_VP, _VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.c_uint32, C.POINTER(C.c_uint8), C.POINTER(_VP)]),
     "dfd_shuffle_stream_next": (C.c_int, [_VP, C.POINTER(DfdColumn), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "dfd_shuffle_stream_stats": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

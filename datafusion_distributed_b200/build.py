@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 OBJ_DIR = os.environ.get("DFD_OBJ_DIR", "/tmp/dfd_b200_obj")  # object cache lives outside the repo (gpurun ships the tree)
 
-SOURCES = ["dfd_api.cu", "dfd_exec.cu", "dfd_exchange.cu", "dfd_scatter_twopass_local.cu", "dfd_scatter_twopass_peer.cu",
+SOURCES = ["dfd_api.cu", "dfd_exec.cu", "dfd_exchange.cu", "dfd_reduce.cu", "dfd_scatter_twopass_local.cu", "dfd_scatter_twopass_peer.cu",
            "dfd_scatter_onepass_local.cu", "dfd_scatter_onepass_peer.cu", "dfd_scatter_follow_local.cu", "dfd_scatter_follow_peer.cu"]
 TUNABLE = {s for s in SOURCES if s.startswith("dfd_scatter_") or s == "dfd_api.cu"}  # sources that see the tile-geometry macros
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]

@@ -1637,9 +1637,11 @@ int dfd_exchange_gather(dfd_exchange* x, int route, const dfd_column* in_cols, i
                         int consumer_tasks, dfd_column* out_cols) {
     if (!x || !in_cols || !out_cols || !slice_starts || P < 1 || n_cols < 1)
         return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_exchange_gather: bad arguments");
-    if (route != DFD_ROUTE_COALESCE && route != DFD_ROUTE_BROADCAST) return set_error(DFD_ERR_INVALID_ARGUMENT, "unknown route %d", route);
-    if (consumer_tasks < 1 || consumer_tasks > x->world)
-        return set_error(DFD_ERR_INVALID_ARGUMENT, "consumer_tasks %d not in [1, %d workers]", consumer_tasks, x->world);
+    if (route != DFD_ROUTE_COALESCE && route != DFD_ROUTE_BROADCAST && route != DFD_ROUTE_SHUFFLE)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "unknown route %d", route);
+    if (consumer_tasks < 1 || consumer_tasks > x->world || (route == DFD_ROUTE_SHUFFLE && consumer_tasks != x->world))
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "consumer_tasks %d not in [1, %d workers] (pre-partitioned shuffle: == workers)", consumer_tasks, x->world);
+    const uint32_t n_slices = route == DFD_ROUTE_SHUFFLE ? P * (uint32_t)x->world : P;
     dfd_ctx* c = x->ctx;
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->device), "cudaSetDevice");
@@ -1659,14 +1661,14 @@ int dfd_exchange_gather(dfd_exchange* x, int route, const dfd_column* in_cols, i
         q.values = (const char*)ic.values; q.offsets = (const char*)ic.offsets; q.validity = (const char*)ic.validity; q.offset = ic.offset;
     }
     // device copy of the slice boundaries + scratch for the per-slice byte offsets
-    const size_t need = ((size_t)(P + 1) * 8 + 255) / 256 * 256 + (size_t)(V + 1) * P * 8 + 256;
+    const size_t need = ((size_t)(n_slices + 1) * 8 + 255) / 256 * 256 + (size_t)(V + 1) * n_slices * 8 + 256;
     int rc;
     if ((rc = x->recv_tmp.ensure(need, c->device))) return rc;
     int64_t* d_starts = (int64_t*)x->recv_tmp.ptr;
-    char* scratch = (char*)x->recv_tmp.ptr + ((size_t)(P + 1) * 8 + 255) / 256 * 256;
-    for (uint32_t j = 0; j < P; ++j)
+    char* scratch = (char*)x->recv_tmp.ptr + ((size_t)(n_slices + 1) * 8 + 255) / 256 * 256;
+    for (uint32_t j = 0; j < n_slices; ++j)
         if (slice_starts[j + 1] < slice_starts[j]) return set_error(DFD_ERR_INVALID_ARGUMENT, "slice_starts must be non-decreasing");
-    CUDA_TRY(cudaMemcpyAsync(d_starts, slice_starts, sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice, s), "H2D slice starts");
+    CUDA_TRY(cudaMemcpyAsync(d_starts, slice_starts, sizeof(int64_t) * (n_slices + 1), cudaMemcpyHostToDevice, s), "H2D slice starts");
     CUDA_TRY(cudaStreamSynchronize(s), "sync");  // (slice_starts is caller memory)
     Route R{route, P, x->world, consumer_tasks};
     x->shuffles++;

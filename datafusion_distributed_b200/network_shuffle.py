@@ -256,6 +256,21 @@ class NetworkShuffleExec:
             raise IndexError(partition)
         return self._out, [(int(a), int(n)) for a, n in zip(self._seg_starts[partition], self._seg_counts[partition])]
 
+    def shuffle_partitioned(self, exchange: ShuffleExchange, in_cols: Sequence[DeviceColumn], part_starts: Sequence[int],
+                            nullable: Optional[Sequence[bool]] = None):
+        """The exchange half alone, for rows that are ALREADY hash-partitioned on this worker into P x T global partitions
+        (`dfd_partition_device` [+ `PartialReduceExec`]): `dfd_exchange_gather(DFD_ROUTE_SHUFFLE)`.  Returns
+        (out columns, seg_starts[P][T], seg_counts[P][T])."""
+        P, T = self.properties.partition_count, exchange.world
+        starts = (C.c_int64 * (P * T + 1))(*[int(v) for v in part_starts])
+        c_out = (nv.DfdColumn * len(in_cols))()
+        for i, c in enumerate(in_cols):
+            if (nullable[i] if nullable is not None else bool(c.validity)):
+                c_out[i].validity = 1
+        nv.check(nv.lib().dfd_exchange_gather(exchange._h, nv.ROUTE_SHUFFLE, columns_to_c(in_cols), len(in_cols), starts, P, T, c_out))
+        self._pending = (c_out, [c.arrow_type for c in in_cols], exchange)
+        return self.collect(exchange)
+
     def shuffle_rounds(self, exchange: ShuffleExchange, in_cols: Sequence[DeviceColumn], n_rows: int,
                        nullable: Optional[Sequence[bool]] = None):
         """Back-pressured shuffle (`dfd_shuffle_stream_*`): a generator of rounds (out columns, seg_starts[P][T],

@@ -66,6 +66,10 @@ class HashPartitioner:
         except Exception:
             pass
 
+    def part_starts_device_ptr(self) -> int:
+        """Device address of the int64 part_starts[N+1] of the last dense `partition()` call."""
+        return nv.lib().dfd_partitioner_part_starts_device(self._h) or 0
+
     def partition_ids(self, cols: Sequence[DeviceColumn], n_rows: int) -> np.ndarray:
         """dest[i] = create_hashes(keys)[i] % N, computed on the GPU."""
         out = self.ctx.alloc(max(n_rows * 4, 4))
@@ -115,3 +119,25 @@ class HashPartitioner:
         starts, counts = (C.c_int64 * N)(), (C.c_int64 * N)()
         nv.check(nv.lib().dfd_partitioner_collect(self._h, starts, counts))
         return np.frombuffer(starts, dtype=np.int64).copy(), np.frombuffer(counts, dtype=np.int64).copy()
+
+
+class PartialReduceExec:
+    """≙ AggregateExec(mode = PartialReduce) above the producers' hash RepartitionExec
+    (src/distributed_planner/partial_reduce_below_network_shuffles.rs:17-100): merges rows with equal group keys inside
+    each destination partition of a partitioned device table (`dfd_partial_reduce_device`)."""
+
+    def __init__(self, ctx: WorkerContext, key_cols: Sequence[int], agg_ops: Sequence[int]):
+        """agg_ops[c] = nv.AGG_* for state column c, -1 for the group-key columns."""
+        self.ctx, self.key_cols, self.agg_ops = ctx, [int(k) for k in key_cols], [int(a) for a in agg_ops]
+
+    def reduce(self, cols: Sequence[DeviceColumn], n_rows: int, part_starts_device: int, num_partitions: int,
+               out_cols: Optional[List[DeviceColumn]] = None):
+        """-> (out_cols, out_part_starts[N+1]); `part_starts_device` = device pointer to the input's int64 part_starts[N+1]."""
+        if out_cols is None:
+            out_cols = [DeviceColumn.empty_like(self.ctx, c, n_rows) for c in cols]
+        keys = (C.c_int32 * len(self.key_cols))(*self.key_cols)
+        ops = (C.c_int32 * len(self.agg_ops))(*self.agg_ops)
+        starts = (C.c_int64 * (num_partitions + 1))()
+        nv.check(nv.lib().dfd_partial_reduce_device(self.ctx.handle, columns_to_c(cols), len(cols), n_rows, keys, len(self.key_cols), ops,
+                                                    part_starts_device, num_partitions, columns_to_c(out_cols), starts, None))
+        return out_cols, np.frombuffer(starts, dtype=np.int64).copy()

@@ -359,6 +359,29 @@ uint64_t dfd_exchange_onepass_fallbacks(const dfd_exchange* x);
  * since the last call: [0] k_xchg_signal_ready, [1] k_scatter_onepass<PEER> (+ follow-ups), [2] k_xchg_publish_wait. */
 int dfd_exchange_phase_ms(dfd_exchange* x, double* out3, uint64_t* n_shuffles);
 
+/* ---- device-side PartialReduce ahead of the shuffle ----------------------------------------------------------------
+ * The reference inserts AggregateExec(mode = PartialReduce) above the producers' hash RepartitionExec
+ * (src/distributed_planner/partial_reduce_below_network_shuffles.rs:17-100): once rows are hash-partitioned, equal group
+ * keys share a destination, so merging their aggregate states there shrinks the shuffle.  Input: a DENSE partitioned
+ * table on the device (the output of dfd_partition_device: partition p = rows [part_starts[p], part_starts[p+1])),
+ * `key_cols` = the group-by columns, agg_ops[c] = how state column c merges (-1 for the key columns).  Output: one row
+ * per distinct key, partition p = rows [out_part_starts[p], out_part_starts[p+1]) of out_cols (capacity n_rows; row order
+ * inside a partition is unspecified, like a hash aggregate's).  Feed it to dfd_exchange_gather(DFD_ROUTE_SHUFFLE) — the
+ * rows never leave the GPU between Partial aggregation, repartition, PartialReduce and the exchange.
+ * Fixed-width non-null keys and states (nullable group keys / states: DFD_ERR_UNSUPPORTED).  Synchronous. */
+typedef enum {
+    DFD_AGG_SUM_I64 = 0,  /* also COUNT states */
+    DFD_AGG_SUM_F64 = 1,
+    DFD_AGG_MIN_I64 = 2,
+    DFD_AGG_MAX_I64 = 3,
+    DFD_AGG_SUM_I128 = 4, /* Decimal128 sums */
+    DFD_AGG_MIN_F64 = 5,
+    DFD_AGG_MAX_F64 = 6
+} dfd_agg_op;
+int dfd_partial_reduce_device(dfd_ctx* ctx, const dfd_column* in_cols, int n_cols, int64_t n_rows, const int32_t* key_cols, int n_keys,
+                              const int32_t* agg_ops, const int64_t* part_starts_device, uint32_t num_partitions,
+                              const dfd_column* out_cols, int64_t* out_part_starts_host, int64_t* out_part_starts_device);
+
 /* ---- back-pressure: a shuffle delivered in rounds ----------------------------------------------------------------
  * Replaces the reference's byte-budget back-pressure between WorkerConnection and its consumers
  * (src/worker/worker_connection_pool.rs:151-153, 251-257): a consumer that cannot hold more data throttles its producers,
@@ -381,6 +404,10 @@ void dfd_shuffle_stream_end(dfd_shuffle_stream* s);
  * transport of the shuffle (flag-based count all-gather + k_push_runs peer stores; every column kind; NCCL-free).
  * Every worker is producer task `rank` and holds P partitions = the row slices [slice_starts[j], slice_starts[j+1])
  * of in_cols; workers 0 .. consumer_tasks-1 are the consumer tasks.
+ *   DFD_ROUTE_SHUFFLE  : the rows are ALREADY hash-partitioned into partitions x workers slices (global partitions, e.g. by
+ *                        dfd_partition_device [+ dfd_partial_reduce_device]): slice g goes to consumer g / partitions as
+ *                        segment (g % partitions) * T + r — the exchange half of the shuffle without re-partitioning.
+ *                        consumer_tasks must equal the number of workers; slice_starts has partitions x workers + 1 entries.
  *   DFD_ROUTE_COALESCE : consumer c receives the P partitions of each producer in its contiguous group
  *                        (dfd_coalesce_task_group == the reference's task_group); its output partition
  *                        i = (producer - group.start) * P + j; groups shorter than the longest get empty partitions.
