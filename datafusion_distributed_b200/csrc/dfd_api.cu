@@ -88,6 +88,13 @@ static int build_keyset(const dfd_partitioner* p, const dfd_column* cols, int n_
         kc.kind = c.kind;
         kc.width = (int16_t)c.width;
         kc.mode = (int16_t)p->key_modes[k];
+        if (kc.mode == KEY_HASH_DICTIONARY) {
+            if (c.kind != DFD_COL_FIXED || (c.width != 1 && c.width != 2 && c.width != 4 && c.width != 8))
+                return set_error(DFD_ERR_INVALID_ARGUMENT, "key column %d: dictionary indices must be a fixed-width integer column", ci);
+            if (!p->key_dicts[k].hashes) return set_error(DFD_ERR_INVALID_ARGUMENT, "key column %d: no dictionary set (dfd_partitioner_set_key_dictionary)", ci);
+            kc.offsets = p->key_dicts[k].hashes;
+            kc.dict_validity = p->key_dicts[k].validity;
+        }
         switch (c.kind) {
             case DFD_COL_FIXED:
                 if (c.width != 1 && c.width != 2 && c.width != 4 && c.width != 8 && c.width != 16)
@@ -575,6 +582,32 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int 
     return job.run_scatter(p->d_part_starts, nullptr, 1, 1, nullptr);
 }
 
+int dfd::hash_columns_locked(Ctx* c, const dfd_column* cols, int n_cols, int64_t n_rows, const uint64_t* seeds, uint64_t* hashes_device,
+                             cudaStream_t stream) {
+    if (!cols || n_cols < 1 || n_cols > MAX_KEYS || n_rows < 0 || !hashes_device)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "hash_columns: bad arguments");
+    dfd_partitioner tmp;
+    tmp.ctx = c;
+    tmp.N = 1;
+    for (int i = 0; i < n_cols; ++i) tmp.key_cols.push_back(i);
+    tmp.key_modes.assign((size_t)n_cols, DFD_KEY_HASH_PLAIN);
+    tmp.key_dicts.assign((size_t)n_cols, dfd_partitioner::KeyDict{});
+    static const uint64_t PI2[4] = {0x452821e638d01377ULL, 0xbe5466cf34e90c6cULL, 0xc0ac29b7c97c50ddULL, 0x3f84d5b5b5470917ULL};
+    uint64_t sd[4] = {0, 0, 0, 0};
+    if (seeds) memcpy(sd, seeds, sizeof sd);
+    tmp.st = HashState{sd[0] ^ PI2[0], sd[1] ^ PI2[1], sd[2] ^ PI2[2], sd[3] ^ PI2[3]};
+    if (n_rows == 0) return DFD_OK;
+    KeySet ks;
+    int rc = build_keyset(&tmp, cols, n_cols, &ks);
+    if (rc) return rc;
+    int64_t blocks = (n_rows + 255) / 256;
+    if (blocks > (int64_t)c->sm_count * 32) blocks = (int64_t)c->sm_count * 32;
+    k_row_hashes<<<(unsigned)blocks, 256, 0, stream>>>(ks, tmp.st, n_rows, hashes_device);
+    LAUNCH_CHECK("k_row_hashes");
+    c->metrics.kernel_launches++;
+    return DFD_OK;
+}
+
 extern "C" {
 
 int dfd_abi_version(void) { return DFD_ABI_VERSION; }
@@ -779,6 +812,7 @@ int dfd_partitioner_create(dfd_ctx* c, uint32_t num_partitions, const int32_t* k
     p->N = num_partitions;
     p->key_cols.assign(key_cols, key_cols + n_keys);
     p->key_modes.assign((size_t)n_keys, DFD_KEY_HASH_PLAIN);
+    p->key_dicts.assign((size_t)n_keys, dfd_partitioner::KeyDict{});
     // ahash RandomState::with_seeds: seed ^ PI2 (random_state.rs); DataFusion's
     // REPARTITION_RANDOM_STATE uses seeds (0,0,0,0).
     static const uint64_t PI2[4] = {0x452821e638d01377ULL, 0xbe5466cf34e90c6cULL, 0xc0ac29b7c97c50ddULL,
@@ -819,11 +853,31 @@ void dfd_partitioner_destroy(dfd_partitioner* p) {
 
 uint32_t dfd_partitioner_num_partitions(const dfd_partitioner* p) { return p ? p->N : 0; }
 
+int dfd_partitioner_set_key_dictionary(dfd_partitioner* p, int key_index, const uint64_t* dict_hashes_device, const uint8_t* dict_validity_device) {
+    if (!p) return set_error(DFD_ERR_INVALID_ARGUMENT, "partitioner is NULL");
+    if (key_index < 0 || key_index >= (int)p->key_cols.size()) return set_error(DFD_ERR_INVALID_ARGUMENT, "key index %d out of range", key_index);
+    std::lock_guard<std::mutex> lk(p->ctx->mu);
+    if (!dict_hashes_device) {  // back to a plain key
+        p->key_modes[(size_t)key_index] = DFD_KEY_HASH_PLAIN;
+        p->key_dicts[(size_t)key_index] = dfd_partitioner::KeyDict{};
+        return DFD_OK;
+    }
+    p->key_modes[(size_t)key_index] = KEY_HASH_DICTIONARY;
+    p->key_dicts[(size_t)key_index] = dfd_partitioner::KeyDict{dict_hashes_device, dict_validity_device};
+    return DFD_OK;
+}
+
+int dfd_hash_columns_device(dfd_ctx* c, const dfd_column* cols, int n_cols, int64_t n_rows, const uint64_t* seeds, uint64_t* hashes_device) {
+    if (!c) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_hash_columns_device: ctx is NULL");
+    CTX_GUARD(c);
+    return hash_columns_locked(c, cols, n_cols, n_rows, seeds, hashes_device, c->stream);
+}
+
 int dfd_partitioner_set_key_hash_mode(dfd_partitioner* p, int key_index, int mode) {
     if (!p) return set_error(DFD_ERR_INVALID_ARGUMENT, "partitioner is NULL");
     if (key_index < 0 || key_index >= (int)p->key_cols.size()) return set_error(DFD_ERR_INVALID_ARGUMENT, "key index %d out of range", key_index);
     if (mode != DFD_KEY_HASH_PLAIN && mode != DFD_KEY_HASH_INTERVAL_DAY_TIME && mode != DFD_KEY_HASH_INTERVAL_MONTH_DAY_NANO)
-        return set_error(DFD_ERR_INVALID_ARGUMENT, "unknown key hash mode %d", mode);
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "unknown key hash mode %d (dictionary keys: dfd_partitioner_set_key_dictionary)", mode);
     std::lock_guard<std::mutex> lk(p->ctx->mu);
     p->key_modes[(size_t)key_index] = mode;
     return DFD_OK;

@@ -33,8 +33,13 @@ namespace {
 struct FieldInfo {
     std::string name, format;
     int64_t flags = 0;
-    int32_t kind = DFD_COL_FIXED;
+    int32_t kind = DFD_COL_FIXED;   // layout the DEVICE sees (a Utf8View column is Utf8 there; a dictionary column is its indices)
     int32_t width = 0;
+    bool view = false;             // Arrow Utf8View / BinaryView ("vu" / "vz"): converted to offsets + bytes on input, back to views on output
+    bool dict = false;             // dictionary-encoded: `format` is the index type, dict_* describe the values
+    std::string dict_format;
+    int64_t dict_flags = 0;
+    int32_t dict_kind = DFD_COL_FIXED, dict_width = 0;
     bool var() const { return kind == DFD_COL_UTF8 || kind == DFD_COL_LARGE_UTF8 || kind == DFD_COL_BINARY; }
     size_t ow() const { return kind == DFD_COL_LARGE_UTF8 ? 8 : 4; }  // offset width of var-width kinds
 };
@@ -52,6 +57,10 @@ bool parse_format(const char* f, int32_t* kind, int32_t* width) {
         case 'u': *kind = DFD_COL_UTF8; *width = 0; return f[1] == 0;
         case 'U': *kind = DFD_COL_LARGE_UTF8; *width = 0; return f[1] == 0;
         case 'z': *kind = DFD_COL_BINARY; *width = 0; return f[1] == 0;
+        case 'v':  // Utf8View / BinaryView: 16-byte views + variadic data buffers; hashed over the string bytes exactly like Utf8 / Binary
+            if (f[1] == 'u' && f[2] == 0) { *kind = DFD_COL_UTF8; *width = 0; return true; }
+            if (f[1] == 'z' && f[2] == 0) { *kind = DFD_COL_BINARY; *width = 0; return true; }
+            return false;
         case 'd': {  // d:precision,scale[,bitwidth]
             int p = 0, s = 0, bw = 128;
             int n = sscanf(f, "d:%d,%d,%d", &p, &s, &bw);
@@ -72,8 +81,21 @@ bool parse_format(const char* f, int32_t* kind, int32_t* width) {
 
 struct PinnedPool;
 
+// An input record batch shared by everything that still points into it: in-flight H2D copies and, for dictionary
+// columns, the dictionaries of the output batches (which travel by reference).  Released when the last user lets go.
+struct SharedInput {
+    ArrowArray array;
+    explicit SharedInput(const ArrowArray& a) : array(a) {}
+    ~SharedInput() {
+        if (array.release) array.release(&array);
+    }
+};
+
 // One D2H landing buffer (pinned): all columns of one chunk, destination-sorted.
 struct OutChunk {
+    std::vector<void*> views;        // per column: 16-byte views of a Utf8View / BinaryView column (host, built at emission)
+    std::vector<int64_t> view_sizes; // per column: the "variadic buffer sizes" buffer of such an array (one data buffer)
+    std::vector<std::shared_ptr<SharedInput>> inputs;  // input batches whose dictionaries this chunk's batches reference
     std::vector<void*> values;    // per column: values (fixed / bool) or string bytes (var-width, grown on demand)
     std::vector<void*> validity;  // per column (may be null)
     std::vector<void*> offsets;   // per column (var-width only)
@@ -120,12 +142,15 @@ struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
             c->validity.push_back(b);
             c->offsets.push_back(o);
             c->data_cap.push_back(0);
+            c->views.push_back(f.view ? malloc((size_t)(chunk_rows + 16) * 16) : nullptr);
+            c->view_sizes.push_back(0);
         }
         std::lock_guard<std::mutex> lk(mu);
         all.push_back(c);
         return c;
     }
     void give_back(OutChunk* c) {
+        c->inputs.clear();  // (drops the references to the input batches whose dictionaries were handed out)
         std::lock_guard<std::mutex> lk(mu);
         free_list.push_back(c);
     }
@@ -137,6 +162,7 @@ struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
                 if (p) cudaFreeHost(p);
             for (void* p : c->offsets)
                 if (p) cudaFreeHost(p);
+            for (void* p : c->views) free(p);
             delete c;
         }
     }
@@ -154,16 +180,22 @@ struct BatchPriv {
     OutChunk* chunk;
     std::vector<ArrowArray> children;
     std::vector<ArrowArray*> child_ptrs;
-    std::vector<const void*> child_bufs;  // 3 per child (validity, values|offsets, string bytes)
+    std::vector<const void*> child_bufs;  // 4 per child (validity, values|offsets|views, string bytes, variadic sizes)
+    std::vector<ArrowArray> dicts;        // per child: shallow copy of the input dictionary (dictionary columns)
+    std::vector<std::shared_ptr<SharedInput>> dict_owner;  // keeps that dictionary's batch alive
     const void* struct_bufs[1] = {nullptr};
 };
+
+void dict_release(ArrowArray* a) { a->release = nullptr; }  // (the buffers belong to the SharedInput held by the batch)
 
 void child_release(ArrowArray* a) { a->release = nullptr; }
 
 void batch_release(ArrowArray* a) {
     BatchPriv* p = (BatchPriv*)a->private_data;
-    for (ArrowArray& c : p->children)
+    for (ArrowArray& c : p->children) {
+        if (c.dictionary && c.dictionary->release) c.dictionary->release(c.dictionary);
         if (c.release) c.release(&c);
+    }
     chunk_unref(p->chunk);
     delete p;
     a->release = nullptr;
@@ -173,6 +205,7 @@ struct SchemaPriv {
     std::vector<FieldInfo> fields;
     std::vector<ArrowSchema> children;
     std::vector<ArrowSchema*> child_ptrs;
+    std::vector<ArrowSchema> dicts;  // per child: schema of the dictionary values (dictionary columns)
 };
 
 void schema_child_release(ArrowSchema* s) { s->release = nullptr; }
@@ -190,6 +223,7 @@ int export_schema(const std::vector<FieldInfo>& fields, ArrowSchema* out) {
     p->fields = fields;
     p->children.resize(fields.size());
     p->child_ptrs.resize(fields.size());
+    p->dicts.resize(fields.size());
     for (size_t i = 0; i < fields.size(); ++i) {
         ArrowSchema& c = p->children[i];
         memset(&c, 0, sizeof c);
@@ -197,6 +231,15 @@ int export_schema(const std::vector<FieldInfo>& fields, ArrowSchema* out) {
         c.name = p->fields[i].name.c_str();
         c.flags = p->fields[i].flags;
         c.release = schema_child_release;
+        if (p->fields[i].dict) {
+            ArrowSchema& d = p->dicts[i];
+            memset(&d, 0, sizeof d);
+            d.format = p->fields[i].dict_format.c_str();
+            d.name = "";
+            d.flags = p->fields[i].dict_flags;
+            d.release = schema_child_release;
+            c.dictionary = &d;
+        }
         p->child_ptrs[i] = &c;
     }
     memset(out, 0, sizeof *out);
@@ -213,15 +256,17 @@ struct PartQueue {
     std::deque<ArrowArray> batches;
 };
 
-struct HeldInput {  // an input batch whose buffers an in-flight H2D still reads
-    ArrowArray array;
-};
+using HeldInput = std::shared_ptr<SharedInput>;  // an input batch whose buffers an in-flight H2D still reads
 
 struct Slot {
     std::vector<void*> d_in, d_in_valid, d_out, d_out_valid;  // per column device buffers
     std::vector<void*> d_in_off, d_out_off;                   // var-width: offsets buffers
     std::vector<size_t> in_cap, out_cap;                      // var-width: capacity of d_in / d_out (string bytes)
     std::vector<int64_t> first_off, data_bytes;               // var-width: first input offset / byte count of the chunk
+    std::vector<std::vector<char>> view_off, view_bytes;      // Utf8View input converted to offsets + contiguous bytes (host staging)
+    std::vector<dfd::Scratch> dict_buf;                       // dictionary KEY columns: [hashes | offsets | data | validity] of the values
+    std::vector<const uint64_t*> dict_hashes;                 //   device pointers handed to the partitioner for this chunk
+    std::vector<const uint8_t*> dict_valid;
     int64_t* h_part_starts = nullptr;                        // pinned [N+1]
     cudaEvent_t e_h2d = nullptr, e_k = nullptr, e_d2h = nullptr;
     bool k_recorded = false, d2h_recorded = false;
@@ -241,6 +286,7 @@ struct dfd_repartition_exec {
     dfd_ctx* ctx = nullptr;
     dfd_partitioner* part = nullptr;
     std::vector<FieldInfo> fields;
+    std::vector<int> key_of_field;  // index into the partitioner's key list, or -1
     uint32_t N = 0;
     int64_t chunk_rows = 0;
     int depth = 3;
@@ -284,14 +330,36 @@ int fail(dfd_repartition_exec* x, int code, const std::string& msg) {
 int emit_slot(dfd_repartition_exec* x, Slot& s) {
     if (!s.in_flight) return DFD_OK;
     XCUDA(x, cudaEventSynchronize(s.e_d2h), "D2H");
-    for (HeldInput& h : s.held)
-        if (h.array.release) h.array.release(&h.array);
-    s.held.clear();
     OutChunk* oc = s.out;
+    for (const FieldInfo& f : x->fields)
+        if (f.dict) { oc->inputs = s.held; break; }  // the output batches reference the inputs' dictionaries
+    s.held.clear();
     s.out = nullptr;
     s.in_flight = false;
     const size_t C = x->fields.size();
     int made = 0;
+    for (size_t c = 0; c < C; ++c) {
+        if (!x->fields[c].view) continue;
+        // Utf8View output: 16-byte views over the chunk's single data buffer (inline when <= 12 bytes)
+        const int32_t* off = (const int32_t*)oc->offsets[c];
+        const uint8_t* data = (const uint8_t*)oc->values[c];
+        uint8_t* views = (uint8_t*)oc->views[c];
+        const int64_t rows = s.rows;
+        for (int64_t r = 0; r < rows; ++r) {
+            uint8_t* v = views + (size_t)r * 16;
+            const int32_t o = off[r], len = off[r + 1] - o;
+            memset(v, 0, 16);
+            *(int32_t*)v = len;
+            if (len <= 12) {
+                memcpy(v + 4, data + o, (size_t)len);
+            } else {
+                memcpy(v + 4, data + o, 4);
+                *(int32_t*)(v + 8) = 0;
+                *(int32_t*)(v + 12) = o;
+            }
+        }
+        oc->view_sizes[c] = off[rows];
+    }
     oc->refs.store(1);  // guard while slicing
     oc->pool = x->pool;
     for (uint32_t p = 0; p < x->N; ++p) {
@@ -302,21 +370,33 @@ int emit_slot(dfd_repartition_exec* x, Slot& s) {
         bp->chunk = oc;
         bp->children.resize(C);
         bp->child_ptrs.resize(C);
-        bp->child_bufs.resize(3 * C);
+        bp->child_bufs.resize(4 * C);
+        bp->dicts.resize(C);
         for (size_t c = 0; c < C; ++c) {
             ArrowArray& a = bp->children[c];
             memset(&a, 0, sizeof a);
             bool hv = s.has_valid[c];
-            const bool var = x->fields[c].var();
-            bp->child_bufs[3 * c] = hv ? oc->validity[c] : nullptr;
-            bp->child_bufs[3 * c + 1] = var ? oc->offsets[c] : oc->values[c];
-            bp->child_bufs[3 * c + 2] = var ? oc->values[c] : nullptr;
+            const FieldInfo& f = x->fields[c];
+            const bool var = f.var();
+            bp->child_bufs[4 * c] = hv ? oc->validity[c] : nullptr;
+            bp->child_bufs[4 * c + 1] = f.view ? oc->views[c] : (var ? oc->offsets[c] : oc->values[c]);
+            bp->child_bufs[4 * c + 2] = var ? oc->values[c] : nullptr;
+            bp->child_bufs[4 * c + 3] = f.view ? (const void*)&oc->view_sizes[c] : nullptr;
             a.length = cnt;
             a.offset = start;  // zero-copy slice of the chunk-wide destination-sorted buffer
             a.null_count = hv ? -1 : 0;
-            a.n_buffers = var ? 3 : 2;
-            a.buffers = &bp->child_bufs[3 * c];
+            a.n_buffers = f.view ? 4 : (var ? 3 : 2);  // view arrays: validity, views, one data buffer, variadic buffer sizes
+            a.buffers = &bp->child_bufs[4 * c];
             a.release = child_release;
+            if (f.dict && !oc->inputs.empty()) {
+                // the dictionary travels by reference: a shallow copy of the input batch's dictionary, kept alive by the shared input
+                const ArrowArray* src = oc->inputs.back()->array.children[c]->dictionary;
+                bp->dicts[c] = *src;
+                bp->dicts[c].release = dict_release;
+                bp->dicts[c].private_data = nullptr;
+                bp->dict_owner.push_back(oc->inputs.back());
+                a.dictionary = &bp->dicts[c];
+            }
             bp->child_ptrs[c] = &a;
         }
         ArrowArray top;
@@ -372,6 +452,11 @@ int flush_current(dfd_repartition_exec* x) {
             XCUDA(x, cudaMemsetAsync(s.d_out[i], 0, PinnedPool::bitmap_bytes(s.rows), c->stream), "memset");
         if (s.has_valid[i]) XCUDA(x, cudaMemsetAsync(s.d_out_valid[i], 0, PinnedPool::bitmap_bytes(s.rows), c->stream), "memset");
     }
+    for (size_t i = 0; i < C; ++i)  // dictionary keys of this chunk (caller holds the context lock: set the fields directly)
+        if (x->fields[i].dict && x->key_of_field[i] >= 0) {
+            x->part->key_modes[(size_t)x->key_of_field[i]] = dfd::KEY_HASH_DICTIONARY;
+            x->part->key_dicts[(size_t)x->key_of_field[i]] = dfd_partitioner::KeyDict{s.dict_hashes[i], s.dict_valid[i]};
+        }
     int rc = partition_device_locked(x->part, in.data(), (int)C, s.rows, out.data(), c->stream);
     if (rc) return fail(x, rc, dfd_last_error());
     XCUDA(x, cudaMemcpyAsync(s.h_part_starts, x->part->d_part_starts, sizeof(int64_t) * (x->N + 1), cudaMemcpyDeviceToHost, c->stream),
@@ -434,7 +519,7 @@ int open_next_slot(dfd_repartition_exec* x) {
 bool batch_is_plain(const dfd_repartition_exec* x, const ArrowArray* b) {
     for (size_t i = 0; i < x->fields.size(); ++i) {
         const ArrowArray* c = b->children[i];
-        if (x->fields[i].kind != DFD_COL_FIXED) return false;
+        if (x->fields[i].kind != DFD_COL_FIXED || x->fields[i].dict) return false;
         if (c->null_count != 0 && c->n_buffers > 0 && c->buffers[0] != nullptr) return false;
     }
     return true;
@@ -456,7 +541,79 @@ int stage_rows(dfd_repartition_exec* x, const ArrowArray* b, int64_t start, int6
         const bool hv = !plain && c->null_count != 0 && c->n_buffers > 0 && c->buffers[0] != nullptr;
         const int64_t bit_off = (hv || f.kind == DFD_COL_BOOL) ? (lo & 7) : 0;
         const size_t bitmap_nb = (size_t)((bit_off + n + 7) >> 3);
-        if (f.var()) {
+        if (f.dict && x->key_of_field[i] >= 0) {
+            // dictionary KEY: hash the dictionary values once on the device (DataFusion hash_dictionary); rows pick dict_hashes[index]
+            const ArrowArray* d = c->dictionary;
+            if (!d) return fail(x, DFD_ERR_INVALID_ARGUMENT, "column " + f.name + ": dictionary array without a dictionary");
+            const int64_t dn = d->offset + d->length;
+            const bool dvar = f.dict_kind == DFD_COL_UTF8 || f.dict_kind == DFD_COL_LARGE_UTF8 || f.dict_kind == DFD_COL_BINARY;
+            const size_t dow = f.dict_kind == DFD_COL_LARGE_UTF8 ? 8 : 4;
+            const bool dhv = d->null_count != 0 && d->n_buffers > 0 && d->buffers[0] != nullptr;
+            int64_t dbytes = 0;
+            if (dvar) dbytes = dow == 4 ? ((const int32_t*)d->buffers[1])[dn] : ((const int64_t*)d->buffers[1])[dn];
+            auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+            const size_t o_hash = 0, o_off = al((size_t)(d->length + 1) * 8), o_data = o_off + al(dvar ? (size_t)(dn + 1) * dow : 0);
+            const size_t vbytes = f.dict_kind == DFD_COL_BOOL ? (size_t)((dn + 7) / 8) : (dvar ? (size_t)dbytes : (size_t)dn * f.dict_width);
+            const size_t o_valid = o_data + al(vbytes + 16), total = o_valid + al((size_t)((dn + 7) / 8) + 16);
+            int rc2 = s.dict_buf[i].ensure(total, x->ctx->device);
+            if (rc2) return fail(x, rc2, dfd_last_error());
+            char* db = (char*)s.dict_buf[i].ptr;
+            if (dvar) XCUDA(x, cudaMemcpyAsync(db + o_off, d->buffers[1], (size_t)(dn + 1) * dow, cudaMemcpyHostToDevice, x->s_h2d), "H2D dictionary offsets");
+            if (vbytes) XCUDA(x, cudaMemcpyAsync(db + o_data, d->buffers[dvar ? 2 : 1], vbytes, cudaMemcpyHostToDevice, x->s_h2d), "H2D dictionary values");
+            if (dhv) XCUDA(x, cudaMemcpyAsync(db + o_valid, d->buffers[0], (size_t)((dn + 7) / 8), cudaMemcpyHostToDevice, x->s_h2d), "H2D dictionary validity");
+            dfd_column dc{f.dict_kind, f.dict_width, db + o_data, dvar ? (void*)(db + o_off) : nullptr, dhv ? (uint8_t*)(db + o_valid) : nullptr, d->offset,
+                          (int64_t)vbytes};
+            rc2 = hash_columns_locked(x->ctx, &dc, 1, d->length, nullptr, (uint64_t*)(db + o_hash), x->s_h2d);
+            if (rc2) return fail(x, rc2, dfd_last_error());
+            s.dict_hashes[i] = (const uint64_t*)(db + o_hash);
+            // the validity handed to the partitioner is indexed by dictionary index (0-based): re-base with the values' offset
+            s.dict_valid[i] = dhv ? (const uint8_t*)(db + o_valid) : nullptr;
+            if (dhv && d->offset != 0) return fail(x, DFD_ERR_UNSUPPORTED, "column " + f.name + ": sliced dictionary values with nulls are not supported yet");
+            x->bytes_h2d += vbytes + (dvar ? (size_t)(dn + 1) * dow : 0);
+        }
+        if (f.var() && f.view) {
+            // Utf8View / BinaryView -> offsets + contiguous bytes on the host (16-byte views: len | 12 inline bytes, or len | prefix |
+            // buffer index | offset into one of the variadic data buffers), then the column is an ordinary Utf8 / Binary one
+            std::vector<char>& vo = s.view_off[i];
+            std::vector<char>& vb = s.view_bytes[i];
+            vo.resize((size_t)(n + 1) * 4);
+            int32_t* off32 = (int32_t*)vo.data();
+            const uint8_t* views = (const uint8_t*)c->buffers[1];
+            const uint8_t* valid = (c->null_count != 0 && c->buffers[0]) ? (const uint8_t*)c->buffers[0] : nullptr;
+            int64_t total = 0;
+            for (int64_t r = 0; r < n; ++r) {
+                const uint8_t* v = views + (size_t)(lo + r) * 16;
+                int32_t len = *(const int32_t*)v;
+                if (valid && !((valid[(lo + r) >> 3] >> ((lo + r) & 7)) & 1)) len = 0;
+                off32[r] = (int32_t)total;
+                total += len;
+            }
+            off32[n] = (int32_t)total;
+            if (total > 0x7fffffffLL) return fail(x, DFD_ERR_UNSUPPORTED, "column " + f.name + ": more than 2 GiB of view data in one chunk");
+            vb.resize((size_t)total + 16);
+            for (int64_t r = 0; r < n; ++r) {
+                const int32_t len = off32[r + 1] - off32[r];
+                if (!len) continue;
+                const uint8_t* v = views + (size_t)(lo + r) * 16;
+                const uint8_t* src = len <= 12 ? v + 4 : (const uint8_t*)c->buffers[2 + *(const int32_t*)(v + 8)] + *(const int32_t*)(v + 12);
+                memcpy(vb.data() + off32[r], src, (size_t)len);
+            }
+            if ((size_t)total > s.in_cap[i]) {
+                cudaFree(s.d_in[i]); cudaFree(s.d_out[i]);
+                s.d_in[i] = s.d_out[i] = nullptr;
+                s.in_cap[i] = s.out_cap[i] = 0;
+                size_t want = (size_t)total + (size_t)total / 4 + 256;
+                XCUDA(x, cudaMalloc(&s.d_in[i], want), "cudaMalloc(string bytes)");
+                XCUDA(x, cudaMalloc(&s.d_out[i], want), "cudaMalloc(string bytes)");
+                s.in_cap[i] = s.out_cap[i] = want;
+            }
+            // (validity keeps its sub-byte bit offset; the offsets are placed at the same logical index)
+            XCUDA(x, cudaMemcpyAsync((char*)s.d_in_off[i] + (size_t)bit_off * 4, vo.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, x->s_h2d), "H2D offsets");
+            if (total) XCUDA(x, cudaMemcpyAsync(s.d_in[i], vb.data(), (size_t)total, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
+            s.first_off[i] = 0;
+            s.data_bytes[i] = total;
+            x->bytes_h2d += (size_t)total + (size_t)(n + 1) * 4;
+        } else if (f.var()) {
             // offsets (n + 1 entries, kept absolute) at logical index bit_off; the bytes they span at d_in
             const size_t ow = f.ow();
             const char* offs = (const char*)c->buffers[1];
@@ -536,11 +693,18 @@ int dfd_schema_supported(const struct ArrowSchema* schema) {
     for (int64_t i = 0; i < schema->n_children; ++i) {
         const ArrowSchema* c = schema->children[i];
         int32_t k, w;
-        if (c->dictionary)
-            return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): dictionary arrays are not supported yet", (long long)i, c->name ? c->name : "");
         if (!c->format || !parse_format(c->format, &k, &w))
             return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): Arrow format '%s' is not supported", (long long)i, c->name ? c->name : "",
                              c->format ? c->format : "(null)");
+        if (c->dictionary) {  // Dictionary<integer index, flat values>: indices are scattered, the dictionary travels by reference
+            if (k != DFD_COL_FIXED || !strchr("cCsSiIlL", c->format[0]) || c->format[1])
+                return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): dictionary index type '%s' is not an integer", (long long)i, c->name ? c->name : "", c->format);
+            int32_t dk, dw;
+            const ArrowSchema* d = c->dictionary;
+            if (d->dictionary || d->n_children > 0 || !d->format || !parse_format(d->format, &dk, &dw))
+                return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): dictionary value type '%s' is not supported", (long long)i, c->name ? c->name : "",
+                                 d->format ? d->format : "(null)");
+        }
     }
     return DFD_OK;
 }
@@ -562,12 +726,25 @@ int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, 
         f.name = c->name ? c->name : "";
         f.format = c->format ? c->format : "";
         f.flags = c->flags;
-        if (c->dictionary) return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): dictionary arrays are not supported yet", (long long)i, f.name.c_str());
         if (!parse_format(f.format.c_str(), &f.kind, &f.width))
             return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): Arrow format '%s' is not supported", (long long)i, f.name.c_str(), f.format.c_str());
-        bool is_key = false;
-        for (int k = 0; k < n_keys; ++k) is_key |= key_cols && key_cols[k] == i;
-        (void)is_key;
+        f.view = f.format[0] == 'v';
+        int key_index = -1;
+        for (int k = 0; k < n_keys; ++k)
+            if (key_cols && key_cols[k] == i) key_index = k;
+        if (c->dictionary) {
+            const ArrowSchema* d = c->dictionary;
+            if (f.kind != DFD_COL_FIXED || !strchr("cCsSiIlL", f.format[0]) || f.format[1])
+                return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): dictionary index type '%s' is not an integer", (long long)i, f.name.c_str(), f.format.c_str());
+            f.dict = true;
+            f.dict_format = d->format ? d->format : "";
+            f.dict_flags = d->flags;
+            if (d->dictionary || d->n_children > 0 || !parse_format(f.dict_format.c_str(), &f.dict_kind, &f.dict_width))
+                return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): dictionary value type '%s' is not supported", (long long)i, f.name.c_str(), f.dict_format.c_str());
+            if (key_index >= 0 && f.dict_format[0] == 'v')
+                return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): dictionary KEY with view-typed values is not supported", (long long)i, f.name.c_str());
+        }
+        x->key_of_field.push_back(key_index);
         x->fields.push_back(f);
     }
     for (int k = 0; k < n_keys; ++k)
@@ -606,6 +783,8 @@ int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, 
             s.d_in_off.assign(C, nullptr); s.d_out_off.assign(C, nullptr);
             s.in_cap.assign(C, 0); s.out_cap.assign(C, 0);
             s.first_off.assign(C, 0); s.data_bytes.assign(C, 0);
+            s.view_off.resize(C); s.view_bytes.resize(C);
+            s.dict_buf.resize(C); s.dict_hashes.assign(C, nullptr); s.dict_valid.assign(C, nullptr);
             for (size_t i = 0; i < C && e == cudaSuccess; ++i) {
                 const FieldInfo& f = x->fields[i];
                 if (f.var()) {  // offsets now, string bytes on demand
@@ -664,8 +843,7 @@ void dfd_repartition_exec_destroy(dfd_repartition_exec* x) {
         if (x->s_d2h) cudaStreamSynchronize(x->s_d2h);
         cudaStreamSynchronize(x->ctx->stream);
         for (Slot& s : x->slots) {
-            for (HeldInput& h : s.held)
-                if (h.array.release) h.array.release(&h.array);
+            s.held.clear();
             if (s.out) { s.out->refs.store(1); s.out->pool = x->pool; chunk_unref(s.out); }
             for (void* p : s.d_in) cudaFree(p);
             for (void* p : s.d_in_valid) cudaFree(p);
@@ -673,6 +851,7 @@ void dfd_repartition_exec_destroy(dfd_repartition_exec* x) {
             for (void* p : s.d_out_valid) cudaFree(p);
             for (void* p : s.d_in_off) cudaFree(p);
             for (void* p : s.d_out_off) cudaFree(p);
+            for (dfd::Scratch& b : s.dict_buf) cudaFree(b.ptr);
             if (s.h_part_starts) cudaFreeHost(s.h_part_starts);
             if (s.e_h2d) cudaEventDestroy(s.e_h2d);
             if (s.e_k) cudaEventDestroy(s.e_k);
@@ -705,42 +884,27 @@ int dfd_repartition_exec_push(dfd_repartition_exec* x, struct ArrowArray* batch)
             return fail(x, DFD_ERR_INVALID_ARGUMENT, "record batch children shorter than the batch, or non-zero struct offset");
         }
     const bool plain = batch_is_plain(x, batch);
+    // ownership of the batch moves to a shared holder: every chunk that stages rows from it (and, for dictionary columns,
+    // every output batch that references its dictionaries) keeps it alive
+    HeldInput holder = std::make_shared<SharedInput>(*batch);
+    batch->release = nullptr;
+    const ArrowArray* in = &holder->array;
     int rc = DFD_OK;
     int64_t done = 0;
     while (done < R) {
         if (x->cur_open) {
             Slot& s = x->slots[x->cur];
             bool must_flush = s.rows > 0 && (!plain || !s.plain || s.rows == x->chunk_rows);
-            if (must_flush) {
-                if ((rc = flush_current(x))) { drop(); return rc; }
-            }
+            if (must_flush && (rc = flush_current(x))) return rc;
         }
-        if (!x->cur_open && (rc = open_next_slot(x))) { drop(); return rc; }
+        if (!x->cur_open && (rc = open_next_slot(x))) return rc;
         Slot& s = x->slots[x->cur];
         int64_t room = x->chunk_rows - s.rows;
         int64_t n = R - done < room ? R - done : room;
-        if ((rc = stage_rows(x, batch, done, n, plain))) { drop(); return rc; }
+        if ((rc = stage_rows(x, in, done, n, plain))) return rc;
+        s.held.push_back(holder);
         done += n;
-        if (s.rows == x->chunk_rows || !plain) {
-            // keep the input alive until this chunk's H2D has completed (emit_slot releases it)
-            if (done == R) {
-                HeldInput h;
-                h.array = *batch;
-                batch->release = nullptr;  // ownership moved
-                s.held.push_back(h);
-            }
-            if ((rc = flush_current(x))) return rc;
-            if (done < R) {
-                // the same batch continues in the next slot: wait for this slot's H2D before moving on
-                // (the batch is released only after its last piece) — nothing to do, events order it
-            }
-        }
-    }
-    if (batch->release) {  // plain batch fully appended to a still-open chunk
-        HeldInput h;
-        h.array = *batch;
-        batch->release = nullptr;
-        x->slots[x->cur].held.push_back(h);
+        if ((s.rows == x->chunk_rows || !plain) && (rc = flush_current(x))) return rc;
     }
     return emit_ready(x);
 }

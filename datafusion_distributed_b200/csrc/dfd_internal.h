@@ -53,6 +53,8 @@ struct dfd_partitioner {
     uint32_t N = 0;
     std::vector<int32_t> key_cols;
     std::vector<int32_t> key_modes;  // dfd_key_hash_mode per key column
+    struct KeyDict { const uint64_t* hashes = nullptr; const uint8_t* validity = nullptr; };
+    std::vector<KeyDict> key_dicts;  // DFD_KEY_HASH_DICTIONARY: device hashes / validity of the dictionary values
     dfd::HashState st{};
     dfd::ModN mod{};
     int64_t* d_part_starts = nullptr;  // [N+1]
@@ -130,6 +132,9 @@ int launch_scatter_onepass_local(const ScatterParams& sp, int width, bool fast, 
 int launch_scatter_onepass_peer(const ScatterParams& sp, int width, bool fast, int sm_count, size_t smem, cudaStream_t stream);
 int launch_scatter_follow_local(const ScatterParams& sp, int width, bool fast, int sm_count, size_t smem, cudaStream_t stream);
 int launch_scatter_follow_peer(const ScatterParams& sp, int width, bool fast, int sm_count, size_t smem, cudaStream_t stream);
+
+// create_hashes over device columns -> raw u64 row hashes (dictionary values, parity hook).  Caller holds ctx->mu.
+int hash_columns_locked(Ctx* c, const dfd_column* cols, int n_cols, int64_t n_rows, const uint64_t* seeds, uint64_t* hashes_device, cudaStream_t stream);
 
 // Launches K1 -> K1b -> K2 on `stream`; caller holds ctx->mu and has set the device.
 int partition_device_locked(Partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,

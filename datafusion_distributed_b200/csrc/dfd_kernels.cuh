@@ -97,6 +97,13 @@ static __global__ void k_partition_ids(KeySet keys, HashState st, ModN mod, int6
         dest[r] = mod_n(row_hash<false>(keys, r, st), mod);
 }
 
+// create_hashes over the given key columns, raw 64-bit hashes (used for dictionary VALUES: DataFusion's hash_dictionary
+// hashes the values array once and rows pick dict_hashes[index]; also a parity hook for create_hashes itself)
+static __global__ void k_row_hashes(KeySet keys, HashState st, int64_t n_rows, uint64_t* __restrict__ out) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x)
+        out[r] = row_hash<false>(keys, r, st);
+}
+
 // ---------------------------------------------------------------------------
 // K1: per-tile destination histogram.  Tile t covers rows [t*T, (t+1)*T) —
 // the same tiling K2 uses.  hist is destination-major ([N][n_tiles]) so the

@@ -51,6 +51,23 @@ class HashPartitioner:
         """Interval(DayTime) / Interval(MonthDayNano) keys hash field by field (`dfd_partitioner_set_key_hash_mode`)."""
         nv.check(nv.lib().dfd_partitioner_set_key_hash_mode(self._h, key_index, mode))
 
+    def set_key_dictionary(self, key_index: int, dictionary_values):
+        """Key column `key_index` holds dictionary INDICES of `dictionary_values` (a pyarrow Array, or None to make the key
+        plain again): hash the values once on the device (`dfd_hash_columns_device`) and let rows take
+        dict_hashes[index] (`dfd_partitioner_set_key_dictionary`) — DataFusion's hash_dictionary."""
+        if not hasattr(self, "_dicts"):
+            self._dicts = {}
+        if dictionary_values is None:
+            nv.check(nv.lib().dfd_partitioner_set_key_dictionary(self._h, key_index, None, None))
+            self._dicts.pop(key_index, None)
+            return
+        vals = DeviceColumn.from_arrow(self.ctx, dictionary_values)
+        n = len(dictionary_values)
+        hashes = self.ctx.alloc(max(n * 8, 8))
+        nv.check(nv.lib().dfd_hash_columns_device(self.ctx.handle, columns_to_c([vals]), 1, n, None, hashes.ptr))
+        nv.check(nv.lib().dfd_partitioner_set_key_dictionary(self._h, key_index, hashes.ptr, vals.validity or None))
+        self._dicts[key_index] = (vals, hashes)  # keep the device buffers alive
+
     @property
     def num_partitions(self) -> int:
         return self.partitioning.partition_count

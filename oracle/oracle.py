@@ -173,6 +173,12 @@ class _Cols:
             return
         if isinstance(col, pa.ChunkedArray):
             col = col.combine_chunks()
+        if isinstance(col, pa.DictionaryArray):
+            # DataFusion hash_dictionary: a row hashes as its dictionary VALUE (null index / null value: skipped) — exactly the
+            # hash of the decoded array
+            col = col.dictionary_decode()
+        if pa.types.is_string_view(col.type) if hasattr(pa.types, "is_string_view") else False:
+            col = col.cast(pa.string())  # Utf8View hashes over the string bytes exactly like Utf8
         assert isinstance(col, pa.Array), type(col)
         self.keep.append(col)
         bufs = col.buffers()

@@ -90,7 +90,10 @@ def test_schema_support_helpers_run_without_a_gpu(built):
         k, w = C.c_int32(-1), C.c_int32(-1)
         assert L.dfd_arrow_format_layout(fmt, C.byref(k), C.byref(w)) == 0, fmt
         assert (k.value, w.value) == (kind, width), fmt
-    for fmt in (b"+l", b"+s", b"vu", b"d:76,0,256", b"w:16", b"n", b"Z"):
+    for fmt, (kind, width) in {b"vu": (2, 0), b"vz": (4, 0)}.items():  # Utf8View / BinaryView move as Utf8 / Binary on the device
+        k, w = C.c_int32(-1), C.c_int32(-1)
+        assert L.dfd_arrow_format_layout(fmt, C.byref(k), C.byref(w)) == 0 and (k.value, w.value) == (kind, width), fmt
+    for fmt in (b"+l", b"+s", b"d:76,0,256", b"w:16", b"n", b"Z"):
         assert L.dfd_arrow_format_layout(fmt, None, None) == 6, fmt  # DFD_ERR_UNSUPPORTED
 
     def supported(schema):
@@ -104,8 +107,11 @@ def test_schema_support_helpers_run_without_a_gpu(built):
     ok = pa.schema([("id", pa.int64()), ("metric", pa.float64()), ("flag", pa.bool_()), ("label", pa.string()), ("raw", pa.uint8()),
                     ("ts", pa.timestamp("ns")), ("count", pa.int32()), ("price", pa.decimal128(15, 2)), ("blob", pa.binary())])
     assert supported(ok)[0] == 0
-    # the two columns of the reference's bench fixture (src/execution_plans/benchmarks/fixture.rs:13-33) that are still "next"
-    st, why = supported(pa.schema([("id", pa.int64()), ("category", pa.dictionary(pa.int32(), pa.string()))]))
-    assert st == 6 and "dictionary" in why
+    # the reference's bench fixture (src/execution_plans/benchmarks/fixture.rs:13-33): Dictionary<Int32, Utf8> is supported
+    # (indices scattered, dictionary by reference), and so are view types; List<Utf8> is the one column still "next"
+    assert supported(pa.schema([("id", pa.int64()), ("category", pa.dictionary(pa.int32(), pa.string())), ("v", pa.string_view()),
+                                ("bv", pa.binary_view()), ("d8", pa.dictionary(pa.int8(), pa.int64()))]))[0] == 0
+    st, why = supported(pa.schema([("id", pa.int64()), ("nested", pa.dictionary(pa.int32(), pa.list_(pa.int32())))]))
+    assert st == 6 and "dictionary value type" in why
     st, why = supported(pa.schema([("id", pa.int64()), ("tags", pa.list_(pa.string()))]))
     assert st == 6 and "tags" in why

@@ -179,3 +179,42 @@ def test_all_empty_strings_chunk(ctx):
         total += out.num_rows
     assert total == n
     ex.close()
+
+
+def test_utf8view_and_dictionary_columns_round_trip(ctx):
+    """Utf8View columns (what DataFusion reads parquet strings as by default) and Dictionary<Int32, Utf8> columns (the
+    reference's bench schema, src/execution_plans/benchmarks/fixture.rs:13-33), as keys and as payload: the output
+    batches keep the input schema (views stay views, dictionaries travel by reference) and every destination equals the
+    oracle's rows, in order.  The reference GC's such arrays before its network hop (impl_execute_task.rs:248-271); here
+    the output views point into one compact per-chunk data buffer, which is the same effect."""
+    rnd = random.Random(9)
+    n, N = 40_000, 12
+    words = ["", "a", "hello", "x" * 12, "y" * 13, "a-much-longer-string-than-twelve-bytes", "ünïcödé-" * 3]
+    sv = pa.array([rnd.choice([None] + words) + ("" if rnd.random() < 0.5 else str(rnd.getrandbits(20))) if rnd.random() > 0.1 else None
+                   for _ in range(n)], type=pa.string()).cast(pa.string_view())
+    dict_values = pa.array(["red", "green", None, "blue-" * 5, ""], type=pa.string())
+    cat = pa.DictionaryArray.from_arrays(pa.array([rnd.choice([None, 0, 1, 2, 3, 4]) for _ in range(n)], type=pa.int32()), dict_values)
+    idv = pa.array([rnd.getrandbits(30) for _ in range(n)], type=pa.int64())
+    bv = pa.array([None if rnd.random() < 0.2 else bytes(rnd.getrandbits(8) for _ in range(rnd.randint(0, 20))) for _ in range(n)],
+                  type=pa.binary()).cast(pa.binary_view())
+    table = pa.table([idv, sv, cat, bv], names=["id", "label", "category", "raw"])
+    for keys in ([0], [1], [2], [2, 1, 0]):
+        ex = dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash(keys, N), chunk_rows=8_192)
+        cuts = [0, 5, 5_000, 5_003, 20_001, n]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            for rb in table.slice(a, b - a).to_batches(max_chunksize=3_000):
+                ex.push_batch(rb)
+        ex.finish()
+        outs = collect(ex, N)
+        dest = orc.partition_ids([table.column(k).combine_chunks() for k in keys], n, N)
+        order, starts = expected_partitions(dest, N)
+        for p in range(N):
+            want = table.take(pa.array(order[starts[p]:starts[p + 1]]))
+            assert outs[p].schema.equals(table.schema), (keys, p, outs[p].schema)
+            assert outs[p].num_rows == want.num_rows, (keys, p)
+            for name in table.column_names:
+                got_c, want_c = outs[p].column(name).combine_chunks(), want.column(name).combine_chunks()
+                if pa.types.is_dictionary(got_c.type):
+                    got_c, want_c = got_c.dictionary_decode(), want_c.dictionary_decode()
+                assert got_c.cast(want_c.type).equals(want_c), (keys, p, name)
+        ex.close()

@@ -386,3 +386,37 @@ def test_interval_keys_hash_field_by_field_on_gpu(ctx):
     assert not np.array_equal(plain, orc.partition_ids([("interval_day_time", raw_dt.view(np.uint8))], n, 1000))
     with pytest.raises(dfd.DfdError):
         dfd.HashPartitioner(ctx, dfd.Partitioning.Hash([0], 8)).set_key_hash_mode(0, 7)
+
+
+def test_dictionary_keys_hash_through_their_values(ctx):
+    """Dictionary<Int32, Utf8> / Dictionary<Int8, Int64> key columns (the reference's bench schema: fixture.rs:13-33):
+    placement equals hashing the decoded values; null indices and null dictionary values contribute nothing."""
+    rnd = random.Random(4)
+    n = 30_000
+    values = pa.array(["alpha", None, "", "gamma-" * 9, "δ", "zz"], type=pa.string())
+    idx = pa.array([rnd.choice([None, 0, 1, 2, 3, 4, 5]) for _ in range(n)], type=pa.int32())
+    d = pa.DictionaryArray.from_arrays(idx, values)
+    other = pa.array([rnd.getrandbits(20) for _ in range(n)], type=pa.int64())
+    ivalues = pa.array([7, -1, None, 1 << 40], type=pa.int64())
+    idx8 = pa.array([rnd.choice([None, 0, 1, 2, 3]) for _ in range(n)], type=pa.int8())
+    d2 = pa.DictionaryArray.from_arrays(idx8, ivalues)
+    cols = dev_cols(ctx, [idx, other, idx8])  # the INDICES travel as plain fixed-width columns
+    for N in (8, 48, 1000):
+        part = dfd.HashPartitioner(ctx, dfd.Partitioning.Hash([0], N))
+        part.set_key_dictionary(0, values)
+        assert np.array_equal(part.partition_ids(cols, n), orc.partition_ids([d], n, N)), N
+        part = dfd.HashPartitioner(ctx, dfd.Partitioning.Hash([1, 0, 2], N))
+        part.set_key_dictionary(1, values)
+        part.set_key_dictionary(2, ivalues)
+        assert np.array_equal(part.partition_ids(cols, n), orc.partition_ids([other, d, d2], n, N)), N
+    # and the scatter itself (indices + payload) with a dictionary key
+    part = dfd.HashPartitioner(ctx, dfd.Partitioning.Hash([0], 12))
+    part.set_key_dictionary(0, values)
+    outs, starts = part.partition(cols, n)
+    dest = orc.partition_ids([d], n, 12)
+    order, ref_starts = expected_partitions(dest, 12)
+    assert np.array_equal(starts, ref_starts)
+    assert outs[0].to_arrow(ctx, 0, n).equals(idx.take(pa.array(order)))
+    assert outs[1].to_arrow(ctx, 0, n).equals(other.take(pa.array(order)))
+    part.set_key_dictionary(0, None)
+    assert np.array_equal(part.partition_ids([cols[1]], n), orc.partition_ids([other], n, 12))  # plain key again
