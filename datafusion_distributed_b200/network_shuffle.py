@@ -226,10 +226,12 @@ class NetworkShuffleExec:
             data = pa.py_buffer(grab(col.values + start * col.width, count * col.width).tobytes())
             return pa.Array.from_buffers(col.arrow_type, count, [validity_buf, data], null_count=null_count)
         ow = 8 if col.kind == nv.COL_LARGE_UTF8 else 4
+        if count == 0:
+            return pa.array([], type=col.arrow_type)
         off = grab(col.offsets + start * ow, (count + 1) * ow).view(np.int64 if ow == 8 else np.int32)
-        lo, hi = (int(off[0]), int(off[-1])) if count else (0, 0)
+        lo, hi = int(off[0]), int(off[-1])
         data = pa.py_buffer(grab(col.values + lo, hi - lo).tobytes())
-        offs = pa.py_buffer((off - lo).astype(off.dtype).tobytes()) if count else pa.py_buffer(np.zeros(1, dtype=off.dtype if count else np.int32).tobytes())
+        offs = pa.py_buffer((off - lo).astype(off.dtype).tobytes())
         return pa.Array.from_buffers(col.arrow_type, count, [validity_buf, offs, data], null_count=null_count)
 
     def collect(self, exchange: ShuffleExchange):

@@ -116,8 +116,8 @@ def test_single_partition_and_pinned_input(ctx):
 
 def test_operator_errors(ctx):
     with pytest.raises(dfd.DfdError) as e:
-        dfd.RepartitionExec(ctx, pa.schema([("s", pa.dictionary(pa.int32(), pa.string()))]), dfd.Partitioning.Hash([0], 4))
-    assert e.value.status == 6  # DFD_ERR_UNSUPPORTED: dictionary arrays are a "next" row
+        dfd.RepartitionExec(ctx, pa.schema([("s", pa.list_(pa.string()))]), dfd.Partitioning.Hash([0], 4))
+    assert e.value.status == 6  # DFD_ERR_UNSUPPORTED: nested types are the remaining "next" part of SURVEY §8 f1
     sch = pa.schema([("k", pa.int64())])
     with pytest.raises(dfd.DfdError):
         dfd.RepartitionExec(ctx, sch, dfd.Partitioning.Hash([1], 4))
@@ -190,7 +190,7 @@ def test_utf8view_and_dictionary_columns_round_trip(ctx):
     rnd = random.Random(9)
     n, N = 40_000, 12
     words = ["", "a", "hello", "x" * 12, "y" * 13, "a-much-longer-string-than-twelve-bytes", "ünïcödé-" * 3]
-    sv = pa.array([rnd.choice([None] + words) + ("" if rnd.random() < 0.5 else str(rnd.getrandbits(20))) if rnd.random() > 0.1 else None
+    sv = pa.array([rnd.choice(words) + ("" if rnd.random() < 0.5 else str(rnd.getrandbits(20))) if rnd.random() > 0.1 else None
                    for _ in range(n)], type=pa.string()).cast(pa.string_view())
     dict_values = pa.array(["red", "green", None, "blue-" * 5, ""], type=pa.string())
     cat = pa.DictionaryArray.from_arrays(pa.array([rnd.choice([None, 0, 1, 2, 3, 4]) for _ in range(n)], type=pa.int32()), dict_values)
@@ -198,6 +198,8 @@ def test_utf8view_and_dictionary_columns_round_trip(ctx):
     bv = pa.array([None if rnd.random() < 0.2 else bytes(rnd.getrandbits(8) for _ in range(rnd.randint(0, 20))) for _ in range(n)],
                   type=pa.binary()).cast(pa.binary_view())
     table = pa.table([idv, sv, cat, bv], names=["id", "label", "category", "raw"])
+    # (pyarrow has no take / hash kernels for view types: the expectation is computed on the same data as Utf8 / Binary)
+    plain = pa.table([idv, sv.cast(pa.string()), cat, bv.cast(pa.binary())], names=table.column_names)
     for keys in ([0], [1], [2], [2, 1, 0]):
         ex = dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash(keys, N), chunk_rows=8_192)
         cuts = [0, 5, 5_000, 5_003, 20_001, n]
@@ -206,10 +208,10 @@ def test_utf8view_and_dictionary_columns_round_trip(ctx):
                 ex.push_batch(rb)
         ex.finish()
         outs = collect(ex, N)
-        dest = orc.partition_ids([table.column(k).combine_chunks() for k in keys], n, N)
+        dest = orc.partition_ids([plain.column(k).combine_chunks() for k in keys], n, N)
         order, starts = expected_partitions(dest, N)
         for p in range(N):
-            want = table.take(pa.array(order[starts[p]:starts[p + 1]]))
+            want = plain.take(pa.array(order[starts[p]:starts[p + 1]]))
             assert outs[p].schema.equals(table.schema), (keys, p, outs[p].schema)
             assert outs[p].num_rows == want.num_rows, (keys, p)
             for name in table.column_names:

@@ -58,6 +58,8 @@ def upload(ctx, cols):
 
     keep, dcols = [], []
     for c in cols:
+        if c.shape[0] == 0:  # (a zero-element torch tensor has no storage: give the descriptor a real address)
+            c = np.zeros((1,) + c.shape[1:], dtype=c.dtype)
         t = torch.from_numpy(np.ascontiguousarray(c)).cuda()
         keep.append(t)
         if c.ndim == 2:
