@@ -67,7 +67,8 @@ class DfdMetrics(C.Structure):
 
 
 class DfdExecOptions(C.Structure):
-    _fields_ = [("chunk_rows", C.c_int64), ("pipeline_depth", C.c_int32), ("pinned_pool_chunks", C.c_int32)]
+    _fields_ = [("chunk_rows", C.c_int64), ("pipeline_depth", C.c_int32), ("pinned_pool_chunks", C.c_int32),
+                ("max_pinned_chunks", C.c_int32), ("reserved", C.c_int32)]
 
 
 class DfdExecStats(C.Structure):

@@ -324,6 +324,7 @@ struct dfd_exchange {
     // NCCL mode staging (locally partitioned columns)
     Scratch send;
     Scratch recv_tmp;  // receiver-side temporaries (u8 images of bitmaps, string lengths)
+    Scratch bytes_all; // NCCL mode: all-gathered per-destination byte counts of the string columns (reused across shuffles)
     // fused mode: receive window + peers' mappings
     void* window = nullptr;
     size_t window_bytes = 0;
@@ -481,6 +482,7 @@ void dfd_exchange_destroy(dfd_exchange* x) {
         cudaFree(x->d_abort);
         cudaFree(x->send.ptr);
         cudaFree(x->recv_tmp.ptr);
+        cudaFree(x->bytes_all.ptr);
         cudaFree(x->in_stage[0].ptr);
         cudaFree(x->in_stage[1].ptr);
         for (int i = 0; i < 2; ++i) {
@@ -1199,12 +1201,13 @@ int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* part, int mode, const d
     std::vector<int64_t> h_first(V * N), h_bytes(V * (size_t)T * N);
     int64_t* d_bytes_all = nullptr;
     if (V) {
-        CUDA_TRY(cudaMalloc((void**)&d_bytes_all, sizeof(int64_t) * V * (size_t)T * N), "cudaMalloc(byte counts)");
+        if ((rc = x->bytes_all.ensure(sizeof(int64_t) * V * (size_t)T * N + 256, c->device))) return rc;
+        d_bytes_all = (int64_t*)x->bytes_all.ptr;
         for (size_t v = 0; v < V; ++v) {
             int64_t* d_meta = (int64_t*)(sb + meta_off) + v * 2 * N;
             if (T > 1) {
                 ncclResult_t r = n->AllGather(d_meta, d_bytes_all + v * (size_t)T * N, N, ncclInt64, x->comm, s);
-                if (r != ncclSuccess) { cudaFree(d_bytes_all); return nccl_error(r, "ncclAllGather(byte counts)"); }
+                if (r != ncclSuccess) return nccl_error(r, "ncclAllGather(byte counts)");
             } else {
                 cudaMemcpyAsync(d_bytes_all + v * N, d_meta, sizeof(int64_t) * N, cudaMemcpyDeviceToDevice, s);
             }
@@ -1213,7 +1216,6 @@ int dfd_shuffle_device(dfd_exchange* x, dfd_partitioner* part, int mode, const d
         cudaMemcpyAsync(h_bytes.data(), d_bytes_all, sizeof(int64_t) * V * (size_t)T * N, cudaMemcpyDeviceToHost, s);
     }
     cudaError_t se = cudaStreamSynchronize(s);
-    if (d_bytes_all) cudaFree(d_bytes_all);
     if (se != cudaSuccess) return cuda_error(se, "count exchange");
     std::vector<int64_t> send_start(N), recv_start((size_t)P * T);
     int64_t recv_rows = 0;

@@ -109,8 +109,10 @@ struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
     int64_t chunk_rows = 0;
     std::vector<FieldInfo> fields;
     std::mutex mu;
+    std::condition_variable cv;
     std::vector<OutChunk*> free_list;
     std::vector<OutChunk*> all;
+    size_t max_chunks = 0;  // 0 = unbounded; otherwise acquire() blocks until a consumer returns a chunk (back-pressure)
 
     static size_t value_bytes(const FieldInfo& f, int64_t rows) {
         if (f.var()) return 0;  // string bytes are sized per chunk
@@ -118,9 +120,24 @@ struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
     }
     static size_t bitmap_bytes(int64_t rows) { return (size_t)((rows + 63) / 64 * 8 + 8); }
 
+    static void destroy_chunk(OutChunk* c) {
+        for (void* p : c->values)
+            if (p) cudaFreeHost(p);
+        for (void* p : c->validity)
+            if (p) cudaFreeHost(p);
+        for (void* p : c->offsets)
+            if (p) cudaFreeHost(p);
+        for (void* p : c->views) free(p);
+        delete c;
+    }
+
+    // A pooled pinned chunk.  With a bound (`max_chunks`), the producer BLOCKS here until a consumer has released a chunk:
+    // that is the operator's back-pressure (the reference bounds the same hand-off with its byte budget,
+    // src/worker/worker_connection_pool.rs:151-153, 251-257).
     OutChunk* acquire() {
         {
-            std::lock_guard<std::mutex> lk(mu);
+            std::unique_lock<std::mutex> lk(mu);
+            if (max_chunks && free_list.empty() && all.size() >= max_chunks) cv.wait(lk, [&] { return !free_list.empty(); });
             if (!free_list.empty()) {
                 OutChunk* c = free_list.back();
                 free_list.pop_back();
@@ -134,10 +151,17 @@ struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
             void* v = nullptr;
             void* b = nullptr;
             void* o = nullptr;
-            if (!f.var() && cudaHostAlloc(&v, value_bytes(f, chunk_rows), cudaHostAllocPortable) != cudaSuccess) return nullptr;
-            if ((f.flags & ARROW_FLAG_NULLABLE) && cudaHostAlloc(&b, bitmap_bytes(chunk_rows), cudaHostAllocPortable) != cudaSuccess)
+            bool ok = true;
+            if (!f.var() && cudaHostAlloc(&v, value_bytes(f, chunk_rows), cudaHostAllocPortable) != cudaSuccess) ok = false;
+            if (ok && (f.flags & ARROW_FLAG_NULLABLE) && cudaHostAlloc(&b, bitmap_bytes(chunk_rows), cudaHostAllocPortable) != cudaSuccess) ok = false;
+            if (ok && f.var() && cudaHostAlloc(&o, (size_t)(chunk_rows + 16) * f.ow(), cudaHostAllocPortable) != cudaSuccess) ok = false;
+            if (!ok) {  // free what this chunk already holds: nothing leaks on a failed allocation
+                if (v) cudaFreeHost(v);
+                if (b) cudaFreeHost(b);
+                if (o) cudaFreeHost(o);
+                destroy_chunk(c);
                 return nullptr;
-            if (f.var() && cudaHostAlloc(&o, (size_t)(chunk_rows + 16) * f.ow(), cudaHostAllocPortable) != cudaSuccess) return nullptr;
+            }
             c->values.push_back(v);
             c->validity.push_back(b);
             c->offsets.push_back(o);
@@ -151,20 +175,14 @@ struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
     }
     void give_back(OutChunk* c) {
         c->inputs.clear();  // (drops the references to the input batches whose dictionaries were handed out)
-        std::lock_guard<std::mutex> lk(mu);
-        free_list.push_back(c);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            free_list.push_back(c);
+        }
+        cv.notify_one();
     }
     ~PinnedPool() {
-        for (OutChunk* c : all) {
-            for (void* p : c->values)
-                if (p) cudaFreeHost(p);
-            for (void* p : c->validity)
-                if (p) cudaFreeHost(p);
-            for (void* p : c->offsets)
-                if (p) cudaFreeHost(p);
-            for (void* p : c->views) free(p);
-            delete c;
-        }
+        for (OutChunk* c : all) destroy_chunk(c);
     }
 };
 
@@ -819,6 +837,8 @@ int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, 
     x->pool->device = ctx->device;
     x->pool->chunk_rows = x->chunk_rows;
     x->pool->fields = x->fields;
+    x->pool->max_chunks = (opts && opts->max_pinned_chunks > 0) ? (size_t)opts->max_pinned_chunks : 0;
+    if (x->pool->max_chunks && x->pool->max_chunks < (size_t)pool_chunks) x->pool->max_chunks = (size_t)pool_chunks;
     std::vector<OutChunk*> pre;
     for (int i = 0; i < pool_chunks; ++i) {
         OutChunk* c = x->pool->acquire();

@@ -69,14 +69,14 @@ class RepartitionExec:
     """`RepartitionExec::try_new(input, Partitioning::Hash(exprs, n))` on one GPU worker."""
 
     def __init__(self, ctx: WorkerContext, schema, partitioning: Partitioning, chunk_rows: int = 0,
-                 pipeline_depth: int = 0, pinned_pool_chunks: int = 0):
+                 pipeline_depth: int = 0, pinned_pool_chunks: int = 0, max_pinned_chunks: int = 0):
         self.ctx = ctx
         self.schema = schema
         self.partitioning = partitioning
         cs = nv.ArrowSchemaStruct()
         schema._export_to_c(C.addressof(cs))
         keys = (C.c_int32 * len(partitioning.key_cols))(*partitioning.key_cols)
-        opts = nv.DfdExecOptions(chunk_rows, pipeline_depth, pinned_pool_chunks)
+        opts = nv.DfdExecOptions(chunk_rows, pipeline_depth, pinned_pool_chunks, max_pinned_chunks, 0)
         self._h = C.c_void_p()
         try:
             nv.check(nv.lib().dfd_repartition_exec_create(ctx.handle, C.byref(cs), keys, len(partitioning.key_cols),

@@ -221,7 +221,9 @@ int dfd_partitioner_collect(dfd_partitioner* p, int64_t* part_starts_host, int64
  *   schema    : struct ("+s") schema of the input batches (borrowed)
  *   push      : feed one input RecordBatch (struct ArrowArray); ownership of
  *               `batch` moves to the operator (released after its H2D copy).
- *               Single producer thread; may block on the pipeline.
+ *               Single producer thread; blocks on the pipeline depth, and — with
+ *               dfd_exec_options.max_pinned_chunks — on consumers that have not
+ *               released their batches yet (back-pressure).
  *   finish    : end of input; drains the pipeline.
  *   run       : pull `input` (≙ child.execute()) to exhaustion, then finish.
  *   execute   : stream of destination `partition`'s batches; get_next blocks
@@ -232,8 +234,14 @@ int dfd_partitioner_collect(dfd_partitioner* p, int64_t* part_starts_host, int64
  *               (src/worker/worker_connection_pool.rs:393-397).
  * Rows inside (one input chunk, one destination) keep input order.
  * Supported columns: fixed-width primitives (incl. Decimal128, timestamps,
- * dates), Boolean, Utf8 / LargeUtf8 / Binary, all nullable.  Dictionary, view
- * and nested types: DFD_ERR_UNSUPPORTED (remaining part). */
+ * dates, intervals), Boolean, Utf8 / LargeUtf8 / Binary, Utf8View / BinaryView
+ * (converted to offsets + bytes on the way in; the output batches carry
+ * compact views over one data buffer per chunk — the effect of the reference's
+ * `gc()` before its network hop, src/worker/impl_execute_task.rs:248-271) and
+ * Dictionary<integer, flat values> (the indices are scattered, every output
+ * batch references the input batch's dictionary; dictionary KEYS are hashed
+ * through their values on the device), all nullable.  Nested types (List,
+ * Struct, Map): DFD_ERR_UNSUPPORTED (remaining part). */
 typedef struct dfd_repartition_exec dfd_repartition_exec;
 
 /* Pure host helpers (no GPU needed) for the plan hook that decides whether a stage-head
@@ -253,6 +261,11 @@ typedef struct {
     int64_t chunk_rows;         /* rows per device chunk; 0 = 4Mi                   */
     int32_t pipeline_depth;     /* chunks in flight (H2D | kernels | D2H); 0 = 3    */
     int32_t pinned_pool_chunks; /* pinned output chunks preallocated; 0 = depth + 1 */
+    int32_t max_pinned_chunks;  /* 0 = the pool grows on demand (a slow consumer costs pinned memory, nothing blocks);
+                                   > 0 = hard bound: push()/finish() BLOCK until a consumer releases a chunk — the
+                                   operator's back-pressure (needs concurrent consumers, like the reference's bounded
+                                   hand-off, src/worker/worker_connection_pool.rs:151-153) */
+    int32_t reserved;
 } dfd_exec_options;
 
 typedef struct {

@@ -220,3 +220,36 @@ def test_utf8view_and_dictionary_columns_round_trip(ctx):
                     got_c, want_c = got_c.dictionary_decode(), want_c.dictionary_decode()
                 assert got_c.cast(want_c.type).equals(want_c), (keys, p, name)
         ex.close()
+
+
+def test_bounded_pinned_pool_blocks_the_producer_until_consumers_release(ctx):
+    """max_pinned_chunks: the producer's push() blocks (back-pressure) instead of growing pinned memory without bound;
+    with concurrent consumers everything still arrives, in order."""
+    import threading
+    import time
+
+    n, N = 400_000, 4
+    cols = cfg2_columns(n, 2)
+    table = pa.table(cols, names=["k", "v"])
+    ex = dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash([0], N), chunk_rows=16_384, pipeline_depth=2, pinned_pool_chunks=3,
+                             max_pinned_chunks=3)
+    got = [[] for _ in range(N)]
+
+    def consume(p):
+        for rb in ex.execute(p):
+            time.sleep(0.0005)  # a slow consumer: holds its batch for a moment before dropping it
+            got[p].append(rb.column(1).to_numpy().copy())
+            del rb
+
+    threads = [threading.Thread(target=consume, args=(p,)) for p in range(N)]
+    for t in threads:
+        t.start()
+    for rb in table.to_batches(max_chunksize=8_192):
+        ex.push_batch(rb)
+    ex.finish()
+    for t in threads:
+        t.join()
+    ref, counts, starts = orc.repartition_table(cols, [0], N, 8192, 1)
+    for p in range(N):
+        assert np.array_equal(np.concatenate(got[p]), ref[1][starts[p]:starts[p + 1]])
+    ex.close()
