@@ -435,8 +435,104 @@ def run_cfg3(args, torch, dfd, world):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------- agg ----
+
+def run_agg(args, torch, dfd, world):
+    """PartialReduce ahead of the shuffle: the producer's Partial-aggregate output (group key + 4 states) enters
+    from HOST memory once, is repartitioned (K1/K1b/K2), reduced per destination (dfd_partial_reduce_device) and — at world > 1 —
+    exchanged (pre-partitioned shuffle) on the device; only the REDUCED rows come back to the host.  e2e = wall clock over the
+    whole table, H2D of every chunk and D2H of every reduced chunk inside the timed region."""
+    from datafusion_distributed_b200 import _native as nv
+
+    dist, rank, local_rank, ctx, ex = _dist_setup(torch, dfd, world)
+    n_total = args.rows
+    groups = 1 << 16
+    P = 8 // world if 8 % world == 0 else 1
+    N = P * world
+    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    n = hi - lo
+    chunk = 1 << 22
+    ops = [-1, nv.AGG_SUM_I64, nv.AGG_SUM_I64, nv.AGG_MIN_I64, nv.AGG_MAX_I64]
+    pt = dfd.PinnedTable(ctx, n, [np.int64] * 5)
+    rng = np.random.Generator(np.random.PCG64([77, rank]))
+    for a in range(0, n, chunk):
+        b = min(a + chunk, n)
+        pt.columns[0][a:b] = rng.integers(0, groups, b - a, dtype=np.int64) * 2_654_435_761
+        for j in range(1, 5):
+            pt.columns[j][a:b] = rng.integers(-(1 << 40), 1 << 40, b - a, dtype=np.int64)
+    lib_stream = torch.cuda.ExternalStream(ctx.stream_ptr())
+    d_in = [torch.empty(chunk, dtype=torch.int64, device="cuda") for _ in range(5)]
+    d_part = [torch.empty(chunk, dtype=torch.int64, device="cuda") for _ in range(5)]
+    d_red = [torch.empty(chunk, dtype=torch.int64, device="cuda") for _ in range(5)]
+    h_red = dfd.PinnedTable(ctx, chunk, [np.int64] * 5)
+    h_red_t = [torch.from_numpy(c) for c in h_red.columns]
+    h_in_t = [torch.from_numpy(c) for c in pt.columns]
+    part = dfd.HashPartitioner(ctx, dfd.Partitioning.Hash([0], N))
+    red = dfd.PartialReduceExec(ctx, [0], ops)
+    node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0], P), uuid.uuid4(), 9, world, world)
+    if world > 1:
+        ex.setup_window(64 << 20)
+    in_cols = [dfd.DeviceColumn.from_torch(t) for t in d_in]
+    part_cols = [dfd.DeviceColumn.from_torch(t) for t in d_part]
+    red_cols = [dfd.DeviceColumn.from_torch(t) for t in d_red]
+
+    def one_pass():
+        rows_out = h2d = d2h = 0
+        for a in range(0, n, chunk):
+            m = min(chunk, n - a)
+            with torch.cuda.stream(lib_stream):
+                for j in range(5):
+                    d_in[j][:m].copy_(h_in_t[j][a:a + m], non_blocking=True)
+            h2d += m * 40
+            part.partition(in_cols, m, part_cols, sync=False)
+            _, out_starts = red.reduce(part_cols, m, part.part_starts_device_ptr(), N, red_cols)
+            g = int(out_starts[-1])
+            if world > 1:
+                wcols, ss, sc = node.shuffle_partitioned(ex, red_cols, out_starts)
+                g = int(sc.sum())
+                for q in range(P):  # the consumer reads its segments from the window: copy them to the host
+                    for r in range(world):
+                        cnt = int(sc[q, r])
+                        if cnt:
+                            for j in range(5):
+                                nv.check(nv.lib().dfd_memcpy_d2h(ctx.handle, h_red.columns[j].ctypes.data, wcols[j].values + int(ss[q, r]) * 8, cnt * 8))
+            else:
+                with torch.cuda.stream(lib_stream):
+                    for j in range(5):
+                        h_red_t[j][:g].copy_(d_red[j][:g], non_blocking=True)
+                lib_stream.synchronize()
+            rows_out += g
+            d2h += g * 40
+        return rows_out, h2d, d2h
+
+    one_pass()
+    times = []
+    for _ in range(max(2, args.steps // 3)):
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        rows_out, h2d, d2h = one_pass()
+        times.append(_allreduce(torch, dist, world, time.perf_counter() - t0, "max"))
+    sec = sum(times) / len(times)
+    tot_out = int(_allreduce(torch, dist, world, rows_out, "sum"))
+    if rank == 0:
+        _emit({"metric": "shuffle rows/sec, end to end with device-side PartialReduce (group key + 4 aggregate states, 65 536 groups)",
+               "value": n_total / sec, "unit": "rows/s", "n_gpus": world, "steps": len(times), "warmup": 1, "ms_per_step": sec * 1e3,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+               "config": {"workload": f"agg: {n_total} Partial-aggregate rows x (key Int64 + sum, count, min, max Int64), Hash([key], {N}), chunks of "
+                                      f"{chunk} rows: H2D -> k_tile_hist/k_scan_tiles/k_scatter -> PartialReduce -> "
+                                      + ("pre-partitioned exchange -> " if world > 1 else "") + "D2H of the reduced rows only", "rows": n_total},
+               "e2e": {"value": n_total / sec, "unit": "rows/s", "h2d_bytes_per_step": int(_allreduce(torch, dist, world, h2d, "sum")),
+                       "d2h_bytes_per_step": int(_allreduce(torch, dist, world, d2h, "sum")), "rows_after_reduce": tot_out,
+                       "reduction": n_total / max(tot_out, 1)},
+               "gpu_launches": int(ctx.metrics()["kernel_launches"])})
+    ex.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run(args, torch, dfd, world):
-    {"cfg3": run_cfg3, "cfg4": run_cfg4, "cfg5": run_cfg5}[args.workload](args, torch, dfd, world)
+    {"cfg3": run_cfg3, "cfg4": run_cfg4, "cfg5": run_cfg5, "agg": run_agg}[args.workload](args, torch, dfd, world)
 
 
 # ------------------------------------------------------------------------------ CPU reference arm (cfg4) ----
