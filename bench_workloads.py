@@ -270,7 +270,9 @@ def run_cfg5(args, torch, dfd, world):
     str_bytes = arrays[1].buffers()[2].size
     dcols = [dfd.DeviceColumn.from_arrow(ctx, a) for a in arrays]
     row_bytes_avg = 8 + 8 + 4 + str_bytes / max(n, 1)
-    ex.setup_window(int(n * row_bytes_avg * 2.2) + (64 << 20))  # skewed destinations: generous window
+    # (every worker must pass the same window size: derive it from the largest producer)
+    win = int(_allreduce(torch, dist, world, int(n * row_bytes_avg * 2.2) + (64 << 20), "max"))
+    ex.setup_window((win + 4095) // 4096 * 4096)  # skewed destinations: generous window
     node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0, 1], P), uuid.uuid4(), 5, world, world)
     nullable = [False, False, False]
 
@@ -476,9 +478,13 @@ def run_agg(args, torch, dfd, world):
     part_cols = [dfd.DeviceColumn.from_torch(t) for t in d_part]
     red_cols = [dfd.DeviceColumn.from_torch(t) for t in d_red]
 
+    dbg = os.environ.get("DFD_BENCH_DEBUG")
+
     def one_pass():
         rows_out = h2d = d2h = 0
         for a in range(0, n, chunk):
+            if dbg:
+                print(f"[agg rank {rank}] chunk at row {a} t={time.perf_counter():.3f}", file=sys.stderr, flush=True)
             m = min(chunk, n - a)
             with torch.cuda.stream(lib_stream):
                 for j in range(5):
@@ -515,6 +521,8 @@ def run_agg(args, torch, dfd, world):
         times.append(_allreduce(torch, dist, world, time.perf_counter() - t0, "max"))
     sec = sum(times) / len(times)
     tot_out = int(_allreduce(torch, dist, world, rows_out, "sum"))
+    h2d_all = int(_allreduce(torch, dist, world, h2d, "sum"))  # (collectives: every rank, not only the printing one)
+    d2h_all = int(_allreduce(torch, dist, world, d2h, "sum"))
     if rank == 0:
         _emit({"metric": "shuffle rows/sec, end to end with device-side PartialReduce (group key + 4 aggregate states, 65 536 groups)",
                "value": n_total / sec, "unit": "rows/s", "n_gpus": world, "steps": len(times), "warmup": 1, "ms_per_step": sec * 1e3,
@@ -522,8 +530,7 @@ def run_agg(args, torch, dfd, world):
                "config": {"workload": f"agg: {n_total} Partial-aggregate rows x (key Int64 + sum, count, min, max Int64), Hash([key], {N}), chunks of "
                                       f"{chunk} rows: H2D -> k_tile_hist/k_scan_tiles/k_scatter -> PartialReduce -> "
                                       + ("pre-partitioned exchange -> " if world > 1 else "") + "D2H of the reduced rows only", "rows": n_total},
-               "e2e": {"value": n_total / sec, "unit": "rows/s", "h2d_bytes_per_step": int(_allreduce(torch, dist, world, h2d, "sum")),
-                       "d2h_bytes_per_step": int(_allreduce(torch, dist, world, d2h, "sum")), "rows_after_reduce": tot_out,
+               "e2e": {"value": n_total / sec, "unit": "rows/s", "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all, "rows_after_reduce": tot_out,
                        "reduction": n_total / max(tot_out, 1)},
                "gpu_launches": int(ctx.metrics()["kernel_launches"])})
     ex.close()

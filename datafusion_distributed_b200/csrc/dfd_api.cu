@@ -263,7 +263,9 @@ int dfd::PartitionJob::prepare(Partitioner* part, const dfd_column* in_cols, int
     // scratch: hist u32 [N][n_tiles] | tile_base u32 [N][n_tiles] | totals i64 [N] | done u32
     size_t hist_bytes = (((size_t)N * n_tiles * 4) + 255) & ~(size_t)255;
     size_t tot_bytes = (((size_t)N * 8) + 255) & ~(size_t)255;
-    size_t need = 2 * hist_bytes + tot_bytes + 256;
+    // (+ 2 B per row of destination ids when the keys are not the trivial single-i64 case and the launch is two-pass)
+    const size_t cache_bytes = (!ks.fast_i64 && !onepass_tiling) ? ((((size_t)n_rows * 2) + 255) & ~(size_t)255) : 0;
+    size_t need = 2 * hist_bytes + tot_bytes + 256 + cache_bytes;
     bool fresh = need > c->scratch.bytes;
     rc = c->scratch.ensure(need, c->device);
     if (rc) return rc;
@@ -271,6 +273,7 @@ int dfd::PartitionJob::prepare(Partitioner* part, const dfd_column* in_cols, int
     d_base = (uint32_t*)((char*)c->scratch.ptr + hist_bytes);
     d_totals = (int64_t*)((char*)c->scratch.ptr + 2 * hist_bytes);
     d_done = (unsigned*)((char*)c->scratch.ptr + 2 * hist_bytes + tot_bytes);
+    d_dest_cache = cache_bytes ? (uint16_t*)((char*)c->scratch.ptr + 2 * hist_bytes + tot_bytes + 256) : nullptr;
     if (fresh || c->scratch_done != d_done) {
         cudaError_t e = cudaMemsetAsync(d_done, 0, 256, stream);
         if (e != cudaSuccess) return cuda_error(e, "cudaMemsetAsync(done)");
@@ -306,7 +309,7 @@ int dfd::PartitionJob::run_hist_scan() {
         size_t smem = (size_t)N * 4;
         const int nf = N <= 4 ? 1 : N <= 8 ? 2 : N <= 16 ? 4 : 0;
         const unsigned grid = (unsigned)n_tiles;
-#define HIST(FAST, NF) k_tile_hist<TILE_THREADS, TILE_K, FAST, NF><<<grid, TILE_THREADS, smem, stream>>>(ks, p->st, p->mod, n_rows, n_tiles, N, d_hist)
+#define HIST(FAST, NF) k_tile_hist<TILE_THREADS, TILE_K, FAST, NF><<<grid, TILE_THREADS, smem, stream>>>(ks, p->st, p->mod, n_rows, n_tiles, N, d_hist, d_dest_cache)
         if (ks.fast_i64) {
             switch (nf) { case 1: HIST(true, 1); break; case 2: HIST(true, 2); break; case 4: HIST(true, 4); break; default: HIST(true, 0); }
         } else {
@@ -342,6 +345,7 @@ int dfd::PartitionJob::run_scatter(const int64_t* dest_base, void* const* peer_b
         sp.N = N;
         sp.parts_per_rank = parts_per_rank ? parts_per_rank : 1;
         sp.abort_flag = abort_flag;
+        sp.dest_cache = d_dest_cache;
         if (peer) {
             if (world > MAX_RANKS) return set_error(DFD_ERR_UNSUPPORTED, "world size %d > %d", world, MAX_RANKS);
             for (int r = 0; r < world; ++r) sp.peer_base[r] = peer_base[r];
@@ -435,42 +439,43 @@ int dfd::PartitionJob::run_onepass(const OnePassLayout& L) {
             if (L.world > MAX_RANKS) return set_error(DFD_ERR_UNSUPPORTED, "world size %d > %d", L.world, MAX_RANKS);
             for (int r = 0; r < L.world; ++r) sp.peer_base[r] = L.peer_base[r];
         }
+        // ONE single-pass launch moves every fixed-width column (any mix of widths up to the widest, per-column element type
+        // inside the kernel): the rows are hashed and ranked once.  Bit columns (validity / booleans) and columns beyond the
+        // per-launch limit follow through k_scatter on the same tiling, driven by the counts / cursors the first launch leaves.
+        std::vector<PayloadCol> fixed, rest;
+        int maxw = 0;
+        for (const PayloadCol& pc : passes) {
+            if (pc.width > 0 && fixed.size() < (size_t)MAX_COLS_PER_LAUNCH) { fixed.push_back(pc); if (pc.width > maxw) maxw = pc.width; }
+            else rest.push_back(pc);
+        }
+        if (fixed.empty()) return set_error(DFD_ERR_INTERNAL, "single-pass mode needs a fixed-width column");
+        {
+            for (size_t i = 0; i < fixed.size(); ++i) sp.cols[i] = fixed[i];
+            sp.n_cols = (int32_t)fixed.size();
+            sp.stage_width = maxw;
+            sp.hist_out = rest.empty() ? nullptr : d_hist;
+            sp.base_out = rest.empty() ? nullptr : d_base;
+            int rc = launch_scatter(sp, maxw, ks.fast_i64 != 0 && maxw >= 8, peer, 1, c->sm_count, 0, stream);
+            if (rc) return rc;
+            ++launches;
+            // the follow-up launches take the two-pass code path over the counts / cursors just written
+            sp.hist = d_hist;
+            sp.tile_base = d_base;
+            sp.abort_flag = L.d_overflow;
+        }
         static const int kWidths[6] = {8, 4, 16, 2, 1, 0};
-        int n_groups = 0;
-        for (int wi = 0; wi < 6; ++wi)
-            for (const PayloadCol& pc : passes)
-                if (pc.width == kWidths[wi]) { ++n_groups; break; }
-        if (passes.size() > 0 && passes.size() > (size_t)MAX_COLS_PER_LAUNCH) n_groups += 1;  // more than one launch for sure
-        bool first = true;
-        for (int wi = 0; wi < 6; ++wi) {
+        for (int wi = 0; wi < 6 && !rest.empty(); ++wi) {
             const int width = kWidths[wi];
             std::vector<PayloadCol> group;
-            for (const PayloadCol& pc : passes)
+            for (const PayloadCol& pc : rest)
                 if (pc.width == width) group.push_back(pc);
             if (group.empty()) continue;
-            if (first && width == 0) return set_error(DFD_ERR_INTERNAL, "single-pass mode needs a fixed-width column");
             sp.stage_width = width ? width : 1;
-            size_t smem = scatter_smem_bytes<TILE_THREADS, TILE_K>(N, sp.stage_width, peer, use_aligned(N, peer), first);
-            if (smem > 227 * 1024)
-                return set_error(DFD_ERR_UNSUPPORTED, "num_partitions %u needs %zu B of shared memory per CTA", N, smem);
             for (size_t f0 = 0; f0 < group.size(); f0 += MAX_COLS_PER_LAUNCH) {
                 size_t n = group.size() - f0 < (size_t)MAX_COLS_PER_LAUNCH ? group.size() - f0 : (size_t)MAX_COLS_PER_LAUNCH;
                 for (size_t i = 0; i < n; ++i) sp.cols[i] = group[f0 + i];
                 sp.n_cols = (int32_t)n;
-                int rc;
-                if (first) {
-                    const bool more = n_groups > 1 || group.size() > (size_t)MAX_COLS_PER_LAUNCH;
-                    sp.hist_out = more ? d_hist : nullptr;
-                    sp.base_out = more ? d_base : nullptr;
-                    rc = launch_scatter(sp, width, ks.fast_i64 != 0 && width == 8, peer, 1, c->sm_count, smem, stream);
-                    first = false;
-                    // the follow-up launches take the two-pass code path over the counts / cursors just written
-                    sp.hist = d_hist;
-                    sp.tile_base = d_base;
-                    sp.abort_flag = L.d_overflow;
-                } else {
-                    rc = launch_scatter(sp, width, ks.fast_i64 != 0, peer, 2, c->sm_count, smem, stream);
-                }
+                int rc = launch_scatter(sp, width, ks.fast_i64 != 0, peer, 2, c->sm_count, 0, stream);
                 if (rc) return rc;
                 ++launches;
             }
@@ -502,7 +507,9 @@ static int launch_varwidth(const dfd::PartitionJob::VarCol& vc, const uint32_t* 
     LAUNCH_CHECK("k_var_scan_block_sums");
     k_var_write_offsets<OFF><<<(unsigned)n_blocks, VAR_BLOCK, 0, stream>>>(in_off, vc.in.offset, d_src, n_rows, d_block_sums, out_off);
     LAUNCH_CHECK("k_var_write_offsets");
-    k_var_copy_bytes<OFF><<<(unsigned)(sm_count * 16), 256, 0, stream>>>(in_off, vc.in.offset, (const uint8_t*)vc.in.values, d_src, out_off,
+    const int64_t copy_blocks = (n_rows + 255) / 256;
+    (void)sm_count;
+    k_var_copy_bytes<OFF><<<(unsigned)(copy_blocks > 0x7fffffffLL ? 0x7fffffffLL : copy_blocks), 256, 0, stream>>>(in_off, vc.in.offset, (const uint8_t*)vc.in.values, d_src, out_off,
                                                                        (uint8_t*)vc.out.values, n_rows);
     LAUNCH_CHECK("k_var_copy_bytes");
     return DFD_OK;

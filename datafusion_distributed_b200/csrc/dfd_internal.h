@@ -91,6 +91,7 @@ struct PartitionJob {
     uint32_t* d_base = nullptr;
     int64_t* d_totals = nullptr;  // [N] rows per destination (after run_hist_scan)
     unsigned* d_done = nullptr;
+    uint16_t* d_dest_cache = nullptr;  // two-pass, non-trivial keys: destination of every row (written by K1, read by every K2 launch)
     cudaEvent_t* ev = nullptr;
     int prepare(Partitioner* part, const dfd_column* in_cols, int n_cols, int64_t rows, const dfd_column* out_cols,
                 bool peer_mode, cudaStream_t st);

@@ -116,7 +116,8 @@ static __global__ void k_row_hashes(KeySet keys, HashState st, int64_t n_rows, u
 // ---------------------------------------------------------------------------
 template <int THREADS, int K, bool FAST_I64, int NF>
 __global__ void __launch_bounds__(THREADS) k_tile_hist(KeySet keys, HashState st, ModN mod, int64_t n_rows,
-                                                        int64_t n_tiles, uint32_t N, uint32_t* __restrict__ hist) {
+                                                        int64_t n_tiles, uint32_t N, uint32_t* __restrict__ hist,
+                                                        uint16_t* __restrict__ dest_cache /* nullptr: do not cache */) {
     constexpr int T = THREADS * K;
     static_assert(K * 32 < 65536, "16-bit packed counters");
     extern __shared__ uint32_t s_hist[];
@@ -136,6 +137,13 @@ __global__ void __launch_bounds__(THREADS) k_tile_hist(KeySet keys, HashState st
             for (int j = 0; j < K; ++j) {
                 int t = j * THREADS + (int)threadIdx.x;
                 d[j] = t < tile_rows ? mod_n(row_hash<FAST_I64>(keys, row0 + t, st), mod) : N;
+            }
+        }
+        if (!FAST_I64 && dest_cache) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                int t = j * THREADS + (int)threadIdx.x;
+                if (t < tile_rows) dest_cache[row0 + t] = (uint16_t)d[j];
             }
         }
         if constexpr (NF > 0) {
@@ -538,7 +546,8 @@ __device__ __forceinline__ void rank_rows(const ScatterParams& P, int64_t row0, 
     for (int j = 0; j < K; ++j) {
         int t = t0 + j * 32;
         bool valid = t < tile_rows;
-        uint32_t d = valid ? mod_n(row_hash<FAST_I64>(P.keys, row0 + t, P.st), P.mod) : N;
+        uint32_t d = N;
+        if (valid) d = (!FAST_I64 && P.dest_cache) ? (uint32_t)P.dest_cache[row0 + t] : mod_n(row_hash<FAST_I64>(P.keys, row0 + t, P.st), P.mod);
         unsigned peers = peers_of(d, nbits);
         uint32_t rank = __popc(peers & ((1u << lane) - 1));
         uint32_t base = valid ? wc[d] : 0;
@@ -795,7 +804,7 @@ __global__ void __launch_bounds__(THREADS + 32, MIN_CTAS) k_scatter_onepass(cons
             const int rows = (int)((P.n_rows - row0) < T ? (P.n_rows - row0) : T);
             for (int c = 0; c < P.n_cols; ++c) {
                 const int slot = acquire_slot();
-                fill(slot, P.cols[c].in, P.cols[c].in_offset + row0, rows, (uint32_t)sizeof(V), true);
+                fill(slot, P.cols[c].in, P.cols[c].in_offset + row0, rows, (uint32_t)P.cols[c].width, true);  // (width <= sizeof(V): one slot)
             }
             cur = nxt;
         }
@@ -980,11 +989,24 @@ __global__ void __launch_bounds__(THREADS + 32, MIN_CTAS) k_scatter_onepass(cons
 #pragma unroll 1
             for (int c = 0; c < P.n_cols; ++c) {
                 const int slot = wait_item();
-                const V* in = (const V*)(smem + (uint32_t)slot * slot_bytes);
-                V* out = (V*)P.cols[c].out;
+                const unsigned char* in_raw = smem + (uint32_t)slot * slot_bytes;
+                void* out_raw = P.cols[c].out;
+                // one launch moves columns of every width <= sizeof(V) (the rows were ranked once): the element type is per column
+                auto copy_col = [&](auto tag) {
+                    using E = decltype(tag);
+                    const E* in = (const E*)in_raw;
+                    E* out = (E*)out_raw;
 #pragma unroll
-                for (int k = 0; k < K; ++k)
-                    if (orow[k] != SLOT_NONE) st_stream(out + orow[k], in[src[k]]);
+                    for (int k = 0; k < K; ++k)
+                        if (orow[k] != SLOT_NONE) st_stream(out + orow[k], in[src[k]]);
+                };
+                switch (P.cols[c].width) {
+                    case 16: if constexpr (sizeof(V) >= 16) copy_col(uint4{}); break;
+                    case 8: if constexpr (sizeof(V) >= 8) copy_col((unsigned long long)0); break;
+                    case 4: if constexpr (sizeof(V) >= 4) copy_col((unsigned)0); break;
+                    case 2: if constexpr (sizeof(V) >= 2) copy_col((unsigned short)0); break;
+                    default: copy_col((unsigned char)0); break;
+                }
                 release_item(slot);
             }
         } else {
@@ -993,15 +1015,26 @@ __global__ void __launch_bounds__(THREADS + 32, MIN_CTAS) k_scatter_onepass(cons
 #pragma unroll 1
             for (int c = 0; c < P.n_cols; ++c) {
                 const int slot = wait_item();
-                const V* in = (const V*)(smem + (uint32_t)slot * slot_bytes);
+                const unsigned char* in_raw = smem + (uint32_t)slot * slot_bytes;
                 const size_t col_out = (size_t)P.cols[c].out;  // local: pointer; peer: byte offset into every window
+                auto copy_col = [&](auto tag) {
+                    using E = decltype(tag);
+                    const E* in = (const E*)in_raw;
 #pragma unroll
-                for (int k = 0; k < KV; ++k) {
-                    if (slot_of[k] != SLOT_NONE && !overflow) {
-                        const uint32_t i = slot_of[k] & 0xffffu, p = slot_of[k] >> 16;
-                        V* o = PEER ? (V*)((char*)OUT_BASE[p] + col_out) : (V*)col_out;  // peer: the owner's window (NVLink store)
-                        st_stream(o + ((int64_t)i + DELTA[p]), in[SRC16[i]]);
+                    for (int k = 0; k < KV; ++k) {
+                        if (slot_of[k] != SLOT_NONE && !overflow) {
+                            const uint32_t i = slot_of[k] & 0xffffu, p = slot_of[k] >> 16;
+                            E* o = PEER ? (E*)((char*)OUT_BASE[p] + col_out) : (E*)col_out;  // peer: the owner's window (NVLink store)
+                            st_stream(o + ((int64_t)i + DELTA[p]), in[SRC16[i]]);
+                        }
                     }
+                };
+                switch (P.cols[c].width) {
+                    case 16: if constexpr (sizeof(V) >= 16) copy_col(uint4{}); break;
+                    case 8: if constexpr (sizeof(V) >= 8) copy_col((unsigned long long)0); break;
+                    case 4: if constexpr (sizeof(V) >= 4) copy_col((unsigned)0); break;
+                    case 2: if constexpr (sizeof(V) >= 2) copy_col((unsigned short)0); break;
+                    default: copy_col((unsigned char)0); break;
                 }
                 release_item(slot);
             }
@@ -1100,6 +1133,8 @@ template <typename OFF>
 __global__ void __launch_bounds__(256) k_var_copy_bytes(const OFF* __restrict__ in_off, int64_t in_offset,
                                                          const uint8_t* __restrict__ in_data, const uint32_t* __restrict__ src,
                                                          const OFF* __restrict__ out_off, uint8_t* __restrict__ out_data, int64_t n) {
+    // (launched with one thread per row: the three dependent loads src -> offsets -> bytes are latency bound, so the more rows
+    //  in flight the better)
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = (int64_t)src[j] + in_offset;
         const uint8_t* s = in_data + in_off[r];

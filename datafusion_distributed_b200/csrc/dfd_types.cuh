@@ -52,6 +52,9 @@ struct ScatterParams {
     // finished reading the previous shuffle's rows (checked by every CTA before its first store to a peer)
     const unsigned long long* ready_flags;
     unsigned long long ready_epoch;
+    // two-pass mode, non-trivial keys (strings, several keys, nullable keys): K1 leaves every row's destination here so that
+    // the K2 launches (one per column width) do not hash the keys again
+    const uint16_t* dest_cache;
 };
 
 // Header at the start of every worker's receive window (peer-memory flags of the single-pass exchange; no NCCL on the
