@@ -101,12 +101,17 @@ struct AHasher {
     __device__ __forceinline__ uint64_t finish() const {
         return rotl64(folded_multiply(buffer, pad), (unsigned)(buffer & 63));
     }
-    // little-endian read of n (<= 8) bytes at an arbitrary address
+    // little-endian read of n (1..8) bytes at an arbitrary address: the one or two ALIGNED 8-byte words that cover
+    // [p, p+n) are loaded and funnel-shifted (a byte loop costs up to 8 dependent loads per call and dominated string-key
+    // hashing).  Only words that contain requested bytes are touched, so nothing outside the buffer's 8-byte-aligned extent
+    // is read (Arrow buffers are at least 8-byte aligned).
     static __device__ __forceinline__ uint64_t rd(const uint8_t* p, int n) {
-        uint64_t v = 0;
-#pragma unroll 1
-        for (int i = 0; i < n; ++i) v |= (uint64_t)p[i] << (8 * i);
-        return v;
+        const uintptr_t a = (uintptr_t)p;
+        const unsigned sh = (unsigned)(a & 7u) * 8u;
+        const uint64_t* w = (const uint64_t*)(a & ~(uintptr_t)7);
+        uint64_t v = w[0] >> sh;
+        if (sh && (int)(a & 7u) + n > 8) v |= w[1] << (64u - sh);
+        return n >= 8 ? v : (v & ((1ULL << (8 * n)) - 1ULL));
     }
     // AHasher::write(&[u8]) (fallback_hash.rs) with operations.rs read_small
     __device__ void write(const uint8_t* data, uint64_t len) {
