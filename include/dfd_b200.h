@@ -133,7 +133,9 @@ int dfd_timer_stop(dfd_ctx* ctx, float* out_ms);
  *   seeds    : ahash RandomState::with_seeds arguments; NULL selects
  *              DataFusion's REPARTITION_RANDOM_STATE = (0,0,0,0)
  * num_partitions must be in [1, 4096] (DFD_MAX_PARTITIONS; DataFusion stages use target_partitions x tasks,
- * typically tens to hundreds). */
+ * typically tens to hundreds); the per-CTA shared-memory need of the scatter kernels is checked at create time.
+ * The peer-store exchange transports keep an extra per-destination table in shared memory and accept up to
+ * ~3 400 partitions (DFD_ERR_UNSUPPORTED above; the push and NCCL transports have no such limit). */
 #define DFD_MAX_PARTITIONS 4096
 int dfd_partitioner_create(dfd_ctx* ctx, uint32_t num_partitions, const int32_t* key_cols,
                            int n_keys, const uint64_t* seeds, dfd_partitioner** out);
