@@ -36,6 +36,18 @@ struct FieldInfo {
     int32_t kind = DFD_COL_FIXED;   // layout the DEVICE sees (a Utf8View column is Utf8 there; a dictionary column is its indices)
     int32_t width = 0;
     bool view = false;             // Arrow Utf8View / BinaryView ("vu" / "vz"): converted to offsets + bytes on input, back to views on output
+    // List<Utf8 / Binary> payload: the visible field is a PLACEHOLDER without a device column of its own; its rows travel as
+    // three hidden Binary device columns appended after the visible fields (all scattered by the same K2/K4 passes):
+    //   h_len   row -> the int32 LENGTHS of its child elements (4 bytes per element); carries the list's validity bitmap
+    //   h_bytes row -> the bytes of its child strings (contiguous per row)
+    //   h_valid row -> one byte per child element (its validity), only when the child field is nullable
+    // After the scatter the child offsets are an exclusive scan of the gathered lengths and the child validity is re-packed.
+    bool list = false, hidden = false;
+    int h_len = -1, h_bytes = -1, h_valid = -1;
+    int owner = -1, role = 0;  // hidden columns: the list field they belong to; role 1 = lengths, 2 = bytes, 3 = element validity
+    std::string child_name, child_format;
+    int64_t child_flags = 0;
+    bool nodev() const { return list; }
     bool dict = false;             // dictionary-encoded: `format` is the index type, dict_* describe the values
     std::string dict_format;
     int64_t dict_flags = 0;
@@ -152,6 +164,11 @@ struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
             void* b = nullptr;
             void* o = nullptr;
             bool ok = true;
+            if (f.nodev()) {  // list placeholder: no buffers of its own
+                c->values.push_back(nullptr); c->validity.push_back(nullptr); c->offsets.push_back(nullptr); c->data_cap.push_back(0);
+                c->views.push_back(nullptr); c->view_sizes.push_back(0);
+                continue;
+            }
             if (!f.var() && cudaHostAlloc(&v, value_bytes(f, chunk_rows), cudaHostAllocPortable) != cudaSuccess) ok = false;
             if (ok && (f.flags & ARROW_FLAG_NULLABLE) && cudaHostAlloc(&b, bitmap_bytes(chunk_rows), cudaHostAllocPortable) != cudaSuccess) ok = false;
             if (ok && f.var() && cudaHostAlloc(&o, (size_t)(chunk_rows + 16) * f.ow(), cudaHostAllocPortable) != cudaSuccess) ok = false;
@@ -199,6 +216,9 @@ struct BatchPriv {
     std::vector<ArrowArray> children;
     std::vector<ArrowArray*> child_ptrs;
     std::vector<const void*> child_bufs;  // 4 per child (validity, values|offsets|views, string bytes, variadic sizes)
+    std::vector<ArrowArray> grand;        // per child: the values array of a list column (child of the child)
+    std::vector<ArrowArray*> grand_ptrs;
+    std::vector<const void*> grand_bufs;  // 3 per child (validity, offsets, bytes of the list's values array)
     std::vector<ArrowArray> dicts;        // per child: shallow copy of the input dictionary (dictionary columns)
     std::vector<std::shared_ptr<SharedInput>> dict_owner;  // keeps that dictionary's batch alive
     const void* struct_bufs[1] = {nullptr};
@@ -224,6 +244,8 @@ struct SchemaPriv {
     std::vector<ArrowSchema> children;
     std::vector<ArrowSchema*> child_ptrs;
     std::vector<ArrowSchema> dicts;  // per child: schema of the dictionary values (dictionary columns)
+    std::vector<ArrowSchema> items;  // per child: the item field of a list column
+    std::vector<ArrowSchema*> item_ptrs;
 };
 
 void schema_child_release(ArrowSchema* s) { s->release = nullptr; }
@@ -238,17 +260,32 @@ void schema_release(ArrowSchema* s) {
 int export_schema(const std::vector<FieldInfo>& fields, ArrowSchema* out) {
     SchemaPriv* p = new (std::nothrow) SchemaPriv();
     if (!p) return ENOMEM;
-    p->fields = fields;
-    p->children.resize(fields.size());
-    p->child_ptrs.resize(fields.size());
-    p->dicts.resize(fields.size());
-    for (size_t i = 0; i < fields.size(); ++i) {
+    for (const FieldInfo& f : fields)
+        if (!f.hidden) p->fields.push_back(f);  // (hidden list columns are an implementation detail)
+    const size_t nf = p->fields.size();
+    p->children.resize(nf);
+    p->child_ptrs.resize(nf);
+    p->dicts.resize(nf);
+    p->items.resize(nf);
+    p->item_ptrs.resize(nf);
+    for (size_t i = 0; i < nf; ++i) {
         ArrowSchema& c = p->children[i];
         memset(&c, 0, sizeof c);
         c.format = p->fields[i].format.c_str();
         c.name = p->fields[i].name.c_str();
         c.flags = p->fields[i].flags;
         c.release = schema_child_release;
+        if (p->fields[i].list) {
+            ArrowSchema& it = p->items[i];
+            memset(&it, 0, sizeof it);
+            it.format = p->fields[i].child_format.c_str();
+            it.name = p->fields[i].child_name.c_str();
+            it.flags = p->fields[i].child_flags;
+            it.release = schema_child_release;
+            p->item_ptrs[i] = &it;
+            c.n_children = 1;
+            c.children = &p->item_ptrs[i];
+        }
         if (p->fields[i].dict) {
             ArrowSchema& d = p->dicts[i];
             memset(&d, 0, sizeof d);
@@ -263,7 +300,7 @@ int export_schema(const std::vector<FieldInfo>& fields, ArrowSchema* out) {
     memset(out, 0, sizeof *out);
     out->format = "+s";
     out->name = "";
-    out->n_children = (int64_t)fields.size();
+    out->n_children = (int64_t)nf;
     out->children = p->child_ptrs.data();
     out->release = schema_release;
     out->private_data = p;
@@ -282,6 +319,7 @@ struct Slot {
     std::vector<size_t> in_cap, out_cap;                      // var-width: capacity of d_in / d_out (string bytes)
     std::vector<int64_t> first_off, data_bytes;               // var-width: first input offset / byte count of the chunk
     std::vector<std::vector<char>> view_off, view_bytes;      // Utf8View input converted to offsets + contiguous bytes (host staging)
+    std::vector<dfd::Scratch> list_tmp;                       // list fields: [child offsets | child validity bits | scan block sums] (device)
     std::vector<dfd::Scratch> dict_buf;                       // dictionary KEY columns: [hashes | offsets | data | validity] of the values
     std::vector<const uint64_t*> dict_hashes;                 //   device pointers handed to the partitioner for this chunk
     std::vector<const uint8_t*> dict_valid;
@@ -305,6 +343,9 @@ struct dfd_repartition_exec {
     dfd_partitioner* part = nullptr;
     std::vector<FieldInfo> fields;
     std::vector<int> key_of_field;  // index into the partitioner's key list, or -1
+    size_t n_visible = 0;           // fields [0, n_visible) are the schema's columns; the rest are hidden device columns (lists)
+    std::vector<int> dev_fields;    // fields that own a device column, in launch order; dev_pos[field] = its position there
+    std::vector<int> dev_pos;
     uint32_t N = 0;
     int64_t chunk_rows = 0;
     int depth = 3;
@@ -354,8 +395,13 @@ int emit_slot(dfd_repartition_exec* x, Slot& s) {
     s.held.clear();
     s.out = nullptr;
     s.in_flight = false;
-    const size_t C = x->fields.size();
+    const size_t C = x->n_visible;  // the output batches carry the schema's columns; hidden list columns are folded into their list
     int made = 0;
+    for (size_t c = 0; c < C; ++c) {
+        if (!x->fields[c].list) continue;
+        int32_t* lo32 = (int32_t*)oc->offsets[(size_t)x->fields[c].h_len];  // byte offsets into the 4-byte lengths -> element offsets
+        for (int64_t r = 0; r <= s.rows; ++r) lo32[r] >>= 2;
+    }
     for (size_t c = 0; c < C; ++c) {
         if (!x->fields[c].view) continue;
         // Utf8View output: 16-byte views over the chunk's single data buffer (inline when <= 12 bytes)
@@ -390,11 +436,42 @@ int emit_slot(dfd_repartition_exec* x, Slot& s) {
         bp->child_ptrs.resize(C);
         bp->child_bufs.resize(4 * C);
         bp->dicts.resize(C);
+        bp->grand.resize(C);
+        bp->grand_ptrs.resize(C);
+        bp->grand_bufs.resize(3 * C);
         for (size_t c = 0; c < C; ++c) {
             ArrowArray& a = bp->children[c];
             memset(&a, 0, sizeof a);
             bool hv = s.has_valid[c];
             const FieldInfo& f = x->fields[c];
+            if (f.list) {
+                // List<Utf8>: list offsets + validity from the lengths column, values array (offsets from the device scan, bytes, validity)
+                const size_t hl = (size_t)f.h_len, hb = (size_t)f.h_bytes;
+                const bool lv = s.has_valid[hl];
+                bp->child_bufs[4 * c] = lv ? oc->validity[hl] : nullptr;
+                bp->child_bufs[4 * c + 1] = oc->offsets[hl];
+                ArrowArray& g = bp->grand[c];
+                memset(&g, 0, sizeof g);
+                bp->grand_bufs[3 * c] = f.h_valid >= 0 ? oc->values[(size_t)f.h_valid] : nullptr;
+                bp->grand_bufs[3 * c + 1] = oc->values[hl];
+                bp->grand_bufs[3 * c + 2] = oc->values[hb];
+                g.length = s.data_bytes[hl] / 4;
+                g.null_count = f.h_valid >= 0 ? -1 : 0;
+                g.n_buffers = 3;
+                g.buffers = &bp->grand_bufs[3 * c];
+                g.release = child_release;
+                bp->grand_ptrs[c] = &g;
+                a.length = cnt;
+                a.offset = start;
+                a.null_count = lv ? -1 : 0;
+                a.n_buffers = 2;
+                a.buffers = &bp->child_bufs[4 * c];
+                a.n_children = 1;
+                a.children = &bp->grand_ptrs[c];
+                a.release = child_release;
+                bp->child_ptrs[c] = &a;
+                continue;
+            }
             const bool var = f.var();
             bp->child_bufs[4 * c] = hv ? oc->validity[c] : nullptr;
             bp->child_bufs[4 * c + 1] = f.view ? oc->views[c] : (var ? oc->offsets[c] : oc->values[c]);
@@ -454,17 +531,19 @@ int flush_current(dfd_repartition_exec* x) {
     XCUDA(x, cudaEventRecord(s.e_h2d, x->s_h2d), "record h2d");
     XCUDA(x, cudaStreamWaitEvent(c->stream, s.e_h2d, 0), "wait h2d");
     if (s.d2h_recorded) XCUDA(x, cudaStreamWaitEvent(c->stream, s.e_d2h, 0), "wait d2h");
-    std::vector<dfd_column> in(C), out(C);
-    for (size_t i = 0; i < C; ++i) {
+    const size_t D = x->dev_fields.size();  // device columns: every field except the list placeholders (+ the hidden list columns)
+    std::vector<dfd_column> in(D), out(D);
+    for (size_t k = 0; k < D; ++k) {
+        const size_t i = (size_t)x->dev_fields[k];
         const FieldInfo& f = x->fields[i];
         if (f.var()) {
             // offsets stay absolute: point `values` so that values + first_off is the first copied byte
-            in[i] = dfd_column{f.kind, 0, (char*)s.d_in[i] - s.first_off[i], s.d_in_off[i], s.has_valid[i] ? (uint8_t*)s.d_in_valid[i] : nullptr,
+            in[k] = dfd_column{f.kind, 0, (char*)s.d_in[i] - s.first_off[i], s.d_in_off[i], s.has_valid[i] ? (uint8_t*)s.d_in_valid[i] : nullptr,
                                s.in_offset[i], (int64_t)s.in_cap[i]};
-            out[i] = dfd_column{f.kind, 0, s.d_out[i], s.d_out_off[i], s.has_valid[i] ? (uint8_t*)s.d_out_valid[i] : nullptr, 0, (int64_t)s.out_cap[i]};
+            out[k] = dfd_column{f.kind, 0, s.d_out[i], s.d_out_off[i], s.has_valid[i] ? (uint8_t*)s.d_out_valid[i] : nullptr, 0, (int64_t)s.out_cap[i]};
         } else {
-            in[i] = dfd_column{f.kind, f.width, s.d_in[i], nullptr, s.has_valid[i] ? (uint8_t*)s.d_in_valid[i] : nullptr, s.in_offset[i], 0};
-            out[i] = dfd_column{f.kind, f.width, s.d_out[i], nullptr, s.has_valid[i] ? (uint8_t*)s.d_out_valid[i] : nullptr, 0, 0};
+            in[k] = dfd_column{f.kind, f.width, s.d_in[i], nullptr, s.has_valid[i] ? (uint8_t*)s.d_in_valid[i] : nullptr, s.in_offset[i], 0};
+            out[k] = dfd_column{f.kind, f.width, s.d_out[i], nullptr, s.has_valid[i] ? (uint8_t*)s.d_out_valid[i] : nullptr, 0, 0};
         }
         if (f.kind == DFD_COL_BOOL)
             XCUDA(x, cudaMemsetAsync(s.d_out[i], 0, PinnedPool::bitmap_bytes(s.rows), c->stream), "memset");
@@ -475,8 +554,31 @@ int flush_current(dfd_repartition_exec* x) {
             x->part->key_modes[(size_t)x->key_of_field[i]] = dfd::KEY_HASH_DICTIONARY;
             x->part->key_dicts[(size_t)x->key_of_field[i]] = dfd_partitioner::KeyDict{s.dict_hashes[i], s.dict_valid[i]};
         }
-    int rc = partition_device_locked(x->part, in.data(), (int)C, s.rows, out.data(), c->stream);
+    int rc = partition_device_locked(x->part, in.data(), (int)D, s.rows, out.data(), c->stream);
     if (rc) return fail(x, rc, dfd_last_error());
+    // list fields: child offsets = exclusive scan of the gathered element lengths; child validity bytes -> bitmap
+    std::vector<const void*> d2h_src(C, nullptr);
+    std::vector<size_t> d2h_nb(C, 0);
+    for (size_t i = 0; i < x->n_visible; ++i) {
+        const FieldInfo& f = x->fields[i];
+        if (!f.list) continue;
+        const int64_t ne = s.data_bytes[(size_t)f.h_len] / 4;
+        auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        const size_t o_off = 0, o_bits = al((size_t)(ne + 1) * 4 + 16), o_sums = o_bits + al((size_t)(ne + 63) / 64 * 8 + 16);
+        const size_t total = o_sums + al((size_t)(ne / 2048 + 4) * 8);
+        int rc2 = s.list_tmp[i].ensure(total, c->device);
+        if (rc2) return fail(x, rc2, dfd_last_error());
+        char* lt = (char*)s.list_tmp[i].ptr;
+        if ((rc2 = launch_lengths_to_offsets(s.d_out[(size_t)f.h_len], 4, ne, (unsigned long long*)(lt + o_sums), lt + o_off, c->stream)))
+            return fail(x, rc2, dfd_last_error());
+        d2h_src[(size_t)f.h_len] = lt + o_off;
+        d2h_nb[(size_t)f.h_len] = (size_t)(ne + 1) * 4;
+        if (f.h_valid >= 0) {
+            if ((rc2 = launch_bytes_to_bits((const uint8_t*)s.d_out[(size_t)f.h_valid], ne, lt + o_bits, c->stream))) return fail(x, rc2, dfd_last_error());
+            d2h_src[(size_t)f.h_valid] = lt + o_bits;
+            d2h_nb[(size_t)f.h_valid] = (size_t)((ne + 31) / 32 * 4);
+        }
+    }
     XCUDA(x, cudaMemcpyAsync(s.h_part_starts, x->part->d_part_starts, sizeof(int64_t) * (x->N + 1), cudaMemcpyDeviceToHost, c->stream),
           "D2H part_starts");
     XCUDA(x, cudaEventRecord(s.e_k, c->stream), "record k");
@@ -485,11 +587,14 @@ int flush_current(dfd_repartition_exec* x) {
     s.out = x->pool->acquire();
     if (!s.out) return fail(x, DFD_ERR_OOM, "pinned host allocation failed");
     XCUDA(x, cudaStreamWaitEvent(x->s_d2h, s.e_k, 0), "wait k");
-    for (size_t i = 0; i < C; ++i) {
+    for (size_t k = 0; k < D; ++k) {
+        const size_t i = (size_t)x->dev_fields[k];
         const FieldInfo& f = x->fields[i];
         size_t nb = f.kind == DFD_COL_BOOL ? (size_t)((s.rows + 7) / 8) : (size_t)s.rows * f.width;
+        const void* src = s.d_out[i];
         if (f.var()) {
             nb = (size_t)s.data_bytes[i];
+            if (d2h_src[i]) { src = d2h_src[i]; nb = d2h_nb[i]; }  // list columns: scanned child offsets / re-packed child validity
             if (s.out->data_cap[i] < nb || !s.out->values[i]) {  // grow this pinned chunk's string buffer (never NULL, even for 0 bytes)
                 if (s.out->values[i]) cudaFreeHost(s.out->values[i]);
                 s.out->values[i] = nullptr;
@@ -498,10 +603,12 @@ int flush_current(dfd_repartition_exec* x) {
                 XCUDA(x, cudaHostAlloc(&s.out->values[i], want, cudaHostAllocPortable), "cudaHostAlloc(string bytes)");
                 s.out->data_cap[i] = want;
             }
-            XCUDA(x, cudaMemcpyAsync(s.out->offsets[i], s.d_out_off[i], (size_t)(s.rows + 1) * f.ow(), cudaMemcpyDeviceToHost, x->s_d2h), "D2H offsets");
-            x->bytes_d2h += (size_t)(s.rows + 1) * f.ow();
+            if (!f.hidden || f.role == 1) {  // (the per-row offsets of the hidden bytes / validity columns are not needed on the host)
+                XCUDA(x, cudaMemcpyAsync(s.out->offsets[i], s.d_out_off[i], (size_t)(s.rows + 1) * f.ow(), cudaMemcpyDeviceToHost, x->s_d2h), "D2H offsets");
+                x->bytes_d2h += (size_t)(s.rows + 1) * f.ow();
+            }
         }
-        if (nb) XCUDA(x, cudaMemcpyAsync(s.out->values[i], s.d_out[i], nb, cudaMemcpyDeviceToHost, x->s_d2h), "D2H");
+        if (nb) XCUDA(x, cudaMemcpyAsync(s.out->values[i], src, nb, cudaMemcpyDeviceToHost, x->s_d2h), "D2H");
         x->bytes_d2h += nb;
         if (s.has_valid[i]) {
             XCUDA(x, cudaMemcpyAsync(s.out->validity[i], s.d_out_valid[i], (size_t)((s.rows + 7) / 8), cudaMemcpyDeviceToHost, x->s_d2h), "D2H");
@@ -535,7 +642,7 @@ int open_next_slot(dfd_repartition_exec* x) {
 }
 
 bool batch_is_plain(const dfd_repartition_exec* x, const ArrowArray* b) {
-    for (size_t i = 0; i < x->fields.size(); ++i) {
+    for (size_t i = 0; i < x->n_visible; ++i) {
         const ArrowArray* c = b->children[i];
         if (x->fields[i].kind != DFD_COL_FIXED || x->fields[i].dict) return false;
         if (c->null_count != 0 && c->n_buffers > 0 && c->buffers[0] != nullptr) return false;
@@ -552,13 +659,83 @@ int stage_rows(dfd_repartition_exec* x, const ArrowArray* b, int64_t start, int6
     const size_t C = x->fields.size();
     std::lock_guard<std::mutex> lk(x->ctx->mu);
     XCUDA(x, cudaSetDevice(x->ctx->device), "cudaSetDevice");
-    for (size_t i = 0; i < C; ++i) {
+    // a hidden / converted variable-width column whose offsets (int32, n + 1 entries, starting at 0) and bytes were built on the host
+    auto stage_var_host = [&](size_t h, const char* off32, const char* bytes, int64_t total, int64_t bit_off) -> int {
+        if ((size_t)total > s.in_cap[h]) {
+            cudaFree(s.d_in[h]); cudaFree(s.d_out[h]);
+            s.d_in[h] = s.d_out[h] = nullptr;
+            s.in_cap[h] = s.out_cap[h] = 0;
+            size_t want = (size_t)total + (size_t)total / 4 + 256;
+            XCUDA(x, cudaMalloc(&s.d_in[h], want), "cudaMalloc(string bytes)");
+            XCUDA(x, cudaMalloc(&s.d_out[h], want), "cudaMalloc(string bytes)");
+            s.in_cap[h] = s.out_cap[h] = want;
+        }
+        XCUDA(x, cudaMemcpyAsync((char*)s.d_in_off[h] + (size_t)bit_off * 4, off32, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, x->s_h2d), "H2D offsets");
+        if (total) XCUDA(x, cudaMemcpyAsync(s.d_in[h], bytes, (size_t)total, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
+        s.first_off[h] = 0;
+        s.data_bytes[h] = total;
+        s.in_offset[h] = bit_off;
+        x->bytes_h2d += (size_t)total + (size_t)(n + 1) * 4;
+        return DFD_OK;
+    };
+    for (size_t i = 0; i < x->n_visible; ++i) {
         const FieldInfo& f = x->fields[i];
         const ArrowArray* c = b->children[i];
         const int64_t lo = c->offset + start;
         const bool hv = !plain && c->null_count != 0 && c->n_buffers > 0 && c->buffers[0] != nullptr;
         const int64_t bit_off = (hv || f.kind == DFD_COL_BOOL) ? (lo & 7) : 0;
         const size_t bitmap_nb = (size_t)((bit_off + n + 7) >> 3);
+        if (f.list) {
+            // List<Utf8 / Binary>: build the three hidden Binary columns of these rows on the host (index arithmetic only; the
+            // string bytes are a contiguous range of the child's data buffer and go to the device straight from there)
+            if (c->n_children != 1 || !c->children[0]) return fail(x, DFD_ERR_INVALID_ARGUMENT, "column " + f.name + ": list array without a child");
+            const ArrowArray* v = c->children[0];
+            const int32_t* loff = (const int32_t*)c->buffers[1];
+            const int32_t* coff = (const int32_t*)v->buffers[1] + v->offset;
+            const uint8_t* cvalid = (v->null_count != 0 && v->buffers[0]) ? (const uint8_t*)v->buffers[0] : nullptr;
+            const int64_t e0 = loff[lo], e1 = loff[lo + n], ne = e1 - e0;
+            if (ne < 0) return fail(x, DFD_ERR_INVALID_ARGUMENT, "column " + f.name + ": list offsets are not monotonic");
+            const size_t hl = (size_t)f.h_len, hb = (size_t)f.h_bytes;
+            std::vector<char>& ol = s.view_off[hl];
+            std::vector<char>& dl = s.view_bytes[hl];
+            std::vector<char>& ob = s.view_off[hb];
+            ol.resize((size_t)(n + 1) * 4); ob.resize((size_t)(n + 1) * 4); dl.resize((size_t)ne * 4 + 16);
+            int32_t* ol32 = (int32_t*)ol.data();
+            int32_t* ob32 = (int32_t*)ob.data();
+            int32_t* len32 = (int32_t*)dl.data();
+            if (ne * 4 > 0x7fffffffLL) return fail(x, DFD_ERR_UNSUPPORTED, "column " + f.name + ": too many list elements in one chunk");
+            for (int64_t r = 0; r <= n; ++r) {
+                ol32[r] = (int32_t)(4 * ((int64_t)loff[lo + r] - e0));
+                ob32[r] = coff[loff[lo + r]] - coff[e0];
+            }
+            for (int64_t k = 0; k < ne; ++k) len32[k] = coff[e0 + k + 1] - coff[e0 + k];
+            int rc2 = stage_var_host(hl, ol.data(), dl.data(), ne * 4, bit_off);
+            if (rc2) return rc2;
+            if ((rc2 = stage_var_host(hb, ob.data(), (const char*)v->buffers[2] + coff[e0], (int64_t)coff[e1] - coff[e0], 0))) return rc2;
+            s.has_valid[hb] = false;
+            if (f.h_valid >= 0) {
+                const size_t hvx = (size_t)f.h_valid;
+                std::vector<char>& ov = s.view_off[hvx];
+                std::vector<char>& dv = s.view_bytes[hvx];
+                ov.resize((size_t)(n + 1) * 4); dv.resize((size_t)ne + 16);
+                int32_t* ov32 = (int32_t*)ov.data();
+                for (int64_t r = 0; r <= n; ++r) ov32[r] = (int32_t)((int64_t)loff[lo + r] - e0);
+                for (int64_t k = 0; k < ne; ++k) {
+                    const int64_t bit = v->offset + e0 + k;
+                    dv[(size_t)k] = cvalid ? (char)((cvalid[bit >> 3] >> (bit & 7)) & 1) : (char)1;
+                }
+                if ((rc2 = stage_var_host(hvx, ov.data(), dv.data(), ne, 0))) return rc2;
+                s.has_valid[hvx] = false;
+            }
+            if (hv) {  // the list's own validity rides on the lengths column
+                const char* src = (const char*)c->buffers[0] + (lo >> 3);
+                XCUDA(x, cudaMemcpyAsync(s.d_in_valid[hl], src, bitmap_nb, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
+                x->bytes_h2d += bitmap_nb;
+            }
+            s.has_valid[hl] = hv;
+            s.has_valid[i] = false;
+            continue;
+        }
         if (f.dict && x->key_of_field[i] >= 0) {
             // dictionary KEY: hash the dictionary values once on the device (DataFusion hash_dictionary); rows pick dict_hashes[index]
             const ArrowArray* d = c->dictionary;
@@ -705,12 +882,20 @@ int dfd_arrow_format_layout(const char* format, int32_t* kind, int32_t* width) {
     return DFD_OK;
 }
 
+// List<Utf8> / List<Binary> (int32 list offsets, int32 child offsets): the one nested shape the shuffle path moves (payload only)
+static bool list_child_ok(const ArrowSchema* c) {
+    if (!c->format || strcmp(c->format, "+l") != 0 || c->n_children != 1 || !c->children || !c->children[0]) return false;
+    const ArrowSchema* v = c->children[0];
+    return v->format && (strcmp(v->format, "u") == 0 || strcmp(v->format, "z") == 0) && !v->dictionary && v->n_children == 0;
+}
+
 int dfd_schema_supported(const struct ArrowSchema* schema) {
     if (!schema || !schema->format || strcmp(schema->format, "+s") != 0)
         return set_error(DFD_ERR_INVALID_ARGUMENT, "schema must be a struct (record batch) schema");
     for (int64_t i = 0; i < schema->n_children; ++i) {
         const ArrowSchema* c = schema->children[i];
         int32_t k, w;
+        if (list_child_ok(c)) continue;  // List<Utf8 / Binary> payload (as a KEY it is refused when the operator is created)
         if (!c->format || !parse_format(c->format, &k, &w))
             return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): Arrow format '%s' is not supported", (long long)i, c->name ? c->name : "",
                              c->format ? c->format : "(null)");
@@ -744,12 +929,24 @@ int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, 
         f.name = c->name ? c->name : "";
         f.format = c->format ? c->format : "";
         f.flags = c->flags;
-        if (!parse_format(f.format.c_str(), &f.kind, &f.width))
-            return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): Arrow format '%s' is not supported", (long long)i, f.name.c_str(), f.format.c_str());
-        f.view = f.format[0] == 'v';
         int key_index = -1;
         for (int k = 0; k < n_keys; ++k)
             if (key_cols && key_cols[k] == i) key_index = k;
+        if (list_child_ok(c)) {
+            if (key_index >= 0) return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): list columns cannot be hash keys", (long long)i, f.name.c_str());
+            f.list = true;
+            f.kind = -1;
+            f.width = 0;
+            f.child_name = c->children[0]->name ? c->children[0]->name : "item";
+            f.child_format = c->children[0]->format;
+            f.child_flags = c->children[0]->flags;
+            x->key_of_field.push_back(-1);
+            x->fields.push_back(f);
+            continue;
+        }
+        if (!parse_format(f.format.c_str(), &f.kind, &f.width))
+            return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): Arrow format '%s' is not supported", (long long)i, f.name.c_str(), f.format.c_str());
+        f.view = f.format[0] == 'v';
         if (c->dictionary) {
             const ArrowSchema* d = c->dictionary;
             if (f.kind != DFD_COL_FIXED || !strchr("cCsSiIlL", f.format[0]) || f.format[1])
@@ -768,7 +965,37 @@ int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, 
     for (int k = 0; k < n_keys; ++k)
         if (!key_cols || key_cols[k] < 0 || key_cols[k] >= (int)x->fields.size())
             return set_error(DFD_ERR_INVALID_ARGUMENT, "key column index out of range");
-    int rc = dfd_partitioner_create(ctx, num_partitions, key_cols, n_keys, nullptr, &x->part);
+    // hidden device columns of the list fields, appended after the visible ones
+    x->n_visible = x->fields.size();
+    for (size_t i = 0; i < x->n_visible; ++i) {
+        if (!x->fields[i].list) continue;
+        auto hidden = [&](const char* tag, bool nullable) {
+            FieldInfo h;
+            h.name = x->fields[i].name + "." + tag;
+            h.format = "z";
+            h.kind = DFD_COL_BINARY;
+            h.width = 0;
+            h.hidden = true;
+            h.owner = (int)i;
+            h.role = tag[0] == 'l' ? 1 : tag[0] == 'b' ? 2 : 3;
+            h.flags = nullable ? ARROW_FLAG_NULLABLE : 0;
+            x->key_of_field.push_back(-1);
+            x->fields.push_back(h);
+            return (int)x->fields.size() - 1;
+        };
+        x->fields[i].h_len = hidden("lengths", (x->fields[i].flags & ARROW_FLAG_NULLABLE) != 0);
+        x->fields[i].h_bytes = hidden("bytes", false);
+        if (x->fields[i].child_flags & ARROW_FLAG_NULLABLE) x->fields[i].h_valid = hidden("validity", false);
+    }
+    x->dev_pos.assign(x->fields.size(), -1);
+    for (size_t i = 0; i < x->fields.size(); ++i)
+        if (!x->fields[i].nodev()) {
+            x->dev_pos[i] = (int)x->dev_fields.size();
+            x->dev_fields.push_back((int)i);
+        }
+    std::vector<int32_t> dev_keys(n_keys);
+    for (int k = 0; k < n_keys; ++k) dev_keys[k] = x->dev_pos[(size_t)key_cols[k]];  // keys address the compact device column list
+    int rc = dfd_partitioner_create(ctx, num_partitions, dev_keys.data(), n_keys, nullptr, &x->part);
     if (rc) return rc;  // (x has no CUDA resources yet; unique_ptr frees it)
     for (int k = 0; k < n_keys; ++k) {  // interval keys hash field by field (arrow's derived Hash), not as one integer
         const std::string& fmt = x->fields[(size_t)key_cols[k]].format;
@@ -803,8 +1030,10 @@ int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, 
             s.first_off.assign(C, 0); s.data_bytes.assign(C, 0);
             s.view_off.resize(C); s.view_bytes.resize(C);
             s.dict_buf.resize(C); s.dict_hashes.assign(C, nullptr); s.dict_valid.assign(C, nullptr);
+            s.list_tmp.resize(C);
             for (size_t i = 0; i < C && e == cudaSuccess; ++i) {
                 const FieldInfo& f = x->fields[i];
+                if (f.nodev()) continue;  // list placeholder: its rows live in the hidden columns
                 if (f.var()) {  // offsets now, string bytes on demand
                     e = cudaMalloc(&s.d_in_off[i], (size_t)(x->chunk_rows + 16) * f.ow());
                     if (e == cudaSuccess) e = cudaMalloc(&s.d_out_off[i], (size_t)(x->chunk_rows + 16) * f.ow());
@@ -872,6 +1101,7 @@ void dfd_repartition_exec_destroy(dfd_repartition_exec* x) {
             for (void* p : s.d_in_off) cudaFree(p);
             for (void* p : s.d_out_off) cudaFree(p);
             for (dfd::Scratch& b : s.dict_buf) cudaFree(b.ptr);
+            for (dfd::Scratch& b : s.list_tmp) cudaFree(b.ptr);
             if (s.h_part_starts) cudaFreeHost(s.h_part_starts);
             if (s.e_h2d) cudaEventDestroy(s.e_h2d);
             if (s.e_k) cudaEventDestroy(s.e_k);
@@ -891,9 +1121,9 @@ int dfd_repartition_exec_push(dfd_repartition_exec* x, struct ArrowArray* batch)
     if (!x || !batch) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_repartition_exec_push: NULL argument");
     auto drop = [&]() { if (batch->release) batch->release(batch); };
     if (x->finished) { drop(); return set_error(DFD_ERR_INVALID_ARGUMENT, "push after finish/error: %s", x->error.c_str()); }
-    if (batch->n_children != (int64_t)x->fields.size()) {
+    if (batch->n_children != (int64_t)x->n_visible) {
         drop();
-        return fail(x, DFD_ERR_INVALID_ARGUMENT, "batch has " + std::to_string(batch->n_children) + " columns, schema has " + std::to_string(x->fields.size()));
+        return fail(x, DFD_ERR_INVALID_ARGUMENT, "batch has " + std::to_string(batch->n_children) + " columns, schema has " + std::to_string(x->n_visible));
     }
     const int64_t R = batch->length;
     x->rows_in += (uint64_t)R;

@@ -242,20 +242,27 @@ int dfd_partitioner_collect(dfd_partitioner* p, int64_t* part_starts_host, int64
  * `gc()` before its network hop, src/worker/impl_execute_task.rs:248-271) and
  * Dictionary<integer, flat values> (the indices are scattered, every output
  * batch references the input batch's dictionary; dictionary KEYS are hashed
- * through their values on the device), all nullable.  Nested types (List,
- * Struct, Map): DFD_ERR_UNSUPPORTED (remaining part). */
+ * through their values on the device), all nullable.  List<Utf8> and
+ * List<Binary> (int32 offsets; the `tags` column of the reference's bench
+ * schema, src/execution_plans/benchmarks/fixture.rs:13-33) move as PAYLOAD:
+ * the operator splits a list column into three hidden variable-width device
+ * columns (element lengths + the list's validity, element bytes, element
+ * validity), scatters them with the ordinary variable-width kernels, rebuilds
+ * the child offsets with a device scan and exports nested Arrow arrays; as a
+ * hash KEY a list is refused at create time.  Other nested types (Struct, Map,
+ * List of anything else): DFD_ERR_UNSUPPORTED. */
 typedef struct dfd_repartition_exec dfd_repartition_exec;
 
 /* Pure host helpers (no GPU needed) for the plan hook that decides whether a stage-head
  * `RepartitionExec(Hash)` can be swapped for the GPU operator
  * (`Worker::add_on_plan_hook`, src/worker/worker_service.rs:91-96):
  *   dfd_arrow_format_layout : Arrow C format string -> (dfd_col_kind, value width);
- *                             DFD_ERR_UNSUPPORTED for dictionary-less types this path does
- *                             not move yet (views, lists, structs, 256-bit decimals ...).
+ *                             DFD_ERR_UNSUPPORTED for formats with no flat layout
+ *                             (nested types, 256-bit decimals, fixed-size binary ...).
  *   dfd_schema_supported    : DFD_OK iff every column of the record-batch schema is
- *                             supported (and no column is dictionary-encoded);
- *                             otherwise DFD_ERR_UNSUPPORTED with the reason in
- *                             dfd_last_error(). */
+ *                             supported — flat columns, views, Dictionary<integer, flat>
+ *                             and List<Utf8 / Binary>; otherwise DFD_ERR_UNSUPPORTED with
+ *                             the reason in dfd_last_error(). */
 int dfd_arrow_format_layout(const char* format, int32_t* kind, int32_t* width);
 int dfd_schema_supported(const struct ArrowSchema* schema);
 

@@ -108,10 +108,18 @@ def test_schema_support_helpers_run_without_a_gpu(built):
                     ("ts", pa.timestamp("ns")), ("count", pa.int32()), ("price", pa.decimal128(15, 2)), ("blob", pa.binary())])
     assert supported(ok)[0] == 0
     # the reference's bench fixture (src/execution_plans/benchmarks/fixture.rs:13-33): Dictionary<Int32, Utf8> is supported
-    # (indices scattered, dictionary by reference), and so are view types; List<Utf8> is the one column still "next"
+    # (indices scattered, dictionary by reference), and so are view types and List<Utf8> (lengths + bytes as hidden columns)
     assert supported(pa.schema([("id", pa.int64()), ("category", pa.dictionary(pa.int32(), pa.string())), ("v", pa.string_view()),
                                 ("bv", pa.binary_view()), ("d8", pa.dictionary(pa.int8(), pa.int64()))]))[0] == 0
     st, why = supported(pa.schema([("id", pa.int64()), ("nested", pa.dictionary(pa.int32(), pa.list_(pa.int32())))]))
     assert st == 6 and "dictionary value type" in why
-    st, why = supported(pa.schema([("id", pa.int64()), ("tags", pa.list_(pa.string()))]))
-    assert st == 6 and "tags" in why
+    assert supported(pa.schema([("id", pa.int64()), ("tags", pa.list_(pa.string())), ("blobs", pa.list_(pa.binary()))]))[0] == 0
+    # the reference's 9-column fixture schema, whole
+    fixture = pa.schema([pa.field("id", pa.int64(), False), pa.field("metric", pa.float64(), False), ("flag", pa.bool_()), ("label", pa.string()),
+                         ("category", pa.dictionary(pa.int32(), pa.string())), pa.field("raw", pa.uint8(), False),
+                         pa.field("ts", pa.timestamp("ns"), False), pa.field("count", pa.int32(), False), ("tags", pa.list_(pa.string()))])
+    assert supported(fixture)[0] == 0
+    st, why = supported(pa.schema([("id", pa.int64()), ("nums", pa.list_(pa.int32()))]))
+    assert st == 6 and "nums" in why
+    st, why = supported(pa.schema([("id", pa.int64()), ("s", pa.struct([("a", pa.int32())]))]))
+    assert st == 6 and "s" in why

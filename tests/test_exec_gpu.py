@@ -115,9 +115,12 @@ def test_single_partition_and_pinned_input(ctx):
 
 
 def test_operator_errors(ctx):
-    with pytest.raises(dfd.DfdError) as e:
+    with pytest.raises(dfd.DfdError) as e:  # List<Utf8> travels as payload, but is not a hash key
         dfd.RepartitionExec(ctx, pa.schema([("s", pa.list_(pa.string()))]), dfd.Partitioning.Hash([0], 4))
-    assert e.value.status == 6  # DFD_ERR_UNSUPPORTED: nested types are the remaining "next" part of SURVEY §8 f1
+    assert e.value.status == 6  # DFD_ERR_UNSUPPORTED
+    with pytest.raises(dfd.DfdError) as e:  # other nested types are still out of scope
+        dfd.RepartitionExec(ctx, pa.schema([("k", pa.int64()), ("s", pa.list_(pa.int32()))]), dfd.Partitioning.Hash([0], 4))
+    assert e.value.status == 6
     sch = pa.schema([("k", pa.int64())])
     with pytest.raises(dfd.DfdError):
         dfd.RepartitionExec(ctx, sch, dfd.Partitioning.Hash([1], 4))
@@ -220,6 +223,90 @@ def test_utf8view_and_dictionary_columns_round_trip(ctx):
                     got_c, want_c = got_c.dictionary_decode(), want_c.dictionary_decode()
                 assert got_c.cast(want_c.type).equals(want_c), (keys, p, name)
         ex.close()
+
+
+def reference_fixture_table(n, seed):
+    """Random rows of the reference's 9-column bench schema (src/execution_plans/benchmarks/fixture.rs:13-33)."""
+    rnd = random.Random(seed)
+    rng = np.random.default_rng(seed)
+    words = ["", "a", "tag", "hello-world", "x" * 40, "ünï", "0123456789abcdef"]
+
+    def maybe(v, p=0.1):
+        return None if rnd.random() < p else v
+
+    schema = pa.schema([pa.field("id", pa.int64(), False), pa.field("metric", pa.float64(), False), ("flag", pa.bool_()), ("label", pa.string()),
+                        ("category", pa.dictionary(pa.int32(), pa.string())), pa.field("raw", pa.uint8(), False),
+                        pa.field("ts", pa.timestamp("ns"), False), pa.field("count", pa.int32(), False), ("tags", pa.list_(pa.string()))])
+    cat = pa.DictionaryArray.from_arrays(pa.array([maybe(rnd.randrange(4)) for _ in range(n)], type=pa.int32()),
+                                         pa.array(["alpha", "beta", "", "gamma-" * 4], type=pa.string()))
+    tags = pa.array([maybe([maybe(rnd.choice(words) + str(rnd.getrandbits(8)), 0.15) for _ in range(rnd.choice([0, 0, 1, 2, 3, 7]))], 0.12)
+                     for _ in range(n)], type=pa.list_(pa.string()))
+    cols = [pa.array(rng.integers(-2**40, 2**40, n), type=pa.int64()), pa.array(rng.standard_normal(n)),
+            pa.array([maybe(rnd.random() < 0.5) for _ in range(n)], type=pa.bool_()),
+            pa.array([maybe(rnd.choice(words) + str(rnd.getrandbits(12))) for _ in range(n)], type=pa.string()), cat,
+            pa.array(rng.integers(0, 256, n).astype(np.uint8)), pa.array(rng.integers(0, 2**60, n), type=pa.timestamp("ns")),
+            pa.array(rng.integers(-2**31, 2**31, n).astype(np.int32)), tags]
+    return pa.Table.from_arrays(cols, schema=schema)
+
+
+@pytest.mark.parametrize("keys", [[0], [3], [4, 0], [7, 2]])
+def test_reference_bench_fixture_schema_with_list_column(ctx, keys):
+    """All nine columns of the reference's shuffle-bench schema, List<Utf8> included, through the operator: the schema
+    that comes out is the one that went in and every destination holds the oracle's rows in the oracle's order — null
+    lists, empty lists, null elements and sliced input batches included."""
+    n, N = 30_000, 16
+    table = reference_fixture_table(n, 21)
+    ex = dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash(keys, N), chunk_rows=8_192)
+    cuts = [0, 3, 4_000, 4_003, 17_001, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        for rb in table.slice(a, b - a).to_batches(max_chunksize=2_500):
+            ex.push_batch(rb)
+    ex.finish()
+    outs = collect(ex, N)
+    dest = orc.partition_ids([table.column(k).combine_chunks() for k in keys], n, N)
+    order, starts = expected_partitions(dest, N)
+    total = 0
+    for p in range(N):
+        want = table.take(pa.array(order[starts[p]:starts[p + 1]]))
+        assert outs[p].schema.equals(table.schema), (p, outs[p].schema)
+        assert outs[p].num_rows == want.num_rows, p
+        total += outs[p].num_rows
+        for name in table.column_names:
+            got_c, want_c = outs[p].column(name).combine_chunks(), want.column(name).combine_chunks()
+            if pa.types.is_dictionary(got_c.type):
+                got_c, want_c = got_c.dictionary_decode(), want_c.dictionary_decode()
+            assert got_c.equals(want_c), (keys, p, name)
+        for chunk in outs[p].column("tags").chunks:
+            chunk.validate(full=True)
+    assert total == n
+    ex.close()
+
+
+def test_list_column_edge_shapes(ctx):
+    """List<Binary> and List<Utf8> payload: all-null lists, all-empty lists, a batch with no list elements at all, and a child
+    array that is itself sliced (non-zero child offset)."""
+    N = 5
+    ids = pa.array(range(1000), type=pa.int64())
+    base = pa.array([[b"a", None, b"ccc"] if i % 3 == 0 else ([] if i % 3 == 1 else None) for i in range(1200)], type=pa.list_(pa.binary()))
+    sliced = base.slice(200, 1000)  # list offsets start inside the child
+    empties = pa.array([[] for _ in range(1000)], type=pa.list_(pa.string()))
+    nulls = pa.array([None] * 1000, type=pa.list_(pa.string()))
+    flat = pa.array([str(i) for i in range(3000)], type=pa.string()).slice(500, 2000)  # child with its own offset
+    fromchild = pa.ListArray.from_arrays(pa.array(range(0, 2001, 2), type=pa.int32()), flat)
+    table = pa.table([ids, sliced, empties, nulls, fromchild], names=["id", "b", "e", "n", "c"])
+    ex = dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash([0], N), chunk_rows=512)
+    for rb in table.to_batches(max_chunksize=300):
+        ex.push_batch(rb)
+    ex.finish()
+    outs = collect(ex, N)
+    dest = orc.partition_ids([ids], 1000, N)
+    order, starts = expected_partitions(dest, N)
+    for p in range(N):
+        want = table.take(pa.array(order[starts[p]:starts[p + 1]]))
+        assert outs[p].schema.equals(table.schema)
+        for name in table.column_names:
+            assert outs[p].column(name).combine_chunks().equals(want.column(name).combine_chunks()), (p, name)
+    ex.close()
 
 
 def test_bounded_pinned_pool_blocks_the_producer_until_consumers_release(ctx):
