@@ -313,12 +313,28 @@ struct PartQueue {
 
 using HeldInput = std::shared_ptr<SharedInput>;  // an input batch whose buffers an in-flight H2D still reads
 
+struct VarPrep {  // rows of one variable-width device column as they will be staged: n + 1 source offsets (the first being
+    const char* off = nullptr;   // `first`) and the bytes they span
+    int64_t first = 0;
+    const char* bytes = nullptr;
+    int64_t nbytes = 0;
+};
+
+struct DictId {  // identity of a dictionary: values buffer, offset, length
+    const void* p = nullptr;
+    int64_t offset = 0, length = 0;
+    bool operator==(const DictId& o) const { return p == o.p && offset == o.offset && length == o.length; }
+};
+
 struct Slot {
     std::vector<void*> d_in, d_in_valid, d_out, d_out_valid;  // per column device buffers
     std::vector<void*> d_in_off, d_out_off;                   // var-width: offsets buffers
     std::vector<size_t> in_cap, out_cap;                      // var-width: capacity of d_in / d_out (string bytes)
     std::vector<int64_t> first_off, data_bytes;               // var-width: first input offset / byte count of the chunk
-    std::vector<std::vector<char>> view_off, view_bytes;      // Utf8View input converted to offsets + contiguous bytes (host staging)
+    std::vector<uint8_t*> h_valid, h_bool;                    // pinned, allocated on first use: the chunk's validity / boolean bitmaps,
+                                                              //   concatenated on the host at bit granularity (bit r = row r of the chunk)
+    std::vector<char*> h_off;                                 // pinned: the chunk's var-width offsets, re-based onto the chunk's byte buffer
+    std::vector<DictId> dict_id;                              // dictionary columns: identity of the chunk's dictionary
     std::vector<dfd::Scratch> list_tmp;                       // list fields: [child offsets | child validity bits | scan block sums] (device)
     std::vector<dfd::Scratch> dict_buf;                       // dictionary KEY columns: [hashes | offsets | data | validity] of the values
     std::vector<const uint64_t*> dict_hashes;                 //   device pointers handed to the partitioner for this chunk
@@ -328,8 +344,6 @@ struct Slot {
     bool k_recorded = false, d2h_recorded = false;
     // state of the chunk currently in this slot
     int64_t rows = 0;
-    bool plain = true;
-    std::vector<int64_t> in_offset;  // per column logical offset (bit columns / validity)
     std::vector<bool> has_valid;
     OutChunk* out = nullptr;
     bool in_flight = false;
@@ -362,6 +376,9 @@ struct dfd_repartition_exec {
     int error_code = 0;
     std::string error;
     uint64_t rows_in = 0, rows_out = 0, bytes_h2d = 0, bytes_d2h = 0;
+    // host scratch of the batch being staged (pageable: an H2D from it has been staged by the time cudaMemcpyAsync returns)
+    std::vector<std::vector<char>> tmp_off, tmp_bytes;
+    std::vector<VarPrep> prep;
 };
 
 namespace {
@@ -528,6 +545,23 @@ int flush_current(dfd_repartition_exec* x) {
     if (s.rows == 0) return DFD_OK;
     std::lock_guard<std::mutex> lk(c->mu);
     XCUDA(x, cudaSetDevice(c->device), "cudaSetDevice");
+    for (int fi : x->dev_fields) {  // the buffers concatenated on the host while staging: bitmaps and re-based offsets
+        const size_t i = (size_t)fi;
+        const FieldInfo& f = x->fields[i];
+        const size_t bm = (size_t)((s.rows + 7) / 8);
+        if (s.has_valid[i]) {
+            XCUDA(x, cudaMemcpyAsync(s.d_in_valid[i], s.h_valid[i], bm, cudaMemcpyHostToDevice, x->s_h2d), "H2D validity");
+            x->bytes_h2d += bm;
+        }
+        if (f.kind == DFD_COL_BOOL) {
+            XCUDA(x, cudaMemcpyAsync(s.d_in[i], s.h_bool[i], bm, cudaMemcpyHostToDevice, x->s_h2d), "H2D boolean values");
+            x->bytes_h2d += bm;
+        }
+        if (f.var()) {
+            XCUDA(x, cudaMemcpyAsync(s.d_in_off[i], s.h_off[i], (size_t)(s.rows + 1) * f.ow(), cudaMemcpyHostToDevice, x->s_h2d), "H2D offsets");
+            x->bytes_h2d += (size_t)(s.rows + 1) * f.ow();
+        }
+    }
     XCUDA(x, cudaEventRecord(s.e_h2d, x->s_h2d), "record h2d");
     XCUDA(x, cudaStreamWaitEvent(c->stream, s.e_h2d, 0), "wait h2d");
     if (s.d2h_recorded) XCUDA(x, cudaStreamWaitEvent(c->stream, s.e_d2h, 0), "wait d2h");
@@ -537,12 +571,10 @@ int flush_current(dfd_repartition_exec* x) {
         const size_t i = (size_t)x->dev_fields[k];
         const FieldInfo& f = x->fields[i];
         if (f.var()) {
-            // offsets stay absolute: point `values` so that values + first_off is the first copied byte
-            in[k] = dfd_column{f.kind, 0, (char*)s.d_in[i] - s.first_off[i], s.d_in_off[i], s.has_valid[i] ? (uint8_t*)s.d_in_valid[i] : nullptr,
-                               s.in_offset[i], (int64_t)s.in_cap[i]};
+            in[k] = dfd_column{f.kind, 0, s.d_in[i], s.d_in_off[i], s.has_valid[i] ? (uint8_t*)s.d_in_valid[i] : nullptr, 0, (int64_t)s.in_cap[i]};
             out[k] = dfd_column{f.kind, 0, s.d_out[i], s.d_out_off[i], s.has_valid[i] ? (uint8_t*)s.d_out_valid[i] : nullptr, 0, (int64_t)s.out_cap[i]};
         } else {
-            in[k] = dfd_column{f.kind, f.width, s.d_in[i], nullptr, s.has_valid[i] ? (uint8_t*)s.d_in_valid[i] : nullptr, s.in_offset[i], 0};
+            in[k] = dfd_column{f.kind, f.width, s.d_in[i], nullptr, s.has_valid[i] ? (uint8_t*)s.d_in_valid[i] : nullptr, 0, 0};
             out[k] = dfd_column{f.kind, f.width, s.d_out[i], nullptr, s.has_valid[i] ? (uint8_t*)s.d_out_valid[i] : nullptr, 0, 0};
         }
         if (f.kind == DFD_COL_BOOL)
@@ -634,112 +666,252 @@ int open_next_slot(dfd_repartition_exec* x) {
         XCUDA(x, cudaStreamWaitEvent(x->s_h2d, s.e_k, 0), "wait k (h2d)");
     }
     s.rows = 0;
-    s.plain = true;
-    std::fill(s.in_offset.begin(), s.in_offset.end(), 0);
     std::fill(s.has_valid.begin(), s.has_valid.end(), false);
+    std::fill(s.data_bytes.begin(), s.data_bytes.end(), 0);
+    std::fill(s.dict_id.begin(), s.dict_id.end(), DictId{});
     x->cur_open = true;
     return DFD_OK;
 }
 
-bool batch_is_plain(const dfd_repartition_exec* x, const ArrowArray* b) {
-    for (size_t i = 0; i < x->n_visible; ++i) {
-        const ArrowArray* c = b->children[i];
-        if (x->fields[i].kind != DFD_COL_FIXED || x->fields[i].dict) return false;
-        if (c->null_count != 0 && c->n_buffers > 0 && c->buffers[0] != nullptr) return false;
+// append bits [lo, lo + n) of `src` (nullptr = all ones) to the bitmap `dst` at bit position `at`; bits of the last byte
+// beyond at + n are left zero, so the next append continues cleanly
+void append_bits(uint8_t* dst, int64_t at, const uint8_t* src, int64_t lo, int64_t n) {
+    auto get = [&](int64_t k) -> unsigned { return src ? (unsigned)((src[(lo + k) >> 3] >> ((lo + k) & 7)) & 1) : 1u; };
+    int64_t i = 0;
+    for (; i < n && ((at + i) & 7); ++i) {  // head: up to the next byte boundary of the destination
+        uint8_t& d = dst[(at + i) >> 3];
+        const uint8_t m = (uint8_t)(1u << ((at + i) & 7));
+        d = get(i) ? (uint8_t)(d | m) : (uint8_t)(d & ~m);
     }
-    return true;
+    uint8_t* d = dst + ((at + i) >> 3);
+    const int64_t nb = (n - i) >> 3;  // whole destination bytes
+    if (nb > 0) {
+        if (!src) {
+            memset(d, 0xff, (size_t)nb);
+        } else {
+            const int sh = (int)((lo + i) & 7);
+            const uint8_t* sp = src + ((lo + i) >> 3);
+            if (sh == 0) memcpy(d, sp, (size_t)nb);
+            else
+                for (int64_t b = 0; b < nb; ++b) d[b] = (uint8_t)((sp[b] >> sh) | (sp[b + 1] << (8 - sh)));
+        }
+        i += nb * 8;
+        d += nb;
+    }
+    if (i < n) {  // tail: a partial byte, upper bits zero
+        unsigned v = 0;
+        for (int64_t k = i; k < n; ++k) v |= get(k) << (k - i);
+        *d = (uint8_t)v;
+    }
 }
 
-// copy rows [start, start+n) of `b` into the current slot (appending for plain batches).
-// A non-plain batch (bit-packed values or validity bitmaps) is alone in its chunk:
-// its bitmaps keep their sub-byte bit offset (lo & 7) and the fixed-width values of the
-// same column are placed at that logical offset too, so one `offset` addresses both.
-int stage_rows(dfd_repartition_exec* x, const ArrowArray* b, int64_t start, int64_t n, bool plain) {
+const uint8_t* validity_of(const ArrowArray* c) {
+    return (c->null_count != 0 && c->n_buffers > 0 && c->buffers[0]) ? (const uint8_t*)c->buffers[0] : nullptr;
+}
+
+DictId dict_identity(const ArrowArray* d) {
+    return DictId{d->n_buffers > 0 ? d->buffers[d->n_buffers - 1] : nullptr, d->offset, d->length};
+}
+
+// Host-side preparation of rows [start, start + n) of `b` for the open chunk: where every variable-width device column's
+// offsets and bytes come from (views and lists are converted to offsets + bytes here, index arithmetic only), and whether
+// these rows can JOIN the chunk (`*fits`): same dictionaries, and string bytes within the offset width.  The chunk's
+// byte buffers grow here when the rows need more room.
+int prepare_rows(dfd_repartition_exec* x, const ArrowArray* b, int64_t start, int64_t n, bool* fits) {
     Slot& s = x->slots[x->cur];
-    const size_t C = x->fields.size();
-    std::lock_guard<std::mutex> lk(x->ctx->mu);
-    XCUDA(x, cudaSetDevice(x->ctx->device), "cudaSetDevice");
-    // a hidden / converted variable-width column whose offsets (int32, n + 1 entries, starting at 0) and bytes were built on the host
-    auto stage_var_host = [&](size_t h, const char* off32, const char* bytes, int64_t total, int64_t bit_off) -> int {
-        if ((size_t)total > s.in_cap[h]) {
-            cudaFree(s.d_in[h]); cudaFree(s.d_out[h]);
-            s.d_in[h] = s.d_out[h] = nullptr;
-            s.in_cap[h] = s.out_cap[h] = 0;
-            size_t want = (size_t)total + (size_t)total / 4 + 256;
-            XCUDA(x, cudaMalloc(&s.d_in[h], want), "cudaMalloc(string bytes)");
-            XCUDA(x, cudaMalloc(&s.d_out[h], want), "cudaMalloc(string bytes)");
-            s.in_cap[h] = s.out_cap[h] = want;
-        }
-        XCUDA(x, cudaMemcpyAsync((char*)s.d_in_off[h] + (size_t)bit_off * 4, off32, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, x->s_h2d), "H2D offsets");
-        if (total) XCUDA(x, cudaMemcpyAsync(s.d_in[h], bytes, (size_t)total, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
-        s.first_off[h] = 0;
-        s.data_bytes[h] = total;
-        s.in_offset[h] = bit_off;
-        x->bytes_h2d += (size_t)total + (size_t)(n + 1) * 4;
-        return DFD_OK;
-    };
+    *fits = true;
     for (size_t i = 0; i < x->n_visible; ++i) {
         const FieldInfo& f = x->fields[i];
         const ArrowArray* c = b->children[i];
         const int64_t lo = c->offset + start;
-        const bool hv = !plain && c->null_count != 0 && c->n_buffers > 0 && c->buffers[0] != nullptr;
-        const int64_t bit_off = (hv || f.kind == DFD_COL_BOOL) ? (lo & 7) : 0;
-        const size_t bitmap_nb = (size_t)((bit_off + n + 7) >> 3);
+        if (validity_of(c) && !(f.flags & ARROW_FLAG_NULLABLE) && c->null_count > 0)
+            return fail(x, DFD_ERR_INVALID_ARGUMENT, "column " + f.name + ": nulls in a column the schema declares non-nullable");
         if (f.list) {
-            // List<Utf8 / Binary>: build the three hidden Binary columns of these rows on the host (index arithmetic only; the
-            // string bytes are a contiguous range of the child's data buffer and go to the device straight from there)
+            // List<Utf8 / Binary> -> three hidden Binary columns: row -> its elements' int32 lengths, row -> its elements' bytes
+            // (one contiguous range of the child's data buffer), row -> one validity byte per element
             if (c->n_children != 1 || !c->children[0]) return fail(x, DFD_ERR_INVALID_ARGUMENT, "column " + f.name + ": list array without a child");
             const ArrowArray* v = c->children[0];
             const int32_t* loff = (const int32_t*)c->buffers[1];
             const int32_t* coff = (const int32_t*)v->buffers[1] + v->offset;
-            const uint8_t* cvalid = (v->null_count != 0 && v->buffers[0]) ? (const uint8_t*)v->buffers[0] : nullptr;
+            const uint8_t* cvalid = validity_of(v);
             const int64_t e0 = loff[lo], e1 = loff[lo + n], ne = e1 - e0;
             if (ne < 0) return fail(x, DFD_ERR_INVALID_ARGUMENT, "column " + f.name + ": list offsets are not monotonic");
+            if (ne * 4 > 0x7fffffffLL) return fail(x, DFD_ERR_UNSUPPORTED, "column " + f.name + ": too many list elements in one chunk");
             const size_t hl = (size_t)f.h_len, hb = (size_t)f.h_bytes;
-            std::vector<char>& ol = s.view_off[hl];
-            std::vector<char>& dl = s.view_bytes[hl];
-            std::vector<char>& ob = s.view_off[hb];
-            ol.resize((size_t)(n + 1) * 4); ob.resize((size_t)(n + 1) * 4); dl.resize((size_t)ne * 4 + 16);
+            std::vector<char>& ol = x->tmp_off[hl];
+            std::vector<char>& dl = x->tmp_bytes[hl];
+            std::vector<char>& ob = x->tmp_off[hb];
+            ol.resize((size_t)(n + 1) * 4);
+            ob.resize((size_t)(n + 1) * 4);
+            dl.resize((size_t)ne * 4 + 16);
             int32_t* ol32 = (int32_t*)ol.data();
             int32_t* ob32 = (int32_t*)ob.data();
             int32_t* len32 = (int32_t*)dl.data();
-            if (ne * 4 > 0x7fffffffLL) return fail(x, DFD_ERR_UNSUPPORTED, "column " + f.name + ": too many list elements in one chunk");
             for (int64_t r = 0; r <= n; ++r) {
                 ol32[r] = (int32_t)(4 * ((int64_t)loff[lo + r] - e0));
                 ob32[r] = coff[loff[lo + r]] - coff[e0];
             }
             for (int64_t k = 0; k < ne; ++k) len32[k] = coff[e0 + k + 1] - coff[e0 + k];
-            int rc2 = stage_var_host(hl, ol.data(), dl.data(), ne * 4, bit_off);
-            if (rc2) return rc2;
-            if ((rc2 = stage_var_host(hb, ob.data(), (const char*)v->buffers[2] + coff[e0], (int64_t)coff[e1] - coff[e0], 0))) return rc2;
-            s.has_valid[hb] = false;
+            x->prep[hl] = VarPrep{ol.data(), 0, dl.data(), ne * 4};
+            x->prep[hb] = VarPrep{ob.data(), 0, (const char*)v->buffers[2] + coff[e0], (int64_t)coff[e1] - coff[e0]};
             if (f.h_valid >= 0) {
-                const size_t hvx = (size_t)f.h_valid;
-                std::vector<char>& ov = s.view_off[hvx];
-                std::vector<char>& dv = s.view_bytes[hvx];
-                ov.resize((size_t)(n + 1) * 4); dv.resize((size_t)ne + 16);
+                const size_t hv = (size_t)f.h_valid;
+                std::vector<char>& ov = x->tmp_off[hv];
+                std::vector<char>& dv = x->tmp_bytes[hv];
+                ov.resize((size_t)(n + 1) * 4);
+                dv.resize((size_t)ne + 16);
                 int32_t* ov32 = (int32_t*)ov.data();
                 for (int64_t r = 0; r <= n; ++r) ov32[r] = (int32_t)((int64_t)loff[lo + r] - e0);
                 for (int64_t k = 0; k < ne; ++k) {
                     const int64_t bit = v->offset + e0 + k;
                     dv[(size_t)k] = cvalid ? (char)((cvalid[bit >> 3] >> (bit & 7)) & 1) : (char)1;
                 }
-                if ((rc2 = stage_var_host(hvx, ov.data(), dv.data(), ne, 0))) return rc2;
-                s.has_valid[hvx] = false;
+                x->prep[hv] = VarPrep{ov.data(), 0, dv.data(), ne};
             }
-            if (hv) {  // the list's own validity rides on the lengths column
-                const char* src = (const char*)c->buffers[0] + (lo >> 3);
-                XCUDA(x, cudaMemcpyAsync(s.d_in_valid[hl], src, bitmap_nb, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
-                x->bytes_h2d += bitmap_nb;
+        } else if (f.var() && f.view) {
+            // Utf8View / BinaryView -> offsets + contiguous bytes (16-byte views: len | 12 inline bytes, or len | prefix |
+            // buffer index | offset into one of the variadic data buffers); from here on an ordinary Utf8 / Binary column
+            std::vector<char>& vo = x->tmp_off[i];
+            std::vector<char>& vb = x->tmp_bytes[i];
+            vo.resize((size_t)(n + 1) * 4);
+            int32_t* off32 = (int32_t*)vo.data();
+            const uint8_t* views = (const uint8_t*)c->buffers[1];
+            const uint8_t* valid = validity_of(c);
+            int64_t total = 0;
+            for (int64_t r = 0; r < n; ++r) {
+                const uint8_t* v = views + (size_t)(lo + r) * 16;
+                int32_t len = *(const int32_t*)v;
+                if (valid && !((valid[(lo + r) >> 3] >> ((lo + r) & 7)) & 1)) len = 0;
+                off32[r] = (int32_t)total;
+                total += len;
+                if (total > 0x7fffffffLL) return fail(x, DFD_ERR_UNSUPPORTED, "column " + f.name + ": more than 2 GiB of view data in one chunk");
             }
-            s.has_valid[hl] = hv;
-            s.has_valid[i] = false;
+            off32[n] = (int32_t)total;
+            vb.resize((size_t)total + 16);
+            for (int64_t r = 0; r < n; ++r) {
+                const int32_t len = off32[r + 1] - off32[r];
+                if (!len) continue;
+                const uint8_t* v = views + (size_t)(lo + r) * 16;
+                const uint8_t* src = len <= 12 ? v + 4 : (const uint8_t*)c->buffers[2 + *(const int32_t*)(v + 8)] + *(const int32_t*)(v + 12);
+                memcpy(vb.data() + off32[r], src, (size_t)len);
+            }
+            x->prep[i] = VarPrep{vo.data(), 0, vb.data(), total};
+        } else if (f.var()) {
+            const size_t ow = f.ow();
+            const char* offs = (const char*)c->buffers[1];
+            int64_t first, last;
+            if (ow == 4) { first = ((const int32_t*)offs)[lo]; last = ((const int32_t*)offs)[lo + n]; }
+            else { first = ((const int64_t*)offs)[lo]; last = ((const int64_t*)offs)[lo + n]; }
+            if (last < first) return fail(x, DFD_ERR_INVALID_ARGUMENT, "column " + f.name + ": offsets are not monotonic");
+            x->prep[i] = VarPrep{offs + (size_t)lo * ow, first, (const char*)c->buffers[2] + first, last - first};
+        } else if (f.dict) {
+            if (!c->dictionary) return fail(x, DFD_ERR_INVALID_ARGUMENT, "column " + f.name + ": dictionary array without a dictionary");
+            const DictId id = dict_identity(c->dictionary);
+            if (s.rows > 0 && !(s.dict_id[i] == id)) *fits = false;  // one dictionary per chunk (it travels by reference)
+        }
+    }
+    if (!*fits) return DFD_OK;
+    for (int fi : x->dev_fields) {
+        const size_t h = (size_t)fi;
+        const FieldInfo& f = x->fields[h];
+        if (!f.var()) continue;
+        const int64_t need = s.data_bytes[h] + x->prep[h].nbytes;
+        if (f.ow() == 4 && need > 0x7fffffffLL) {
+            if (s.rows > 0) { *fits = false; return DFD_OK; }
+            return fail(x, DFD_ERR_UNSUPPORTED, "column " + f.name + ": more than 2 GiB of string data in one chunk (use a smaller chunk_rows or LargeUtf8)");
+        }
+        if ((size_t)need <= s.in_cap[h]) continue;
+        // grow the chunk's byte buffers, keeping what is already staged (the copy is ordered after the H2D appends on the same
+        // stream; cudaFree waits for it).  Sized for a FULL chunk at the bytes per row seen so far, and at least doubled, so
+        // that growth is rare and the following batches join the chunk instead of cutting it
+        std::lock_guard<std::mutex> lk(x->ctx->mu);
+        XCUDA(x, cudaSetDevice(x->ctx->device), "cudaSetDevice");
+        size_t want = (size_t)need + (size_t)need / 4 + 256;
+        if (want < 2 * s.in_cap[h]) want = 2 * s.in_cap[h];
+        const double per_row = (double)need / (double)(s.rows + n);
+        double full = per_row * (double)x->chunk_rows * 1.25;
+        if (full > (double)(1ull << 30)) full = (double)(1ull << 30);
+        if ((size_t)full > want) want = (size_t)full;
+        if (f.ow() == 4 && want > 0x7fffffffull + 256) want = 0x7fffffffull + 256;
+        void* bigger = nullptr;
+        XCUDA(x, cudaMalloc(&bigger, want), "cudaMalloc(string bytes)");
+        if (s.data_bytes[h] > 0) {
+            cudaError_t ce = cudaMemcpyAsync(bigger, s.d_in[h], (size_t)s.data_bytes[h], cudaMemcpyDeviceToDevice, x->s_h2d);
+            if (ce != cudaSuccess) {
+                cudaFree(bigger);
+                return fail(x, DFD_ERR_CUDA, std::string("grow string bytes: ") + cudaGetErrorString(ce));
+            }
+        }
+        cudaFree(s.d_in[h]);
+        cudaFree(s.d_out[h]);
+        s.d_in[h] = bigger;
+        s.d_out[h] = nullptr;
+        s.in_cap[h] = want;
+        s.out_cap[h] = 0;
+        XCUDA(x, cudaMalloc(&s.d_out[h], want), "cudaMalloc(string bytes)");
+        s.out_cap[h] = want;
+    }
+    return DFD_OK;
+}
+
+// copy rows [start, start + n) of `b` (prepared by prepare_rows) to the end of the open chunk.  Fixed-width values and
+// string bytes go to the device straight from the batch; bitmaps (validity, boolean values) and string offsets are
+// concatenated on the host — bit-granular, offsets re-based onto the chunk's byte buffer — and follow when the chunk is
+// flushed.  A column gets a validity bitmap from the first batch that has one (earlier rows count as valid).
+int stage_rows(dfd_repartition_exec* x, const ArrowArray* b, int64_t start, int64_t n) {
+    Slot& s = x->slots[x->cur];
+    std::lock_guard<std::mutex> lk(x->ctx->mu);
+    XCUDA(x, cudaSetDevice(x->ctx->device), "cudaSetDevice");
+    auto host_bitmap = [&](std::vector<uint8_t*>& v, size_t i) -> uint8_t* {
+        if (!v[i] && cudaHostAlloc((void**)&v[i], PinnedPool::bitmap_bytes(x->chunk_rows) + 8, cudaHostAllocPortable) != cudaSuccess) v[i] = nullptr;
+        return v[i];
+    };
+    auto stage_validity = [&](size_t i, const uint8_t* valid, int64_t lo) -> int {
+        if (!valid && !s.has_valid[i]) return DFD_OK;
+        uint8_t* hb = host_bitmap(s.h_valid, i);
+        if (!hb) return fail(x, DFD_ERR_OOM, "pinned host allocation failed");
+        if (!s.has_valid[i]) {
+            append_bits(hb, 0, nullptr, 0, s.rows);
+            s.has_valid[i] = true;
+        }
+        append_bits(hb, s.rows, valid, lo, n);
+        return DFD_OK;
+    };
+    auto stage_var = [&](size_t h) -> int {
+        const VarPrep& p = x->prep[h];
+        const int64_t base = s.data_bytes[h];
+        if (x->fields[h].ow() == 4) {
+            int32_t* dst = (int32_t*)s.h_off[h] + s.rows;
+            const int32_t* src = (const int32_t*)p.off;
+            const int64_t delta = base - p.first;
+            for (int64_t r = 0; r <= n; ++r) dst[r] = (int32_t)(src[r] + delta);
+        } else {
+            int64_t* dst = (int64_t*)s.h_off[h] + s.rows;
+            const int64_t* src = (const int64_t*)p.off;
+            const int64_t delta = base - p.first;
+            for (int64_t r = 0; r <= n; ++r) dst[r] = src[r] + delta;
+        }
+        if (p.nbytes) XCUDA(x, cudaMemcpyAsync((char*)s.d_in[h] + base, p.bytes, (size_t)p.nbytes, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
+        s.data_bytes[h] = base + p.nbytes;
+        x->bytes_h2d += (size_t)p.nbytes;
+        return DFD_OK;
+    };
+    int rc2 = DFD_OK;
+    for (size_t i = 0; i < x->n_visible; ++i) {
+        const FieldInfo& f = x->fields[i];
+        const ArrowArray* c = b->children[i];
+        const int64_t lo = c->offset + start;
+        const uint8_t* valid = (f.flags & ARROW_FLAG_NULLABLE) ? validity_of(c) : nullptr;
+        if (f.list) {
+            if ((rc2 = stage_var((size_t)f.h_len)) || (rc2 = stage_var((size_t)f.h_bytes))) return rc2;
+            if (f.h_valid >= 0 && (rc2 = stage_var((size_t)f.h_valid))) return rc2;
+            if ((rc2 = stage_validity((size_t)f.h_len, valid, lo))) return rc2;  // the list's own validity rides on the lengths column
             continue;
         }
-        if (f.dict && x->key_of_field[i] >= 0) {
-            // dictionary KEY: hash the dictionary values once on the device (DataFusion hash_dictionary); rows pick dict_hashes[index]
+        if (f.dict && s.rows == 0) s.dict_id[i] = dict_identity(c->dictionary);
+        if (f.dict && x->key_of_field[i] >= 0 && s.rows == 0) {
+            // dictionary KEY: hash the dictionary values once per chunk on the device (DataFusion hash_dictionary); rows pick dict_hashes[index]
             const ArrowArray* d = c->dictionary;
-            if (!d) return fail(x, DFD_ERR_INVALID_ARGUMENT, "column " + f.name + ": dictionary array without a dictionary");
             const int64_t dn = d->offset + d->length;
             const bool dvar = f.dict_kind == DFD_COL_UTF8 || f.dict_kind == DFD_COL_LARGE_UTF8 || f.dict_kind == DFD_COL_BINARY;
             const size_t dow = f.dict_kind == DFD_COL_LARGE_UTF8 ? 8 : 4;
@@ -750,7 +922,7 @@ int stage_rows(dfd_repartition_exec* x, const ArrowArray* b, int64_t start, int6
             const size_t o_hash = 0, o_off = al((size_t)(d->length + 1) * 8), o_data = o_off + al(dvar ? (size_t)(dn + 1) * dow : 0);
             const size_t vbytes = f.dict_kind == DFD_COL_BOOL ? (size_t)((dn + 7) / 8) : (dvar ? (size_t)dbytes : (size_t)dn * f.dict_width);
             const size_t o_valid = o_data + al(vbytes + 16), total = o_valid + al((size_t)((dn + 7) / 8) + 16);
-            int rc2 = s.dict_buf[i].ensure(total, x->ctx->device);
+            rc2 = s.dict_buf[i].ensure(total, x->ctx->device);
             if (rc2) return fail(x, rc2, dfd_last_error());
             char* db = (char*)s.dict_buf[i].ptr;
             if (dvar) XCUDA(x, cudaMemcpyAsync(db + o_off, d->buffers[1], (size_t)(dn + 1) * dow, cudaMemcpyHostToDevice, x->s_h2d), "H2D dictionary offsets");
@@ -766,92 +938,21 @@ int stage_rows(dfd_repartition_exec* x, const ArrowArray* b, int64_t start, int6
             if (dhv && d->offset != 0) return fail(x, DFD_ERR_UNSUPPORTED, "column " + f.name + ": sliced dictionary values with nulls are not supported yet");
             x->bytes_h2d += vbytes + (dvar ? (size_t)(dn + 1) * dow : 0);
         }
-        if (f.var() && f.view) {
-            // Utf8View / BinaryView -> offsets + contiguous bytes on the host (16-byte views: len | 12 inline bytes, or len | prefix |
-            // buffer index | offset into one of the variadic data buffers), then the column is an ordinary Utf8 / Binary one
-            std::vector<char>& vo = s.view_off[i];
-            std::vector<char>& vb = s.view_bytes[i];
-            vo.resize((size_t)(n + 1) * 4);
-            int32_t* off32 = (int32_t*)vo.data();
-            const uint8_t* views = (const uint8_t*)c->buffers[1];
-            const uint8_t* valid = (c->null_count != 0 && c->buffers[0]) ? (const uint8_t*)c->buffers[0] : nullptr;
-            int64_t total = 0;
-            for (int64_t r = 0; r < n; ++r) {
-                const uint8_t* v = views + (size_t)(lo + r) * 16;
-                int32_t len = *(const int32_t*)v;
-                if (valid && !((valid[(lo + r) >> 3] >> ((lo + r) & 7)) & 1)) len = 0;
-                off32[r] = (int32_t)total;
-                total += len;
-            }
-            off32[n] = (int32_t)total;
-            if (total > 0x7fffffffLL) return fail(x, DFD_ERR_UNSUPPORTED, "column " + f.name + ": more than 2 GiB of view data in one chunk");
-            vb.resize((size_t)total + 16);
-            for (int64_t r = 0; r < n; ++r) {
-                const int32_t len = off32[r + 1] - off32[r];
-                if (!len) continue;
-                const uint8_t* v = views + (size_t)(lo + r) * 16;
-                const uint8_t* src = len <= 12 ? v + 4 : (const uint8_t*)c->buffers[2 + *(const int32_t*)(v + 8)] + *(const int32_t*)(v + 12);
-                memcpy(vb.data() + off32[r], src, (size_t)len);
-            }
-            if ((size_t)total > s.in_cap[i]) {
-                cudaFree(s.d_in[i]); cudaFree(s.d_out[i]);
-                s.d_in[i] = s.d_out[i] = nullptr;
-                s.in_cap[i] = s.out_cap[i] = 0;
-                size_t want = (size_t)total + (size_t)total / 4 + 256;
-                XCUDA(x, cudaMalloc(&s.d_in[i], want), "cudaMalloc(string bytes)");
-                XCUDA(x, cudaMalloc(&s.d_out[i], want), "cudaMalloc(string bytes)");
-                s.in_cap[i] = s.out_cap[i] = want;
-            }
-            // (validity keeps its sub-byte bit offset; the offsets are placed at the same logical index)
-            XCUDA(x, cudaMemcpyAsync((char*)s.d_in_off[i] + (size_t)bit_off * 4, vo.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, x->s_h2d), "H2D offsets");
-            if (total) XCUDA(x, cudaMemcpyAsync(s.d_in[i], vb.data(), (size_t)total, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
-            s.first_off[i] = 0;
-            s.data_bytes[i] = total;
-            x->bytes_h2d += (size_t)total + (size_t)(n + 1) * 4;
-        } else if (f.var()) {
-            // offsets (n + 1 entries, kept absolute) at logical index bit_off; the bytes they span at d_in
-            const size_t ow = f.ow();
-            const char* offs = (const char*)c->buffers[1];
-            int64_t first, last;
-            if (ow == 4) { first = ((const int32_t*)offs)[lo]; last = ((const int32_t*)offs)[lo + n]; }
-            else { first = ((const int64_t*)offs)[lo]; last = ((const int64_t*)offs)[lo + n]; }
-            const int64_t nbytes = last - first;
-            if (nbytes < 0) return fail(x, DFD_ERR_INVALID_ARGUMENT, "column " + f.name + ": offsets are not monotonic");
-            if ((size_t)nbytes > s.in_cap[i]) {  // grow (the slot is idle: it was emitted before being reopened)
-                cudaFree(s.d_in[i]); cudaFree(s.d_out[i]);
-                s.d_in[i] = s.d_out[i] = nullptr;
-                s.in_cap[i] = s.out_cap[i] = 0;
-                size_t want = (size_t)nbytes + (size_t)nbytes / 4 + 256;
-                XCUDA(x, cudaMalloc(&s.d_in[i], want), "cudaMalloc(string bytes)");
-                XCUDA(x, cudaMalloc(&s.d_out[i], want), "cudaMalloc(string bytes)");
-                s.in_cap[i] = s.out_cap[i] = want;
-            }
-            XCUDA(x, cudaMemcpyAsync((char*)s.d_in_off[i] + (size_t)bit_off * ow, offs + (size_t)lo * ow, (size_t)(n + 1) * ow,
-                                     cudaMemcpyHostToDevice, x->s_h2d), "H2D offsets");
-            if (nbytes) XCUDA(x, cudaMemcpyAsync(s.d_in[i], (const char*)c->buffers[2] + first, (size_t)nbytes, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
-            s.first_off[i] = first;
-            s.data_bytes[i] = nbytes;
-            x->bytes_h2d += (size_t)nbytes + (size_t)(n + 1) * ow;
+        if (f.var()) {
+            if ((rc2 = stage_var(i))) return rc2;
         } else if (f.kind == DFD_COL_FIXED) {
             const char* src = (const char*)c->buffers[1] + (size_t)lo * f.width;
-            char* dst = (char*)s.d_in[i] + (size_t)(s.rows + bit_off) * f.width;
+            char* dst = (char*)s.d_in[i] + (size_t)s.rows * f.width;
             XCUDA(x, cudaMemcpyAsync(dst, src, (size_t)n * f.width, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
             x->bytes_h2d += (size_t)n * f.width;
-        } else {  // bool values: copy the covering bytes
-            const char* src = (const char*)c->buffers[1] + (lo >> 3);
-            XCUDA(x, cudaMemcpyAsync(s.d_in[i], src, bitmap_nb, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
-            x->bytes_h2d += bitmap_nb;
+        } else {  // boolean values: one more bitmap
+            uint8_t* hb = host_bitmap(s.h_bool, i);
+            if (!hb) return fail(x, DFD_ERR_OOM, "pinned host allocation failed");
+            append_bits(hb, s.rows, (const uint8_t*)c->buffers[1], lo, n);
         }
-        if (hv) {
-            const char* src = (const char*)c->buffers[0] + (lo >> 3);
-            XCUDA(x, cudaMemcpyAsync(s.d_in_valid[i], src, bitmap_nb, cudaMemcpyHostToDevice, x->s_h2d), "H2D");
-            x->bytes_h2d += bitmap_nb;
-        }
-        if (!plain) s.in_offset[i] = bit_off;
-        s.has_valid[i] = hv;
+        if ((rc2 = stage_validity(i, valid, lo))) return rc2;
     }
     s.rows += n;
-    s.plain = plain;
     return DFD_OK;
 }
 
@@ -1023,12 +1124,11 @@ int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, 
         x->slots.resize(x->depth);
         for (Slot& s : x->slots) {
             s.d_in.assign(C, nullptr); s.d_in_valid.assign(C, nullptr); s.d_out.assign(C, nullptr); s.d_out_valid.assign(C, nullptr);
-            s.in_offset.assign(C, 0);
             s.has_valid.assign(C, false);
+            s.h_valid.assign(C, nullptr); s.h_bool.assign(C, nullptr); s.h_off.assign(C, nullptr); s.dict_id.assign(C, DictId{});
             s.d_in_off.assign(C, nullptr); s.d_out_off.assign(C, nullptr);
             s.in_cap.assign(C, 0); s.out_cap.assign(C, 0);
             s.first_off.assign(C, 0); s.data_bytes.assign(C, 0);
-            s.view_off.resize(C); s.view_bytes.resize(C);
             s.dict_buf.resize(C); s.dict_hashes.assign(C, nullptr); s.dict_valid.assign(C, nullptr);
             s.list_tmp.resize(C);
             for (size_t i = 0; i < C && e == cudaSuccess; ++i) {
@@ -1036,6 +1136,7 @@ int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, 
                 if (f.nodev()) continue;  // list placeholder: its rows live in the hidden columns
                 if (f.var()) {  // offsets now, string bytes on demand
                     e = cudaMalloc(&s.d_in_off[i], (size_t)(x->chunk_rows + 16) * f.ow());
+                    if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.h_off[i], (size_t)(x->chunk_rows + 16) * f.ow(), cudaHostAllocPortable);
                     if (e == cudaSuccess) e = cudaMalloc(&s.d_out_off[i], (size_t)(x->chunk_rows + 16) * f.ow());
                     if (e == cudaSuccess && (f.flags & ARROW_FLAG_NULLABLE)) {
                         e = cudaMalloc(&s.d_in_valid[i], PinnedPool::bitmap_bytes(x->chunk_rows) + 8);
@@ -1078,6 +1179,9 @@ int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, 
         pre.push_back(c);
     }
     for (OutChunk* c : pre) x->pool->give_back(c);
+    x->tmp_off.resize(x->fields.size());
+    x->tmp_bytes.resize(x->fields.size());
+    x->prep.resize(x->fields.size());
     x->cur = x->depth - 1;  // open_next_slot() starts at slot 0
     *out = x.release();
     return DFD_OK;
@@ -1100,6 +1204,9 @@ void dfd_repartition_exec_destroy(dfd_repartition_exec* x) {
             for (void* p : s.d_out_valid) cudaFree(p);
             for (void* p : s.d_in_off) cudaFree(p);
             for (void* p : s.d_out_off) cudaFree(p);
+            for (uint8_t* p : s.h_valid) if (p) cudaFreeHost(p);
+            for (uint8_t* p : s.h_bool) if (p) cudaFreeHost(p);
+            for (char* p : s.h_off) if (p) cudaFreeHost(p);
             for (dfd::Scratch& b : s.dict_buf) cudaFree(b.ptr);
             for (dfd::Scratch& b : s.list_tmp) cudaFree(b.ptr);
             if (s.h_part_starts) cudaFreeHost(s.h_part_starts);
@@ -1133,7 +1240,6 @@ int dfd_repartition_exec_push(dfd_repartition_exec* x, struct ArrowArray* batch)
             drop();
             return fail(x, DFD_ERR_INVALID_ARGUMENT, "record batch children shorter than the batch, or non-zero struct offset");
         }
-    const bool plain = batch_is_plain(x, batch);
     // ownership of the batch moves to a shared holder: every chunk that stages rows from it (and, for dictionary columns,
     // every output batch that references its dictionaries) keeps it alive
     HeldInput holder = std::make_shared<SharedInput>(*batch);
@@ -1142,19 +1248,27 @@ int dfd_repartition_exec_push(dfd_repartition_exec* x, struct ArrowArray* batch)
     int rc = DFD_OK;
     int64_t done = 0;
     while (done < R) {
-        if (x->cur_open) {
-            Slot& s = x->slots[x->cur];
-            bool must_flush = s.rows > 0 && (!plain || !s.plain || s.rows == x->chunk_rows);
-            if (must_flush && (rc = flush_current(x))) return rc;
-        }
         if (!x->cur_open && (rc = open_next_slot(x))) return rc;
         Slot& s = x->slots[x->cur];
-        int64_t room = x->chunk_rows - s.rows;
-        int64_t n = R - done < room ? R - done : room;
-        if ((rc = stage_rows(x, in, done, n, plain))) return rc;
+        const int64_t room = x->chunk_rows - s.rows;
+        if (room == 0) {
+            if ((rc = flush_current(x))) return rc;
+            continue;
+        }
+        const int64_t n = R - done < room ? R - done : room;
+        // batches of every shape are APPENDED to the open chunk (bitmaps concatenated at bit granularity, string offsets
+        // re-based); the chunk is cut early only when these rows cannot join it: another dictionary, or string bytes beyond
+        // what 32-bit offsets address
+        bool fits = true;
+        if ((rc = prepare_rows(x, in, done, n, &fits))) return rc;
+        if (!fits) {
+            if ((rc = flush_current(x))) return rc;
+            continue;  // (prepared again against an empty chunk, which always fits or grows)
+        }
+        if ((rc = stage_rows(x, in, done, n))) return rc;
         s.held.push_back(holder);
         done += n;
-        if ((s.rows == x->chunk_rows || !plain) && (rc = flush_current(x))) return rc;
+        if (s.rows == x->chunk_rows && (rc = flush_current(x))) return rc;
     }
     return emit_ready(x);
 }

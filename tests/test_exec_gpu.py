@@ -225,6 +225,45 @@ def test_utf8view_and_dictionary_columns_round_trip(ctx):
         ex.close()
 
 
+def test_small_batches_of_every_shape_coalesce_into_full_chunks(ctx):
+    """Batches with validity bitmaps, booleans, strings, views, dictionaries and lists are appended to the open chunk (bitmaps
+    concatenated at bit granularity, string offsets re-based) like plain ones: 400 ragged batches of ~75 rows make 4 chunks of
+    8192 rows, not 400 — and the rows still match the oracle in order.  Columns that gain a validity bitmap half-way through a
+    chunk (first batches without nulls) and a second dictionary (cuts the chunk) are part of the input."""
+    rnd = random.Random(31)
+    n, N = 30_000, 6
+    table = reference_fixture_table(n, 32)
+    # the first 5 000 rows have no nulls at all in `label` / `flag` (no validity buffers in those batches)
+    label = table.column("label").combine_chunks().to_pylist()
+    flag = table.column("flag").combine_chunks().to_pylist()
+    for r in range(5_000):
+        label[r] = label[r] if label[r] is not None else "filled"
+        flag[r] = bool(flag[r])
+    table = table.set_column(3, table.schema.field("label"), pa.array(label, type=pa.string()))
+    table = table.set_column(2, table.schema.field("flag"), pa.array(flag, type=pa.bool_()))
+    ex = dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash([0], N), chunk_rows=8_192)
+    a, pushed = 0, 0
+    while a < n:
+        b = min(n, a + rnd.randint(1, 150))
+        ex.push_batch(table.slice(a, b - a).combine_chunks().to_batches()[0])
+        a, pushed = b, pushed + 1
+    ex.finish()
+    assert pushed > 300
+    outs = [ex.execute(p).read_all() for p in range(N)]
+    dest = orc.partition_ids([table.column(0).combine_chunks()], n, N)
+    order, starts = expected_partitions(dest, N)
+    for p in range(N):
+        want = table.take(pa.array(order[starts[p]:starts[p + 1]]))
+        assert outs[p].num_rows == want.num_rows
+        assert len(outs[p].column(0).chunks) <= 4, len(outs[p].column(0).chunks)  # one batch per CHUNK and destination
+        for name in table.column_names:
+            got_c, want_c = outs[p].column(name).combine_chunks(), want.column(name).combine_chunks()
+            if pa.types.is_dictionary(got_c.type):
+                got_c, want_c = got_c.dictionary_decode(), want_c.dictionary_decode()
+            assert got_c.equals(want_c), (p, name)
+    ex.close()
+
+
 def reference_fixture_table(n, seed):
     """Random rows of the reference's 9-column bench schema (src/execution_plans/benchmarks/fixture.rs:13-33)."""
     rnd = random.Random(seed)
