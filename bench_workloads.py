@@ -232,7 +232,7 @@ def run_cfg4(args, torch, dfd, world):
 
             peak, src = B.measured_peaks()
             ach = 2.0 * row_bytes * n_total / (ms / 1e3) / 1e9
-            roof = {"bound": "hbm", "kernel": "k_scatter_onepass (8-byte group) + k_scatter (16-byte group)", "achieved": ach, "peak": peak,
+            roof = {"bound": "hbm", "kernel": "k_scatter_onepass (one launch, mixed 8- and 16-byte columns)", "achieved": ach, "peak": peak,
                     "unit": "GB/s", "frac": ach / peak, "peak_source": src, "traffic": None, "algorithmic_bytes_per_row": 2 * row_bytes}
         else:
             alg = row_bytes * n * (world - 1) / world

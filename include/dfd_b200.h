@@ -234,7 +234,12 @@ int dfd_partitioner_collect(dfd_partitioner* p, int64_t* part_starts_host, int64
  *               batches are emitted; an operator error is delivered to every
  *               partition stream (EIO + get_last_error), like the reference
  *               (src/worker/worker_connection_pool.rs:393-397).
- * Rows inside (one input chunk, one destination) keep input order.
+ * Rows inside (one input chunk, one destination) keep input order.  Input
+ * batches of every shape (validity bitmaps, booleans, strings, views, lists)
+ * are appended to the open chunk until it holds chunk_rows rows — bitmaps are
+ * concatenated at bit granularity, string offsets re-based — so small batches
+ * cost no extra kernel launches; only a batch with a DIFFERENT dictionary
+ * (or > 2 GiB of string bytes under 32-bit offsets) starts a new chunk early.
  * Supported columns: fixed-width primitives (incl. Decimal128, timestamps,
  * dates, intervals), Boolean, Utf8 / LargeUtf8 / Binary, Utf8View / BinaryView
  * (converted to offsets + bytes on the way in; the output batches carry
