@@ -933,42 +933,58 @@ __global__ void __launch_bounds__(THREADS + 32, MIN_CTAS) k_scatter_onepass(cons
         if (threadIdx.x == 0) S_MISC[0] = 0;
         block_sync<THREADS, BAR>();  // (also: SRC16 / DEST8 of this tile are visible, DELTA is free)
         // ---- decoupled look-back: exclusive prefix of every destination over the lower tiles
-        for (uint32_t p = (uint32_t)w; p < N; p += W) {
-            const uint32_t cnt = TS[p + 1] - TS[p];
-            uint32_t excl = 0;
-            if (tile > 0) {
-                const unsigned long long* d = P.lb_desc + (int64_t)p * P.n_tiles;
-                int64_t j = tile - 1;  // lane 0 looks at the nearest predecessor
-                for (;;) {
-                    const int64_t idx = j - lane;
-                    uint32_t st = LB_PREFIX, val = 0;
-                    if (idx >= 0) {
-                        unsigned long long v;
-                        uint32_t hi;
-                        do {
-                            v = lb_load(d + idx);
-                            hi = (uint32_t)(v >> 32);
-                        } while ((hi >> 2) != P.lb_epoch || (hi & 3u) == 0u);
-                        st = hi & 3u;
-                        val = (uint32_t)v;
-                    }
-                    const unsigned pm = __ballot_sync(0xffffffffu, st == LB_PREFIX);
-                    const int first = __ffs(pm) - 1;  // nearest predecessor with an inclusive prefix (-1: none)
-                    excl += __reduce_add_sync(0xffffffffu, (first < 0 || lane <= first) ? val : 0u);
-                    if (pm) break;
-                    j -= 32;
-                }
-                if (lane == 0) lb_store(P.lb_desc + (int64_t)p * P.n_tiles + tile, lb_pack(P.lb_epoch, LB_PREFIX, excl + cnt));
+        // (a warp owns destinations w, w+W, ...: the first window of predecessor descriptors is loaded for LBQ of them at once,
+        //  so their L2 round trips overlap instead of queueing behind each other — with N = 48 that is 6 per warp)
+        constexpr int LBQ = 8;
+        for (uint32_t p0 = (uint32_t)w; p0 < N; p0 += W * LBQ) {
+            unsigned long long first[LBQ];
+#pragma unroll
+            for (int q = 0; q < LBQ; ++q) {
+                const uint32_t p = p0 + (uint32_t)q * W;
+                const int64_t idx = tile - 1 - lane;
+                first[q] = (p < N && idx >= 0) ? lb_load(P.lb_desc + (int64_t)p * P.n_tiles + idx) : 0ull;
             }
-            if (lane == 0) {
-                const int64_t cap = P.dest_cap ? P.dest_cap[p] : P.region_stride;
-                if ((int64_t)excl + (int64_t)cnt > cap) S_MISC[0] = 1;
-                DELTA[p] = region_base_of<PEER>(P, p) + (int64_t)excl - (int64_t)TS[p];
-                if (P.hist_out) {
-                    P.hist_out[(int64_t)p * P.n_tiles + tile] = cnt;
-                    P.base_out[(int64_t)p * P.n_tiles + tile] = excl;
+#pragma unroll
+            for (int q = 0; q < LBQ; ++q) {
+                const uint32_t p = p0 + (uint32_t)q * W;
+                if (p >= N) break;
+                const uint32_t cnt = TS[p + 1] - TS[p];
+                uint32_t excl = 0;
+                if (tile > 0) {
+                    const unsigned long long* d = P.lb_desc + (int64_t)p * P.n_tiles;
+                    int64_t j = tile - 1;  // lane 0 looks at the nearest predecessor
+                    unsigned long long v = first[q];
+                    for (;;) {
+                        const int64_t idx = j - lane;
+                        uint32_t st = LB_PREFIX, val = 0;
+                        if (idx >= 0) {
+                            uint32_t hi = (uint32_t)(v >> 32);
+                            while ((hi >> 2) != P.lb_epoch || (hi & 3u) == 0u) {
+                                v = lb_load(d + idx);
+                                hi = (uint32_t)(v >> 32);
+                            }
+                            st = hi & 3u;
+                            val = (uint32_t)v;
+                        }
+                        const unsigned pm = __ballot_sync(0xffffffffu, st == LB_PREFIX);
+                        const int firstp = __ffs(pm) - 1;  // nearest predecessor with an inclusive prefix (-1: none)
+                        excl += __reduce_add_sync(0xffffffffu, (firstp < 0 || lane <= firstp) ? val : 0u);
+                        if (pm) break;
+                        j -= 32;
+                        v = (j - lane) >= 0 ? lb_load(d + (j - lane)) : 0ull;
+                    }
+                    if (lane == 0) lb_store(P.lb_desc + (int64_t)p * P.n_tiles + tile, lb_pack(P.lb_epoch, LB_PREFIX, excl + cnt));
                 }
-                if (tile == P.n_tiles - 1) P.totals_out[p] = (int64_t)excl + (int64_t)cnt;
+                if (lane == 0) {
+                    const int64_t cap = P.dest_cap ? P.dest_cap[p] : P.region_stride;
+                    if ((int64_t)excl + (int64_t)cnt > cap) S_MISC[0] = 1;
+                    DELTA[p] = region_base_of<PEER>(P, p) + (int64_t)excl - (int64_t)TS[p];
+                    if (P.hist_out) {
+                        P.hist_out[(int64_t)p * P.n_tiles + tile] = cnt;
+                        P.base_out[(int64_t)p * P.n_tiles + tile] = excl;
+                    }
+                    if (tile == P.n_tiles - 1) P.totals_out[p] = (int64_t)excl + (int64_t)cnt;
+                }
             }
         }
         block_sync<THREADS, BAR>();
@@ -1128,24 +1144,45 @@ __global__ void __launch_bounds__(VAR_BLOCK) k_var_write_offsets(const OFF* __re
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out_off[n] = (OFF)block_sums[gridDim.x];
 }
 
-// bytes of output row j <- bytes of input row src[j]; one thread per row
+// bytes of output row j <- bytes of input row src[j].  A warp takes 32 consecutive output rows: every lane resolves its
+// row's (source offset, length, destination offset) — the three dependent loads src -> offsets -> bytes, 32 rows in flight
+// per warp — then the warp copies the non-empty rows one after the other with all 32 lanes on consecutive bytes, so both
+// the loads and the stores of a string are coalesced whatever its length (a thread-per-row byte loop is neither, and a
+// warp runs as long as its longest string).
 template <typename OFF>
 __global__ void __launch_bounds__(256) k_var_copy_bytes(const OFF* __restrict__ in_off, int64_t in_offset,
                                                          const uint8_t* __restrict__ in_data, const uint32_t* __restrict__ src,
                                                          const OFF* __restrict__ out_off, uint8_t* __restrict__ out_data, int64_t n) {
-    // (launched with one thread per row: the three dependent loads src -> offsets -> bytes are latency bound, so the more rows
-    //  in flight the better)
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = (int64_t)src[j] + in_offset;
-        const uint8_t* s = in_data + in_off[r];
-        const int64_t len = (int64_t)(in_off[r + 1] - in_off[r]);
-        uint8_t* d = out_data + out_off[j];
-        int64_t i = 0;
-        if ((((uintptr_t)s ^ (uintptr_t)d) & 7) == 0) {  // co-aligned: byte head, 8-byte body
-            for (; i < len && ((uintptr_t)(s + i) & 7); ++i) d[i] = s[i];
-            for (; i + 8 <= len; i += 8) *(uint64_t*)(d + i) = *(const uint64_t*)(s + i);
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = ((((int64_t)blockIdx.x * blockDim.x) + threadIdx.x) >> 5) << 5; base < n; base += n_warps << 5) {
+        const int64_t j = base + lane;
+        int64_t so = 0, dof = 0, len = 0;
+        if (j < n) {
+            const int64_t r = (int64_t)src[j] + in_offset;
+            so = (int64_t)in_off[r];
+            len = (int64_t)in_off[r + 1] - so;
+            dof = (int64_t)out_off[j];
         }
-        for (; i < len; ++i) d[i] = s[i];
+        unsigned todo = __ballot_sync(0xffffffffu, len > 0);
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint8_t* s = in_data + __shfl_sync(0xffffffffu, so, l);
+            uint8_t* d = out_data + __shfl_sync(0xffffffffu, dof, l);
+            const int64_t L = __shfl_sync(0xffffffffu, len, l);
+            if (L >= 256 && (((uintptr_t)s ^ (uintptr_t)d) & 7) == 0) {  // long, co-aligned: byte head, 8-byte body
+                const int64_t head = (int64_t)((8 - ((uintptr_t)d & 7)) & 7);
+                if (lane < head) d[lane] = s[lane];
+                const int64_t words = (L - head) >> 3;
+                const uint64_t* s8 = (const uint64_t*)(s + head);
+                uint64_t* d8 = (uint64_t*)(d + head);
+                for (int64_t i = lane; i < words; i += 32) d8[i] = s8[i];
+                for (int64_t i = head + (words << 3) + lane; i < L; i += 32) d[i] = s[i];
+            } else {
+                for (int64_t i = lane; i < L; i += 32) d[i] = s[i];
+            }
+        }
     }
 }
 
