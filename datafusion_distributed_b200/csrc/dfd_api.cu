@@ -455,7 +455,10 @@ int dfd::PartitionJob::run_onepass(const OnePassLayout& L) {
             sp.stage_width = maxw;
             sp.hist_out = rest.empty() ? nullptr : d_hist;
             sp.base_out = rest.empty() ? nullptr : d_base;
-            int rc = launch_scatter(sp, maxw, ks.fast_i64 != 0 && maxw >= 8, peer, 1, c->sm_count, 0, stream);
+            // the ring's element type is at most 8 bytes: 16-byte columns travel as two row-range items per tile (see the kernel),
+            // which keeps the slots at tile x 8 bytes and the CTA count per SM independent of the schema
+            const int ring_w = maxw > 8 ? 8 : maxw;
+            int rc = launch_scatter(sp, ring_w, ks.fast_i64 != 0 && ring_w >= 8, peer, 1, c->sm_count, 0, stream);
             if (rc) return rc;
             ++launches;
             // the follow-up launches take the two-pass code path over the counts / cursors just written

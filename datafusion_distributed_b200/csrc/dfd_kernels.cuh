@@ -803,8 +803,24 @@ __global__ void __launch_bounds__(THREADS + 32, MIN_CTAS) k_scatter_onepass(cons
             const int64_t row0 = cur * T;
             const int rows = (int)((P.n_rows - row0) < T ? (P.n_rows - row0) : T);
             for (int c = 0; c < P.n_cols; ++c) {
-                const int slot = acquire_slot();
-                fill(slot, P.cols[c].in, P.cols[c].in_offset + row0, rows, (uint32_t)P.cols[c].width, true);  // (width <= sizeof(V): one slot)
+                // a column wider than the ring's element type (16-byte values in an 8-byte ring) arrives as width / sizeof(V)
+                // items of T * sizeof(V) bytes each: consecutive ROW RANGES of the tile — the ring slots stay small enough for
+                // 4 resident CTAs whatever the schema
+                const uint32_t cw = (uint32_t)P.cols[c].width;
+                const int parts = cw > (uint32_t)sizeof(V) ? (int)(cw / (uint32_t)sizeof(V)) : 1;
+                const int rows_per = T / parts;
+                for (int h = 0; h < parts; ++h) {
+                    const int slot = acquire_slot();
+                    int rr = rows - h * rows_per;
+                    rr = rr < 0 ? 0 : (rr > rows_per ? rows_per : rr);
+                    if (rr > 0) {
+                        fill(slot, P.cols[c].in, P.cols[c].in_offset + row0 + h * rows_per, rr, cw, true);
+                    } else {  // ragged last tile: nothing in this range
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(FULL + slot);
+                        ++seq;
+                    }
+                }
             }
             cur = nxt;
         }
@@ -1004,55 +1020,86 @@ __global__ void __launch_bounds__(THREADS + 32, MIN_CTAS) k_scatter_onepass(cons
             }
 #pragma unroll 1
             for (int c = 0; c < P.n_cols; ++c) {
-                const int slot = wait_item();
-                const unsigned char* in_raw = smem + (uint32_t)slot * slot_bytes;
                 void* out_raw = P.cols[c].out;
-                // one launch moves columns of every width <= sizeof(V) (the rows were ranked once): the element type is per column
-                auto copy_col = [&](auto tag) {
-                    using E = decltype(tag);
-                    const E* in = (const E*)in_raw;
-                    E* out = (E*)out_raw;
+                const int cw = P.cols[c].width;
+                const int parts = cw > (int)sizeof(V) ? cw / (int)sizeof(V) : 1;  // (see the producer: wide columns come in row ranges)
+                for (int h = 0; h < parts; ++h) {
+                    const int slot = wait_item();
+                    const unsigned char* in_raw = smem + (uint32_t)slot * slot_bytes;
+                    // one launch moves columns of every width (the rows were ranked once): the element type is per column
+                    auto copy_col = [&](auto tag, auto split) {
+                        using E = decltype(tag);
+                        const E* in = (const E*)in_raw;
+                        E* out = (E*)out_raw;
+                        if constexpr (decltype(split)::value) {
+                            const uint32_t rows_per = (uint32_t)T / (uint32_t)parts, lo = (uint32_t)h * rows_per;
 #pragma unroll
-                    for (int k = 0; k < K; ++k)
-                        if (orow[k] != SLOT_NONE) st_stream(out + orow[k], in[src[k]]);
-                };
-                switch (P.cols[c].width) {
-                    case 16: if constexpr (sizeof(V) >= 16) copy_col(uint4{}); break;
-                    case 8: if constexpr (sizeof(V) >= 8) copy_col((unsigned long long)0); break;
-                    case 4: if constexpr (sizeof(V) >= 4) copy_col((unsigned)0); break;
-                    case 2: if constexpr (sizeof(V) >= 2) copy_col((unsigned short)0); break;
-                    default: copy_col((unsigned char)0); break;
+                            for (int k = 0; k < K; ++k) {
+                                const uint32_t sr = src[k] - lo;  // source row relative to this range (wraps when below it)
+                                if (orow[k] != SLOT_NONE && sr < rows_per) st_stream(out + orow[k], in[sr]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < K; ++k)
+                                if (orow[k] != SLOT_NONE) st_stream(out + orow[k], in[src[k]]);
+                        }
+                    };
+                    if (parts > 1) {
+                        if constexpr (sizeof(V) == 8) copy_col(uint4{}, std::true_type{});  // (the host only sends 16-byte columns this way)
+                    } else {
+                        switch (cw) {
+                            case 16: if constexpr (sizeof(V) >= 16) copy_col(uint4{}, std::false_type{}); break;
+                            case 8: if constexpr (sizeof(V) >= 8) copy_col((unsigned long long)0, std::false_type{}); break;
+                            case 4: if constexpr (sizeof(V) >= 4) copy_col((unsigned)0, std::false_type{}); break;
+                            case 2: if constexpr (sizeof(V) >= 2) copy_col((unsigned short)0, std::false_type{}); break;
+                            default: copy_col((unsigned char)0, std::false_type{}); break;
+                        }
+                    }
+                    release_item(slot);
                 }
-                release_item(slot);
             }
         } else {
             uint32_t slot_of[KV];
             compute_slots<THREADS, K, KV, BAR>(slot_of, N, tile_rows, TS, DELTA, (uint32_t*)(smem + L.off_vs), S_SCAN);
 #pragma unroll 1
             for (int c = 0; c < P.n_cols; ++c) {
-                const int slot = wait_item();
-                const unsigned char* in_raw = smem + (uint32_t)slot * slot_bytes;
                 const size_t col_out = (size_t)P.cols[c].out;  // local: pointer; peer: byte offset into every window
-                auto copy_col = [&](auto tag) {
-                    using E = decltype(tag);
-                    const E* in = (const E*)in_raw;
+                const int cw = P.cols[c].width;
+                const int parts = cw > (int)sizeof(V) ? cw / (int)sizeof(V) : 1;
+                for (int h = 0; h < parts; ++h) {
+                    const int slot = wait_item();
+                    const unsigned char* in_raw = smem + (uint32_t)slot * slot_bytes;
+                    auto copy_col = [&](auto tag, auto split) {
+                        using E = decltype(tag);
+                        const E* in = (const E*)in_raw;
+                        const uint32_t rows_per = (uint32_t)T / (uint32_t)parts, lo = (uint32_t)h * rows_per;
 #pragma unroll
-                    for (int k = 0; k < KV; ++k) {
-                        if (slot_of[k] != SLOT_NONE && !overflow) {
-                            const uint32_t i = slot_of[k] & 0xffffu, p = slot_of[k] >> 16;
-                            E* o = PEER ? (E*)((char*)OUT_BASE[p] + col_out) : (E*)col_out;  // peer: the owner's window (NVLink store)
-                            st_stream(o + ((int64_t)i + DELTA[p]), in[SRC16[i]]);
+                        for (int k = 0; k < KV; ++k) {
+                            if (slot_of[k] != SLOT_NONE && !overflow) {
+                                const uint32_t i = slot_of[k] & 0xffffu, p = slot_of[k] >> 16;
+                                uint32_t sr = SRC16[i];
+                                if constexpr (decltype(split)::value) {
+                                    sr -= lo;
+                                    if (sr >= rows_per) continue;
+                                }
+                                E* o = PEER ? (E*)((char*)OUT_BASE[p] + col_out) : (E*)col_out;  // peer: the owner's window (NVLink store)
+                                st_stream(o + ((int64_t)i + DELTA[p]), in[sr]);
+                            }
+                        }
+                    };
+                    if (parts > 1) {
+                        if constexpr (sizeof(V) == 8) copy_col(uint4{}, std::true_type{});
+                    } else {
+                        switch (cw) {
+                            case 16: if constexpr (sizeof(V) >= 16) copy_col(uint4{}, std::false_type{}); break;
+                            case 8: if constexpr (sizeof(V) >= 8) copy_col((unsigned long long)0, std::false_type{}); break;
+                            case 4: if constexpr (sizeof(V) >= 4) copy_col((unsigned)0, std::false_type{}); break;
+                            case 2: if constexpr (sizeof(V) >= 2) copy_col((unsigned short)0, std::false_type{}); break;
+                            default: copy_col((unsigned char)0, std::false_type{}); break;
                         }
                     }
-                };
-                switch (P.cols[c].width) {
-                    case 16: if constexpr (sizeof(V) >= 16) copy_col(uint4{}); break;
-                    case 8: if constexpr (sizeof(V) >= 8) copy_col((unsigned long long)0); break;
-                    case 4: if constexpr (sizeof(V) >= 4) copy_col((unsigned)0); break;
-                    case 2: if constexpr (sizeof(V) >= 2) copy_col((unsigned short)0); break;
-                    default: copy_col((unsigned char)0); break;
+                    release_item(slot);
                 }
-                release_item(slot);
             }
         }
         tile = next;

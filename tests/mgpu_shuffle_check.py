@@ -138,6 +138,44 @@ def main():
             raise
         print(f"rank {rank}: skewed shuffle reported DFD_ERR_CAPACITY (window too small for the hot destination)", flush=True)
     dist.barrier()
+    # mixed widths over the single-pass exchange: Int64 key + Int32 + Decimal128-shaped 16-byte values (the 16-byte column
+    # rides the 8-byte ring as two row-range items per tile) + Int16, N = 48 like TPC-H q5's lineitem shuffle
+    if 48 % world == 0:
+        mrows = 400_003
+        rng = np.random.Generator(np.random.PCG64(77))
+        wk = rng.integers(-(2**62), 2**62, mrows, dtype=np.int64)
+        w4 = rng.integers(-(2**31), 2**31 - 1, mrows, dtype=np.int32)
+        w16 = rng.integers(-(2**62), 2**62, (mrows, 2), dtype=np.int64)
+        w2 = rng.integers(-(2**15), 2**15 - 1, mrows, dtype=np.int16)
+        wl, wh = rank * mrows // world, (rank + 1) * mrows // world
+        host = [wk, w4, w16, w2]
+        widths = [8, 4, 16, 2]
+        keep = [torch.from_numpy(np.ascontiguousarray(a[wl:wh])).cuda() for a in host]
+        torch.cuda.synchronize()
+        wcols = [dfd.DeviceColumn(nv.COL_FIXED, w, t.data_ptr(), length=wh - wl, keep=t) for w, t in zip(widths, keep)]
+        Pw = 48 // world
+        node = dfd.NetworkShuffleExec.try_new(dfd.Partitioning.Hash([0], Pw), uuid.uuid4(), 7, world, world)
+        node.shuffle_onepass(ex, wcols, wh - wl)
+        outs, seg_starts, seg_counts = node.collect(ex)
+        wdest = orc.partition_ids([wk], mrows, 48)
+        for q in range(Pw):
+            g = rank * Pw + q
+            for r in range(world):
+                rlo, rhi = r * mrows // world, (r + 1) * mrows // world
+                want_idx = np.nonzero(wdest[rlo:rhi] == g)[0] + rlo
+                a, cnt = int(seg_starts[q, r]), int(seg_counts[q, r])
+                if cnt != len(want_idx):
+                    failures += 1
+                    print(f"rank {rank}: COUNT MISMATCH mixed widths q={q} r={r}: {cnt} != {len(want_idx)}", flush=True)
+                    continue
+                for c, w in enumerate(widths):
+                    got = np.empty(cnt * w, dtype=np.uint8)
+                    if cnt:
+                        nv.check(nv.lib().dfd_memcpy_d2h(ctx.handle, got.ctypes.data, outs[c].values + a * w, cnt * w))
+                    if not np.array_equal(got, np.ascontiguousarray(host[c][want_idx]).view(np.uint8).reshape(-1)):
+                        failures += 1
+                        print(f"rank {rank}: MISMATCH mixed widths q={q} r={r} width={w}", flush=True)
+        dist.barrier()
     # NCCL mode with nullable / boolean / string columns: per destination, rows from the producers in task order
     import pyarrow as pa
     from tests.test_exchange_gpu import _mixed_table
