@@ -612,7 +612,7 @@ def main():
     ap.add_argument("--exchange", default="onepass", choices=["onepass", "fused", "nccl"],
                     help="multi-GPU transport: single-pass fused (peer stores + peer-memory flags), two-pass fused, or NCCL send/recv")
     ap.add_argument("--parity-rows", type=int, default=1 << 21, help="rows of the multi-GPU bit-parity check run before the timed region")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5", "agg"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5", "agg", "fixture"],
                     help="cfg2 = the BASELINE.json headline (default; what the driver runs); cfg3/4/5 = the other configs (bench_workloads.py)")
     ap.add_argument("--kernel", default="onepass", choices=["onepass", "twopass"],
                     help="1-GPU partition path: single-pass k_scatter<ONEPASS> (regions) or K1/K1b/K2 (dense)")

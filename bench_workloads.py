@@ -538,8 +538,150 @@ def run_agg(args, torch, dfd, world):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------- fixture ----
+
+def fixture_table(n: int, seed: int = 3):
+    """`n` random rows of the reference's own shuffle-bench schema (src/execution_plans/benchmarks/fixture.rs:13-33):
+    id Int64, metric Float64, flag Boolean?, label Utf8?, category Dictionary<Int32, Utf8>?, raw UInt8, ts Timestamp(ns),
+    count Int32, tags List<Utf8?>? — built with vectorised numpy / pyarrow kernels (the reference uses arrow's
+    create_random_batch)."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pool = pa.array([f"label-{i:05d}-" + "x" * (i % 23) for i in range(4096)], type=pa.string())
+    tagpool = pa.array([f"t{i}" + "y" * (i % 7) for i in range(512)], type=pa.string())
+
+    def mask(p):
+        return pa.array(rng.random(n) < p)
+
+    label = pc.if_else(mask(0.1), pa.scalar(None, pa.string()), pc.take(pool, pa.array(rng.integers(0, 4096, n, dtype=np.int32))))
+    flag = pc.if_else(mask(0.1), pa.scalar(None, pa.bool_()), pa.array(rng.random(n) < 0.5))
+    cat_idx = pc.if_else(mask(0.1), pa.scalar(None, pa.int32()), pa.array(rng.integers(0, 16, n, dtype=np.int32)))
+    category = pa.DictionaryArray.from_arrays(cat_idx, pa.array([f"category-{i}" for i in range(16)], type=pa.string()))
+    lens = rng.integers(0, 4, n, dtype=np.int32)
+    offs = np.zeros(n + 1, dtype=np.int32)
+    np.cumsum(lens, out=offs[1:])
+    ne = int(offs[-1])
+    elems = pc.if_else(pa.array(rng.random(ne) < 0.1), pa.scalar(None, pa.string()), pc.take(tagpool, pa.array(rng.integers(0, 512, ne, dtype=np.int32))))
+    tags = pa.ListArray.from_arrays(pa.array(offs), elems, mask=pa.array(rng.random(n) < 0.1))
+    schema = pa.schema([pa.field("id", pa.int64(), False), pa.field("metric", pa.float64(), False), ("flag", pa.bool_()), ("label", pa.string()),
+                        ("category", pa.dictionary(pa.int32(), pa.string())), pa.field("raw", pa.uint8(), False),
+                        pa.field("ts", pa.timestamp("ns"), False), pa.field("count", pa.int32(), False), ("tags", pa.list_(pa.string()))])
+    cols = [pa.array(rng.integers(-(2**62), 2**62, n, dtype=np.int64)), pa.array(rng.standard_normal(n)), flag, label, category,
+            pa.array(rng.integers(0, 256, n).astype(np.uint8)), pa.array(rng.integers(0, 2**60, n, dtype=np.int64)).cast(pa.timestamp("ns")),
+            pa.array(rng.integers(-(2**31), 2**31 - 1, n).astype(np.int32)), tags]
+    return pa.Table.from_arrays(cols, schema=schema)
+
+
+def run_fixture(args, torch, dfd, world):
+    """The reference's own bench schema (9 columns: nullable booleans / strings, a dictionary, a List<Utf8>) in the reference's
+    own batch size (8192 rows) through the host operator, HOST batches in, HOST batches out: what a worker's
+    RepartitionExec(Hash) sees.  Every batch is appended to the open device chunk (bit-granular bitmap concatenation, string
+    offsets re-based), so the kernels still run on 1 Mi-row chunks.  Parity: a 100 000-row prefix against the oracle's
+    partition ids + pyarrow take, values and order.  CPU arm beside it: the same batches through oracle partition ids +
+    arrow `take` per destination (what RepartitionExec does with arrow-rs), one thread per input partition."""
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+
+    import pyarrow as pa
+
+    from oracle import oracle as orc
+    from tests.util import expected_partitions
+
+    dist, rank, local_rank, ctx, ex = _dist_setup(torch, dfd, world)
+    N = 8
+    n = args.rows if args.rows != (1 << 26) else 1 << 22
+    table = fixture_table(n)
+    batches = table.to_batches(max_chunksize=8192)
+
+    def through_operator(bs, check=None):
+        op = dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash([0], N), chunk_rows=1 << 20, pipeline_depth=3, pinned_pool_chunks=6)
+        readers = [op.execute(p) for p in range(N)]
+        got = [[] for _ in range(N)]
+
+        def consume(p):
+            for rb in readers[p]:
+                got[p].append(rb if check else rb.num_rows)
+
+        ths = [threading.Thread(target=consume, args=(p,)) for p in range(N)]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for b in bs:
+            op.push_batch(b)
+        op.finish()
+        for t in ths:
+            t.join()
+        dt = time.perf_counter() - t0
+        st = op.stats()
+        del readers
+        op.close()
+        return dt, st, got
+
+    # ---- parity on a prefix
+    m = min(n, 100_000)
+    pre = table.slice(0, m)
+    _, _, got = through_operator(pre.to_batches(max_chunksize=8192), check=True)
+    dest = orc.partition_ids([pre.column(0).combine_chunks()], m, N)
+    order, starts = expected_partitions(dest, N)
+    bad = 0
+    for p in range(N):
+        want = pre.take(pa.array(order[starts[p]:starts[p + 1]]))
+        have = pa.Table.from_batches(got[p], schema=table.schema) if got[p] else table.schema.empty_table()
+        for name in table.column_names:
+            a, b = have.column(name).combine_chunks(), want.column(name).combine_chunks()
+            if pa.types.is_dictionary(a.type):
+                a, b = a.dictionary_decode(), b.dictionary_decode()
+            if not a.equals(b):
+                bad += 1
+    if bad:
+        _emit({"workload": "fixture", "parity_checked": False, "mismatching_columns": bad})
+        sys.exit(3)
+
+    # ---- timed: the whole table in 8192-row batches
+    through_operator(batches)
+    times, st = [], None
+    for _ in range(max(2, args.steps // 3)):
+        dt, st, got = through_operator(batches)
+        assert sum(sum(g) for g in got) == n
+        times.append(dt)
+    sec = sum(times) / len(times)
+
+    # ---- CPU arm: partition ids + arrow take per destination, input partitions on a thread pool
+    threads = min(32, os.cpu_count() or 1)
+    sample = batches[: max(1, min(len(batches), (1 << 21) // 8192))]
+
+    def cpu_one(b):
+        d = orc.partition_ids([b.column(0)], b.num_rows, N)
+        o, s = expected_partitions(d, N)
+        return sum(b.take(pa.array(o[s[p]:s[p + 1]])).num_rows for p in range(N) if s[p + 1] > s[p])
+
+    with ThreadPoolExecutor(threads) as tp:
+        list(tp.map(cpu_one, sample[:threads]))
+        t0 = time.perf_counter()
+        rows_cpu = sum(tp.map(cpu_one, sample))
+        cpu_sec = time.perf_counter() - t0
+    if rank == 0:
+        _emit({"metric": "shuffle rows/sec, end to end (reference bench schema, 8192-row batches)", "value": n / sec, "unit": "rows/s", "n_gpus": world,
+               "steps": len(times), "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "mixed (i64/f64/bool/utf8/dictionary/u8/timestamp/i32/list<utf8>)", "data": "synthetic",
+               "config": {"workload": f"fixture: {n} rows of the reference's 9-column bench schema (fixture.rs:13-33), {len(batches)} input batches of 8192 "
+                                      f"rows, Hash([id], {N}), chunk_rows 1 Mi, host batches in / host batches out", "rows": n},
+               "parity_checked": True, "parity_rows": m,
+               "e2e": {"value": n / sec, "unit": "rows/s", "h2d_bytes_per_step": int(st["bytes_h2d"]), "d2h_bytes_per_step": int(st["bytes_d2h"]),
+                       "output_batches": int(sum(len(g) for g in got)), "input_batches": len(batches)},
+               "cpu_baseline": {"value": rows_cpu / cpu_sec, "unit": "rows/s", "cores": threads, "kind": "port",
+                                "sample": f"{rows_cpu} rows ({len(sample)} batches): oracle partition ids + pyarrow take per destination, "
+                                          f"{threads} threads over input batches"},
+               "gpu_launches": int(ctx.metrics()["kernel_launches"])})
+    ex.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run(args, torch, dfd, world):
-    {"cfg3": run_cfg3, "cfg4": run_cfg4, "cfg5": run_cfg5, "agg": run_agg}[args.workload](args, torch, dfd, world)
+    {"cfg3": run_cfg3, "cfg4": run_cfg4, "cfg5": run_cfg5, "agg": run_agg, "fixture": run_fixture}[args.workload](args, torch, dfd, world)
 
 
 # ------------------------------------------------------------------------------ CPU reference arm (cfg4) ----
