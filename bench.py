@@ -288,6 +288,40 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def measure_pcie(torch, mib: int = 256, reps: int = 6):
+    """Measured PCIe copy rates of this box (pinned host memory <-> HBM, CUDA events): each direction alone and both at
+    once on two streams — the ceiling of the host-to-host (`e2e`) number, which moves every byte once in each direction."""
+    nbytes = mib << 20
+    h_in, h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory(), torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_a, d_b = torch.empty(nbytes, dtype=torch.uint8, device="cuda"), torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(h2d: bool, d2h: bool) -> float:
+        torch.cuda.synchronize()
+        start = torch.cuda.Event(enable_timing=True)
+        start.record()
+        ends = []
+        for on, st, dst, src in ((h2d, s1, d_a, h_in), (d2h, s2, h_out, d_b)):
+            if not on:
+                continue
+            st.wait_event(start)
+            with torch.cuda.stream(st):
+                for _ in range(reps):
+                    dst.copy_(src, non_blocking=True)
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(st)
+                ends.append(e)
+        torch.cuda.synchronize()
+        return max(start.elapsed_time(e) for e in ends) / 1e3
+
+    run(True, True)
+    total = nbytes * reps / 1e9
+    out = {"h2d_gbs": total / run(True, False), "d2h_gbs": total / run(False, True), "duplex_gbs_per_direction": total / run(True, True),
+           "how": f"{reps} x {mib} MiB pinned copies per direction, CUDA events"}
+    del h_in, h_out, d_a, d_b
+    return out
+
+
 def run_e2e(ctx, dfd, n, args):
     """Same metric through the reference-facing operator (RepartitionExec over the C-ABI)
     with HOST buffers: pinned Arrow record batches in, per-destination Arrow batches out,
@@ -310,7 +344,7 @@ def run_e2e(ctx, dfd, n, args):
     st = None
     for it in range(2 + max(1, args.steps // 2)):
         ex = dfd.RepartitionExec(ctx, schema, dfd.Partitioning.Hash([0], NUM_PARTITIONS), chunk_rows=args.e2e_chunk_rows,
-                                 pipeline_depth=3, pinned_pool_chunks=6)
+                                 pipeline_depth=3, pinned_pool_chunks=args.e2e_pool_chunks)
         readers = [ex.execute(p) for p in range(NUM_PARTITIONS)]
         counts = [0] * NUM_PARTITIONS
 
@@ -337,9 +371,18 @@ def run_e2e(ctx, dfd, n, args):
             times.append(dt)
     best = sum(times) / len(times)
     pt.close()
+    import torch
+
+    pcie = measure_pcie(torch)
     return {"value": n / best, "unit": "rows/s", "h2d_bytes_per_step": int(st["bytes_h2d"]), "d2h_bytes_per_step": int(st["bytes_d2h"]),
             "ms_per_step": best * 1e3, "steps": len(times), "batch_rows": args.e2e_batch_rows, "chunk_rows": args.e2e_chunk_rows,
-            "api": "RepartitionExec.push_batch/finish/execute(partition) over dfd_repartition_exec_* (Arrow C Data / C Stream)"}
+            "api": "RepartitionExec.push_batch/finish/execute(partition) over dfd_repartition_exec_* (Arrow C Data / C Stream)",
+            # the last operator of the loop: pinned output chunks it held / pinned itself / took over from the context's cache,
+            # and where the producer thread's time went
+            "operator": {"pinned_chunks": int(st["pinned_chunks"]), "pinned_chunks_allocated": int(st["pinned_chunks_allocated"]),
+                         "pinned_chunks_reused": int(st["pinned_chunks_reused"]), "push_ms": st["ns_push"] / 1e6,
+                         "wait_d2h_ms": st["ns_wait_d2h"] / 1e6, "wait_pool_ms": st["ns_wait_pool"] / 1e6},
+            "pcie": pcie, "frac_of_pcie_duplex": (int(st["bytes_h2d"]) / best / 1e9) / pcie["duplex_gbs_per_direction"]}
 
 
 TRAFFIC_ONEPASS = 8.564484e9  # dram__bytes_read.sum + dram__bytes_write.sum of one k_scatter_onepass launch at cfg-2 (profiles/r02c_ncu_summary.md)
@@ -609,6 +652,7 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the worker to its GPU's NUMA node")
     ap.add_argument("--e2e-batch-rows", type=int, default=1 << 20)
     ap.add_argument("--e2e-chunk-rows", type=int, default=1 << 20)
+    ap.add_argument("--e2e-pool-chunks", type=int, default=6, help="pinned output chunks the operator pre-allocates (the pool grows on demand)")
     ap.add_argument("--exchange", default="onepass", choices=["onepass", "fused", "nccl"],
                     help="multi-GPU transport: single-pass fused (peer stores + peer-memory flags), two-pass fused, or NCCL send/recv")
     ap.add_argument("--parity-rows", type=int, default=1 << 21, help="rows of the multi-GPU bit-parity check run before the timed region")

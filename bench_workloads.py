@@ -670,7 +670,10 @@ def run_fixture(args, torch, dfd, world):
                                       f"rows, Hash([id], {N}), chunk_rows 1 Mi, host batches in / host batches out", "rows": n},
                "parity_checked": True, "parity_rows": m,
                "e2e": {"value": n / sec, "unit": "rows/s", "h2d_bytes_per_step": int(st["bytes_h2d"]), "d2h_bytes_per_step": int(st["bytes_d2h"]),
-                       "output_batches": int(sum(len(g) for g in got)), "input_batches": len(batches)},
+                       "output_batches": int(sum(len(g) for g in got)), "input_batches": len(batches),
+                       "operator": {"pinned_chunks": int(st["pinned_chunks"]), "pinned_chunks_allocated": int(st["pinned_chunks_allocated"]),
+                                    "pinned_chunks_reused": int(st["pinned_chunks_reused"]), "push_ms": st["ns_push"] / 1e6,
+                                    "wait_d2h_ms": st["ns_wait_d2h"] / 1e6, "wait_pool_ms": st["ns_wait_pool"] / 1e6}},
                "cpu_baseline": {"value": rows_cpu / cpu_sec, "unit": "rows/s", "cores": threads, "kind": "port",
                                 "sample": f"{rows_cpu} rows ({len(sample)} batches): oracle partition ids + pyarrow take per destination, "
                                           f"{threads} threads over input batches"},

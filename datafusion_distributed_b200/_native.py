@@ -72,7 +72,8 @@ class DfdExecOptions(C.Structure):
 
 
 class DfdExecStats(C.Structure):
-    _fields_ = [("rows_in", C.c_uint64), ("rows_out", C.c_uint64), ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64)]
+    _fields_ = [(n, C.c_uint64) for n in ("rows_in", "rows_out", "bytes_h2d", "bytes_d2h", "pinned_chunks", "pinned_chunks_allocated",
+                                          "pinned_chunks_reused", "ns_push", "ns_wait_d2h", "ns_wait_pool")]
 
 
 class ArrowSchemaStruct(C.Structure):

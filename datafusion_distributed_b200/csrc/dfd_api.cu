@@ -681,6 +681,7 @@ void dfd_ctx_destroy(dfd_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    c->pinned_cache.reset();  // unpins the cached output chunks of finished host operators
     if (c->scratch.ptr) cudaFree(c->scratch.ptr);
     if (c->flush.ptr) cudaFree(c->flush.ptr);
     if (c->var_scratch.ptr) cudaFree(c->var_scratch.ptr);

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -116,6 +117,70 @@ struct OutChunk {
     std::shared_ptr<PinnedPool> pool;
 };
 
+void destroy_out_chunk(OutChunk* c) {
+    for (void* p : c->values)
+        if (p) cudaFreeHost(p);
+    for (void* p : c->validity)
+        if (p) cudaFreeHost(p);
+    for (void* p : c->offsets)
+        if (p) cudaFreeHost(p);
+    for (void* p : c->views) free(p);
+    delete c;
+}
+
+// Pinned output chunks of FINISHED operators, kept by the worker context for the next operator with the same column
+// layout and chunk size.  Pinning memory is slow (cudaHostAlloc of a 64 MiB chunk costs milliseconds — as long as
+// moving several chunks over PCIe), and a worker runs the same stage shapes again and again: the reference's workers
+// get the same effect from their caching allocator (mimalloc, benchmarks/cdk/bin/worker.rs:32).  Bounded by bytes
+// (DFD_PINNED_CACHE_BYTES, default 4 GiB); freed with the context.
+struct PinnedCache {
+    struct Entry {
+        std::string layout;
+        int64_t chunk_rows;
+        OutChunk* chunk;
+        size_t bytes;
+    };
+    std::mutex mu;
+    std::vector<Entry> entries;
+    size_t bytes = 0, max_bytes = (size_t)4 << 30;
+    int device = 0;
+    PinnedCache() {
+        if (const char* e = getenv("DFD_PINNED_CACHE_BYTES")) max_bytes = (size_t)strtoull(e, nullptr, 10);
+    }
+    OutChunk* take(const std::string& layout, int64_t chunk_rows) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (size_t i = entries.size(); i-- > 0;)
+            if (entries[i].chunk_rows == chunk_rows && entries[i].layout == layout) {
+                OutChunk* c = entries[i].chunk;
+                bytes -= entries[i].bytes;
+                entries.erase(entries.begin() + (long)i);
+                return c;
+            }
+        return nullptr;
+    }
+    bool put(const std::string& layout, int64_t chunk_rows, OutChunk* c, size_t nbytes) {  // false: over budget, caller frees
+        std::lock_guard<std::mutex> lk(mu);
+        if (bytes + nbytes > max_bytes) return false;
+        entries.push_back(Entry{layout, chunk_rows, c, nbytes});
+        bytes += nbytes;
+        return true;
+    }
+    ~PinnedCache() {
+        cudaSetDevice(device);
+        for (Entry& e : entries) destroy_out_chunk(e.chunk);
+    }
+};
+
+std::shared_ptr<PinnedCache> pinned_cache_of(dfd_ctx* ctx) {  // caller holds no lock; the slot is written once under ctx->mu
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->pinned_cache) {
+        auto pc = std::make_shared<PinnedCache>();
+        pc->device = ctx->device;
+        ctx->pinned_cache = pc;
+    }
+    return std::static_pointer_cast<PinnedCache>(ctx->pinned_cache);
+}
+
 struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
     int device = 0;
     int64_t chunk_rows = 0;
@@ -125,6 +190,9 @@ struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
     std::vector<OutChunk*> free_list;
     std::vector<OutChunk*> all;
     size_t max_chunks = 0;  // 0 = unbounded; otherwise acquire() blocks until a consumer returns a chunk (back-pressure)
+    std::weak_ptr<PinnedCache> cache;  // the worker context's cache (gone once the context is destroyed)
+    std::string layout;                // what makes two pools' chunks interchangeable: per field kind / width / nullable / view
+    std::atomic<uint64_t> n_allocated{0}, n_reused{0};  // chunks pinned by this pool / taken over from the context's cache
 
     static size_t value_bytes(const FieldInfo& f, int64_t rows) {
         if (f.var()) return 0;  // string bytes are sized per chunk
@@ -132,15 +200,24 @@ struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
     }
     static size_t bitmap_bytes(int64_t rows) { return (size_t)((rows + 63) / 64 * 8 + 8); }
 
-    static void destroy_chunk(OutChunk* c) {
-        for (void* p : c->values)
-            if (p) cudaFreeHost(p);
-        for (void* p : c->validity)
-            if (p) cudaFreeHost(p);
-        for (void* p : c->offsets)
-            if (p) cudaFreeHost(p);
-        for (void* p : c->views) free(p);
-        delete c;
+    void set_fields(const std::vector<FieldInfo>& fs) {
+        fields = fs;
+        layout.clear();
+        for (const FieldInfo& f : fields) {
+            char b[64];
+            snprintf(b, sizeof b, "%d:%d:%d:%d:%d;", (int)f.kind, (int)f.width, (int)((f.flags & ARROW_FLAG_NULLABLE) != 0), (int)f.view, (int)f.nodev());
+            layout += b;
+        }
+    }
+    size_t chunk_bytes(const OutChunk* c) const {  // pinned bytes one chunk holds right now
+        size_t n = 0;
+        for (size_t i = 0; i < fields.size(); ++i) {
+            const FieldInfo& f = fields[i];
+            if (f.nodev()) continue;
+            n += f.var() ? c->data_cap[i] + (size_t)(chunk_rows + 16) * f.ow() : value_bytes(f, chunk_rows);
+            if (f.flags & ARROW_FLAG_NULLABLE) n += bitmap_bytes(chunk_rows);
+        }
+        return n;
     }
 
     // A pooled pinned chunk.  With a bound (`max_chunks`), the producer BLOCKS here until a consumer has released a chunk:
@@ -156,6 +233,15 @@ struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
                 return c;
             }
         }
+        if (std::shared_ptr<PinnedCache> pc = cache.lock())
+            if (OutChunk* c = pc->take(layout, chunk_rows)) {  // a chunk a finished operator of the same shape left behind
+                c->refs.store(0);
+                c->inputs.clear();
+                n_reused.fetch_add(1);
+                std::lock_guard<std::mutex> lk(mu);
+                all.push_back(c);
+                return c;
+            }
         OutChunk* c = new (std::nothrow) OutChunk();
         if (!c) return nullptr;
         cudaSetDevice(device);
@@ -176,7 +262,7 @@ struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
                 if (v) cudaFreeHost(v);
                 if (b) cudaFreeHost(b);
                 if (o) cudaFreeHost(o);
-                destroy_chunk(c);
+                destroy_out_chunk(c);
                 return nullptr;
             }
             c->values.push_back(v);
@@ -186,6 +272,7 @@ struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
             c->views.push_back(f.view ? malloc((size_t)(chunk_rows + 16) * 16) : nullptr);
             c->view_sizes.push_back(0);
         }
+        n_allocated.fetch_add(1);
         std::lock_guard<std::mutex> lk(mu);
         all.push_back(c);
         return c;
@@ -198,8 +285,15 @@ struct PinnedPool : std::enable_shared_from_this<PinnedPool> {
         }
         cv.notify_one();
     }
+    // The pool dies with its operator and the last output batch: its chunks go to the context's cache (if the context is
+    // still there and the cache has room), otherwise the memory is unpinned.
     ~PinnedPool() {
-        for (OutChunk* c : all) destroy_chunk(c);
+        std::shared_ptr<PinnedCache> pc = cache.lock();
+        cudaSetDevice(device);
+        for (OutChunk* c : all) {
+            c->inputs.clear();
+            if (!pc || !pc->put(layout, chunk_rows, c, chunk_bytes(c))) destroy_out_chunk(c);
+        }
     }
 };
 
@@ -376,12 +470,20 @@ struct dfd_repartition_exec {
     int error_code = 0;
     std::string error;
     uint64_t rows_in = 0, rows_out = 0, bytes_h2d = 0, bytes_d2h = 0;
+    uint64_t ns_push = 0, ns_wait_d2h = 0, ns_wait_pool = 0;  // producer-thread time: inside push/finish; of which blocked on a D2H / on the pinned pool
     // host scratch of the batch being staged (pageable: an H2D from it has been staged by the time cudaMemcpyAsync returns)
     std::vector<std::vector<char>> tmp_off, tmp_bytes;
     std::vector<VarPrep> prep;
 };
 
 namespace {
+
+struct ScopedNs {  // adds the scope's wall time to a counter
+    uint64_t& acc;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit ScopedNs(uint64_t& a) : acc(a) {}
+    ~ScopedNs() { acc += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 int fail(dfd_repartition_exec* x, int code, const std::string& msg) {
     {
@@ -405,7 +507,11 @@ int fail(dfd_repartition_exec* x, int code, const std::string& msg) {
 // hand the finished chunk in `s` to the per-destination queues
 int emit_slot(dfd_repartition_exec* x, Slot& s) {
     if (!s.in_flight) return DFD_OK;
-    XCUDA(x, cudaEventSynchronize(s.e_d2h), "D2H");
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        XCUDA(x, cudaEventSynchronize(s.e_d2h), "D2H");
+        x->ns_wait_d2h += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    }
     OutChunk* oc = s.out;
     for (const FieldInfo& f : x->fields)
         if (f.dict) { oc->inputs = s.held; break; }  // the output batches reference the inputs' dictionaries
@@ -616,7 +722,11 @@ int flush_current(dfd_repartition_exec* x) {
     XCUDA(x, cudaEventRecord(s.e_k, c->stream), "record k");
     s.k_recorded = true;
     // D2H of the destination-sorted chunk into a pooled pinned buffer
-    s.out = x->pool->acquire();
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        s.out = x->pool->acquire();
+        x->ns_wait_pool += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    }
     if (!s.out) return fail(x, DFD_ERR_OOM, "pinned host allocation failed");
     XCUDA(x, cudaStreamWaitEvent(x->s_d2h, s.e_k, 0), "wait k");
     for (size_t k = 0; k < D; ++k) {
@@ -1166,7 +1276,8 @@ int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, 
     x->pool = std::make_shared<PinnedPool>();
     x->pool->device = ctx->device;
     x->pool->chunk_rows = x->chunk_rows;
-    x->pool->fields = x->fields;
+    x->pool->set_fields(x->fields);
+    x->pool->cache = pinned_cache_of(ctx);
     x->pool->max_chunks = (opts && opts->max_pinned_chunks > 0) ? (size_t)opts->max_pinned_chunks : 0;
     if (x->pool->max_chunks && x->pool->max_chunks < (size_t)pool_chunks) x->pool->max_chunks = (size_t)pool_chunks;
     std::vector<OutChunk*> pre;
@@ -1226,6 +1337,7 @@ void dfd_repartition_exec_destroy(dfd_repartition_exec* x) {
 
 int dfd_repartition_exec_push(dfd_repartition_exec* x, struct ArrowArray* batch) {
     if (!x || !batch) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_repartition_exec_push: NULL argument");
+    ScopedNs timed(x->ns_push);
     auto drop = [&]() { if (batch->release) batch->release(batch); };
     if (x->finished) { drop(); return set_error(DFD_ERR_INVALID_ARGUMENT, "push after finish/error: %s", x->error.c_str()); }
     if (batch->n_children != (int64_t)x->n_visible) {
@@ -1276,6 +1388,7 @@ int dfd_repartition_exec_push(dfd_repartition_exec* x, struct ArrowArray* batch)
 int dfd_repartition_exec_finish(dfd_repartition_exec* x) {
     if (!x) return set_error(DFD_ERR_INVALID_ARGUMENT, "NULL exec");
     if (x->finished) return x->error_code ? set_error(x->error_code, "%s", x->error.c_str()) : DFD_OK;
+    ScopedNs timed(x->ns_push);
     int rc = flush_current(x);
     if (rc) return rc;
     for (int i = 0; i < x->depth; ++i) {
@@ -1449,6 +1562,16 @@ int dfd_repartition_exec_stats(dfd_repartition_exec* x, dfd_exec_stats* out) {
     out->rows_out = x->rows_out;
     out->bytes_h2d = x->bytes_h2d;
     out->bytes_d2h = x->bytes_d2h;
+    out->pinned_chunks = 0;
+    if (x->pool) {
+        std::lock_guard<std::mutex> pl(x->pool->mu);
+        out->pinned_chunks = (uint64_t)x->pool->all.size();
+    }
+    out->pinned_chunks_allocated = x->pool ? x->pool->n_allocated.load() : 0;
+    out->pinned_chunks_reused = x->pool ? x->pool->n_reused.load() : 0;
+    out->ns_push = x->ns_push;
+    out->ns_wait_d2h = x->ns_wait_d2h;
+    out->ns_wait_pool = x->ns_wait_pool;
     return DFD_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -44,6 +45,7 @@ struct dfd_ctx {
     dfd::Scratch lb;           // single-pass mode: [ticket, done | 256 B] [look-back descriptors u64 [N][n_tiles]]
     uint32_t lb_epoch = 0;     // epoch of the last single-pass launch (30 bits; descriptors of older epochs are stale)
     dfd_metrics metrics = {};
+    std::shared_ptr<void> pinned_cache;  // host operator: pinned output chunks of finished operators (dfd_exec.cu: PinnedCache)
     std::mutex mu;
 };
 

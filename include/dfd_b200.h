@@ -284,6 +284,13 @@ typedef struct {
 
 typedef struct {
     uint64_t rows_in, rows_out, bytes_h2d, bytes_d2h;
+    /* pinned output chunks: held by this operator now / pinned by it (cudaHostAlloc) / taken over from the worker
+     * context's cache of chunks that finished operators of the same column layout left behind (the role of the
+     * reference workers' caching allocator, benchmarks/cdk/bin/worker.rs:32; bound: env DFD_PINNED_CACHE_BYTES, 4 GiB) */
+    uint64_t pinned_chunks, pinned_chunks_allocated, pinned_chunks_reused;
+    /* producer-thread wall time inside push()/finish(), and the parts of it spent blocked on a D2H copy of a slot
+     * being recycled and on the pinned pool (allocation, or back-pressure when max_pinned_chunks is set) */
+    uint64_t ns_push, ns_wait_d2h, ns_wait_pool;
 } dfd_exec_stats;
 
 int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, const int32_t* key_cols,

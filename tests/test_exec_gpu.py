@@ -379,3 +379,42 @@ def test_bounded_pinned_pool_blocks_the_producer_until_consumers_release(ctx):
     for p in range(N):
         assert np.array_equal(np.concatenate(got[p]), ref[1][starts[p]:starts[p + 1]])
     ex.close()
+
+
+def test_pinned_chunks_are_reused_by_the_next_operator_of_the_same_shape(ctx):
+    """The worker context keeps the pinned output chunks of finished operators: a second operator with the same column
+    layout and chunk size pins nothing new (the reference's workers get this from their caching allocator,
+    benchmarks/cdk/bin/worker.rs:32), a different layout does not take them, and the results stay bit-identical."""
+    n, N = 200_000, 8
+    cols = cfg2_columns(n, 3)
+    table = pa.table(cols, names=["k", "a", "b"])
+    ref, counts, starts = orc.repartition_table(cols, [0], N, 8192, 1)
+
+    def run(schema_table, chunk_rows):
+        ex = dfd.RepartitionExec(ctx, schema_table.schema, dfd.Partitioning.Hash([0], N), chunk_rows=chunk_rows, pinned_pool_chunks=4)
+        for rb in schema_table.to_batches(max_chunksize=8_192):
+            ex.push_batch(rb)
+        ex.finish()
+        outs = collect(ex, N)
+        st = ex.stats()
+        ex.close()
+        return outs, st
+
+    outs, st1 = run(table, 32_768)
+    assert st1["pinned_chunks"] >= 4 and st1["pinned_chunks_allocated"] + st1["pinned_chunks_reused"] == st1["pinned_chunks"]
+    for p in range(N):
+        assert np.array_equal(outs[p].column("b").to_numpy(), ref[2][starts[p]:starts[p + 1]])
+    del outs  # the last output batch returns its chunk; the pool dies and hands its chunks to the context
+    outs, st2 = run(table, 32_768)
+    assert st2["pinned_chunks_reused"] >= 4 and st2["pinned_chunks_allocated"] == 0, st2
+    for p in range(N):
+        assert outs[p].num_rows == counts[p]
+        for c, name in enumerate(["k", "a", "b"]):
+            assert np.array_equal(outs[p].column(name).to_numpy(), ref[c][starts[p]:starts[p + 1]])
+    del outs
+    # another chunk size / another layout: nothing is taken over
+    _, st3 = run(table, 16_384)
+    assert st3["pinned_chunks_reused"] == 0
+    _, st4 = run(table.select(["k", "a"]), 32_768)
+    assert st4["pinned_chunks_reused"] == 0
+    assert st4["ns_push"] > 0
