@@ -140,6 +140,7 @@ SIGNATURES = {
     "dfd_repartition_exec_destroy": (None, [_VP]),
     "dfd_repartition_exec_push": (C.c_int, [_VP, C.POINTER(ArrowArrayStruct)]),
     "dfd_repartition_exec_finish": (C.c_int, [_VP]),
+    "dfd_repartition_exec_abort": (C.c_int, [_VP, C.c_char_p]),
     "dfd_repartition_exec_run": (C.c_int, [_VP, C.POINTER(ArrowArrayStreamStruct)]),
     "dfd_repartition_exec_execute": (C.c_int, [_VP, C.c_uint32, C.POINTER(ArrowArrayStreamStruct)]),
     "dfd_repartition_exec_stats": (C.c_int, [_VP, C.POINTER(DfdExecStats)]),

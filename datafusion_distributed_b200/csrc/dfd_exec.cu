@@ -1403,6 +1403,13 @@ int dfd_repartition_exec_finish(dfd_repartition_exec* x) {
     return DFD_OK;
 }
 
+int dfd_repartition_exec_abort(dfd_repartition_exec* x, const char* message) {
+    if (!x) return set_error(DFD_ERR_INVALID_ARGUMENT, "NULL exec");
+    if (x->finished) return DFD_OK;  // already finished or failed: the first outcome stands
+    fail(x, DFD_ERR_INTERNAL, std::string("aborted by the producer: ") + (message ? message : "input failed"));
+    return DFD_OK;
+}
+
 int dfd_repartition_exec_run(dfd_repartition_exec* x, struct ArrowArrayStream* input) {
     if (!x || !input || !input->get_next) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_repartition_exec_run: NULL argument");
     int rc = DFD_OK;

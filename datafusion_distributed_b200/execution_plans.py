@@ -101,6 +101,11 @@ class RepartitionExec:
     def finish(self):
         nv.check(nv.lib().dfd_repartition_exec_finish(self._h))
 
+    def abort(self, message: str):
+        """The producer's input failed: every partition stream ends with an error carrying `message`
+        (≙ RepartitionExec forwarding an input error to all of its output partitions)."""
+        nv.check(nv.lib().dfd_repartition_exec_abort(self._h, message.encode()))
+
     def run(self, reader):
         """Pull a pyarrow RecordBatchReader (≙ child.execute()) to exhaustion."""
         cs = nv.ArrowArrayStreamStruct()

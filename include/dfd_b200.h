@@ -299,6 +299,11 @@ int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, 
 void dfd_repartition_exec_destroy(dfd_repartition_exec* x);
 int dfd_repartition_exec_push(dfd_repartition_exec* x, struct ArrowArray* batch);
 int dfd_repartition_exec_finish(dfd_repartition_exec* x);
+/* The producer's INPUT failed: instead of finish(), fail the operator — every partition stream's get_next returns EIO
+ * with `message` (rows already queued are still delivered first), exactly as RepartitionExec forwards an input error
+ * to all of its output partitions and as the reference fans a task failure out (worker_connection_pool.rs:393-397).
+ * Call from the producer thread (in place of push/finish).  No effect after finish() or an earlier error. */
+int dfd_repartition_exec_abort(dfd_repartition_exec* x, const char* message);
 int dfd_repartition_exec_run(dfd_repartition_exec* x, struct ArrowArrayStream* input);
 int dfd_repartition_exec_execute(dfd_repartition_exec* x, uint32_t partition, struct ArrowArrayStream* out);
 int dfd_repartition_exec_stats(dfd_repartition_exec* x, dfd_exec_stats* out);

@@ -127,6 +127,7 @@ public:
     const Partitioning& output_partitioning() const { return partitioning_; }
     void push_batch(ArrowArray* batch) { check(dfd_repartition_exec_push(h_, batch)); }  // ownership moves
     void finish() { check(dfd_repartition_exec_finish(h_)); }
+    void abort(const std::string& message) { check(dfd_repartition_exec_abort(h_, message.c_str())); }  // input failed: every stream ends with EIO + message
     void run(ArrowArrayStream* input) { check(dfd_repartition_exec_run(h_, input)); }
     // ≙ ExecutionPlan::execute(partition, ctx) -> SendableRecordBatchStream
     void execute(uint32_t partition, ArrowArrayStream* out) { check(dfd_repartition_exec_execute(h_, partition, out)); }

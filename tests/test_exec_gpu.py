@@ -139,6 +139,37 @@ def test_operator_errors(ctx):
     ex.close()
 
 
+def test_abort_fails_every_partition_stream_after_the_queued_rows(ctx):
+    """The producer's input failed mid-way (dfd_repartition_exec_abort): like RepartitionExec forwarding an input error to
+    all of its outputs, every partition stream delivers what was already queued and then ends with the input's message."""
+    n, N = 40_000, 4
+    cols = cfg2_columns(n, 2)
+    table = pa.table(cols, names=["k", "v"])
+    ex = dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash([0], N), chunk_rows=8_192)
+    for rb in table.to_batches(max_chunksize=8_192):
+        ex.push_batch(rb)
+    ex.abort("parquet page 7 is corrupt")
+    ex.abort("a second failure does not replace the first")
+    for p in range(N):
+        reader, rows, err = ex.execute(p), 0, None
+        try:
+            for rb in reader:
+                rows += rb.num_rows
+        except Exception as e:  # pyarrow raises from get_next's EIO with get_last_error's text
+            err = str(e)
+        assert err is not None and "parquet page 7 is corrupt" in err, (p, rows, err)
+    with pytest.raises(dfd.DfdError):
+        ex.push_batch(table.to_batches()[0])
+    ex.close()
+    # abort after a clean finish is a no-op: the streams end normally
+    ex = dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash([0], N))
+    ex.push_batch(table.to_batches()[0])
+    ex.finish()
+    ex.abort("too late")
+    assert sum(ex.execute(p).read_all().num_rows for p in range(N)) == table.to_batches()[0].num_rows
+    ex.close()
+
+
 def test_utf8_keys_and_payload_through_the_operator(ctx):
     """cfg-3 / cfg-5 shapes through the host operator: Utf8 keys, Utf8 / LargeUtf8 / Binary payload, nulls, slices."""
     rnd = random.Random(12)
