@@ -345,10 +345,10 @@ def run_cfg5(args, torch, dfd, world):
     if rank == 0:
         pr = part_rows.cpu().numpy()
         ach = sent_max * (world - 1) / max(world, 1) / (ms_push / 1e3) / 1e9 if world > 1 else None
-        _emit({"metric": "shuffle rows/sec (ClickBench GROUP BY UserID, SearchPhrase stand-in, 100M rows, Int64 + Utf8 keys, skewed)",
+        _emit({"metric": f"shuffle rows/sec (ClickBench GROUP BY UserID, SearchPhrase stand-in, {n_total / 1e6:g}M rows, Int64 + Utf8 keys, skewed)",
                "value": n_total / (ms_push / 1e3), "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": ms_push, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64/utf8", "data": "synthetic",
-               "config": {"workload": "cfg5: 100M rows, UserID Int64 Zipf(1.1) over 17M ids, SearchPhrase Utf8 (70% empty, Zipf over 6M phrases of "
+               "config": {"workload": f"cfg5: {n_total / 1e6:g}M rows (the config names 100M on 8 GPUs = 12.5M per GPU; --rows scales it to the GPUs used), UserID Int64 Zipf(1.1) over 17M ids, SearchPhrase Utf8 (70% empty, Zipf over 6M phrases of "
                                       "5-60 B), c Int64; Hash([UserID, SearchPhrase], 3 x tasks), device-resident", "rows": n_total,
                           "num_partitions": N, "partitions_per_task": P, "exchange": "push (local partition -> flag all-gather -> k_push_runs peer stores)"},
                "parity_checked": True, "parity_rows": n_chk,
