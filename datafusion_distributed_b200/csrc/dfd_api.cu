@@ -196,14 +196,20 @@ int dfd::PartitionJob::prepare(Partitioner* part, const dfd_column* in_cols, int
         } else if (ic.kind == DFD_COL_UTF8 || ic.kind == DFD_COL_LARGE_UTF8 || ic.kind == DFD_COL_BINARY) {
             if (peer) return set_error(DFD_ERR_UNSUPPORTED, "column %d: variable-width columns need the NCCL exchange mode", i);
             if (!ic.offsets || !oc.offsets) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: offsets is NULL", i);
-            // capacity check needs the input's byte count: two small D2H reads
+            // capacity check needs the input's byte count: two small D2H reads and a stream sync — unless the caller built
+            // the offsets itself and vouches for in_cols[i].values_bytes (the host operator: a sync here would hold its
+            // producer thread until the chunk's H2D has landed, serialising staging with the copies)
             const size_t ow = ic.kind == DFD_COL_LARGE_UTF8 ? 8 : 4;
             int64_t first = 0, last = 0;
-            cudaError_t e = cudaMemcpyAsync(&first, (const char*)ic.offsets + (size_t)ic.offset * ow, ow, cudaMemcpyDeviceToHost, stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(&last, (const char*)ic.offsets + (size_t)(ic.offset + n_rows) * ow, ow, cudaMemcpyDeviceToHost, stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-            if (e != cudaSuccess) return cuda_error(e, "reading variable-width offsets");
-            if (ow == 4) { first = (int32_t)first; last = (int32_t)last; }
+            if (var_bytes_known) {
+                last = ic.values_bytes;
+            } else {
+                cudaError_t e = cudaMemcpyAsync(&first, (const char*)ic.offsets + (size_t)ic.offset * ow, ow, cudaMemcpyDeviceToHost, stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(&last, (const char*)ic.offsets + (size_t)(ic.offset + n_rows) * ow, ow, cudaMemcpyDeviceToHost, stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+                if (e != cudaSuccess) return cuda_error(e, "reading variable-width offsets");
+                if (ow == 4) { first = (int32_t)first; last = (int32_t)last; }
+            }
             const int64_t nbytes = last - first;
             if (nbytes < 0) return set_error(DFD_ERR_INVALID_ARGUMENT, "column %d: offsets are not monotonic", i);
             if (oc.values_bytes < nbytes)
@@ -584,8 +590,9 @@ int dfd::launch_lengths_to_offsets(const void* len, int ow, int64_t n, unsigned 
 }
 
 int dfd::partition_device_locked(Partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,
-                                 const dfd_column* out_cols, cudaStream_t stream) {
+                                 const dfd_column* out_cols, cudaStream_t stream, bool var_bytes_known) {
     PartitionJob job;
+    job.var_bytes_known = var_bytes_known;
     int rc = job.prepare(p, in_cols, n_cols, n_rows, out_cols, false, stream);
     if (rc) return rc;
     if ((rc = job.run_hist_scan())) return rc;

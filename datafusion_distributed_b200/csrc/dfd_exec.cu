@@ -677,7 +677,8 @@ int flush_current(dfd_repartition_exec* x) {
         const size_t i = (size_t)x->dev_fields[k];
         const FieldInfo& f = x->fields[i];
         if (f.var()) {
-            in[k] = dfd_column{f.kind, 0, s.d_in[i], s.d_in_off[i], s.has_valid[i] ? (uint8_t*)s.d_in_valid[i] : nullptr, 0, (int64_t)s.in_cap[i]};
+            // (values_bytes = the bytes staged into this chunk: the offsets were built here, so the partitioner need not read them back)
+            in[k] = dfd_column{f.kind, 0, s.d_in[i], s.d_in_off[i], s.has_valid[i] ? (uint8_t*)s.d_in_valid[i] : nullptr, 0, s.data_bytes[i]};
             out[k] = dfd_column{f.kind, 0, s.d_out[i], s.d_out_off[i], s.has_valid[i] ? (uint8_t*)s.d_out_valid[i] : nullptr, 0, (int64_t)s.out_cap[i]};
         } else {
             in[k] = dfd_column{f.kind, f.width, s.d_in[i], nullptr, s.has_valid[i] ? (uint8_t*)s.d_in_valid[i] : nullptr, 0, 0};
@@ -692,7 +693,7 @@ int flush_current(dfd_repartition_exec* x) {
             x->part->key_modes[(size_t)x->key_of_field[i]] = dfd::KEY_HASH_DICTIONARY;
             x->part->key_dicts[(size_t)x->key_of_field[i]] = dfd_partitioner::KeyDict{s.dict_hashes[i], s.dict_valid[i]};
         }
-    int rc = partition_device_locked(x->part, in.data(), (int)D, s.rows, out.data(), c->stream);
+    int rc = partition_device_locked(x->part, in.data(), (int)D, s.rows, out.data(), c->stream, /*var_bytes_known=*/true);
     if (rc) return fail(x, rc, dfd_last_error());
     // list fields: child offsets = exclusive scan of the gathered element lengths; child validity bytes -> bitmap
     std::vector<const void*> d2h_src(C, nullptr);

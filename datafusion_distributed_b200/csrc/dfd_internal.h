@@ -87,6 +87,7 @@ struct PartitionJob {
     unsigned long long* d_block_sums = nullptr;
     uint64_t bytes = 0;
     int64_t n_rows = 0, n_tiles = 0;
+    bool var_bytes_known = false;        // set before prepare(): in_cols[i].values_bytes IS the byte count of a var-width input (no D2H read + sync)
     bool onepass_tiling = false;         // set before prepare(): tile the rows for the single-pass kernel (ONEPASS_K rows per thread)
     int64_t out_rows = -1;               // rows of the OUTPUT row space (-1: n_rows; single-pass regions: N * region_rows)
     uint32_t* d_hist = nullptr;
@@ -141,6 +142,6 @@ int hash_columns_locked(Ctx* c, const dfd_column* cols, int n_cols, int64_t n_ro
 
 // Launches K1 -> K1b -> K2 on `stream`; caller holds ctx->mu and has set the device.
 int partition_device_locked(Partitioner* p, const dfd_column* in_cols, int n_cols, int64_t n_rows,
-                            const dfd_column* out_cols, cudaStream_t stream);
+                            const dfd_column* out_cols, cudaStream_t stream, bool var_bytes_known = false);
 
 }  // namespace dfd
