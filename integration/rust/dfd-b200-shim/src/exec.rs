@@ -154,6 +154,16 @@ impl GpuRepartitionExec {
         })
     }
 
+    pub fn key_columns(&self) -> &[i32] {
+        &self.key_columns
+    }
+    pub fn num_partitions(&self) -> usize {
+        self.num_partitions
+    }
+    pub fn options(&self) -> GpuRepartitionOptions {
+        self.options
+    }
+
     /// First caller creates the operator and starts ONE feeder: every input partition is polled concurrently (like
     /// RepartitionExec's per-input tasks) and funnelled through a bounded channel into a single blocking thread, because
     /// `push` / `finish` are single-producer and may block on the device pipeline.

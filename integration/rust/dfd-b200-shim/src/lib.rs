@@ -7,10 +7,15 @@
 //!   src/worker/impl_set_plan.rs:122-124): every stage-head hash `RepartitionExec` whose keys are plain columns and whose
 //!   schema `dfd_schema_supported` accepts is swapped one-for-one (no node added or removed, as the hook's contract asks).
 //!
+//! * [`GpuRepartitionCodec`] — `PhysicalExtensionCodec` for the node, for deployments that place it on the coordinator
+//!   instead of through the worker hook.
+//!
 //! Not compiled in the build image (no Rust toolchain there); see Cargo.toml.
+pub mod codec;
 pub mod exec;
 pub mod ffi;
 pub mod hook;
 
+pub use codec::GpuRepartitionCodec;
 pub use exec::{GpuContext, GpuRepartitionExec, GpuRepartitionOptions};
 pub use hook::{install_gpu_repartition_hook, rewrite_hash_repartitions};
