@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "dfd_b200.h"
+#include "dfd_host_staging.h"
 #include "dfd_internal.h"
 
 using namespace dfd;
@@ -529,22 +530,8 @@ int emit_slot(dfd_repartition_exec* x, Slot& s) {
         if (!x->fields[c].view) continue;
         // Utf8View output: 16-byte views over the chunk's single data buffer (inline when <= 12 bytes)
         const int32_t* off = (const int32_t*)oc->offsets[c];
-        const uint8_t* data = (const uint8_t*)oc->values[c];
-        uint8_t* views = (uint8_t*)oc->views[c];
         const int64_t rows = s.rows;
-        for (int64_t r = 0; r < rows; ++r) {
-            uint8_t* v = views + (size_t)r * 16;
-            const int32_t o = off[r], len = off[r + 1] - o;
-            memset(v, 0, 16);
-            *(int32_t*)v = len;
-            if (len <= 12) {
-                memcpy(v + 4, data + o, (size_t)len);
-            } else {
-                memcpy(v + 4, data + o, 4);
-                *(int32_t*)(v + 8) = 0;
-                *(int32_t*)(v + 12) = o;
-            }
-        }
+        dfd::host::build_views(off, (const uint8_t*)oc->values[c], rows, (uint8_t*)oc->views[c]);
         oc->view_sizes[c] = off[rows];
     }
     oc->refs.store(1);  // guard while slicing
@@ -784,37 +771,7 @@ int open_next_slot(dfd_repartition_exec* x) {
     return DFD_OK;
 }
 
-// append bits [lo, lo + n) of `src` (nullptr = all ones) to the bitmap `dst` at bit position `at`; bits of the last byte
-// beyond at + n are left zero, so the next append continues cleanly
-void append_bits(uint8_t* dst, int64_t at, const uint8_t* src, int64_t lo, int64_t n) {
-    auto get = [&](int64_t k) -> unsigned { return src ? (unsigned)((src[(lo + k) >> 3] >> ((lo + k) & 7)) & 1) : 1u; };
-    int64_t i = 0;
-    for (; i < n && ((at + i) & 7); ++i) {  // head: up to the next byte boundary of the destination
-        uint8_t& d = dst[(at + i) >> 3];
-        const uint8_t m = (uint8_t)(1u << ((at + i) & 7));
-        d = get(i) ? (uint8_t)(d | m) : (uint8_t)(d & ~m);
-    }
-    uint8_t* d = dst + ((at + i) >> 3);
-    const int64_t nb = (n - i) >> 3;  // whole destination bytes
-    if (nb > 0) {
-        if (!src) {
-            memset(d, 0xff, (size_t)nb);
-        } else {
-            const int sh = (int)((lo + i) & 7);
-            const uint8_t* sp = src + ((lo + i) >> 3);
-            if (sh == 0) memcpy(d, sp, (size_t)nb);
-            else
-                for (int64_t b = 0; b < nb; ++b) d[b] = (uint8_t)((sp[b] >> sh) | (sp[b + 1] << (8 - sh)));
-        }
-        i += nb * 8;
-        d += nb;
-    }
-    if (i < n) {  // tail: a partial byte, upper bits zero
-        unsigned v = 0;
-        for (int64_t k = i; k < n; ++k) v |= get(k) << (k - i);
-        *d = (uint8_t)v;
-    }
-}
+using dfd::host::append_bits;  // (bit-granular bitmap concatenation: dfd_host_staging.h, CPU-tested)
 
 const uint8_t* validity_of(const ArrowArray* c) {
     return (c->null_count != 0 && c->n_buffers > 0 && c->buffers[0]) ? (const uint8_t*)c->buffers[0] : nullptr;
@@ -855,30 +812,20 @@ int prepare_rows(dfd_repartition_exec* x, const ArrowArray* b, int64_t start, in
             ol.resize((size_t)(n + 1) * 4);
             ob.resize((size_t)(n + 1) * 4);
             dl.resize((size_t)ne * 4 + 16);
-            int32_t* ol32 = (int32_t*)ol.data();
-            int32_t* ob32 = (int32_t*)ob.data();
-            int32_t* len32 = (int32_t*)dl.data();
-            for (int64_t r = 0; r <= n; ++r) {
-                ol32[r] = (int32_t)(4 * ((int64_t)loff[lo + r] - e0));
-                ob32[r] = coff[loff[lo + r]] - coff[e0];
-            }
-            for (int64_t k = 0; k < ne; ++k) len32[k] = coff[e0 + k + 1] - coff[e0 + k];
-            x->prep[hl] = VarPrep{ol.data(), 0, dl.data(), ne * 4};
-            x->prep[hb] = VarPrep{ob.data(), 0, (const char*)v->buffers[2] + coff[e0], (int64_t)coff[e1] - coff[e0]};
+            int32_t* ov32 = nullptr;
+            char* dvb = nullptr;
             if (f.h_valid >= 0) {
-                const size_t hv = (size_t)f.h_valid;
-                std::vector<char>& ov = x->tmp_off[hv];
-                std::vector<char>& dv = x->tmp_bytes[hv];
+                std::vector<char>& ov = x->tmp_off[(size_t)f.h_valid];
+                std::vector<char>& dv = x->tmp_bytes[(size_t)f.h_valid];
                 ov.resize((size_t)(n + 1) * 4);
                 dv.resize((size_t)ne + 16);
-                int32_t* ov32 = (int32_t*)ov.data();
-                for (int64_t r = 0; r <= n; ++r) ov32[r] = (int32_t)((int64_t)loff[lo + r] - e0);
-                for (int64_t k = 0; k < ne; ++k) {
-                    const int64_t bit = v->offset + e0 + k;
-                    dv[(size_t)k] = cvalid ? (char)((cvalid[bit >> 3] >> (bit & 7)) & 1) : (char)1;
-                }
-                x->prep[hv] = VarPrep{ov.data(), 0, dv.data(), ne};
+                ov32 = (int32_t*)ov.data();
+                dvb = dv.data();
             }
+            dfd::host::split_list_rows(loff, coff, cvalid, v->offset, lo, n, (int32_t*)ol.data(), (int32_t*)ob.data(), (int32_t*)dl.data(), ov32, dvb);
+            x->prep[hl] = VarPrep{ol.data(), 0, dl.data(), ne * 4};
+            x->prep[hb] = VarPrep{ob.data(), 0, (const char*)v->buffers[2] + coff[e0], (int64_t)coff[e1] - coff[e0]};
+            if (f.h_valid >= 0) x->prep[(size_t)f.h_valid] = VarPrep{(const char*)ov32, 0, dvb, ne};
         } else if (f.var() && f.view) {
             // Utf8View / BinaryView -> offsets + contiguous bytes (16-byte views: len | 12 inline bytes, or len | prefix |
             // buffer index | offset into one of the variadic data buffers); from here on an ordinary Utf8 / Binary column
@@ -887,25 +834,10 @@ int prepare_rows(dfd_repartition_exec* x, const ArrowArray* b, int64_t start, in
             vo.resize((size_t)(n + 1) * 4);
             int32_t* off32 = (int32_t*)vo.data();
             const uint8_t* views = (const uint8_t*)c->buffers[1];
-            const uint8_t* valid = validity_of(c);
-            int64_t total = 0;
-            for (int64_t r = 0; r < n; ++r) {
-                const uint8_t* v = views + (size_t)(lo + r) * 16;
-                int32_t len = *(const int32_t*)v;
-                if (valid && !((valid[(lo + r) >> 3] >> ((lo + r) & 7)) & 1)) len = 0;
-                off32[r] = (int32_t)total;
-                total += len;
-                if (total > 0x7fffffffLL) return fail(x, DFD_ERR_UNSUPPORTED, "column " + f.name + ": more than 2 GiB of view data in one chunk");
-            }
-            off32[n] = (int32_t)total;
+            const int64_t total = dfd::host::view_offsets(views, validity_of(c), lo, n, off32);
+            if (total < 0) return fail(x, DFD_ERR_UNSUPPORTED, "column " + f.name + ": more than 2 GiB of view data in one chunk");
             vb.resize((size_t)total + 16);
-            for (int64_t r = 0; r < n; ++r) {
-                const int32_t len = off32[r + 1] - off32[r];
-                if (!len) continue;
-                const uint8_t* v = views + (size_t)(lo + r) * 16;
-                const uint8_t* src = len <= 12 ? v + 4 : (const uint8_t*)c->buffers[2 + *(const int32_t*)(v + 8)] + *(const int32_t*)(v + 12);
-                memcpy(vb.data() + off32[r], src, (size_t)len);
-            }
+            dfd::host::view_bytes(views, c->buffers + 2, lo, n, off32, vb.data());
             x->prep[i] = VarPrep{vo.data(), 0, vb.data(), total};
         } else if (f.var()) {
             const size_t ow = f.ow();

@@ -1,0 +1,121 @@
+// dfd_host_staging.h — the pure index arithmetic of the host operator's staging (dfd_exec.cu): no CUDA, no operator
+// state, plain pointers in and out.  Kept apart so that the CPU test-suite can run exactly this code against pyarrow
+// (tests/test_host_staging.py compiles it with g++): bitmap concatenation at bit granularity, Utf8View / BinaryView ->
+// offsets + bytes and back, List<Utf8 / Binary> rows -> the three hidden Binary device columns.
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+namespace dfd {
+namespace host {
+
+// append bits [lo, lo + n) of `src` (nullptr = all ones) to the bitmap `dst` at bit position `at`; bits of the last byte
+// beyond at + n are left zero, so the next append continues cleanly
+inline void append_bits(uint8_t* dst, int64_t at, const uint8_t* src, int64_t lo, int64_t n) {
+    auto get = [&](int64_t k) -> unsigned { return src ? (unsigned)((src[(lo + k) >> 3] >> ((lo + k) & 7)) & 1) : 1u; };
+    int64_t i = 0;
+    for (; i < n && ((at + i) & 7); ++i) {  // head: up to the next byte boundary of the destination
+        uint8_t& d = dst[(at + i) >> 3];
+        const uint8_t m = (uint8_t)(1u << ((at + i) & 7));
+        d = get(i) ? (uint8_t)(d | m) : (uint8_t)(d & ~m);
+    }
+    uint8_t* d = dst + ((at + i) >> 3);
+    const int64_t nb = (n - i) >> 3;  // whole destination bytes
+    if (nb > 0) {
+        if (!src) {
+            memset(d, 0xff, (size_t)nb);
+        } else {
+            const int sh = (int)((lo + i) & 7);
+            const uint8_t* sp = src + ((lo + i) >> 3);
+            if (sh == 0) memcpy(d, sp, (size_t)nb);
+            else
+                for (int64_t b = 0; b < nb; ++b) d[b] = (uint8_t)((sp[b] >> sh) | (sp[b + 1] << (8 - sh)));
+        }
+        i += nb * 8;
+        d += nb;
+    }
+    if (i < n) {  // tail: a partial byte, upper bits zero
+        unsigned v = 0;
+        for (int64_t k = i; k < n; ++k) v |= get(k) << (k - i);
+        *d = (uint8_t)v;
+    }
+}
+
+// Utf8View / BinaryView rows [lo, lo + n) -> int32 offsets (off32[0] = 0 ... off32[n] = total bytes); a null row has length 0.
+// 16-byte views: int32 length | 12 inline bytes, or int32 length | 4-byte prefix | int32 buffer index | int32 offset.
+// Returns the total byte count, or -1 when it does not fit 32-bit offsets.
+inline int64_t view_offsets(const uint8_t* views, const uint8_t* valid, int64_t lo, int64_t n, int32_t* off32) {
+    int64_t total = 0;
+    for (int64_t r = 0; r < n; ++r) {
+        const uint8_t* v = views + (size_t)(lo + r) * 16;
+        int32_t len;
+        memcpy(&len, v, 4);
+        if (valid && !((valid[(lo + r) >> 3] >> ((lo + r) & 7)) & 1)) len = 0;
+        off32[r] = (int32_t)total;
+        total += len;
+        if (total > 0x7fffffffLL) return -1;
+    }
+    off32[n] = (int32_t)total;
+    return total;
+}
+
+// ... and their bytes, contiguous in row order (`data_buffers` = the array's variadic data buffers, i.e. buffers + 2)
+inline void view_bytes(const uint8_t* views, const void* const* data_buffers, int64_t lo, int64_t n, const int32_t* off32, char* out) {
+    for (int64_t r = 0; r < n; ++r) {
+        const int32_t len = off32[r + 1] - off32[r];
+        if (!len) continue;
+        const uint8_t* v = views + (size_t)(lo + r) * 16;
+        int32_t buf, pos;
+        memcpy(&buf, v + 8, 4);
+        memcpy(&pos, v + 12, 4);
+        const uint8_t* src = len <= 12 ? v + 4 : (const uint8_t*)data_buffers[buf] + pos;
+        memcpy(out + off32[r], src, (size_t)len);
+    }
+}
+
+// offsets + bytes -> 16-byte views over ONE data buffer (buffer index 0), inline when <= 12 bytes: the output side
+inline void build_views(const int32_t* off, const uint8_t* data, int64_t rows, uint8_t* views) {
+    for (int64_t r = 0; r < rows; ++r) {
+        uint8_t* v = views + (size_t)r * 16;
+        const int32_t o = off[r], len = off[r + 1] - o;
+        memset(v, 0, 16);
+        memcpy(v, &len, 4);
+        if (len <= 12) {
+            memcpy(v + 4, data + o, (size_t)len);
+        } else {
+            const int32_t zero = 0;
+            memcpy(v + 4, data + o, 4);
+            memcpy(v + 8, &zero, 4);
+            memcpy(v + 12, &o, 4);
+        }
+    }
+}
+
+// List<Utf8 / Binary> rows [lo, lo + n) -> the hidden device columns' host staging:
+//   len_off[n + 1]   byte offsets of every row into the LENGTHS column (4 bytes per child element)
+//   bytes_off[n + 1] byte offsets of every row into the child strings' bytes (relative to the first element's first byte)
+//   lengths[ne]      int32 length of every child element
+//   valid_off[n + 1], valid_bytes[ne]  (optional: pass nullptr) one validity byte per child element
+// `loff` = the list's int32 offsets, `coff` = the child's int32 offsets already advanced by the child's array offset,
+// `cvalid` / `cvalid_offset` = the child's validity bitmap (nullptr: all valid) and the child's array offset.
+// Returns the number of child elements ne (callers size lengths / valid_bytes with loff[lo + n] - loff[lo] beforehand).
+inline int64_t split_list_rows(const int32_t* loff, const int32_t* coff, const uint8_t* cvalid, int64_t cvalid_offset, int64_t lo, int64_t n,
+                               int32_t* len_off, int32_t* bytes_off, int32_t* lengths, int32_t* valid_off, char* valid_bytes) {
+    const int64_t e0 = loff[lo], e1 = loff[lo + n], ne = e1 - e0;
+    for (int64_t r = 0; r <= n; ++r) {
+        len_off[r] = (int32_t)(4 * ((int64_t)loff[lo + r] - e0));
+        bytes_off[r] = coff[loff[lo + r]] - coff[e0];
+    }
+    for (int64_t k = 0; k < ne; ++k) lengths[k] = coff[e0 + k + 1] - coff[e0 + k];
+    if (valid_off) {
+        for (int64_t r = 0; r <= n; ++r) valid_off[r] = (int32_t)((int64_t)loff[lo + r] - e0);
+        for (int64_t k = 0; k < ne; ++k) {
+            const int64_t bit = cvalid_offset + e0 + k;
+            valid_bytes[k] = cvalid ? (char)((cvalid[bit >> 3] >> (bit & 7)) & 1) : (char)1;
+        }
+    }
+    return ne;
+}
+
+}  // namespace host
+}  // namespace dfd
