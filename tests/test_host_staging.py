@@ -142,3 +142,35 @@ def test_list_rows_split_into_lengths_bytes_validity(shim, seed, elem_nulls):
         data = np.frombuffer(cb[2], dtype=np.uint8) if cb[2] is not None else np.zeros(0, dtype=np.uint8)
         start = int(coff[e0])
         assert data[start:start + int(bytes_off[n])].tobytes() == "".join(e for e in elems if e is not None).encode()
+
+
+def test_list_rows_with_a_sliced_child_array(shim):
+    """The child of a ListArray may itself carry an array offset (children[0]->offset != 0 in the C Data export): child
+    offsets and child validity are addressed relative to it."""
+    rnd = random.Random(11)
+    pool = pa.array(random_strings(rnd, 300, 0.2), type=pa.string())
+    k = 37
+    child = pool.slice(k)  # offset 37 into shared buffers
+    sizes = [rnd.randint(0, 3) for _ in range(80)]
+    offs = np.zeros(len(sizes) + 1, dtype=np.int32)
+    np.cumsum(sizes, out=offs[1:])
+    arr = pa.ListArray.from_arrays(pa.array(offs), child)
+    assert arr.values.offset == k
+    rows = arr.to_pylist()
+    lo, n = 5, 60
+    loff = np.frombuffer(arr.buffers()[1], dtype=np.int32)
+    cb = arr.values.buffers()
+    coff = np.frombuffer(cb[1], dtype=np.int32)[k:]
+    cvalid = np.frombuffer(cb[0], dtype=np.uint8)
+    e0, e1 = int(loff[lo]), int(loff[lo + n])
+    ne = e1 - e0
+    len_off, bytes_off, valid_off = (np.empty(n + 1, dtype=np.int32) for _ in range(3))
+    lengths, valid_bytes = np.empty(ne + 4, dtype=np.int32), np.empty(ne + 16, dtype=np.uint8)
+    assert shim.t_split_list_rows(ptr(loff), ptr(coff), ptr(cvalid), C.c_int64(k), C.c_int64(lo), C.c_int64(n), ptr(len_off), ptr(bytes_off),
+                                  ptr(lengths), ptr(valid_off), ptr(valid_bytes)) == ne
+    elems = [e for r in rows[lo:lo + n] for e in r]
+    assert np.array_equal(lengths[:ne], [0 if e is None else len(e) for e in elems])
+    assert np.array_equal(valid_bytes[:ne], [0 if e is None else 1 for e in elems])
+    data = np.frombuffer(cb[2], dtype=np.uint8)
+    start = int(coff[e0])
+    assert data[start:start + int(bytes_off[n])].tobytes() == "".join(e for e in elems if e is not None).encode()
