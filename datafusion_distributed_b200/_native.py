@@ -166,6 +166,8 @@ SIGNATURES = {
     "dfd_shuffle_stream_stats": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "dfd_shuffle_stream_end": (None, [_VP]),
     "dfd_coalesce_task_group": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dfd_route_segment_source": (C.c_int, [C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_uint32),
+                                           C.POINTER(C.c_uint32)]),
     "dfd_exchange_gather": (C.c_int, [_VP, C.c_int, C.POINTER(DfdColumn), C.c_int, C.POINTER(C.c_int64), C.c_uint32, C.c_int, C.POINTER(DfdColumn)]),
     "dfd_exchange_pending_segments": (C.c_uint32, [_VP]),
     "dfd_shuffle_host": (C.c_int, [_VP, _VP, C.POINTER(DfdColumn), C.c_int, C.c_int64, C.c_uint32, C.c_int, C.POINTER(DfdColumn),

@@ -1633,6 +1633,27 @@ int dfd_coalesce_task_group(int input_task_count, int task_index, int task_count
     return DFD_OK;
 }
 
+int dfd_route_segment_source(int route, uint32_t partitions, int producer_tasks, int consumer_tasks, int consumer, uint32_t segment,
+                             int* producer, uint32_t* slice, uint32_t* n_segments) {
+    if ((route != DFD_ROUTE_SHUFFLE && route != DFD_ROUTE_COALESCE && route != DFD_ROUTE_BROADCAST) || partitions < 1 || producer_tasks < 1 ||
+        consumer_tasks < 1 || consumer_tasks > producer_tasks || consumer < 0 || consumer >= producer_tasks)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_route_segment_source: bad arguments");
+    if (route == DFD_ROUTE_SHUFFLE && consumer_tasks != producer_tasks)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_route_segment_source: a shuffle has as many consumer tasks as workers");
+    const Route R{route, partitions, producer_tasks, consumer_tasks};
+    const uint32_t n = R.n_segments(consumer);
+    if (n_segments) *n_segments = n;
+    if (producer || slice) {
+        if (segment >= n) return set_error(DFD_ERR_INVALID_ARGUMENT, "dfd_route_segment_source: segment %u out of range [0,%u)", segment, n);
+        int r = -1;
+        uint32_t g = 0;
+        R.source(consumer, segment, &r, &g);
+        if (producer) *producer = r;
+        if (slice) *slice = g;
+    }
+    return DFD_OK;
+}
+
 /* Coalesce / broadcast over the same NVLink transport (no repartition): this worker, as producer task `rank`, holds
  * `P` partitions = the row slices [slice_starts[j], slice_starts[j+1]) of in_cols. */
 int dfd_exchange_gather(dfd_exchange* x, int route, const dfd_column* in_cols, int n_cols, const int64_t* slice_starts, uint32_t P,

@@ -470,6 +470,14 @@ void dfd_shuffle_stream_end(dfd_shuffle_stream* s);
  * pairs in the order above; out_cols are set like in dfd_shuffle_device_onepass (same nullable convention). */
 enum { DFD_ROUTE_SHUFFLE = 0, DFD_ROUTE_COALESCE = 1, DFD_ROUTE_BROADCAST = 2 };
 int dfd_coalesce_task_group(int input_task_count, int task_index, int task_count, int* start_task, int* len, int* max_len);
+/* Pure host helper (no GPU): the routing table every worker derives for an exchange — which producer task and which of its
+ * slices feed segment `segment` of consumer task `consumer` (`*producer` = -1: a padding segment of an uneven coalesce
+ * group), and how many segments that consumer has (`*n_segments`; 0 for workers that are not consumer tasks).  Out pointers
+ * may be NULL.  This is the index arithmetic of NetworkShuffleExec::execute (network_shuffle.rs:219-231: off = P x task_index,
+ * partition off + p from every producer), NetworkCoalesceExec::execute (network_coalesce.rs:205-226) and
+ * NetworkBroadcastExec::execute (network_broadcast.rs:230-241). */
+int dfd_route_segment_source(int route, uint32_t partitions, int producer_tasks, int consumer_tasks, int consumer, uint32_t segment,
+                             int* producer, uint32_t* slice, uint32_t* n_segments);
 int dfd_exchange_gather(dfd_exchange* x, int route, const dfd_column* in_cols, int n_cols, const int64_t* slice_starts,
                         uint32_t partitions, int consumer_tasks, dfd_column* out_cols);
 uint32_t dfd_exchange_pending_segments(const dfd_exchange* x);

@@ -153,3 +153,79 @@ def test_coalesce_task_groups_match_the_reference(built):
     import pytest as _pt
     with _pt.raises(ValueError):
         dfd.NetworkCoalesceExec.try_new(3, __import__("uuid").uuid4(), 1, 0, 9)
+
+
+def _route_source(route, P, T, Cn, consumer, segment=None):
+    import ctypes as C
+
+    from datafusion_distributed_b200 import _native as nv
+
+    prod, sl, nseg = C.c_int(-7), C.c_uint32(0), C.c_uint32(0)
+    if segment is None:
+        nv.check(nv.lib().dfd_route_segment_source(route, P, T, Cn, consumer, 0, None, None, C.byref(nseg)))
+        return nseg.value
+    nv.check(nv.lib().dfd_route_segment_source(route, P, T, Cn, consumer, segment, C.byref(prod), C.byref(sl), C.byref(nseg)))
+    return prod.value, sl.value
+
+
+def test_routing_table_is_the_reference_execute_arithmetic(built):
+    """dfd_route_segment_source (the table every worker derives before pushing) against a restatement of the three
+    `execute(partition, ctx)` bodies of the reference: which input task, and which of its partitions, every consumer
+    partition stream reads (network_shuffle.rs:219-231, network_coalesce.rs:186-226, network_broadcast.rs:230-241)."""
+    SHUFFLE, COALESCE, BROADCAST = 0, 1, 2
+    for T in (1, 2, 3, 4, 8):
+        for P in (1, 3, 6):
+            # --- NetworkShuffleExec::execute: off = P * task_index; partition off + p from EVERY input task (select_all)
+            for task_index in range(T):
+                assert _route_source(SHUFFLE, P, T, T, task_index) == P * T
+                off = P * task_index
+                for p in range(P):
+                    streams = {(input_task, off + p) for input_task in range(T)}
+                    got = {_route_source(SHUFFLE, P, T, T, task_index, p * T + r) for r in range(T)}
+                    assert got == streams
+                    for r in range(T):  # producer order inside a partition == input task order
+                        assert _route_source(SHUFFLE, P, T, T, task_index, p * T + r) == (r, off + p)
+            # --- NetworkBroadcastExec::execute: the same loop over input tasks; the producer's BroadcastExec serves this
+            # consumer's replica of its partition p under index off + p, i.e. producer slice p
+            for Cn in range(1, T + 1):
+                for task_index in range(T):
+                    n = _route_source(BROADCAST, P, T, Cn, task_index)
+                    assert n == (P * T if task_index < Cn else 0)
+                    for s in range(n):
+                        assert _route_source(BROADCAST, P, T, Cn, task_index, s) == (s % T, s // T)
+            # --- NetworkCoalesceExec::execute
+            for Cn in range(1, T + 1):
+                base, extra = divmod(T, Cn)
+                max_len = base + (1 if extra else 0)
+                seen = []
+                for task_index in range(Cn):
+                    length = base + (1 if task_index < extra else 0)
+                    start = task_index * base + min(task_index, extra)
+                    partition_count = max_len * P  # what the node advertises: partitions_per_task x the largest group
+                    assert _route_source(COALESCE, P, T, Cn, task_index) == partition_count
+                    for partition in range(partition_count):
+                        input_task_offset, target_partition = divmod(partition, P)
+                        want = (-1, target_partition) if input_task_offset >= length else (start + input_task_offset, target_partition)
+                        assert _route_source(COALESCE, P, T, Cn, task_index, partition) == want
+                        if want[0] >= 0:
+                            seen.append(want)
+                assert sorted(seen) == [(r, g) for r in range(T) for g in range(P)]  # every producer partition read exactly once
+                for idle in range(Cn, T):
+                    assert _route_source(COALESCE, P, T, Cn, idle) == 0
+
+
+def test_routing_table_rejects_bad_arguments(built):
+    import ctypes as C
+
+    import datafusion_distributed_b200 as dfd
+    from datafusion_distributed_b200 import _native as nv
+
+    f = nv.lib().dfd_route_segment_source
+    n = C.c_uint32(0)
+    assert f(0, 4, 2, 1, 0, 0, None, None, C.byref(n)) != 0   # shuffle: consumers == workers
+    assert f(3, 4, 2, 2, 0, 0, None, None, C.byref(n)) != 0   # unknown route
+    assert f(1, 0, 2, 2, 0, 0, None, None, C.byref(n)) != 0   # no partitions
+    assert f(1, 4, 2, 3, 0, 0, None, None, C.byref(n)) != 0   # more consumers than workers
+    p = C.c_int(0)
+    assert f(2, 4, 2, 2, 0, 8, C.byref(p), None, None) != 0   # segment out of range
+    assert "out of range" in dfd.last_error() if hasattr(dfd, "last_error") else True
