@@ -636,6 +636,15 @@ int flush_current(dfd_repartition_exec* x) {
     const size_t C = x->fields.size();
     x->cur_open = false;
     if (s.rows == 0) return DFD_OK;
+    // the pinned landing buffer of this chunk FIRST, before the context lock is taken: with max_pinned_chunks this is where
+    // the producer waits for a consumer to release a chunk (back-pressure), and other operators of the same worker context
+    // must keep running meanwhile
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        s.out = x->pool->acquire();
+        x->ns_wait_pool += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    }
+    if (!s.out) return fail(x, DFD_ERR_OOM, "pinned host allocation failed");
     std::lock_guard<std::mutex> lk(c->mu);
     XCUDA(x, cudaSetDevice(c->device), "cudaSetDevice");
     for (int fi : x->dev_fields) {  // the buffers concatenated on the host while staging: bitmaps and re-based offsets
@@ -709,13 +718,7 @@ int flush_current(dfd_repartition_exec* x) {
           "D2H part_starts");
     XCUDA(x, cudaEventRecord(s.e_k, c->stream), "record k");
     s.k_recorded = true;
-    // D2H of the destination-sorted chunk into a pooled pinned buffer
-    {
-        const auto t0 = std::chrono::steady_clock::now();
-        s.out = x->pool->acquire();
-        x->ns_wait_pool += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
-    }
-    if (!s.out) return fail(x, DFD_ERR_OOM, "pinned host allocation failed");
+    // D2H of the destination-sorted chunk into the pooled pinned buffer taken above
     XCUDA(x, cudaStreamWaitEvent(x->s_d2h, s.e_k, 0), "wait k");
     for (size_t k = 0; k < D; ++k) {
         const size_t i = (size_t)x->dev_fields[k];
