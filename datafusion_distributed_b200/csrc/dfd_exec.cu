@@ -470,8 +470,10 @@ struct dfd_repartition_exec {
     bool finished = false;
     int error_code = 0;
     std::string error;
-    uint64_t rows_in = 0, rows_out = 0, bytes_h2d = 0, bytes_d2h = 0;
-    uint64_t ns_push = 0, ns_wait_d2h = 0, ns_wait_pool = 0;  // producer-thread time: inside push/finish; of which blocked on a D2H / on the pinned pool
+    // counters: written by the producer thread, read by dfd_repartition_exec_stats from any thread (relaxed atomics)
+    std::atomic<uint64_t> rows_in{0}, bytes_h2d{0}, bytes_d2h{0};
+    uint64_t rows_out = 0;  // (under `mu`)
+    std::atomic<uint64_t> ns_push{0}, ns_wait_d2h{0}, ns_wait_pool{0};  // producer-thread time: inside push/finish; of which blocked on a D2H / on the pinned pool
     // host scratch of the batch being staged (pageable: an H2D from it has been staged by the time cudaMemcpyAsync returns)
     std::vector<std::vector<char>> tmp_off, tmp_bytes;
     std::vector<VarPrep> prep;
@@ -480,9 +482,9 @@ struct dfd_repartition_exec {
 namespace {
 
 struct ScopedNs {  // adds the scope's wall time to a counter
-    uint64_t& acc;
+    std::atomic<uint64_t>& acc;
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-    explicit ScopedNs(uint64_t& a) : acc(a) {}
+    explicit ScopedNs(std::atomic<uint64_t>& a) : acc(a) {}
     ~ScopedNs() { acc += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); }
 };
 
