@@ -30,6 +30,13 @@ def out_path(tag: str = "") -> str:
 OUT = out_path(os.environ.get("DFD_LIB_TAG", ""))
 
 
+def object_path(src: str) -> str:
+    """Where build() caches the object of a source compiled with the default flags (used by the CPU host-logic harness of the
+    test-suite, which links the product's own dfd_exec object against a host stand-in of the CUDA runtime)."""
+    key = hashlib.sha1(" ".join(NVCC_FLAGS).encode()).hexdigest()[:10]
+    return os.path.join(OBJ_DIR, f"{os.path.splitext(src)[0]}.{key}.o")
+
+
 def _newest_source() -> float:
     t = 0.0
     for d in (CSRC, os.path.join(ROOT, "include")):

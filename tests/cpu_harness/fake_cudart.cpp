@@ -1,0 +1,46 @@
+// TEST INFRASTRUCTURE (CPU suite only; never shipped, never loaded by the product package).
+//
+// A host-memory stand-in for the handful of CUDA runtime entry points the host operator (csrc/dfd_exec.cu) calls, so
+// that the operator's HOST logic — chunk coalescing, bitmap / offset staging, list and view conversion, slicing of the
+// destination-sorted chunk into Arrow batches, error fan-out, the pinned pool and its cache — can be exercised by
+// `pytest -m "not gpu"` with the very object file nvcc built for the product.  "Device" memory is host memory, streams
+// and events complete immediately (every copy is synchronous), and the partition kernels are replaced by the CPU
+// oracle in harness_dfd.cu.  Nothing here is a CPU fallback of the product: it is linked only into the test library
+// tests/test_exec_cpu_harness.py builds under a temporary directory.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+
+extern "C" {
+typedef int cudaError_t_;  // cudaError_t is a C enum: int-sized in the ABI
+struct FakeHandle { int dummy; };
+
+static void* fake_alloc(size_t n) {
+    void* p = nullptr;
+    if (posix_memalign(&p, 256, n ? n : 1) != 0) return nullptr;
+    memset(p, 0xCD, n);  // poison: the operator must not rely on zeroed allocations
+    return p;
+}
+
+cudaError_t_ cudaSetDevice(int) { return 0; }
+cudaError_t_ cudaMalloc(void** p, size_t n) { *p = fake_alloc(n); return *p ? 0 : 2; }
+cudaError_t_ cudaFree(void* p) { free(p); return 0; }
+cudaError_t_ cudaHostAlloc(void** p, size_t n, unsigned) { *p = fake_alloc(n); return *p ? 0 : 2; }
+cudaError_t_ cudaFreeHost(void* p) { free(p); return 0; }
+cudaError_t_ cudaMemcpyAsync(void* dst, const void* src, size_t n, int, void*) { if (n) memmove(dst, src, n); return 0; }
+cudaError_t_ cudaMemsetAsync(void* dst, int v, size_t n, void*) { if (n) memset(dst, v, n); return 0; }
+cudaError_t_ cudaStreamCreateWithFlags(void** s, unsigned) { *s = new FakeHandle(); return 0; }
+cudaError_t_ cudaStreamDestroy(void* s) { delete (FakeHandle*)s; return 0; }
+cudaError_t_ cudaStreamSynchronize(void*) { return 0; }
+cudaError_t_ cudaStreamWaitEvent(void*, void*, unsigned) { return 0; }
+cudaError_t_ cudaEventCreateWithFlags(void** e, unsigned) { *e = new FakeHandle(); return 0; }
+cudaError_t_ cudaEventDestroy(void* e) { delete (FakeHandle*)e; return 0; }
+cudaError_t_ cudaEventRecord(void*, void*) { return 0; }
+cudaError_t_ cudaEventQuery(void*) { return 0; }
+cudaError_t_ cudaEventSynchronize(void*) { return 0; }
+const char* cudaGetErrorString(cudaError_t_) { return "fake CUDA runtime (CPU test harness)"; }
+// fat-binary registration emitted by nvcc for every .cu object: nothing to register
+void** __cudaRegisterFatBinary(void*) { static void* h = nullptr; return &h; }
+void __cudaRegisterFatBinaryEnd(void**) {}
+void __cudaUnregisterFatBinary(void**) {}
+}
