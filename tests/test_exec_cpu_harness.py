@@ -37,7 +37,10 @@ def _build_harness(tmp):
     dfd_obj, rt_obj, out = os.path.join(tmp, "harness_dfd.o"), os.path.join(tmp, "fake_cudart.o"), os.path.join(tmp, "libdfd_exec_harness.so")
     subprocess.check_call([NVCC] + NVCC_FLAGS + inc + ["-c", os.path.join(HARNESS, "harness_dfd.cu"), "-o", dfd_obj])
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-Wall", "-c", os.path.join(HARNESS, "fake_cudart.cpp"), "-o", rt_obj])
-    subprocess.check_call(["g++", "-shared", "-o", out, exec_obj, dfd_obj, rt_obj, oracle_so, f"-Wl,-rpath,{os.path.dirname(oracle_so)}", "-lpthread"])
+    # -Bsymbolic: the library's calls to cuda* / dfd_* bind to ITS OWN definitions even when the process has already loaded the
+    # real CUDA runtime or libdfd_b200.so (other tests of the same session do)
+    subprocess.check_call(["g++", "-shared", "-Wl,-Bsymbolic", "-o", out, exec_obj, dfd_obj, rt_obj, oracle_so,
+                           f"-Wl,-rpath,{os.path.dirname(oracle_so)}", "-lpthread"])
     return out
 
 
