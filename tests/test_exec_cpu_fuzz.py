@@ -146,3 +146,30 @@ def test_random_schema_and_batching_matches_the_oracle(harness, seed):  # noqa: 
             g = g.combine_chunks()
             assert g.cast(w.type).equals(w), (kinds, keys, N, chunk_rows, p, name)
     ex.close()
+
+
+def test_long_strings_grow_the_chunk_buffers(harness):  # noqa: F811
+    """Strings of tens of kilobytes (a plain column, a view column and the elements of a list): the chunk's device byte
+    buffers and the pinned landing buffers grow while batches are appended, without losing what is already staged."""
+    ns, ctx = harness
+    rnd = random.Random(3)
+    n, N = 1500, 5
+    big = pa.array([None if rnd.random() < 0.05 else ("x" * rnd.choice([0, 10, 3000, 20000]) + str(i)) for i in range(n)], type=pa.string())
+    key = pa.array(np.arange(n, dtype=np.int64))
+    lst = pa.array([[("y" * rnd.choice([1, 500, 9000])) + str(i) for _ in range(rnd.randint(0, 3))] for i in range(n)], type=pa.list_(pa.string()))
+    fed = pa.table([key, big, lst, big.cast(pa.string_view())], names=["k", "s", "l", "v"])
+    plain = pa.table([key, big, lst, big], names=["k", "s", "l", "v"])
+    dest = orc.partition_ids([key], n, N)
+    order, starts = expected_partitions(dest, N)
+    for chunk_rows in (64, 1000):
+        ex = ns.RepartitionExec(ctx, fed.schema, ns.Partitioning.Hash([0], N), chunk_rows=chunk_rows)
+        for rb in fed.to_batches(max_chunksize=333):
+            ex.push_batch(rb)
+        ex.finish()
+        outs = [ex.execute(p).read_all() for p in range(N)]
+        for p in range(N):
+            want = plain.take(pa.array(order[starts[p]:starts[p + 1]]))
+            for name in fed.column_names:
+                g, w = outs[p].column(name).combine_chunks(), want.column(name).combine_chunks()
+                assert g.cast(w.type).equals(w), (chunk_rows, p, name)
+        ex.close()
