@@ -7,6 +7,7 @@
 // and events complete immediately (every copy is synchronous), and the partition kernels are replaced by the CPU
 // oracle in harness_dfd.cu.  Nothing here is a CPU fallback of the product: it is linked only into the test library
 // tests/test_exec_cpu_harness.py builds under a temporary directory.
+#include <atomic>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -29,19 +30,50 @@ extern "C" {
 typedef int cudaError_t_;  // cudaError_t is a C enum: int-sized in the ABI
 struct FakeHandle { int dummy; };
 
+// ---- bookkeeping for the tests: live allocations (leak check) and one-shot fault injection -----------------------------
+static std::atomic<long> g_live{0};          // device + pinned allocations not yet freed
+static std::atomic<long> g_fail_in[3];       // > 0: fail the n-th call from now of {cudaMalloc, cudaHostAlloc, cudaMemcpyAsync}
+static bool inject(int what) {
+    long v = g_fail_in[what].load();
+    while (v > 0)
+        if (g_fail_in[what].compare_exchange_weak(v, v - 1)) return v == 1;
+    return false;
+}
+long harness_live_allocations(void) { return g_live.load(); }
+void harness_fail_nth(int what, long n) { g_fail_in[what].store(n); }
+
 static void* fake_alloc(size_t n) {
     void* p = nullptr;
     if (posix_memalign(&p, 256, n ? n : 1) != 0) return nullptr;
     memset(p, 0xCD, n);  // poison: the operator must not rely on zeroed allocations
+    g_live.fetch_add(1);
     return p;
+}
+static void fake_free(void* p) {
+    if (p) g_live.fetch_sub(1);
+    free(p);
 }
 
 cudaError_t_ cudaSetDevice(int) { return 0; }
-cudaError_t_ cudaMalloc(void** p, size_t n) { *p = fake_alloc(n); return *p ? 0 : 2; }
-cudaError_t_ cudaFree(void* p) { free(p); return 0; }
-cudaError_t_ cudaHostAlloc(void** p, size_t n, unsigned) { *p = fake_alloc(n); return *p ? 0 : 2; }
-cudaError_t_ cudaFreeHost(void* p) { free(p); return 0; }
-cudaError_t_ cudaMemcpyAsync(void* dst, const void* src, size_t n, int, void*) { if (n) memmove(dst, src, n); return 0; }
+cudaError_t_ cudaMalloc(void** p, size_t n) {
+    *p = nullptr;
+    if (inject(0)) return 2;  // cudaErrorMemoryAllocation
+    *p = fake_alloc(n);
+    return *p ? 0 : 2;
+}
+cudaError_t_ cudaFree(void* p) { fake_free(p); return 0; }
+cudaError_t_ cudaHostAlloc(void** p, size_t n, unsigned) {
+    *p = nullptr;
+    if (inject(1)) return 2;
+    *p = fake_alloc(n);
+    return *p ? 0 : 2;
+}
+cudaError_t_ cudaFreeHost(void* p) { fake_free(p); return 0; }
+cudaError_t_ cudaMemcpyAsync(void* dst, const void* src, size_t n, int, void*) {
+    if (inject(2)) return 719;  // cudaErrorLaunchFailure: a sticky device error
+    if (n) memmove(dst, src, n);
+    return 0;
+}
 cudaError_t_ cudaMemsetAsync(void* dst, int v, size_t n, void*) { if (n) memset(dst, v, n); return 0; }
 cudaError_t_ cudaStreamCreateWithFlags(void** s, unsigned) { *s = new FakeHandle(); return 0; }
 cudaError_t_ cudaStreamDestroy(void* s) { delete (FakeHandle*)s; return 0; }

@@ -37,10 +37,11 @@ int dfd::cuda_error(cudaError_t e, const char* what) { return set_error(DFD_ERR_
 
 int dfd::Scratch::ensure(size_t need, int) {
     if (need <= bytes) return DFD_OK;
-    free(ptr);
+    cudaFree(ptr);  // (the stand-in runtime: the operator releases these with cudaFree too)
     ptr = nullptr;
     bytes = 0;
-    if (posix_memalign(&ptr, 256, need + need / 4 + 256) != 0) return set_error(DFD_ERR_OOM, "harness: out of memory");
+    cudaError_t e = cudaMalloc(&ptr, need + need / 4 + 256);
+    if (e != cudaSuccess) return cuda_error(e, "cudaMalloc(scratch)");
     bytes = need + need / 4 + 256;
     return DFD_OK;
 }

@@ -192,3 +192,83 @@ def test_the_product_package_never_loads_the_harness():
         for p in paths:
             text = open(p, errors="replace").read()
             assert "cpu_harness" not in text and "fake_cudart" not in text and "libdfd_exec_harness" not in text, p
+
+
+def _fixture_like_table(n, seed=5):
+    import random
+
+    import numpy as np
+
+    rnd = random.Random(seed)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    words = ["", "a", "hello", "x" * 13, "a-much-longer-string-than-twelve-bytes"]
+    label = pa.array([None if rnd.random() < 0.1 else rnd.choice(words) + str(rnd.getrandbits(12)) for _ in range(n)], type=pa.string())
+    cat = pa.DictionaryArray.from_arrays(pa.array([rnd.choice([None, 0, 1, 2]) for _ in range(n)], type=pa.int32()), pa.array(["red", None, "blue"]))
+    tags = pa.array([None if rnd.random() < 0.1 else [rnd.choice([None, "t1", "tag-two"]) for _ in range(rnd.randint(0, 3))] for _ in range(n)],
+                    type=pa.list_(pa.string()))
+    return pa.table([pa.array(rng.integers(0, 2**40, n, dtype=np.int64)), pa.array([rnd.choice([None, True, False]) for _ in range(n)]), label,
+                     label.cast(pa.string_view()), cat, tags], names=["id", "flag", "label", "view", "category", "tags"])
+
+
+def _run_once(ns, ctx, table, keys, **opts):
+    ex = ns.RepartitionExec(ctx, table.schema, ns.Partitioning.Hash(keys, 4), **opts)
+    try:
+        for rb in table.to_batches(max_chunksize=500):
+            ex.push_batch(rb)
+        ex.finish()
+        rows = sum(ex.execute(p).read_all().num_rows for p in range(4))
+    finally:
+        ex.close()
+    return rows
+
+
+def test_no_allocation_outlives_the_operator_and_its_context(harness):
+    """Leak check on the stand-in runtime: after operators with every column kind (dictionary KEY included) are closed and
+    their worker context destroyed (which empties the pinned-chunk cache), every device / pinned allocation has been freed."""
+    import gc
+
+    ns, _ = harness
+    lib = harness[1].lib
+    lib.harness_live_allocations.restype = C.c_long
+    base = lib.harness_live_allocations()
+    ctx = _Ctx(lib)
+    table = _fixture_like_table(3000)
+    assert _run_once(ns, ctx, table, [0], chunk_rows=1024) == 3000
+    assert _run_once(ns, ctx, table, [4, 2], chunk_rows=256, pinned_pool_chunks=2) == 3000   # dictionary + string keys
+    assert _run_once(ns, ctx, table, [0], chunk_rows=1024) == 3000                          # takes its chunks from the cache
+    gc.collect()
+    assert lib.harness_live_allocations() > base  # (the context still caches the pinned chunks of the finished operators)
+    ctx.close()
+    gc.collect()
+    assert lib.harness_live_allocations() == base
+
+
+@pytest.mark.parametrize("what,name", [(0, "cudaMalloc"), (1, "cudaHostAlloc"), (2, "cudaMemcpyAsync")])
+def test_injected_cuda_failures_surface_as_errors_and_leak_nothing(harness, what, name):
+    """Fail the n-th cudaMalloc / cudaHostAlloc / cudaMemcpyAsync for n = 1, 2, 3, ... of an operator's life (create, stage,
+    flush, D2H): the failure must come back as an error from create / push / finish or from a partition stream — never a
+    crash, never a hang — and once everything is closed no allocation is left behind."""
+    import gc
+
+    ns, _ = harness
+    lib = harness[1].lib
+    lib.harness_live_allocations.restype = C.c_long
+    lib.harness_fail_nth.argtypes = [C.c_int, C.c_long]
+    table = _fixture_like_table(1500)
+    failures = 0
+    for n in list(range(1, 40)) + [60, 90, 150, 400]:
+        base = lib.harness_live_allocations()
+        ctx = _Ctx(lib)
+        lib.harness_fail_nth(what, n)
+        try:
+            rows = _run_once(ns, ctx, table, [4, 0], chunk_rows=512)
+            assert rows == 1500  # the countdown was longer than this operator's life (or the failing call was not on its path)
+        except (HarnessError, pa.ArrowException, OSError) as e:
+            failures += 1
+            assert "fake CUDA" in str(e) or "failed" in str(e) or "alloc" in str(e).lower() or "cuda" in str(e).lower(), str(e)
+        finally:
+            lib.harness_fail_nth(what, 0)
+            ctx.close()
+            gc.collect()
+        assert lib.harness_live_allocations() == base, (name, n)
+    assert failures >= 5, (name, failures)
