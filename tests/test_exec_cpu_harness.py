@@ -23,6 +23,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-std=c++17",
 
 
 def _build_harness(tmp):
+    if os.environ.get("DFD_TEST_HARNESS_SO"):  # a prebuilt variant of the harness, e.g. compiled with -fsanitize=address
+        return os.environ["DFD_TEST_HARNESS_SO"]  # (recipe: tests/cpu_harness/README.md); still test-only
     from datafusion_distributed_b200 import build as b
     from oracle import oracle as orc
 
