@@ -109,9 +109,21 @@ inline int64_t split_list_rows(const int32_t* loff, const int32_t* coff, const u
     for (int64_t k = 0; k < ne; ++k) lengths[k] = coff[e0 + k + 1] - coff[e0 + k];
     if (valid_off) {
         for (int64_t r = 0; r <= n; ++r) valid_off[r] = (int32_t)((int64_t)loff[lo + r] - e0);
-        for (int64_t k = 0; k < ne; ++k) {
-            const int64_t bit = cvalid_offset + e0 + k;
-            valid_bytes[k] = cvalid ? (char)((cvalid[bit >> 3] >> (bit & 7)) & 1) : (char)1;
+        if (!cvalid) {
+            memset(valid_bytes, 1, (size_t)ne);
+        } else {
+            // bits [first, first + ne) of the child's validity -> one byte each: bit by bit up to a byte boundary of the
+            // bitmap, then eight at a time (byte b -> 8 bytes: replicate, isolate bit i in byte i, normalise to 0 / 1)
+            const int64_t first = cvalid_offset + e0;
+            int64_t k = 0;
+            for (; k < ne && ((first + k) & 7); ++k) valid_bytes[k] = (char)((cvalid[(first + k) >> 3] >> ((first + k) & 7)) & 1);
+            const uint8_t* src = cvalid + ((first + k) >> 3);
+            for (; k + 8 <= ne; k += 8, ++src) {
+                const uint64_t spread = ((uint64_t)*src * 0x0101010101010101ULL) & 0x8040201008040201ULL;
+                const uint64_t ones = ((spread + 0x7f7f7f7f7f7f7f7fULL) >> 7) & 0x0101010101010101ULL;  // byte i = 1 iff byte i of spread != 0
+                memcpy(valid_bytes + k, &ones, 8);  // (little endian: byte 0 = bit 0)
+            }
+            for (; k < ne; ++k) valid_bytes[k] = (char)((cvalid[(first + k) >> 3] >> ((first + k) & 7)) & 1);
         }
     }
     return ne;

@@ -8,6 +8,7 @@
 // oracle in harness_dfd.cu.  Nothing here is a CPU fallback of the product: it is linked only into the test library
 // tests/test_exec_cpu_harness.py builds under a temporary directory.
 #include <atomic>
+#include <chrono>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -39,10 +40,18 @@ static bool inject(int what) {
         if (g_fail_in[what].compare_exchange_weak(v, v - 1)) return v == 1;
     return false;
 }
+static std::atomic<unsigned long long> g_copy_ns{0}, g_copy_bytes{0}, g_copy_calls{0};  // what the copies cost on the host (profiling aid)
 long harness_live_allocations(void) { return g_live.load(); }
+unsigned long long harness_copy_ns(void) { return g_copy_ns.load(); }
+unsigned long long harness_copy_bytes(void) { return g_copy_bytes.load(); }
+unsigned long long harness_copy_calls(void) { return g_copy_calls.load(); }
+static std::atomic<unsigned long long> g_alloc_ns{0};
+unsigned long long harness_alloc_ns(void) { return g_alloc_ns.load(); }
 void harness_fail_nth(int what, long n) { g_fail_in[what].store(n); }
 
 static void* fake_alloc(size_t n) {
+    struct T { std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+               ~T() { g_alloc_ns += (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); } } timed;
     void* p = nullptr;
     if (posix_memalign(&p, 256, n ? n : 1) != 0) return nullptr;
     memset(p, 0xCD, n);  // poison: the operator must not rely on zeroed allocations
@@ -71,7 +80,11 @@ cudaError_t_ cudaHostAlloc(void** p, size_t n, unsigned) {
 cudaError_t_ cudaFreeHost(void* p) { fake_free(p); return 0; }
 cudaError_t_ cudaMemcpyAsync(void* dst, const void* src, size_t n, int, void*) {
     if (inject(2)) return 719;  // cudaErrorLaunchFailure: a sticky device error
+    const auto t0 = std::chrono::steady_clock::now();
     if (n) memmove(dst, src, n);
+    g_copy_ns += (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    g_copy_bytes += n;
+    g_copy_calls += 1;
     return 0;
 }
 cudaError_t_ cudaMemsetAsync(void* dst, int v, size_t n, void*) { if (n) memset(dst, v, n); return 0; }
