@@ -906,8 +906,19 @@ static int push_slices_locked(dfd_exchange* x, const std::vector<PushCol>& pc, c
             }
             if (q.nullable) { Lo.reg_valid[i] = off; off += al((size_t)run / 8 + 16); }
         }
-        if (off > x->window_bytes)
+        if (off > x->window_bytes) {
+            // Every worker takes this branch (same matrices).  Nobody may start the next exchange — and overwrite its metadata
+            // slots in the peers' headers — before every worker has read THIS epoch's metadata: close the epoch with the
+            // done barrier, exactly as a successful exchange does (the back-pressured stream retries at once with a finer
+            // round, dfd_shuffle_stream_next).
+            k_xchg_done_barrier<<<1, 32, 0, s>>>(hdr, x->d_peer_hdr, x->rank, T, epoch, x->d_flags + 1);
+            CUDA_TRY(cudaGetLastError(), "k_xchg_done_barrier");
+            c->metrics.kernel_launches += 2;
+            CUDA_TRY(cudaMemcpyAsync(x->h_seg_flags + MAX_RANKS, x->d_flags + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H timeout flag");
+            CUDA_TRY(cudaStreamSynchronize(s), "push exchange (capacity)");
+            if (x->h_seg_flags[MAX_RANKS]) return set_error(DFD_ERR_INTERNAL, "a peer worker never acknowledged the over-full round (did it fail?)");
             return set_error(DFD_ERR_CAPACITY, "consumer %d needs %zu B of receive window for this exchange, windows hold %zu B", o, off, x->window_bytes);
+        }
     }
     // ---- my runs as producer: walk every consumer's segments and emit the ones I feed
     std::vector<PushRun> runs;

@@ -98,6 +98,72 @@ cudaError_t_ cudaEventRecord(void*, void*) { return 0; }
 cudaError_t_ cudaEventQuery(void*) { return 0; }
 cudaError_t_ cudaEventSynchronize(void*) { return 0; }
 const char* cudaGetErrorString(cudaError_t_) { return "fake CUDA runtime (CPU test harness)"; }
+// ---- what the exchange (csrc/dfd_exchange.cu) needs on top: IPC handles, synchronous copies, kernel launches ------------
+struct FakeIpcHandle { char reserved[64]; };  // cudaIpcMemHandle_t: the "handle" is the pointer (all workers are threads of one process)
+cudaError_t_ cudaIpcGetMemHandle(FakeIpcHandle* h, void* p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return 0; }
+cudaError_t_ cudaIpcOpenMemHandle(void** p, FakeIpcHandle h, unsigned) { memcpy(p, h.reserved, sizeof *p); return 0; }
+cudaError_t_ cudaIpcCloseMemHandle(void*) { return 0; }
+cudaError_t_ cudaMemcpy(void* dst, const void* src, size_t n, int) { if (n) memmove(dst, src, n); return 0; }
+cudaError_t_ cudaMemset(void* dst, int v, size_t n) { if (n) memset(dst, v, n); return 0; }
+cudaError_t_ cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, int, void*) {
+    for (size_t r = 0; r < height; ++r) memmove((char*)dst + r * dpitch, (const char*)src + r * spitch, width);
+    return 0;
+}
+cudaError_t_ cudaEventCreate(void** e) { *e = new FakeHandle(); return 0; }
+cudaError_t_ cudaEventElapsedTime(float* ms, void*, void*) { *ms = 0.f; return 0; }
+
+// Kernel launches: nvcc's host stubs call __cudaPushCallConfiguration / __cudaPopCallConfiguration / cudaLaunchKernel with the
+// host-side function pointer it registered under the kernel's (mangled) device name.  The harness registers CPU
+// emulations by name fragment (harness_register_kernel); a launch of a kernel without one fails with
+// cudaErrorNotSupported, which the library sees through cudaGetLastError like any launch failure.
+struct FakeDim3 { unsigned x, y, z; };
+typedef int (*HarnessKernel)(FakeDim3 grid, FakeDim3 block, void** args);
+struct KernelEntry { const void* host_fun; char name[256]; HarnessKernel cpu; };
+static KernelEntry g_kernels[256];
+static std::atomic<int> g_n_kernels{0};
+struct CpuKernel { char fragment[64]; HarnessKernel fn; };
+static CpuKernel g_cpu_kernels[32];
+static std::atomic<int> g_n_cpu_kernels{0};
+static thread_local cudaError_t_ t_last_error = 0;
+static thread_local struct { FakeDim3 grid, block; size_t smem; void* stream; } t_config;
+
+void harness_register_kernel(const char* name_fragment, HarnessKernel fn) {
+    const int i = g_n_cpu_kernels.fetch_add(1);
+    strncpy(g_cpu_kernels[i].fragment, name_fragment, sizeof g_cpu_kernels[i].fragment - 1);
+    g_cpu_kernels[i].fn = fn;
+    for (int k = 0; k < g_n_kernels.load(); ++k)  // (fat binaries may have registered their kernels before this constructor ran)
+        if (!g_kernels[k].cpu && strstr(g_kernels[k].name, name_fragment)) g_kernels[k].cpu = fn;
+}
+void __cudaRegisterFunction(void**, const char* host_fun, char*, const char* device_name, int, void*, void*, void*, void*, int*) {
+    const int i = g_n_kernels.fetch_add(1);
+    if (i >= 256) return;
+    g_kernels[i].host_fun = host_fun;
+    strncpy(g_kernels[i].name, device_name, sizeof g_kernels[i].name - 1);
+    g_kernels[i].cpu = nullptr;
+    for (int k = 0; k < g_n_cpu_kernels.load(); ++k)
+        if (strstr(device_name, g_cpu_kernels[k].fragment)) g_kernels[i].cpu = g_cpu_kernels[k].fn;
+}
+unsigned __cudaPushCallConfiguration(FakeDim3 grid, FakeDim3 block, size_t smem, void* stream) {
+    t_config.grid = grid; t_config.block = block; t_config.smem = smem; t_config.stream = stream;
+    return 0;
+}
+cudaError_t_ __cudaPopCallConfiguration(FakeDim3* grid, FakeDim3* block, size_t* smem, void** stream) {
+    *grid = t_config.grid; *block = t_config.block; *smem = t_config.smem; *stream = t_config.stream;
+    return 0;
+}
+cudaError_t_ cudaLaunchKernel(const void* func, FakeDim3 grid, FakeDim3 block, void** args, size_t, void*) {
+    for (int k = 0; k < g_n_kernels.load(); ++k)
+        if (g_kernels[k].host_fun == func) {
+            if (!g_kernels[k].cpu) break;
+            const int rc = g_kernels[k].cpu(grid, block, args);
+            if (rc) t_last_error = rc;
+            return rc;
+        }
+    t_last_error = 801;  // cudaErrorNotSupported: no CPU emulation of this kernel in the harness
+    return 801;
+}
+cudaError_t_ cudaGetLastError(void) { const cudaError_t_ e = t_last_error; t_last_error = 0; return e; }
+
 // fat-binary registration emitted by nvcc for every .cu object: nothing to register
 void** __cudaRegisterFatBinary(void*) { static void* h = nullptr; return &h; }
 void __cudaRegisterFatBinaryEnd(void**) {}

@@ -17,6 +17,8 @@
 #include "dfd_internal.h"
 #include "df_oracle.h"
 
+int harness_partition(dfd_partitioner* p, const dfd_column* in, int n_cols, int64_t n, const dfd_column* out);
+
 namespace {
 std::atomic<uint64_t> g_ns_kernels{0};  // time spent in the stand-ins of the kernels (not host logic of the operator)
 struct KernelTime {
@@ -99,6 +101,12 @@ int dfd::hash_columns_locked(Ctx*, const dfd_column* cols, int n_cols, int64_t n
 }
 
 int dfd::partition_device_locked(Partitioner* p, const dfd_column* in, int n_cols, int64_t n, const dfd_column* out, cudaStream_t, bool) {
+    return harness_partition(p, in, n_cols, n, out);
+}
+
+// the stand-in of K1/K1b/K2/K4 (also used by the exchange harness, harness_exchange.cu)
+int harness_partition(dfd_partitioner* p, const dfd_column* in, int n_cols, int64_t n, const dfd_column* out) {
+    using dfd::set_error;
     KernelTime kernel_time;
     const uint32_t N = p->N;
     const orc_random_state st = orc_repartition_random_state();

@@ -1,0 +1,164 @@
+// TEST INFRASTRUCTURE (CPU suite only): what csrc/dfd_exchange.cu needs besides the stand-in runtime to run its push
+// transport (every column kind; shuffle / coalesce / broadcast routes; back-pressure rounds) with THREADS as workers:
+//   * the PartitionJob stages and the small conversion launches, restated with the CPU oracle;
+//   * CPU emulations of the exchange kernels that path launches (k_slice_rows, k_xchg_allgather_meta, k_push_runs,
+//     k_xchg_done_barrier), registered by name with the stand-in runtime's cudaLaunchKernel.
+// The single-pass peer scatter and the two-pass fused / NCCL-mode transports are NOT emulated (their launches fail with
+// cudaErrorNotSupported): they are covered on real GPUs (tests/mgpu_shuffle_check.py, bench.py --gpus N parity).
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "dfd_b200.h"
+#include "dfd_internal.h"
+
+int harness_partition(dfd_partitioner* p, const dfd_column* in, int n_cols, int64_t n, const dfd_column* out);
+
+namespace {
+inline bool bit(const uint8_t* b, int64_t i) { return (b[i >> 3] >> (i & 7)) & 1; }
+}  // namespace
+
+// ---- PartitionJob: the exchange only uses the local (non-peer) form in the push transport -------------------------------
+int dfd::PartitionJob::prepare(Partitioner* part, const dfd_column* in_cols, int n_cols, int64_t rows, const dfd_column* out_cols, bool peer_mode, cudaStream_t st) {
+    p = part;
+    stream = st;
+    peer = peer_mode;
+    n_rows = rows;
+    var_cols.clear();
+    for (int i = 0; i < n_cols; ++i) var_cols.push_back(VarCol{in_cols[i], out_cols[i]});  // (all columns: the stand-in needs nothing else)
+    if (peer_mode) return set_error(DFD_ERR_UNSUPPORTED, "harness: the peer-store scatter is not emulated on the CPU");
+    return DFD_OK;
+}
+int dfd::PartitionJob::run_hist_scan() { return DFD_OK; }
+int dfd::PartitionJob::run_scatter(const int64_t*, void* const* peer_base, int, uint32_t, const int32_t*) {
+    if (peer_base) return set_error(DFD_ERR_UNSUPPORTED, "harness: the peer-store scatter is not emulated on the CPU");
+    std::vector<dfd_column> in, out;
+    for (const VarCol& v : var_cols) { in.push_back(v.in); out.push_back(v.out); }
+    return harness_partition(p, in.data(), (int)in.size(), n_rows, out.data());  // writes p->d_part_starts like K1b
+}
+int dfd::PartitionJob::run_onepass(const OnePassLayout&) { return set_error(DFD_ERR_UNSUPPORTED, "harness: the single-pass peer scatter is not emulated on the CPU"); }
+
+int dfd::launch_bits_to_bytes(const uint8_t* bits, int64_t bit_offset, int64_t n, uint8_t* out, cudaStream_t) {
+    for (int64_t i = 0; i < n; ++i) out[i] = bit(bits, i + bit_offset) ? 1 : 0;
+    return DFD_OK;
+}
+int dfd::launch_offsets_to_lengths(const void* off, int ow, int64_t n, void* len, cudaStream_t) {
+    for (int64_t i = 0; i < n; ++i) {
+        if (ow == 8) ((int64_t*)len)[i] = ((const int64_t*)off)[i + 1] - ((const int64_t*)off)[i];
+        else ((int32_t*)len)[i] = ((const int32_t*)off)[i + 1] - ((const int32_t*)off)[i];
+    }
+    return DFD_OK;
+}
+int dfd::launch_var_dest_bytes(const void* off, int ow, const int64_t* part_starts, uint32_t N, int64_t* bytes, int64_t* first, cudaStream_t) {
+    for (uint32_t g = 0; g < N; ++g) {
+        const int64_t a = ow == 8 ? ((const int64_t*)off)[part_starts[g]] : (int64_t)((const int32_t*)off)[part_starts[g]];
+        const int64_t b = ow == 8 ? ((const int64_t*)off)[part_starts[g + 1]] : (int64_t)((const int32_t*)off)[part_starts[g + 1]];
+        bytes[g] = b - a;
+        first[g] = a;
+    }
+    return DFD_OK;
+}
+
+// ---- CPU emulations of the exchange kernels of the push transport ------------------------------------------------------
+namespace {
+struct FakeDim3 { unsigned x, y, z; };
+typedef int (*HarnessKernel)(FakeDim3 grid, FakeDim3 block, void** args);
+extern "C" void harness_register_kernel(const char* name_fragment, HarnessKernel fn);
+
+template <typename T>
+T arg(void** args, int i) { T v; memcpy(&v, args[i], sizeof v); return v; }
+
+inline void store_release(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline unsigned long long load_acquire(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+
+// wait until flags[t] >= epoch for every t < world; 20 s bound like the kernels' clock64 bound
+bool wait_flags(const unsigned long long* flags, int world, unsigned long long epoch) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int t = 0; t < world; ++t)
+        while (load_acquire(&flags[t]) < epoch) {
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) return false;
+            __builtin_ia32_pause();
+        }
+    return true;
+}
+
+// k_slice_rows(const int64_t* starts, uint32_t n, int64_t* rows)
+int cpu_slice_rows(FakeDim3, FakeDim3, void** a) {
+    const int64_t* starts = arg<const int64_t*>(a, 0);
+    const uint32_t n = arg<uint32_t>(a, 1);
+    int64_t* rows = arg<int64_t*>(a, 2);
+    for (uint32_t g = 0; g < n; ++g) rows[g] = starts[g + 1] - starts[g];
+    return 0;
+}
+
+// k_xchg_allgather_meta(local, peer_hdr, rank, world, epoch, my_meta, n_meta, timed_out)
+int cpu_allgather_meta(FakeDim3, FakeDim3, void** a) {
+    dfd::ExchangeHeader* local = arg<dfd::ExchangeHeader*>(a, 0);
+    dfd::ExchangeHeader* const* peer = arg<dfd::ExchangeHeader* const*>(a, 1);
+    const int rank = arg<int>(a, 2), world = arg<int>(a, 3);
+    const unsigned long long epoch = arg<unsigned long long>(a, 4);
+    const int64_t* my_meta = arg<const int64_t*>(a, 5);
+    const uint32_t n_meta = arg<uint32_t>(a, 6);
+    int32_t* timed_out = arg<int32_t*>(a, 7);
+    for (int o = 0; o < world; ++o)
+        for (uint32_t i = 0; i < n_meta; ++i) peer[o]->meta[rank][i] = my_meta[i];
+    for (int o = 0; o < world; ++o) store_release(&peer[o]->meta_flag[rank], epoch);
+    if (!wait_flags(local->meta_flag, world, epoch)) *timed_out = 1;
+    return 0;
+}
+
+// k_xchg_done_barrier(local, peer_hdr, rank, world, epoch, timed_out)
+int cpu_done_barrier(FakeDim3, FakeDim3, void** a) {
+    dfd::ExchangeHeader* local = arg<dfd::ExchangeHeader*>(a, 0);
+    dfd::ExchangeHeader* const* peer = arg<dfd::ExchangeHeader* const*>(a, 1);
+    const int rank = arg<int>(a, 2), world = arg<int>(a, 3);
+    const unsigned long long epoch = arg<unsigned long long>(a, 4);
+    int32_t* timed_out = arg<int32_t*>(a, 5);
+    for (int o = 0; o < world; ++o) store_release(&peer[o]->done[rank], epoch);
+    if (!wait_flags(local->done, world, epoch)) *timed_out = 1;
+    return 0;
+}
+
+// the run descriptor of k_push_runs — a COPY of the private struct in csrc/dfd_exchange.cu (same field order and types;
+// a mismatch shows up at once as garbage segments in every test of tests/test_exchange_cpu_harness.py)
+struct PushRun {
+    const char* src;
+    char* dst;
+    long long n;
+    long long a, b;
+    int kind;
+    int first_block;
+};
+enum { RUN_BYTES = 0, RUN_BITS = 1, RUN_OFF32 = 2, RUN_OFF64 = 3, RUN_ONES = 4 };
+
+// k_push_runs(const PushRun* runs, int n_runs)
+int cpu_push_runs(FakeDim3, FakeDim3, void** a) {
+    const PushRun* runs = arg<const PushRun*>(a, 0);
+    const int n_runs = arg<int>(a, 1);
+    for (int i = 0; i < n_runs; ++i) {
+        const PushRun& r = runs[i];
+        switch (r.kind) {
+            case RUN_BYTES: if (r.n) memmove(r.dst, r.src, (size_t)r.n); break;
+            case RUN_BITS: {
+                const size_t words = (size_t)((r.n + 31) / 32);
+                memset(r.dst, 0, words * 4);
+                for (long long k = 0; k < r.n; ++k)
+                    if (bit((const uint8_t*)r.src, r.a + k)) r.dst[k >> 3] = (char)(r.dst[k >> 3] | (1 << (k & 7)));
+                break;
+            }
+            case RUN_ONES: memset(r.dst, 0xff, (size_t)((r.n + 31) / 32) * 4); break;
+            case RUN_OFF32: for (long long k = 0; k < r.n; ++k) ((int*)r.dst)[k] = (int)((long long)((const int*)r.src)[k] - r.a + r.b); break;
+            default: for (long long k = 0; k < r.n; ++k) ((long long*)r.dst)[k] = ((const long long*)r.src)[k] - r.a + r.b; break;
+        }
+    }
+    return 0;
+}
+
+__attribute__((constructor)) void register_exchange_kernels() {
+    harness_register_kernel("k_slice_rows", cpu_slice_rows);
+    harness_register_kernel("k_xchg_allgather_meta", cpu_allgather_meta);
+    harness_register_kernel("k_xchg_done_barrier", cpu_done_barrier);
+    harness_register_kernel("k_push_runs", cpu_push_runs);
+}
+}  // namespace

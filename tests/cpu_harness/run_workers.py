@@ -1,0 +1,268 @@
+"""Sub-process body of tests/test_exchange_cpu_harness.py: T worker THREADS drive the product's exchange code (the object
+nvcc built from csrc/dfd_exchange.cu, linked against the stand-in CUDA runtime / NCCL and the CPU oracle) through its
+push transport and compare every (partition, producer) segment with the single-node oracle — values and order.
+
+    python run_workers.py <harness.so> <world> <scenario> [seed]
+
+scenario: shuffle | stream | coalesce | broadcast | mismatch"""
+import ctypes as C
+import os
+import sys
+import threading
+import traceback
+
+import numpy as np
+import pyarrow as pa
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from datafusion_distributed_b200 import _native as nv  # noqa: E402  (ctypes struct definitions only; the product library is not loaded)
+from oracle import oracle as orc  # noqa: E402
+
+VP = C.c_void_p
+COL = nv.DfdColumn
+
+
+def bind(lib):
+    sig = {
+        "dfd_last_error": (C.c_char_p, []),
+        "harness_ctx_create": (VP, []),
+        "harness_ctx_destroy": (None, [VP]),
+        "dfd_nccl_unique_id": (C.c_int, [VP]),
+        "dfd_exchange_create": (C.c_int, [VP, C.c_int, C.c_int, VP, C.POINTER(VP)]),
+        "dfd_exchange_destroy": (None, [VP]),
+        "dfd_exchange_setup_window": (C.c_int, [VP, C.c_size_t]),
+        "dfd_partitioner_create": (C.c_int, [VP, C.c_uint32, C.POINTER(C.c_int32), C.c_int, VP, C.POINTER(VP)]),
+        "dfd_partitioner_destroy": (None, [VP]),
+        "dfd_shuffle_device_onepass": (C.c_int, [VP, VP, C.POINTER(COL), C.c_int, C.c_int64, C.c_uint32, C.POINTER(COL)]),
+        "dfd_exchange_collect": (C.c_int, [VP, C.POINTER(COL), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+        "dfd_exchange_gather": (C.c_int, [VP, C.c_int, C.POINTER(COL), C.c_int, C.POINTER(C.c_int64), C.c_uint32, C.c_int, C.POINTER(COL)]),
+        "dfd_exchange_pending_segments": (C.c_uint32, [VP]),
+        "dfd_shuffle_stream_begin": (C.c_int, [VP, VP, C.POINTER(COL), C.c_int, C.c_int64, C.c_uint32, C.POINTER(C.c_uint8), C.POINTER(VP)]),
+        "dfd_shuffle_stream_next": (C.c_int, [VP, C.POINTER(COL), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+        "dfd_shuffle_stream_end": (None, [VP]),
+        "dfd_shuffle_stream_stats": (C.c_int, [VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(lib, name)
+        f.restype, f.argtypes = res, args
+
+
+class Failed(Exception):
+    pass
+
+
+def check(lib, rc, what):
+    if rc != 0:
+        raise Failed(f"{what}: status {rc}: {lib.dfd_last_error().decode('utf-8', 'replace')}")
+
+
+def local_table(rank, n, seed):
+    """Producer `rank`'s rows: Int64 key (nullable), Int32, Boolean (nullable), Utf8 (nullable), Float64."""
+    rng = np.random.Generator(np.random.PCG64(seed * 100 + rank))
+    key = pa.array(rng.integers(0, 1 << 40, n, dtype=np.int64), mask=rng.random(n) < 0.05)
+    i32 = pa.array(rng.integers(-(2**31), 2**31 - 1, n).astype(np.int32))
+    flag = pa.array(rng.random(n) < 0.5, mask=rng.random(n) < 0.1)
+    words = np.array(["", "a", "hello", "x" * 13, "a-much-longer-string-than-twelve-bytes", "ünï"], dtype=object)
+    s = pa.array([None if rng.random() < 0.1 else str(words[rng.integers(0, len(words))]) + str(int(rng.integers(0, 1000))) for _ in range(n)], type=pa.string())
+    f64 = pa.array(rng.standard_normal(n))
+    return pa.table([key, i32, flag, s, f64], names=["key", "i32", "flag", "s", "f64"])
+
+
+def to_columns(table, keep):
+    """pyarrow columns -> dfd_column descriptors over their (host == 'device') buffers."""
+    cols = (COL * table.num_columns)()
+    for i, name in enumerate(table.column_names):
+        a = table.column(name).combine_chunks()
+        keep.append(a)
+        b = a.buffers()
+        c = cols[i]
+        c.offset = a.offset
+        c.validity = b[0].address if (b[0] is not None and a.null_count > 0) else None
+        t = a.type
+        if pa.types.is_boolean(t):
+            c.kind, c.width, c.values = nv.COL_BOOL, 0, b[1].address
+        elif pa.types.is_string(t):
+            c.kind, c.width, c.offsets = nv.COL_UTF8, 0, b[1].address
+            c.values = b[2].address if b[2] is not None else None
+            c.values_bytes = b[2].size if b[2] is not None else 0
+        else:
+            c.kind, c.width, c.values = nv.COL_FIXED, t.bit_width // 8, b[1].address
+    return cols
+
+
+def segment_to_arrow(col, field, start, count):
+    """rows [start, start + count) of an output column in the receive window -> a pyarrow array (zero copy)."""
+    t = field.type
+    if count == 0:
+        return pa.array([], type=t)  # (an empty segment owns no offsets)
+    validity = None
+    if col.validity:
+        validity = pa.foreign_buffer(col.validity, (start + count + 7) // 8 + 8)
+    if pa.types.is_boolean(t):
+        return pa.Array.from_buffers(t, count, [validity, pa.foreign_buffer(col.values, (start + count + 7) // 8 + 8)], offset=start)
+    if pa.types.is_string(t):
+        offs = np.ctypeslib.as_array(C.cast(col.offsets, C.POINTER(C.c_int32)), shape=(start + count + 1,))
+        nbytes = int(offs[start + count]) if count else 0
+        return pa.Array.from_buffers(t, count, [validity, pa.foreign_buffer(col.offsets, 4 * (start + count + 1)), pa.foreign_buffer(col.values, max(nbytes, 1))],
+                                     offset=start)
+    return pa.Array.from_buffers(t, count, [validity, pa.foreign_buffer(col.values, (start + count) * (t.bit_width // 8) + 8)], offset=start)
+
+
+def nullable_outs(table):
+    outs = (COL * table.num_columns)()
+    for i, f in enumerate(table.schema):
+        outs[i].validity = 1 if f.nullable and table.column(i).null_count >= 0 and f.name in ("key", "flag", "s") else None  # the schema's flags
+    return outs
+
+
+def worker(lib, rank, world, uid, scenario, seed, errors, barrier):
+    try:
+        ctx = VP(lib.harness_ctx_create())
+        ex = VP()
+        check(lib, lib.dfd_exchange_create(ctx, rank, world, uid, C.byref(ex)), "dfd_exchange_create")
+        window = (24 << 10) if scenario == "stream" else (8 << 20)
+        if scenario == "mismatch" and rank == world - 1:
+            window += 4096
+        rc = lib.dfd_exchange_setup_window(ex, window)
+        if scenario == "mismatch":
+            # every worker sees that the windows differ (the sizes travel with the IPC handles) and refuses
+            assert rc == 1 and b"same size" in lib.dfd_last_error(), (rc, lib.dfd_last_error())
+            lib.dfd_exchange_destroy(ex)
+            lib.harness_ctx_destroy(ctx)
+            return
+        check(lib, rc, "dfd_exchange_setup_window")
+        P = 3
+        N = P * world
+        n = [0, 1, 700, 1500, 333, 1000, 64, 2000][rank % 8] if scenario != "stream" else 1200 + 100 * rank
+        tables = [local_table(r, ([0, 1, 700, 1500, 333, 1000, 64, 2000][r % 8] if scenario != "stream" else 1200 + 100 * r), seed) for r in range(world)]
+        mine = tables[rank]
+        keep = []
+        in_cols = to_columns(mine, keep)
+        keys = (C.c_int32 * 2)(0, 3)  # Hash([key, s], N): an Int64 and a Utf8 key
+        part = VP()
+        check(lib, lib.dfd_partitioner_create(ctx, N, keys, 2, None, C.byref(part)), "dfd_partitioner_create")
+        fields = list(mine.schema)
+        dests = [orc.partition_ids([t.column("key"), t.column("s")], t.num_rows, N) for t in tables]
+
+        def verify(outs, starts, counts, n_seg, source, rows_of):
+            for sgm in range(n_seg):
+                r, rows = source(sgm)
+                cnt = int(counts[sgm])
+                want = tables[r].take(pa.array(rows)) if r >= 0 else mine.slice(0, 0)
+                assert cnt == want.num_rows, (scenario, rank, sgm, cnt, want.num_rows)
+                for c, f in enumerate(fields):
+                    got = segment_to_arrow(outs[c], f, int(starts[sgm]), cnt)
+                    got.validate(full=True)
+                    assert got.equals(want.column(c).combine_chunks()), (scenario, rank, sgm, f.name)
+                rows_of[0] += cnt
+
+        total = [0]
+        if scenario == "shuffle":
+            outs = nullable_outs(mine)
+            check(lib, lib.dfd_shuffle_device_onepass(ex, part, in_cols, len(fields), mine.num_rows, P, outs), "dfd_shuffle_device_onepass")
+            starts, counts = (C.c_int64 * (P * world))(), (C.c_int64 * (P * world))()
+            check(lib, lib.dfd_exchange_collect(ex, outs, starts, counts), "dfd_exchange_collect")
+            # NetworkShuffleExec::execute: partition q of consumer `rank` = global partition rank * P + q from every producer
+            verify(outs, starts, counts, P * world, lambda s: (s % world, np.nonzero(dests[s % world] == rank * P + s // world)[0]), total)
+            assert total[0] == sum(int((d // P == rank).sum()) for d in dests)
+        elif scenario == "stream":
+            nullable = (C.c_uint8 * len(fields))(1, 0, 1, 1, 0)
+            st = VP()
+            check(lib, lib.dfd_shuffle_stream_begin(ex, part, in_cols, len(fields), mine.num_rows, P, nullable, C.byref(st)), "dfd_shuffle_stream_begin")
+            got = {(q, r): [] for q in range(P) for r in range(world)}
+            while True:
+                outs = (COL * len(fields))()
+                starts, counts, done = (C.c_int64 * (P * world))(), (C.c_int64 * (P * world))(), C.c_int(0)
+                check(lib, lib.dfd_shuffle_stream_next(st, outs, starts, counts, C.byref(done)), "dfd_shuffle_stream_next")
+                if done.value:
+                    break
+                for sgm in range(P * world):  # drain the window before the next round overwrites it
+                    cnt = int(counts[sgm])
+                    if cnt:
+                        got[(sgm // world, sgm % world)].append(pa.table([segment_to_arrow(outs[c], f, int(starts[sgm]), cnt) for c, f in enumerate(fields)],
+                                                                         names=mine.column_names).combine_chunks().to_pydict())
+                barrier.wait()  # (a real consumer would hand the rows on; all workers enter the next round together anyway)
+            rounds, splits = C.c_uint64(0), C.c_uint64(0)
+            lib.dfd_shuffle_stream_stats(st, C.byref(rounds), C.byref(splits))
+            assert rounds.value > 1 and splits.value >= 1, (rounds.value, splits.value)  # the window is too small for one round
+            lib.dfd_shuffle_stream_end(st)
+            for (q, r), pieces in got.items():
+                want = tables[r].take(pa.array(np.nonzero(dests[r] == rank * P + q)[0])).to_pydict()
+                have = {k: [v for p in pieces for v in p[k]] for k in mine.column_names}
+                assert have == want or (not pieces and all(len(v) == 0 for v in want.values())), (rank, q, r)
+        else:
+            route = {"coalesce": 1, "broadcast": 2}[scenario]
+            consumers = max(1, world - 1) if scenario == "coalesce" else world
+            # this producer's P partitions = P row slices of its table (no repartition)
+            cuts = sorted({0, mine.num_rows} | {int(x) for x in np.random.Generator(np.random.PCG64(seed + rank)).integers(0, mine.num_rows + 1, P - 1)})
+            while len(cuts) < P + 1:
+                cuts.append(mine.num_rows)
+            all_cuts = []
+            for r in range(world):
+                nr = tables[r].num_rows
+                c_ = sorted({0, nr} | {int(x) for x in np.random.Generator(np.random.PCG64(seed + r)).integers(0, nr + 1, P - 1)})
+                while len(c_) < P + 1:
+                    c_.append(nr)
+                all_cuts.append(c_)
+            slice_starts = (C.c_int64 * (P + 1))(*all_cuts[rank])
+            outs = nullable_outs(mine)
+            check(lib, lib.dfd_exchange_gather(ex, route, in_cols, len(fields), slice_starts, P, consumers, outs), "dfd_exchange_gather")
+            nseg = lib.dfd_exchange_pending_segments(ex)
+            starts, counts = (C.c_int64 * max(nseg, 1))(), (C.c_int64 * max(nseg, 1))()
+            check(lib, lib.dfd_exchange_collect(ex, outs, starts, counts), "dfd_exchange_collect")
+            if scenario == "broadcast":
+                assert nseg == P * world
+                src = lambda s: (s % world, np.arange(all_cuts[s % world][s // world], all_cuts[s % world][s // world + 1]))  # noqa: E731
+            else:
+                base, extra = divmod(world, consumers)
+                if rank >= consumers:
+                    assert nseg == 0
+                    src = None
+                else:
+                    length, start = base + (1 if rank < extra else 0), rank * base + min(rank, extra)
+                    assert nseg == (base + (1 if extra else 0)) * P
+
+                    def src(s):
+                        off, g = divmod(s, P)
+                        if off >= length:
+                            return -1, np.arange(0)
+                        r = start + off
+                        return r, np.arange(all_cuts[r][g], all_cuts[r][g + 1])
+            if src:
+                verify(outs, starts, counts, nseg, src, total)
+        barrier.wait()  # nobody tears its window down while a peer may still read flags in it
+        lib.dfd_partitioner_destroy(part)
+        lib.dfd_exchange_destroy(ex)
+        lib.harness_ctx_destroy(ctx)
+    except BaseException:  # noqa: BLE001
+        errors.append(f"rank {rank}: " + traceback.format_exc())
+        try:
+            barrier.abort()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def main():
+    so, world, scenario = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+    seed = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+    lib = C.CDLL(so)
+    bind(lib)
+    uid = (C.c_uint8 * 128)()
+    if world > 1:
+        rc = lib.dfd_nccl_unique_id(uid)
+        assert rc == 0, lib.dfd_last_error()
+    errors, barrier = [], threading.Barrier(world)
+    threads = [threading.Thread(target=worker, args=(lib, r, world, uid, scenario, seed, errors, barrier)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    if errors or any(t.is_alive() for t in threads):
+        print("\n".join(errors) or "a worker thread hung", file=sys.stderr)
+        os._exit(1)
+    print(f"WORKERS_OK world={world} scenario={scenario}")
+
+
+if __name__ == "__main__":
+    main()
