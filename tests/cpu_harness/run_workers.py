@@ -159,13 +159,35 @@ def worker(lib, rank, world, uid, scenario, seed, errors, barrier):
 
         total = [0]
         if scenario == "shuffle":
-            outs = nullable_outs(mine)
-            check(lib, lib.dfd_shuffle_device_onepass(ex, part, in_cols, len(fields), mine.num_rows, P, outs), "dfd_shuffle_device_onepass")
-            starts, counts = (C.c_int64 * (P * world))(), (C.c_int64 * (P * world))()
-            check(lib, lib.dfd_exchange_collect(ex, outs, starts, counts), "dfd_exchange_collect")
-            # NetworkShuffleExec::execute: partition q of consumer `rank` = global partition rank * P + q from every producer
-            verify(outs, starts, counts, P * world, lambda s: (s % world, np.nonzero(dests[s % world] == rank * P + s // world)[0]), total)
-            assert total[0] == sum(int((d // P == rank).sum()) for d in dests)
+            # three shuffles in a row over the same windows (the epoch flags tell the rounds apart; a consumer's window is only
+            # overwritten after it has announced the next shuffle), the last one through the pre-partitioned route
+            for rep in range(3):
+                if rep:
+                    tables = [local_table(r, [5, 0, 900, 64, 1, 1300, 700, 33][(r + rep) % 8], seed + 17 * rep) for r in range(world)]
+                    mine = tables[rank]
+                    keep.clear()
+                    in_cols = to_columns(mine, keep)
+                    dests = [orc.partition_ids([t.column("key"), t.column("s")], t.num_rows, N) for t in tables]
+                outs = nullable_outs(mine)
+                if rep < 2:
+                    check(lib, lib.dfd_shuffle_device_onepass(ex, part, in_cols, len(fields), mine.num_rows, P, outs), "dfd_shuffle_device_onepass")
+                else:
+                    # DFD_ROUTE_SHUFFLE: the rows are ALREADY grouped by global partition (what dfd_partition_device [+ PartialReduce]
+                    # leaves behind); only the exchange half runs
+                    order = np.argsort(dests[rank], kind="stable")
+                    sorted_mine = mine.take(pa.array(order))
+                    keep.clear()
+                    in_cols = to_columns(sorted_mine, keep)
+                    cnt = np.bincount(dests[rank], minlength=N)
+                    slice_starts = (C.c_int64 * (N + 1))(0, *np.cumsum(cnt).tolist())
+                    check(lib, lib.dfd_exchange_gather(ex, 0, in_cols, len(fields), slice_starts, P, world, outs), "dfd_exchange_gather(shuffle)")
+                starts, counts = (C.c_int64 * (P * world))(), (C.c_int64 * (P * world))()
+                check(lib, lib.dfd_exchange_collect(ex, outs, starts, counts), "dfd_exchange_collect")
+                # NetworkShuffleExec::execute: partition q of consumer `rank` = global partition rank * P + q from every producer
+                total[0] = 0
+                verify(outs, starts, counts, P * world, lambda s: (s % world, np.nonzero(dests[s % world] == rank * P + s // world)[0]), total)
+                assert total[0] == sum(int((d // P == rank).sum()) for d in dests)
+                barrier.wait()  # (the test reads the window from Python: finish before the next shuffle may overwrite it)
         elif scenario == "stream":
             nullable = (C.c_uint8 * len(fields))(1, 0, 1, 1, 0)
             st = VP()
