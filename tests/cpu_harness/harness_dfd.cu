@@ -18,6 +18,7 @@
 #include "df_oracle.h"
 
 int harness_partition(dfd_partitioner* p, const dfd_column* in, int n_cols, int64_t n, const dfd_column* out);
+int harness_destinations(dfd_partitioner* p, const dfd_column* in, int n_cols, int64_t n, std::vector<uint64_t>* hashes);
 
 namespace {
 std::atomic<uint64_t> g_ns_kernels{0};  // time spent in the stand-ins of the kernels (not host logic of the operator)
@@ -105,13 +106,13 @@ int dfd::partition_device_locked(Partitioner* p, const dfd_column* in, int n_col
 }
 
 // the stand-in of K1/K1b/K2/K4 (also used by the exchange harness, harness_exchange.cu)
-int harness_partition(dfd_partitioner* p, const dfd_column* in, int n_cols, int64_t n, const dfd_column* out) {
+// create_hashes over the key columns -> destination id of every row (h % N)
+int harness_destinations(dfd_partitioner* p, const dfd_column* in, int n_cols, int64_t n, std::vector<uint64_t>* hashes) {
     using dfd::set_error;
-    KernelTime kernel_time;
-    const uint32_t N = p->N;
     const orc_random_state st = orc_repartition_random_state();
-    // ---- create_hashes over the key columns (column 0 overwrites, later columns combine, null keys are skipped)
-    std::vector<uint64_t> h((size_t)n, 0), one((size_t)n);
+    std::vector<uint64_t>& h = *hashes;
+    h.assign((size_t)n, 0);
+    std::vector<uint64_t> one((size_t)n);
     for (size_t k = 0; k < p->key_cols.size(); ++k) {
         if (p->key_cols[k] >= n_cols) return set_error(DFD_ERR_INVALID_ARGUMENT, "key column %d out of range", p->key_cols[k]);
         const dfd_column& c = in[p->key_cols[k]];
@@ -141,6 +142,15 @@ int harness_partition(dfd_partitioner* p, const dfd_column* in, int n_cols, int6
             h[(size_t)i] = k >= 1 ? orc_combine_hashes(one[(size_t)i], h[(size_t)i]) : one[(size_t)i];
         }
     }
+    return DFD_OK;
+}
+
+int harness_partition(dfd_partitioner* p, const dfd_column* in, int n_cols, int64_t n, const dfd_column* out) {
+    using dfd::set_error;
+    KernelTime kernel_time;
+    const uint32_t N = p->N;
+    std::vector<uint64_t> h;
+    if (int rc = harness_destinations(p, in, n_cols, n, &h)) return rc;
     // ---- stable partition: row indices grouped by destination, in row order
     std::vector<int64_t> counts(N), starts(N + 1);
     std::vector<uint32_t> idx((size_t)(n > 0 ? n : 1));

@@ -3,8 +3,10 @@
 //   * the PartitionJob stages and the small conversion launches, restated with the CPU oracle;
 //   * CPU emulations of the exchange kernels that path launches (k_slice_rows, k_xchg_allgather_meta, k_push_runs,
 //     k_xchg_done_barrier), registered by name with the stand-in runtime's cudaLaunchKernel.
-// The single-pass peer scatter and the two-pass fused / NCCL-mode transports are NOT emulated (their launches fail with
-// cudaErrorNotSupported): they are covered on real GPUs (tests/mgpu_shuffle_check.py, bench.py --gpus N parity).
+// and to run the single-pass exchange (fixed-width non-null schemas) with its overflow -> exact two-pass re-run:
+//   * PartitionJob::run_onepass<PEER> / run_scatter<PEER> as row loops that store into the owners' windows;
+//   * k_xchg_signal_ready, k_xchg_publish_wait, k_exchange_plan.
+// The NCCL-mode transport (ncclSend / ncclRecv) is NOT emulated: it is covered on real GPUs (tests/mgpu_shuffle_check.py).
 #include <chrono>
 #include <cstdint>
 #include <cstring>
@@ -14,30 +16,99 @@
 #include "dfd_internal.h"
 
 int harness_partition(dfd_partitioner* p, const dfd_column* in, int n_cols, int64_t n, const dfd_column* out);
+int harness_destinations(dfd_partitioner* p, const dfd_column* in, int n_cols, int64_t n, std::vector<uint64_t>* hashes);
 
 namespace {
 inline bool bit(const uint8_t* b, int64_t i) { return (b[i >> 3] >> (i & 7)) & 1; }
 }  // namespace
 
-// ---- PartitionJob: the exchange only uses the local (non-peer) form in the push transport -------------------------------
+// ---- PartitionJob: local form (push transport) and peer form (single-pass / two-pass fused exchange) ---------------------
+namespace {
+thread_local std::vector<uint32_t> t_dest;  // destination of every row of the job this worker (= thread) is running
+bool wait_flags(const unsigned long long* flags, int world, unsigned long long epoch);
+
+int destinations_of(dfd::PartitionJob& job) {
+    std::vector<dfd_column> in;
+    for (const dfd::PartitionJob::VarCol& v : job.var_cols) in.push_back(v.in);
+    std::vector<uint64_t> h;
+    if (int rc = harness_destinations(job.p, in.data(), (int)in.size(), job.n_rows, &h)) return rc;
+    t_dest.resize((size_t)job.n_rows);
+    for (int64_t i = 0; i < job.n_rows; ++i) t_dest[(size_t)i] = (uint32_t)(h[(size_t)i] % job.p->N);
+    return DFD_OK;
+}
+}  // namespace
+
 int dfd::PartitionJob::prepare(Partitioner* part, const dfd_column* in_cols, int n_cols, int64_t rows, const dfd_column* out_cols, bool peer_mode, cudaStream_t st) {
     p = part;
     stream = st;
     peer = peer_mode;
     n_rows = rows;
     var_cols.clear();
-    for (int i = 0; i < n_cols; ++i) var_cols.push_back(VarCol{in_cols[i], out_cols[i]});  // (all columns: the stand-in needs nothing else)
-    if (peer_mode) return set_error(DFD_ERR_UNSUPPORTED, "harness: the peer-store scatter is not emulated on the CPU");
+    for (int i = 0; i < n_cols; ++i) {
+        if (peer_mode && (in_cols[i].kind != DFD_COL_FIXED || in_cols[i].validity)) return set_error(DFD_ERR_UNSUPPORTED, "column %d: peer stores move fixed-width non-null columns", i);
+        var_cols.push_back(VarCol{in_cols[i], out_cols[i]});  // (all columns: the stand-in needs nothing else)
+    }
+    int rc = p->ctx->scratch.ensure(sizeof(int64_t) * (size_t)p->N + 256, p->ctx->device);
+    if (rc) return rc;
+    d_totals = (int64_t*)p->ctx->scratch.ptr;
     return DFD_OK;
 }
-int dfd::PartitionJob::run_hist_scan() { return DFD_OK; }
-int dfd::PartitionJob::run_scatter(const int64_t*, void* const* peer_base, int, uint32_t, const int32_t*) {
-    if (peer_base) return set_error(DFD_ERR_UNSUPPORTED, "harness: the peer-store scatter is not emulated on the CPU");
+
+// K1 + K1b: per-destination totals (the exchange all-gathers them in the two-pass fused path)
+int dfd::PartitionJob::run_hist_scan() {
+    if (!peer) return DFD_OK;  // (the local form partitions in run_scatter)
+    if (int rc = destinations_of(*this)) return rc;
+    memset(d_totals, 0, sizeof(int64_t) * (size_t)p->N);
+    for (uint32_t g : t_dest) d_totals[g]++;
+    return DFD_OK;
+}
+
+// K2.  Local: dense destination-sorted output + part_starts.  Peer: row k of destination g goes to row dest_base[g] + k of
+// the window slot of g's owner (out.values is the column's byte offset inside every slot); nothing is written once the plan
+// kernel has raised the abort flag.
+int dfd::PartitionJob::run_scatter(const int64_t* dest_base, void* const* peer_base, int, uint32_t parts_per_rank, const int32_t* abort_flag) {
     std::vector<dfd_column> in, out;
     for (const VarCol& v : var_cols) { in.push_back(v.in); out.push_back(v.out); }
-    return harness_partition(p, in.data(), (int)in.size(), n_rows, out.data());  // writes p->d_part_starts like K1b
+    if (!peer_base) return harness_partition(p, in.data(), (int)in.size(), n_rows, out.data());  // writes p->d_part_starts like K1b
+    if (abort_flag && *abort_flag) return DFD_OK;
+    std::vector<int64_t> cursor(p->N, 0);
+    for (int64_t i = 0; i < n_rows; ++i) {
+        const uint32_t g = t_dest[(size_t)i];
+        const int64_t row = dest_base[g] + cursor[g]++;
+        char* base = (char*)peer_base[g / parts_per_rank];
+        for (size_t c = 0; c < in.size(); ++c) {
+            const size_t w = (size_t)in[c].width;
+            memcpy(base + (size_t)out[c].values + (size_t)row * w, (const char*)in[c].values + (size_t)(i + in[c].offset) * w, w);
+        }
+    }
+    return DFD_OK;
 }
-int dfd::PartitionJob::run_onepass(const OnePassLayout&) { return set_error(DFD_ERR_UNSUPPORTED, "harness: the single-pass peer scatter is not emulated on the CPU"); }
+
+// k_scatter_onepass<PEER>: every (partition q of consumer o, producer `rank`) pair owns rows [(q T + rank) sub_cap, + sub_cap)
+// of every column of o's slot; rows beyond a sub-window are dropped and flagged (the counts stay exact), and no store is
+// issued before every consumer has released its window for this epoch.
+int dfd::PartitionJob::run_onepass(const OnePassLayout& L) {
+    if (!L.peer_base) return set_error(DFD_ERR_UNSUPPORTED, "harness: only the peer form of the single-pass scatter is emulated");
+    if (L.ready_flags && !wait_flags(L.ready_flags, L.world, L.ready_epoch)) return set_error(DFD_ERR_INTERNAL, "harness: a consumer never released its window");
+    if (int rc = destinations_of(*this)) return rc;
+    const uint32_t N = p->N, P = L.parts_per_rank;
+    std::vector<int64_t> count(N, 0);
+    bool overflow = false;
+    for (int64_t i = 0; i < n_rows; ++i) {
+        const uint32_t g = t_dest[(size_t)i];
+        const int64_t k = count[g]++;
+        if (k >= L.region_stride) { overflow = true; continue; }
+        const int64_t row = ((int64_t)(g % P) * L.world + L.rank) * L.region_stride + k;
+        char* base = (char*)L.peer_base[g / P];
+        for (const VarCol& v : var_cols) {
+            const size_t w = (size_t)v.in.width;
+            memcpy(base + (size_t)v.out.values + (size_t)row * w, (const char*)v.in.values + (size_t)(i + v.in.offset) * w, w);
+        }
+    }
+    memcpy(L.d_totals, count.data(), sizeof(int64_t) * (size_t)N);
+    if (overflow) *L.d_overflow = 1;
+    return DFD_OK;
+}
 
 int dfd::launch_bits_to_bytes(const uint8_t* bits, int64_t bit_offset, int64_t n, uint8_t* out, cudaStream_t) {
     for (int64_t i = 0; i < n; ++i) out[i] = bit(bits, i + bit_offset) ? 1 : 0;
@@ -155,7 +226,69 @@ int cpu_push_runs(FakeDim3, FakeDim3, void** a) {
     return 0;
 }
 
+// k_xchg_signal_ready(peer_hdr, rank, world, epoch): "my window is free" into every producer's header
+int cpu_signal_ready(FakeDim3, FakeDim3, void** a) {
+    dfd::ExchangeHeader* const* peer = arg<dfd::ExchangeHeader* const*>(a, 0);
+    const int rank = arg<int>(a, 1), world = arg<int>(a, 2);
+    const unsigned long long epoch = arg<unsigned long long>(a, 3);
+    for (int o = 0; o < world; ++o) store_release(&peer[o]->ready[rank], epoch);
+    return 0;
+}
+
+// k_xchg_publish_wait(local, peer_hdr, rank, world, P, epoch, totals, overflow, timed_out)
+int cpu_publish_wait(FakeDim3, FakeDim3, void** a) {
+    dfd::ExchangeHeader* local = arg<dfd::ExchangeHeader*>(a, 0);
+    dfd::ExchangeHeader* const* peer = arg<dfd::ExchangeHeader* const*>(a, 1);
+    const int rank = arg<int>(a, 2), world = arg<int>(a, 3);
+    const uint32_t P = arg<uint32_t>(a, 4);
+    const unsigned long long epoch = arg<unsigned long long>(a, 5);
+    const int64_t* totals = arg<const int64_t*>(a, 6);
+    const int32_t* overflow = arg<const int32_t*>(a, 7);
+    int32_t* timed_out = arg<int32_t*>(a, 8);
+    for (uint32_t g = 0; g < P * (uint32_t)world; ++g) peer[g / P]->counts[rank][g % P] = totals[g];
+    for (int o = 0; o < world; ++o) peer[o]->overflow[rank] = *overflow;
+    for (int o = 0; o < world; ++o) store_release(&peer[o]->done[rank], epoch);
+    if (!wait_flags(local->done, world, epoch)) *timed_out = 1;
+    return 0;
+}
+
+// k_exchange_plan(counts[T][N], world, P, rank, capacity_rows, dest_base[N], my_part_starts[P+1], abort_flag)
+int cpu_exchange_plan(FakeDim3, FakeDim3, void** a) {
+    const int64_t* counts = arg<const int64_t*>(a, 0);
+    const int world = arg<int>(a, 1);
+    const uint32_t P = arg<uint32_t>(a, 2);
+    const int rank = arg<int>(a, 3);
+    const int64_t capacity_rows = arg<int64_t>(a, 4);
+    int64_t* dest_base = arg<int64_t*>(a, 5);
+    int64_t* my_part_starts = arg<int64_t*>(a, 6);
+    int32_t* abort_flag = arg<int32_t*>(a, 7);
+    const uint32_t N = P * (uint32_t)world;
+    int overflow = 0;
+    for (int o = 0; o < world; ++o) {
+        int64_t run = 0;
+        for (uint32_t q = 0; q < P; ++q) {
+            const uint32_t g = (uint32_t)o * P + q;
+            if (o == rank) my_part_starts[q] = run;
+            int64_t before_me = 0, tot = 0;
+            for (int r = 0; r < world; ++r) {
+                const int64_t c = counts[(int64_t)r * N + g];
+                if (r < rank) before_me += c;
+                tot += c;
+            }
+            dest_base[g] = run + before_me;
+            run += tot;
+        }
+        if (o == rank) my_part_starts[P] = run;
+        if (run > capacity_rows) overflow = 1;
+    }
+    *abort_flag = overflow;
+    return 0;
+}
+
 __attribute__((constructor)) void register_exchange_kernels() {
+    harness_register_kernel("k_xchg_signal_ready", cpu_signal_ready);
+    harness_register_kernel("k_xchg_publish_wait", cpu_publish_wait);
+    harness_register_kernel("k_exchange_plan", cpu_exchange_plan);
     harness_register_kernel("k_slice_rows", cpu_slice_rows);
     harness_register_kernel("k_xchg_allgather_meta", cpu_allgather_meta);
     harness_register_kernel("k_xchg_done_barrier", cpu_done_barrier);

@@ -4,7 +4,7 @@ push transport and compare every (partition, producer) segment with the single-n
 
     python run_workers.py <harness.so> <world> <scenario> [seed]
 
-scenario: shuffle | stream | coalesce | broadcast | mismatch"""
+scenario: shuffle | stream | coalesce | broadcast | mismatch | onepass | onepass_overflow"""
 import ctypes as C
 import os
 import sys
@@ -42,6 +42,7 @@ def bind(lib):
         "dfd_shuffle_stream_next": (C.c_int, [VP, C.POINTER(COL), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
         "dfd_shuffle_stream_end": (None, [VP]),
         "dfd_shuffle_stream_stats": (C.c_int, [VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "dfd_exchange_onepass_fallbacks": (C.c_uint64, [VP]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)
@@ -67,6 +68,16 @@ def local_table(rank, n, seed):
     s = pa.array([None if rng.random() < 0.1 else str(words[rng.integers(0, len(words))]) + str(int(rng.integers(0, 1000))) for _ in range(n)], type=pa.string())
     f64 = pa.array(rng.standard_normal(n))
     return pa.table([key, i32, flag, s, f64], names=["key", "i32", "flag", "s", "f64"])
+
+
+def fixed_table(rank, n, seed, skew):
+    """Producer `rank`'s rows for the single-pass exchange: fixed-width, non-null (key Int64, Int32, Float64, Int64)."""
+    rng = np.random.Generator(np.random.PCG64(seed * 1000 + rank))
+    key = rng.integers(0, 1 << 50, n, dtype=np.int64)
+    if skew:
+        key[rng.random(n) < 0.7] = 424242  # one hot key: its (partition, producer) sub-window overflows
+    return pa.table([pa.array(key), pa.array(rng.integers(-(2**31), 2**31 - 1, n).astype(np.int32)), pa.array(rng.standard_normal(n)),
+                     pa.array(np.arange(n, dtype=np.int64) * 8 + rank)], names=["key", "i32", "f64", "rid"])
 
 
 def to_columns(table, keep):
@@ -122,6 +133,8 @@ def worker(lib, rank, world, uid, scenario, seed, errors, barrier):
         ex = VP()
         check(lib, lib.dfd_exchange_create(ctx, rank, world, uid, C.byref(ex)), "dfd_exchange_create")
         window = (24 << 10) if scenario == "stream" else (8 << 20)
+        if scenario == "onepass_overflow":
+            window = 6000 * 28  # capacity 6000 rows of 28 bytes: sub-windows of 992 rows at 2 workers x 3 partitions
         if scenario == "mismatch" and rank == world - 1:
             window += 4096
         rc = lib.dfd_exchange_setup_window(ex, window)
@@ -158,7 +171,31 @@ def worker(lib, rank, world, uid, scenario, seed, errors, barrier):
                 rows_of[0] += cnt
 
         total = [0]
-        if scenario == "shuffle":
+        if scenario in ("onepass", "onepass_overflow"):
+            # the single-pass exchange (fixed-width non-null schema): peer stores into (partition, producer) sub-windows, counts
+            # and completion as peer-memory flags; a sub-window that overflows on ANY worker makes every worker re-run exactly
+            for rep in range(2):
+                tables = [fixed_table(r, 2000 + 10 * r, seed + rep, scenario == "onepass_overflow") for r in range(world)]
+                mine = tables[rank]
+                fields = list(mine.schema)
+                keep.clear()
+                in_cols = to_columns(mine, keep)
+                k1 = (C.c_int32 * 1)(0)
+                part1 = VP()
+                check(lib, lib.dfd_partitioner_create(ctx, N, k1, 1, None, C.byref(part1)), "dfd_partitioner_create")
+                dests = [orc.partition_ids([t.column("key")], t.num_rows, N) for t in tables]
+                outs = (COL * len(fields))()
+                check(lib, lib.dfd_shuffle_device_onepass(ex, part1, in_cols, len(fields), mine.num_rows, P, outs), "dfd_shuffle_device_onepass")
+                starts, counts = (C.c_int64 * (P * world))(), (C.c_int64 * (P * world))()
+                check(lib, lib.dfd_exchange_collect(ex, outs, starts, counts), "dfd_exchange_collect")
+                total[0] = 0
+                verify(outs, starts, counts, P * world, lambda s: (s % world, np.nonzero(dests[s % world] == rank * P + s // world)[0]), total)
+                assert total[0] == sum(int((d // P == rank).sum()) for d in dests)
+                fb = lib.dfd_exchange_onepass_fallbacks(ex)
+                assert fb == (rep + 1 if scenario == "onepass_overflow" else 0), fb
+                barrier.wait()
+                lib.dfd_partitioner_destroy(part1)
+        elif scenario == "shuffle":
             # three shuffles in a row over the same windows (the epoch flags tell the rounds apart; a consumer's window is only
             # overwritten after it has announced the next shuffle), the last one through the pre-partitioned route
             for rep in range(3):

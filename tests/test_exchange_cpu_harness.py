@@ -7,8 +7,10 @@ dlopen("libnccl.so.2")) and the CPU oracle in place of the partition kernels.  T
 push transport exactly as T GPU workers would: window set-up with size agreement, the flag all-gather of row / byte counts,
 every worker deriving every consumer's layout, `k_push_runs`-shaped copies into the owners' windows, the done barrier —
 for the shuffle (NetworkShuffleExec), the back-pressured rounds, NetworkCoalesceExec and NetworkBroadcastExec routes, with
-nullable / boolean / string columns, and compare every (partition, producer) segment with the single-node oracle.
-The single-pass peer scatter, the two-pass fused and the NCCL-mode transports are NOT emulated (real GPUs only)."""
+nullable / boolean / string columns, and compare every (partition, producer) segment with the single-node oracle.  The
+single-pass exchange (fixed-width non-null schemas: ready flags, peer stores into (partition, producer) sub-windows, publish /
+wait, and the overflow -> exact two-pass re-run that every worker must take together) runs the same way, its scatter kernels
+replaced by row loops.  The NCCL-mode transport (ncclSend / ncclRecv) is NOT emulated (real GPUs only)."""
 import os
 import subprocess
 import sys
@@ -76,6 +78,16 @@ def test_coalesce_route_with_uneven_groups(exchange_harness, world):
 @pytest.mark.parametrize("world", [2, 4])
 def test_broadcast_route(exchange_harness, world):
     run(exchange_harness, world, "broadcast")
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_single_pass_exchange_sub_windows_and_flags(exchange_harness, world):
+    run(exchange_harness, world, "onepass")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_single_pass_overflow_makes_every_worker_rerun_exactly(exchange_harness, world):
+    run(exchange_harness, world, "onepass_overflow")
 
 
 def test_workers_refuse_windows_of_different_sizes(exchange_harness):
