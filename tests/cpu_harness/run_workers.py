@@ -4,7 +4,7 @@ push transport and compare every (partition, producer) segment with the single-n
 
     python run_workers.py <harness.so> <world> <scenario> [seed]
 
-scenario: shuffle | stream | coalesce | broadcast | mismatch | onepass | onepass_overflow"""
+scenario: shuffle | stream | coalesce | broadcast | mismatch | onepass | onepass_overflow | host"""
 import ctypes as C
 import os
 import sys
@@ -43,6 +43,7 @@ def bind(lib):
         "dfd_shuffle_stream_end": (None, [VP]),
         "dfd_shuffle_stream_stats": (C.c_int, [VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "dfd_exchange_onepass_fallbacks": (C.c_uint64, [VP]),
+        "dfd_shuffle_host": (C.c_int, [VP, VP, C.POINTER(COL), C.c_int, C.c_int64, C.c_uint32, C.c_int, C.POINTER(COL), C.c_int64, C.POINTER(C.c_int64)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)
@@ -193,6 +194,42 @@ def worker(lib, rank, world, uid, scenario, seed, errors, barrier):
                 assert total[0] == sum(int((d // P == rank).sum()) for d in dests)
                 fb = lib.dfd_exchange_onepass_fallbacks(ex)
                 assert fb == (rep + 1 if scenario == "onepass_overflow" else 0), fb
+                barrier.wait()
+                lib.dfd_partitioner_destroy(part1)
+        elif scenario == "host":
+            # dfd_shuffle_host: HOST columns in, HOST columns out, the rows cut into chunks that pipeline H2D | fused shuffle | D2H
+            # through the two halves of the receive window; output is chunk-major, producers contiguous per (chunk, partition)
+            for n_chunks in (1, 3, 4):
+                tables = [fixed_table(r, 1500 + 7 * r, seed + n_chunks, False) for r in range(world)]
+                mine = tables[rank]
+                fields = list(mine.schema)
+                keep.clear()
+                in_cols = to_columns(mine, keep)
+                k1 = (C.c_int32 * 1)(0)
+                part1 = VP()
+                check(lib, lib.dfd_partitioner_create(ctx, N, k1, 1, None, C.byref(part1)), "dfd_partitioner_create")
+                dests = [orc.partition_ids([t.column("key")], t.num_rows, N) for t in tables]
+                cap = sum(t.num_rows for t in tables)
+                bufs = [np.zeros(cap * (f.type.bit_width // 8) + 64, dtype=np.uint8) for f in fields]
+                outs = (COL * len(fields))()
+                for i, f in enumerate(fields):
+                    outs[i].kind, outs[i].width, outs[i].values = nv.COL_FIXED, f.type.bit_width // 8, bufs[i].ctypes.data
+                cps = (C.c_int64 * (n_chunks * (P + 1)))()
+                check(lib, lib.dfd_shuffle_host(ex, part1, in_cols, len(fields), mine.num_rows, P, n_chunks, outs, cap, cps), "dfd_shuffle_host")
+                for ch in range(n_chunks):
+                    for q in range(P):
+                        a, b = cps[ch * (P + 1) + q], cps[ch * (P + 1) + q + 1]
+                        want_rows = []
+                        for r in range(world):  # producers in task order, each with the rows of ITS chunk `ch`
+                            nr = tables[r].num_rows
+                            lo, hi = nr * ch // n_chunks, nr * (ch + 1) // n_chunks
+                            want_rows.append(tables[r].slice(lo, hi - lo).take(pa.array(np.nonzero(dests[r][lo:hi] == rank * P + q)[0])))
+                        want = pa.concat_tables(want_rows)
+                        assert b - a == want.num_rows, (n_chunks, ch, q, a, b, want.num_rows)
+                        for i, f in enumerate(fields):
+                            w = f.type.bit_width // 8
+                            got = pa.Array.from_buffers(f.type, b - a, [None, pa.py_buffer(bufs[i][a * w:b * w].tobytes())])
+                            assert got.equals(want.column(i).combine_chunks()), (n_chunks, ch, q, f.name)
                 barrier.wait()
                 lib.dfd_partitioner_destroy(part1)
         elif scenario == "shuffle":

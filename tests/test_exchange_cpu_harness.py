@@ -90,5 +90,10 @@ def test_single_pass_overflow_makes_every_worker_rerun_exactly(exchange_harness,
     run(exchange_harness, world, "onepass_overflow")
 
 
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_host_to_host_shuffle_in_chunks(exchange_harness, world):
+    run(exchange_harness, world, "host")
+
+
 def test_workers_refuse_windows_of_different_sizes(exchange_harness):
     run(exchange_harness, 3, "mismatch")
