@@ -9,6 +9,7 @@
 // The NCCL-mode transport (ncclSend / ncclRecv) is NOT emulated: it is covered on real GPUs (tests/mgpu_shuffle_check.py).
 #include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -143,12 +144,13 @@ T arg(void** args, int i) { T v; memcpy(&v, args[i], sizeof v); return v; }
 inline void store_release(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline unsigned long long load_acquire(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 
-// wait until flags[t] >= epoch for every t < world; 20 s bound like the kernels' clock64 bound
+// wait until flags[t] >= epoch for every t < world; bounded like the kernels' clock64 bound (HARNESS_FLAG_TIMEOUT_MS, default 20 s)
 bool wait_flags(const unsigned long long* flags, int world, unsigned long long epoch) {
+    static const long timeout_ms = getenv("HARNESS_FLAG_TIMEOUT_MS") ? atol(getenv("HARNESS_FLAG_TIMEOUT_MS")) : 20000;
     const auto t0 = std::chrono::steady_clock::now();
     for (int t = 0; t < world; ++t)
         while (load_acquire(&flags[t]) < epoch) {
-            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) return false;
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(timeout_ms)) return false;
             __builtin_ia32_pause();
         }
     return true;

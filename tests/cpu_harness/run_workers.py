@@ -4,7 +4,7 @@ push transport and compare every (partition, producer) segment with the single-n
 
     python run_workers.py <harness.so> <world> <scenario> [seed]
 
-scenario: shuffle | stream | coalesce | broadcast | mismatch | onepass | onepass_overflow | host"""
+scenario: shuffle | stream | coalesce | broadcast | mismatch | onepass | onepass_overflow | host | peer_missing"""
 import ctypes as C
 import os
 import sys
@@ -172,7 +172,14 @@ def worker(lib, rank, world, uid, scenario, seed, errors, barrier):
                 rows_of[0] += cnt
 
         total = [0]
-        if scenario in ("onepass", "onepass_overflow"):
+        if scenario == "peer_missing":
+            # the last worker fails before the exchange (it never enters the collective): the others must come back with an error
+            # after the bounded flag wait — never hang (the coordinator then cancels the stage, impl_execute_task.rs:138-155)
+            if rank != world - 1:
+                outs = nullable_outs(mine)
+                rc = lib.dfd_shuffle_device_onepass(ex, part, in_cols, len(fields), mine.num_rows, P, outs)
+                assert rc == 5 and b"never published" in lib.dfd_last_error(), (rc, lib.dfd_last_error())  # DFD_ERR_INTERNAL
+        elif scenario in ("onepass", "onepass_overflow"):
             # the single-pass exchange (fixed-width non-null schema): peer stores into (partition, producer) sub-windows, counts
             # and completion as peer-memory flags; a sub-window that overflows on ANY worker makes every worker re-run exactly
             for rep in range(2):

@@ -52,9 +52,9 @@ def exchange_harness(built, tmp_path_factory):
     return so, tmp
 
 
-def run(exchange_harness, world, scenario, seed=1):
+def run(exchange_harness, world, scenario, seed=1, **extra_env):
     so, tmp = exchange_harness
-    env = dict(os.environ, LD_LIBRARY_PATH=tmp + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    env = dict(os.environ, LD_LIBRARY_PATH=tmp + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""), **extra_env)
     out = subprocess.run([sys.executable, os.path.join(HARNESS, "run_workers.py"), so, str(world), scenario, str(seed)], env=env, capture_output=True, text=True,
                          timeout=300)
     assert out.returncode == 0 and f"WORKERS_OK world={world} scenario={scenario}" in out.stdout, out.stdout[-2000:] + out.stderr[-6000:]
@@ -93,6 +93,10 @@ def test_single_pass_overflow_makes_every_worker_rerun_exactly(exchange_harness,
 @pytest.mark.parametrize("world", [1, 2, 3])
 def test_host_to_host_shuffle_in_chunks(exchange_harness, world):
     run(exchange_harness, world, "host")
+
+
+def test_a_missing_peer_is_an_error_after_a_bounded_wait_not_a_hang(exchange_harness):
+    run(exchange_harness, 3, "peer_missing", HARNESS_FLAG_TIMEOUT_MS="400")
 
 
 def test_workers_refuse_windows_of_different_sizes(exchange_harness):
