@@ -4,7 +4,7 @@ push transport and compare every (partition, producer) segment with the single-n
 
     python run_workers.py <harness.so> <world> <scenario> [seed]
 
-scenario: shuffle | stream | coalesce | broadcast | mismatch | onepass | onepass_overflow | host | peer_missing"""
+scenario: shuffle | stream | coalesce | broadcast | mismatch | onepass | onepass_overflow | host | peer_missing | mixed"""
 import ctypes as C
 import os
 import sys
@@ -172,7 +172,54 @@ def worker(lib, rank, world, uid, scenario, seed, errors, barrier):
                 rows_of[0] += cnt
 
         total = [0]
-        if scenario == "peer_missing":
+
+        def one_single_pass(data_seed):
+            tabs = [fixed_table(r, 900 + 11 * r, data_seed, False) for r in range(world)]
+            kp = []
+            cols_ = to_columns(tabs[rank], kp)
+            k1 = (C.c_int32 * 1)(0)
+            p1 = VP()
+            check(lib, lib.dfd_partitioner_create(ctx, N, k1, 1, None, C.byref(p1)), "dfd_partitioner_create")
+            d_ = [orc.partition_ids([t.column("key")], t.num_rows, N) for t in tabs]
+            o_ = (COL * tabs[rank].num_columns)()
+            check(lib, lib.dfd_shuffle_device_onepass(ex, p1, cols_, tabs[rank].num_columns, tabs[rank].num_rows, P, o_), "dfd_shuffle_device_onepass")
+            st_, ct_ = (C.c_int64 * (P * world))(), (C.c_int64 * (P * world))()
+            check(lib, lib.dfd_exchange_collect(ex, o_, st_, ct_), "dfd_exchange_collect")
+            for sgm in range(P * world):
+                r, q = sgm % world, sgm // world
+                want = tabs[r].take(pa.array(np.nonzero(d_[r] == rank * P + q)[0]))
+                assert int(ct_[sgm]) == want.num_rows
+                for c, f in enumerate(tabs[rank].schema):
+                    assert segment_to_arrow(o_[c], f, int(st_[sgm]), int(ct_[sgm])).equals(want.column(c).combine_chunks()), ("single pass", rank, sgm, f.name)
+            barrier.wait()
+            lib.dfd_partitioner_destroy(p1)
+
+        def one_push(data_seed):
+            tabs = [local_table(r, 400 + 13 * r, data_seed) for r in range(world)]
+            kp = []
+            cols_ = to_columns(tabs[rank], kp)
+            d_ = [orc.partition_ids([t.column("key"), t.column("s")], t.num_rows, N) for t in tabs]
+            o_ = nullable_outs(tabs[rank])
+            check(lib, lib.dfd_shuffle_device_onepass(ex, part, cols_, tabs[rank].num_columns, tabs[rank].num_rows, P, o_), "dfd_shuffle_device_onepass")
+            st_, ct_ = (C.c_int64 * (P * world))(), (C.c_int64 * (P * world))()
+            check(lib, lib.dfd_exchange_collect(ex, o_, st_, ct_), "dfd_exchange_collect")
+            for sgm in range(P * world):
+                r, q = sgm % world, sgm // world
+                want = tabs[r].take(pa.array(np.nonzero(d_[r] == rank * P + q)[0]))
+                assert int(ct_[sgm]) == want.num_rows
+                for c, f in enumerate(tabs[rank].schema):
+                    assert segment_to_arrow(o_[c], f, int(st_[sgm]), int(ct_[sgm])).equals(want.column(c).combine_chunks()), ("push", rank, sgm, f.name)
+            barrier.wait()
+
+        if scenario == "mixed":
+            # the transports share one window, one epoch counter and the done flags: alternate them on the same exchange
+            one_single_pass(seed)
+            one_push(seed + 1)
+            one_push(seed + 2)
+            one_single_pass(seed + 3)
+            one_single_pass(seed + 4)
+            one_push(seed + 5)
+        elif scenario == "peer_missing":
             # the last worker fails before the exchange (it never enters the collective): the others must come back with an error
             # after the bounded flag wait — never hang (the coordinator then cancels the stage, impl_execute_task.rs:138-155)
             if rank != world - 1:

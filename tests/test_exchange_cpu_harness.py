@@ -95,6 +95,11 @@ def test_host_to_host_shuffle_in_chunks(exchange_harness, world):
     run(exchange_harness, world, "host")
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_transports_alternate_on_one_window(exchange_harness, world):
+    run(exchange_harness, world, "mixed")
+
+
 def test_a_missing_peer_is_an_error_after_a_bounded_wait_not_a_hang(exchange_harness):
     run(exchange_harness, 3, "peer_missing", HARNESS_FLAG_TIMEOUT_MS="400")
 
