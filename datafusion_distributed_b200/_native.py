@@ -135,6 +135,7 @@ SIGNATURES = {
     "dfd_partitioner_collect": (C.c_int, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dfd_arrow_format_layout": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "dfd_schema_supported": (C.c_int, [C.POINTER(ArrowSchemaStruct)]),
+    "dfd_repartition_supported": (C.c_int, [_VP, C.POINTER(C.c_int32), C.c_int]),
     "dfd_repartition_exec_create": (C.c_int, [_VP, C.POINTER(ArrowSchemaStruct), C.POINTER(C.c_int32), C.c_int, C.c_uint32,
                                               C.POINTER(DfdExecOptions), C.POINTER(_VP)]),
     "dfd_repartition_exec_destroy": (None, [_VP]),

@@ -58,6 +58,10 @@ struct FieldInfo {
     size_t ow() const { return kind == DFD_COL_LARGE_UTF8 ? 8 : 4; }  // offset width of var-width kinds
 };
 
+// LargeBinary and FixedSizeBinary values are hashed by DataFusion as byte slices with a length prefix; the device hashes a
+// LARGE_UTF8 column as strings and a FIXED column as an integer: such columns travel as payload but cannot be hash keys.
+bool hashable_format(const char* f) { return f[0] != 'Z' && f[0] != 'w'; }
+
 // Arrow format string -> physical layout (Arrow C data interface, "Data type description")
 bool parse_format(const char* f, int32_t* kind, int32_t* width) {
     *kind = DFD_COL_FIXED;
@@ -71,6 +75,13 @@ bool parse_format(const char* f, int32_t* kind, int32_t* width) {
         case 'u': *kind = DFD_COL_UTF8; *width = 0; return f[1] == 0;
         case 'U': *kind = DFD_COL_LARGE_UTF8; *width = 0; return f[1] == 0;
         case 'z': *kind = DFD_COL_BINARY; *width = 0; return f[1] == 0;
+        case 'Z': *kind = DFD_COL_LARGE_UTF8; *width = 0; return f[1] == 0;  // LargeBinary MOVES like LargeUtf8 (int64 offsets + bytes); payload only
+        case 'w': {  // FixedSizeBinary(N), N in {1, 2, 4, 8, 16} (e.g. 16-byte UUIDs): N-byte values; payload only
+            int nb = 0;
+            if (sscanf(f, "w:%d", &nb) != 1 || (nb != 1 && nb != 2 && nb != 4 && nb != 8 && nb != 16)) return false;
+            *width = nb;
+            return true;
+        }
         case 'v':  // Utf8View / BinaryView: 16-byte views + variadic data buffers; hashed over the string bytes exactly like Utf8 / Binary
             if (f[1] == 'u' && f[2] == 0) { *kind = DFD_COL_UTF8; *width = 0; return true; }
             if (f[1] == 'z' && f[2] == 0) { *kind = DFD_COL_BINARY; *width = 0; return true; }
@@ -1038,25 +1049,52 @@ static bool list_child_ok(const ArrowSchema* c) {
     return v->format && (strcmp(v->format, "u") == 0 || strcmp(v->format, "z") == 0) && !v->dictionary && v->n_children == 0;
 }
 
+// One column of the record-batch schema: can the operator move it, and — if it is hash key `is_key` — hash it like DataFusion?
+static int check_column(const ArrowSchema* c, long long i, bool is_key) {
+    const char* name = c->name ? c->name : "";
+    int32_t k, w;
+    if (list_child_ok(c)) {  // List<Utf8 / Binary>: payload only
+        if (is_key) return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): list columns cannot be hash keys", i, name);
+        return DFD_OK;
+    }
+    if (!c->format || !parse_format(c->format, &k, &w))
+        return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): Arrow format '%s' is not supported", i, name, c->format ? c->format : "(null)");
+    if (c->dictionary) {  // Dictionary<integer index, flat values>: indices are scattered, the dictionary travels by reference
+        if (k != DFD_COL_FIXED || !strchr("cCsSiIlL", c->format[0]) || c->format[1])
+            return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): dictionary index type '%s' is not an integer", i, name, c->format);
+        int32_t dk, dw;
+        const ArrowSchema* d = c->dictionary;
+        if (d->dictionary || d->n_children > 0 || !d->format || !parse_format(d->format, &dk, &dw))
+            return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): dictionary value type '%s' is not supported", i, name, d->format ? d->format : "(null)");
+        if (is_key && d->format[0] == 'v')
+            return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): dictionary KEY with view-typed values is not supported", i, name);
+        if (is_key && !hashable_format(d->format))
+            return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): dictionary values of type '%s' cannot be hash keys", i, name, d->format);
+        return DFD_OK;
+    }
+    if (is_key && !hashable_format(c->format))
+        return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): columns of type '%s' travel as payload but cannot be hash keys", i, name, c->format);
+    return DFD_OK;
+}
+
 int dfd_schema_supported(const struct ArrowSchema* schema) {
     if (!schema || !schema->format || strcmp(schema->format, "+s") != 0)
         return set_error(DFD_ERR_INVALID_ARGUMENT, "schema must be a struct (record batch) schema");
+    for (int64_t i = 0; i < schema->n_children; ++i)
+        if (int rc = check_column(schema->children[i], (long long)i, false)) return rc;
+    return DFD_OK;
+}
+
+int dfd_repartition_supported(const struct ArrowSchema* schema, const int32_t* key_cols, int n_keys) {
+    if (!schema || !schema->format || strcmp(schema->format, "+s") != 0)
+        return set_error(DFD_ERR_INVALID_ARGUMENT, "schema must be a struct (record batch) schema");
+    if (n_keys < 1 || n_keys > MAX_KEYS || !key_cols) return set_error(DFD_ERR_INVALID_ARGUMENT, "n_keys %d not in [1, %d]", n_keys, MAX_KEYS);
+    for (int k = 0; k < n_keys; ++k)
+        if (key_cols[k] < 0 || key_cols[k] >= schema->n_children) return set_error(DFD_ERR_INVALID_ARGUMENT, "key column index out of range");
     for (int64_t i = 0; i < schema->n_children; ++i) {
-        const ArrowSchema* c = schema->children[i];
-        int32_t k, w;
-        if (list_child_ok(c)) continue;  // List<Utf8 / Binary> payload (as a KEY it is refused when the operator is created)
-        if (!c->format || !parse_format(c->format, &k, &w))
-            return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): Arrow format '%s' is not supported", (long long)i, c->name ? c->name : "",
-                             c->format ? c->format : "(null)");
-        if (c->dictionary) {  // Dictionary<integer index, flat values>: indices are scattered, the dictionary travels by reference
-            if (k != DFD_COL_FIXED || !strchr("cCsSiIlL", c->format[0]) || c->format[1])
-                return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): dictionary index type '%s' is not an integer", (long long)i, c->name ? c->name : "", c->format);
-            int32_t dk, dw;
-            const ArrowSchema* d = c->dictionary;
-            if (d->dictionary || d->n_children > 0 || !d->format || !parse_format(d->format, &dk, &dw))
-                return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): dictionary value type '%s' is not supported", (long long)i, c->name ? c->name : "",
-                                 d->format ? d->format : "(null)");
-        }
+        bool is_key = false;
+        for (int k = 0; k < n_keys; ++k) is_key |= key_cols[k] == i;
+        if (int rc = check_column(schema->children[i], (long long)i, is_key)) return rc;
     }
     return DFD_OK;
 }
@@ -1068,6 +1106,11 @@ int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, 
     if (!schema->format || strcmp(schema->format, "+s") != 0)
         return set_error(DFD_ERR_INVALID_ARGUMENT, "schema must be a struct (record batch) schema, got format '%s'",
                          schema->format ? schema->format : "(null)");
+    for (int64_t i = 0; i < schema->n_children; ++i) {  // (the same checks the plan hook runs through dfd_repartition_supported)
+        bool is_key = false;
+        for (int k = 0; k < n_keys; ++k) is_key |= key_cols && key_cols[k] == i;
+        if (int rc = check_column(schema->children[i], (long long)i, is_key)) return rc;
+    }
     std::unique_ptr<dfd_repartition_exec> x(new (std::nothrow) dfd_repartition_exec());
     if (!x) return set_error(DFD_ERR_OOM, "out of host memory");
     x->ctx = ctx;

@@ -254,7 +254,9 @@ int dfd_partitioner_collect(dfd_partitioner* p, int64_t* part_starts_host, int64
  * columns (element lengths + the list's validity, element bytes, element
  * validity), scatters them with the ordinary variable-width kernels, rebuilds
  * the child offsets with a device scan and exports nested Arrow arrays; as a
- * hash KEY a list is refused at create time.  Other nested types (Struct, Map,
+ * hash KEY a list is refused at create time.  LargeBinary and FixedSizeBinary of
+ * 1 / 2 / 4 / 8 / 16 bytes (UUIDs) also move as payload only (DataFusion hashes
+ * them as byte slices).  Other nested types (Struct, Map,
  * List of anything else): DFD_ERR_UNSUPPORTED. */
 typedef struct dfd_repartition_exec dfd_repartition_exec;
 
@@ -263,13 +265,19 @@ typedef struct dfd_repartition_exec dfd_repartition_exec;
  * (`Worker::add_on_plan_hook`, src/worker/worker_service.rs:91-96):
  *   dfd_arrow_format_layout : Arrow C format string -> (dfd_col_kind, value width);
  *                             DFD_ERR_UNSUPPORTED for formats with no flat layout
- *                             (nested types, 256-bit decimals, fixed-size binary ...).
+ *                             (nested types, 256-bit decimals, FixedSizeBinary of other than 1/2/4/8/16 bytes ...).
+ *                             LargeBinary reports the LargeUtf8 layout (int64 offsets + bytes: how it MOVES).
  *   dfd_schema_supported    : DFD_OK iff every column of the record-batch schema is
  *                             supported — flat columns, views, Dictionary<integer, flat>
  *                             and List<Utf8 / Binary>; otherwise DFD_ERR_UNSUPPORTED with
- *                             the reason in dfd_last_error(). */
+ *                             the reason in dfd_last_error().
+ *   dfd_repartition_supported : the same with the hash KEY columns taken into account — what the hook should ask before
+ *                             swapping a RepartitionExec(Hash(keys, n)): lists, LargeBinary and FixedSizeBinary(1/2/4/8/16)
+ *                             columns travel as payload but cannot be hash keys (DataFusion hashes them as byte slices),
+ *                             nor can dictionaries with view-typed values.  dfd_repartition_exec_create applies the same checks. */
 int dfd_arrow_format_layout(const char* format, int32_t* kind, int32_t* width);
 int dfd_schema_supported(const struct ArrowSchema* schema);
+int dfd_repartition_supported(const struct ArrowSchema* schema, const int32_t* key_cols, int n_keys);
 
 typedef struct {
     int64_t chunk_rows;         /* rows per device chunk; 0 = 4Mi                   */

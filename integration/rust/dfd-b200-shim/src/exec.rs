@@ -127,10 +127,11 @@ pub fn hash_key_columns(partitioning: &Partitioning) -> Option<(Vec<i32>, usize)
     }
 }
 
-/// Pure host check (no GPU call): `dfd_schema_supported`.
-pub fn schema_supported(schema: &SchemaRef) -> bool {
+/// Pure host check (no GPU call): `dfd_repartition_supported` — every column can be moved and every KEY column hashed the
+/// way DataFusion hashes it.
+pub fn repartition_supported(schema: &SchemaRef, key_columns: &[i32]) -> bool {
     match FFI_ArrowSchema::try_from(schema.as_ref()) {
-        Ok(s) => unsafe { ffi::dfd_schema_supported(&s) == ffi::DFD_OK },
+        Ok(s) => unsafe { ffi::dfd_repartition_supported(&s, key_columns.as_ptr(), key_columns.len() as i32) == ffi::DFD_OK },
         Err(_) => false,
     }
 }
@@ -140,7 +141,7 @@ impl GpuRepartitionExec {
     /// unsupported column types): the hook then leaves the node alone.
     pub fn try_from_repartition(r: &RepartitionExec, ctx: Arc<GpuContext>, options: GpuRepartitionOptions) -> Option<Self> {
         let (key_columns, num_partitions) = hash_key_columns(r.partitioning())?;
-        if !schema_supported(&r.schema()) {
+        if !repartition_supported(&r.schema(), &key_columns) {
             return None;
         }
         Some(Self {

@@ -60,6 +60,8 @@ extern "C" {
     pub fn dfd_ctx_destroy(ctx: *mut dfd_ctx);
     /// Pure host predicate (no GPU touched): can the GPU operator move every column of this record-batch schema?
     pub fn dfd_schema_supported(schema: *const FFI_ArrowSchema) -> c_int;
+    /// The same with the hash key columns taken into account (lists / LargeBinary / FixedSizeBinary move as payload only).
+    pub fn dfd_repartition_supported(schema: *const FFI_ArrowSchema, key_cols: *const i32, n_keys: c_int) -> c_int;
     /// `RepartitionExec::try_new(input, Partitioning::Hash(cols, n))` (network_shuffle.rs:126-134)
     pub fn dfd_repartition_exec_create(
         ctx: *mut dfd_ctx,

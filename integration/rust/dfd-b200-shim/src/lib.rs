@@ -5,7 +5,7 @@
 //!   GPU operator (`dfd_repartition_exec_*`).
 //! * [`install_gpu_repartition_hook`] — `Worker::add_on_plan_hook` (src/worker/worker_service.rs:91-96, applied at
 //!   src/worker/impl_set_plan.rs:122-124): every stage-head hash `RepartitionExec` whose keys are plain columns and whose
-//!   schema `dfd_schema_supported` accepts is swapped one-for-one (no node added or removed, as the hook's contract asks).
+//!   schema and keys `dfd_repartition_supported` accepts is swapped one-for-one (no node added or removed, as the hook's contract asks).
 //!
 //! * [`GpuRepartitionCodec`] — `PhysicalExtensionCodec` for the node, for deployments that place it on the coordinator
 //!   instead of through the worker hook.

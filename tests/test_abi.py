@@ -93,7 +93,11 @@ def test_schema_support_helpers_run_without_a_gpu(built):
     for fmt, (kind, width) in {b"vu": (2, 0), b"vz": (4, 0)}.items():  # Utf8View / BinaryView move as Utf8 / Binary on the device
         k, w = C.c_int32(-1), C.c_int32(-1)
         assert L.dfd_arrow_format_layout(fmt, C.byref(k), C.byref(w)) == 0 and (k.value, w.value) == (kind, width), fmt
-    for fmt in (b"+l", b"+s", b"d:76,0,256", b"w:16", b"n", b"Z"):
+    # LargeBinary moves like LargeUtf8 (int64 offsets + bytes), FixedSizeBinary(1/2/4/8/16) like an N-byte value: payload only
+    for fmt, (kind, width) in {b"Z": (3, 0), b"w:16": (0, 16), b"w:4": (0, 4)}.items():
+        k, w = C.c_int32(-1), C.c_int32(-1)
+        assert L.dfd_arrow_format_layout(fmt, C.byref(k), C.byref(w)) == 0 and (k.value, w.value) == (kind, width), fmt
+    for fmt in (b"+l", b"+s", b"d:76,0,256", b"w:12", b"w:32", b"n"):
         assert L.dfd_arrow_format_layout(fmt, None, None) == 6, fmt  # DFD_ERR_UNSUPPORTED
 
     def supported(schema):
@@ -123,3 +127,22 @@ def test_schema_support_helpers_run_without_a_gpu(built):
     assert st == 6 and "nums" in why
     st, why = supported(pa.schema([("id", pa.int64()), ("s", pa.struct([("a", pa.int32())]))]))
     assert st == 6 and "s" in why
+
+    # dfd_repartition_supported: the same, with the hash keys taken into account (what the plan hook asks)
+    def repartition_supported(schema, keys):
+        cs = nv.ArrowSchemaStruct()
+        schema._export_to_c(C.addressof(cs))
+        try:
+            return L.dfd_repartition_supported(C.byref(cs), (C.c_int32 * len(keys))(*keys), len(keys)), L.dfd_last_error().decode()
+        finally:
+            C.CFUNCTYPE(None, C.c_void_p)(cs.release)(C.addressof(cs))
+
+    wide = pa.schema([("id", pa.int64()), ("uuid", pa.binary(16)), ("blob", pa.large_binary()), ("tags", pa.list_(pa.string())), ("label", pa.string_view()),
+                      ("cat", pa.dictionary(pa.int32(), pa.string())), ("dv", pa.dictionary(pa.int32(), pa.string_view())),
+                      ("db", pa.dictionary(pa.int16(), pa.large_binary()))])
+    assert supported(wide)[0] == 0
+    assert repartition_supported(wide, [0])[0] == 0 and repartition_supported(wide, [0, 4, 5])[0] == 0
+    for key, word in ((1, "payload"), (2, "payload"), (3, "list"), (6, "view-typed"), (7, "dictionary values")):
+        st, why = repartition_supported(wide, [0, key])
+        assert st == 6 and word in why, (key, why)
+    assert repartition_supported(wide, [9])[0] == 1 and repartition_supported(wide, [])[0] == 1  # DFD_ERR_INVALID_ARGUMENT

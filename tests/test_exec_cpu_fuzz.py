@@ -66,6 +66,15 @@ def _column(rnd, rng, kind, n):
         vals[rnd.randrange(n)] = rnd.randbytes(21)
         p = pa.array(vals, type=pa.binary())
         return p.cast(pa.binary_view()), p, False
+    if kind == "large_binary?":
+        a = pa.array([None if rnd.random() < 0.1 else rnd.randbytes(rnd.randint(0, 25)) for _ in range(n)], type=pa.large_binary())
+        return a, a, False  # payload only: DataFusion hashes it as a byte slice
+    if kind == "uuid":
+        a = pa.array([rnd.randbytes(16) for _ in range(n)], type=pa.binary(16))
+        return a, a, False
+    if kind == "fsb4?":
+        a = pa.array([None if rnd.random() < 0.1 else rnd.randbytes(4) for _ in range(n)], type=pa.binary(4))
+        return a, a, False
     if kind.startswith("dict"):
         index_type = {"dict8": pa.int8(), "dict16": pa.int16(), "dict32": pa.int32()}[kind]
         # the dictionary CHANGES along the column: pieces with their own values (the operator cuts its chunk there)
@@ -94,7 +103,7 @@ def _column(rnd, rng, kind, n):
 
 
 KINDS = ["i64", "i32?", "u8", "f64", "bool?", "date32", "dec128?", "utf8?", "large_utf8", "binary?", "string_view?", "binary_view", "dict8", "dict16",
-         "dict32", "list<utf8>?", "list<binary>"]
+         "dict32", "list<utf8>?", "list<binary>", "large_binary?", "uuid", "fsb4?"]
 
 
 @pytest.mark.parametrize("seed", range(24))

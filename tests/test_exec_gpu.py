@@ -449,3 +449,32 @@ def test_pinned_chunks_are_reused_by_the_next_operator_of_the_same_shape(ctx):
     _, st4 = run(table.select(["k", "a"]), 32_768)
     assert st4["pinned_chunks_reused"] == 0
     assert st4["ns_push"] > 0
+
+
+def test_large_binary_and_fixed_size_binary_travel_as_payload(ctx):
+    """LargeBinary (int64 offsets + bytes) and FixedSizeBinary(16) / (4) — UUIDs — move through the operator as payload with
+    their types intact; as hash KEYS they are refused when the operator is created (DataFusion hashes them as byte slices,
+    which the device does not do for these layouts)."""
+    rnd = random.Random(21)
+    n, N = 30_000, 6
+    key = pa.array([rnd.getrandbits(40) for _ in range(n)], type=pa.int64())
+    uuid = pa.array([rnd.randbytes(16) for _ in range(n)], type=pa.binary(16))
+    tag4 = pa.array([None if rnd.random() < 0.1 else rnd.randbytes(4) for _ in range(n)], type=pa.binary(4))
+    blob = pa.array([None if rnd.random() < 0.1 else rnd.randbytes(rnd.randint(0, 40)) for _ in range(n)], type=pa.large_binary())
+    table = pa.table([key, uuid, tag4, blob], names=["key", "uuid", "tag4", "blob"])
+    ex = dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash([0], N), chunk_rows=8_192)
+    for rb in table.to_batches(max_chunksize=3_000):
+        ex.push_batch(rb)
+    ex.finish()
+    outs = collect(ex, N)
+    dest = orc.partition_ids([key], n, N)
+    order, starts = expected_partitions(dest, N)
+    for p in range(N):
+        want = table.take(pa.array(order[starts[p]:starts[p + 1]]))
+        assert outs[p].schema.equals(table.schema), p
+        assert outs[p].equals(want), p
+    ex.close()
+    for bad_key in (1, 2, 3):
+        with pytest.raises(dfd.DfdError) as e:
+            dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash([0, bad_key], N))
+        assert e.value.status == 6 and "cannot be hash keys" in str(e.value)
