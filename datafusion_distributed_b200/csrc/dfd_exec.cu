@@ -49,6 +49,7 @@ struct FieldInfo {
     int owner = -1, role = 0;  // hidden columns: the list field they belong to; role 1 = lengths, 2 = bytes, 3 = element validity
     std::string child_name, child_format;
     int64_t child_flags = 0;
+    int32_t child_width = 0;       // list child: 0 = Utf8 / Binary (offsets + bytes), > 0 = fixed-width primitive of that many bytes
     bool nodev() const { return list; }
     bool dict = false;             // dictionary-encoded: `format` is the index type, dict_* describe the values
     std::string dict_format;
@@ -576,11 +577,11 @@ int emit_slot(dfd_repartition_exec* x, Slot& s) {
                 ArrowArray& g = bp->grand[c];
                 memset(&g, 0, sizeof g);
                 bp->grand_bufs[3 * c] = f.h_valid >= 0 ? oc->values[(size_t)f.h_valid] : nullptr;
-                bp->grand_bufs[3 * c + 1] = oc->values[hl];
+                bp->grand_bufs[3 * c + 1] = f.child_width > 0 ? oc->values[hb] : oc->values[hl];  // primitive child: [validity, values]
                 bp->grand_bufs[3 * c + 2] = oc->values[hb];
                 g.length = s.data_bytes[hl] / 4;
                 g.null_count = f.h_valid >= 0 ? -1 : 0;
-                g.n_buffers = 3;
+                g.n_buffers = f.child_width > 0 ? 2 : 3;
                 g.buffers = &bp->grand_bufs[3 * c];
                 g.release = child_release;
                 bp->grand_ptrs[c] = &g;
@@ -717,10 +718,15 @@ int flush_current(dfd_repartition_exec* x) {
         int rc2 = s.list_tmp[i].ensure(total, c->device);
         if (rc2) return fail(x, rc2, dfd_last_error());
         char* lt = (char*)s.list_tmp[i].ptr;
-        if ((rc2 = launch_lengths_to_offsets(s.d_out[(size_t)f.h_len], 4, ne, (unsigned long long*)(lt + o_sums), lt + o_off, c->stream)))
-            return fail(x, rc2, dfd_last_error());
-        d2h_src[(size_t)f.h_len] = lt + o_off;
-        d2h_nb[(size_t)f.h_len] = (size_t)(ne + 1) * 4;
+        if (f.child_width > 0) {  // primitive child: no child offsets; the gathered lengths themselves are not needed on the host
+            d2h_src[(size_t)f.h_len] = lt + o_off;
+            d2h_nb[(size_t)f.h_len] = 0;
+        } else {
+            if ((rc2 = launch_lengths_to_offsets(s.d_out[(size_t)f.h_len], 4, ne, (unsigned long long*)(lt + o_sums), lt + o_off, c->stream)))
+                return fail(x, rc2, dfd_last_error());
+            d2h_src[(size_t)f.h_len] = lt + o_off;
+            d2h_nb[(size_t)f.h_len] = (size_t)(ne + 1) * 4;
+        }
         if (f.h_valid >= 0) {
             if ((rc2 = launch_bytes_to_bits((const uint8_t*)s.d_out[(size_t)f.h_valid], ne, lt + o_bits, c->stream))) return fail(x, rc2, dfd_last_error());
             d2h_src[(size_t)f.h_valid] = lt + o_bits;
@@ -816,11 +822,13 @@ int prepare_rows(dfd_repartition_exec* x, const ArrowArray* b, int64_t start, in
             if (c->n_children != 1 || !c->children[0]) return fail(x, DFD_ERR_INVALID_ARGUMENT, "column " + f.name + ": list array without a child");
             const ArrowArray* v = c->children[0];
             const int32_t* loff = (const int32_t*)c->buffers[1];
-            const int32_t* coff = (const int32_t*)v->buffers[1] + v->offset;
+            const int32_t cw = f.child_width;
+            const int32_t* coff = cw > 0 ? nullptr : (const int32_t*)v->buffers[1] + v->offset;
             const uint8_t* cvalid = validity_of(v);
             const int64_t e0 = loff[lo], e1 = loff[lo + n], ne = e1 - e0;
             if (ne < 0) return fail(x, DFD_ERR_INVALID_ARGUMENT, "column " + f.name + ": list offsets are not monotonic");
-            if (ne * 4 > 0x7fffffffLL) return fail(x, DFD_ERR_UNSUPPORTED, "column " + f.name + ": too many list elements in one chunk");
+            if (ne * 4 > 0x7fffffffLL || ne * (int64_t)(cw > 0 ? cw : 1) > 0x7fffffffLL)
+                return fail(x, DFD_ERR_UNSUPPORTED, "column " + f.name + ": too many list elements in one chunk");
             const size_t hl = (size_t)f.h_len, hb = (size_t)f.h_bytes;
             std::vector<char>& ol = x->tmp_off[hl];
             std::vector<char>& dl = x->tmp_bytes[hl];
@@ -838,9 +846,14 @@ int prepare_rows(dfd_repartition_exec* x, const ArrowArray* b, int64_t start, in
                 ov32 = (int32_t*)ov.data();
                 dvb = dv.data();
             }
-            dfd::host::split_list_rows(loff, coff, cvalid, v->offset, lo, n, (int32_t*)ol.data(), (int32_t*)ob.data(), (int32_t*)dl.data(), ov32, dvb);
+            if (cw > 0) {
+                dfd::host::split_list_rows_fixed(loff, cw, cvalid, v->offset, lo, n, (int32_t*)ol.data(), (int32_t*)ob.data(), (int32_t*)dl.data(), ov32, dvb);
+                x->prep[hb] = VarPrep{ob.data(), 0, (const char*)v->buffers[1] + (size_t)(v->offset + e0) * (size_t)cw, ne * (int64_t)cw};
+            } else {
+                dfd::host::split_list_rows(loff, coff, cvalid, v->offset, lo, n, (int32_t*)ol.data(), (int32_t*)ob.data(), (int32_t*)dl.data(), ov32, dvb);
+                x->prep[hb] = VarPrep{ob.data(), 0, (const char*)v->buffers[2] + coff[e0], (int64_t)coff[e1] - coff[e0]};
+            }
             x->prep[hl] = VarPrep{ol.data(), 0, dl.data(), ne * 4};
-            x->prep[hb] = VarPrep{ob.data(), 0, (const char*)v->buffers[2] + coff[e0], (int64_t)coff[e1] - coff[e0]};
             if (f.h_valid >= 0) x->prep[(size_t)f.h_valid] = VarPrep{(const char*)ov32, 0, dvb, ne};
         } else if (f.var() && f.view) {
             // Utf8View / BinaryView -> offsets + contiguous bytes (16-byte views: len | 12 inline bytes, or len | prefix |
@@ -1042,11 +1055,18 @@ int dfd_arrow_format_layout(const char* format, int32_t* kind, int32_t* width) {
     return DFD_OK;
 }
 
-// List<Utf8> / List<Binary> (int32 list offsets, int32 child offsets): the one nested shape the shuffle path moves (payload only)
-static bool list_child_ok(const ArrowSchema* c) {
+// List<Utf8> / List<Binary> / List<fixed-width primitive> (int32 list offsets): the nested shapes the shuffle path moves
+// (payload only).  *child_width = 0 for string children, the value width for primitive ones (array_agg / median states).
+static bool list_child_ok(const ArrowSchema* c, int32_t* child_width = nullptr) {
     if (!c->format || strcmp(c->format, "+l") != 0 || c->n_children != 1 || !c->children || !c->children[0]) return false;
     const ArrowSchema* v = c->children[0];
-    return v->format && (strcmp(v->format, "u") == 0 || strcmp(v->format, "z") == 0) && !v->dictionary && v->n_children == 0;
+    if (!v->format || v->dictionary || v->n_children != 0) return false;
+    int32_t k = 0, w = 0;
+    if (strcmp(v->format, "u") == 0 || strcmp(v->format, "z") == 0) w = 0;
+    else if (parse_format(v->format, &k, &w) && k == DFD_COL_FIXED && v->format[0] != 'w') { /* ints, floats, decimals, dates, times */ }
+    else return false;
+    if (child_width) *child_width = w;
+    return true;
 }
 
 // One column of the record-batch schema: can the operator move it, and — if it is hash key `is_key` — hash it like DataFusion?
@@ -1124,9 +1144,11 @@ int dfd_repartition_exec_create(dfd_ctx* ctx, const struct ArrowSchema* schema, 
         int key_index = -1;
         for (int k = 0; k < n_keys; ++k)
             if (key_cols && key_cols[k] == i) key_index = k;
-        if (list_child_ok(c)) {
+        int32_t child_width = 0;
+        if (list_child_ok(c, &child_width)) {
             if (key_index >= 0) return set_error(DFD_ERR_UNSUPPORTED, "column %lld (%s): list columns cannot be hash keys", (long long)i, f.name.c_str());
             f.list = true;
+            f.child_width = child_width;
             f.kind = -1;
             f.width = 0;
             f.child_name = c->children[0]->name ? c->children[0]->name : "item";

@@ -129,5 +129,29 @@ inline int64_t split_list_rows(const int32_t* loff, const int32_t* coff, const u
     return ne;
 }
 
+// List<fixed-width primitive> rows (child values of `w` bytes, no child offsets): the same three hidden columns — every element
+// still owns one int32 in the LENGTHS column (its value, w, is not used: the column is what carries the per-row element counts
+// and the list's validity through the scatter), the BYTES column is the rows' contiguous ranges of the child's values buffer.
+inline int64_t split_list_rows_fixed(const int32_t* loff, int32_t w, const uint8_t* cvalid, int64_t cvalid_offset, int64_t lo, int64_t n, int32_t* len_off,
+                                     int32_t* bytes_off, int32_t* lengths, int32_t* valid_off, char* valid_bytes) {
+    const int64_t e0 = loff[lo], e1 = loff[lo + n], ne = e1 - e0;
+    for (int64_t r = 0; r <= n; ++r) {
+        const int64_t k = (int64_t)loff[lo + r] - e0;
+        len_off[r] = (int32_t)(4 * k);
+        bytes_off[r] = (int32_t)(k * w);
+        if (valid_off) valid_off[r] = (int32_t)k;
+    }
+    for (int64_t k = 0; k < ne; ++k) lengths[k] = w;
+    if (valid_off) {
+        if (!cvalid) {
+            memset(valid_bytes, 1, (size_t)ne);
+        } else {
+            const int64_t first = cvalid_offset + e0;
+            for (int64_t k = 0; k < ne; ++k) valid_bytes[k] = (char)((cvalid[(first + k) >> 3] >> ((first + k) & 7)) & 1);
+        }
+    }
+    return ne;
+}
+
 }  // namespace host
 }  // namespace dfd

@@ -254,10 +254,12 @@ int dfd_partitioner_collect(dfd_partitioner* p, int64_t* part_starts_host, int64
  * columns (element lengths + the list's validity, element bytes, element
  * validity), scatters them with the ordinary variable-width kernels, rebuilds
  * the child offsets with a device scan and exports nested Arrow arrays; as a
- * hash KEY a list is refused at create time.  LargeBinary and FixedSizeBinary of
+ * hash KEY a list is refused at create time.  List<fixed-width primitive> (the
+ * partial states of array_agg / median) moves the same way, without child offsets.
+ * LargeBinary and FixedSizeBinary of
  * 1 / 2 / 4 / 8 / 16 bytes (UUIDs) also move as payload only (DataFusion hashes
  * them as byte slices).  Other nested types (Struct, Map,
- * List of anything else): DFD_ERR_UNSUPPORTED. */
+ * List of lists / booleans / dictionaries): DFD_ERR_UNSUPPORTED. */
 typedef struct dfd_repartition_exec dfd_repartition_exec;
 
 /* Pure host helpers (no GPU needed) for the plan hook that decides whether a stage-head

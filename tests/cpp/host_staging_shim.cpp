@@ -15,4 +15,8 @@ int64_t t_split_list_rows(const int32_t* loff, const int32_t* coff, const uint8_
                           int32_t* bytes_off, int32_t* lengths, int32_t* valid_off, char* valid_bytes) {
     return dfd::host::split_list_rows(loff, coff, cvalid, cvalid_offset, lo, n, len_off, bytes_off, lengths, valid_off, valid_bytes);
 }
+int64_t t_split_list_rows_fixed(const int32_t* loff, int32_t w, const uint8_t* cvalid, int64_t cvalid_offset, int64_t lo, int64_t n, int32_t* len_off,
+                                int32_t* bytes_off, int32_t* lengths, int32_t* valid_off, char* valid_bytes) {
+    return dfd::host::split_list_rows_fixed(loff, w, cvalid, cvalid_offset, lo, n, len_off, bytes_off, lengths, valid_off, valid_bytes);
+}
 }

@@ -123,8 +123,11 @@ def test_schema_support_helpers_run_without_a_gpu(built):
                          ("category", pa.dictionary(pa.int32(), pa.string())), pa.field("raw", pa.uint8(), False),
                          pa.field("ts", pa.timestamp("ns"), False), pa.field("count", pa.int32(), False), ("tags", pa.list_(pa.string()))])
     assert supported(fixture)[0] == 0
-    st, why = supported(pa.schema([("id", pa.int64()), ("nums", pa.list_(pa.int32()))]))
-    assert st == 6 and "nums" in why
+    assert supported(pa.schema([("id", pa.int64()), ("nums", pa.list_(pa.int32())), ("xs", pa.list_(pa.float64()))]))[0] == 0  # primitive children too
+    st, why = supported(pa.schema([("id", pa.int64()), ("nested", pa.list_(pa.list_(pa.int32())))]))
+    assert st == 6 and "nested" in why
+    st, why = supported(pa.schema([("id", pa.int64()), ("flags", pa.list_(pa.bool_()))]))
+    assert st == 6 and "flags" in why
     st, why = supported(pa.schema([("id", pa.int64()), ("s", pa.struct([("a", pa.int32())]))]))
     assert st == 6 and "s" in why
 

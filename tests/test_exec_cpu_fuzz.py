@@ -88,6 +88,16 @@ def _column(rnd, rng, kind, n):
         # (pyarrow cannot unify dictionaries that hold null values: the expectation works on the decoded strings, which is also
         # what DataFusion's hash_dictionary hashes)
         return pa.chunked_array(pieces), pa.chunked_array([p.dictionary_decode() for p in pieces]), True
+    if kind in ("list<i64>?", "list<f32>"):
+        prim = kind == "list<f32>"
+        rows = []
+        for _ in range(n):
+            if not prim and rnd.random() < 0.1:
+                rows.append(None)
+            else:
+                rows.append([float(rnd.randint(-99, 99)) / 4 if prim else (None if rnd.random() < 0.2 else rnd.getrandbits(50)) for _ in range(rnd.randint(0, 4))])
+        a = pa.array(rows, type=pa.list_(pa.float32() if prim else pa.int64()))
+        return a, a, False
     if kind in ("list<utf8>?", "list<binary>"):
         binary = kind == "list<binary>"
         rows = []
@@ -103,7 +113,7 @@ def _column(rnd, rng, kind, n):
 
 
 KINDS = ["i64", "i32?", "u8", "f64", "bool?", "date32", "dec128?", "utf8?", "large_utf8", "binary?", "string_view?", "binary_view", "dict8", "dict16",
-         "dict32", "list<utf8>?", "list<binary>", "large_binary?", "uuid", "fsb4?"]
+         "dict32", "list<utf8>?", "list<binary>", "large_binary?", "uuid", "fsb4?", "list<i64>?", "list<f32>"]
 
 
 @pytest.mark.parametrize("seed", range(24))

@@ -170,6 +170,7 @@ CASES = [
     ("test_bounded_pinned_pool_blocks_the_producer_until_consumers_release", {}),
     ("test_pinned_chunks_are_reused_by_the_next_operator_of_the_same_shape", {}),
     ("test_large_binary_and_fixed_size_binary_travel_as_payload", {}),
+    ("test_lists_of_primitives_travel_as_payload", {}),
 ]
 
 

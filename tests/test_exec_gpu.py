@@ -119,7 +119,10 @@ def test_operator_errors(ctx):
         dfd.RepartitionExec(ctx, pa.schema([("s", pa.list_(pa.string()))]), dfd.Partitioning.Hash([0], 4))
     assert e.value.status == 6  # DFD_ERR_UNSUPPORTED
     with pytest.raises(dfd.DfdError) as e:  # other nested types are still out of scope
-        dfd.RepartitionExec(ctx, pa.schema([("k", pa.int64()), ("s", pa.list_(pa.int32()))]), dfd.Partitioning.Hash([0], 4))
+        dfd.RepartitionExec(ctx, pa.schema([("k", pa.int64()), ("s", pa.list_(pa.list_(pa.int32())))]), dfd.Partitioning.Hash([0], 4))
+    assert e.value.status == 6
+    with pytest.raises(dfd.DfdError) as e:
+        dfd.RepartitionExec(ctx, pa.schema([("k", pa.int64()), ("s", pa.struct([("a", pa.int32())]))]), dfd.Partitioning.Hash([0], 4))
     assert e.value.status == 6
     sch = pa.schema([("k", pa.int64())])
     with pytest.raises(dfd.DfdError):
@@ -478,3 +481,46 @@ def test_large_binary_and_fixed_size_binary_travel_as_payload(ctx):
         with pytest.raises(dfd.DfdError) as e:
             dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash([0, bad_key], N))
         assert e.value.status == 6 and "cannot be hash keys" in str(e.value)
+
+
+def test_lists_of_primitives_travel_as_payload(ctx):
+    """List<Int64> / List<Float32> / List<Decimal128> (the partial states of array_agg / median) through the operator: nullable
+    lists, nullable elements, empty lists, sliced batches — every destination equals the oracle's rows in order."""
+    import decimal
+
+    rnd = random.Random(33)
+    n, N = 20_000, 5
+    key = pa.array([rnd.getrandbits(40) for _ in range(n)], type=pa.int64())
+
+    def lists(make, typ, null_rows, null_elems):
+        rows = []
+        for _ in range(n):
+            if rnd.random() < null_rows:
+                rows.append(None)
+            else:
+                rows.append([None if rnd.random() < null_elems else make() for _ in range(rnd.choice([0, 0, 1, 2, 5]))])
+        return pa.array(rows, type=pa.list_(typ))
+
+    l64 = lists(lambda: rnd.getrandbits(60) - (1 << 59), pa.int64(), 0.1, 0.15)
+    f32 = lists(lambda: float(rnd.randint(-1000, 1000)) / 8, pa.float32(), 0.0, 0.0)
+    dec = lists(lambda: decimal.Decimal(rnd.randint(-10**12, 10**12)).scaleb(-2), pa.decimal128(18, 2), 0.05, 0.1)
+    table = pa.table([key, l64, f32, dec], names=["key", "l64", "f32", "dec"])
+    ex = dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash([0], N), chunk_rows=4_096)
+    cuts = [0, 7, 3_000, 3_001, 11_111, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        for rb in table.slice(a, b - a).to_batches(max_chunksize=1_500):
+            ex.push_batch(rb)
+    ex.finish()
+    outs = collect(ex, N)
+    dest = orc.partition_ids([key], n, N)
+    order, starts = expected_partitions(dest, N)
+    for p in range(N):
+        want = table.take(pa.array(order[starts[p]:starts[p + 1]]))
+        assert outs[p].schema.equals(table.schema), p
+        outs[p].validate(full=True)
+        for name in table.column_names:
+            assert outs[p].column(name).combine_chunks().equals(want.column(name).combine_chunks()), (p, name)
+    ex.close()
+    with pytest.raises(dfd.DfdError) as e:
+        dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash([1], N))
+    assert e.value.status == 6

@@ -174,3 +174,35 @@ def test_list_rows_with_a_sliced_child_array(shim):
     data = np.frombuffer(cb[2], dtype=np.uint8)
     start = int(coff[e0])
     assert data[start:start + int(bytes_off[n])].tobytes() == "".join(e for e in elems if e is not None).encode()
+
+
+def test_list_of_primitives_rows_split(shim):
+    """List<Int64> rows -> element counts (through the lengths column's offsets), the rows' byte ranges of the child values and one
+    validity byte per element, with a sliced list and a sliced child."""
+    rnd = random.Random(13)
+    pool = pa.array([None if rnd.random() < 0.2 else rnd.getrandbits(40) for _ in range(500)], type=pa.int64())
+    k = 11
+    child = pool.slice(k)
+    sizes = [rnd.randint(0, 4) for _ in range(120)]
+    offs = np.zeros(len(sizes) + 1, dtype=np.int32)
+    np.cumsum(sizes, out=offs[1:])
+    arr = pa.ListArray.from_arrays(pa.array(offs), child)
+    rows = arr.to_pylist()
+    lo, n, w = 9, 100, 8
+    loff = np.frombuffer(arr.buffers()[1], dtype=np.int32)
+    cb = arr.values.buffers()
+    cvalid = np.frombuffer(cb[0], dtype=np.uint8)
+    e0, e1 = int(loff[lo]), int(loff[lo + n])
+    ne = e1 - e0
+    len_off, bytes_off, valid_off = (np.empty(n + 1, dtype=np.int32) for _ in range(3))
+    lengths, valid_bytes = np.empty(ne + 4, dtype=np.int32), np.empty(ne + 16, dtype=np.uint8)
+    shim.t_split_list_rows_fixed.restype = C.c_int64
+    assert shim.t_split_list_rows_fixed(ptr(loff), C.c_int32(w), ptr(cvalid), C.c_int64(k), C.c_int64(lo), C.c_int64(n), ptr(len_off), ptr(bytes_off),
+                                        ptr(lengths), ptr(valid_off), ptr(valid_bytes)) == ne
+    per_row = [len(r) for r in rows[lo:lo + n]]
+    assert np.array_equal(np.diff(len_off), [4 * c for c in per_row]) and np.array_equal(np.diff(bytes_off), [w * c for c in per_row])
+    assert np.array_equal(np.diff(valid_off), per_row) and (lengths[:ne] == w).all()
+    elems = [e for r in rows[lo:lo + n] for e in r]
+    assert np.array_equal(valid_bytes[:ne], [0 if e is None else 1 for e in elems])
+    values = np.frombuffer(cb[1], dtype=np.int64)[k + e0:k + e1]
+    assert [int(v) for v, e in zip(values, elems) if e is not None] == [e for e in elems if e is not None]
