@@ -2,7 +2,9 @@
 // resolves with dlopen("libnccl.so.2") — built as libnccl.so.2 into pytest's temporary directory and put on
 // LD_LIBRARY_PATH of the sub-process that runs the multi-worker harness test, where every worker is a THREAD of one process and
 // "device" memory is host memory (fake_cudart.cpp).  Collectives block until every rank of the communicator has arrived.
+#include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -23,6 +25,8 @@ struct Group {
     std::condition_variable cv;
     std::vector<const void*> send;
     std::vector<long long> scratch;
+    std::map<std::pair<int, int>, std::deque<std::vector<char>>> mail;  // (source, destination) -> messages in flight
+    std::condition_variable mail_cv;
     void barrier(std::unique_lock<std::mutex>& lk) {
         const int gen = generation;
         if (++arrived == world) { arrived = 0; ++generation; cv.notify_all(); }
@@ -89,9 +93,30 @@ ncclResult_t ncclAllReduce(const void* send, void* recv, size_t count, ncclDataT
     g->barrier(lk);
     return 0;
 }
-// point-to-point (the NCCL-mode exchange) is not emulated: that mode is covered on real GPUs only
-ncclResult_t ncclSend(const void*, size_t, ncclDataType_t, int, ncclComm_t, void*) { return 5; }
-ncclResult_t ncclRecv(void*, size_t, ncclDataType_t, int, ncclComm_t, void*) { return 5; }
+// point-to-point: a send never blocks (the payload is copied into the (source, destination) mailbox), a receive waits for
+// the next message of that pair — the order of a pair's messages is the order of the calls, as NCCL guarantees inside and
+// across groups; ncclGroupStart / ncclGroupEnd therefore have nothing to do.
+ncclResult_t ncclSend(const void* buf, size_t count, ncclDataType_t t, int peer, ncclComm_t c, void*) {
+    Group* g = c->g;
+    if (peer < 0 || peer >= g->world) return 4;
+    const size_t nb = count * type_size(t);
+    std::unique_lock<std::mutex> lk(g->mu);
+    g->mail[{c->rank, peer}].emplace_back((const char*)buf, (const char*)buf + nb);
+    g->mail_cv.notify_all();
+    return 0;
+}
+ncclResult_t ncclRecv(void* buf, size_t count, ncclDataType_t t, int peer, ncclComm_t c, void*) {
+    Group* g = c->g;
+    if (peer < 0 || peer >= g->world) return 4;
+    const size_t nb = count * type_size(t);
+    std::unique_lock<std::mutex> lk(g->mu);
+    auto& q = g->mail[{peer, c->rank}];
+    if (!g->mail_cv.wait_for(lk, std::chrono::seconds(60), [&] { return !q.empty(); })) return 6;  // ncclRemoteError: the sender never came
+    if (q.front().size() != nb) return 4;  // both sides must agree on the message size (they derive it from the same count matrix)
+    memcpy(buf, q.front().data(), nb);
+    q.pop_front();
+    return 0;
+}
 ncclResult_t ncclGroupStart(void) { return 0; }
 ncclResult_t ncclGroupEnd(void) { return 0; }
 }

@@ -6,7 +6,7 @@
 // and to run the single-pass exchange (fixed-width non-null schemas) with its overflow -> exact two-pass re-run:
 //   * PartitionJob::run_onepass<PEER> / run_scatter<PEER> as row loops that store into the owners' windows;
 //   * k_xchg_signal_ready, k_xchg_publish_wait, k_exchange_plan.
-// The NCCL-mode transport (ncclSend / ncclRecv) is NOT emulated: it is covered on real GPUs (tests/mgpu_shuffle_check.py).
+// The NCCL-mode transport needs nothing more here: its sends / receives go through the stand-in NCCL's mailboxes (fake_nccl.cpp).
 #include <chrono>
 #include <cstdint>
 #include <cstdlib>
@@ -57,7 +57,6 @@ int dfd::PartitionJob::prepare(Partitioner* part, const dfd_column* in_cols, int
 
 // K1 + K1b: per-destination totals (the exchange all-gathers them in the two-pass fused path)
 int dfd::PartitionJob::run_hist_scan() {
-    if (!peer) return DFD_OK;  // (the local form partitions in run_scatter)
     if (int rc = destinations_of(*this)) return rc;
     memset(d_totals, 0, sizeof(int64_t) * (size_t)p->N);
     for (uint32_t g : t_dest) d_totals[g]++;

@@ -4,7 +4,7 @@ push transport and compare every (partition, producer) segment with the single-n
 
     python run_workers.py <harness.so> <world> <scenario> [seed]
 
-scenario: shuffle | stream | coalesce | broadcast | mismatch | onepass | onepass_overflow | host | peer_missing | mixed"""
+scenario: shuffle | stream | coalesce | broadcast | mismatch | onepass | onepass_overflow | host | peer_missing | mixed | nccl | fused"""
 import ctypes as C
 import os
 import sys
@@ -43,6 +43,7 @@ def bind(lib):
         "dfd_shuffle_stream_end": (None, [VP]),
         "dfd_shuffle_stream_stats": (C.c_int, [VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "dfd_exchange_onepass_fallbacks": (C.c_uint64, [VP]),
+        "dfd_shuffle_device": (C.c_int, [VP, VP, C.c_int, C.POINTER(COL), C.c_int, C.c_int64, C.c_uint32, C.POINTER(COL), C.c_int64, C.POINTER(C.c_int64)]),
         "dfd_shuffle_host": (C.c_int, [VP, VP, C.POINTER(COL), C.c_int, C.c_int64, C.c_uint32, C.c_int, C.POINTER(COL), C.c_int64, C.POINTER(C.c_int64)]),
     }
     for name, (res, args) in sig.items():
@@ -211,7 +212,57 @@ def worker(lib, rank, world, uid, scenario, seed, errors, barrier):
                     assert segment_to_arrow(o_[c], f, int(st_[sgm]), int(ct_[sgm])).equals(want.column(c).combine_chunks()), ("push", rank, sgm, f.name)
             barrier.wait()
 
-        if scenario == "mixed":
+        if scenario in ("nccl", "fused"):
+            # dfd_shuffle_device: the dense layout (per partition, producers contiguous in task order) through the NCCL-mode
+            # transport (every column kind; grouped ncclSend / ncclRecv of values, u8 images of bitmaps, string lengths + bytes) or
+            # the two-pass fused transport (all-gathered counts -> plan -> peer stores; fixed-width non-null)
+            for rep in range(2):
+                if scenario == "nccl":
+                    tabs = [local_table(r, [0, 1, 700, 1500, 333, 1000, 64, 2000][(r + rep) % 8], seed + rep) for r in range(world)]
+                    kcols, pt = ["key", "s"], part
+                else:
+                    tabs = [fixed_table(r, 800 + 5 * r, seed + rep, False) for r in range(world)]
+                    kcols = ["key"]
+                    pt = VP()
+                    check(lib, lib.dfd_partitioner_create(ctx, N, (C.c_int32 * 1)(0), 1, None, C.byref(pt)), "dfd_partitioner_create")
+                t_me = tabs[rank]
+                flds = list(t_me.schema)
+                kp = []
+                cols_ = to_columns(t_me, kp)
+                d_ = [orc.partition_ids([t.column(k) for k in kcols], t.num_rows, N) for t in tabs]
+                cap = sum(t.num_rows for t in tabs) + 8
+                o_ = (COL * len(flds))()
+                bufs = []
+                for i, f in enumerate(flds):
+                    o_[i].kind, o_[i].width = cols_[i].kind, cols_[i].width
+                    if scenario == "fused":
+                        continue  # (the fused transport hands out window pointers)
+                    if pa.types.is_string(f.type):
+                        nbytes = sum(t.column(i).combine_chunks().buffers()[2].size if t.column(i).combine_chunks().buffers()[2] is not None else 0 for t in tabs) + 64
+                        ob, vb = np.zeros(cap + 1, dtype=np.int32), np.zeros(nbytes, dtype=np.uint8)
+                        o_[i].offsets, o_[i].values, o_[i].values_bytes = ob.ctypes.data, vb.ctypes.data, nbytes
+                        bufs += [ob, vb]
+                    else:
+                        vb = np.zeros(cap * max(1, f.type.bit_width // 8) + 64, dtype=np.uint8)
+                        o_[i].values = vb.ctypes.data
+                        bufs.append(vb)
+                    if f.name in ("key", "flag", "s"):  # the schema's nullable columns: a validity buffer on EVERY worker
+                        nb_ = np.zeros(cap // 8 + 64, dtype=np.uint8)
+                        o_[i].validity = nb_.ctypes.data
+                        bufs.append(nb_)
+                ps = (C.c_int64 * (P + 1))()
+                check(lib, lib.dfd_shuffle_device(ex, pt, 0 if scenario == "nccl" else 1, cols_, len(flds), t_me.num_rows, P, o_, cap, ps), "dfd_shuffle_device")
+                for q in range(P):
+                    want = pa.concat_tables([tabs[r].take(pa.array(np.nonzero(d_[r] == rank * P + q)[0])) for r in range(world)])
+                    assert ps[q + 1] - ps[q] == want.num_rows, (scenario, rank, q)
+                    for c, f in enumerate(flds):
+                        got = segment_to_arrow(o_[c], f, int(ps[q]), int(ps[q + 1] - ps[q]))
+                        got.validate(full=True)
+                        assert got.equals(want.column(c).combine_chunks()), (scenario, rank, q, f.name)
+                barrier.wait()
+                if scenario == "fused":
+                    lib.dfd_partitioner_destroy(pt)
+        elif scenario == "mixed":
             # the transports share one window, one epoch counter and the done flags: alternate them on the same exchange
             one_single_pass(seed)
             one_push(seed + 1)

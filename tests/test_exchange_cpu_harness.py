@@ -10,7 +10,8 @@ for the shuffle (NetworkShuffleExec), the back-pressured rounds, NetworkCoalesce
 nullable / boolean / string columns, and compare every (partition, producer) segment with the single-node oracle.  The
 single-pass exchange (fixed-width non-null schemas: ready flags, peer stores into (partition, producer) sub-windows, publish /
 wait, and the overflow -> exact two-pass re-run that every worker must take together) runs the same way, its scatter kernels
-replaced by row loops.  The NCCL-mode transport (ncclSend / ncclRecv) is NOT emulated (real GPUs only)."""
+replaced by row loops, and so do the two-pass fused transport and the NCCL-mode transport (grouped ncclSend / ncclRecv through
+mailboxes of the stand-in NCCL)."""
 import os
 import subprocess
 import sys
@@ -88,6 +89,16 @@ def test_single_pass_exchange_sub_windows_and_flags(exchange_harness, world):
 @pytest.mark.parametrize("world", [2, 3])
 def test_single_pass_overflow_makes_every_worker_rerun_exactly(exchange_harness, world):
     run(exchange_harness, world, "onepass_overflow")
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4])
+def test_nccl_mode_moves_every_column_kind(exchange_harness, world):
+    run(exchange_harness, world, "nccl")
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_two_pass_fused_transport_dense_layout(exchange_harness, world):
+    run(exchange_harness, world, "fused")
 
 
 @pytest.mark.parametrize("world", [1, 2, 3])
