@@ -878,8 +878,20 @@ int prepare_rows(dfd_repartition_exec* x, const ArrowArray* b, int64_t start, in
             x->prep[i] = VarPrep{offs + (size_t)lo * ow, first, (const char*)c->buffers[2] + first, last - first};
         } else if (f.dict) {
             if (!c->dictionary) return fail(x, DFD_ERR_INVALID_ARGUMENT, "column " + f.name + ": dictionary array without a dictionary");
+            // one dictionary per chunk (it travels by reference).  A batch whose dictionary is a different OBJECT with the same
+            // values (readers re-materialise the dictionary for every batch) joins the chunk and is served by the chunk's first one
             const DictId id = dict_identity(c->dictionary);
-            if (s.rows > 0 && !(s.dict_id[i] == id)) *fits = false;  // one dictionary per chunk (it travels by reference)
+            if (s.rows > 0 && !(s.dict_id[i] == id)) {
+                const ArrowArray* mine = !s.held.empty() && s.held.front()->array.children[i] ? s.held.front()->array.children[i]->dictionary : nullptr;
+                const ArrowArray* theirs = c->dictionary;
+                const bool dvar = f.dict_kind == DFD_COL_UTF8 || f.dict_kind == DFD_COL_LARGE_UTF8 || f.dict_kind == DFD_COL_BINARY;
+                const bool comparable = mine && f.dict_format[0] != 'v' && mine->length == theirs->length && mine->n_buffers == theirs->n_buffers &&
+                                        mine->length <= (1 << 20);  // (a linear comparison per batch: keep it to dictionaries worth their name)
+                if (!comparable || !dfd::host::flat_arrays_equal(mine->length, dvar ? (f.dict_kind == DFD_COL_LARGE_UTF8 ? 8 : 4) : 0,
+                                                                  f.dict_kind == DFD_COL_BOOL ? 0 : f.dict_width, mine->buffers, mine->offset, mine->null_count,
+                                                                  theirs->buffers, theirs->offset, theirs->null_count))
+                    *fits = false;
+            }
         }
     }
     if (!*fits) return DFD_OK;

@@ -153,5 +153,39 @@ inline int64_t split_list_rows_fixed(const int32_t* loff, int32_t w, const uint8
     return ne;
 }
 
+// Do two flat Arrow arrays hold the same values?  (dictionaries of consecutive batches: readers re-materialise the same
+// dictionary for every batch, and a chunk can keep ONE of them for all its rows.)  `var_ow` = 0 for fixed-width values of
+// `width` bytes (0 = bit-packed booleans), 4 / 8 for Utf8 / Binary / LargeUtf8 offsets.  Buffers follow the Arrow C layout:
+// validity (may be NULL = all valid), then values, or offsets + data.  Null slots compare equal whatever lies under them.
+inline bool flat_arrays_equal(int64_t length, int var_ow, int width, const void* const* a_bufs, int64_t a_offset, int64_t a_nulls, const void* const* b_bufs,
+                              int64_t b_offset, int64_t b_nulls) {
+    const uint8_t* av = a_nulls != 0 ? (const uint8_t*)a_bufs[0] : nullptr;
+    const uint8_t* bv = b_nulls != 0 ? (const uint8_t*)b_bufs[0] : nullptr;
+    auto valid = [](const uint8_t* v, int64_t i) { return !v || ((v[i >> 3] >> (i & 7)) & 1); };
+    for (int64_t i = 0; i < length; ++i) {
+        const bool x = valid(av, a_offset + i), y = valid(bv, b_offset + i);
+        if (x != y) return false;
+        if (!x) continue;
+        if (var_ow == 0 && width == 0) {  // booleans
+            if (valid((const uint8_t*)a_bufs[1], a_offset + i) != valid((const uint8_t*)b_bufs[1], b_offset + i)) return false;
+        } else if (var_ow == 0) {
+            if (memcmp((const char*)a_bufs[1] + (size_t)(a_offset + i) * (size_t)width, (const char*)b_bufs[1] + (size_t)(b_offset + i) * (size_t)width, (size_t)width) != 0)
+                return false;
+        } else {
+            int64_t a0, a1, b0, b1;
+            if (var_ow == 8) {
+                a0 = ((const int64_t*)a_bufs[1])[a_offset + i]; a1 = ((const int64_t*)a_bufs[1])[a_offset + i + 1];
+                b0 = ((const int64_t*)b_bufs[1])[b_offset + i]; b1 = ((const int64_t*)b_bufs[1])[b_offset + i + 1];
+            } else {
+                a0 = ((const int32_t*)a_bufs[1])[a_offset + i]; a1 = ((const int32_t*)a_bufs[1])[a_offset + i + 1];
+                b0 = ((const int32_t*)b_bufs[1])[b_offset + i]; b1 = ((const int32_t*)b_bufs[1])[b_offset + i + 1];
+            }
+            if (a1 - a0 != b1 - b0) return false;
+            if (a1 > a0 && memcmp((const char*)a_bufs[2] + a0, (const char*)b_bufs[2] + b0, (size_t)(a1 - a0)) != 0) return false;
+        }
+    }
+    return true;
+}
+
 }  // namespace host
 }  // namespace dfd

@@ -171,6 +171,7 @@ CASES = [
     ("test_pinned_chunks_are_reused_by_the_next_operator_of_the_same_shape", {}),
     ("test_large_binary_and_fixed_size_binary_travel_as_payload", {}),
     ("test_lists_of_primitives_travel_as_payload", {}),
+    ("test_equal_dictionaries_of_consecutive_batches_share_a_chunk", {}),
 ]
 
 

@@ -524,3 +524,38 @@ def test_lists_of_primitives_travel_as_payload(ctx):
     with pytest.raises(dfd.DfdError) as e:
         dfd.RepartitionExec(ctx, table.schema, dfd.Partitioning.Hash([1], N))
     assert e.value.status == 6
+
+
+def test_equal_dictionaries_of_consecutive_batches_share_a_chunk(ctx):
+    """Readers re-materialise a column's dictionary for every batch: batches whose dictionaries are different OBJECTS with the same
+    values are appended to the same chunk (one launch, one output batch per destination), a batch with other values still cuts it."""
+    rnd = random.Random(3)
+    values = ["red", "green", None, "blue-" * 4, ""]
+    n_batches, rows, N = 20, 1_000, 4
+    batches, all_rows = [], []
+    for b in range(n_batches):
+        vals = list(values) if b != 12 else ["other", "values", None, "here", "!"]   # batch 12 really has another dictionary
+        dictionary = pa.array(list(vals), type=pa.string())                           # a fresh object (fresh buffers) every time
+        idx = pa.array([rnd.choice([None, 0, 1, 2, 3, 4]) for _ in range(rows)], type=pa.int32())
+        key = pa.array([rnd.getrandbits(40) for _ in range(rows)], type=pa.int64())
+        batches.append(pa.record_batch([key, pa.DictionaryArray.from_arrays(idx, dictionary)], names=["key", "cat"]))
+        all_rows.append(pa.table([key, pa.DictionaryArray.from_arrays(idx, dictionary).dictionary_decode()], names=["key", "cat"]))
+    plain = pa.concat_tables(all_rows)
+    for keys in ([0], [1, 0]):
+        ex = dfd.RepartitionExec(ctx, batches[0].schema, dfd.Partitioning.Hash(keys, N), chunk_rows=8_192)
+        for rb in batches:
+            ex.push_batch(rb)
+        ex.finish()
+        readers = [ex.execute(p) for p in range(N)]
+        outs = [[rb for rb in r] for r in readers]
+        dest = orc.partition_ids([plain.column(k) for k in keys], plain.num_rows, N)
+        order, starts = expected_partitions(dest, N)
+        for p in range(N):
+            want = plain.take(pa.array(order[starts[p]:starts[p + 1]]))
+            got_key = pa.concat_arrays([rb.column(0) for rb in outs[p]])
+            got_cat = pa.concat_arrays([rb.column(1).dictionary_decode() for rb in outs[p]])
+            assert got_key.equals(want.column("key").combine_chunks()) and got_cat.equals(want.column("cat").combine_chunks()), (keys, p)
+            # 20 000 rows in chunks of 8 192, cut once more before and after batch 12: a handful of output batches, not 20
+            assert len(outs[p]) <= 6, (keys, p, len(outs[p]))
+        del outs, readers
+        ex.close()
