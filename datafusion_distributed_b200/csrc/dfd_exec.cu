@@ -886,7 +886,7 @@ int prepare_rows(dfd_repartition_exec* x, const ArrowArray* b, int64_t start, in
                 const ArrowArray* theirs = c->dictionary;
                 const bool dvar = f.dict_kind == DFD_COL_UTF8 || f.dict_kind == DFD_COL_LARGE_UTF8 || f.dict_kind == DFD_COL_BINARY;
                 const bool comparable = mine && f.dict_format[0] != 'v' && mine->length == theirs->length && mine->n_buffers == theirs->n_buffers &&
-                                        mine->length <= (1 << 20);  // (a linear comparison per batch: keep it to dictionaries worth their name)
+                                        mine->length <= (1 << 16);  // (a linear comparison per batch: only worth it for small dictionaries — a batch's own)
                 if (!comparable || !dfd::host::flat_arrays_equal(mine->length, dvar ? (f.dict_kind == DFD_COL_LARGE_UTF8 ? 8 : 4) : 0,
                                                                   f.dict_kind == DFD_COL_BOOL ? 0 : f.dict_width, mine->buffers, mine->offset, mine->null_count,
                                                                   theirs->buffers, theirs->offset, theirs->null_count))
